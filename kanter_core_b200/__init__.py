@@ -1,0 +1,12 @@
+"""kanter_core_b200 — B200-native evaluation backend for kanter_core / vismut_core.
+
+The package is the host-side mirror of the crate's interface (api.py) over the
+C ABI of libkanter_b200.so (csrc/, include/kanter_b200.h).  Importing it loads
+the shared library and fails loudly if it has not been built.
+"""
+from ._lib import MATH_EXACT, MATH_FAST, TexProError, lib  # noqa: F401
+from .api import (  # noqa: F401
+    Edge, EmbeddedSlotDataId, LiveGraph, MixType, Node, NodeGraph, NodeId, NodeState, NodeType,
+    ResizeFilter, ResizePolicy, Side, Size, Slot, SlotData, SlotId, SlotImage, SlotType,
+    TextureProcessor, graph_to_dict,
+)

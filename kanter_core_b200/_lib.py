@@ -1,0 +1,211 @@
+"""ctypes binding of libkanter_b200.so (the C ABI declared in include/kanter_b200.h).
+
+The library is the product: if it is missing this module raises, there is no
+fallback of any kind (and nothing here may import the CPU oracle).
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libkanter_b200.so")
+
+# ---- enums (include/kanter_b200.h) ------------------------------------------
+KC_OK = 0
+ERR_NAMES = {
+    1: "Generic", 2: "Canceled", 3: "Image", 4: "InvalidBufferCount", 5: "InvalidNodeId",
+    6: "InvalidNodeType", 7: "InvalidSlotId", 8: "InvalidSlotType", 9: "InvalidEdge",
+    10: "NoSlotData", 11: "SlotOccupied", 12: "SlotNotOccupied", 13: "UnableToLock",
+    14: "NodeProcessing", 15: "PoisonError", 16: "TryLockError", 17: "NodeDirty", 18: "Io",
+    19: "InvalidName", 100: "Cuda", 101: "InvalidArgument",
+}
+(NODE_INPUT_GRAY, NODE_INPUT_RGBA, NODE_OUTPUT_GRAY, NODE_OUTPUT_RGBA, NODE_GRAPH, NODE_IMAGE,
+ NODE_EMBED, NODE_WRITE, NODE_VALUE, NODE_MIX, NODE_HEIGHT_TO_NORMAL, NODE_SEPARATE_RGBA,
+ NODE_COMBINE_RGBA) = range(13)
+MATH_EXACT, MATH_FAST = 0, 1
+IMAGE_GRAY, IMAGE_RGBA = 0, 1
+SIDE_INPUT, SIDE_OUTPUT = 0, 1
+
+
+class kc_options(C.Structure):
+    _fields_ = [("math_mode", C.c_int32), ("fuse", C.c_int32), ("reserved", C.c_int32 * 6)]
+
+
+class kc_image(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("planes", C.c_void_p * 4)]
+
+
+class kc_slot_data(C.Structure):
+    _fields_ = [("node_id", C.c_uint32), ("slot_id", C.c_uint32), ("image", kc_image)]
+
+
+class kc_embedded_slot_data(C.Structure):
+    _fields_ = [("slot_data_id", C.c_uint32), ("slot_id", C.c_uint32), ("image", kc_image)]
+
+
+class kc_edge(C.Structure):
+    _fields_ = [("output_id", C.c_uint32), ("input_id", C.c_uint32), ("output_slot", C.c_uint32),
+                ("input_slot", C.c_uint32)]
+
+
+class kc_node_desc(C.Structure):
+    _fields_ = [("node_id", C.c_uint32), ("node_type", C.c_int32), ("value", C.c_float),
+                ("mix_type", C.c_int32), ("name", C.c_char_p), ("graph", C.c_void_p),
+                ("embed_id", C.c_uint32), ("resize_policy", C.c_int32), ("policy_slot", C.c_uint32),
+                ("policy_width", C.c_uint32), ("policy_height", C.c_uint32),
+                ("resize_filter", C.c_int32)]
+
+
+class kc_slot(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("slot_id", C.c_uint32), ("slot_type", C.c_int32)]
+
+
+P = C.POINTER
+vp, u32, i32, sz, f32 = C.c_void_p, C.c_uint32, C.c_int32, C.c_size_t, C.c_float
+u64 = C.c_uint64
+
+# name -> (restype, argtypes); restype i32 means "status code"
+SIGNATURES = {
+    "kc_abi_version": (i32, []),
+    "kc_last_error": (C.c_char_p, []),
+    "kc_error_string": (C.c_char_p, [i32]),
+    "kc_free": (None, [vp]),
+    "kc_host_alloc": (i32, [sz, P(vp)]),
+    "kc_host_free": (i32, [vp]),
+    "kc_options_default": (None, [P(kc_options)]),
+    "kc_context_create": (i32, [i32, P(kc_options), P(vp)]),
+    "kc_context_destroy": (i32, [vp]),
+    "kc_context_synchronize": (i32, [vp]),
+    "kc_context_device": (i32, [vp, P(i32)]),
+    "kc_context_stream": (i32, [vp, P(vp)]),
+    "kc_context_set_math_mode": (i32, [vp, i32]),
+    "kc_context_set_fuse": (i32, [vp, i32]),
+    "kc_context_stats": (i32, [vp, P(u64), P(u64)]),
+    "kc_event_create": (i32, [P(vp)]),
+    "kc_event_destroy": (i32, [vp]),
+    "kc_event_record": (i32, [vp, vp]),
+    "kc_event_elapsed_ms": (i32, [vp, vp, P(f32)]),
+    "kc_plane_create": (i32, [vp, u32, u32, P(vp)]),
+    "kc_plane_from_value": (i32, [vp, u32, u32, f32, P(vp)]),
+    "kc_plane_from_host": (i32, [vp, u32, u32, vp, P(vp)]),
+    "kc_plane_wrap_device": (i32, [vp, u32, u32, vp, P(vp)]),
+    "kc_plane_retain": (i32, [vp]),
+    "kc_plane_release": (i32, [vp]),
+    "kc_plane_size": (i32, [vp, P(u32), P(u32)]),
+    "kc_plane_is_constant": (i32, [vp, P(i32), P(f32)]),
+    "kc_plane_device_ptr": (i32, [vp, P(vp)]),
+    "kc_plane_upload": (i32, [vp, vp]),
+    "kc_plane_download": (i32, [vp, vp]),
+    "kc_image_from_u8": (i32, [vp, vp, u32, u32, u32, P(kc_image)]),
+    "kc_image_from_host_planes": (i32, [vp, i32, u32, u32, P(vp), P(kc_image)]),
+    "kc_image_from_value": (i32, [vp, u32, u32, f32, i32, P(kc_image)]),
+    "kc_image_as_type": (i32, [vp, P(kc_image), i32, P(kc_image)]),
+    "kc_image_to_u8": (i32, [vp, P(kc_image), i32, vp]),
+    "kc_image_to_u8_device": (i32, [vp, P(kc_image), i32, vp]),
+    "kc_image_download": (i32, [vp, P(kc_image), P(vp)]),
+    "kc_image_retain": (i32, [P(kc_image)]),
+    "kc_image_release": (i32, [P(kc_image)]),
+    "kc_mix": (i32, [vp, i32, P(kc_image), P(kc_image), P(kc_image)]),
+    "kc_height_to_normal": (i32, [vp, P(kc_image), P(kc_image)]),
+    "kc_resize": (i32, [vp, P(kc_image), u32, u32, i32, P(kc_image)]),
+    "kc_separate_rgba": (i32, [vp, P(kc_image), P(kc_image)]),
+    "kc_combine_rgba": (i32, [vp, P(P(kc_image)), P(kc_image)]),
+    "kc_calculate_size": (i32, [P(kc_slot_data), sz, P(kc_edge), sz, i32, u32, u32, u32, P(u32), P(u32)]),
+    "kc_process_node": (i32, [vp, P(kc_node_desc), P(kc_slot_data), sz, P(kc_embedded_slot_data), sz,
+                              P(kc_slot_data), sz, P(kc_edge), sz, P(kc_slot_data), sz, P(sz)]),
+    "kc_graph_create": (i32, [P(vp)]),
+    "kc_graph_destroy": (i32, [vp]),
+    "kc_graph_clone": (i32, [vp, P(vp)]),
+    "kc_graph_from_json": (i32, [C.c_char_p, P(vp)]),
+    "kc_graph_from_path": (i32, [C.c_char_p, P(vp)]),
+    "kc_graph_export_json": (i32, [vp, P(vp)]),
+    "kc_graph_export_json_path": (i32, [vp, C.c_char_p]),
+    "kc_graph_add_node": (i32, [vp, P(kc_node_desc), P(u32)]),
+    "kc_graph_add_node_with_id": (i32, [vp, P(kc_node_desc)]),
+    "kc_graph_remove_node": (i32, [vp, u32]),
+    "kc_graph_connect": (i32, [vp, u32, u32, u32, u32]),
+    "kc_graph_try_connect": (i32, [vp, u32, u32, u32, u32]),
+    "kc_graph_disconnect_slot": (i32, [vp, u32, i32, u32]),
+    "kc_graph_remove_edge": (i32, [vp, P(kc_edge)]),
+    "kc_graph_node_count": (i32, [vp, P(sz)]),
+    "kc_graph_node_at": (i32, [vp, sz, P(kc_node_desc)]),
+    "kc_graph_node": (i32, [vp, u32, P(kc_node_desc)]),
+    "kc_graph_set_node": (i32, [vp, P(kc_node_desc)]),
+    "kc_graph_edge_count": (i32, [vp, P(sz)]),
+    "kc_graph_edge_at": (i32, [vp, sz, P(kc_edge)]),
+    "kc_graph_input_slot_id_with_name": (i32, [vp, C.c_char_p, P(u32)]),
+    "kc_graph_output_slot_id_with_name": (i32, [vp, C.c_char_p, P(u32)]),
+    "kc_graph_output_ids": (i32, [vp, P(u32), sz, P(sz)]),
+    "kc_graph_input_ids": (i32, [vp, P(u32), sz, P(sz)]),
+    "kc_node_input_slots": (i32, [P(kc_node_desc), P(kc_slot), sz, P(sz)]),
+    "kc_node_output_slots": (i32, [P(kc_node_desc), P(kc_slot), sz, P(sz)]),
+    "kc_live_graph_create": (i32, [vp, P(vp)]),
+    "kc_live_graph_destroy": (i32, [vp]),
+    "kc_live_graph_set_node_graph": (i32, [vp, vp]),
+    "kc_live_graph_node_graph": (i32, [vp, P(vp)]),
+    "kc_live_graph_set_use_cache": (i32, [vp, i32]),
+    "kc_live_graph_set_auto_update": (i32, [vp, i32]),
+    "kc_live_graph_add_node": (i32, [vp, P(kc_node_desc), P(u32)]),
+    "kc_live_graph_add_node_with_id": (i32, [vp, P(kc_node_desc)]),
+    "kc_live_graph_remove_node": (i32, [vp, u32]),
+    "kc_live_graph_connect": (i32, [vp, u32, u32, u32, u32]),
+    "kc_live_graph_disconnect_slot": (i32, [vp, u32, i32, u32]),
+    "kc_live_graph_set_node": (i32, [vp, P(kc_node_desc)]),
+    "kc_live_graph_add_input_slot_data": (i32, [vp, u32, u32, P(kc_image)]),
+    "kc_live_graph_clear_input_slot_data": (i32, [vp]),
+    "kc_live_graph_embed_slot_data_with_id": (i32, [vp, P(kc_image), u32, u32]),
+    "kc_live_graph_replace_embedded": (i32, [vp, P(kc_image), u32]),
+    "kc_live_graph_set_image_data_u8": (i32, [vp, u32, vp, u32, u32, u32]),
+    "kc_live_graph_request": (i32, [vp, P(u32), sz]),
+    "kc_live_graph_await_clean": (i32, [vp, u32]),
+    "kc_live_graph_cancel": (i32, [vp]),
+    "kc_live_graph_node_state": (i32, [vp, u32, P(i32)]),
+    "kc_live_graph_slot_data": (i32, [vp, u32, u32, P(kc_image)]),
+    "kc_live_graph_slot_data_size": (i32, [vp, u32, u32, P(u32), P(u32)]),
+    "kc_live_graph_node_slot_ids": (i32, [vp, u32, P(u32), sz, P(sz)]),
+    "kc_live_graph_buffer_rgba": (i32, [vp, u32, u32, vp, sz]),
+    "kc_live_graph_buffer_srgba": (i32, [vp, u32, u32, vp, sz]),
+    "kc_live_graph_read_rgba": (i32, [vp, u32, u32, i32, vp, sz]),
+    "kc_live_graph_last_run_stats": (i32, [vp, P(u64), P(u64), P(u64)]),
+}
+
+_NO_STATUS = {"kc_abi_version"}
+
+
+class TexProError(Exception):
+    """`TexProError` (src/error.rs:5-27); `.kind` is the variant name."""
+
+    def __init__(self, code, message=""):
+        self.code = code
+        self.kind = ERR_NAMES.get(code, "Unknown(%d)" % code)
+        super().__init__("%s: %s" % (self.kind, message))
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "kanter_core_b200: %s is missing. Build it with `python -m kanter_core_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here == the library does not export the ABI
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(code):
+    if code != KC_OK:
+        msg = lib.kc_last_error()
+        raise TexProError(code, msg.decode("utf-8", "replace") if msg else "")
+
+
+def call(name, *args):
+    """Call a status-returning entry point, raising TexProError on failure."""
+    rc = getattr(lib, name)(*args)
+    if name not in _NO_STATUS:
+        check(rc)
+    return rc

@@ -1,0 +1,806 @@
+"""Host-side mirror of the vismut_core (kanter_core) public interface, on top of
+the C ABI.  Same names, argument meaning and error behaviour as the crate, so a
+test written against the reference reads the same here:
+
+    tex_pro = TextureProcessor.new()
+    live_graph = tex_pro.new_live_graph()
+    mix = live_graph.add_node(Node.new(NodeType.Mix(MixType.Add)))
+    live_graph.connect(a, mix, SlotId(0), SlotId(0))
+    rgba8 = LiveGraph.await_clean_read(live_graph, out).buffer_rgba(out, SlotId(0))
+
+Reference: src/lib.rs:1-13 and the modules it exports.  All pixel work happens
+in libkanter_b200.so on the GPU; this file only moves handles around.
+"""
+import ctypes as C
+import enum
+import json as _json
+
+import numpy as np
+
+from . import _lib
+from ._lib import TexProError, call, kc_edge, kc_image, kc_node_desc, kc_options, kc_slot
+
+
+# ---- ids, sizes, enums (src/node_graph.rs:592-624, src/slot_data.rs:5-30) -------
+class NodeId(int):
+    def __repr__(self):
+        return "NodeId(%d)" % int(self)
+
+
+class SlotId(int):
+    def __repr__(self):
+        return "SlotId(%d)" % int(self)
+
+
+class EmbeddedSlotDataId(int):  # src/node/embed.rs:13-14
+    pass
+
+
+class Size:
+    def __init__(self, width, height):
+        self.width, self.height = int(width), int(height)
+
+    @staticmethod
+    def new(width, height):
+        return Size(width, height)
+
+    def pixel_count(self):
+        return (self.width * self.height) & 0xFFFFFFFF  # u32 multiply, src/slot_data.rs:27-29
+
+    def __eq__(self, o):
+        return isinstance(o, Size) and (self.width, self.height) == (o.width, o.height)
+
+    def __iter__(self):
+        return iter((self.width, self.height))
+
+    def __repr__(self):
+        return "%dx%d" % (self.width, self.height)
+
+
+class MixType(enum.IntEnum):  # src/node/mix.rs:20-26
+    Add = 0
+    Subtract = 1
+    Multiply = 2
+    Divide = 3
+    Pow = 4
+
+    @staticmethod
+    def default():
+        return MixType.Add
+
+
+class ResizeFilter(enum.IntEnum):  # src/node/mod.rs:63-69
+    Nearest = 0
+    Triangle = 1
+    CatmullRom = 2
+    Gaussian = 3
+    Lanczos3 = 4
+
+    @staticmethod
+    def default():
+        return ResizeFilter.Triangle
+
+
+class ResizePolicy:  # src/node/mod.rs:33-40
+    _NAMES = ["MostPixels", "LeastPixels", "LargestAxes", "SmallestAxes", "SpecificSlot", "SpecificSize"]
+
+    def __init__(self, kind, slot=0, size=None):
+        self.kind, self.slot, self.size = kind, SlotId(slot), size or Size(0, 0)
+
+    @staticmethod
+    def SpecificSlot(slot_id):
+        return ResizePolicy(4, slot=slot_id)
+
+    @staticmethod
+    def SpecificSize(size):
+        return ResizePolicy(5, size=size)
+
+    @staticmethod
+    def default():
+        return ResizePolicy.MostPixels
+
+    def __eq__(self, o):
+        return isinstance(o, ResizePolicy) and (self.kind, int(self.slot), tuple(self.size)) == (o.kind, int(o.slot), tuple(o.size))
+
+    def __repr__(self):
+        return self._NAMES[self.kind]
+
+
+ResizePolicy.MostPixels = ResizePolicy(0)
+ResizePolicy.LeastPixels = ResizePolicy(1)
+ResizePolicy.LargestAxes = ResizePolicy(2)
+ResizePolicy.SmallestAxes = ResizePolicy(3)
+
+
+class Side(enum.IntEnum):  # src/node/mod.rs:101-105
+    Input = 0
+    Output = 1
+
+
+class SlotType(enum.IntEnum):  # src/node/mod.rs:197-202
+    Gray = 0
+    Rgba = 1
+    GrayOrRgba = 2
+
+
+class NodeState(enum.IntEnum):  # src/live_graph.rs:23-37
+    Clean = 0
+    Dirty = 1
+    Requested = 2
+    Prioritised = 3
+    Processing = 4
+    ProcessingDirty = 5
+
+
+class NodeType:
+    """`enum NodeType`, src/node/node_type.rs:14-28."""
+    _NAMES = ["InputGray", "InputRgba", "OutputGray", "OutputRgba", "Graph", "Image", "Embed", "Write",
+              "Value", "Mix", "HeightToNormal", "SeparateRgba", "CombineRgba"]
+
+    def __init__(self, kind, payload=None):
+        self.kind, self.payload = kind, payload
+
+    InputGray = staticmethod(lambda name: NodeType(_lib.NODE_INPUT_GRAY, str(name)))
+    InputRgba = staticmethod(lambda name: NodeType(_lib.NODE_INPUT_RGBA, str(name)))
+    OutputGray = staticmethod(lambda name: NodeType(_lib.NODE_OUTPUT_GRAY, str(name)))
+    OutputRgba = staticmethod(lambda name: NodeType(_lib.NODE_OUTPUT_RGBA, str(name)))
+    Graph = staticmethod(lambda graph: NodeType(_lib.NODE_GRAPH, graph))
+    Image = staticmethod(lambda path: NodeType(_lib.NODE_IMAGE, str(path)))
+    Embed = staticmethod(lambda esd_id: NodeType(_lib.NODE_EMBED, EmbeddedSlotDataId(esd_id)))
+    Write = staticmethod(lambda path: NodeType(_lib.NODE_WRITE, str(path)))
+    Value = staticmethod(lambda v: NodeType(_lib.NODE_VALUE, float(np.float32(v))))
+    Mix = staticmethod(lambda mix_type: NodeType(_lib.NODE_MIX, MixType(mix_type)))
+
+    def is_input(self):
+        return self.kind in (_lib.NODE_INPUT_GRAY, _lib.NODE_INPUT_RGBA)
+
+    def is_output(self):
+        return self.kind in (_lib.NODE_OUTPUT_GRAY, _lib.NODE_OUTPUT_RGBA)
+
+    def name(self):
+        return self.payload if self.kind <= _lib.NODE_OUTPUT_RGBA else None
+
+    def __eq__(self, o):  # discriminant comparison, node_type.rs:50-54
+        return isinstance(o, NodeType) and self.kind == o.kind
+
+    def __repr__(self):
+        return self._NAMES[self.kind] if self.payload is None else "%s(%r)" % (self._NAMES[self.kind], self.payload)
+
+
+NodeType.HeightToNormal = NodeType(_lib.NODE_HEIGHT_TO_NORMAL)
+NodeType.SeparateRgba = NodeType(_lib.NODE_SEPARATE_RGBA)
+NodeType.CombineRgba = NodeType(_lib.NODE_COMBINE_RGBA)
+
+
+class Slot:  # src/node/mod.rs:223-238
+    def __init__(self, name, slot_id, slot_type):
+        self.name, self.slot_id, self.slot_type = name, SlotId(slot_id), SlotType(slot_type)
+
+    def __repr__(self):
+        return "Slot(%r, %d, %s)" % (self.name, self.slot_id, self.slot_type.name)
+
+
+class Node:
+    """`struct Node`, src/node/mod.rs:114-123."""
+
+    def __init__(self, node_type, node_id=0):
+        self.node_id = NodeId(node_id)
+        self.node_type = node_type
+        self.resize_policy = ResizePolicy.default()
+        self.resize_filter = ResizeFilter.default()
+
+    new = staticmethod(lambda node_type: Node(node_type))
+    with_id = staticmethod(lambda node_type, node_id: Node(node_type, node_id))
+
+    def _desc(self):
+        """(kc_node_desc, keepalive) for the C ABI."""
+        d = kc_node_desc()
+        t = self.node_type
+        keep = []
+        d.node_id = int(self.node_id)
+        d.node_type = t.kind
+        if t.kind == _lib.NODE_VALUE:
+            d.value = t.payload
+        elif t.kind == _lib.NODE_MIX:
+            d.mix_type = int(t.payload)
+        elif t.kind == _lib.NODE_EMBED:
+            d.embed_id = int(t.payload)
+        elif t.kind == _lib.NODE_GRAPH:
+            d.graph = t.payload._h
+            keep.append(t.payload)
+        elif t.payload is not None:
+            b = t.payload.encode("utf-8")
+            keep.append(b)
+            d.name = b
+        d.resize_policy = self.resize_policy.kind
+        d.policy_slot = int(self.resize_policy.slot)
+        d.policy_width, d.policy_height = self.resize_policy.size.width, self.resize_policy.size.height
+        d.resize_filter = int(self.resize_filter)
+        return d, keep
+
+    @staticmethod
+    def _from_desc(d):
+        k = d.node_type
+        if k == _lib.NODE_VALUE:
+            t = NodeType(k, float(d.value))
+        elif k == _lib.NODE_MIX:
+            t = NodeType(k, MixType(d.mix_type))
+        elif k == _lib.NODE_EMBED:
+            t = NodeType(k, EmbeddedSlotDataId(d.embed_id))
+        elif k == _lib.NODE_GRAPH:
+            t = NodeType(k, NodeGraph._clone_of(d.graph))
+        elif k in (_lib.NODE_HEIGHT_TO_NORMAL, _lib.NODE_SEPARATE_RGBA, _lib.NODE_COMBINE_RGBA):
+            t = NodeType(k)
+        else:
+            t = NodeType(k, (d.name or b"").decode("utf-8"))
+        n = Node(t, d.node_id)
+        if d.resize_policy == 4:
+            n.resize_policy = ResizePolicy.SpecificSlot(SlotId(d.policy_slot))
+        elif d.resize_policy == 5:
+            n.resize_policy = ResizePolicy.SpecificSize(Size(d.policy_width, d.policy_height))
+        else:
+            n.resize_policy = ResizePolicy(d.resize_policy)
+        n.resize_filter = ResizeFilter(d.resize_filter)
+        return n
+
+    def _slots(self, fn):
+        d, keep = self._desc()
+        arr = (kc_slot * 64)()
+        n = C.c_size_t()
+        call(fn, C.byref(d), arr, 64, C.byref(n))
+        return [Slot(arr[i].name.decode(), arr[i].slot_id, arr[i].slot_type) for i in range(n.value)]
+
+    def input_slots(self):  # node_type.rs:141-175
+        return self._slots("kc_node_input_slots")
+
+    def output_slots(self):  # node_type.rs:177-211
+        return self._slots("kc_node_output_slots")
+
+    def input_slot_with_name(self, name):
+        for s in self.input_slots():
+            if s.name == name:
+                return s
+        raise TexProError(19, "no input slot named %r" % name)
+
+    def output_slot_with_name(self, name):
+        for s in self.output_slots():
+            if s.name == name:
+                return s
+        raise TexProError(19, "no output slot named %r" % name)
+
+    def __repr__(self):
+        return "Node(%d, %r)" % (self.node_id, self.node_type)
+
+
+class Edge:  # src/edge.rs:9-14
+    def __init__(self, output_id, input_id, output_slot, input_slot):
+        self.output_id, self.input_id = NodeId(output_id), NodeId(input_id)
+        self.output_slot, self.input_slot = SlotId(output_slot), SlotId(input_slot)
+
+    new = staticmethod(lambda a, b, c, d: Edge(a, b, c, d))
+
+    def _tuple(self):
+        return (int(self.output_id), int(self.input_id), int(self.output_slot), int(self.input_slot))
+
+    def __eq__(self, o):
+        return isinstance(o, Edge) and self._tuple() == o._tuple()
+
+    def __repr__(self):
+        return "Edge(%d:%d -> %d:%d)" % (self.output_id, self.output_slot, self.input_id, self.input_slot)
+
+
+class _GraphView:
+    """Read-side of a kc_graph handle; shared by NodeGraph and LiveGraph."""
+
+    def _graph_handle(self):
+        raise NotImplementedError
+
+    @property
+    def nodes(self):
+        h = self._graph_handle()
+        n = C.c_size_t()
+        call("kc_graph_node_count", h, C.byref(n))
+        out = []
+        for i in range(n.value):
+            d = kc_node_desc()
+            call("kc_graph_node_at", h, i, C.byref(d))
+            out.append(Node._from_desc(d))
+        return out
+
+    @property
+    def edges(self):
+        h = self._graph_handle()
+        n = C.c_size_t()
+        call("kc_graph_edge_count", h, C.byref(n))
+        out = []
+        for i in range(n.value):
+            e = kc_edge()
+            call("kc_graph_edge_at", h, i, C.byref(e))
+            out.append(Edge(e.output_id, e.input_id, e.output_slot, e.input_slot))
+        return out
+
+    def node(self, node_id):
+        d = kc_node_desc()
+        call("kc_graph_node", self._graph_handle(), int(node_id), C.byref(d))
+        return Node._from_desc(d)
+
+    def has_node_with_id(self, node_id):
+        self.node(node_id)
+
+    def node_ids(self):
+        return [n.node_id for n in self.nodes]
+
+    def _ids(self, fn):
+        arr = (C.c_uint32 * 4096)()
+        n = C.c_size_t()
+        call(fn, self._graph_handle(), arr, 4096, C.byref(n))
+        return [NodeId(arr[i]) for i in range(n.value)]
+
+    def output_ids(self):
+        return self._ids("kc_graph_output_ids")
+
+    def input_ids(self):
+        return self._ids("kc_graph_input_ids")
+
+    def input_slot_id_with_name(self, name):
+        s = C.c_uint32()
+        call("kc_graph_input_slot_id_with_name", self._graph_handle(), name.encode(), C.byref(s))
+        return SlotId(s.value)
+
+    def output_slot_id_with_name(self, name):
+        s = C.c_uint32()
+        call("kc_graph_output_slot_id_with_name", self._graph_handle(), name.encode(), C.byref(s))
+        return SlotId(s.value)
+
+    def input_edges(self, node_id):
+        return [e for e in self.edges if e.input_id == node_id]
+
+    def get_parents(self, node_id):
+        return sorted({e.output_id for e in self.edges if e.input_id == node_id})
+
+    def get_children(self, node_id):
+        self.has_node_with_id(node_id)
+        return sorted({e.input_id for e in self.edges if e.output_id == node_id})
+
+    def export_json_string(self):
+        p = C.c_void_p()
+        call("kc_graph_export_json", self._graph_handle(), C.byref(p))
+        try:
+            return C.string_at(p).decode("utf-8")
+        finally:
+            _lib.lib.kc_free(p)
+
+
+class NodeGraph(_GraphView):
+    """`struct NodeGraph`, src/node_graph.rs:17-22."""
+
+    def __init__(self, handle=None):
+        if handle is None:
+            h = C.c_void_p()
+            call("kc_graph_create", C.byref(h))
+            handle = h
+        self._h = handle
+
+    new = staticmethod(lambda: NodeGraph())
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            _lib.lib.kc_graph_destroy(self._h)
+            self._h = None
+
+    def _graph_handle(self):
+        return self._h
+
+    @staticmethod
+    def _clone_of(raw_handle):
+        h = C.c_void_p()
+        call("kc_graph_clone", raw_handle, C.byref(h))
+        return NodeGraph(h)
+
+    def clone(self):
+        return NodeGraph._clone_of(self._h)
+
+    @staticmethod
+    def from_path(path):  # :33-46
+        h = C.c_void_p()
+        call("kc_graph_from_path", str(path).encode(), C.byref(h))
+        return NodeGraph(h)
+
+    @staticmethod
+    def from_json(text):
+        h = C.c_void_p()
+        call("kc_graph_from_json", text.encode("utf-8"), C.byref(h))
+        return NodeGraph(h)
+
+    def export_json(self, path):  # :98-102
+        call("kc_graph_export_json_path", self._h, str(path).encode())
+
+    def add_node(self, node):  # :332-337
+        d, keep = node._desc()
+        out = C.c_uint32()
+        call("kc_graph_add_node", self._h, C.byref(d), C.byref(out))
+        return NodeId(out.value)
+
+    def add_node_with_id(self, node):  # :339-348
+        d, keep = node._desc()
+        call("kc_graph_add_node_with_id", self._h, C.byref(d))
+
+    def remove_node(self, node_id):
+        call("kc_graph_remove_node", self._h, int(node_id))
+
+    def connect(self, output_node, input_node, output_slot, input_slot):  # :416-446
+        call("kc_graph_connect", self._h, int(output_node), int(input_node), int(output_slot), int(input_slot))
+        return Edge(output_node, input_node, output_slot, input_slot)
+
+    def try_connect(self, output_node, input_node, output_slot, input_slot):  # :394-413
+        call("kc_graph_try_connect", self._h, int(output_node), int(input_node), int(output_slot), int(input_slot))
+
+    def disconnect_slot(self, node_id, side, slot_id):  # :500-520
+        call("kc_graph_disconnect_slot", self._h, int(node_id), int(side), int(slot_id))
+
+    def remove_edge(self, edge):
+        e = kc_edge(*edge._tuple())
+        call("kc_graph_remove_edge", self._h, C.byref(e))
+
+    def set_mix_type(self, node_id, mix_type):  # :48-63
+        n = self.node(node_id)
+        if n.node_type.kind != _lib.NODE_MIX:
+            raise TexProError(5, "node %d is not a Mix node" % node_id)
+        n.node_type = NodeType.Mix(mix_type)
+        d, keep = n._desc()
+        call("kc_graph_set_node", self._h, C.byref(d))
+
+
+# ---- pixel data -------------------------------------------------------------------
+class SlotImage:
+    """`enum SlotImage { Gray(plane), Rgba([plane; 4]) }`, src/slot_image.rs:16-19.
+    Owns one reference on each device plane."""
+
+    def __init__(self, ctx, raw):
+        self._ctx = ctx          # _Context
+        self._im = raw           # kc_image (owned references)
+
+    def __del__(self):
+        im = getattr(self, "_im", None)
+        if im is not None and self._ctx is not None and self._ctx._h:
+            _lib.lib.kc_image_release(C.byref(im))
+            self._im = None
+
+    # constructors
+    @staticmethod
+    def from_value(tex_pro, size, value, rgba):  # :28-64
+        im = kc_image()
+        call("kc_image_from_value", tex_pro._ctx._h, size.width, size.height, float(value), int(bool(rgba)), C.byref(im))
+        return SlotImage(tex_pro._ctx, im)
+
+    @staticmethod
+    def from_planes(tex_pro, planes):
+        """planes: one (Gray) or four (Rgba) float32 arrays of shape (h, w)."""
+        arrs = [np.ascontiguousarray(p, dtype=np.float32) for p in planes]
+        if len(arrs) not in (1, 4):
+            raise TexProError(4, "need 1 or 4 planes")
+        h, w = arrs[0].shape
+        ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+        im = kc_image()
+        call("kc_image_from_host_planes", tex_pro._ctx._h, 1 if len(arrs) == 4 else 0, w, h, ptrs, C.byref(im))
+        call("kc_context_synchronize", tex_pro._ctx._h)  # the host arrays may go away after this returns
+        return SlotImage(tex_pro._ctx, im)
+
+    @staticmethod
+    def from_u8(tex_pro, samples):
+        """Decoded interleaved u8 samples, shape (h, w) or (h, w, c): deconstruct_image, src/shared.rs:16-56."""
+        a = np.ascontiguousarray(samples, dtype=np.uint8)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        h, w, c = a.shape
+        im = kc_image()
+        call("kc_image_from_u8", tex_pro._ctx._h, a.ctypes.data, w, h, c, C.byref(im))
+        call("kc_context_synchronize", tex_pro._ctx._h)
+        return SlotImage(tex_pro._ctx, im)
+
+    def is_rgba(self):
+        return self._im.kind == _lib.IMAGE_RGBA
+
+    def size(self):  # :116-121
+        w, h = C.c_uint32(), C.c_uint32()
+        call("kc_plane_size", self._im.planes[0], C.byref(w), C.byref(h))
+        return Size(w.value, h.value)
+
+    def _n(self):
+        return 4 if self.is_rgba() else 1
+
+    def to_u8(self, srgb=False):  # :142-207
+        s = self.size()
+        out = np.empty((s.height, s.width, 4), dtype=np.uint8)
+        call("kc_image_to_u8", self._ctx._h, C.byref(self._im), int(bool(srgb)), out.ctypes.data)
+        return out
+
+    def to_u8_srgb(self):
+        return self.to_u8(True)
+
+    def as_type(self, rgba):  # :212-256
+        im = kc_image()
+        call("kc_image_as_type", self._ctx._h, C.byref(self._im), int(bool(rgba)), C.byref(im))
+        return SlotImage(self._ctx, im)
+
+    def planes(self):
+        """The f32 planes on the host, one (h, w) array per plane."""
+        out = []
+        for c in range(self._n()):
+            w, h = C.c_uint32(), C.c_uint32()
+            call("kc_plane_size", self._im.planes[c], C.byref(w), C.byref(h))
+            a = np.empty((h.value, w.value), dtype=np.float32)
+            call("kc_plane_download", self._im.planes[c], a.ctypes.data)
+            out.append(a)
+        return out
+
+    bufs = planes
+
+    def plane_is_constant(self, c):
+        k, v = C.c_int32(), C.c_float()
+        call("kc_plane_is_constant", self._im.planes[c], C.byref(k), C.byref(v))
+        return bool(k.value), v.value
+
+    def plane_handles(self):
+        return [self._im.planes[c] for c in range(self._n())]
+
+    def same_plane(self, c, other, oc):
+        return self._im.planes[c] == other._im.planes[oc]
+
+
+class SlotData:  # src/slot_data.rs:35-39
+    def __init__(self, node_id, slot_id, image):
+        self.node_id, self.slot_id, self.image = NodeId(node_id), SlotId(slot_id), image
+
+    new = staticmethod(lambda n, s, i: SlotData(n, s, i))
+
+    def size(self):
+        return self.image.size()
+
+
+class _Context:
+    def __init__(self, device, math_mode, fuse):
+        o = kc_options()
+        _lib.lib.kc_options_default(C.byref(o))
+        o.math_mode = int(math_mode)
+        o.fuse = int(bool(fuse))
+        self._h = C.c_void_p()
+        call("kc_context_create", int(device), C.byref(o), C.byref(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.lib.kc_context_destroy(self._h)
+            self._h = None
+
+
+def _decode_image(path):
+    """Host-side codec for Image nodes (image::open + as_flat_samples_u8,
+    src/shared.rs:16-56,241): 8-bit samples, 1..4 channels."""
+    from PIL import Image as PILImage
+    im = PILImage.open(path)
+    if im.mode in ("1", "I", "F", "I;16"):
+        im = im.convert("L")
+    elif im.mode == "P":
+        im = im.convert("RGBA" if "transparency" in im.info else "RGB")
+    elif im.mode not in ("L", "LA", "RGB", "RGBA"):
+        im = im.convert("RGBA")
+    return np.asarray(im, dtype=np.uint8)
+
+
+class TextureProcessor:
+    """`TextureProcessor`, src/texture_processor.rs:17-115.  One per device: owns
+    the CUDA context/stream/plane pool that replace the engine and
+    transient-buffer threads."""
+
+    def __init__(self, memory_threshold=None, device=0, math_mode=_lib.MATH_EXACT, fuse=True):
+        self.memory_threshold = memory_threshold
+        self._ctx = _Context(device, math_mode, fuse)
+        self._live_graphs = []
+
+    @staticmethod
+    def new(memory_threshold=None, **kw):
+        return TextureProcessor(memory_threshold, **kw)
+
+    def new_live_graph(self):  # :58-63
+        lg = LiveGraph(self)
+        self._live_graphs.append(lg)
+        return lg
+
+    def push_live_graph(self, live_graph):  # :65-69
+        self._live_graphs.append(live_graph)
+
+    def set_math_mode(self, mode):
+        call("kc_context_set_math_mode", self._ctx._h, int(mode))
+
+    def set_fuse(self, fuse):
+        call("kc_context_set_fuse", self._ctx._h, int(bool(fuse)))
+
+    def synchronize(self):
+        call("kc_context_synchronize", self._ctx._h)
+
+    def stats(self):
+        k, b = C.c_uint64(), C.c_uint64()
+        call("kc_context_stats", self._ctx._h, C.byref(k), C.byref(b))
+        return {"kernel_launches": k.value, "bytes_memory": b.value}
+
+    def bytes_memory(self):  # TransientBufferQueue::bytes_memory, src/transient_buffer.rs:413-420
+        return self.stats()["bytes_memory"]
+
+    def close(self):
+        for lg in self._live_graphs:
+            lg.close()
+        self._live_graphs = []
+        self._ctx.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class LiveGraph(_GraphView):
+    """`LiveGraph`, src/live_graph.rs:63-74."""
+
+    def __init__(self, tex_pro):
+        self._tp = tex_pro
+        self._ctx = tex_pro._ctx
+        self._h = C.c_void_p()
+        call("kc_live_graph_create", self._ctx._h, C.byref(self._h))
+        self._use_cache = False
+        self._auto_update = False
+        self._images_loaded = {}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._ctx._h:
+            _lib.lib.kc_live_graph_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        self.close()
+
+    # RwLock-style accessors so code written for Arc<RwLock<LiveGraph>> reads the same
+    def write(self):
+        return self
+
+    def read(self):
+        return self
+
+    def unwrap(self):
+        return self
+
+    def _graph_handle(self):
+        g = C.c_void_p()
+        call("kc_live_graph_node_graph", self._h, C.byref(g))
+        return g
+
+    use_cache = property(lambda s: s._use_cache, lambda s, v: (setattr(s, "_use_cache", bool(v)), call("kc_live_graph_set_use_cache", s._h, int(bool(v))))[0])
+    auto_update = property(lambda s: s._auto_update, lambda s, v: (setattr(s, "_auto_update", bool(v)), call("kc_live_graph_set_auto_update", s._h, int(bool(v))))[0])
+
+    def set_node_graph(self, node_graph):
+        call("kc_live_graph_set_node_graph", self._h, node_graph._h)
+        self._images_loaded = {}
+
+    def add_node(self, node):
+        d, keep = node._desc()
+        out = C.c_uint32()
+        call("kc_live_graph_add_node", self._h, C.byref(d), C.byref(out))
+        return NodeId(out.value)
+
+    def add_node_with_id(self, node):
+        d, keep = node._desc()
+        call("kc_live_graph_add_node_with_id", self._h, C.byref(d))
+
+    def remove_node(self, node_id):
+        call("kc_live_graph_remove_node", self._h, int(node_id))
+
+    def connect(self, output_node, input_node, output_slot, input_slot):
+        call("kc_live_graph_connect", self._h, int(output_node), int(input_node), int(output_slot), int(input_slot))
+        return Edge(output_node, input_node, output_slot, input_slot)
+
+    def disconnect_slot(self, node_id, side, slot_id):
+        call("kc_live_graph_disconnect_slot", self._h, int(node_id), int(side), int(slot_id))
+
+    def set_node(self, node):
+        d, keep = node._desc()
+        call("kc_live_graph_set_node", self._h, C.byref(d))
+
+    def add_input_slot_data(self, slot_data):  # :347-350
+        call("kc_live_graph_add_input_slot_data", self._h, int(slot_data.node_id), int(slot_data.slot_id), C.byref(slot_data.image._im))
+
+    def embed_slot_data_with_id(self, slot_data, esd_id):  # :324-341
+        call("kc_live_graph_embed_slot_data_with_id", self._h, C.byref(slot_data.image._im), int(slot_data.slot_id), int(esd_id))
+        return EmbeddedSlotDataId(esd_id)
+
+    def replace_embedded(self, image, esd_id):
+        call("kc_live_graph_replace_embedded", self._h, C.byref(image._im), int(esd_id))
+
+    def _load_images(self):
+        # the Image node's codec runs on the host side of the boundary
+        for n in self.nodes:
+            if n.node_type.kind == _lib.NODE_IMAGE and self._images_loaded.get(int(n.node_id)) != n.node_type.payload:
+                try:
+                    px = _decode_image(n.node_type.payload)
+                except Exception:
+                    self._images_loaded[int(n.node_id)] = n.node_type.payload
+                    continue  # unreadable => the node yields 1x1 magenta (src/node/image.rs:13-18)
+                if px.ndim == 2:
+                    px = px[:, :, None]
+                px = np.ascontiguousarray(px)
+                call("kc_live_graph_set_image_data_u8", self._h, int(n.node_id), px.ctypes.data, px.shape[1], px.shape[0], px.shape[2])
+                self._images_loaded[int(n.node_id)] = n.node_type.payload
+
+    def request(self, node_id):  # :219-227 (+ the engine's work)
+        self._load_images()
+        ids = (C.c_uint32 * 1)(int(node_id))
+        call("kc_live_graph_request", self._h, ids, 1)
+
+    def request_many(self, node_ids):
+        self._load_images()
+        ids = (C.c_uint32 * len(node_ids))(*[int(i) for i in node_ids])
+        call("kc_live_graph_request", self._h, ids, len(node_ids))
+
+    prioritise = request
+
+    @staticmethod
+    def await_clean_read(live_graph, node_id):  # :181-195
+        live_graph._load_images()
+        call("kc_live_graph_await_clean", live_graph._h, int(node_id))
+        return live_graph
+
+    await_clean_write = await_clean_read
+
+    def cancel(self):
+        call("kc_live_graph_cancel", self._h)
+
+    def node_state(self, node_id):  # :243-249
+        s = C.c_int32()
+        call("kc_live_graph_node_state", self._h, int(node_id), C.byref(s))
+        return NodeState(s.value)
+
+    def slot_data(self, node_id, slot_id):  # :415-420
+        im = kc_image()
+        call("kc_live_graph_slot_data", self._h, int(node_id), int(slot_id), C.byref(im))
+        return SlotData(node_id, slot_id, SlotImage(self._ctx, im))
+
+    def node_slot_datas(self, node_id):  # :389-405
+        arr = (C.c_uint32 * 64)()
+        n = C.c_size_t()
+        call("kc_live_graph_node_slot_ids", self._h, int(node_id), arr, 64, C.byref(n))
+        return [self.slot_data(node_id, arr[i]) for i in range(n.value)]
+
+    def slot_data_size(self, node_id, slot_id):  # :407-409
+        w, h = C.c_uint32(), C.c_uint32()
+        call("kc_live_graph_slot_data_size", self._h, int(node_id), int(slot_id), C.byref(w), C.byref(h))
+        return Size(w.value, h.value)
+
+    def buffer_rgba(self, node_id, slot_id):  # :93-95
+        s = self.slot_data_size(node_id, slot_id)
+        out = np.empty((s.height, s.width, 4), dtype=np.uint8)
+        call("kc_live_graph_buffer_rgba", self._h, int(node_id), int(slot_id), out.ctypes.data, out.nbytes)
+        return out
+
+    def buffer_srgba(self, node_id, slot_id):  # :127-153
+        s = self.slot_data_size(node_id, slot_id)
+        out = np.empty((s.height, s.width, 4), dtype=np.uint8)
+        call("kc_live_graph_buffer_srgba", self._h, int(node_id), int(slot_id), out.ctypes.data, out.nbytes)
+        return out
+
+    def read_rgba(self, node_id, slot_id, size, srgb=False, out=None):
+        """await_clean_read + buffer_rgba as one call; the f32->RGBA8 conversion is
+        fused into the kernel that computes the node (no f32 round trip)."""
+        self._load_images()
+        if out is None:
+            out = np.empty((size.height, size.width, 4), dtype=np.uint8)
+        call("kc_live_graph_read_rgba", self._h, int(node_id), int(slot_id), int(bool(srgb)), out.ctypes.data, out.nbytes)
+        return out
+
+    def last_run_stats(self):
+        k, g, b = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        call("kc_live_graph_last_run_stats", self._h, C.byref(k), C.byref(g), C.byref(b))
+        return {"kernels": k.value, "fused_groups": g.value, "algorithmic_bytes": b.value}
+
+
+def graph_to_dict(graph_view):
+    """serde-shaped dict of a NodeGraph/LiveGraph (for comparisons in tests)."""
+    return _json.loads(graph_view.export_json_string())

@@ -1,0 +1,72 @@
+"""Builds libkanter_b200.so in-tree with nvcc for sm_100a.
+
+Usage: python -m kanter_core_b200.build [--force]
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libkanter_b200.so")
+SOURCES = ["kc_context.cu", "kc_kernels.cu", "kc_fusion.cu", "kc_h2n.cu", "kc_resize.cu", "kc_graph.cu", "kc_exec.cu"]
+HEADERS = ["kc_internal.h", "kc_graph.h", os.path.join("..", "..", "include", "kanter_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",            # the reference never contracts a*b+c; FMAs are written out where wanted
+    "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
+    "-Xptxas", "-v",
+    "-cudart", "static",
+]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.sep not in cand or os.path.exists(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        o = os.path.join(objdir, s.replace(".cu", ".o"))
+        objs.append(o)
+        cmd = [nvcc_path()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log = []
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        log.append("== %s ==\n%s" % (s, out))
+        failed |= p.returncode != 0
+    with open(os.path.join(objdir, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if failed:
+        sys.stderr.write("\n".join(log))
+        raise RuntimeError("nvcc failed")
+    if verbose:
+        print("\n".join(log))
+    cmd = [nvcc_path(), "-shared", "-cudart", "static", "-o", LIB] + objs
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

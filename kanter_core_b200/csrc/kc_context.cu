@@ -1,0 +1,510 @@
+// kc_context.cu — context, device-resident planes and SlotImage handles.
+//
+// Replaces the reference's pixel-buffer layer: `Buffer`/`SlotImage`
+// (src/slot_image.rs:12-19), `SlotData` (src/slot_data.rs:35-39) and the
+// in-memory half of `TransientBuffer{,Container}` (src/transient_buffer.rs:28-31,
+// 188-247).  Planes are f32, row-major, one allocation per channel, in HBM,
+// immutable once written, reference counted.  Constant planes (`vec![v; n]`)
+// stay descriptors until somebody needs their pixels.
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+
+#include "kc_internal.h"
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void kc_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* kc_last_error(void) { return g_err; }
+extern "C" int32_t kc_abi_version(void) { return KC_ABI_VERSION; }
+extern "C" void kc_free(void* p) { free(p); }
+
+extern "C" const char* kc_error_string(int32_t code) {
+    // Display for TexProError, src/error.rs:37-64
+    switch (code) {
+        case KC_OK: return "Ok";
+        case KC_ERR_GENERIC: return "Something went wrong";
+        case KC_ERR_CANCELED: return "Node processing was canceled";
+        case KC_ERR_IMAGE: return "Image error";
+        case KC_ERR_INVALID_BUFFER_COUNT: return "Invalid number of channels";
+        case KC_ERR_INVALID_NODE_ID: return "Invalid `NodeId`";
+        case KC_ERR_INVALID_NODE_TYPE: return "Invalid `NodeType`";
+        case KC_ERR_INVALID_SLOT_ID: return "Invalid `SlotId`";
+        case KC_ERR_INVALID_SLOT_TYPE: return "Invalid `SlotType`";
+        case KC_ERR_INVALID_EDGE: return "Invalid `Edge`";
+        case KC_ERR_NO_SLOT_DATA: return "Could not find a `SlotData`";
+        case KC_ERR_SLOT_OCCUPIED: return "`SlotId` is already in use";
+        case KC_ERR_SLOT_NOT_OCCUPIED: return "`SlotId` is not in use";
+        case KC_ERR_UNABLE_TO_LOCK: return "Unable to get a lock";
+        case KC_ERR_NODE_PROCESSING: return "Error during node processing";
+        case KC_ERR_POISON: return "Error with poisoned lock";
+        case KC_ERR_TRY_LOCK: return "Error when trying to lock";
+        case KC_ERR_NODE_DIRTY: return "The node is not up to date";
+        case KC_ERR_IO: return "I/O error";
+        case KC_ERR_INVALID_NAME:
+            return "Invalid name, can only contain lowercase letters, numbers and underscores";
+        case KC_ERR_CUDA: return "CUDA error";
+        case KC_ERR_INVALID_ARGUMENT: return "Invalid argument";
+        default: return "Unknown error";
+    }
+}
+
+extern "C" int32_t kc_host_alloc(size_t bytes, void** out) {
+    if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "kc_host_alloc: out is NULL");
+    KC_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return KC_OK;
+}
+extern "C" int32_t kc_host_free(void* p) {
+    if (p) KC_CUDA(cudaFreeHost(p));
+    return KC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" void kc_options_default(kc_options* o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->math_mode = KC_MATH_EXACT;
+    o->fuse = 1;
+}
+
+extern "C" int32_t kc_context_create(int32_t device, const kc_options* opts, kc_context** out) {
+    if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "kc_context_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        KC_FAIL(KC_ERR_CUDA, "no CUDA device available (%s); this backend has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, n);
+    cudaDeviceProp prop;
+    KC_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        KC_FAIL(KC_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device,
+                prop.major, prop.minor);
+    auto* ctx = new kc_context();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    kc_options_default(&ctx->opts);
+    if (opts) ctx->opts = *opts;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    KC_CUDA(cudaSetDevice(device));
+    KC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    // keep freed planes in the stream-ordered pool instead of returning them to the driver
+    cudaMemPool_t pool;
+    KC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    KC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    cudaSetDevice(prev);
+    *out = ctx;
+    return KC_OK;
+}
+
+static void axis_table_free(KcAxisTable& t) {
+    if (t.d_left) cudaFree(t.d_left);
+    if (t.d_count) cudaFree(t.d_count);
+    if (t.d_weights) cudaFree(t.d_weights);
+    t.d_left = t.d_count = nullptr;
+    t.d_weights = nullptr;
+}
+
+extern "C" int32_t kc_context_destroy(kc_context* ctx) {
+    if (!ctx) return KC_OK;
+    {
+        KcGuard g(ctx);
+        cudaStreamSynchronize(ctx->stream);
+        for (auto& kv : ctx->axis_tables) axis_table_free(*kv.second);
+        ctx->axis_tables.clear();
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+    return KC_OK;
+}
+
+extern "C" int32_t kc_context_synchronize(kc_context* ctx) {
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    KcGuard g(ctx);
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KC_OK;
+}
+extern "C" int32_t kc_context_device(const kc_context* ctx, int32_t* device) {
+    if (!ctx || !device) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    *device = ctx->device;
+    return KC_OK;
+}
+extern "C" int32_t kc_context_stream(const kc_context* ctx, void** stream) {
+    if (!ctx || !stream) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    *stream = (void*)ctx->stream;
+    return KC_OK;
+}
+extern "C" int32_t kc_context_set_math_mode(kc_context* ctx, int32_t mode) {
+    if (!ctx || (mode != KC_MATH_EXACT && mode != KC_MATH_FAST)) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad math mode");
+    ctx->opts.math_mode = mode;
+    return KC_OK;
+}
+extern "C" int32_t kc_context_set_fuse(kc_context* ctx, int32_t fuse) {
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    ctx->opts.fuse = fuse ? 1 : 0;
+    return KC_OK;
+}
+extern "C" int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_launches, uint64_t* bytes_live) {
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (kernel_launches) *kernel_launches = ctx->kernel_launches;
+    if (bytes_live) *bytes_live = ctx->bytes_live;
+    return KC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// planes
+// ---------------------------------------------------------------------------
+int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out) {
+    auto* p = new kc_plane();
+    p->ctx = ctx;
+    p->w = w;
+    p->h = h;
+    p->kind = KC_PLANE_DEVICE;
+    // round up to a whole float4 so the vector kernels' last access stays in bounds
+    size_t bytes = ((p->bytes() + 15) / 16) * 16;
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync((void**)&p->dptr, bytes, ctx->stream);
+    if (e != cudaSuccess) {
+        delete p;
+        KC_FAIL(KC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    ctx->bytes_live += bytes;
+    *out = p;
+    return KC_OK;
+}
+
+kc_plane* kcp_new_const(kc_context* ctx, uint32_t w, uint32_t h, float v) {
+    auto* p = new kc_plane();
+    p->ctx = ctx;
+    p->w = w;
+    p->h = h;
+    p->kind = KC_PLANE_CONST;
+    p->value = v;
+    return p;
+}
+
+kc_plane* kcp_new_expr(kc_context* ctx, int op, kc_plane* a, kc_plane* b) {
+    auto* p = new kc_plane();
+    p->ctx = ctx;
+    // constants broadcast; the size comes from whichever side has pixels
+    const kc_plane* sz = (a->kind != KC_PLANE_CONST) ? a : b;
+    p->w = sz->w;
+    p->h = sz->h;
+    p->kind = KC_PLANE_EXPR;
+    p->op = op;
+    p->a = a;
+    p->b = b;
+    kcp_retain(a);
+    kcp_retain(b);
+    return p;
+}
+
+void kcp_retain(kc_plane* p) {
+    if (p) p->refs.fetch_add(1, std::memory_order_relaxed);
+}
+
+void kcp_release(kc_plane* p) {
+    // iterative so that long lazy chains cannot overflow the stack
+    std::vector<kc_plane*> work;
+    if (p) work.push_back(p);
+    while (!work.empty()) {
+        kc_plane* q = work.back();
+        work.pop_back();
+        if (q->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) continue;
+        if (q->kind == KC_PLANE_DEVICE && q->owned && q->dptr) {
+            KcGuard g(q->ctx);
+            cudaFreeAsync(q->dptr, q->ctx->stream);
+            size_t bytes = ((q->bytes() + 15) / 16) * 16;
+            if (bytes == 0) bytes = 16;
+            q->ctx->bytes_live -= bytes;
+        } else if (q->kind == KC_PLANE_EXPR) {
+            if (q->a) work.push_back(q->a);
+            if (q->b) work.push_back(q->b);
+        }
+        delete q;
+    }
+}
+
+void kci_retain(const kc_image* im) {
+    for (int c = 0; c < 4; ++c)
+        if (im->planes[c]) kcp_retain(im->planes[c]);
+}
+void kci_release(kc_image* im) {
+    for (int c = 0; c < 4; ++c) {
+        if (im->planes[c]) kcp_release(im->planes[c]);
+        im->planes[c] = nullptr;
+    }
+}
+
+extern "C" int32_t kc_plane_create(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out) {
+    if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    return kcp_new_device(ctx, w, h, out);
+}
+
+extern "C" int32_t kc_plane_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, kc_plane** out) {
+    if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = kcp_new_const(ctx, w, h, v);
+    return KC_OK;
+}
+
+extern "C" int32_t kc_plane_from_host(kc_context* ctx, uint32_t w, uint32_t h, const float* host, kc_plane** out) {
+    if (!ctx || !out || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    kc_plane* p = nullptr;
+    KC_TRY(kcp_new_device(ctx, w, h, &p));
+    cudaError_t e = cudaMemcpyAsync(p->dptr, host, p->bytes(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        kcp_release(p);
+        KC_FAIL(KC_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    }
+    *out = p;
+    return KC_OK;
+}
+
+extern "C" int32_t kc_plane_wrap_device(kc_context* ctx, uint32_t w, uint32_t h, void* device_ptr, kc_plane** out) {
+    if (!ctx || !out || !device_ptr) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (((uintptr_t)device_ptr & 15) != 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "device pointer must be 16-byte aligned");
+    auto* p = new kc_plane();
+    p->ctx = ctx;
+    p->w = w;
+    p->h = h;
+    p->kind = KC_PLANE_DEVICE;
+    p->dptr = (float*)device_ptr;
+    p->owned = false;
+    *out = p;
+    return KC_OK;
+}
+
+extern "C" int32_t kc_plane_retain(kc_plane* p) {
+    if (!p) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane is NULL");
+    kcp_retain(p);
+    return KC_OK;
+}
+extern "C" int32_t kc_plane_release(kc_plane* p) {
+    if (!p) return KC_OK;
+    kc_context* ctx = p->ctx;
+    KcGuard g(ctx);
+    kcp_release(p);
+    return KC_OK;
+}
+extern "C" int32_t kc_plane_size(const kc_plane* p, uint32_t* w, uint32_t* h) {
+    if (!p) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane is NULL");
+    if (w) *w = p->w;
+    if (h) *h = p->h;
+    return KC_OK;
+}
+extern "C" int32_t kc_plane_is_constant(const kc_plane* p, int32_t* is_const, float* value) {
+    if (!p) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane is NULL");
+    if (is_const) *is_const = p->kind == KC_PLANE_CONST;
+    if (value) *value = p->kind == KC_PLANE_CONST ? p->value : 0.0f;
+    return KC_OK;
+}
+extern "C" int32_t kc_plane_device_ptr(kc_plane* p, void** device_ptr) {
+    if (!p || !device_ptr) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(p->ctx);
+    KC_TRY(kcp_force(p->ctx, &p, 1));
+    *device_ptr = p->dptr;
+    return KC_OK;
+}
+extern "C" int32_t kc_plane_upload(kc_plane* p, const float* host) {
+    if (!p || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (p->kind != KC_PLANE_DEVICE) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane has no device storage");
+    KcGuard g(p->ctx);
+    KC_CUDA(cudaMemcpyAsync(p->dptr, host, p->bytes(), cudaMemcpyHostToDevice, p->ctx->stream));
+    return KC_OK;
+}
+extern "C" int32_t kc_plane_download(kc_plane* p, float* host) {
+    if (!p || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (p->kind == KC_PLANE_CONST) {  // a descriptor: fill on the host, no device work
+        size_t n = p->count();
+        for (size_t i = 0; i < n; ++i) host[i] = p->value;
+        return KC_OK;
+    }
+    KcGuard g(p->ctx);
+    KC_TRY(kcp_force(p->ctx, &p, 1));
+    KC_CUDA(cudaMemcpyAsync(host, p->dptr, p->bytes(), cudaMemcpyDeviceToHost, p->ctx->stream));
+    KC_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    return KC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// images
+// ---------------------------------------------------------------------------
+extern "C" int32_t kc_image_from_u8(kc_context* ctx, const uint8_t* samples, uint32_t w, uint32_t h,
+                                    uint32_t channels, kc_image* out) {
+    // deconstruct_image, src/shared.rs:16-56: u8/255 per sample, channels dealt
+    // round-robin, absent colour planes 0.0, absent alpha 1.0.  read_slot_image
+    // (:218-261) always ends up with four planes, i.e. an Rgba image.
+    if (!ctx || !samples || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (channels < 1 || channels > 4) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "channels must be 1..4, got %u", channels);
+    KcGuard g(ctx);
+    kci_clear(out);
+    out->kind = KC_IMAGE_RGBA;
+    out->width = w;
+    out->height = h;
+    size_t n = (size_t)w * h;
+    uint8_t* d_samples = nullptr;
+    KC_CUDA(cudaMallocAsync((void**)&d_samples, n * channels + 16, ctx->stream));
+    cudaError_t e = cudaMemcpyAsync(d_samples, samples, n * channels, cudaMemcpyHostToDevice, ctx->stream);
+    float* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+    int32_t rc = e == cudaSuccess ? KC_OK : KC_ERR_CUDA;
+    for (uint32_t c = 0; c < 4 && rc == KC_OK; ++c) {
+        if (c < channels) {
+            rc = kcp_new_device(ctx, w, h, &out->planes[c]);
+            if (rc == KC_OK) ptrs[c] = out->planes[c]->dptr;
+        } else {
+            out->planes[c] = kcp_new_const(ctx, w, h, c == 3 ? 1.0f : 0.0f);
+        }
+    }
+    if (rc == KC_OK) rc = kck_from_u8(ctx, d_samples, channels, n, ptrs);
+    cudaFreeAsync(d_samples, ctx->stream);
+    if (rc != KC_OK) {
+        kci_release(out);
+        if (e != cudaSuccess) kc_set_error("upload failed: %s", cudaGetErrorString(e));
+        return rc;
+    }
+    return KC_OK;
+}
+
+extern "C" int32_t kc_image_from_host_planes(kc_context* ctx, int32_t kind, uint32_t w, uint32_t h,
+                                             const float* const* planes, kc_image* out) {
+    if (!ctx || !planes || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    kci_clear(out);
+    out->kind = kind == KC_IMAGE_RGBA ? KC_IMAGE_RGBA : KC_IMAGE_GRAY;
+    out->width = w;
+    out->height = h;
+    int np = kci_nplanes(out);
+    for (int c = 0; c < np; ++c) {
+        int32_t rc = kc_plane_from_host(ctx, w, h, planes[c], &out->planes[c]);
+        if (rc != KC_OK) {
+            kci_release(out);
+            return rc;
+        }
+    }
+    return KC_OK;
+}
+
+extern "C" int32_t kc_image_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, int32_t rgba, kc_image* out) {
+    // SlotImage::from_value, src/slot_image.rs:28-64: alpha is 1.0 whatever v is
+    if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    kci_clear(out);
+    out->width = w;
+    out->height = h;
+    if (rgba) {
+        out->kind = KC_IMAGE_RGBA;
+        for (int c = 0; c < 3; ++c) out->planes[c] = kcp_new_const(ctx, w, h, v);
+        out->planes[3] = kcp_new_const(ctx, w, h, 1.0f);
+    } else {
+        out->kind = KC_IMAGE_GRAY;
+        out->planes[0] = kcp_new_const(ctx, w, h, v);
+    }
+    return KC_OK;
+}
+
+extern "C" int32_t kc_image_retain(const kc_image* img) {
+    if (!img) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "image is NULL");
+    kci_retain(img);
+    return KC_OK;
+}
+extern "C" int32_t kc_image_release(kc_image* img) {
+    if (!img) return KC_OK;
+    kc_context* ctx = nullptr;
+    for (int c = 0; c < 4; ++c)
+        if (img->planes[c]) ctx = img->planes[c]->ctx;
+    if (!ctx) return KC_OK;
+    KcGuard g(ctx);
+    kci_release(img);
+    return KC_OK;
+}
+
+extern "C" int32_t kc_image_download(kc_context* ctx, const kc_image* in, float* const* host_planes) {
+    if (!ctx || !in || !host_planes) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    int np = kci_nplanes(in);
+    // one fused launch for whatever is still lazy, then the copies
+    std::vector<kc_plane*> lazy;
+    for (int c = 0; c < np; ++c)
+        if (in->planes[c]->kind == KC_PLANE_EXPR) lazy.push_back(in->planes[c]);
+    if (!lazy.empty()) KC_TRY(kcp_force(ctx, lazy.data(), lazy.size()));
+    for (int c = 0; c < np; ++c) {
+        kc_plane* p = in->planes[c];
+        if (p->kind == KC_PLANE_CONST) {
+            size_t n = p->count();
+            for (size_t i = 0; i < n; ++i) host_planes[c][i] = p->value;
+        } else {
+            KC_CUDA(cudaMemcpyAsync(host_planes[c], p->dptr, p->bytes(), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KC_OK;
+}
+
+extern "C" int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, int32_t srgb, void* device_rgba8) {
+    if (!ctx || !in || !device_rgba8) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (((uintptr_t)device_rgba8 & 15) != 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "device pointer must be 16-byte aligned");
+    KcGuard g(ctx);
+    return kcp_export_rgba8(ctx, in, srgb, (uint32_t*)device_rgba8);
+}
+
+extern "C" int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) {
+    // SlotImage::to_u8 / to_u8_srgb, src/slot_image.rs:142-207
+    if (!ctx || !in || !host_rgba8) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    size_t n = (size_t)in->planes[0]->w * in->planes[0]->h;
+    uint32_t* d = nullptr;
+    KC_CUDA(cudaMallocAsync((void**)&d, ((n * 4 + 15) / 16) * 16 + 16, ctx->stream));
+    int32_t rc = kcp_export_rgba8(ctx, in, srgb, d);
+    if (rc == KC_OK) {
+        cudaError_t e = cudaMemcpyAsync(host_rgba8, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) {
+            kc_set_error("download failed: %s", cudaGetErrorString(e));
+            rc = KC_ERR_CUDA;
+        }
+    }
+    cudaFreeAsync(d, ctx->stream);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// device-side timing on the context's stream (what bench.py uses: CUDA events
+// recorded on the stream the kernels are launched on)
+// ---------------------------------------------------------------------------
+extern "C" int32_t kc_event_create(void** out) {
+    if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "out is NULL");
+    cudaEvent_t e;
+    KC_CUDA(cudaEventCreate(&e));
+    *out = (void*)e;
+    return KC_OK;
+}
+extern "C" int32_t kc_event_destroy(void* ev) {
+    if (ev) KC_CUDA(cudaEventDestroy((cudaEvent_t)ev));
+    return KC_OK;
+}
+extern "C" int32_t kc_event_record(kc_context* ctx, void* ev) {
+    if (!ctx || !ev) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    KC_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->stream));
+    return KC_OK;
+}
+extern "C" int32_t kc_event_elapsed_ms(void* start, void* stop, float* ms) {
+    if (!start || !stop || !ms) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+    KC_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return KC_OK;
+}

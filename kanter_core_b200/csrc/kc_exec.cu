@@ -1,0 +1,1074 @@
+// kc_exec.cu — per-node operators, the process_node seam and the LiveGraph
+// evaluator.  Host code; all pixel work is delegated to the kernels through
+// lazy expression planes (kc_fusion.cu) or the stencil / resize launchers.
+//
+// Reference: src/node/node_type.rs:98-138,213-267 (dispatch), src/shared.rs:61-216
+// (size policy + resize pre-pass), src/node/*.rs (node bodies), src/live_graph.rs
+// and src/engine.rs:34-307 (state machine, scheduling, parent-data freeing).
+#include <algorithm>
+#include <cstring>
+#include <set>
+
+#include "kc_graph.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// RAII image: owns one reference per plane
+// ---------------------------------------------------------------------------
+struct Img {
+    kc_image im;
+    Img() { kci_clear(&im); }
+    explicit Img(const kc_image& borrowed) : im(borrowed) { kci_retain(&im); }
+    Img(const Img& o) : im(o.im) { kci_retain(&im); }
+    Img(Img&& o) noexcept : im(o.im) { kci_clear(&o.im); }
+    Img& operator=(Img o) noexcept {
+        std::swap(im, o.im);
+        return *this;
+    }
+    ~Img() { kci_release(&im); }
+    bool rgba() const { return im.kind == KC_IMAGE_RGBA; }
+    uint32_t w() const { return im.planes[0]->w; }
+    uint32_t h() const { return im.planes[0]->h; }
+    // takes ownership of p's reference
+    void set(int c, kc_plane* p) {
+        if (im.planes[c]) kcp_release(im.planes[c]);
+        im.planes[c] = p;
+        if (c == 0) { im.width = p->w; im.height = p->h; }
+    }
+    void alias(int c, kc_plane* p) {
+        kcp_retain(p);
+        set(c, p);
+    }
+    kc_image release() {  // hand the references to a caller-owned kc_image
+        kc_image out = im;
+        kci_clear(&im);
+        return out;
+    }
+};
+
+struct Slot {
+    uint32_t node_id = 0, slot_id = 0;
+    Img image;
+};
+
+Img img_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, bool rgba) {  // slot_image.rs:28-64
+    Img out;
+    if (rgba) {
+        out.im.kind = KC_IMAGE_RGBA;
+        for (int c = 0; c < 3; ++c) out.set(c, kcp_new_const(ctx, w, h, v));
+        out.set(3, kcp_new_const(ctx, w, h, 1.0f));
+    } else {
+        out.im.kind = KC_IMAGE_GRAY;
+        out.set(0, kcp_new_const(ctx, w, h, v));
+    }
+    return out;
+}
+
+Img img_pixel(kc_context* ctx, float v) {  // Gray(pixel_buffer(v)), src/node/mod.rs:240-244
+    return img_from_value(ctx, 1, 1, v, false);
+}
+
+// one lazily evaluated per-pixel op; returns a new reference.  Constant operands
+// fold on the host (glibc powf == the reference's f32::powf).
+kc_plane* lazy_op(kc_context* ctx, int op, kc_plane* a, kc_plane* b) {
+    if (a->kind == KC_PLANE_CONST && b->kind == KC_PLANE_CONST)
+        return kcp_new_const(ctx, a->w, a->h, kc_host_mix(op, a->value, b->value));
+    return kcp_new_expr(ctx, op, a, b);
+}
+
+int32_t force_if_eager(kc_context* ctx, Img& im) {
+    if (ctx->opts.fuse) return KC_OK;
+    std::vector<kc_plane*> lazy;
+    for (int c = 0; c < kci_nplanes(&im.im); ++c)
+        if (im.im.planes[c]->kind == KC_PLANE_EXPR) lazy.push_back(im.im.planes[c]);
+    return lazy.empty() ? KC_OK : kcp_force(ctx, lazy.data(), lazy.size());
+}
+
+// SlotImage::as_type, src/slot_image.rs:212-256
+int32_t img_as_type(kc_context* ctx, const Img& in, bool rgba, Img& out) {
+    if (in.rgba() == rgba) {
+        out = in;
+        return KC_OK;
+    }
+    Img r;
+    if (!in.rgba()) {
+        r.im.kind = KC_IMAGE_RGBA;
+        for (int c = 0; c < 3; ++c) r.alias(c, in.im.planes[0]);
+        r.set(3, kcp_new_const(ctx, in.w(), in.h(), 1.0f));
+    } else {
+        r.im.kind = KC_IMAGE_GRAY;
+        // ((r + g) + b) / 3.0, :247-250
+        kc_plane* rg = lazy_op(ctx, KC_MIX_ADD, in.im.planes[0], in.im.planes[1]);
+        kc_plane* rgb = lazy_op(ctx, KC_MIX_ADD, rg, in.im.planes[2]);
+        kc_plane* three = kcp_new_const(ctx, in.w(), in.h(), 3.0f);
+        r.set(0, lazy_op(ctx, KC_MIX_DIVIDE, rgb, three));
+        kcp_release(rg);
+        kcp_release(rgb);
+        kcp_release(three);
+        KC_TRY(force_if_eager(ctx, r));
+    }
+    out = std::move(r);
+    return KC_OK;
+}
+
+// mix::process, src/node/mix.rs:51-134
+int32_t img_mix(kc_context* ctx, int mix_type, const Img* left, const Img* right, Img& out) {
+    if (mix_type < KC_MIX_ADD || mix_type > KC_MIX_POW) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad mix type %d", mix_type);
+    Img l, r;
+    if (left) {
+        l = *left;
+        if (right) KC_TRY(img_as_type(ctx, *right, l.rgba(), r));
+        else r = img_from_value(ctx, l.w(), l.h(), 0.0f, l.rgba());
+    } else if (right) {
+        r = *right;
+        l = img_from_value(ctx, r.w(), r.h(), 0.0f, r.rgba());
+    } else {
+        out = img_from_value(ctx, 1, 1, 0.0f, false);  // :77-83
+        return KC_OK;
+    }
+    const int np = l.rgba() ? 3 : 1;
+    for (int c = 0; c < np; ++c) {
+        const kc_plane *a = l.im.planes[c], *b = r.im.planes[c];
+        if (a->kind != KC_PLANE_CONST && b->kind != KC_PLANE_CONST && (a->w != b->w || a->h != b->h))
+            KC_FAIL(KC_ERR_GENERIC, "mix: operand sizes differ (%ux%u vs %ux%u); resize first", a->w, a->h, b->w, b->h);
+    }
+    Img res;
+    res.im.kind = l.rgba() ? KC_IMAGE_RGBA : KC_IMAGE_GRAY;
+    for (int c = 0; c < np; ++c) {
+        kc_plane* p = lazy_op(ctx, mix_type, l.im.planes[c], r.im.planes[c]);
+        // the result has the LEFT image's size (ImageBuffer::from_fn(size.width, ..), :140)
+        p->w = l.w();
+        p->h = l.h();
+        res.set(c, p);
+    }
+    if (l.rgba()) res.set(3, kcp_new_const(ctx, l.w(), l.h(), 1.0f));  // :203-212
+    KC_TRY(force_if_eager(ctx, res));
+    out = std::move(res);
+    return KC_OK;
+}
+
+// height_to_normal::process, src/node/height_to_normal.rs:16-77
+int32_t img_h2n(kc_context* ctx, const Img& in, Img& out) {
+    if (in.rgba()) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "HeightToNormal needs a Gray input");
+    kc_plane* src = in.im.planes[0];
+    KC_TRY(kcp_force(ctx, &src, 1));
+    Img res;
+    res.im.kind = KC_IMAGE_RGBA;
+    for (int c = 0; c < 3; ++c) {
+        kc_plane* p = nullptr;
+        KC_TRY(kcp_new_device(ctx, src->w, src->h, &p));
+        res.set(c, p);
+    }
+    res.set(3, kcp_new_const(ctx, src->w, src->h, 1.0f));  // from_buffers_rgb, slot_image.rs:90-102
+    KC_TRY(kck_height_to_normal(ctx, src->dptr, src->w, src->h, res.im.planes[0]->dptr, res.im.planes[1]->dptr,
+                                res.im.planes[2]->dptr));
+    ctx->run_bytes += (uint64_t)src->bytes() * 4;
+    out = std::move(res);
+    return KC_OK;
+}
+
+// one plane through imageops::resize; returns a new reference
+int32_t plane_resize(kc_context* ctx, kc_plane* src, uint32_t w, uint32_t h, int filter, kc_plane** out) {
+    if (filter < KC_FILTER_NEAREST || filter > KC_FILTER_LANCZOS3) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad filter %d", filter);
+    if (src->kind == KC_PLANE_CONST && src->w == 1 && src->h == 1) {
+        // A 1x1 source (every Value node) has a single tap per axis whose
+        // normalised weight is w/w.  When that is exactly 1.0 the result is the
+        // constant  clamp(0 + (0 + v*1)*1, 0, 1)  everywhere: fold it.
+        std::vector<uint32_t> l, n;
+        std::vector<float> wt;
+        uint32_t mt = 0;
+        bool unit = true;
+        for (uint32_t len : {h, w}) {
+            kc_resize_axis_host(1, len, filter, l, n, wt, mt);
+            for (uint32_t o = 0; o < len && unit; ++o) unit = n[o] == 1 && wt[(size_t)o * mt] == 1.0f;
+        }
+        if (unit) {
+            float v = 0.0f + src->value * 1.0f;
+            v = 0.0f + v * 1.0f;
+            v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+            *out = kcp_new_const(ctx, w, h, v);
+            return KC_OK;
+        }
+    }
+    KC_TRY(kcp_force(ctx, &src, 1));
+    kc_plane* dst = nullptr;
+    KC_TRY(kcp_new_device(ctx, w, h, &dst));
+    int32_t rc = kck_resize_plane(ctx, src->dptr, src->w, src->h, dst->dptr, w, h, filter);
+    if (rc != KC_OK) {
+        kcp_release(dst);
+        return rc;
+    }
+    ctx->run_bytes += (uint64_t)src->bytes() + dst->bytes();
+    *out = dst;
+    return KC_OK;
+}
+
+int32_t img_resize(kc_context* ctx, const Img& in, uint32_t w, uint32_t h, int filter, Img& out) {
+    if (in.w() == w && in.h() == h) {
+        out = in;
+        return KC_OK;
+    }
+    Img res;
+    res.im.kind = in.im.kind;
+    for (int c = 0; c < kci_nplanes(&in.im); ++c) {
+        // planes shared between channels (Gray -> Rgba aliasing) are resized once
+        int same = -1;
+        for (int d = 0; d < c; ++d)
+            if (in.im.planes[d] == in.im.planes[c]) same = d;
+        if (same >= 0) {
+            res.alias(c, res.im.planes[same]);
+            continue;
+        }
+        kc_plane* p = nullptr;
+        KC_TRY(plane_resize(ctx, in.im.planes[c], w, h, filter, &p));
+        res.set(c, p);
+    }
+    out = std::move(res);
+    return KC_OK;
+}
+
+struct Size2 { uint32_t w, h; };
+inline uint32_t pixel_count(Size2 s) { return s.w * s.h; }  // u32 multiply, slot_data.rs:27-29
+
+// calculate_size, src/shared.rs:61-139.  `edges` sorted by input slot.
+Size2 calculate_size(const std::vector<Slot>& sd, const std::vector<kc_edge>& edges, int policy, uint32_t pslot,
+                     uint32_t pw, uint32_t ph) {
+    auto sz = [](const Slot& s) { return Size2{s.image.w(), s.image.h()}; };
+    switch (policy) {
+        case KC_POLICY_MOST_PIXELS: {
+            if (sd.empty()) return Size2{1, 1};
+            size_t best = 0;  // max_by keeps the last maximum
+            for (size_t i = 1; i < sd.size(); ++i)
+                if (pixel_count(sz(sd[i])) >= pixel_count(sz(sd[best]))) best = i;
+            return sz(sd[best]);
+        }
+        case KC_POLICY_LEAST_PIXELS: {
+            size_t best = 0;  // min_by keeps the first minimum
+            for (size_t i = 1; i < sd.size(); ++i)
+                if (pixel_count(sz(sd[i])) < pixel_count(sz(sd[best]))) best = i;
+            return sz(sd[best]);
+        }
+        case KC_POLICY_LARGEST_AXES: {
+            Size2 s{0, 0};
+            for (const Slot& d : sd) { s.w = std::max(s.w, d.image.w()); s.h = std::max(s.h, d.image.h()); }
+            return s;
+        }
+        case KC_POLICY_SMALLEST_AXES: {
+            Size2 s{UINT32_MAX, UINT32_MAX};
+            for (const Slot& d : sd) { s.w = std::min(s.w, d.image.w()); s.h = std::min(s.h, d.image.h()); }
+            return s;
+        }
+        case KC_POLICY_SPECIFIC_SLOT: {
+            const kc_edge* e = nullptr;
+            for (const kc_edge& c : edges)
+                if (c.input_slot == pslot) { e = &c; break; }
+            if (!e && !edges.empty()) e = &edges.front();
+            if (!e) return Size2{1, 1};
+            for (const Slot& d : sd)
+                if (d.slot_id == e->output_slot && d.node_id == e->output_id) return sz(d);
+            return Size2{1, 1};
+        }
+        default: return Size2{pw, ph};
+    }
+}
+
+const Slot* with_slot(const std::vector<Slot>& v, uint32_t slot) {  // process_shared.rs:22-30
+    for (const Slot& s : v)
+        if (s.slot_id == slot) return &s;
+    return nullptr;
+}
+
+struct ImagePixels {
+    uint32_t w = 0, h = 0, ch = 0;
+    std::vector<uint8_t> px;
+    Img uploaded;       // device copy, made on first use
+    bool have_upload = false;
+};
+using ImageStore = std::map<std::string, ImagePixels>;
+
+int32_t eval_nested(kc_context* ctx, const KcNode& node, const std::vector<Slot>& sd, ImageStore* images, std::vector<Slot>& out);
+
+// process_node + process_node_internal, src/node/node_type.rs:98-138,213-267.
+// `input_data[i]` is the slot data feeding `node_edges[i]` (graph edge order).
+int32_t process_node(kc_context* ctx, const KcNode& node, const std::vector<Slot>& input_data,
+                     const std::vector<kc_edge>& node_edges, const std::vector<kc_embedded_slot_data>& embedded,
+                     const std::vector<Slot>& input_slot_datas, ImageStore* images, std::vector<Slot>& out) {
+    if (input_data.size() != node_edges.size()) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "one slot data per edge is required");
+    std::vector<kc_edge> edges = node_edges;
+    std::stable_sort(edges.begin(), edges.end(), [](const kc_edge& a, const kc_edge& b) { return a.input_slot < b.input_slot; });
+
+    // resize_buffers, src/shared.rs:141-216
+    std::vector<Slot> rs;
+    if (!input_data.empty()) {
+        Size2 size = calculate_size(input_data, edges, node.policy, node.policy_slot, node.policy_w, node.policy_h);
+        for (const Slot& d : input_data) {
+            Slot r;
+            r.node_id = d.node_id;
+            r.slot_id = d.slot_id;
+            KC_TRY(img_resize(ctx, d.image, size.w, size.h, node.filter, r.image));
+            rs.push_back(std::move(r));
+        }
+    }
+    // assign_slot_ids, :250-267
+    std::vector<Slot> sd;
+    for (const kc_edge& e : edges) {
+        const Slot* f = nullptr;
+        for (const Slot& d : rs)
+            if (e.output_slot == d.slot_id && e.output_id == d.node_id) { f = &d; break; }
+        if (!f) KC_FAIL(KC_ERR_GENERIC, "edge %u:%u -> %u:%u has no slot data", e.output_id, e.output_slot, e.input_id, e.input_slot);
+        Slot s;
+        s.node_id = e.input_id;
+        s.slot_id = e.input_slot;
+        s.image = f->image;
+        sd.push_back(std::move(s));
+    }
+
+    out.clear();
+    auto push = [&](uint32_t slot, Img im) {
+        Slot s;
+        s.node_id = node.node_id;
+        s.slot_id = slot;
+        s.image = std::move(im);
+        out.push_back(std::move(s));
+    };
+    switch (node.type) {
+        case KC_NODE_INPUT_RGBA:  // src/node/input_rgba.rs:7-13 (takes the first input unconditionally)
+            if (input_slot_datas.empty()) KC_FAIL(KC_ERR_GENERIC, "InputRgba without input slot data");
+            push(0, input_slot_datas[0].image);
+            break;
+        case KC_NODE_INPUT_GRAY:  // src/node/input_gray.rs:7-16
+            for (const Slot& d : input_slot_datas)
+                if (d.node_id == node.node_id) {
+                    Slot s = d;  // cloned as is, slot id included
+                    out.push_back(std::move(s));
+                    break;
+                }
+            break;
+        case KC_NODE_OUTPUT_RGBA:
+        case KC_NODE_OUTPUT_GRAY:  // src/node/output.rs:12-33
+            if (!sd.empty()) {
+                push(0, sd[0].image);
+            } else if (node.type == KC_NODE_OUTPUT_RGBA) {
+                Img im;
+                im.im.kind = KC_IMAGE_RGBA;
+                for (int c = 0; c < 3; ++c) im.set(c, kcp_new_const(ctx, 1, 1, 0.0f));
+                im.set(3, kcp_new_const(ctx, 1, 1, 1.0f));
+                push(0, std::move(im));
+            } else {
+                push(0, img_pixel(ctx, 0.0f));
+            }
+            break;
+        case KC_NODE_GRAPH:  // src/node/graph.rs:14-51
+            KC_TRY(eval_nested(ctx, node, sd, images, out));
+            break;
+        case KC_NODE_IMAGE: {  // src/node/image.rs:10-26
+            ImagePixels* px = nullptr;
+            if (images) {
+                auto it = images->find(node.name);
+                if (it != images->end()) px = &it->second;
+            }
+            if (!px) {  // unreadable file => 1x1 magenta
+                Img im;
+                im.im.kind = KC_IMAGE_RGBA;
+                im.set(0, kcp_new_const(ctx, 1, 1, 1.0f));
+                im.set(1, kcp_new_const(ctx, 1, 1, 0.0f));
+                im.set(2, kcp_new_const(ctx, 1, 1, 1.0f));
+                im.set(3, kcp_new_const(ctx, 1, 1, 1.0f));
+                push(0, std::move(im));
+            } else {
+                if (!px->have_upload) {
+                    kc_image raw;
+                    KC_TRY(kc_image_from_u8(ctx, px->px.data(), px->w, px->h, px->ch, &raw));
+                    px->uploaded = Img(raw);
+                    kci_release(&raw);
+                    px->have_upload = true;
+                }
+                push(0, px->uploaded);
+            }
+            break;
+        }
+        case KC_NODE_EMBED: {  // src/node/embed.rs:33-50
+            const kc_embedded_slot_data* f = nullptr;
+            for (const kc_embedded_slot_data& e : embedded)
+                if (e.slot_data_id == node.embed_id) { f = &e; break; }
+            if (!f) KC_FAIL(KC_ERR_NODE_PROCESSING, "no embedded slot data with id %u", node.embed_id);
+            push(0, Img(f->image));
+            break;
+        }
+        case KC_NODE_WRITE:  // src/node/write.rs:5-21: file output belongs to the host application
+            break;
+        case KC_NODE_VALUE:  // src/node/value.rs:14-26
+            push(0, img_pixel(ctx, node.value));
+            break;
+        case KC_NODE_MIX: {  // src/node/mix.rs:51-134
+            const Slot* l = with_slot(sd, 0);
+            const Slot* r = with_slot(sd, 1);
+            Img res;
+            KC_TRY(img_mix(ctx, node.mix_type, l ? &l->image : nullptr, r ? &r->image : nullptr, res));
+            push(0, std::move(res));
+            break;
+        }
+        case KC_NODE_HEIGHT_TO_NORMAL: {  // src/node/height_to_normal.rs:16-77
+            const Slot* in = with_slot(sd, 0);
+            if (!in || in->image.rgba()) break;  // Ok(Vec::new()) => InvalidBufferCount below
+            Img res;
+            KC_TRY(img_h2n(ctx, in->image, res));
+            push(0, std::move(res));
+            break;
+        }
+        case KC_NODE_SEPARATE_RGBA: {  // src/node/separate_rgba.rs:38-69
+            if (!sd.empty() && sd[0].image.rgba()) {
+                for (int c = 0; c < 4; ++c) {
+                    Img im;
+                    im.alias(0, sd[0].image.im.planes[c]);
+                    push((uint32_t)c, std::move(im));
+                }
+            } else {
+                for (int c = 0; c < 4; ++c) push((uint32_t)c, img_pixel(ctx, 0.0f));
+            }
+            break;
+        }
+        case KC_NODE_COMBINE_RGBA: {  // src/node/combine_rgba.rs:14-97
+            uint32_t w = 1, h = 1;
+            if (!sd.empty()) { w = sd[0].image.w(); h = sd[0].image.h(); }
+            Img res;
+            res.im.kind = KC_IMAGE_RGBA;
+            kc_plane* zero = nullptr;
+            for (int c = 0; c < 4; ++c) {
+                const Slot* s = with_slot(sd, (uint32_t)c);
+                if (s) {
+                    if (s->image.rgba()) {
+                        if (zero) kcp_release(zero);
+                        KC_FAIL(KC_ERR_GENERIC, "It shouldn't be possible to connect an RGBA image into this slot");
+                    }
+                    res.alias(c, s->image.im.planes[0]);
+                } else if (c == 3) {
+                    res.set(c, kcp_new_const(ctx, w, h, 1.0f));
+                } else {
+                    if (!zero) zero = kcp_new_const(ctx, w, h, 0.0f);
+                    res.alias(c, zero);
+                }
+            }
+            if (zero) kcp_release(zero);
+            push(0, std::move(res));
+            break;
+        }
+        default: KC_FAIL(KC_ERR_INVALID_NODE_TYPE, "unknown node type %d", node.type);
+    }
+    // output count check, node_type.rs:124-137
+    if (!kcg_is_output(node.type) && out.size() != kcg_output_slots(node).size()) {
+        out.clear();
+        KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "the number of output buffers does not match the number of output slots");
+    }
+    return KC_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// LiveGraph
+// ---------------------------------------------------------------------------
+struct kc_live_graph {
+    kc_context* ctx = nullptr;
+    kc_graph graph;
+    std::vector<Slot> slot_datas;
+    std::vector<Slot> inputs;
+    std::vector<kc_embedded_slot_data> embeds;  // images own references
+    ImageStore own_images;
+    ImageStore* images = &own_images;
+    std::map<uint32_t, int> state;
+    bool use_cache = false, auto_update = false;
+    uint64_t last_kernels = 0, last_groups = 0, last_bytes = 0;
+
+    ~kc_live_graph() {
+        for (auto& e : embeds) kci_release(&e.image);
+    }
+
+    void remove_nodes_data(uint32_t id) {  // live_graph.rs:352-359
+        slot_datas.erase(std::remove_if(slot_datas.begin(), slot_datas.end(), [&](const Slot& s) { return s.node_id == id; }),
+                         slot_datas.end());
+    }
+    const Slot* find_slot(uint32_t node, uint32_t slot) const {
+        for (const Slot& s : slot_datas)
+            if (s.node_id == node && s.slot_id == slot) return &s;
+        return nullptr;
+    }
+    bool has_data(uint32_t node) const {
+        for (const Slot& s : slot_datas)
+            if (s.node_id == node) return true;
+        return false;
+    }
+    std::vector<uint32_t> children(uint32_t id) const {
+        std::vector<uint32_t> c;
+        for (const kc_edge& e : graph.edges)
+            if (e.output_id == id) c.push_back(e.input_id);
+        std::sort(c.begin(), c.end());
+        c.erase(std::unique(c.begin(), c.end()), c.end());
+        return c;
+    }
+    std::vector<uint32_t> parents(uint32_t id) const {
+        std::vector<uint32_t> c;
+        for (const kc_edge& e : graph.edges)
+            if (e.input_id == id) c.push_back(e.output_id);
+        std::sort(c.begin(), c.end());
+        c.erase(std::unique(c.begin(), c.end()), c.end());
+        return c;
+    }
+    // set_state(Dirty) with propagation to all children, live_graph.rs:515-537
+    void set_dirty(uint32_t id) {
+        std::vector<uint32_t> work{id};
+        std::set<uint32_t> seen;
+        while (!work.empty()) {
+            uint32_t n = work.back();
+            work.pop_back();
+            if (!seen.insert(n).second) continue;
+            auto it = state.find(n);
+            if (it == state.end()) continue;
+            it->second = KC_STATE_DIRTY;
+            remove_nodes_data(n);
+            for (uint32_t c : children(n)) work.push_back(c);
+        }
+    }
+    void reset_states() {
+        state.clear();
+        for (const KcNode& n : graph.nodes) state[n.node_id] = KC_STATE_DIRTY;
+    }
+
+    int32_t evaluate(const uint32_t* ids, size_t n_ids, bool materialise);
+};
+
+int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool materialise) {
+    KcGuard guard(ctx);
+    ctx->cancel.store(false);
+    const uint64_t k0 = ctx->run_kernels, g0 = ctx->run_groups, b0 = ctx->run_bytes;
+    std::set<uint32_t> requested(ids, ids + n_ids);
+    for (uint32_t id : requested)
+        if (!kcg_find(graph, id)) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", id);
+
+    // 1. which nodes must run: requested nodes and their ancestors that are not
+    //    Clean, or Clean but whose data has been freed (engine.rs:253-262)
+    std::set<uint32_t> todo;
+    {
+        std::vector<uint32_t> work(requested.begin(), requested.end());
+        while (!work.empty()) {
+            uint32_t id = work.back();
+            work.pop_back();
+            if (todo.count(id)) continue;
+            if (state[id] == KC_STATE_CLEAN && has_data(id)) continue;
+            todo.insert(id);
+            for (uint32_t p : parents(id)) work.push_back(p);
+        }
+    }
+    for (uint32_t id : todo)
+        if (state[id] == KC_STATE_CLEAN) state[id] = KC_STATE_DIRTY;
+    for (uint32_t id : requested)
+        if (state[id] != KC_STATE_CLEAN) state[id] = KC_STATE_REQUESTED;
+
+    // 2. run them in dependency order (ties: position in the node vector)
+    size_t remaining = todo.size();
+    int32_t rc = KC_OK;
+    while (remaining > 0 && rc == KC_OK) {
+        bool progressed = false;
+        for (const KcNode& node : graph.nodes) {
+            if (!todo.count(node.node_id) || state[node.node_id] == KC_STATE_CLEAN) continue;
+            bool ready = true;
+            for (const kc_edge& e : graph.edges)
+                if (e.input_id == node.node_id && kcg_find(graph, e.output_id) && state[e.output_id] != KC_STATE_CLEAN) ready = false;
+            if (!ready) continue;
+            if (ctx->cancel.load()) { rc = KC_ERR_CANCELED; kc_set_error("evaluation canceled"); break; }
+            state[node.node_id] = KC_STATE_PROCESSING;
+            // gather the inputs in graph-edge order, engine.rs:217-262
+            std::vector<kc_edge> ne;
+            std::vector<Slot> in;
+            for (const kc_edge& e : graph.edges) {
+                if (e.input_id != node.node_id) continue;
+                const Slot* f = find_slot(e.output_id, e.output_slot);
+                if (!f) { rc = KC_ERR_NO_SLOT_DATA; kc_set_error("node %u has no data in slot %u", e.output_id, e.output_slot); break; }
+                ne.push_back(e);
+                in.push_back(*f);
+            }
+            if (rc != KC_OK) break;
+            std::vector<Slot> out;
+            rc = process_node(ctx, node, in, ne, embeds, inputs, images, out);
+            if (rc != KC_OK) break;
+            in.clear();
+            remove_nodes_data(node.node_id);
+            for (Slot& s : out) slot_datas.push_back(std::move(s));
+            state[node.node_id] = KC_STATE_CLEAN;
+            // free the parents' data once every child of theirs has run, engine.rs:58-75
+            // (nodes the caller asked for keep theirs)
+            if (!use_cache) {
+                for (uint32_t p : parents(node.node_id)) {
+                    if (requested.count(p)) continue;
+                    bool all = true;
+                    for (uint32_t c : children(p))
+                        if (state[c] != KC_STATE_CLEAN && state[c] != KC_STATE_PROCESSING) all = false;
+                    if (all) remove_nodes_data(p);
+                }
+            }
+            --remaining;
+            progressed = true;
+        }
+        if (rc == KC_OK && !progressed) {
+            rc = KC_ERR_NODE_DIRTY;
+            kc_set_error("the graph has a cycle; %zu nodes can never become clean", remaining);
+        }
+    }
+    if (rc != KC_OK) {
+        for (uint32_t id : todo)
+            if (state[id] != KC_STATE_CLEAN) { state[id] = KC_STATE_DIRTY; remove_nodes_data(id); }
+        return rc;
+    }
+    // 3. the requested nodes' planes become real pixels, in as few kernels as possible
+    if (materialise) {
+        std::vector<kc_plane*> roots;
+        for (const Slot& s : slot_datas)
+            if (requested.count(s.node_id) || use_cache)
+                for (int c = 0; c < kci_nplanes(&s.image.im); ++c) {
+                    kc_plane* p = s.image.im.planes[c];
+                    if (p->kind != KC_PLANE_DEVICE && std::find(roots.begin(), roots.end(), p) == roots.end()) roots.push_back(p);
+                }
+        if (!roots.empty()) KC_TRY(kcp_force(ctx, roots.data(), roots.size()));
+    }
+    last_kernels = ctx->run_kernels - k0;
+    last_groups = ctx->run_groups - g0;
+    last_bytes = ctx->run_bytes - b0;
+    return KC_OK;
+}
+
+namespace {
+
+// graph::process, src/node/graph.rs:14-51: the nested graph is evaluated in
+// place.  Because per-pixel nodes are lazy, this inlines it into the parent's
+// expression DAG: a nested graph costs no kernels of its own.
+int32_t eval_nested(kc_context* ctx, const KcNode& node, const std::vector<Slot>& sd, ImageStore* images, std::vector<Slot>& out) {
+    if (!node.graph) KC_FAIL(KC_ERR_INVALID_NODE_TYPE, "Graph node without a NodeGraph");
+    kc_live_graph inner;
+    inner.ctx = ctx;
+    inner.graph = *node.graph;
+    inner.reset_states();
+    inner.images = images;
+    for (const Slot& d : sd) {  // outer input SlotId == inner Input node's NodeId, :25-31
+        Slot s;
+        s.node_id = d.slot_id;
+        s.slot_id = 0;
+        s.image = d.image;
+        inner.inputs.push_back(std::move(s));
+    }
+    std::vector<uint32_t> outs;
+    for (const KcNode& m : inner.graph.nodes)
+        if (kcg_is_output(m.type)) outs.push_back(m.node_id);
+    KC_TRY(inner.evaluate(outs.data(), outs.size(), false));
+    for (uint32_t oid : outs)
+        for (const Slot& d : inner.slot_datas)
+            if (d.node_id == oid) {
+                Slot s;
+                s.node_id = node.node_id;
+                s.slot_id = oid;  // :40-46
+                s.image = d.image;
+                out.push_back(std::move(s));
+            }
+    return KC_OK;
+}
+
+Img borrow(const kc_image* im) { return im ? Img(*im) : Img(); }
+
+int32_t check_image(const kc_image* im, const char* what) {
+    if (!im) return KC_OK;
+    const int np = im->kind == KC_IMAGE_RGBA ? 4 : 1;
+    for (int c = 0; c < np; ++c)
+        if (!im->planes[c]) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "%s: plane %d is NULL", what, c);
+    return KC_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI: per-node operators
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int32_t kc_image_as_type(kc_context* ctx, const kc_image* in, int32_t rgba, kc_image* out) {
+    if (!ctx || !in || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(in, "as_type"));
+    KcGuard g(ctx);
+    Img res;
+    KC_TRY(img_as_type(ctx, borrow(in), rgba != 0, res));
+    *out = res.release();
+    return KC_OK;
+}
+
+int32_t kc_mix(kc_context* ctx, int32_t mix_type, const kc_image* left, const kc_image* right, kc_image* out) {
+    if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(left, "mix left"));
+    KC_TRY(check_image(right, "mix right"));
+    KcGuard g(ctx);
+    Img l = borrow(left), r = borrow(right), res;
+    KC_TRY(img_mix(ctx, mix_type, left ? &l : nullptr, right ? &r : nullptr, res));
+    *out = res.release();
+    return KC_OK;
+}
+
+int32_t kc_height_to_normal(kc_context* ctx, const kc_image* in, kc_image* out) {
+    if (!ctx || !in || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(in, "height_to_normal"));
+    KcGuard g(ctx);
+    Img res;
+    KC_TRY(img_h2n(ctx, borrow(in), res));
+    *out = res.release();
+    return KC_OK;
+}
+
+int32_t kc_resize(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, int32_t filter, kc_image* out) {
+    if (!ctx || !in || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(in, "resize"));
+    KcGuard g(ctx);
+    Img res;
+    KC_TRY(img_resize(ctx, borrow(in), w, h, filter, res));
+    *out = res.release();
+    return KC_OK;
+}
+
+int32_t kc_separate_rgba(kc_context* ctx, const kc_image* in, kc_image out[4]) {
+    if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(in, "separate_rgba"));
+    KcGuard g(ctx);
+    for (int c = 0; c < 4; ++c) {
+        Img im;
+        if (in && in->kind == KC_IMAGE_RGBA) im.alias(0, in->planes[c]);
+        else im = img_pixel(ctx, 0.0f);
+        out[c] = im.release();
+    }
+    return KC_OK;
+}
+
+int32_t kc_combine_rgba(kc_context* ctx, const kc_image* const channels[4], kc_image* out) {
+    if (!ctx || !channels || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    KcNode node;
+    node.type = KC_NODE_COMBINE_RGBA;
+    std::vector<Slot> in;
+    std::vector<kc_edge> edges;
+    for (uint32_t c = 0; c < 4; ++c) {
+        if (!channels[c]) continue;
+        KC_TRY(check_image(channels[c], "combine_rgba"));
+        Slot s;
+        s.node_id = 1 + c;
+        s.slot_id = 0;
+        s.image = borrow(channels[c]);
+        in.push_back(std::move(s));
+        edges.push_back(kc_edge{1 + c, 0, 0, c});
+    }
+    // combine is only defined on equally sized inputs; process_node resizes first
+    std::vector<Slot> res;
+    std::vector<kc_embedded_slot_data> none;
+    std::vector<Slot> no_inputs;
+    KC_TRY(process_node(ctx, node, in, edges, none, no_inputs, nullptr, res));
+    *out = res[0].image.release();
+    return KC_OK;
+}
+
+int32_t kc_calculate_size(const kc_slot_data* slot_datas, size_t n_slot_datas, const kc_edge* edges, size_t n_edges,
+                          int32_t policy, uint32_t policy_slot, uint32_t policy_w, uint32_t policy_h, uint32_t* out_w,
+                          uint32_t* out_h) {
+    if (!out_w || !out_h || (n_slot_datas && !slot_datas) || (n_edges && !edges)) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    std::vector<Slot> sd;
+    for (size_t i = 0; i < n_slot_datas; ++i) {
+        KC_TRY(check_image(&slot_datas[i].image, "calculate_size"));
+        Slot s;
+        s.node_id = slot_datas[i].node_id;
+        s.slot_id = slot_datas[i].slot_id;
+        s.image = Img(slot_datas[i].image);
+        sd.push_back(std::move(s));
+    }
+    std::vector<kc_edge> es(edges, edges + n_edges);
+    std::stable_sort(es.begin(), es.end(), [](const kc_edge& a, const kc_edge& b) { return a.input_slot < b.input_slot; });
+    if ((policy == KC_POLICY_LEAST_PIXELS) && sd.empty()) KC_FAIL(KC_ERR_GENERIC, "LeastPixels needs at least one input");
+    Size2 s = calculate_size(sd, es, policy, policy_slot, policy_w, policy_h);
+    *out_w = s.w;
+    *out_h = s.h;
+    return KC_OK;
+}
+
+int32_t kc_process_node(kc_context* ctx, const kc_node_desc* node, const kc_slot_data* slot_datas, size_t n_slot_datas,
+                        const kc_embedded_slot_data* embedded, size_t n_embedded, const kc_slot_data* input_slot_datas,
+                        size_t n_input_slot_datas, const kc_edge* edges, size_t n_edges, kc_slot_data* out, size_t out_cap,
+                        size_t* n_out) {
+    if (!ctx || !node || !n_out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (n_slot_datas != n_edges) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "edges.len() != slot_datas.len()");  // assert_eq!, node_type.rs:221-226
+    KcGuard g(ctx);
+    KcNode k;
+    kcg_from_desc(*node, k);
+    auto conv = [](const kc_slot_data* v, size_t n, std::vector<Slot>& o) -> int32_t {
+        for (size_t i = 0; i < n; ++i) {
+            KC_TRY(check_image(&v[i].image, "process_node"));
+            Slot s;
+            s.node_id = v[i].node_id;
+            s.slot_id = v[i].slot_id;
+            s.image = Img(v[i].image);
+            o.push_back(std::move(s));
+        }
+        return KC_OK;
+    };
+    std::vector<Slot> in, inputs, res;
+    KC_TRY(conv(slot_datas, n_slot_datas, in));
+    KC_TRY(conv(input_slot_datas, n_input_slot_datas, inputs));
+    std::vector<kc_embedded_slot_data> emb(embedded, embedded + n_embedded);
+    std::vector<kc_edge> es(edges, edges + n_edges);
+    KC_TRY(process_node(ctx, k, in, es, emb, inputs, nullptr, res));
+    *n_out = res.size();
+    if (res.size() > out_cap) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "output capacity %zu < %zu results", out_cap, res.size());
+    for (size_t i = 0; i < res.size(); ++i) {
+        out[i].node_id = res[i].node_id;
+        out[i].slot_id = res[i].slot_id;
+        out[i].image = res[i].image.release();
+    }
+    return KC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI: LiveGraph
+// ---------------------------------------------------------------------------
+int32_t kc_live_graph_create(kc_context* ctx, kc_live_graph** out) {
+    if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    auto* lg = new kc_live_graph();
+    lg->ctx = ctx;
+    *out = lg;
+    return KC_OK;
+}
+int32_t kc_live_graph_destroy(kc_live_graph* lg) {
+    if (!lg) return KC_OK;
+    {
+        KcGuard g(lg->ctx);
+        lg->slot_datas.clear();
+        lg->inputs.clear();
+        lg->own_images.clear();
+        for (auto& e : lg->embeds) kci_release(&e.image);
+        lg->embeds.clear();
+    }
+    delete lg;
+    return KC_OK;
+}
+int32_t kc_live_graph_set_node_graph(kc_live_graph* lg, const kc_graph* g) {
+    if (!lg || !g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard guard(lg->ctx);
+    lg->graph = *g;
+    lg->reset_states();
+    lg->slot_datas.clear();
+    return KC_OK;
+}
+int32_t kc_live_graph_node_graph(const kc_live_graph* lg, const kc_graph** out) {
+    if (!lg || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = &lg->graph;
+    return KC_OK;
+}
+int32_t kc_live_graph_set_use_cache(kc_live_graph* lg, int32_t v) {
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    lg->use_cache = v != 0;
+    return KC_OK;
+}
+int32_t kc_live_graph_set_auto_update(kc_live_graph* lg, int32_t v) {
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    lg->auto_update = v != 0;
+    return KC_OK;
+}
+int32_t kc_live_graph_add_node(kc_live_graph* lg, const kc_node_desc* node, uint32_t* out_node_id) {
+    if (!lg || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    uint32_t id = 0;
+    KC_TRY(kc_graph_add_node(&lg->graph, node, &id));
+    lg->state[id] = KC_STATE_DIRTY;  // add_node_internal, live_graph.rs:445-449
+    if (out_node_id) *out_node_id = id;
+    return KC_OK;
+}
+int32_t kc_live_graph_add_node_with_id(kc_live_graph* lg, const kc_node_desc* node) {
+    if (!lg || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(kc_graph_add_node_with_id(&lg->graph, node));
+    lg->state[node->node_id] = KC_STATE_DIRTY;
+    return KC_OK;
+}
+int32_t kc_live_graph_remove_node(kc_live_graph* lg, uint32_t node_id) {
+    // LiveGraph::remove_node, live_graph.rs:451-475
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard guard(lg->ctx);
+    std::vector<kc_edge> removed;
+    std::vector<uint32_t> kids = lg->children(node_id);
+    KC_TRY(kcg_remove_node(lg->graph, node_id, &removed));
+    lg->remove_nodes_data(node_id);
+    lg->state.erase(node_id);
+    for (uint32_t c : kids) lg->set_dirty(c);
+    return KC_OK;
+}
+int32_t kc_live_graph_connect(kc_live_graph* lg, uint32_t o, uint32_t i, uint32_t os, uint32_t is) {
+    // LiveGraph::connect, live_graph.rs:487-511
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard guard(lg->ctx);
+    KC_TRY(kcg_connect(lg->graph, o, i, os, is));
+    lg->set_dirty(i);
+    return KC_OK;
+}
+int32_t kc_live_graph_disconnect_slot(kc_live_graph* lg, uint32_t node_id, int32_t side, uint32_t slot_id) {
+    // LiveGraph::disconnect_slot, live_graph.rs:577-603
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard guard(lg->ctx);
+    std::vector<kc_edge> removed;
+    KC_TRY(kcg_disconnect_slot(lg->graph, node_id, side, slot_id, &removed));
+    for (const kc_edge& e : removed) lg->set_dirty(e.input_id);
+    return KC_OK;
+}
+int32_t kc_live_graph_set_node(kc_live_graph* lg, const kc_node_desc* node) {
+    // node_mut / set_node_with_id, live_graph.rs:369-387: the node and its children become dirty
+    if (!lg || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard guard(lg->ctx);
+    KC_TRY(kc_graph_set_node(&lg->graph, node));
+    lg->set_dirty(node->node_id);
+    return KC_OK;
+}
+int32_t kc_live_graph_add_input_slot_data(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, const kc_image* image) {
+    if (!lg || !image) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(image, "add_input_slot_data"));
+    KcGuard guard(lg->ctx);
+    Slot s;
+    s.node_id = node_id;
+    s.slot_id = slot_id;
+    s.image = Img(*image);
+    lg->inputs.push_back(std::move(s));
+    for (const KcNode& n : lg->graph.nodes)
+        if (kcg_is_input(n.type)) lg->set_dirty(n.node_id);
+    return KC_OK;
+}
+int32_t kc_live_graph_clear_input_slot_data(kc_live_graph* lg) {
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard guard(lg->ctx);
+    lg->inputs.clear();
+    for (const KcNode& n : lg->graph.nodes)
+        if (kcg_is_input(n.type)) lg->set_dirty(n.node_id);
+    return KC_OK;
+}
+int32_t kc_live_graph_embed_slot_data_with_id(kc_live_graph* lg, const kc_image* image, uint32_t slot_id, uint32_t embed_id) {
+    // embed_slot_data_with_id, live_graph.rs:324-341
+    if (!lg || !image) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(image, "embed_slot_data_with_id"));
+    for (const auto& e : lg->embeds)
+        if (e.slot_data_id == embed_id) KC_FAIL(KC_ERR_INVALID_SLOT_ID, "embedded slot data id %u already in use", embed_id);
+    kc_embedded_slot_data e;
+    e.slot_data_id = embed_id;
+    e.slot_id = slot_id;
+    e.image = *image;
+    kci_retain(&e.image);
+    lg->embeds.push_back(e);
+    return KC_OK;
+}
+int32_t kc_live_graph_replace_embedded(kc_live_graph* lg, const kc_image* image, uint32_t embed_id) {
+    if (!lg || !image) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(image, "replace_embedded"));
+    KcGuard guard(lg->ctx);
+    for (auto& e : lg->embeds)
+        if (e.slot_data_id == embed_id) {
+            kci_retain(image);
+            kci_release(&e.image);
+            e.image = *image;
+            for (const KcNode& n : lg->graph.nodes)
+                if (n.type == KC_NODE_EMBED && n.embed_id == embed_id) lg->set_dirty(n.node_id);
+            return KC_OK;
+        }
+    KC_FAIL(KC_ERR_INVALID_SLOT_ID, "no embedded slot data with id %u", embed_id);
+}
+int32_t kc_live_graph_set_image_data_u8(kc_live_graph* lg, uint32_t node_id, const uint8_t* samples, uint32_t w, uint32_t h,
+                                        uint32_t channels) {
+    if (!lg || !samples) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (channels < 1 || channels > 4) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "channels must be 1..4");
+    KcGuard guard(lg->ctx);
+    const KcNode* n = kcg_find(lg->graph, node_id);
+    if (!n || n->type != KC_NODE_IMAGE) KC_FAIL(KC_ERR_INVALID_NODE_ID, "node %u is not an Image node", node_id);
+    ImagePixels& px = (*lg->images)[n->name];
+    px.w = w;
+    px.h = h;
+    px.ch = channels;
+    px.px.assign(samples, samples + (size_t)w * h * channels);
+    px.uploaded = Img();
+    px.have_upload = false;
+    lg->set_dirty(node_id);
+    return KC_OK;
+}
+int32_t kc_live_graph_request(kc_live_graph* lg, const uint32_t* node_ids, size_t n) {
+    if (!lg || (n && !node_ids)) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    return lg->evaluate(node_ids, n, true);
+}
+int32_t kc_live_graph_await_clean(kc_live_graph* lg, uint32_t node_id) {
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(lg->evaluate(&node_id, 1, true));
+    return kc_context_synchronize(lg->ctx);
+}
+int32_t kc_live_graph_cancel(kc_live_graph* lg) {
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    lg->ctx->cancel.store(true);
+    return KC_OK;
+}
+int32_t kc_live_graph_node_state(const kc_live_graph* lg, uint32_t node_id, int32_t* state) {
+    if (!lg || !state) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    auto it = lg->state.find(node_id);
+    if (it == lg->state.end()) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
+    *state = it->second;
+    return KC_OK;
+}
+int32_t kc_live_graph_slot_data(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, kc_image* out) {
+    if (!lg || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    const Slot* s = lg->find_slot(node_id, slot_id);
+    if (!s) KC_FAIL(KC_ERR_NO_SLOT_DATA, "Could not find a `SlotData` for node %u slot %u", node_id, slot_id);
+    *out = s->image.im;
+    kci_retain(out);
+    return KC_OK;
+}
+int32_t kc_live_graph_slot_data_size(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint32_t* w, uint32_t* h) {
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    const Slot* s = lg->find_slot(node_id, slot_id);
+    if (!s) KC_FAIL(KC_ERR_NO_SLOT_DATA, "Could not find a `SlotData` for node %u slot %u", node_id, slot_id);
+    if (w) *w = s->image.w();
+    if (h) *h = s->image.h();
+    return KC_OK;
+}
+int32_t kc_live_graph_node_slot_ids(const kc_live_graph* lg, uint32_t node_id, uint32_t* slot_ids, size_t cap, size_t* n) {
+    if (!lg || !n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    size_t c = 0;
+    for (const Slot& s : lg->slot_datas)
+        if (s.node_id == node_id) {
+            if (slot_ids && c < cap) slot_ids[c] = s.slot_id;
+            ++c;
+        }
+    *n = c;
+    return KC_OK;
+}
+static int32_t buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int srgb, uint8_t* host, size_t cap) {
+    if (!lg || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    const Slot* s = lg->find_slot(node_id, slot_id);
+    if (!s) KC_FAIL(KC_ERR_NO_SLOT_DATA, "Could not find a `SlotData` for node %u slot %u", node_id, slot_id);
+    size_t need = (size_t)s->image.w() * s->image.h() * 4;
+    if (cap < need) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "buffer of %zu bytes is too small for %zu", cap, need);
+    return kc_image_to_u8(lg->ctx, &s->image.im, srgb, host);
+}
+int32_t kc_live_graph_buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host, size_t cap) {
+    return buffer_rgba(lg, node_id, slot_id, 0, host, cap);
+}
+int32_t kc_live_graph_buffer_srgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host, size_t cap) {
+    return buffer_rgba(lg, node_id, slot_id, 1, host, cap);
+}
+int32_t kc_live_graph_read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap) {
+    if (!lg || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    const uint64_t k0 = lg->ctx->run_kernels, g0 = lg->ctx->run_groups, b0 = lg->ctx->run_bytes;
+    KC_TRY(lg->evaluate(&node_id, 1, false));  // planes stay lazy: the export kernel computes them
+    int32_t rc = buffer_rgba(lg, node_id, slot_id, srgb, host, cap);
+    lg->last_kernels = lg->ctx->run_kernels - k0;
+    lg->last_groups = lg->ctx->run_groups - g0;
+    lg->last_bytes = lg->ctx->run_bytes - b0;
+    return rc;
+}
+int32_t kc_live_graph_last_run_stats(const kc_live_graph* lg, uint64_t* kernels, uint64_t* fused_groups, uint64_t* algorithmic_bytes) {
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (kernels) *kernels = lg->last_kernels;
+    if (fused_groups) *fused_groups = lg->last_groups;
+    if (algorithmic_bytes) *algorithmic_bytes = lg->last_bytes;
+    return KC_OK;
+}
+
+}  // extern "C"

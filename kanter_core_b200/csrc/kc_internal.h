@@ -1,0 +1,194 @@
+// kc_internal.h — internal types shared by the host code and the CUDA kernels
+// of libkanter_b200.so.  Nothing here is part of the ABI (include/kanter_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/kanter_b200.h"
+
+// ---- error plumbing --------------------------------------------------------
+void kc_set_error(const char* fmt, ...);
+#define KC_FAIL(code, ...)        \
+    do {                          \
+        kc_set_error(__VA_ARGS__); \
+        return (code);            \
+    } while (0)
+#define KC_CUDA(expr)                                                                  \
+    do {                                                                               \
+        cudaError_t e__ = (expr);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            kc_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, \
+                         __LINE__, cudaGetErrorString(e__));                           \
+            return KC_ERR_CUDA;                                                        \
+        }                                                                              \
+    } while (0)
+#define KC_TRY(expr)              \
+    do {                          \
+        int32_t rc__ = (expr);    \
+        if (rc__ != KC_OK) return rc__; \
+    } while (0)
+
+// ---- the fused elementwise kernel's op tape ---------------------------------
+// An accumulator machine interpreted once per float4 of pixels, everything in
+// registers: S[k] are the float4s loaded from the kernel's source planes, T[j]
+// temporaries, `acc` the accumulator.  One instruction = op | (arg << 8).
+// arg addresses an operand: 0..7 = S[arg], 8..13 = T[arg-8], 14 = immediate.
+constexpr int KC_MAX_SRC = 8;
+constexpr int KC_MAX_TMP = 6;
+constexpr int KC_MAX_OUT = 6;
+constexpr int KC_MAX_TAPE = 72;
+constexpr int KC_ARG_TMP0 = 8;
+constexpr int KC_ARG_IMM = 14;
+
+enum KcTapeOp : uint32_t {
+    TOP_LD = 0,      // acc = X
+    TOP_ADD,         // acc = acc + X
+    TOP_SUB,         // acc = acc - X
+    TOP_RSUB,        // acc = X - acc
+    TOP_MUL,         // acc = acc * X
+    TOP_DIV,         // acc = acc / X
+    TOP_RDIV,        // acc = X / acc
+    TOP_POW,         // acc = pow(acc, X)
+    TOP_RPOW,        // acc = pow(X, acc)
+    TOP_ST_TMP,      // T[arg] = acc
+    TOP_ST_OUT,      // out[arg][i] = acc
+    TOP_PACK_RGBA,   // rgba8[i] = to_u8(T0,T1,T2,acc)   (arg = 1: sRGB transfer on T0..T2)
+    TOP_PACK_GRAY,   // rgba8[i] = (to_u8(acc) x3, 255)  (arg = 1: sRGB)
+};
+
+struct KcTapeArgs {
+    const float* src[KC_MAX_SRC];
+    float* out[KC_MAX_OUT];
+    uint32_t* out_rgba8;
+    unsigned long long n;  // pixels per plane
+    uint32_t n_src;
+    uint32_t n_instr;
+    uint32_t instr[KC_MAX_TAPE];
+    float imm[KC_MAX_TAPE];
+};
+
+// ---- resize weight tables (host-built, device-resident) ---------------------
+struct KcAxisTable {
+    uint32_t src_len = 0, dst_len = 0, max_taps = 0;
+    int filter = 0;
+    // device arrays: left[dst_len], count[dst_len], weights[max_taps][dst_len] (tap-major)
+    uint32_t* d_left = nullptr;
+    uint32_t* d_count = nullptr;
+    float* d_weights = nullptr;
+    std::vector<uint32_t> h_left, h_count;
+    std::vector<float> h_weights;  // [dst_len][max_taps] on the host
+};
+
+// ---- planes -------------------------------------------------------------------
+enum KcPlaneKind { KC_PLANE_DEVICE = 0, KC_PLANE_CONST = 1, KC_PLANE_EXPR = 2 };
+
+struct kc_plane {
+    std::atomic<int> refs{1};
+    kc_context* ctx = nullptr;
+    uint32_t w = 0, h = 0;
+    int kind = KC_PLANE_DEVICE;
+    // DEVICE
+    float* dptr = nullptr;
+    bool owned = true;
+    // CONST
+    float value = 0.0f;
+    // EXPR: a lazily evaluated  a (op) b ; operands are retained
+    int op = 0;
+    kc_plane* a = nullptr;
+    kc_plane* b = nullptr;
+    // scratch for the fusion planner
+    int mark = 0;          // visit stamp of the last cone collection
+    int uses_in_cone = 0;  // operand references from inside that cone
+    int ktag = 0;          // stamp of the kernel plan this node is computed in
+    int tmp_slot = -1;     // temporary register currently holding the value
+    int out_slot = -1;     // output slot when the node is a kernel output
+    int remaining = 0;     // in-kernel uses not yet emitted
+    int need = 0;          // size of the in-kernel sub-expression
+    bool is_out = false;
+    bool computed = false;
+
+    size_t count() const { return (size_t)w * h; }
+    size_t bytes() const { return count() * sizeof(float); }
+};
+
+struct kc_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    kc_options opts{};
+    std::recursive_mutex mu;
+    uint64_t kernel_launches = 0;
+    uint64_t bytes_live = 0;
+    // per-request accounting (reset by the live graph)
+    uint64_t run_kernels = 0, run_groups = 0, run_bytes = 0;
+    std::map<std::tuple<uint32_t, uint32_t, int>, std::shared_ptr<KcAxisTable>> axis_tables;
+    std::atomic<bool> cancel{false};
+};
+
+// RAII device selection + context lock
+struct KcGuard {
+    kc_context* ctx;
+    int prev = -1;
+    explicit KcGuard(kc_context* c) : ctx(c) {
+        ctx->mu.lock();
+        cudaGetDevice(&prev);
+        if (prev != ctx->device) cudaSetDevice(ctx->device);
+    }
+    ~KcGuard() {
+        if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
+        ctx->mu.unlock();
+    }
+};
+
+// ---- plane helpers (kc_context.cu) -------------------------------------------
+int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out);
+kc_plane* kcp_new_const(kc_context* ctx, uint32_t w, uint32_t h, float v);
+kc_plane* kcp_new_expr(kc_context* ctx, int op, kc_plane* a, kc_plane* b);  // retains a, b
+void kcp_retain(kc_plane* p);
+void kcp_release(kc_plane* p);
+// make every plane in `roots` device-resident, fusing the lazy expressions
+// feeding them into as few kernels as possible (kc_fusion.cu)
+int32_t kcp_force(kc_context* ctx, kc_plane* const* roots, size_t n);
+// RGBA8 export of an image, fusing the conversion into the producing kernel
+int32_t kcp_export_rgba8(kc_context* ctx, const kc_image* img, int srgb, uint32_t* d_out);
+
+inline void kci_clear(kc_image* im) {
+    im->kind = KC_IMAGE_GRAY;
+    im->width = im->height = 0;
+    for (int c = 0; c < 4; ++c) im->planes[c] = nullptr;
+}
+inline int kci_nplanes(const kc_image* im) { return im->kind == KC_IMAGE_RGBA ? 4 : 1; }
+void kci_retain(const kc_image* im);
+void kci_release(kc_image* im);
+
+// ---- kernel launchers (defined in the .cu files) -----------------------------
+int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args);
+int32_t kck_fill(kc_context* ctx, float* dst, size_t n, float v);
+int32_t kck_from_u8(kc_context* ctx, const uint8_t* d_samples, uint32_t channels, size_t n,
+                    float* const planes[4]);
+int32_t kck_height_to_normal(kc_context* ctx, const float* hgt, uint32_t w, uint32_t h, float* r,
+                             float* g, float* b);
+int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst,
+                         uint32_t dw, uint32_t dh, int filter);
+// host-side weight table exactly as image 0.24.0 computes it (kc_resize.cu)
+void kc_resize_axis_host(uint32_t src_len, uint32_t dst_len, int filter, std::vector<uint32_t>& left,
+                         std::vector<uint32_t>& count, std::vector<float>& weights, uint32_t& max_taps);
+
+// host evaluation of one mix op (constant folding; glibc powf == the reference's)
+float kc_host_mix(int op, float l, float r);
+
+// ---- per-node semantics shared by kc_process_node and the live graph ---------
+struct KcSlotData {
+    uint32_t node_id = 0, slot_id = 0;
+    kc_image image{};
+};

@@ -1,0 +1,69 @@
+"""Pins the CPU oracle: every golden check of the reference's test-suite
+(tests/integration_tests.rs) must reproduce BYTE-EXACTLY, plus
+the known-answer values the reference asserts directly.  CPU only."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import graphs
+
+
+@pytest.mark.parametrize("name", sorted(graphs.GOLDEN_CASES))
+def test_oracle_reproduces_reference_golden(name):
+    case = graphs.GOLDEN_CASES[name]()
+    og = graphs.run_oracle(case)
+    got = og.buffer_rgba(int(case.node), 0)
+    want = case.expected()
+    assert got.shape == want.shape == (case.size[1], case.size[0], 4)
+    assert np.array_equal(got, want), "%d bytes differ" % int((got != want).sum())
+
+
+@pytest.mark.parametrize("name,policy,p1,p2,size", graphs.RESIZE_POLICY_CASES, ids=[c[0] for c in graphs.RESIZE_POLICY_CASES])
+def test_oracle_resize_policy_sizes(name, policy, p1, p2, size):
+    # tests/integration_tests.rs:894-949
+    case = graphs.resize_policy_case(policy, p1, p2)
+    og = graphs.run_oracle(case)
+    planes = og.slot(int(case.node), 0)
+    assert planes[0].shape == (size[1], size[0])
+
+
+def test_oracle_read_dirty_read_known_answer():
+    # Value(0.5) -> Combine.red reads back [127, 0, 0, 255]; tests/integration_tests.rs:1388-1437
+    from kanter_core_b200 import Node, NodeGraph, NodeType, SlotId
+    g = NodeGraph.new()
+    v = g.add_node(Node.new(NodeType.Value(0.5)))
+    c = g.add_node(Node.new(NodeType.CombineRgba))
+    g.connect(v, c, SlotId(0), SlotId(0))
+    og = graphs.run_oracle(graphs.Case(g, c))
+    assert og.buffer_rgba(int(c), 0).reshape(-1).tolist() == [127, 0, 0, 255]
+
+
+def test_oracle_special_value_census():
+    # divide_node_gray has 51 868 NaN and 6 231 +inf pixels, all exported as 255
+    case = graphs.mix_node_gray(graphs.MixType.Divide, "divide_node_gray.png")
+    og = graphs.run_oracle(case)
+    p = og.slot(int(case.node), 0)[0]
+    assert int(np.isnan(p).sum()) == 51868
+    assert int(np.isposinf(p).sum()) == 6231
+    rgba = og.buffer_rgba(int(case.node), 0)
+    assert (rgba[np.isnan(p)][:, :3] == 255).all()
+
+
+def test_oracle_u8_roundtrip_is_identity():
+    # u8/255 -> f32 -> clamp*255 trunc round-trips every u8 value (input_output, embedded_node_data)
+    a = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(4, axis=2)
+    planes = oracle.deconstruct_u8(a)
+    assert np.array_equal(oracle.to_u8(planes), a)
+    gray = oracle.deconstruct_u8(a[:, :, :1])
+    assert np.array_equal(gray[1], np.zeros((16, 16), np.float32)) and np.array_equal(gray[3], np.ones((16, 16), np.float32))
+
+
+def test_oracle_resize_weights_triangle_upsample():
+    # Triangle 110 -> 128 (the filter irregular_sizes.png pins): windows of <= 3 taps that sum to 1
+    left, count, w = oracle.resize_weights(110, 128, 1)
+    assert count.max() <= 3 and count.min() >= 1
+    assert np.allclose(w.sum(axis=1), 1.0, atol=1e-6)
+    # 1x1 -> N is a single tap of weight exactly 1.0 for every filter (value_node.png pins Triangle)
+    for f in range(5):
+        l, c, ww = oracle.resize_weights(1, 256, f)
+        assert (c == 1).all() and (ww[:, 0] == 1.0).all() and (l == 0).all()
