@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- graph-evaluation throughput of the B200 backend (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--math fast|exact] [--impl ours|reference]
+
+A step = one evaluation of BASELINE.json configs[1]: Pow(Multiply(A, B), B) on two
+synthetic 4096x4096 RGBA f32 images -> OutputRgba, i.e. one pass of the per-pixel hot
+path (process_node + Mix kernels, src/node/node_type.rs:213, src/node/mix.rs:51) over one
+batch of input.  `value` is measured with the inputs resident in HBM; `e2e` goes through
+the public API from pinned host buffers to RGBA8 bytes on the host every step.
+
+N > 1: one process per GPU (torchrun); every rank evaluates its own graph on its own
+inputs (independent texture graphs, SURVEY.md section 8e: no data-path collective); the
+only communication is the barrier and the max-over-ranks of the device time.
+
+--impl reference times the CPU restatement of the reference engine (oracle/, the Rust
+crate cannot be built here) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SIZE = 4096
+MPIX = SIZE * SIZE / 1e6
+METRIC = "graph_eval_mpixel_per_s"
+UNIT = "Mpixel/s"
+WORKLOAD = "configs[1]: Pow(Multiply(A,B),B), two synthetic %dx%d RGBA f32 images -> OutputRgba" % (SIZE, SIZE)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def make_inputs(seed):
+    r = np.random.default_rng(seed)
+    return [r.random((SIZE, SIZE), dtype=np.float32) for _ in range(4)]
+
+
+# ---------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle's engine on the host cores
+# ---------------------------------------------------------------------------
+def oracle_graph(A, B):
+    import oracle
+    g = oracle.Graph()
+    g.embed(0, A)
+    g.embed(1, B)
+    g.add_node(1, 6, embed_id=0)          # Embed A
+    g.add_node(2, 6, embed_id=1)          # Embed B
+    g.add_node(3, 9, mix_type=2)          # Mix Multiply
+    g.add_node(4, 9, mix_type=4)          # Mix Pow
+    g.add_node(5, 3, name="out")          # OutputRgba
+    g.add_edge(1, 3, 0, 0)
+    g.add_edge(2, 3, 0, 1)
+    g.add_edge(3, 4, 0, 0)
+    g.add_edge(2, 4, 0, 1)
+    g.add_edge(4, 5, 0, 0)
+    return g
+
+
+def cpu_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def run_cpu(steps, warmup):
+    """Copies of the graph evaluated concurrently, one thread per ready node (the
+    reference engine's only parallelism, src/engine.rs:288, src/process_pack.rs:27);
+    every node's pixel loop is single-threaded as in the reference."""
+    A, B = make_inputs(1), make_inputs(2)
+    g = oracle_graph(A, B)
+    threads = min(cpu_threads(), 16)     # 0.5 GiB of intermediates per in-flight copy
+    copies = threads
+    for _ in range(warmup):
+        g.eval_batch_seconds(1, 1)
+    total = 0.0
+    for _ in range(steps):
+        total += g.eval_batch_seconds(copies, threads)
+    value = copies * steps * MPIX / total
+    return value, total / steps * 1e3, threads, "%d steps x %d concurrent copies of the full %dx%d graph, one thread per copy" % (steps, copies, SIZE, SIZE)
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = 1 if args.warmup > 0 else 0
+    value, ms, threads, sample = run_cpu(steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "engine": "CPU restatement of the reference engine (oracle/): Rust toolchain absent, crate not buildable here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.path = "/tmp/kc_clocks_%d_%d.csv" % (os.getpid(), device)
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                p = [x.strip() for x in ln.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for i, nm in enumerate(names):
+                    if p[5 + i].lower().startswith("active"):
+                        reasons.add(nm)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(max(mx))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def ours(args, rank, world, local_rank):
+    import ctypes as C
+
+    import kanter_core_b200 as kc
+    from kanter_core_b200 import MixType, Node, NodeType, SlotId
+    from kanter_core_b200._lib import call
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    math_mode = kc.MATH_FAST if args.math == "fast" else kc.MATH_EXACT
+    tp = kc.TextureProcessor.new(device=local_rank, math_mode=math_mode)
+    ctx = tp._ctx._h
+
+    # pinned host copies of the inputs (rank-specific seeds: independent graphs)
+    hostA = [kc.pinned_empty((SIZE, SIZE)) for _ in range(4)]
+    hostB = [kc.pinned_empty((SIZE, SIZE)) for _ in range(4)]
+    for dst, src in zip(hostA, make_inputs(1 + 2 * rank)):
+        dst[...] = src
+    for dst, src in zip(hostB, make_inputs(2 + 2 * rank)):
+        dst[...] = src
+    host_out = kc.pinned_empty((SIZE, SIZE, 4), np.uint8)
+
+    imgA = kc.SlotImage.from_planes(tp, hostA)
+    imgB = kc.SlotImage.from_planes(tp, hostB)
+
+    lg = tp.new_live_graph()
+    lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, imgA), 0)
+    lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, imgB), 1)
+    a = lg.add_node(Node.new(NodeType.Embed(0)))
+    b = lg.add_node(Node.new(NodeType.Embed(1)))
+    mul = lg.add_node(Node.new(NodeType.Mix(MixType.Multiply)))
+    pw = lg.add_node(Node.new(NodeType.Mix(MixType.Pow)))
+    out = lg.add_node(Node.new(NodeType.OutputRgba("out")))
+    lg.connect(a, mul, SlotId(0), SlotId(0))
+    lg.connect(b, mul, SlotId(0), SlotId(1))
+    lg.connect(mul, pw, SlotId(0), SlotId(0))
+    lg.connect(b, pw, SlotId(0), SlotId(1))
+    lg.connect(pw, out, SlotId(0), SlotId(0))
+
+    def step_resident():
+        # new inputs arrive (same planes, already in HBM): everything downstream is dirty again
+        lg.replace_embedded(imgA, 0)
+        lg.replace_embedded(imgB, 1)
+        lg.request(out)
+
+    # ---- device-resident throughput --------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    tp.synchronize()
+    stats = lg.last_run_stats()
+
+    ev0, ev1 = C.c_void_p(), C.c_void_p()
+    call("kc_event_create", C.byref(ev0))
+    call("kc_event_create", C.byref(ev1))
+    k0 = tp.stats()["kernel_launches"]
+    call("kc_context_set_timing", ctx, 1)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    tp.synchronize()
+    call("kc_event_record", ctx, ev0)
+    for _ in range(args.steps):
+        step_resident()
+    call("kc_event_record", ctx, ev1)
+    tp.synchronize()
+    barrier()
+    ms = C.c_float()
+    call("kc_event_elapsed_ms", ev0, ev1, C.byref(ms))
+    clocks = sampler.stop()
+    kms, kn = C.c_double(), C.c_uint64()
+    call("kc_context_timing_read", ctx, 0, C.byref(kms), C.byref(kn))   # the fused tape kernel
+    call("kc_context_set_timing", ctx, 0)
+    launches = tp.stats()["kernel_launches"] - k0
+    total_ms = max_over_ranks(float(ms.value))
+    value = world * args.steps * MPIX / (total_ms / 1e3)
+
+    # ---- parity spot check of what was just timed (rank 0, cheap sample) -------------------
+    parity = None
+    if rank == 0:
+        import oracle
+        got = lg.slot_data(out, SlotId(0)).image.planes()
+        rows = slice(0, 64)
+        for c in range(3):
+            want = oracle.mix_plane(4, oracle.mix_plane(2, hostA[c][rows], hostB[c][rows]), hostB[c][rows]).astype(np.float64)
+            g = got[c][rows].astype(np.float64)
+            assert (np.abs(g - want) <= 1e-6 + 1e-5 * np.abs(want)).all(), "bench output differs from the oracle"
+        assert np.array_equal(got[3][rows], np.ones((64, SIZE), np.float32))
+        parity = "checked vs CPU oracle on 64 rows x 3 channels: within 1e-5 rel / 1e-6 abs" + (" (bit-exact mode)" if args.math == "exact" else "")
+
+    # ---- end to end through the public API: pinned host f32 planes -> RGBA8 bytes on host ----
+    def step_e2e():
+        ia = kc.SlotImage.from_planes(tp, hostA, sync=False)
+        ib = kc.SlotImage.from_planes(tp, hostB, sync=False)
+        lg.replace_embedded(ia, 0)
+        lg.replace_embedded(ib, 1)
+        lg.read_rgba(out, SlotId(0), kc.Size(SIZE, SIZE), out=host_out)   # synchronises
+
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    tp.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    tp.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * e2e_steps * MPIX / e2e_s
+    h2d = 8 * SIZE * SIZE * 4
+    d2h = SIZE * SIZE * 4
+
+    peak, peak_src = peaks()
+    alg_bytes = stats["algorithmic_bytes"] / max(1, stats["kernels"]) if stats["kernels"] else 0
+    avg_kernel_ms = kms.value / max(1, kn.value)
+    achieved = alg_bytes / (avg_kernel_ms / 1e3) / 1e9 if avg_kernel_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("tape_kernel_%s" % args.math, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "graphs_per_step_per_gpu": 1, "math_mode": args.math,
+                       "parallelism": "independent graphs per GPU, no collective" if world > 1 else "single GPU",
+                       "l2": "inputs (512 MiB) + outputs (256 MiB) per step exceed the 126 MB L2; no flush needed",
+                       "parity": parity},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "path": "pinned host f32 planes -> kc_image_from_host_planes -> fused mul/pow/to_u8 kernel -> RGBA8 on host (read_rgba)"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "kc_tape_kernel<%s>" % ("EXACT" if args.math == "exact" else "FAST"),
+                         "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms,
+                         "launches_timed": int(kn.value), "peak_source": peak_src,
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+        }
+        if world == 1 and not args.no_cpu:
+            v, _ms, threads, sample = run_cpu(1, 0)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        print(json.dumps(line), flush=True)
+
+    for arr in hostA + hostB + [host_out]:
+        kc.free_pinned(arr)
+    tp.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under it, as the driver would
+        port = 29500 + os.getpid() % 1000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -170,6 +170,12 @@ int32_t kc_context_set_fuse(kc_context* ctx, int32_t fuse);
  * src/transient_buffer.rs:413-420) */
 int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_launches, uint64_t* bytes_live);
 
+/* per-launch device timing: while on, every kernel the library launches on the
+ * context is bracketed by CUDA events on the context's stream.  kind: 0 fused
+ * elementwise tape, 1 fill, 2 u8->f32, 3 HeightToNormal, 4 resize vertical,
+ * 5 resize horizontal, -1 all.  Reading waits for the stream and resets the sum. */
+int32_t kc_context_set_timing(kc_context* ctx, int32_t on);
+int32_t kc_context_timing_read(kc_context* ctx, int32_t kind, double* total_ms, uint64_t* launches);
 /* CUDA events on the context's stream, for device-side timing */
 int32_t kc_event_create(void** out_event);
 int32_t kc_event_destroy(void* event);

@@ -8,5 +8,5 @@ from ._lib import MATH_EXACT, MATH_FAST, TexProError, lib  # noqa: F401
 from .api import (  # noqa: F401
     Edge, EmbeddedSlotDataId, LiveGraph, MixType, Node, NodeGraph, NodeId, NodeState, NodeType,
     ResizeFilter, ResizePolicy, Side, Size, Slot, SlotData, SlotId, SlotImage, SlotType,
-    TextureProcessor, graph_to_dict,
+    TextureProcessor, free_pinned, graph_to_dict, pinned_empty,
 )

@@ -81,6 +81,8 @@ SIGNATURES = {
     "kc_context_set_math_mode": (i32, [vp, i32]),
     "kc_context_set_fuse": (i32, [vp, i32]),
     "kc_context_stats": (i32, [vp, P(u64), P(u64)]),
+    "kc_context_set_timing": (i32, [vp, i32]),
+    "kc_context_timing_read": (i32, [vp, i32, P(C.c_double), P(u64)]),
     "kc_event_create": (i32, [P(vp)]),
     "kc_event_destroy": (i32, [vp]),
     "kc_event_record": (i32, [vp, vp]),
@@ -184,7 +186,7 @@ class TexProError(Exception):
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
-            "kanter_core_b200: %s is missing. Build it with `python -m kanter_core_b200.build` "
+            "kanter_core_b200: %s is missing. Build it with `python kanter_core_b200/build.py` "
             "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():

@@ -474,8 +474,10 @@ class SlotImage:
         return SlotImage(tex_pro._ctx, im)
 
     @staticmethod
-    def from_planes(tex_pro, planes):
-        """planes: one (Gray) or four (Rgba) float32 arrays of shape (h, w)."""
+    def from_planes(tex_pro, planes, sync=True):
+        """planes: one (Gray) or four (Rgba) float32 arrays of shape (h, w).  With
+        sync=False the copies are only enqueued: the arrays (pinned, see
+        pinned_empty) must stay alive and unchanged until the stream has passed them."""
         arrs = [np.ascontiguousarray(p, dtype=np.float32) for p in planes]
         if len(arrs) not in (1, 4):
             raise TexProError(4, "need 1 or 4 planes")
@@ -483,7 +485,8 @@ class SlotImage:
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         im = kc_image()
         call("kc_image_from_host_planes", tex_pro._ctx._h, 1 if len(arrs) == 4 else 0, w, h, ptrs, C.byref(im))
-        call("kc_context_synchronize", tex_pro._ctx._h)  # the host arrays may go away after this returns
+        if sync:
+            call("kc_context_synchronize", tex_pro._ctx._h)  # the host arrays may go away after this returns
         return SlotImage(tex_pro._ctx, im)
 
     @staticmethod
@@ -650,6 +653,7 @@ class LiveGraph(_GraphView):
         self._use_cache = False
         self._auto_update = False
         self._images_loaded = {}
+        self._scan_images = False   # set when the graph may have gained an Image node
 
     def close(self):
         if getattr(self, "_h", None) and self._ctx._h:
@@ -680,16 +684,19 @@ class LiveGraph(_GraphView):
     def set_node_graph(self, node_graph):
         call("kc_live_graph_set_node_graph", self._h, node_graph._h)
         self._images_loaded = {}
+        self._scan_images = True
 
     def add_node(self, node):
         d, keep = node._desc()
         out = C.c_uint32()
         call("kc_live_graph_add_node", self._h, C.byref(d), C.byref(out))
+        self._scan_images |= node.node_type.kind == _lib.NODE_IMAGE
         return NodeId(out.value)
 
     def add_node_with_id(self, node):
         d, keep = node._desc()
         call("kc_live_graph_add_node_with_id", self._h, C.byref(d))
+        self._scan_images |= node.node_type.kind == _lib.NODE_IMAGE
 
     def remove_node(self, node_id):
         call("kc_live_graph_remove_node", self._h, int(node_id))
@@ -704,6 +711,7 @@ class LiveGraph(_GraphView):
     def set_node(self, node):
         d, keep = node._desc()
         call("kc_live_graph_set_node", self._h, C.byref(d))
+        self._scan_images |= node.node_type.kind == _lib.NODE_IMAGE
 
     def add_input_slot_data(self, slot_data):  # :347-350
         call("kc_live_graph_add_input_slot_data", self._h, int(slot_data.node_id), int(slot_data.slot_id), C.byref(slot_data.image._im))
@@ -717,6 +725,9 @@ class LiveGraph(_GraphView):
 
     def _load_images(self):
         # the Image node's codec runs on the host side of the boundary
+        if not self._scan_images:
+            return
+        self._scan_images = False
         for n in self.nodes:
             if n.node_type.kind == _lib.NODE_IMAGE and self._images_loaded.get(int(n.node_id)) != n.node_type.payload:
                 try:
@@ -799,6 +810,27 @@ class LiveGraph(_GraphView):
         k, g, b = C.c_uint64(), C.c_uint64(), C.c_uint64()
         call("kc_live_graph_last_run_stats", self._h, C.byref(k), C.byref(g), C.byref(b))
         return {"kernels": k.value, "fused_groups": g.value, "algorithmic_bytes": b.value}
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """A numpy array over page-locked host memory (kc_host_alloc), for asynchronous
+    uploads/downloads.  The memory lives until free_pinned(array)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    call("kc_host_alloc", max(n, 1), C.byref(p))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    _PINNED[a.ctypes.data] = p
+    return a
+
+
+def free_pinned(a):
+    p = _PINNED.pop(a.ctypes.data, None)
+    if p is not None:
+        _lib.lib.kc_host_free(p)
+
+
+_PINNED = {}
 
 
 def graph_to_dict(graph_view):

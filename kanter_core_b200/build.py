@@ -1,6 +1,6 @@
 """Builds libkanter_b200.so in-tree with nvcc for sm_100a.
 
-Usage: python -m kanter_core_b200.build [--force]
+Usage: python kanter_core_b200/build.py [--force]   (run as a script: importing the package needs the built library)
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
 """
 import os

@@ -126,6 +126,8 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) {
         cudaStreamSynchronize(ctx->stream);
         for (auto& kv : ctx->axis_tables) axis_table_free(*kv.second);
         ctx->axis_tables.clear();
+        for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
+        for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -506,5 +508,36 @@ extern "C" int32_t kc_event_elapsed_ms(void* start, void* stop, float* ms) {
     if (!start || !stop || !ms) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
     KC_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
+    return KC_OK;
+}
+
+// per-launch kernel timing: every kernel this library launches on the context is
+// bracketed by two events on the context's stream while timing is on
+extern "C" int32_t kc_context_set_timing(kc_context* ctx, int32_t on) {
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    KcGuard g(ctx);
+    ctx->timing = on != 0;
+    return KC_OK;
+}
+extern "C" int32_t kc_context_timing_read(kc_context* ctx, int32_t kind, double* total_ms, uint64_t* launches) {
+    // waits for the stream, sums the launches of `kind` (-1: all kinds) recorded so far and forgets them
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    KcGuard g(ctx);
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0;
+    uint64_t n = 0;
+    std::vector<kc_context::TimedLaunch> keep;
+    for (auto& t : ctx->timed) {
+        if (kind >= 0 && t.kind != kind) { keep.push_back(t); continue; }
+        float ms = 0.0f;
+        KC_CUDA(cudaEventElapsedTime(&ms, t.start, t.stop));
+        sum += ms;
+        ++n;
+        ctx->event_pool.push_back(t.start);
+        ctx->event_pool.push_back(t.stop);
+    }
+    ctx->timed.swap(keep);
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = n;
     return KC_OK;
 }

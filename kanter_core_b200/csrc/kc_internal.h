@@ -133,6 +133,34 @@ struct kc_context {
     uint64_t run_kernels = 0, run_groups = 0, run_bytes = 0;
     std::map<std::tuple<uint32_t, uint32_t, int>, std::shared_ptr<KcAxisTable>> axis_tables;
     std::atomic<bool> cancel{false};
+    // optional per-launch device timing (kc_context_set_timing)
+    bool timing = false;
+    struct TimedLaunch { int kind; cudaEvent_t start, stop; };
+    std::vector<TimedLaunch> timed;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+// kernel kinds for kc_context_timing_read
+enum { KC_KERNEL_TAPE = 0, KC_KERNEL_FILL, KC_KERNEL_FROM_U8, KC_KERNEL_H2N, KC_KERNEL_RESIZE_V, KC_KERNEL_RESIZE_H, KC_KERNEL_KINDS };
+
+// brackets one kernel launch with CUDA events on the context's stream when timing is on
+struct KcTimed {
+    kc_context* ctx;
+    cudaEvent_t stop = nullptr;
+    KcTimed(kc_context* c, int kind) : ctx(c) {
+        if (!ctx->timing) return;
+        cudaEvent_t ev[2];
+        for (int i = 0; i < 2; ++i) {
+            if (!ctx->event_pool.empty()) { ev[i] = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+            else cudaEventCreate(&ev[i]);
+        }
+        cudaEventRecord(ev[0], ctx->stream);
+        stop = ev[1];
+        ctx->timed.push_back({kind, ev[0], ev[1]});
+    }
+    ~KcTimed() {
+        if (stop) cudaEventRecord(stop, ctx->stream);
+    }
 };
 
 // RAII device selection + context lock

@@ -269,6 +269,7 @@ int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     const int block = 256;
     // persistent-style grid: a whole number of CTAs per SM, grid-stride loop inside
     const int grid = grid_for(ctx, (size_t)((args.n + 3) >> 2), block, 8);
+    KcTimed timed(ctx, KC_KERNEL_TAPE);
     if (ctx->opts.math_mode == KC_MATH_EXACT)
         kc_tape_kernel<true><<<grid, block, 0, ctx->stream>>>(args);
     else
@@ -282,6 +283,7 @@ int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
 int32_t kck_fill(kc_context* ctx, float* dst, size_t n, float v) {
     if (n == 0) return KC_OK;
     const int grid = grid_for(ctx, (n + 3) >> 2, 256, 8);
+    KcTimed timed(ctx, KC_KERNEL_FILL);
     kc_fill_kernel<<<grid, 256, 0, ctx->stream>>>(dst, n, v);
     KC_CUDA(cudaGetLastError());
     ctx->kernel_launches++;
@@ -293,6 +295,7 @@ int32_t kck_from_u8(kc_context* ctx, const uint8_t* d_samples, uint32_t channels
                     float* const planes[4]) {
     if (n == 0) return KC_OK;
     const int grid = grid_for(ctx, (n + 3) >> 2, 256, 8);
+    KcTimed timed(ctx, KC_KERNEL_FROM_U8);
     switch (channels) {
         case 1: kc_from_u8_kernel<1><<<grid, 256, 0, ctx->stream>>>(d_samples, n, planes[0], planes[1], planes[2], planes[3]); break;
         case 2: kc_from_u8_kernel<2><<<grid, 256, 0, ctx->stream>>>(d_samples, n, planes[0], planes[1], planes[2], planes[3]); break;

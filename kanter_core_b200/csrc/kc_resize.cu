@@ -186,11 +186,13 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
     const bool exact = ctx->opts.math_mode == KC_MATH_EXACT;
     {
         dim3 grid((sw + 255) / 256, std::min<uint32_t>(dh, 65535u));
+        KcTimed timed(ctx, KC_KERNEL_RESIZE_V);
         if (exact) kc_resize_v_kernel<true><<<grid, 256, 0, ctx->stream>>>(src, sw, tmp, dh, tv->d_left, tv->d_count, tv->d_weights);
         else kc_resize_v_kernel<false><<<grid, 256, 0, ctx->stream>>>(src, sw, tmp, dh, tv->d_left, tv->d_count, tv->d_weights);
     }
     {
         dim3 grid((dw + 255) / 256, std::min<uint32_t>(dh, 65535u));
+        KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
         if (exact) kc_resize_h_kernel<true><<<grid, 256, 0, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights);
         else kc_resize_h_kernel<false><<<grid, 256, 0, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights);
     }

@@ -1,0 +1,263 @@
+"""GPU kernels against the CPU oracle on seeded random inputs: every Mix op, the
+Rgba->Gray average, export, HeightToNormal and all five resize filters, at
+ragged sizes, in EXACT (bit-exact) and FAST (1e-5 rel / 1e-6 abs) modes."""
+import numpy as np
+import pytest
+
+import kanter_core_b200 as kc
+import oracle
+from kanter_core_b200 import MixType, Node, NodeType, ResizeFilter, ResizePolicy, Size, SlotId
+
+pytestmark = pytest.mark.gpu
+
+REL, ABS = 1e-5, 1e-6  # BASELINE.json north_star tolerance for f32 arithmetic
+
+
+def rnd(seed, h, w, lo=0.0, hi=1.0):
+    r = np.random.default_rng(seed)
+    return (r.random((h, w), dtype=np.float32) * np.float32(hi - lo) + np.float32(lo)).astype(np.float32)
+
+
+def bits_equal(a, b):
+    a, b = np.asarray(a, np.float32), np.asarray(b, np.float32)
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and np.array_equal(na, nb) and np.array_equal(a[~na].view(np.uint32), b[~nb].view(np.uint32))
+
+
+def close(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    na, nb = np.isnan(a), np.isnan(b)
+    if not np.array_equal(na, nb):
+        return False
+    fin = np.isfinite(a) & np.isfinite(b)
+    if not np.array_equal(a[~fin & ~na], b[~fin & ~nb]):
+        return False
+    return bool((np.abs(a[fin] - b[fin]) <= ABS + REL * np.abs(b[fin])).all())
+
+
+def mix_graph(tp, op, left, right):
+    """Mix through the live graph with embedded inputs; returns the result image."""
+    lg = tp.new_live_graph()
+    m = lg.add_node(Node.new(NodeType.Mix(op)))
+    for slot, planes in enumerate((left, right)):
+        if planes is None:
+            continue
+        img = kc.SlotImage.from_planes(tp, planes)
+        lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, img), slot)
+        e = lg.add_node(Node.new(NodeType.Embed(slot)))
+        lg.connect(e, m, SlotId(0), SlotId(slot))
+    kc.LiveGraph.await_clean_read(lg, m)
+    return lg.slot_data(m, SlotId(0)).image
+
+
+SHAPES = [(1, 1), (3, 5), (17, 33), (64, 64), (255, 257)]
+
+
+@pytest.mark.parametrize("op", list(MixType))
+@pytest.mark.parametrize("shape", SHAPES)
+def test_mix_gray_exact(tex_pro, op, shape):
+    h, w = shape
+    l, r = rnd(1, h, w, -1.0, 2.0), rnd(2, h, w, -0.5, 1.5)
+    l.flat[0] = 0.0; r.flat[0] = 0.0  # 0/0, 0^0
+    got = mix_graph(tex_pro, op, [l], [r]).planes()[0]
+    assert bits_equal(got, oracle.mix_plane(int(op), l, r))
+
+
+@pytest.mark.parametrize("op", list(MixType))
+def test_mix_rgba_exact_and_alpha_is_one(tex_pro, op):
+    h, w = 37, 41
+    L = [rnd(10 + c, h, w) for c in range(4)]
+    R = [rnd(20 + c, h, w) for c in range(4)]
+    img = mix_graph(tex_pro, op, L, R)
+    got = img.planes()
+    for c in range(3):
+        assert bits_equal(got[c], oracle.mix_plane(int(op), L[c], R[c]))
+    assert np.array_equal(got[3], np.ones((h, w), np.float32))  # mix.rs:203-212
+    assert img.plane_is_constant(3)[0] is False  # a requested node hands back real planes
+
+
+@pytest.mark.parametrize("op", list(MixType))
+def test_mix_fast_within_tolerance(tex_pro_fast, op):
+    h, w = 128, 96
+    l, r = rnd(3, h, w, 0.0, 1.0), rnd(4, h, w, 0.0, 1.0)
+    l[0, :8] = [0.0, 1.0, 0.5, 2.0, 1e-20, 1e20, -1.0, 0.25]
+    r[0, :8] = [0.0, 5.0, 0.0, 0.5, 0.5, 0.5, 2.0, -3.0]
+    got = mix_graph(tex_pro_fast, op, [l], [r]).planes()[0]
+    assert close(got, oracle.mix_plane(int(op), l, r))
+
+
+def test_mix_type_coercion(tex_pro):
+    # right is converted to left's type (mix.rs:62): Rgba->Gray is ((r+g)+b)/3, Gray->Rgba aliases
+    h, w = 19, 23
+    G = [rnd(5, h, w)]
+    C = [rnd(30 + c, h, w) for c in range(4)]
+    got = mix_graph(tex_pro, MixType.Add, G, C).planes()
+    assert len(got) == 1
+    assert bits_equal(got[0], oracle.mix_plane(0, G[0], oracle.rgb_to_gray(C[0], C[1], C[2])))
+    got = mix_graph(tex_pro, MixType.Multiply, C, G).planes()
+    assert len(got) == 4
+    for c in range(3):
+        assert bits_equal(got[c], oracle.mix_plane(2, C[c], G[0]))
+
+
+def test_mix_missing_sides(tex_pro):
+    h, w = 8, 9
+    C = [rnd(40 + c, h, w) for c in range(4)]
+    got = mix_graph(tex_pro, MixType.Subtract, None, C).planes()  # zeros - right
+    for c in range(3):
+        assert bits_equal(got[c], oracle.mix_plane(1, np.zeros((h, w), np.float32), C[c]))
+    img = mix_graph(tex_pro, MixType.Add, None, None)  # neither: 1x1 Gray 0 (mix.rs:77-83)
+    assert not img.is_rgba() and img.size() == Size(1, 1) and img.planes()[0][0, 0] == 0.0
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (2, 3), (5, 4), (64, 64), (33, 100), (100, 36)])
+def test_height_to_normal_exact(tex_pro, shape):
+    h, w = shape
+    hgt = rnd(7, h, w)
+    img = kc.SlotImage.from_planes(tex_pro, [hgt])
+    res = kc.SlotImage(tex_pro._ctx, _h2n_direct(tex_pro, img))
+    got = res.planes()
+    want = oracle.height_to_normal(hgt)
+    for c_ in range(3):
+        assert bits_equal(got[c_], want[c_]), "channel %d" % c_
+    assert np.array_equal(got[3], np.ones((h, w), np.float32))
+
+
+def _h2n_direct(tp, img):
+    import ctypes as C
+    from kanter_core_b200._lib import call, kc_image
+    out = kc_image()
+    call("kc_height_to_normal", tp._ctx._h, C.byref(img._im), C.byref(out))
+    return out
+
+
+def test_height_to_normal_fast_within_tolerance(tex_pro_fast):
+    hgt = rnd(8, 96, 128)
+    img = kc.SlotImage.from_planes(tex_pro_fast, [hgt])
+    got = kc.SlotImage(tex_pro_fast._ctx, _h2n_direct(tex_pro_fast, img)).planes()
+    want = oracle.height_to_normal(hgt)
+    for c in range(3):
+        assert close(got[c], want[c])
+
+
+def _resize_direct(tp, img, w, h, filt):
+    import ctypes as C
+    from kanter_core_b200._lib import call, kc_image
+    out = kc_image()
+    call("kc_resize", tp._ctx._h, C.byref(img._im), w, h, int(filt), C.byref(out))
+    return kc.SlotImage(tp._ctx, out)
+
+
+RESIZES = [((110, 110), (128, 128)), ((64, 48), (200, 150)), ((256, 256), (100, 77)), ((7, 9), (8, 8)),
+           ((1, 1), (16, 16)), ((5, 1), (3, 9)), ((31, 17), (31, 40))]
+
+
+@pytest.mark.parametrize("filt", list(ResizeFilter))
+@pytest.mark.parametrize("src,dst", RESIZES)
+def test_resize_exact(tex_pro, filt, src, dst):
+    (sw, sh), (dw, dh) = src, dst
+    p = rnd(9, sh, sw, -0.25, 1.25)  # out-of-range values exercise the [0,1] clamp of the second pass
+    img = kc.SlotImage.from_planes(tex_pro, [p])
+    got = _resize_direct(tex_pro, img, dw, dh, filt).planes()[0]
+    want = oracle.resize_plane(p, dw, dh, int(filt))
+    assert bits_equal(got, want)
+
+
+@pytest.mark.parametrize("filt", list(ResizeFilter))
+def test_resize_fast_within_tolerance(tex_pro_fast, filt):
+    p = rnd(11, 40, 50)
+    img = kc.SlotImage.from_planes(tex_pro_fast, [p])
+    got = _resize_direct(tex_pro_fast, img, 123, 99, filt).planes()[0]
+    assert close(got, oracle.resize_plane(p, 123, 99, int(filt)))
+
+
+def test_resize_rgba_with_constant_alpha(tex_pro):
+    # a constant alpha plane goes through the same tap arithmetic as any other plane
+    planes = [rnd(50 + c, 20, 30) for c in range(3)]
+    img = kc.SlotImage.from_planes(tex_pro, planes + [np.ones((20, 30), np.float32)])
+    lg = tex_pro.new_live_graph()
+    lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, img), 0)
+    e = lg.add_node(Node.new(NodeType.Embed(0)))
+    n = Node.new(NodeType.Mix(MixType.Add))
+    n.resize_policy = ResizePolicy.SpecificSize(Size(77, 45))
+    n.resize_filter = ResizeFilter.Lanczos3
+    m = lg.add_node(n)
+    lg.connect(e, m, SlotId(0), SlotId(0))
+    kc.LiveGraph.await_clean_read(lg, m)
+    got = lg.slot_data(m, SlotId(0)).image.planes()
+    for c in range(3):
+        r = oracle.resize_plane(planes[c], 77, 45, 4)
+        assert bits_equal(got[c], oracle.mix_plane(0, r, np.zeros_like(r)))
+
+
+@pytest.mark.parametrize("srgb", [False, True])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 3), (31, 33), (64, 64)])
+def test_to_u8(tex_pro, srgb, shape):
+    h, w = shape
+    P = [rnd(60 + c, h, w, -0.5, 1.5) for c in range(4)]
+    P[0].flat[0] = np.nan; P[1].flat[0] = np.inf; P[2].flat[0] = -np.inf; P[3].flat[0] = -0.0
+    img = kc.SlotImage.from_planes(tex_pro, P)
+    assert np.array_equal(img.to_u8(srgb), oracle.to_u8(P, srgb))
+    g = kc.SlotImage.from_planes(tex_pro, P[:1])
+    assert np.array_equal(g.to_u8(srgb), oracle.to_u8(P[:1], srgb))
+
+
+@pytest.mark.parametrize("ch", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape", [(1, 1), (5, 7), (64, 64), (33, 31)])
+def test_from_u8(tex_pro, ch, shape):
+    h, w = shape
+    a = np.random.default_rng(70).integers(0, 256, (h, w, ch), dtype=np.uint8)
+    got = kc.SlotImage.from_u8(tex_pro, a).planes()
+    want = oracle.deconstruct_u8(a)
+    for c in range(4):
+        assert np.array_equal(got[c], want[c])
+
+
+def test_u8_roundtrip_every_value(tex_pro):
+    a = np.arange(256, dtype=np.uint8).reshape(16, 16, 1).repeat(4, axis=2)
+    assert np.array_equal(kc.SlotImage.from_u8(tex_pro, a).to_u8(), a)
+
+
+def test_long_chain_fuses_and_matches(tex_pro):
+    """A 40-node chain of Mix nodes is cut into a few fused kernels (not 40) and
+    still matches the node-by-node oracle bit for bit."""
+    h, w = 50, 70
+    A, B = rnd(80, h, w, 0.5, 1.5), rnd(81, h, w, 0.5, 1.5)
+    lg = tex_pro.new_live_graph()
+    for i, p in enumerate((A, B)):
+        lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tex_pro, [p])), i)
+    a = lg.add_node(Node.new(NodeType.Embed(0)))
+    b = lg.add_node(Node.new(NodeType.Embed(1)))
+    ops = [MixType.Add, MixType.Multiply, MixType.Subtract, MixType.Divide]
+    cur, want = a, A
+    for i in range(40):
+        m = lg.add_node(Node.new(NodeType.Mix(ops[i % 4])))
+        lg.connect(cur, m, SlotId(0), SlotId(0))
+        lg.connect(b, m, SlotId(0), SlotId(1))
+        want = oracle.mix_plane(int(ops[i % 4]), want, B)
+        cur = m
+    kc.LiveGraph.await_clean_read(lg, cur)
+    st = lg.last_run_stats()
+    assert 1 <= st["kernels"] <= 4, st
+    assert bits_equal(lg.slot_data(cur, SlotId(0)).image.planes()[0], want)
+
+
+def test_shared_subexpression_and_diamond(tex_pro):
+    h, w = 33, 47
+    A, B = rnd(90, h, w), rnd(91, h, w)
+    lg = tex_pro.new_live_graph()
+    for i, p in enumerate((A, B)):
+        lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tex_pro, [p])), i)
+    a = lg.add_node(Node.new(NodeType.Embed(0)))
+    b = lg.add_node(Node.new(NodeType.Embed(1)))
+    s = lg.add_node(Node.new(NodeType.Mix(MixType.Add)))       # s = A + B
+    d = lg.add_node(Node.new(NodeType.Mix(MixType.Subtract)))  # d = A - B
+    p = lg.add_node(Node.new(NodeType.Mix(MixType.Multiply)))  # p = s * d
+    q = lg.add_node(Node.new(NodeType.Mix(MixType.Divide)))    # q = p / s   (s used twice)
+    for (o, i, sl) in [(a, s, 0), (b, s, 1), (a, d, 0), (b, d, 1), (s, p, 0), (d, p, 1), (p, q, 0), (s, q, 1)]:
+        lg.connect(o, i, SlotId(0), SlotId(sl))
+    kc.LiveGraph.await_clean_read(lg, q)
+    assert lg.last_run_stats()["kernels"] == 1
+    S, D = oracle.mix_plane(0, A, B), oracle.mix_plane(1, A, B)
+    want = oracle.mix_plane(3, oracle.mix_plane(2, S, D), S)
+    assert bits_equal(lg.slot_data(q, SlotId(0)).image.planes()[0], want)
