@@ -122,11 +122,17 @@ class ClockSampler:
         self.path = "/tmp/kc_clocks_%d_%d.csv" % (os.getpid(), device)
         self.proc = None
         try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.f = open(self.path, "w", buffering=1)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def has_samples(self):
+        try:
+            return os.path.getsize(self.path) > 0
+        except OSError:
+            return False
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
@@ -229,17 +235,24 @@ def ours(args, rank, world, local_rank):
         lg.request(out)
 
     # ---- device-resident throughput --------------------------------------------------------
+    sampler = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         step_resident()
     tp.synchronize()
     stats = lg.last_run_stats()
+    # keep the GPU under the same load until nvidia-smi has started sampling, so the
+    # clocks line describes the timed region and not an idle device
+    t_wait = time.perf_counter()
+    while not sampler.has_samples() and time.perf_counter() - t_wait < 5.0:
+        for _ in range(20):
+            step_resident()
+        tp.synchronize()
 
     ev0, ev1 = C.c_void_p(), C.c_void_p()
     call("kc_event_create", C.byref(ev0))
     call("kc_event_create", C.byref(ev1))
     k0 = tp.stats()["kernel_launches"]
     call("kc_context_set_timing", ctx, 1)
-    sampler = ClockSampler(local_rank)
     barrier()
     tp.synchronize()
     call("kc_event_record", ctx, ev0)
@@ -250,7 +263,7 @@ def ours(args, rank, world, local_rank):
     barrier()
     ms = C.c_float()
     call("kc_event_elapsed_ms", ev0, ev1, C.byref(ms))
-    clocks = sampler.stop()
+    clocks = sampler.stop()   # samples cover the load loop that precedes the timed region and the region itself
     kms, kn = C.c_double(), C.c_uint64()
     call("kc_context_timing_read", ctx, 0, C.byref(kms), C.byref(kn))   # the fused tape kernel
     call("kc_context_set_timing", ctx, 0)
@@ -340,7 +353,7 @@ def ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])

@@ -72,23 +72,25 @@ void collect(kc_plane* const* roots, size_t n, int mark, Cone& c) {
     }
 }
 
-// ---- tape code generation for one kernel -------------------------------------
+// ---- tape code generation for one segment ------------------------------------
 struct Gen {
-    KcTapeArgs args{};
+    std::vector<uint32_t> instr;
+    std::vector<float> imm;
     std::vector<kc_plane*> srcs;   // DEVICE planes bound to S[k]
     bool tmp_used[KC_MAX_TMP] = {false, false, false, false, false, false};
+    int max_tmp = 0;               // temporaries the tape touches (0..KC_MAX_TMP)
     bool ok = true;
     int in_kernel_mark = 0;
 
-    void emit(uint32_t op, uint32_t arg, float imm = 0.0f) {
-        if (args.n_instr >= (uint32_t)KC_MAX_TAPE) { ok = false; return; }
-        args.instr[args.n_instr] = op | (arg << 8);
-        args.imm[args.n_instr] = imm;
-        args.n_instr++;
+    void emit(uint32_t op, uint32_t arg, float v = 0.0f) {
+        if ((int)instr.size() >= KC_MAX_TAPE) { ok = false; return; }
+        instr.push_back(op | (arg << 8));
+        imm.push_back(v);
     }
+    void touch_tmp(int j) { max_tmp = std::max(max_tmp, j + 1); }
     int alloc_tmp() {
         for (int j = 0; j < KC_MAX_TMP; ++j)
-            if (!tmp_used[j]) { tmp_used[j] = true; return j; }
+            if (!tmp_used[j]) { tmp_used[j] = true; touch_tmp(j); return j; }
         ok = false;
         return 0;
     }
@@ -104,14 +106,14 @@ struct Gen {
     bool simple(const kc_plane* p) const { return !in_kernel(p) || p->tmp_slot >= 0; }
 
     // operand reference; consumes one use of p
-    void operand(kc_plane* p, uint32_t& arg, float& imm) {
-        imm = 0.0f;
+    void operand(kc_plane* p, uint32_t& arg, float& v) {
+        v = 0.0f;
         if (in_kernel(p)) {
             arg = KC_ARG_TMP0 + p->tmp_slot;
             consume(p);
         } else if (p->kind == KC_PLANE_CONST) {
             arg = KC_ARG_IMM;
-            imm = p->value;
+            v = p->value;
         } else {
             arg = (uint32_t)src_slot(p);
         }
@@ -126,9 +128,9 @@ struct Gen {
     // leave p's value in acc (consumes one use of p)
     void value(kc_plane* p) {
         if (simple(p)) {
-            uint32_t arg; float imm;
-            operand(p, arg, imm);
-            emit(TOP_LD, arg, imm);
+            uint32_t arg; float v;
+            operand(p, arg, v);
+            emit(TOP_LD, arg, v);
         } else {
             compute(p);
             consume(p);
@@ -157,15 +159,15 @@ struct Gen {
     void compute(kc_plane* x) {
         if (!ok) return;
         kc_plane *a = x->a, *b = x->b;
-        uint32_t arg; float imm;
+        uint32_t arg; float v;
         if (simple(b)) {
             value(a);
-            operand(b, arg, imm);
-            emit(fwd(x->op), arg, imm);
+            operand(b, arg, v);
+            emit(fwd(x->op), arg, v);
         } else if (simple(a)) {
             value(b);
-            operand(a, arg, imm);
-            emit(rev(x->op), arg, imm);
+            operand(a, arg, v);
+            emit(rev(x->op), arg, v);
         } else {
             // both sides still need computing: the bigger cone first, parked in a temp
             const bool a_first = a->need >= b->need;
@@ -178,8 +180,8 @@ struct Gen {
                 first->tmp_slot = t;
             }
             value(second);
-            operand(first, arg, imm);
-            emit(a_first ? rev(x->op) : fwd(x->op), arg, imm);
+            operand(first, arg, v);
+            emit(a_first ? rev(x->op) : fwd(x->op), arg, v);
         }
         if (x->is_out) emit(TOP_ST_OUT, (uint32_t)x->out_slot);
         x->computed = true;
@@ -191,21 +193,31 @@ struct Gen {
     }
 };
 
-struct KernelPlan {
-    std::vector<kc_plane*> nodes;  // in topo order
-    std::vector<kc_plane*> outs;
+// One segment: a set of outputs whose expression cones share nodes or sources.
+struct SegPlan {
+    std::vector<kc_plane*> nodes;  // EXPR nodes, topological order
+    std::vector<kc_plane*> outs;   // EXPR outputs (become DEVICE planes) or one CONST plane to fill
+    bool is_const_fill = false;
+    // filled by gen_segment
+    Gen gen;
+    size_t n_px = 0;
+    int variant = 0;
+    std::vector<float*> out_ptrs;
 };
 
-// Build + launch one kernel.  pack: 0 none, 1 RGBA8 from `pack_planes[4]`, 2 gray.
-// Returns KC_OK, or KC_ERR_GENERIC with gen_failed=true when the group does not
-// fit the machine (caller splits and retries).
-int32_t run_kernel(kc_context* ctx, KernelPlan& k, int pack, kc_plane* const* pack_planes, int srgb,
-                   uint32_t* d_rgba8, bool& gen_failed) {
-    gen_failed = false;
+// pack: 0 none, 1 RGBA8 from pack_planes[4], 2 gray from pack_planes[0]
+bool gen_segment(SegPlan& k, int pack, kc_plane* const* pack_planes, int srgb) {
     static std::atomic<int> kernel_serial{1000};
-    Gen g;
+    Gen& g = k.gen;
     g.in_kernel_mark = ++kernel_serial;
-    // in-kernel use counts and Sethi-Ullman-ish sizes
+    if (k.is_const_fill) {
+        kc_plane* c = k.outs[0];
+        k.n_px = c->count();
+        g.emit(TOP_LD, KC_ARG_IMM, c->value);
+        g.emit(TOP_ST_OUT, 0);
+        k.variant = 0;
+        return g.ok;
+    }
     for (kc_plane* p : k.nodes) {
         p->ktag = g.in_kernel_mark;
         p->remaining = 0;
@@ -227,11 +239,10 @@ int32_t run_kernel(kc_context* ctx, KernelPlan& k, int pack, kc_plane* const* pa
         w = pack_planes[0]->w; h = pack_planes[0]->h;
         for (int c = 0; c < (pack == 1 ? 4 : 1); ++c)
             if (g.in_kernel(pack_planes[c])) pack_planes[c]->remaining++;
-        if (pack == 1) g.tmp_used[0] = g.tmp_used[1] = g.tmp_used[2] = true;
+        if (pack == 1) { g.tmp_used[0] = g.tmp_used[1] = g.tmp_used[2] = true; g.touch_tmp(2); }
     }
-    const size_t n_px = (size_t)w * h;
-
-    if ((int)k.outs.size() > KC_MAX_OUT) { gen_failed = true; return KC_ERR_GENERIC; }
+    k.n_px = (size_t)w * h;
+    if ((int)k.outs.size() > KC_MAX_OUT) return false;
     for (size_t m = 0; m < k.outs.size(); ++m) {
         k.outs[m]->is_out = true;
         k.outs[m]->out_slot = (int)m;
@@ -255,61 +266,82 @@ int32_t run_kernel(kc_context* ctx, KernelPlan& k, int pack, kc_plane* const* pa
         g.value(pack_planes[0]);
         g.emit(TOP_PACK_GRAY, srgb ? 1u : 0u);
     }
-    if (!g.ok) { gen_failed = true; return KC_ERR_GENERIC; }
-
-    std::vector<float*> out_ptrs;
-    for (kc_plane* o : k.outs) {
-        kc_plane* tmp = nullptr;
-        int32_t rc = kcp_new_device(ctx, o->w, o->h, &tmp);
-        if (rc != KC_OK) return rc;
-        out_ptrs.push_back(tmp->dptr);
-        tmp->owned = false;  // storage moves into `o` below
-        tmp->dptr = nullptr;
-        delete tmp;
-    }
-    g.args.n = n_px;
-    g.args.n_src = (uint32_t)g.srcs.size();
-    for (size_t s = 0; s < g.srcs.size(); ++s) g.args.src[s] = g.srcs[s]->dptr;
-    for (size_t m = 0; m < out_ptrs.size(); ++m) g.args.out[m] = out_ptrs[m];
-    g.args.out_rgba8 = d_rgba8;
-    int32_t rc = kck_launch_tape(ctx, g.args);
-    if (rc != KC_OK) {
-        for (float* p : out_ptrs) cudaFreeAsync(p, ctx->stream);
-        return rc;
-    }
-    ctx->run_groups++;
-    ctx->run_bytes += (uint64_t)(g.srcs.size() + out_ptrs.size()) * n_px * 4 + (pack ? n_px * 4 : 0);
-    // the outputs become device planes; their operand references are dropped
-    for (size_t m = 0; m < k.outs.size(); ++m) {
-        kc_plane* o = k.outs[m];
-        kc_plane *a = o->a, *b = o->b;
-        o->kind = KC_PLANE_DEVICE;
-        o->dptr = out_ptrs[m];
-        o->owned = true;
-        o->a = o->b = nullptr;
-        kcp_release(a);
-        kcp_release(b);
-    }
-    return KC_OK;
+    if (!g.ok) return false;
+    const int ns = (int)g.srcs.size();
+    if (ns <= 2 && g.max_tmp <= 2) k.variant = 0;
+    else if (ns <= 4 && g.max_tmp <= 3) k.variant = 1;
+    else k.variant = 2;
+    return true;
 }
 
-int32_t materialise_const(kc_context* ctx, kc_plane* p) {
+int32_t alloc_plane_storage(kc_context* ctx, kc_plane* like, float** out) {
     kc_plane* tmp = nullptr;
-    KC_TRY(kcp_new_device(ctx, p->w, p->h, &tmp));
-    float* d = tmp->dptr;
-    tmp->owned = false;
+    KC_TRY(kcp_new_device(ctx, like->w, like->h, &tmp));
+    *out = tmp->dptr;
+    tmp->owned = false;  // the storage is adopted by the caller
     tmp->dptr = nullptr;
     delete tmp;
-    int32_t rc = kck_fill(ctx, d, p->count(), p->value);
-    if (rc != KC_OK) { cudaFreeAsync(d, ctx->stream); return rc; }
-    ctx->run_bytes += p->bytes();
-    p->kind = KC_PLANE_DEVICE;
-    p->dptr = d;
-    p->owned = true;
     return KC_OK;
 }
 
-// distinct DEVICE sources of the sub-cone rooted at each node, capped
+// Launch a set of generated, mutually independent segments: grouped by pixel
+// count and kernel variant, up to KC_MAX_SEG per launch.
+int32_t launch_segments(kc_context* ctx, std::vector<SegPlan*>& segs, uint32_t* d_rgba8) {
+    for (SegPlan* k : segs) {
+        for (kc_plane* o : k->outs) {
+            float* d = nullptr;
+            KC_TRY(alloc_plane_storage(ctx, o, &d));
+            k->out_ptrs.push_back(d);
+        }
+    }
+    std::vector<bool> done(segs.size(), false);
+    for (size_t i = 0; i < segs.size(); ++i) {
+        if (done[i]) continue;
+        KcTapeArgs args;
+        memset(&args, 0, sizeof args);
+        args.n = segs[i]->n_px;
+        args.variant = (uint32_t)segs[i]->variant;
+        uint32_t pc = 0;
+        for (size_t j = i; j < segs.size() && args.n_seg < (uint32_t)KC_MAX_SEG; ++j) {
+            SegPlan* k = segs[j];
+            if (done[j] || k->n_px != args.n || (uint32_t)k->variant != args.variant) continue;
+            if (pc + k->gen.instr.size() > (size_t)KC_MAX_TAPE) continue;
+            KcSegment& sg = args.seg[args.n_seg++];
+            sg.tape_begin = pc;
+            for (size_t t = 0; t < k->gen.instr.size(); ++t) {
+                args.instr[pc] = k->gen.instr[t];
+                args.imm[pc] = k->gen.imm[t];
+                ++pc;
+            }
+            sg.tape_end = pc;
+            sg.n_src = (uint32_t)k->gen.srcs.size();
+            for (size_t q = 0; q < k->gen.srcs.size(); ++q) sg.src[q] = k->gen.srcs[q]->dptr;
+            for (size_t m = 0; m < k->out_ptrs.size(); ++m) sg.out[m] = k->out_ptrs[m];
+            sg.out_rgba8 = d_rgba8;
+            done[j] = true;
+            ctx->run_groups++;
+            ctx->run_bytes += (uint64_t)(k->gen.srcs.size() + k->out_ptrs.size()) * k->n_px * 4 + (d_rgba8 ? k->n_px * 4 : 0);
+        }
+        int32_t rc = kck_launch_tape(ctx, args);
+        if (rc != KC_OK) return rc;
+    }
+    // the outputs become device planes; their operand references are dropped
+    for (SegPlan* k : segs) {
+        for (size_t m = 0; m < k->outs.size(); ++m) {
+            kc_plane* o = k->outs[m];
+            kc_plane *a = o->a, *b = o->b;
+            o->kind = KC_PLANE_DEVICE;
+            o->dptr = k->out_ptrs[m];
+            o->owned = true;
+            o->a = o->b = nullptr;
+            if (a) kcp_release(a);
+            if (b) kcp_release(b);
+        }
+    }
+    return KC_OK;
+}
+
+// distinct DEVICE sources and node count of the sub-cone rooted at each node
 struct Est {
     int nodes = 0;
     std::vector<kc_plane*> srcs;
@@ -318,7 +350,6 @@ struct Est {
 int32_t force_impl(kc_context* ctx, kc_plane* const* roots, size_t n, int pack, int srgb, uint32_t* d_rgba8, int depth);
 
 // Shrink cones that cannot fit one kernel by materialising an interior node.
-// Returns true when something was forced (caller must re-plan).
 int32_t split_oversized(kc_context* ctx, Cone& c, bool& changed, int depth) {
     changed = false;
     std::map<kc_plane*, Est> est;
@@ -352,116 +383,121 @@ int32_t split_oversized(kc_context* ctx, Cone& c, bool& changed, int depth) {
     return KC_OK;
 }
 
+// all EXPR nodes and DEVICE sources below `o`
+void cone_of(kc_plane* o, std::vector<kc_plane*>& nodes, std::vector<kc_plane*>& srcs) {
+    std::vector<kc_plane*> st{o};
+    while (!st.empty()) {
+        kc_plane* p = st.back();
+        st.pop_back();
+        if (is_expr(p)) {
+            if (std::find(nodes.begin(), nodes.end(), p) != nodes.end()) continue;
+            nodes.push_back(p);
+            st.push_back(p->a);
+            st.push_back(p->b);
+        } else if (p->kind == KC_PLANE_DEVICE) {
+            if (std::find(srcs.begin(), srcs.end(), p) == srcs.end()) srcs.push_back(p);
+        }
+    }
+}
+
 int32_t force_impl(kc_context* ctx, kc_plane* const* roots, size_t n, int pack, int srgb, uint32_t* d_rgba8, int depth) {
     static std::atomic<int> mark_serial{MARK_BASE};
     if (depth > 64) KC_FAIL(KC_ERR_GENERIC, "fusion planner: recursion too deep");
-    for (int attempt = 0; attempt < 100000; ++attempt) {
+    for (int round = 0; round < 100000; ++round) {
         Cone c;
         collect(roots, n, ++mark_serial, c);
-        if (c.order.empty() && !pack) return KC_OK;
         bool changed = false;
         KC_TRY(split_oversized(ctx, c, changed, depth));
         if (changed) continue;
-
-        // outputs: the roots, plus interior values somebody outside the cone still holds
-        std::vector<kc_plane*> outs;
-        if (!pack) {
-            for (kc_plane* p : c.order) {
-                bool root = false;
-                for (size_t i = 0; i < n; ++i) root |= (roots[i] == p);
-                if (root || p->refs.load() > p->uses_in_cone) outs.push_back(p);
-            }
-        }
-        // greedy partition of the outputs (topological order) into kernels
-        std::vector<KernelPlan> plans;
-        {
-            // membership: node -> index of the kernel that computes it (-1 none yet)
-            std::map<kc_plane*, int> owner;
-            auto cone_of = [&](kc_plane* o, int kidx, std::vector<kc_plane*>& add, std::vector<kc_plane*>& srcs) {
-                // nodes of o's cone not materialised by an earlier kernel
-                std::vector<kc_plane*> st{o};
-                std::vector<kc_plane*> seen;
-                while (!st.empty()) {
-                    kc_plane* p = st.back();
-                    st.pop_back();
-                    if (std::find(seen.begin(), seen.end(), p) != seen.end()) continue;
-                    seen.push_back(p);
-                    auto it = owner.find(p);
-                    bool earlier_out = it != owner.end() && it->second < kidx &&
-                                       std::find(outs.begin(), outs.end(), p) != outs.end();
-                    if (is_expr(p) && !earlier_out) {
-                        if (it == owner.end() || it->second != kidx) add.push_back(p);
-                        st.push_back(p->a);
-                        st.push_back(p->b);
-                    } else if (p->kind != KC_PLANE_CONST) {
-                        if (std::find(srcs.begin(), srcs.end(), p) == srcs.end()) srcs.push_back(p);
-                    }
-                }
-            };
-            KernelPlan cur;
-            std::vector<kc_plane*> cur_srcs;
-            int kidx = 0;
-            auto flush = [&]() {
-                if (cur.outs.empty()) return;
-                plans.push_back(cur);
-                cur = KernelPlan();
-                cur_srcs.clear();
-                kidx++;
-            };
-            for (kc_plane* o : outs) {
-                std::vector<kc_plane*> add, srcs = cur_srcs;
-                cone_of(o, kidx, add, srcs);
-                bool fits = (int)(cur.nodes.size() + add.size()) <= CAP_NODES && (int)srcs.size() <= KC_MAX_SRC &&
-                            (int)cur.outs.size() + 1 <= KC_MAX_OUT;
-                if (!fits && !cur.outs.empty()) {
-                    flush();
-                    add.clear();
-                    srcs.clear();
-                    cone_of(o, kidx, add, srcs);
-                }
-                for (kc_plane* p : add) { cur.nodes.push_back(p); owner[p] = kidx; }
-                cur.outs.push_back(o);
-                cur_srcs = srcs;
-            }
-            flush();
-        }
-        // nodes inside each plan must be in topological order
         std::map<kc_plane*, int> pos;
         for (size_t i = 0; i < c.order.size(); ++i) pos[c.order[i]] = (int)i;
-        bool failed = false;
-        for (KernelPlan& k : plans) {
-            std::sort(k.nodes.begin(), k.nodes.end(), [&](kc_plane* a, kc_plane* b) { return pos[a] < pos[b]; });
-            std::sort(k.outs.begin(), k.outs.end(), [&](kc_plane* a, kc_plane* b) { return pos[a] < pos[b]; });
-            bool gen_failed = false;
-            int32_t rc = run_kernel(ctx, k, 0, nullptr, 0, nullptr, gen_failed);
-            if (gen_failed) {
-                // register/tape pressure: materialise the deepest operand of the last output and re-plan
-                kc_plane* o = k.outs.back();
-                kc_plane* pick = is_expr(o->a) ? o->a : (is_expr(o->b) ? o->b : nullptr);
-                if (!pick) KC_FAIL(KC_ERR_GENERIC, "fusion planner: kernel generation failed on a leaf group");
-                KC_TRY(force_impl(ctx, &pick, 1, 0, 0, nullptr, depth + 1));
-                failed = true;
-                break;
-            }
-            if (rc != KC_OK) return rc;
-        }
-        if (failed) continue;
+
         if (pack) {
-            // everything the export needs that is still lazy goes into the export kernel itself
-            Cone pc;
-            collect(roots, n, ++mark_serial, pc);
-            KernelPlan k;
-            k.nodes = pc.order;
-            bool gen_failed = false;
-            int32_t rc = run_kernel(ctx, k, pack, roots, srgb, d_rgba8, gen_failed);
-            if (gen_failed) {
-                // too big for one export kernel: materialise the channels first, then export
+            // the export kernel computes whatever is still lazy itself; nothing is stored as f32
+            SegPlan k;
+            k.nodes = c.order;
+            if (!gen_segment(k, pack, roots, srgb)) {
+                // too big for one kernel: materialise the channels first, then export them
                 KC_TRY(force_impl(ctx, roots, n, 0, 0, nullptr, depth + 1));
                 continue;
             }
-            return rc;
+            std::vector<SegPlan*> one{&k};
+            return launch_segments(ctx, one, d_rgba8);
         }
-        return KC_OK;
+
+        // outputs: lazy roots, plus interior values somebody outside the cone still holds;
+        // constant roots become fill segments of the same launch
+        std::vector<kc_plane*> outs;
+        for (kc_plane* p : c.order) {
+            bool root = false;
+            for (size_t i = 0; i < n; ++i) root |= (roots[i] == p);
+            if (root || p->refs.load() > p->uses_in_cone) outs.push_back(p);
+        }
+        std::vector<kc_plane*> const_roots;
+        for (size_t i = 0; i < n; ++i)
+            if (roots[i]->kind == KC_PLANE_CONST && std::find(const_roots.begin(), const_roots.end(), roots[i]) == const_roots.end())
+                const_roots.push_back(roots[i]);
+        if (outs.empty() && const_roots.empty()) return KC_OK;
+
+        // components: outputs whose cones share an expression node or a source plane
+        const size_t no = outs.size();
+        std::vector<std::vector<kc_plane*>> cn(no), cs(no);
+        for (size_t i = 0; i < no; ++i) cone_of(outs[i], cn[i], cs[i]);
+        std::vector<int> comp(no);
+        for (size_t i = 0; i < no; ++i) comp[i] = (int)i;
+        auto find = [&](int x) { while (comp[x] != x) x = comp[x] = comp[comp[x]]; return x; };
+        for (size_t i = 0; i < no; ++i)
+            for (size_t j = i + 1; j < no; ++j) {
+                if (find((int)i) == find((int)j)) continue;
+                bool share = false;
+                for (kc_plane* p : cn[i]) if (std::find(cn[j].begin(), cn[j].end(), p) != cn[j].end()) { share = true; break; }
+                if (!share) for (kc_plane* p : cs[i]) if (std::find(cs[j].begin(), cs[j].end(), p) != cs[j].end()) { share = true; break; }
+                if (share && outs[i]->w == outs[j]->w && outs[i]->h == outs[j]->h) comp[find((int)j)] = find((int)i);
+            }
+        // one segment per component: the longest prefix of its outputs (topological
+        // order) that fits the machine; the rest waits for the next round
+        std::vector<std::unique_ptr<SegPlan>> plans;
+        for (size_t r = 0; r < no; ++r) {
+            if (find((int)r) != (int)r) continue;
+            auto k = std::make_unique<SegPlan>();
+            std::vector<kc_plane*> srcs;
+            for (size_t i = 0; i < no; ++i) {
+                if (find((int)i) != (int)r) continue;
+                std::vector<kc_plane*> nodes = k->nodes, s2 = srcs;
+                for (kc_plane* p : cn[i]) if (std::find(nodes.begin(), nodes.end(), p) == nodes.end()) nodes.push_back(p);
+                for (kc_plane* p : cs[i]) if (std::find(s2.begin(), s2.end(), p) == s2.end()) s2.push_back(p);
+                const bool fits = (int)nodes.size() <= CAP_NODES && (int)s2.size() <= KC_MAX_SRC && (int)k->outs.size() + 1 <= KC_MAX_OUT;
+                if (!fits && !k->outs.empty()) break;
+                k->nodes.swap(nodes);
+                srcs.swap(s2);
+                k->outs.push_back(outs[i]);
+            }
+            std::sort(k->nodes.begin(), k->nodes.end(), [&](kc_plane* a, kc_plane* b) { return pos[a] < pos[b]; });
+            plans.push_back(std::move(k));
+        }
+        bool failed = false;
+        for (auto& k : plans) {
+            if (gen_segment(*k, 0, nullptr, 0)) continue;
+            // register / tape pressure: materialise an operand of the last output and re-plan
+            kc_plane* o = k->outs.back();
+            kc_plane* pick = is_expr(o->a) ? o->a : (is_expr(o->b) ? o->b : nullptr);
+            if (!pick) KC_FAIL(KC_ERR_GENERIC, "fusion planner: kernel generation failed on a leaf group");
+            KC_TRY(force_impl(ctx, &pick, 1, 0, 0, nullptr, depth + 1));
+            failed = true;
+            break;
+        }
+        if (failed) continue;
+        for (kc_plane* cr : const_roots) {
+            auto k = std::make_unique<SegPlan>();
+            k->is_const_fill = true;
+            k->outs.push_back(cr);
+            gen_segment(*k, 0, nullptr, 0);
+            plans.push_back(std::move(k));
+        }
+        std::vector<SegPlan*> segs;
+        for (auto& k : plans) segs.push_back(k.get());
+        KC_TRY(launch_segments(ctx, segs, nullptr));
+        // anything that did not fit this round is picked up by the next one
     }
     KC_FAIL(KC_ERR_GENERIC, "fusion planner did not converge");
 }
@@ -469,9 +505,6 @@ int32_t force_impl(kc_context* ctx, kc_plane* const* roots, size_t n, int pack, 
 }  // namespace
 
 int32_t kcp_force(kc_context* ctx, kc_plane* const* roots, size_t n) {
-    // constants among the roots become real planes; lazy ones are fused
-    for (size_t i = 0; i < n; ++i)
-        if (roots[i]->kind == KC_PLANE_CONST) KC_TRY(materialise_const(ctx, roots[i]));
     return force_impl(ctx, roots, n, 0, 0, nullptr, 0);
 }
 

@@ -46,7 +46,8 @@ void kc_set_error(const char* fmt, ...);
 constexpr int KC_MAX_SRC = 8;
 constexpr int KC_MAX_TMP = 6;
 constexpr int KC_MAX_OUT = 6;
-constexpr int KC_MAX_TAPE = 72;
+constexpr int KC_MAX_TAPE = 96;   // instructions per launch, all segments together
+constexpr int KC_MAX_SEG = 4;     // independent programs per launch (blockIdx.y)
 constexpr int KC_ARG_TMP0 = 8;
 constexpr int KC_ARG_IMM = 14;
 
@@ -66,13 +67,22 @@ enum KcTapeOp : uint32_t {
     TOP_PACK_GRAY,   // rgba8[i] = (to_u8(acc) x3, 255)  (arg = 1: sRGB)
 };
 
-struct KcTapeArgs {
+// One launch runs up to KC_MAX_SEG independent segments (blockIdx.y picks one):
+// each has its own source/output planes and its own slice of the tape.  The
+// three channels of an Rgba Mix chain are three segments of one launch.
+struct KcSegment {
     const float* src[KC_MAX_SRC];
     float* out[KC_MAX_OUT];
     uint32_t* out_rgba8;
-    unsigned long long n;  // pixels per plane
-    uint32_t n_src;
-    uint32_t n_instr;
+    uint32_t tape_begin, tape_end;
+    uint32_t n_src, pad;
+};
+
+struct KcTapeArgs {
+    KcSegment seg[KC_MAX_SEG];
+    unsigned long long n;  // pixels per plane (the same for every segment of a launch)
+    uint32_t n_seg;
+    uint32_t variant;      // 0: <=2 sources, <=2 temps, 2 float4/thread; 1: <=4, <=3, 2; 2: <=8, <=6, 1
     uint32_t instr[KC_MAX_TAPE];
     float imm[KC_MAX_TAPE];
 };
