@@ -201,7 +201,6 @@ struct SegPlan {
     // filled by gen_segment
     Gen gen;
     size_t n_px = 0;
-    int variant = 0;
     std::vector<float*> out_ptrs;
 };
 
@@ -215,7 +214,6 @@ bool gen_segment(SegPlan& k, int pack, kc_plane* const* pack_planes, int srgb) {
         k.n_px = c->count();
         g.emit(TOP_LD, KC_ARG_IMM, c->value);
         g.emit(TOP_ST_OUT, 0);
-        k.variant = 0;
         return g.ok;
     }
     for (kc_plane* p : k.nodes) {
@@ -266,12 +264,7 @@ bool gen_segment(SegPlan& k, int pack, kc_plane* const* pack_planes, int srgb) {
         g.value(pack_planes[0]);
         g.emit(TOP_PACK_GRAY, srgb ? 1u : 0u);
     }
-    if (!g.ok) return false;
-    const int ns = (int)g.srcs.size();
-    if (ns <= 2 && g.max_tmp <= 2) k.variant = 0;
-    else if (ns <= 4 && g.max_tmp <= 3) k.variant = 1;
-    else k.variant = 2;
-    return true;
+    return g.ok;
 }
 
 int32_t alloc_plane_storage(kc_context* ctx, kc_plane* like, float** out) {
@@ -285,7 +278,7 @@ int32_t alloc_plane_storage(kc_context* ctx, kc_plane* like, float** out) {
 }
 
 // Launch a set of generated, mutually independent segments: grouped by pixel
-// count and kernel variant, up to KC_MAX_SEG per launch.
+// count, up to KC_MAX_SEG per launch.
 int32_t launch_segments(kc_context* ctx, std::vector<SegPlan*>& segs, uint32_t* d_rgba8) {
     for (SegPlan* k : segs) {
         for (kc_plane* o : k->outs) {
@@ -300,11 +293,11 @@ int32_t launch_segments(kc_context* ctx, std::vector<SegPlan*>& segs, uint32_t* 
         KcTapeArgs args;
         memset(&args, 0, sizeof args);
         args.n = segs[i]->n_px;
-        args.variant = (uint32_t)segs[i]->variant;
+        args.variant = 0;  // becomes the number of temporaries the launch needs
         uint32_t pc = 0;
         for (size_t j = i; j < segs.size() && args.n_seg < (uint32_t)KC_MAX_SEG; ++j) {
             SegPlan* k = segs[j];
-            if (done[j] || k->n_px != args.n || (uint32_t)k->variant != args.variant) continue;
+            if (done[j] || k->n_px != args.n) continue;
             if (pc + k->gen.instr.size() > (size_t)KC_MAX_TAPE) continue;
             KcSegment& sg = args.seg[args.n_seg++];
             sg.tape_begin = pc;
@@ -314,6 +307,7 @@ int32_t launch_segments(kc_context* ctx, std::vector<SegPlan*>& segs, uint32_t* 
                 ++pc;
             }
             sg.tape_end = pc;
+            args.variant = std::max<uint32_t>(args.variant, (uint32_t)k->gen.max_tmp);
             sg.n_src = (uint32_t)k->gen.srcs.size();
             for (size_t q = 0; q < k->gen.srcs.size(); ++q) sg.src[q] = k->gen.srcs[q]->dptr;
             for (size_t m = 0; m < k->out_ptrs.size(); ++m) sg.out[m] = k->out_ptrs[m];

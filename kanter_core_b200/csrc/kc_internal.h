@@ -82,7 +82,7 @@ struct KcTapeArgs {
     KcSegment seg[KC_MAX_SEG];
     unsigned long long n;  // pixels per plane (the same for every segment of a launch)
     uint32_t n_seg;
-    uint32_t variant;      // 0: <=2 sources, <=2 temps, 2 float4/thread; 1: <=4, <=3, 2; 2: <=8, <=6, 1
+    uint32_t variant;      // number of shared-memory temporaries the tapes of this launch touch
     uint32_t instr[KC_MAX_TAPE];
     float imm[KC_MAX_TAPE];
 };

@@ -17,6 +17,8 @@
 // HBM-bound streaming work: 16-byte coalesced accesses, streaming cache hints
 // (every byte is touched once), all source loads of a pixel group issued before
 // the first use, grid.x = SM count x resident CTAs (grid-stride inside).
+#include <cstdlib>
+
 #include "kc_internal.h"
 
 namespace {
@@ -93,6 +95,10 @@ __device__ __noinline__ float kc_pow_special(float x, float y, uint32_t& ix, uin
     return 0.0f;
 }
 
+__device__ __forceinline__ float kc_pow_exact(float x, float y);
+// out-of-line copy for the rare slow path of FAST mode (keeps the hot loop small)
+__device__ __noinline__ float kc_pow_exact_call(float x, float y) { return kc_pow_exact(x, y); }
+
 __device__ __forceinline__ float kc_pow_exact(float x, float y) {
     uint32_t sign_bias = 0;
     uint32_t ix = __float_as_uint(x);
@@ -145,29 +151,36 @@ __device__ __forceinline__ float kc_pow_exact(float x, float y) {
 // FAST: x^y = 2^(y*log2 x) on the special-function unit for positive normal x
 // and |y| <= 16, with the exponent product split so its rounding error does not
 // scale with |log2 x| (x = m*2^e, m in [sqrt(.5), sqrt(2)); t = y*e + y*log2 m).
-// ~4e-7 relative error; anything else takes the exact routine.
-__device__ __forceinline__ float kc_pow_fast(float x, float y) {
+// Branch-free; `bad` collects the lanes whose inputs fall outside that domain
+// (they are redone with the exact routine).  ~4e-7 relative error.
+__device__ __forceinline__ float kc_pow_fast_core(float x, float y, bool& bad) {
     const uint32_t ix = __float_as_uint(x);
-    if (ix - 0x00800000u < 0x7f000000u && fabsf(y) <= 16.0f) {
-        const int e = (int)(ix - 0x3f3504f3u) >> 23;
-        const float m = __uint_as_float(ix - ((uint32_t)e << 23));
-        const float ef = (float)e;
-        const float lm = __log2f(m);
-        const float p1 = y * ef;
-        const float r1 = fmaf(y, ef, -p1);  // exact residual of the product
-        const float nf = rintf(p1);
-        if (fabsf(nf) < 100.0f) {
-            const float f = (p1 - nf) + fmaf(y, lm, r1);
-            const float s = __uint_as_float((uint32_t)((int)nf + 127) << 23);
-            return exp2f(f) * s;
-        }
-    }
-    return kc_pow_exact(x, y);
+    const uint32_t top = (ix - 0x3f3504f3u) & 0xff800000u;
+    const float m = __uint_as_float(ix - top);
+    const float ef = (float)((int)top >> 23);
+    float lm;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lm) : "f"(m));
+    const float p1 = y * ef;
+    const float r1 = fmaf(y, ef, -p1);          // exact residual of the product
+    const float t = p1 + 12582912.0f;           // 1.5 * 2^23: the integer nearest p1 sits in the low mantissa bits
+    const float nf = t - 12582912.0f;
+    const float f = (p1 - nf) + fmaf(y, lm, r1);
+    float e2;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(f));
+    const float s = __int_as_float((__float_as_int(t) << 23) + 0x3f800000);  // 2^n
+    float r = e2 * s;
+    const bool zero_pos = (ix == 0u) && (y > 0.0f);                 // +0 ^ positive = +0 (black pixels)
+    r = zero_pos ? 0.0f : r;
+    bad = !zero_pos && ((ix - 0x00800000u >= 0x7f000000u) || !(fabsf(y) <= 16.0f) || !(fabsf(p1) < 100.0f));
+    return r;
 }
 
 template <bool EXACT>
 __device__ __forceinline__ float kc_pow(float a, float b) {
-    return EXACT ? kc_pow_exact(a, b) : kc_pow_fast(a, b);
+    if (EXACT) return kc_pow_exact(a, b);
+    bool bad;
+    const float r = kc_pow_fast_core(a, b, bad);
+    return bad ? kc_pow_exact_call(a, b) : r;
 }
 
 // SlotImage::f32_to_u8, src/slot_image.rs:142-145:
@@ -192,145 +205,219 @@ __device__ __forceinline__ uint32_t kc_to_u8_srgb(float v) {
     return __float2uint_rz(m);
 }
 
-#define KC_LANES(fn, a, x) make_float4(fn((a).x, (x).x), fn((a).y, (x).y), fn((a).z, (x).z), fn((a).w, (x).w))
-#define KC_LANES_R(fn, a, x) make_float4(fn((x).x, (a).x), fn((x).y, (a).y), fn((x).z, (a).z), fn((x).w, (a).w))
-
+// four lanes at once: one slow-path branch per float4 instead of one per lane
 template <bool EXACT>
-__device__ __forceinline__ float4 tape_binary(uint32_t op, float4 a, float4 x) {
-    switch (op) {
-        case TOP_ADD: return KC_LANES(__fadd_rn, a, x);
-        case TOP_SUB: return KC_LANES(__fsub_rn, a, x);
-        case TOP_RSUB: return KC_LANES_R(__fsub_rn, a, x);
-        case TOP_MUL: return KC_LANES(__fmul_rn, a, x);
-        case TOP_DIV: return KC_LANES(__fdiv_rn, a, x);
-        case TOP_RDIV: return KC_LANES_R(__fdiv_rn, a, x);
-        case TOP_POW: return KC_LANES(kc_pow<EXACT>, a, x);
-        default: return KC_LANES_R(kc_pow<EXACT>, a, x);
+__device__ __forceinline__ float4 kc_pow4(float4 a, float4 b) {
+    if (EXACT) return make_float4(kc_pow_exact(a.x, b.x), kc_pow_exact(a.y, b.y), kc_pow_exact(a.z, b.z), kc_pow_exact(a.w, b.w));
+    bool b0, b1, b2, b3;
+    float4 r = make_float4(kc_pow_fast_core(a.x, b.x, b0), kc_pow_fast_core(a.y, b.y, b1), kc_pow_fast_core(a.z, b.z, b2),
+                           kc_pow_fast_core(a.w, b.w, b3));
+    if (b0 | b1 | b2 | b3) {
+        if (b0) r.x = kc_pow_exact_call(a.x, b.x);
+        if (b1) r.y = kc_pow_exact_call(a.y, b.y);
+        if (b2) r.z = kc_pow_exact_call(a.z, b.z);
+        if (b3) r.w = kc_pow_exact_call(a.w, b.w);
     }
+    return r;
 }
 
-// vector index `idx` of a plane of n pixels: full float4s below nfull, one ragged
-// group of `tail` pixels at nfull.
-__device__ __forceinline__ float4 load_group(const float* p, size_t idx, size_t nfull, int tail) {
-    if (idx < nfull) return __ldcs(reinterpret_cast<const float4*>(p) + idx);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (idx == nfull && tail) {
-        const float* q = p + 4 * nfull;
-        v.x = q[0];
-        if (tail > 1) v.y = q[1];
-        if (tail > 2) v.z = q[2];
-    }
-    return v;
+#define KC_LANES(fn, P_, Q_) make_float4(fn((P_).x, (Q_).x), fn((P_).y, (Q_).y), fn((P_).z, (Q_).z), fn((P_).w, (Q_).w))
+#define KC_LANES_R(fn, P_, Q_) make_float4(fn((Q_).x, (P_).x), fn((Q_).y, (P_).y), fn((Q_).z, (P_).z), fn((Q_).w, (P_).w))
+
+// ---------------------------------------------------------------------------
+// The tile VM.
+//
+// Persistent CTAs walk (segment, tile) work items.  A tile is 1024*V pixels of
+// every source plane of the segment, brought into shared memory by TMA bulk
+// copies (cp.async.bulk, completion on an mbarrier) `stages`-1 tiles ahead of
+// the arithmetic, so the bytes in flight per SM are set by the pipeline depth
+// and not by how many registers the arithmetic needs.  The tape is then
+// interpreted once per tile: each thread keeps the accumulator for its V
+// float4s in registers, operands come from the shared-memory tile (sources) or
+// from shared-memory temporaries, results go straight to global memory with
+// 16-byte streaming stores.  The dispatch cost of an instruction is paid once
+// per 4*V pixels per thread.
+// ---------------------------------------------------------------------------
+constexpr int TVM_THREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void store_group(float* p, size_t idx, float4 v, size_t nfull, int tail) {
-    if (idx < nfull) {
-        __stcs(reinterpret_cast<float4*>(p) + idx, v);
-    } else if (idx == nfull && tail) {
-        float* q = p + 4 * nfull;
-        q[0] = v.x;
-        if (tail > 1) q[1] = v.y;
-        if (tail > 2) q[2] = v.z;
-    }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void store_group_u32(uint32_t* p, size_t idx, uint4 v, size_t nfull, int tail) {
-    if (idx < nfull) {
-        __stcs(reinterpret_cast<uint4*>(p) + idx, v);
-    } else if (idx == nfull && tail) {
-        uint32_t* q = p + 4 * nfull;
-        q[0] = v.x;
-        if (tail > 1) q[1] = v.y;
-        if (tail > 2) q[2] = v.z;
-    }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA, 1-D), bytes a multiple of 16, both sides 16-byte aligned;
+// evict-first in L2: every source byte is read exactly once
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
 }
 
-constexpr int TAPE_BLOCK = 256;
+template <bool EXACT, int V>
+__global__ void __launch_bounds__(TVM_THREADS, 2)
+    kc_tile_vm_kernel(const __grid_constant__ KcTapeArgs A, int stages, int ns_max, uint32_t tiles_per_plane, uint32_t total_work) {
+    constexpr int TILE_PX = 1024 * V;
+    constexpr uint32_t TILE_B = TILE_PX * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);                 // [stages]
+    float* stage_base = reinterpret_cast<float*>(smem_raw + 128);             // [stages][ns_max][TILE_PX]
+    float* tmp_base = stage_base + (size_t)stages * ns_max * TILE_PX;         // [temporaries][TILE_PX]
+    const int tid = threadIdx.x;
+    const unsigned long long n = A.n;
 
-// NS sources, NT temporaries, V float4s per thread and tape pass.
-template <bool EXACT, int NS, int NT, int V, int MINB>
-__global__ void __launch_bounds__(TAPE_BLOCK, MINB) kc_tape_kernel(const __grid_constant__ KcTapeArgs A) {
-    const KcSegment& G = A.seg[blockIdx.y];
-    const size_t nfull = (size_t)(A.n >> 2);
-    const int tail = (int)(A.n & 3ull);
-    const size_t ngroups = nfull + (tail ? 1 : 0);
-    const uint32_t pc0 = G.tape_begin, pc1 = G.tape_end;
-    const uint32_t n_src = G.n_src;
-    for (size_t base = (size_t)blockIdx.x * (V * TAPE_BLOCK); base < ngroups; base += (size_t)gridDim.x * (V * TAPE_BLOCK)) {
-        size_t idx[V];
-#pragma unroll
-        for (int j = 0; j < V; ++j) idx[j] = base + (size_t)j * TAPE_BLOCK + threadIdx.x;
-        // every source load of this pixel group is issued before the first use
-        float4 S[NS][V];
-#pragma unroll
-        for (int k = 0; k < NS; ++k)
-#pragma unroll
-            for (int j = 0; j < V; ++j)
-                S[k][j] = (k < (int)n_src) ? load_group(G.src[k], idx[j], nfull, tail) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 T[NT][V];
+    uint64_t policy = 0;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(&mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t w, int stage) {  // thread 0: start the loads of work item w
+        const uint32_t seg = w / tiles_per_plane, tile = w - seg * tiles_per_plane;
+        const unsigned long long px0 = (unsigned long long)tile * TILE_PX;
+        const KcSegment& G = A.seg[seg];
+        if (G.n_src == 0 || n - px0 < (unsigned long long)TILE_PX) return;  // ragged last tile: loaded cooperatively
+        mbar_expect_tx(&mbar[stage], G.n_src * TILE_B);
+        for (uint32_t k = 0; k < G.n_src; ++k)
+            tma_load_1d(stage_base + ((size_t)stage * ns_max + k) * TILE_PX, G.src[k] + px0, TILE_B, &mbar[stage], policy);
+    };
+
+    const uint32_t w0 = blockIdx.x, wstride = gridDim.x;
+    if (tid == 0)
+        for (int s = 0; s < stages - 1; ++s) {
+            const uint64_t w = (uint64_t)w0 + (uint64_t)s * wstride;
+            if (w < total_work) issue((uint32_t)w, s);
+        }
+    uint32_t phase_bits = 0;  // bit s: parity of stage s's next completion
+    uint32_t k_it = 0;
+    for (uint64_t w = w0; w < total_work; w += wstride, ++k_it) {
+        const int stage = (int)(k_it % (uint32_t)stages);
+        if (tid == 0) {
+            const uint64_t wn = w + (uint64_t)(stages - 1) * wstride;
+            if (wn < total_work) issue((uint32_t)wn, (int)((k_it + stages - 1) % (uint32_t)stages));
+        }
+        const uint32_t seg = (uint32_t)w / tiles_per_plane, tile = (uint32_t)w - seg * tiles_per_plane;
+        const unsigned long long px0 = (unsigned long long)tile * TILE_PX;
+        const unsigned long long rem = n - px0;
+        const bool full = rem >= (unsigned long long)TILE_PX;
+        const KcSegment& G = A.seg[seg];
+        float* sbuf = stage_base + (size_t)stage * ns_max * TILE_PX;
+        if (G.n_src) {
+            if (full) {
+                mbar_wait(&mbar[stage], (phase_bits >> stage) & 1u);
+                phase_bits ^= 1u << stage;
+            } else {
+                for (uint32_t k = 0; k < G.n_src; ++k)
+                    for (int i = tid; i < TILE_PX; i += TVM_THREADS)
+                        sbuf[(size_t)k * TILE_PX + i] = ((unsigned long long)i < rem) ? G.src[k][px0 + i] : 0.0f;
+                __syncthreads();
+            }
+        }
+        // ---- interpret the segment's tape over this tile ---------------------------------
         float4 acc[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int t = 0; t < NT; ++t) T[t][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        for (uint32_t pc = pc0; pc < pc1; ++pc) {
+        for (int j = 0; j < V; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t pc1 = G.tape_end;
+        for (uint32_t pc = G.tape_begin; pc < pc1; ++pc) {
             const uint32_t in = A.instr[pc];
             const uint32_t op = in & 0xffu;
             const uint32_t arg = (in >> 8) & 0xffu;
             if (op <= TOP_RPOW) {
                 float4 x[V];
-                // warp-uniform switch; constant indices keep S/T in registers
-#define KC_FETCH(arr, k) { _Pragma("unroll") for (int j = 0; j < V; ++j) x[j] = arr[k][j]; }
-                switch (arg) {
-                    case 0: KC_FETCH(S, 0) break;
-                    case 1: if (NS > 1) KC_FETCH(S, NS > 1 ? 1 : 0) break;
-                    case 2: if (NS > 2) KC_FETCH(S, NS > 2 ? 2 : 0) break;
-                    case 3: if (NS > 3) KC_FETCH(S, NS > 3 ? 3 : 0) break;
-                    case 4: if (NS > 4) KC_FETCH(S, NS > 4 ? 4 : 0) break;
-                    case 5: if (NS > 5) KC_FETCH(S, NS > 5 ? 5 : 0) break;
-                    case 6: if (NS > 6) KC_FETCH(S, NS > 6 ? 6 : 0) break;
-                    case 7: if (NS > 7) KC_FETCH(S, NS > 7 ? 7 : 0) break;
-                    case 8: KC_FETCH(T, 0) break;
-                    case 9: if (NT > 1) KC_FETCH(T, NT > 1 ? 1 : 0) break;
-                    case 10: if (NT > 2) KC_FETCH(T, NT > 2 ? 2 : 0) break;
-                    case 11: if (NT > 3) KC_FETCH(T, NT > 3 ? 3 : 0) break;
-                    case 12: if (NT > 4) KC_FETCH(T, NT > 4 ? 4 : 0) break;
-                    case 13: if (NT > 5) KC_FETCH(T, NT > 5 ? 5 : 0) break;
-                    default: {
-                        const float v = A.imm[pc];
+                if (arg == (uint32_t)KC_ARG_IMM) {
+                    const float v = A.imm[pc];
 #pragma unroll
-                        for (int j = 0; j < V; ++j) x[j] = make_float4(v, v, v, v);
-                    } break;
-                }
-#undef KC_FETCH
-                if (op == TOP_LD) {
-#pragma unroll
-                    for (int j = 0; j < V; ++j) acc[j] = x[j];
+                    for (int j = 0; j < V; ++j) x[j] = make_float4(v, v, v, v);
                 } else {
+                    const float* base = arg < (uint32_t)KC_ARG_TMP0 ? sbuf + (size_t)arg * TILE_PX : tmp_base + (size_t)(arg - KC_ARG_TMP0) * TILE_PX;
+                    const float4* xp = reinterpret_cast<const float4*>(base) + tid;
 #pragma unroll
-                    for (int j = 0; j < V; ++j) acc[j] = tape_binary<EXACT>(op, acc[j], x[j]);
+                    for (int j = 0; j < V; ++j) x[j] = xp[j * TVM_THREADS];
+                }
+                switch (op) {
+                    case TOP_LD:
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = x[j];
+                        break;
+                    case TOP_ADD:
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES(__fadd_rn, acc[j], x[j]);
+                        break;
+                    case TOP_SUB:
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES(__fsub_rn, acc[j], x[j]);
+                        break;
+                    case TOP_RSUB:
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES_R(__fsub_rn, acc[j], x[j]);
+                        break;
+                    case TOP_MUL:
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES(__fmul_rn, acc[j], x[j]);
+                        break;
+                    case TOP_DIV:
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES(__fdiv_rn, acc[j], x[j]);
+                        break;
+                    case TOP_RDIV:
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES_R(__fdiv_rn, acc[j], x[j]);
+                        break;
+                    case TOP_POW:
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = kc_pow4<EXACT>(acc[j], x[j]);
+                        break;
+                    default:  // TOP_RPOW
+#pragma unroll
+                        for (int j = 0; j < V; ++j) acc[j] = kc_pow4<EXACT>(x[j], acc[j]);
+                        break;
                 }
             } else if (op == TOP_ST_TMP) {
-#define KC_PUT(k) { _Pragma("unroll") for (int j = 0; j < V; ++j) T[k][j] = acc[j]; }
-                switch (arg) {
-                    case 0: KC_PUT(0) break;
-                    case 1: if (NT > 1) KC_PUT(NT > 1 ? 1 : 0) break;
-                    case 2: if (NT > 2) KC_PUT(NT > 2 ? 2 : 0) break;
-                    case 3: if (NT > 3) KC_PUT(NT > 3 ? 3 : 0) break;
-                    case 4: if (NT > 4) KC_PUT(NT > 4 ? 4 : 0) break;
-                    default: if (NT > 5) KC_PUT(NT > 5 ? 5 : 0) break;
-                }
-#undef KC_PUT
-            } else if (op == TOP_ST_OUT) {
-                float* o = G.out[arg];
+                float4* tp = reinterpret_cast<float4*>(tmp_base + (size_t)arg * TILE_PX) + tid;
 #pragma unroll
-                for (int j = 0; j < V; ++j) store_group(o, idx[j], acc[j], nfull, tail);
-            } else if (NT >= 3 || op == TOP_PACK_GRAY) {
+                for (int j = 0; j < V; ++j) tp[j * TVM_THREADS] = acc[j];
+            } else if (op == TOP_ST_OUT) {
+                float* o = G.out[arg] + px0;
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) __stcs(reinterpret_cast<float4*>(o) + j * TVM_THREADS + tid, acc[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        const unsigned long long p = 4ull * (unsigned long long)(j * TVM_THREADS + tid);
+                        if (p + 3 < rem) __stcs(reinterpret_cast<float4*>(o + p), acc[j]);
+                        else if (p < rem) {
+                            o[p] = acc[j].x;
+                            if (p + 1 < rem) o[p + 1] = acc[j].y;
+                            if (p + 2 < rem) o[p + 2] = acc[j].z;
+                        }
+                    }
+                }
+            } else {  // RGBA8 export
+                const float4* t0 = reinterpret_cast<const float4*>(tmp_base) + tid;
+                const float4* t1 = reinterpret_cast<const float4*>(tmp_base + TILE_PX) + tid;
+                const float4* t2 = reinterpret_cast<const float4*>(tmp_base + 2 * TILE_PX) + tid;
+                uint32_t* o = G.out_rgba8 + px0;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     uint32_t px[4];
                     if (op == TOP_PACK_RGBA) {
-                        const float4 tr = T[0][j], tg = T[NT > 1 ? 1 : 0][j], tb = T[NT > 2 ? 2 : 0][j];
+                        const float4 tr = t0[j * TVM_THREADS], tg = t1[j * TVM_THREADS], tb = t2[j * TVM_THREADS];
                         const float r[4] = {tr.x, tr.y, tr.z, tr.w};
                         const float g[4] = {tg.x, tg.y, tg.z, tg.w};
                         const float b[4] = {tb.x, tb.y, tb.z, tb.w};
@@ -350,10 +437,17 @@ __global__ void __launch_bounds__(TAPE_BLOCK, MINB) kc_tape_kernel(const __grid_
                             px[l] = u | (u << 8) | (u << 16) | 0xff000000u;
                         }
                     }
-                    store_group_u32(G.out_rgba8, idx[j], make_uint4(px[0], px[1], px[2], px[3]), nfull, tail);
+                    const unsigned long long p = 4ull * (unsigned long long)(j * TVM_THREADS + tid);
+                    if (p + 3 < rem) __stcs(reinterpret_cast<uint4*>(o + p), make_uint4(px[0], px[1], px[2], px[3]));
+                    else if (p < rem) {
+                        o[p] = px[0];
+                        if (p + 1 < rem) o[p + 1] = px[1];
+                        if (p + 2 < rem) o[p + 2] = px[2];
+                    }
                 }
             }
         }
+        __syncthreads();  // the stage (and the temporaries) may be overwritten from here on
     }
 }
 
@@ -405,28 +499,57 @@ inline int grid_for(kc_context* ctx, size_t work_items, int block, int ctas_per_
     return (int)(want < cap ? want : cap);
 }
 
-template <bool EXACT>
-void launch_tape_variant(const KcTapeArgs& a, dim3 grid, cudaStream_t st) {
-    switch (a.variant) {
-        case 0: kc_tape_kernel<EXACT, 2, 2, 2, 2><<<grid, TAPE_BLOCK, 0, st>>>(a); break;
-        case 1: kc_tape_kernel<EXACT, 4, 3, 2, 2><<<grid, TAPE_BLOCK, 0, st>>>(a); break;
-        default: kc_tape_kernel<EXACT, KC_MAX_SRC, KC_MAX_TMP, 1, 2><<<grid, TAPE_BLOCK, 0, st>>>(a); break;
+template <bool EXACT, int V>
+int32_t launch_tile_vm(kc_context* ctx, const KcTapeArgs& a, int stages, int ns_max, int nt_max) {
+    constexpr int TILE_PX = 1024 * V;
+    const size_t smem = 128 + (size_t)(stages * ns_max + nt_max) * TILE_PX * 4;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        KC_CUDA(cudaFuncSetAttribute(kc_tile_vm_kernel<EXACT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
     }
+    const uint64_t tiles = (a.n + TILE_PX - 1) / TILE_PX;
+    const uint64_t total = tiles * a.n_seg;
+    if (total > 0xffffffffull) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane too large for one launch");
+    const int ctas_per_sm = smem <= 113 * 1024 ? 2 : 1;
+    const uint64_t grid = std::min<uint64_t>(total, (uint64_t)ctx->sm_count * ctas_per_sm);
+    kc_tile_vm_kernel<EXACT, V><<<(unsigned)grid, TVM_THREADS, smem, ctx->stream>>>(a, stages, ns_max, (uint32_t)tiles, (uint32_t)total);
+    return KC_OK;
 }
 
 }  // namespace
 
 int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     if (args.n == 0 || args.n_seg == 0) return KC_OK;
-    const int v = args.variant <= 1 ? 2 : 1;
-    const size_t groups = (size_t)((args.n + 3) >> 2);
-    // a whole number of CTAs per SM across all segments; grid-stride loop inside
-    const int per_seg_cap = std::max(1, (ctx->sm_count * 8) / (int)args.n_seg);
-    size_t want = (groups + (size_t)v * TAPE_BLOCK - 1) / ((size_t)v * TAPE_BLOCK);
-    dim3 grid((unsigned)std::min<size_t>(std::max<size_t>(want, 1), (size_t)per_seg_cap), args.n_seg);
+    int ns_max = 0, nt_max = 0;
+    for (uint32_t s = 0; s < args.n_seg; ++s) ns_max = std::max<int>(ns_max, (int)args.seg[s].n_src);
+    nt_max = (int)args.variant;  // temporaries the tapes touch (set by the planner)
+    // tile size / pipeline depth: the largest tile that leaves room for >= 2 stages and 2 CTAs per SM
+    static const int force_v = getenv("KC_TILE_V") ? atoi(getenv("KC_TILE_V")) : 0;
+    static const int force_stages = getenv("KC_STAGES") ? atoi(getenv("KC_STAGES")) : 0;
+    const size_t budget = 113 * 1024 - 128;
+    int v = 1, stages = 2;
+    bool found = false;
+    for (int cand : {4, 2, 1}) {
+        if (force_v && cand != force_v) continue;
+        const size_t tile_b = (size_t)4096 * cand;
+        for (int st = 4; st >= 2; --st) {
+            if (force_stages && st != force_stages) continue;
+            if ((size_t)(st * ns_max + nt_max) * tile_b <= budget) { v = cand; stages = st; found = true; break; }
+        }
+        if (found) break;
+    }
+    if (!found) { v = force_v ? force_v : 1; stages = force_stages ? force_stages : 2; }
+    if (ns_max == 0) stages = 2;
+    // small planes: do not use a tile bigger than the plane needs
+    while (v > 1 && args.n <= (unsigned long long)512 * v) v >>= 1;
     KcTimed timed(ctx, KC_KERNEL_TAPE);
-    if (ctx->opts.math_mode == KC_MATH_EXACT) launch_tape_variant<true>(args, grid, ctx->stream);
-    else launch_tape_variant<false>(args, grid, ctx->stream);
+    int32_t rc;
+    const bool exact = ctx->opts.math_mode == KC_MATH_EXACT;
+    if (v == 4) rc = exact ? launch_tile_vm<true, 4>(ctx, args, stages, ns_max, nt_max) : launch_tile_vm<false, 4>(ctx, args, stages, ns_max, nt_max);
+    else if (v == 2) rc = exact ? launch_tile_vm<true, 2>(ctx, args, stages, ns_max, nt_max) : launch_tile_vm<false, 2>(ctx, args, stages, ns_max, nt_max);
+    else rc = exact ? launch_tile_vm<true, 1>(ctx, args, stages, ns_max, nt_max) : launch_tile_vm<false, 1>(ctx, args, stages, ns_max, nt_max);
+    KC_TRY(rc);
     KC_CUDA(cudaGetLastError());
     ctx->kernel_launches++;
     ctx->run_kernels++;
