@@ -268,7 +268,7 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 
 template <bool EXACT, int V>
-__global__ void __launch_bounds__(TVM_THREADS, 2)
+__global__ void __launch_bounds__(TVM_THREADS, 2)  // <= 128 registers: two CTAs per SM
     kc_tile_vm_kernel(const __grid_constant__ KcTapeArgs A, int stages, int ns_max, uint32_t tiles_per_plane, uint32_t total_work) {
     constexpr int TILE_PX = 1024 * V;
     constexpr uint32_t TILE_B = TILE_PX * 4;
@@ -511,7 +511,8 @@ int32_t launch_tile_vm(kc_context* ctx, const KcTapeArgs& a, int stages, int ns_
     const uint64_t tiles = (a.n + TILE_PX - 1) / TILE_PX;
     const uint64_t total = tiles * a.n_seg;
     if (total > 0xffffffffull) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane too large for one launch");
-    const int ctas_per_sm = smem <= 113 * 1024 ? 2 : 1;
+    static const int ctas_target = getenv("KC_CTAS") ? atoi(getenv("KC_CTAS")) : 2;
+    const int ctas_per_sm = std::max<int>(1, std::min<int>(ctas_target, (int)((227 * 1024) / (smem + 1024))));
     const uint64_t grid = std::min<uint64_t>(total, (uint64_t)ctx->sm_count * ctas_per_sm);
     kc_tile_vm_kernel<EXACT, V><<<(unsigned)grid, TVM_THREADS, smem, ctx->stream>>>(a, stages, ns_max, (uint32_t)tiles, (uint32_t)total);
     return KC_OK;
@@ -527,19 +528,22 @@ int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     // tile size / pipeline depth: the largest tile that leaves room for >= 2 stages and 2 CTAs per SM
     static const int force_v = getenv("KC_TILE_V") ? atoi(getenv("KC_TILE_V")) : 0;
     static const int force_stages = getenv("KC_STAGES") ? atoi(getenv("KC_STAGES")) : 0;
-    const size_t budget = 113 * 1024 - 128;
+    static const int ctas_target = getenv("KC_CTAS") ? atoi(getenv("KC_CTAS")) : 2;
+    const size_t budget = (size_t)(227 * 1024) / (size_t)std::max(1, ctas_target) - 1024 - 128;
     int v = 1, stages = 2;
     bool found = false;
-    for (int cand : {4, 2, 1}) {
-        if (force_v && cand != force_v) continue;
-        const size_t tile_b = (size_t)4096 * cand;
-        for (int st = 4; st >= 2; --st) {
-            if (force_stages && st != force_stages) continue;
-            if ((size_t)(st * ns_max + nt_max) * tile_b <= budget) { v = cand; stages = st; found = true; break; }
+    for (int pass = 0; pass < 2 && !found; ++pass) {  // pass 0 honours the tuning overrides, pass 1 ignores them
+        for (int cand : {4, 2, 1}) {
+            if (pass == 0 && force_v && cand != force_v) continue;
+            const size_t tile_b = (size_t)4096 * cand;
+            for (int st = 4; st >= 2; --st) {
+                if (pass == 0 && force_stages && st != force_stages) continue;
+                if ((size_t)(st * ns_max + nt_max) * tile_b <= budget) { v = cand; stages = st; found = true; break; }
+            }
+            if (found) break;
         }
-        if (found) break;
     }
-    if (!found) { v = force_v ? force_v : 1; stages = force_stages ? force_stages : 2; }
+    if (!found) { v = 1; stages = 2; }
     if (ns_max == 0) stages = 2;
     // small planes: do not use a tile bigger than the plane needs
     while (v > 1 && args.n <= (unsigned long long)512 * v) v >>= 1;
