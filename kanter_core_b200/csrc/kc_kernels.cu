@@ -151,9 +151,12 @@ __device__ __forceinline__ float kc_pow_exact(float x, float y) {
 // FAST: x^y = 2^(y*log2 x) on the special-function unit for positive normal x
 // and |y| <= 16, with the exponent product split so its rounding error does not
 // scale with |log2 x| (x = m*2^e, m in [sqrt(.5), sqrt(2)); t = y*e + y*log2 m).
-// Branch-free; `bad` collects the lanes whose inputs fall outside that domain
-// (they are redone with the exact routine).  ~4e-7 relative error.
-__device__ __forceinline__ float kc_pow_fast_core(float x, float y, bool& bad) {
+// Branch-free.  `rc`, `ay`, `ap` return the three quantities whose range decides
+// whether the result is valid (checked once per float4 by the caller):
+//   rc = bits(x) - bits(2^-126)  must be < 0x7f000000 (x positive, normal, finite)
+//   ay = |y| <= 16,  ap = |y*e| < 100.
+// +0 ^ positive (black pixels) is answered here: 0.  ~4e-7 relative error.
+__device__ __forceinline__ float kc_pow_fast_core(float x, float y, uint32_t& rc, float& ay, float& ap) {
     const uint32_t ix = __float_as_uint(x);
     const uint32_t top = (ix - 0x3f3504f3u) & 0xff800000u;
     const float m = __uint_as_float(ix - top);
@@ -168,19 +171,20 @@ __device__ __forceinline__ float kc_pow_fast_core(float x, float y, bool& bad) {
     float e2;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(f));
     const float s = __int_as_float((__float_as_int(t) << 23) + 0x3f800000);  // 2^n
-    float r = e2 * s;
-    const bool zero_pos = (ix == 0u) && (y > 0.0f);                 // +0 ^ positive = +0 (black pixels)
-    r = zero_pos ? 0.0f : r;
-    bad = !zero_pos && ((ix - 0x00800000u >= 0x7f000000u) || !(fabsf(y) <= 16.0f) || !(fabsf(p1) < 100.0f));
-    return r;
+    const bool zero_pos = (ix == 0u) & (y > 0.0f);
+    rc = zero_pos ? 0u : ix - 0x00800000u;
+    ay = fabsf(y);
+    ap = zero_pos ? 0.0f : fabsf(p1);
+    return zero_pos ? 0.0f : e2 * s;
 }
 
 template <bool EXACT>
 __device__ __forceinline__ float kc_pow(float a, float b) {
     if (EXACT) return kc_pow_exact(a, b);
-    bool bad;
-    const float r = kc_pow_fast_core(a, b, bad);
-    return bad ? kc_pow_exact_call(a, b) : r;
+    uint32_t rc; float ay, ap;
+    const float r = kc_pow_fast_core(a, b, rc, ay, ap);
+    const bool ok = (rc < 0x7f000000u) & (ay <= 16.0f) & (ap < 100.0f);
+    return ok ? r : kc_pow_exact_call(a, b);
 }
 
 // SlotImage::f32_to_u8, src/slot_image.rs:142-145:
@@ -209,14 +213,20 @@ __device__ __forceinline__ uint32_t kc_to_u8_srgb(float v) {
 template <bool EXACT>
 __device__ __forceinline__ float4 kc_pow4(float4 a, float4 b) {
     if (EXACT) return make_float4(kc_pow_exact(a.x, b.x), kc_pow_exact(a.y, b.y), kc_pow_exact(a.z, b.z), kc_pow_exact(a.w, b.w));
-    bool b0, b1, b2, b3;
-    float4 r = make_float4(kc_pow_fast_core(a.x, b.x, b0), kc_pow_fast_core(a.y, b.y, b1), kc_pow_fast_core(a.z, b.z, b2),
-                           kc_pow_fast_core(a.w, b.w, b3));
-    if (b0 | b1 | b2 | b3) {
-        if (b0) r.x = kc_pow_exact_call(a.x, b.x);
-        if (b1) r.y = kc_pow_exact_call(a.y, b.y);
-        if (b2) r.z = kc_pow_exact_call(a.z, b.z);
-        if (b3) r.w = kc_pow_exact_call(a.w, b.w);
+    uint32_t c0, c1, c2, c3;
+    float y0, y1, y2, y3, p0, p1, p2, p3;
+    float4 r = make_float4(kc_pow_fast_core(a.x, b.x, c0, y0, p0), kc_pow_fast_core(a.y, b.y, c1, y1, p1),
+                           kc_pow_fast_core(a.z, b.z, c2, y2, p2), kc_pow_fast_core(a.w, b.w, c3, y3, p3));
+    // one validity test for the four lanes (NaNs fail the float comparisons)
+    const uint32_t cm = max(max(c0, c1), max(c2, c3));
+    const float ym = fmaxf(fmaxf(y0, y1), fmaxf(y2, y3));
+    const float pm = fmaxf(fmaxf(p0, p1), fmaxf(p2, p3));
+    const bool nan_in = (y0 != y0) | (y1 != y1) | (y2 != y2) | (y3 != y3);  // fmaxf drops NaNs; |y*e| is NaN only if y is
+    if (!((cm < 0x7f000000u) & (ym <= 16.0f) & (pm < 100.0f)) | nan_in) {
+        if (!((c0 < 0x7f000000u) & (y0 <= 16.0f) & (p0 < 100.0f))) r.x = kc_pow_exact_call(a.x, b.x);
+        if (!((c1 < 0x7f000000u) & (y1 <= 16.0f) & (p1 < 100.0f))) r.y = kc_pow_exact_call(a.y, b.y);
+        if (!((c2 < 0x7f000000u) & (y2 <= 16.0f) & (p2 < 100.0f))) r.z = kc_pow_exact_call(a.z, b.z);
+        if (!((c3 < 0x7f000000u) & (y3 <= 16.0f) & (p3 < 100.0f))) r.w = kc_pow_exact_call(a.w, b.w);
     }
     return r;
 }
@@ -267,8 +277,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
-template <bool EXACT, int V>
-__global__ void __launch_bounds__(TVM_THREADS, 2)  // <= 128 registers: two CTAs per SM
+template <bool EXACT, int V, int MINB>
+__global__ void __launch_bounds__(TVM_THREADS, MINB)
     kc_tile_vm_kernel(const __grid_constant__ KcTapeArgs A, int stages, int ns_max, uint32_t tiles_per_plane, uint32_t total_work) {
     constexpr int TILE_PX = 1024 * V;
     constexpr uint32_t TILE_B = TILE_PX * 4;
@@ -499,60 +509,69 @@ inline int grid_for(kc_context* ctx, size_t work_items, int block, int ctas_per_
     return (int)(want < cap ? want : cap);
 }
 
-template <bool EXACT, int V>
-int32_t launch_tile_vm(kc_context* ctx, const KcTapeArgs& a, int stages, int ns_max, int nt_max) {
+template <bool EXACT, int V, int MINB>
+int32_t launch_tile_vm(kc_context* ctx, const KcTapeArgs& a, int stages, int ns_max, int nt_max, int ctas_per_sm) {
     constexpr int TILE_PX = 1024 * V;
     const size_t smem = 128 + (size_t)(stages * ns_max + nt_max) * TILE_PX * 4;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
-        KC_CUDA(cudaFuncSetAttribute(kc_tile_vm_kernel<EXACT, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KC_CUDA(cudaFuncSetAttribute(kc_tile_vm_kernel<EXACT, V, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set = true;
     }
     const uint64_t tiles = (a.n + TILE_PX - 1) / TILE_PX;
     const uint64_t total = tiles * a.n_seg;
     if (total > 0xffffffffull) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane too large for one launch");
-    static const int ctas_target = getenv("KC_CTAS") ? atoi(getenv("KC_CTAS")) : 2;
-    const int ctas_per_sm = std::max<int>(1, std::min<int>(ctas_target, (int)((227 * 1024) / (smem + 1024))));
+    // persistent grid: one CTA per resident slot, each walks work items w, w+grid, ...
     const uint64_t grid = std::min<uint64_t>(total, (uint64_t)ctx->sm_count * ctas_per_sm);
-    kc_tile_vm_kernel<EXACT, V><<<(unsigned)grid, TVM_THREADS, smem, ctx->stream>>>(a, stages, ns_max, (uint32_t)tiles, (uint32_t)total);
+    kc_tile_vm_kernel<EXACT, V, MINB><<<(unsigned)grid, TVM_THREADS, smem, ctx->stream>>>(a, stages, ns_max, (uint32_t)tiles, (uint32_t)total);
     return KC_OK;
+}
+
+struct TvmConfig { int v, ctas, stages; };
+
+// Tile size, CTAs per SM and pipeline depth for a launch with ns_max sources and
+// nt_max shared-memory temporaries per segment.  Measured on B200 (profiles/):
+// 4096-pixel tiles beat smaller ones (the dispatch is amortised over 16 pixels per
+// thread), 3 resident CTAs beat 2 beat 1, and 2 stages are as good as 4.
+TvmConfig pick_config(int ns_max, int nt_max, unsigned long long n) {
+    static const int force_v = getenv("KC_TILE_V") ? atoi(getenv("KC_TILE_V")) : 0;
+    static const int force_stages = getenv("KC_STAGES") ? atoi(getenv("KC_STAGES")) : 0;
+    static const int force_ctas = getenv("KC_CTAS") ? atoi(getenv("KC_CTAS")) : 0;
+    static const TvmConfig order[] = {{4, 3, 0}, {4, 2, 0}, {2, 3, 0}, {2, 2, 0}, {1, 3, 0}, {1, 2, 0}, {4, 1, 0}, {2, 1, 0}, {1, 1, 0}};
+    for (int pass = 0; pass < 2; ++pass) {  // pass 0 honours the tuning overrides, pass 1 ignores them
+        for (const TvmConfig& c : order) {
+            if (pass == 0 && ((force_v && c.v != force_v) || (force_ctas && c.ctas != force_ctas))) continue;
+            // do not use a tile (much) bigger than the plane
+            if (c.v > 1 && n <= (unsigned long long)512 * c.v) continue;
+            const size_t budget = (size_t)(227 * 1024) / (size_t)c.ctas - 1024 - 128;
+            const size_t tile_b = (size_t)4096 * c.v;
+            for (int st = 4; st >= 2; --st) {
+                if (pass == 0 && force_stages && st != force_stages) continue;
+                if (!force_stages && ns_max > 0 && st > 2 && c.ctas >= 2 && (size_t)(st * ns_max + nt_max) * tile_b > budget) continue;
+                if ((size_t)(st * ns_max + nt_max) * tile_b <= budget) return TvmConfig{c.v, c.ctas, ns_max == 0 ? 2 : st};
+            }
+        }
+    }
+    return TvmConfig{1, 1, 2};
 }
 
 }  // namespace
 
 int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     if (args.n == 0 || args.n_seg == 0) return KC_OK;
-    int ns_max = 0, nt_max = 0;
+    int ns_max = 0;
     for (uint32_t s = 0; s < args.n_seg; ++s) ns_max = std::max<int>(ns_max, (int)args.seg[s].n_src);
-    nt_max = (int)args.variant;  // temporaries the tapes touch (set by the planner)
-    // tile size / pipeline depth: the largest tile that leaves room for >= 2 stages and 2 CTAs per SM
-    static const int force_v = getenv("KC_TILE_V") ? atoi(getenv("KC_TILE_V")) : 0;
-    static const int force_stages = getenv("KC_STAGES") ? atoi(getenv("KC_STAGES")) : 0;
-    static const int ctas_target = getenv("KC_CTAS") ? atoi(getenv("KC_CTAS")) : 2;
-    const size_t budget = (size_t)(227 * 1024) / (size_t)std::max(1, ctas_target) - 1024 - 128;
-    int v = 1, stages = 2;
-    bool found = false;
-    for (int pass = 0; pass < 2 && !found; ++pass) {  // pass 0 honours the tuning overrides, pass 1 ignores them
-        for (int cand : {4, 2, 1}) {
-            if (pass == 0 && force_v && cand != force_v) continue;
-            const size_t tile_b = (size_t)4096 * cand;
-            for (int st = 4; st >= 2; --st) {
-                if (pass == 0 && force_stages && st != force_stages) continue;
-                if ((size_t)(st * ns_max + nt_max) * tile_b <= budget) { v = cand; stages = st; found = true; break; }
-            }
-            if (found) break;
-        }
-    }
-    if (!found) { v = 1; stages = 2; }
-    if (ns_max == 0) stages = 2;
-    // small planes: do not use a tile bigger than the plane needs
-    while (v > 1 && args.n <= (unsigned long long)512 * v) v >>= 1;
+    const int nt_max = (int)args.variant;  // temporaries the tapes touch (set by the planner)
+    const TvmConfig c = pick_config(ns_max, nt_max, args.n);
     KcTimed timed(ctx, KC_KERNEL_TAPE);
     int32_t rc;
     const bool exact = ctx->opts.math_mode == KC_MATH_EXACT;
-    if (v == 4) rc = exact ? launch_tile_vm<true, 4>(ctx, args, stages, ns_max, nt_max) : launch_tile_vm<false, 4>(ctx, args, stages, ns_max, nt_max);
-    else if (v == 2) rc = exact ? launch_tile_vm<true, 2>(ctx, args, stages, ns_max, nt_max) : launch_tile_vm<false, 2>(ctx, args, stages, ns_max, nt_max);
-    else rc = exact ? launch_tile_vm<true, 1>(ctx, args, stages, ns_max, nt_max) : launch_tile_vm<false, 1>(ctx, args, stages, ns_max, nt_max);
+    const bool three = c.ctas >= 3;
+#define KC_TVM(E, VV) (three ? launch_tile_vm<E, VV, 3>(ctx, args, c.stages, ns_max, nt_max, c.ctas) : launch_tile_vm<E, VV, 2>(ctx, args, c.stages, ns_max, nt_max, c.ctas))
+    if (c.v == 4) rc = exact ? KC_TVM(true, 4) : KC_TVM(false, 4);
+    else if (c.v == 2) rc = exact ? KC_TVM(true, 2) : KC_TVM(false, 2);
+    else rc = exact ? KC_TVM(true, 1) : KC_TVM(false, 1);
+#undef KC_TVM
     KC_TRY(rc);
     KC_CUDA(cudaGetLastError());
     ctx->kernel_launches++;
