@@ -215,6 +215,9 @@ int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_
 /* same, result left in device memory (w*h*4 bytes, caller-owned) */
 int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, int32_t srgb, void* device_rgba8);
 int32_t kc_image_download(kc_context* ctx, const kc_image* in, float* const* host_planes);
+/* turn the image's lazily evaluated planes into pixels in HBM with one fused launch;
+ * constant planes stay descriptors unless include_constants is set */
+int32_t kc_image_materialize(kc_context* ctx, const kc_image* in, int32_t include_constants);
 int32_t kc_image_retain(const kc_image* img);
 int32_t kc_image_release(kc_image* img);
 

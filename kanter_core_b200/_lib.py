@@ -105,6 +105,7 @@ SIGNATURES = {
     "kc_image_to_u8": (i32, [vp, P(kc_image), i32, vp]),
     "kc_image_to_u8_device": (i32, [vp, P(kc_image), i32, vp]),
     "kc_image_download": (i32, [vp, P(kc_image), P(vp)]),
+    "kc_image_materialize": (i32, [vp, P(kc_image), i32]),
     "kc_image_retain": (i32, [P(kc_image)]),
     "kc_image_release": (i32, [P(kc_image)]),
     "kc_mix": (i32, [vp, i32, P(kc_image), P(kc_image), P(kc_image)]),

@@ -6,6 +6,7 @@
 // 188-247).  Planes are f32, row-major, one allocation per channel, in HBM,
 // immutable once written, reference counted.  Constant planes (`vec![v; n]`)
 // stay descriptors until somebody needs their pixels.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -454,6 +455,21 @@ extern "C" int32_t kc_image_download(kc_context* ctx, const kc_image* in, float*
     }
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
     return KC_OK;
+}
+
+extern "C" int32_t kc_image_materialize(kc_context* ctx, const kc_image* in, int32_t include_constants) {
+    // make the image's planes real pixels in HBM with one fused launch (lazy
+    // expression planes always; constant descriptors only on request)
+    if (!ctx || !in) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    std::vector<kc_plane*> roots;
+    for (int c = 0; c < kci_nplanes(in); ++c) {
+        kc_plane* p = in->planes[c];
+        if (!p) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "plane %d is NULL", c);
+        const bool want = p->kind == KC_PLANE_EXPR || (p->kind == KC_PLANE_CONST && include_constants);
+        if (want && std::find(roots.begin(), roots.end(), p) == roots.end()) roots.push_back(p);
+    }
+    return roots.empty() ? KC_OK : kcp_force(ctx, roots.data(), roots.size());
 }
 
 extern "C" int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, int32_t srgb, void* device_rgba8) {

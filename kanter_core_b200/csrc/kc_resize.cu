@@ -14,6 +14,7 @@
 // multiply and add roundings (EXACT) or FMA (FAST).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "kc_internal.h"
 
@@ -172,6 +173,93 @@ __global__ void __launch_bounds__(256) kc_resize_h_kernel(const float* __restric
     }
 }
 
+// ---------------------------------------------------------------------------
+// Fused V∘H tile kernel for resizes whose tap windows are short (<= FT_MAXT taps
+// per axis: every upsampling, and mild downsampling).  One CTA produces a
+// FT_TW x FT_TH tile of the output: it stages the source patch the tile depends on
+// in shared memory, runs the vertical pass for the tile's rows into a second
+// shared-memory buffer (the unclamped f32 intermediate of the reference, never
+// written to HBM), then each thread owns one output column: its horizontal
+// weights sit in registers and it walks down the tile's rows, so a row of the
+// tile is one coalesced 128-byte store per warp.  Same operation order as the
+// two-pass kernels: vertical taps top to bottom, then horizontal taps left to
+// right, clamp to [0,1] last.
+// ---------------------------------------------------------------------------
+constexpr int FT_TW = 256;   // output columns per CTA (one per thread)
+constexpr int FT_TH = 32;    // output rows per CTA
+constexpr int FT_MAXT = 8;   // taps per axis this kernel supports
+
+template <bool EXACT>
+__global__ void __launch_bounds__(FT_TW) kc_resize_fused_kernel(const float* __restrict__ src, uint32_t sw, uint32_t sh,
+                                                                float* __restrict__ dst, uint32_t dw, uint32_t dh,
+                                                                const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount,
+                                                                const float* __restrict__ vw, const uint32_t* __restrict__ hleft,
+                                                                const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
+                                                                uint32_t pcols, uint32_t prows) {
+    extern __shared__ float fsm[];
+    float* S = fsm;                                   // [prows][pcols]   source patch
+    float* Tm = S + (size_t)prows * pcols;            // [FT_TH][pcols]   vertical-pass result
+    float* Wv = Tm + (size_t)FT_TH * pcols;           // [FT_TH][FT_MAXT] vertical weights of the tile's rows
+    __shared__ uint32_t vl[FT_TH], vc[FT_TH];
+    const int tid = threadIdx.x;
+    const uint32_t ox0 = blockIdx.x * FT_TW, oy0 = blockIdx.y * FT_TH;
+    const uint32_t oxl = min(ox0 + FT_TW, dw) - 1, oyl = min(oy0 + FT_TH, dh) - 1;  // last valid column / row
+    const uint32_t nrow = oyl - oy0 + 1;
+    // source window of the tile (left[] and left[]+count[] are non-decreasing in o)
+    const uint32_t cx0 = hleft[ox0], cx1 = hleft[oxl] + hcount[oxl];
+    const uint32_t ry0 = vleft[oy0], ry1 = vleft[oyl] + vcount[oyl];
+    const uint32_t ncx = cx1 - cx0, nry = ry1 - ry0;
+    if (tid < (int)nrow) {
+        vl[tid] = vleft[oy0 + tid] - ry0;
+        vc[tid] = vcount[oy0 + tid];
+    }
+    for (int i = tid; i < (int)nrow * FT_MAXT; i += FT_TW) {
+        const int r = i / FT_MAXT, k = i - r * FT_MAXT;
+        Wv[i] = vw[(size_t)k * dh + oy0 + r];  // tap-major table; entries past count are 0 and never used
+    }
+    for (uint32_t i = tid; i < nry * ncx; i += FT_TW) {
+        const uint32_t r = i / ncx, c = i - r * ncx;
+        S[r * pcols + c] = __ldg(src + (size_t)(ry0 + r) * sw + cx0 + c);
+    }
+    __syncthreads();
+    // vertical pass: Tm[r][c] = sum_i S[vl[r]+i][c] * Wv[r][i]
+    for (uint32_t i = tid; i < nrow * ncx; i += FT_TW) {
+        const uint32_t r = i / ncx, c = i - r * ncx;
+        const uint32_t l = vl[r], n = vc[r];
+        float acc = 0.0f;
+        for (uint32_t k = 0; k < n; ++k) acc = tap<EXACT>(acc, S[(l + k) * pcols + c], Wv[r * FT_MAXT + k]);
+        Tm[r * pcols + c] = acc;
+    }
+    __syncthreads();
+    // horizontal pass: one output column per thread
+    const uint32_t ox = ox0 + tid;
+    if (ox > oxl) return;
+    const uint32_t l = hleft[ox] - cx0, n = hcount[ox];
+    float w[FT_MAXT];
+#pragma unroll
+    for (int j = 0; j < FT_MAXT; ++j) w[j] = (uint32_t)j < n ? hw[(size_t)j * dw + ox] : 0.0f;
+    float* out = dst + (size_t)oy0 * dw + ox;
+    for (uint32_t r = 0; r < nrow; ++r) {
+        const float* t = Tm + r * pcols + l;
+        float acc = 0.0f;
+#pragma unroll
+        for (int j = 0; j < FT_MAXT; ++j)
+            if ((uint32_t)j < n) acc = tap<EXACT>(acc, t[j], w[j]);
+        acc = acc < 0.0f ? 0.0f : (acc > 1.0f ? 1.0f : acc);  // image::math::utils::clamp keeps NaN
+        __stcs(out + (size_t)r * dw, acc);
+    }
+}
+
+// largest source window any tile of FT_T output elements touches along one axis
+uint32_t max_window(const KcAxisTable& t, uint32_t tile) {
+    uint32_t mx = 0;
+    for (uint32_t o0 = 0; o0 < t.dst_len; o0 += tile) {
+        const uint32_t ol = std::min(o0 + tile, t.dst_len) - 1;
+        mx = std::max(mx, t.h_left[ol] + t.h_count[ol] - t.h_left[o0]);
+    }
+    return mx;
+}
+
 }  // namespace
 
 int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,
@@ -181,6 +269,35 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
     std::shared_ptr<KcAxisTable> tv, th;
     KC_TRY(get_axis(ctx, sh, dh, filter, tv));
     KC_TRY(get_axis(ctx, sw, dw, filter, th));
+    const bool exact_mode = ctx->opts.math_mode == KC_MATH_EXACT;
+    static const bool no_fused = getenv("KC_RESIZE_TWO_PASS") != nullptr;
+    if (!no_fused && tv->max_taps <= (uint32_t)FT_MAXT && th->max_taps <= (uint32_t)FT_MAXT) {
+        const uint32_t pcols = max_window(*th, FT_TW) | 1u;  // odd row pitch: no systematic bank conflicts
+        const uint32_t prows = max_window(*tv, FT_TH);
+        const size_t smem = sizeof(float) * ((size_t)prows * pcols + (size_t)FT_TH * pcols + (size_t)FT_TH * FT_MAXT);
+        if (smem <= 200 * 1024) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                KC_CUDA(cudaFuncSetAttribute(kc_resize_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                KC_CUDA(cudaFuncSetAttribute(kc_resize_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                attr_set = true;
+            }
+            dim3 grid((dw + FT_TW - 1) / FT_TW, (dh + FT_TH - 1) / FT_TH);
+            if (grid.y <= 65535u) {
+                KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
+                if (exact_mode)
+                    kc_resize_fused_kernel<true><<<grid, FT_TW, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights,
+                                                                                      th->d_left, th->d_count, th->d_weights, pcols, prows);
+                else
+                    kc_resize_fused_kernel<false><<<grid, FT_TW, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights,
+                                                                                       th->d_left, th->d_count, th->d_weights, pcols, prows);
+                KC_CUDA(cudaGetLastError());
+                ctx->kernel_launches++;
+                ctx->run_kernels++;
+                return KC_OK;
+            }
+        }
+    }
     float* tmp = nullptr;
     KC_CUDA(cudaMallocAsync((void**)&tmp, sizeof(float) * (size_t)sw * dh, ctx->stream));
     const bool exact = ctx->opts.math_mode == KC_MATH_EXACT;
