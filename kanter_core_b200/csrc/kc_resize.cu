@@ -185,68 +185,115 @@ __global__ void __launch_bounds__(256) kc_resize_h_kernel(const float* __restric
 // two-pass kernels: vertical taps top to bottom, then horizontal taps left to
 // right, clamp to [0,1] last.
 // ---------------------------------------------------------------------------
-constexpr int FT_TW = 256;   // output columns per CTA (one per thread)
-constexpr int FT_TH = 32;    // output rows per CTA
-constexpr int FT_MAXT = 8;   // taps per axis this kernel supports
+constexpr int FT_THREADS = 128;
+constexpr int FT_CPT = 4;                    // consecutive output columns per thread (one float4 store per row)
+constexpr int FT_TW = FT_THREADS * FT_CPT;   // output columns per CTA
+constexpr int FT_TH = 16;                    // output rows per CTA
+constexpr int FT_MAXT = 8;                   // taps per axis this kernel supports
+constexpr int FT_TP = FT_TH + 4;             // pitch of the column-major intermediate: 16-byte aligned, conflict-free
 
 template <bool EXACT>
-__global__ void __launch_bounds__(FT_TW) kc_resize_fused_kernel(const float* __restrict__ src, uint32_t sw, uint32_t sh,
-                                                                float* __restrict__ dst, uint32_t dw, uint32_t dh,
-                                                                const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount,
-                                                                const float* __restrict__ vw, const uint32_t* __restrict__ hleft,
-                                                                const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
-                                                                uint32_t pcols, uint32_t prows) {
-    extern __shared__ float fsm[];
-    float* S = fsm;                                   // [prows][pcols]   source patch
-    float* Tm = S + (size_t)prows * pcols;            // [FT_TH][pcols]   vertical-pass result
-    float* Wv = Tm + (size_t)FT_TH * pcols;           // [FT_TH][FT_MAXT] vertical weights of the tile's rows
+__global__ void __launch_bounds__(FT_THREADS) kc_resize_fused_kernel(const float* __restrict__ src, uint32_t sw, uint32_t sh,
+                                                                     float* __restrict__ dst, uint32_t dw, uint32_t dh,
+                                                                     const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount,
+                                                                     const float* __restrict__ vw, const uint32_t* __restrict__ hleft,
+                                                                     const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
+                                                                     uint32_t pcols, uint32_t prows) {
+    extern __shared__ __align__(16) float fsm[];
+    float* Tm = fsm;                                  // [pcols][FT_TP]   vertical-pass result, column-major
+    float* S = Tm + (size_t)pcols * FT_TP;            // [prows][pcols]   source patch
+    float* Wv = S + (size_t)prows * pcols;            // [FT_TH][FT_MAXT] vertical weights of the tile's rows
     __shared__ uint32_t vl[FT_TH], vc[FT_TH];
     const int tid = threadIdx.x;
     const uint32_t ox0 = blockIdx.x * FT_TW, oy0 = blockIdx.y * FT_TH;
     const uint32_t oxl = min(ox0 + FT_TW, dw) - 1, oyl = min(oy0 + FT_TH, dh) - 1;  // last valid column / row
     const uint32_t nrow = oyl - oy0 + 1;
+    // this thread's four columns: windows and horizontal weights are requested up front,
+    // so their latency overlaps the patch load and the vertical pass
+    uint32_t left[FT_CPT], cnt[FT_CPT];
+    float w[FT_CPT][FT_MAXT];
+#pragma unroll
+    for (int c = 0; c < FT_CPT; ++c) {
+        const uint32_t ox = min(ox0 + FT_CPT * tid + c, oxl);
+        left[c] = __ldg(hleft + ox);
+        cnt[c] = __ldg(hcount + ox);
+#pragma unroll
+        for (int j = 0; j < FT_MAXT; ++j) w[c][j] = __ldg(hw + (size_t)min((uint32_t)j, cnt[c] - 1) * dw + ox);
+    }
     // source window of the tile (left[] and left[]+count[] are non-decreasing in o)
-    const uint32_t cx0 = hleft[ox0], cx1 = hleft[oxl] + hcount[oxl];
-    const uint32_t ry0 = vleft[oy0], ry1 = vleft[oyl] + vcount[oyl];
+    const uint32_t cx0 = __ldg(hleft + ox0), cx1 = __ldg(hleft + oxl) + __ldg(hcount + oxl);
+    const uint32_t ry0 = __ldg(vleft + oy0), ry1 = __ldg(vleft + oyl) + __ldg(vcount + oyl);
     const uint32_t ncx = cx1 - cx0, nry = ry1 - ry0;
-    if (tid < (int)nrow) {
-        vl[tid] = vleft[oy0 + tid] - ry0;
-        vc[tid] = vcount[oy0 + tid];
+    if (tid < FT_TH) {
+        const bool live = (uint32_t)tid < nrow;
+        vl[tid] = live ? vleft[oy0 + tid] - ry0 : 0u;
+        vc[tid] = live ? vcount[oy0 + tid] : 0u;   // rows past the image compute nothing
     }
-    for (int i = tid; i < (int)nrow * FT_MAXT; i += FT_TW) {
+    for (int i = tid; i < (int)nrow * FT_MAXT; i += FT_THREADS) {
         const int r = i / FT_MAXT, k = i - r * FT_MAXT;
-        Wv[i] = vw[(size_t)k * dh + oy0 + r];  // tap-major table; entries past count are 0 and never used
+        Wv[i] = vw[(size_t)k * dh + oy0 + r];  // tap-major table; entries past count are never used
     }
-    for (uint32_t i = tid; i < nry * ncx; i += FT_TW) {
+    for (uint32_t i = tid; i < nry * ncx; i += FT_THREADS) {
         const uint32_t r = i / ncx, c = i - r * ncx;
         S[r * pcols + c] = __ldg(src + (size_t)(ry0 + r) * sw + cx0 + c);
     }
     __syncthreads();
-    // vertical pass: Tm[r][c] = sum_i S[vl[r]+i][c] * Wv[r][i]
-    for (uint32_t i = tid; i < nrow * ncx; i += FT_TW) {
-        const uint32_t r = i / ncx, c = i - r * ncx;
+    // vertical pass: Tm[c][r] = sum_i S[vl[r]+i][c] * Wv[r][i]   (all FT_TH rows, dead ones give 0)
+    for (uint32_t i = tid; i < (uint32_t)FT_TH * ncx; i += FT_THREADS) {
+        const uint32_t c = i / FT_TH, r = i - c * FT_TH;
         const uint32_t l = vl[r], n = vc[r];
         float acc = 0.0f;
         for (uint32_t k = 0; k < n; ++k) acc = tap<EXACT>(acc, S[(l + k) * pcols + c], Wv[r * FT_MAXT + k]);
-        Tm[r * pcols + c] = acc;
+        Tm[c * FT_TP + r] = acc;
     }
     __syncthreads();
-    // horizontal pass: one output column per thread
-    const uint32_t ox = ox0 + tid;
-    if (ox > oxl) return;
-    const uint32_t l = hleft[ox] - cx0, n = hcount[ox];
-    float w[FT_MAXT];
+    // horizontal pass: four adjacent output columns per thread, all rows of the tile accumulate
+    // in registers; taps outermost (the per-column tap count is tested once per tap, not per
+    // pixel), the intermediate is read four rows at a time (LDS.128)
+    if (ox0 + FT_CPT * tid > oxl) return;
+    float acc[FT_CPT][FT_TH];
 #pragma unroll
-    for (int j = 0; j < FT_MAXT; ++j) w[j] = (uint32_t)j < n ? hw[(size_t)j * dw + ox] : 0.0f;
-    float* out = dst + (size_t)oy0 * dw + ox;
-    for (uint32_t r = 0; r < nrow; ++r) {
-        const float* t = Tm + r * pcols + l;
-        float acc = 0.0f;
+    for (int c = 0; c < FT_CPT; ++c)
 #pragma unroll
-        for (int j = 0; j < FT_MAXT; ++j)
-            if ((uint32_t)j < n) acc = tap<EXACT>(acc, t[j], w[j]);
-        acc = acc < 0.0f ? 0.0f : (acc > 1.0f ? 1.0f : acc);  // image::math::utils::clamp keeps NaN
-        __stcs(out + (size_t)r * dw, acc);
+        for (int r = 0; r < FT_TH; ++r) acc[c][r] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < FT_CPT; ++c) {
+        const uint32_t l = left[c] - cx0;
+#pragma unroll
+        for (int j = 0; j < FT_MAXT; ++j) {
+            if ((uint32_t)j < cnt[c]) {
+                const float4* t = reinterpret_cast<const float4*>(Tm + (size_t)(l + j) * FT_TP);
+#pragma unroll
+                for (int q = 0; q < FT_TH / 4; ++q) {
+                    const float4 v = t[q];
+                    acc[c][4 * q + 0] = tap<EXACT>(acc[c][4 * q + 0], v.x, w[c][j]);
+                    acc[c][4 * q + 1] = tap<EXACT>(acc[c][4 * q + 1], v.y, w[c][j]);
+                    acc[c][4 * q + 2] = tap<EXACT>(acc[c][4 * q + 2], v.z, w[c][j]);
+                    acc[c][4 * q + 3] = tap<EXACT>(acc[c][4 * q + 3], v.w, w[c][j]);
+                }
+            }
+        }
+    }
+    const uint32_t oxt = ox0 + FT_CPT * tid;
+    float* out = dst + (size_t)oy0 * dw + oxt;
+    const bool vec = ((dw & 3u) == 0) && (oxt + 3 <= oxl);
+#pragma unroll
+    for (int r = 0; r < FT_TH; ++r) {
+        if ((uint32_t)r < nrow) {
+            float v[FT_CPT];
+#pragma unroll
+            for (int c = 0; c < FT_CPT; ++c) {
+                const float a = acc[c][r];
+                v[c] = a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a);  // image::math::utils::clamp keeps NaN
+            }
+            if (vec) {
+                __stcs(reinterpret_cast<float4*>(out + (size_t)r * dw), make_float4(v[0], v[1], v[2], v[3]));
+            } else {
+#pragma unroll
+                for (int c = 0; c < FT_CPT; ++c)
+                    if (oxt + c <= oxl) out[(size_t)r * dw + c] = v[c];
+            }
+        }
     }
 }
 
@@ -274,7 +321,7 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
     if (!no_fused && tv->max_taps <= (uint32_t)FT_MAXT && th->max_taps <= (uint32_t)FT_MAXT) {
         const uint32_t pcols = max_window(*th, FT_TW) | 1u;  // odd row pitch: no systematic bank conflicts
         const uint32_t prows = max_window(*tv, FT_TH);
-        const size_t smem = sizeof(float) * ((size_t)prows * pcols + (size_t)FT_TH * pcols + (size_t)FT_TH * FT_MAXT);
+        const size_t smem = sizeof(float) * ((size_t)prows * pcols + (size_t)pcols * FT_TP + (size_t)FT_TH * FT_MAXT) + 16;
         if (smem <= 200 * 1024) {
             static bool attr_set = false;
             if (!attr_set) {
@@ -286,10 +333,10 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
             if (grid.y <= 65535u) {
                 KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
                 if (exact_mode)
-                    kc_resize_fused_kernel<true><<<grid, FT_TW, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights,
+                    kc_resize_fused_kernel<true><<<grid, FT_THREADS, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights,
                                                                                       th->d_left, th->d_count, th->d_weights, pcols, prows);
                 else
-                    kc_resize_fused_kernel<false><<<grid, FT_TW, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights,
+                    kc_resize_fused_kernel<false><<<grid, FT_THREADS, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights,
                                                                                        th->d_left, th->d_count, th->d_weights, pcols, prows);
                 KC_CUDA(cudaGetLastError());
                 ctx->kernel_launches++;
