@@ -226,6 +226,15 @@ int32_t kc_image_release(kc_image* img);
 int32_t kc_mix(kc_context* ctx, int32_t mix_type, const kc_image* left, const kc_image* right, kc_image* out);
 /* height_to_normal::process, src/node/height_to_normal.rs:16-77 (Gray in, Rgba out) */
 int32_t kc_height_to_normal(kc_context* ctx, const kc_image* in, kc_image* out);
+/* HeightToNormal on a horizontal strip of a taller image (multi-GPU tiling):
+ * `strip` holds rows [y0, y0+h) of a Gray image `full_height` tall, `halo_row` (w x 1) is the
+ * row above the strip -- row y0-1, or the image's LAST row for the strip that starts at 0
+ * (wrapping_sample_subtract, src/node/process_shared.rs:52-60).  Bit-identical to the
+ * corresponding rows of kc_height_to_normal on the whole image. */
+int32_t kc_height_to_normal_strip(kc_context* ctx, const kc_image* strip, kc_plane* halo_row, uint32_t full_height, kc_image* out);
+/* device-to-device copy of whole rows between planes of equal width (halo rows; works
+ * across devices with peer access: one cudaMemcpyAsync over NVLink) */
+int32_t kc_plane_copy_rows(kc_context* ctx, kc_plane* dst, uint32_t dst_row, kc_plane* src, uint32_t src_row, uint32_t rows);
 /* resize_buffers' per-plane imageops::resize, src/shared.rs:155-201 */
 int32_t kc_resize(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, int32_t filter, kc_image* out);
 /* separate_rgba::process / combine_rgba::process (plane aliasing),

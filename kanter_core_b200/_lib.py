@@ -110,6 +110,8 @@ SIGNATURES = {
     "kc_image_release": (i32, [P(kc_image)]),
     "kc_mix": (i32, [vp, i32, P(kc_image), P(kc_image), P(kc_image)]),
     "kc_height_to_normal": (i32, [vp, P(kc_image), P(kc_image)]),
+    "kc_height_to_normal_strip": (i32, [vp, P(kc_image), vp, u32, P(kc_image)]),
+    "kc_plane_copy_rows": (i32, [vp, vp, u32, vp, u32, u32]),
     "kc_resize": (i32, [vp, P(kc_image), u32, u32, i32, P(kc_image)]),
     "kc_separate_rgba": (i32, [vp, P(kc_image), P(kc_image)]),
     "kc_combine_rgba": (i32, [vp, P(P(kc_image)), P(kc_image)]),

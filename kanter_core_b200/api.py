@@ -812,6 +812,62 @@ class LiveGraph(_GraphView):
         return {"kernels": k.value, "fused_groups": g.value, "algorithmic_bytes": b.value}
 
 
+# ---- the node bodies as plain operators (src/node/*.rs) -------------------------------
+def mix(tex_pro, mix_type, left, right):
+    """mix::process, src/node/mix.rs:51-134; left/right: SlotImage or None."""
+    out = kc_image()
+    call("kc_mix", tex_pro._ctx._h, int(mix_type), C.byref(left._im) if left is not None else None,
+         C.byref(right._im) if right is not None else None, C.byref(out))
+    return SlotImage(tex_pro._ctx, out)
+
+
+def height_to_normal(tex_pro, image):
+    """height_to_normal::process, src/node/height_to_normal.rs:16-77."""
+    out = kc_image()
+    call("kc_height_to_normal", tex_pro._ctx._h, C.byref(image._im), C.byref(out))
+    return SlotImage(tex_pro._ctx, out)
+
+
+def height_to_normal_strip(tex_pro, strip, halo_row, full_height):
+    """HeightToNormal on rows [y0, y0+h) of a taller image; halo_row: Gray w x 1 image holding
+    row (y0-1) mod full_height."""
+    out = kc_image()
+    call("kc_height_to_normal_strip", tex_pro._ctx._h, C.byref(strip._im), halo_row._im.planes[0], int(full_height), C.byref(out))
+    return SlotImage(tex_pro._ctx, out)
+
+
+def resize(tex_pro, image, size, resize_filter):
+    """imageops::resize per plane, src/shared.rs:155-201."""
+    out = kc_image()
+    call("kc_resize", tex_pro._ctx._h, C.byref(image._im), size.width, size.height, int(resize_filter), C.byref(out))
+    return SlotImage(tex_pro._ctx, out)
+
+
+def copy_rows(tex_pro, dst, dst_row, src, src_row, rows, plane=0):
+    """Device-to-device copy of whole rows between planes of equal width (halo rows)."""
+    call("kc_plane_copy_rows", tex_pro._ctx._h, dst._im.planes[plane], int(dst_row), src._im.planes[plane], int(src_row), int(rows))
+
+
+def wrap_device_plane(tex_pro, device_ptr, width, height):
+    """A Gray SlotImage over caller-owned device memory (e.g. torch_tensor.data_ptr())."""
+    pl = C.c_void_p()
+    call("kc_plane_wrap_device", tex_pro._ctx._h, int(width), int(height), C.c_void_p(int(device_ptr)), C.byref(pl))
+    im = kc_image()
+    im.kind, im.width, im.height = _lib.IMAGE_GRAY, int(width), int(height)
+    im.planes[0] = pl
+    return SlotImage(tex_pro._ctx, im)
+
+
+def empty_gray(tex_pro, width, height):
+    """An uninitialised Gray image in HBM (a destination for copy_rows / uploads)."""
+    pl = C.c_void_p()
+    call("kc_plane_create", tex_pro._ctx._h, int(width), int(height), C.byref(pl))
+    im = kc_image()
+    im.kind, im.width, im.height = _lib.IMAGE_GRAY, int(width), int(height)
+    im.planes[0] = pl
+    return SlotImage(tex_pro._ctx, im)
+
+
 def pinned_empty(shape, dtype=np.float32):
     """A numpy array over page-locked host memory (kc_host_alloc), for asynchronous
     uploads/downloads.  The memory lives until free_pinned(array)."""

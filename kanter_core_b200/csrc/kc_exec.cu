@@ -148,11 +148,17 @@ int32_t img_mix(kc_context* ctx, int mix_type, const Img* left, const Img* right
     return KC_OK;
 }
 
-// height_to_normal::process, src/node/height_to_normal.rs:16-77
-int32_t img_h2n(kc_context* ctx, const Img& in, Img& out) {
+// height_to_normal::process, src/node/height_to_normal.rs:16-77.  halo/h_full: strip mode
+// (rows [y0, y0+h) of an image h_full tall; halo = the row above the strip, w x 1).
+int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullptr, uint32_t h_full = 0) {
     if (in.rgba()) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "HeightToNormal needs a Gray input");
     kc_plane* src = in.im.planes[0];
     KC_TRY(kcp_force(ctx, &src, 1));
+    if (halo) {
+        if (halo->w != src->w || halo->h != 1) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "halo row must be %u x 1", src->w);
+        KC_TRY(kcp_force(ctx, &halo, 1));
+    }
+    if (h_full == 0) h_full = src->h;
     Img res;
     res.im.kind = KC_IMAGE_RGBA;
     for (int c = 0; c < 3; ++c) {
@@ -161,8 +167,8 @@ int32_t img_h2n(kc_context* ctx, const Img& in, Img& out) {
         res.set(c, p);
     }
     res.set(3, kcp_new_const(ctx, src->w, src->h, 1.0f));  // from_buffers_rgb, slot_image.rs:90-102
-    KC_TRY(kck_height_to_normal(ctx, src->dptr, src->w, src->h, res.im.planes[0]->dptr, res.im.planes[1]->dptr,
-                                res.im.planes[2]->dptr));
+    KC_TRY(kck_height_to_normal(ctx, src->dptr, src->w, src->h, h_full, halo ? halo->dptr : nullptr, res.im.planes[0]->dptr,
+                                res.im.planes[1]->dptr, res.im.planes[2]->dptr));
     ctx->run_bytes += (uint64_t)src->bytes() * 4;
     out = std::move(res);
     return KC_OK;
@@ -717,6 +723,29 @@ int32_t kc_height_to_normal(kc_context* ctx, const kc_image* in, kc_image* out) 
     Img res;
     KC_TRY(img_h2n(ctx, borrow(in), res));
     *out = res.release();
+    return KC_OK;
+}
+
+int32_t kc_height_to_normal_strip(kc_context* ctx, const kc_image* strip, kc_plane* halo_row, uint32_t full_height, kc_image* out) {
+    if (!ctx || !strip || !halo_row || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(strip, "height_to_normal_strip"));
+    if (full_height < strip->planes[0]->h) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "full height smaller than the strip");
+    KcGuard g(ctx);
+    Img res;
+    KC_TRY(img_h2n(ctx, borrow(strip), res, halo_row, full_height));
+    *out = res.release();
+    return KC_OK;
+}
+
+int32_t kc_plane_copy_rows(kc_context* ctx, kc_plane* dst, uint32_t dst_row, kc_plane* src, uint32_t src_row, uint32_t rows) {
+    if (!ctx || !dst || !src) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (dst->kind != KC_PLANE_DEVICE) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "destination has no device storage");
+    if (dst->w != src->w || dst_row + rows > dst->h || src_row + rows > src->h) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "row range out of bounds");
+    KcGuard g(ctx);
+    KC_TRY(kcp_force(ctx, &src, 1));
+    // a peer copy when the planes live on different devices (NVLink), a plain one otherwise
+    KC_CUDA(cudaMemcpyAsync(dst->dptr + (size_t)dst_row * dst->w, src->dptr + (size_t)src_row * src->w,
+                            sizeof(float) * (size_t)rows * src->w, cudaMemcpyDefault, ctx->stream));
     return KC_OK;
 }
 

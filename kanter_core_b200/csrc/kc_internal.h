@@ -214,8 +214,10 @@ int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args);
 int32_t kck_fill(kc_context* ctx, float* dst, size_t n, float v);
 int32_t kck_from_u8(kc_context* ctx, const uint8_t* d_samples, uint32_t channels, size_t n,
                     float* const planes[4]);
-int32_t kck_height_to_normal(kc_context* ctx, const float* hgt, uint32_t w, uint32_t h, float* r,
-                             float* g, float* b);
+// h_full/halo: for a horizontal strip of a taller image, the full height and the row above
+// the strip (NULL halo + h_full == h: the whole image, toroidal wrap)
+int32_t kck_height_to_normal(kc_context* ctx, const float* hgt, uint32_t w, uint32_t h, uint32_t h_full,
+                             const float* halo, float* r, float* g, float* b);
 int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst,
                          uint32_t dw, uint32_t dh, int filter);
 // host-side weight table exactly as image 0.24.0 computes it (kc_resize.cu)

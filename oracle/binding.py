@@ -25,6 +25,7 @@ _lib.ko_to_u8.argtypes = [vp, vp, vp, vp, u64, i32, vp]
 _lib.ko_mix_plane.argtypes = [i32, vp, vp, u64, vp]
 _lib.ko_rgb_to_gray.argtypes = [vp, vp, vp, u64, vp]
 _lib.ko_height_to_normal.argtypes = [vp, u32, u32, vp, vp, vp]
+_lib.ko_height_to_normal_strip.argtypes = [vp, u32, u32, u32, vp, vp, vp, vp]
 _lib.ko_resize_plane.argtypes = [vp, u32, u32, vp, u32, u32, i32]
 _lib.ko_resize_weights.argtypes = [u32, u32, i32, vp, vp, vp, u32]
 _lib.ko_resize_weights.restype = u32
@@ -96,6 +97,14 @@ def height_to_normal(hgt):
     h, w = hgt.shape
     out = [np.empty((h, w), np.float32) for _ in range(3)]
     _lib.ko_height_to_normal(hgt.ctypes.data, w, h, *[o.ctypes.data for o in out])
+    return out
+
+
+def height_to_normal_strip(strip, h_full, halo_row):
+    strip, halo_row = _c(strip), _c(halo_row)
+    h, w = strip.shape
+    out = [np.empty((h, w), np.float32) for _ in range(3)]
+    _lib.ko_height_to_normal_strip(strip.ctypes.data, w, h, h_full, halo_row.ctypes.data, *[o.ctypes.data for o in out])
     return out
 
 

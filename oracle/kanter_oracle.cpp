@@ -160,15 +160,19 @@ inline V3 v3_cross(V3 a, V3 b) {
     return V3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
 
-void height_to_normal(const float* hgt, uint32_t w, uint32_t h, float* o0, float* o1, float* o2) {
-    const float dx = 1.0f / (float)w;  // :29
-    const float dy = 1.0f / (float)h;  // :30
+// h_full / halo describe a horizontal strip of a taller image (rows [y0, y0+h) of h_full rows,
+// halo = row y0-1 with wrap): the multi-GPU tiling of SURVEY.md 8(e).  halo == NULL and
+// h_full == h is the reference's whole-image case.
+void height_to_normal(const float* hgt, uint32_t w, uint32_t h, uint32_t h_full, const float* halo, float* o0, float* o1,
+                      float* o2) {
+    const float dx = 1.0f / (float)w;       // :29
+    const float dy = 1.0f / (float)h_full;  // :30
     for (uint32_t y = 0; y < h; ++y) {
-        const uint32_t yu = (y == 0) ? h - 1 : y - 1;
+        const float* up_row = (y != 0) ? hgt + (size_t)(y - 1) * w : (halo ? halo : hgt + (size_t)(h - 1) * w);
         for (uint32_t x = 0; x < w; ++x) {
             const uint32_t xl = (x == 0) ? w - 1 : x - 1;
             const float px = hgt[(size_t)y * w + x];
-            const float up = hgt[(size_t)yu * w + x];
+            const float up = up_row[x];
             const float lf = hgt[(size_t)y * w + xl];
             V3 t = v3_normalize(V3{dx, 0.0f, px - lf});   // :58
             V3 b = v3_normalize(V3{0.0f, dy, up - px});   // :59
@@ -570,7 +574,7 @@ int process_node(ko_graph* g, const Node& node, const std::vector<SlotData>& inp
             uint32_t w = in->image.w(), h = in->image.h();
             std::shared_ptr<Plane> o[3];
             for (int c = 0; c < 3; ++c) o[c] = std::make_shared<Plane>(w, h);
-            height_to_normal(in->image.p[0]->px.data(), w, h, o[0]->px.data(), o[1]->px.data(),
+            height_to_normal(in->image.p[0]->px.data(), w, h, h, nullptr, o[0]->px.data(), o[1]->px.data(),
                              o[2]->px.data());
             Image res;
             res.rgba = true;
@@ -771,7 +775,12 @@ void ko_rgb_to_gray(const float* r, const float* g, const float* b, uint64_t n, 
 }
 
 void ko_height_to_normal(const float* hgt, uint32_t w, uint32_t h, float* o0, float* o1, float* o2) {
-    height_to_normal(hgt, w, h, o0, o1, o2);
+    height_to_normal(hgt, w, h, h, nullptr, o0, o1, o2);
+}
+
+void ko_height_to_normal_strip(const float* strip, uint32_t w, uint32_t h, uint32_t h_full, const float* halo_row,
+                               float* o0, float* o1, float* o2) {
+    height_to_normal(strip, w, h, h_full, halo_row, o0, o1, o2);
 }
 
 void ko_resize_plane(const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,

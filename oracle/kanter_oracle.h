@@ -65,6 +65,9 @@ void ko_rgb_to_gray(const float* r, const float* g, const float* b, uint64_t n, 
 /* src/node/height_to_normal.rs:16-77 */
 void ko_height_to_normal(const float* hgt, uint32_t w, uint32_t h,
                          float* out_r, float* out_g, float* out_b);
+/* the same on rows [y0, y0+h) of an image h_full rows tall; halo_row = row (y0-1) mod h_full */
+void ko_height_to_normal_strip(const float* strip, uint32_t w, uint32_t h, uint32_t h_full,
+                               const float* halo_row, float* out_r, float* out_g, float* out_b);
 /* src/shared.rs:159-199 -> image 0.24.0 imageops::resize on one Luma<f32> plane */
 void ko_resize_plane(const float* src, uint32_t sw, uint32_t sh,
                      float* dst, uint32_t dw, uint32_t dh, int filter);

@@ -1,0 +1,125 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[2]: HeightToNormal on a synthetic 8192x8192 Gray height map,
+tiled across the GPUs of one box as horizontal strips with one halo row per strip.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/h2n_strips.py [--size 8192] [--steps 20] [--math fast|exact]
+
+One process per GPU.  Each rank owns rows [y0, y1) of the height map in its own HBM.
+Per step: the last row of every strip goes to the rank below it (NCCL send/recv of
+w*4 bytes over NVLink; rank N-1's row wraps to rank 0), then every rank runs the strip
+kernel.  No collective on the data path.  Rank 0 prints one JSON line; `value` is the
+whole image's Mpixel/s (strong scaling: the image is fixed, the strips shrink).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--size", type=int, default=8192)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+
+    import kanter_core_b200 as kc
+    from kanter_core_b200 import dist as kdist
+    from kanter_core_b200._lib import call
+
+    rank, world, local = kdist.env_rank()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    tp = kc.TextureProcessor.new(device=local, math_mode=kc.MATH_FAST if args.math == "fast" else kc.MATH_EXACT)
+    ctx = tp._ctx._h
+    H = W = args.size
+    y0, y1 = kdist.strip_rows(H, rank, world)
+    # every rank regenerates the same synthetic map and keeps only its strip
+    rng = np.random.default_rng(3)
+    full = rng.random((H, W), dtype=np.float32)
+    strip_host = np.ascontiguousarray(full[y0:y1])
+    want_rows = None
+    if rank == 0:
+        import oracle
+        # parity sample: the first 8 rows of strip 0 (they need the wrapped halo from the LAST strip)
+        want_rows = oracle.height_to_normal_strip(full[0:8], H, full[H - 1]) if args.math == "exact" else \
+            oracle.height_to_normal_strip(full[0:8], H, full[H - 1])
+    del full
+    strip = kc.SlotImage.from_planes(tp, [strip_host])
+
+    # halo staging buffers visible to both torch (NCCL) and the library (raw device pointers)
+    send_t = torch.empty(W, dtype=torch.float32, device="cuda")
+    send_img = kc.wrap_device_plane(tp, send_t.data_ptr(), W, 1)
+
+    def step():
+        # 1. my last row -> staging (device-to-device, on the library's stream)
+        kc.copy_rows(tp, send_img, 0, strip, (y1 - y0) - 1, 1)
+        tp.synchronize()
+        # 2. ring exchange: the row above my strip arrives from rank-1 (wraps at the top)
+        recv_t = kdist.ring_halo_rows(send_t)
+        torch.cuda.current_stream().synchronize()
+        halo = kc.wrap_device_plane(tp, recv_t.data_ptr(), W, 1)
+        # 3. the stencil on my strip
+        out = kc.height_to_normal_strip(tp, strip, halo, H)
+        return out, recv_t
+
+    for _ in range(args.warmup):
+        out, keep = step()
+    tp.synchronize()
+    ev0, ev1 = C.c_void_p(), C.c_void_p()
+    call("kc_event_create", C.byref(ev0))
+    call("kc_event_create", C.byref(ev1))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    import time
+    t0 = time.perf_counter()
+    call("kc_context_set_timing", ctx, 1)
+    for _ in range(args.steps):
+        out, keep = step()
+    tp.synchronize()
+    wall = time.perf_counter() - t0
+    kms, kn = C.c_double(), C.c_uint64()
+    call("kc_context_timing_read", ctx, 3, C.byref(kms), C.byref(kn))
+    call("kc_context_set_timing", ctx, 0)
+    if world > 1:
+        dist.barrier()
+    wall = kdist.max_over_ranks(wall, device="cuda")
+    kernel_ms = kdist.max_over_ranks(kms.value / max(1, kn.value), device="cuda")
+
+    ok = None
+    if rank == 0:
+        got = out.planes()
+        tol = (lambda a, b: np.array_equal(a, b)) if args.math == "exact" else \
+            (lambda a, b: bool((np.abs(a.astype(np.float64) - b) <= 1e-6 + 1e-5 * np.abs(b)).all()))
+        ok = all(tol(got[c][0:8], want_rows[c]) for c in range(3))
+        assert ok, "strip 0 differs from the oracle"
+        px = H * W
+        print(json.dumps({
+            "workload": "configs[2]: HeightToNormal %dx%d Gray, %d horizontal strip(s) + 1 halo row each" % (H, W, world),
+            "metric": "graph_eval_mpixel_per_s", "unit": "Mpixel/s", "n_gpus": world, "scaling": "strong",
+            "value": px * args.steps / wall / 1e6, "ms_per_step_wall": wall / args.steps * 1e3,
+            "strip_kernel_ms_max_over_ranks": kernel_ms,
+            "strip_kernel_GBs_per_gpu": (y1 - y0) * W * 16 / (kernel_ms / 1e3) / 1e9,
+            "halo_bytes_per_boundary": W * 4, "math_mode": args.math,
+            "parity": "rows 0..7 (wrapped halo from the last strip) vs CPU oracle: %s" % ("bit-exact" if args.math == "exact" else "within 1e-5 rel / 1e-6 abs"),
+        }), flush=True)
+    tp.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -261,3 +261,32 @@ def test_shared_subexpression_and_diamond(tex_pro):
     S, D = oracle.mix_plane(0, A, B), oracle.mix_plane(1, A, B)
     want = oracle.mix_plane(3, oracle.mix_plane(2, S, D), S)
     assert bits_equal(lg.slot_data(q, SlotId(0)).image.planes()[0], want)
+
+
+@pytest.mark.parametrize("h,w,parts", [(64, 64, 2), (50, 36, 3), (33, 100, 4), (16, 12, 8)])
+def test_height_to_normal_strips_equal_whole_image(tex_pro, h, w, parts):
+    """The multi-GPU tiling emulated on one GPU: each strip, fed the halo row
+    from the strip above by a device-to-device row copy, gives exactly its rows of the whole."""
+    from kanter_core_b200 import dist as kdist
+    hgt = rnd(21, h, w)
+    whole = kc.height_to_normal(tex_pro, kc.SlotImage.from_planes(tex_pro, [hgt])).planes()
+    want = oracle.height_to_normal(hgt)
+    for c in range(3):
+        assert bits_equal(whole[c], want[c])
+    strips = [kdist.strip_rows(h, r, parts) for r in range(parts)]
+    imgs = [kc.SlotImage.from_planes(tex_pro, [hgt[y0:y1]]) for (y0, y1) in strips]
+    for r, (y0, y1) in enumerate(strips):
+        above = imgs[(r - 1) % parts]
+        halo = kc.empty_gray(tex_pro, w, 1)
+        kc.copy_rows(tex_pro, halo, 0, above, above.size().height - 1, 1)
+        got = kc.height_to_normal_strip(tex_pro, imgs[r], halo, h).planes()
+        for c in range(3):
+            assert bits_equal(got[c], want[c][y0:y1]), (r, c)
+
+
+def test_ops_module_functions(tex_pro):
+    A, B = rnd(31, 20, 24), rnd(32, 20, 24)
+    ia, ib = kc.SlotImage.from_planes(tex_pro, [A]), kc.SlotImage.from_planes(tex_pro, [B])
+    assert bits_equal(kc.mix(tex_pro, MixType.Divide, ia, ib).planes()[0], oracle.mix_plane(3, A, B))
+    assert bits_equal(kc.mix(tex_pro, MixType.Add, ia, None).planes()[0], oracle.mix_plane(0, A, np.zeros_like(A)))
+    assert bits_equal(kc.resize(tex_pro, ia, Size(31, 45), ResizeFilter.CatmullRom).planes()[0], oracle.resize_plane(A, 31, 45, 2))

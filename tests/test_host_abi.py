@@ -1,0 +1,259 @@
+"""CPU-only checks of the host side: the shared library loads and exports every
+symbol include/kanter_b200.h declares, the NodeGraph model behaves like
+src/node_graph.rs, JSON import/export follows the serde schema, and the error
+codes are the TexProError discriminants.  No CUDA device is touched."""
+import ctypes as C
+import json
+import os
+import re
+
+import pytest
+
+import kanter_core_b200 as kc
+from kanter_core_b200 import (MixType, Node, NodeGraph, NodeType, ResizeFilter, ResizePolicy, Side, Size, SlotId,
+                              SlotType, TexProError)
+from kanter_core_b200 import _lib
+from tests import graphs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "kanter_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = declared_symbols()
+    assert len(syms) > 90
+    lib = C.CDLL(_lib.LIB_PATH)
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_the_header():
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+
+
+def test_abi_version_and_error_strings():
+    assert _lib.lib.kc_abi_version() == 1
+    # Display for TexProError, src/error.rs:37-64
+    assert _lib.lib.kc_error_string(4) == b"Invalid number of channels"
+    assert _lib.lib.kc_error_string(10) == b"Could not find a `SlotData`"
+    assert _lib.lib.kc_error_string(19).startswith(b"Invalid name")
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import subprocess, sys
+    # hide every device from a fresh process: context creation must fail with a CUDA error
+    code = ("import kanter_core_b200 as kc\n"
+            "try:\n    kc.TextureProcessor.new()\n    print('CREATED')\n"
+            "except kc.TexProError as e:\n    print('ERR', e.kind)\n")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True).stdout
+    assert "ERR Cuda" in out, out
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "kanter_core_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("CPU oracle", "").replace("the oracle", "") or f == "_lib.py", (dirpath, f)
+
+
+# ---- NodeGraph --------------------------------------------------------------------
+def test_slot_tables_match_the_reference():
+    # src/node/node_type.rs:141-211
+    mix = Node.new(NodeType.Mix(MixType.Add))
+    assert [(s.name, int(s.slot_id), s.slot_type) for s in mix.input_slots()] == [
+        ("left", 0, SlotType.GrayOrRgba), ("right", 1, SlotType.GrayOrRgba)]
+    assert [(s.name, int(s.slot_id), s.slot_type) for s in mix.output_slots()] == [("output", 0, SlotType.GrayOrRgba)]
+    comb = Node.new(NodeType.CombineRgba)
+    assert [s.name for s in comb.input_slots()] == ["red", "green", "blue", "alpha"]
+    sep = Node.new(NodeType.SeparateRgba)
+    assert [int(s.slot_id) for s in sep.output_slots()] == [0, 1, 2, 3]
+    assert Node.new(NodeType.OutputGray("o")).output_slots() == []
+    assert Node.new(NodeType.Value(1.0)).input_slots() == []
+    assert Node.new(NodeType.HeightToNormal).input_slots()[0].slot_type == SlotType.Gray
+    assert Node.new(NodeType.HeightToNormal).output_slots()[0].slot_type == SlotType.Rgba
+    assert mix.input_slot_with_name("right").slot_id == 1
+    with pytest.raises(TexProError) as e:
+        mix.input_slot_with_name("nope")
+    assert e.value.kind == "InvalidName"
+
+
+def test_graph_node_slots_are_inner_node_ids():
+    # NodeGraph::input_slots/output_slots, src/node_graph.rs:299-330
+    inner = NodeGraph.from_path(graphs.INVERT_JSON)
+    n = Node.new(NodeType.Graph(inner))
+    assert [(s.name, int(s.slot_id), s.slot_type) for s in n.input_slots()] == [("in", 808182335, SlotType.Gray)]
+    assert [(s.name, int(s.slot_id), s.slot_type) for s in n.output_slots()] == [("out", 3948812722, SlotType.Gray)]
+    assert inner.input_slot_id_with_name("in") == 808182335
+    assert inner.output_slot_id_with_name("out") == 3948812722
+
+
+def test_connect_rules():
+    g = NodeGraph.new()
+    v = g.add_node(Node.new(NodeType.Value(0.0)))
+    m = g.add_node(Node.new(NodeType.Mix(MixType.default())))
+    # connect_invalid_slot, tests/integration_tests.rs:786-810
+    g.connect(v, m, SlotId(0), SlotId(0))
+    g.connect(v, m, SlotId(0), SlotId(1))
+    with pytest.raises(TexProError) as e:
+        g.connect(v, m, SlotId(0), SlotId(2))
+    assert e.value.kind == "InvalidSlotId"
+    # connecting to an occupied input replaces the edge (src/node_graph.rs:435)
+    v2 = g.add_node(Node.new(NodeType.Value(1.0)))
+    g.connect(v2, m, SlotId(0), SlotId(0))
+    assert [e_._tuple() for e_ in g.edges if e_.input_slot == 0] == [(int(v2), int(m), 0, 0)]
+    # try_connect refuses an occupied slot
+    with pytest.raises(TexProError) as e:
+        g.try_connect(v, m, SlotId(0), SlotId(0))
+    assert e.value.kind == "SlotOccupied"
+    # the same edge twice is an InvalidEdge only if it survives the implicit disconnect: it does not
+    g.connect(v2, m, SlotId(0), SlotId(0))
+    # unknown node
+    with pytest.raises(TexProError) as e:
+        g.connect(999, m, SlotId(0), SlotId(0))
+    assert e.value.kind == "InvalidNodeId"
+
+
+def test_wrong_slot_type():
+    # tests/integration_tests.rs:1330-1347 (Rgba output into a Gray input)
+    g = NodeGraph.new()
+    i = g.add_node(Node.new(NodeType.Image("x.png")))
+    o = g.add_node(Node.new(NodeType.OutputGray("out")))
+    with pytest.raises(TexProError) as e:
+        g.connect(i, o, SlotId(0), SlotId(0))
+    assert e.value.kind == "InvalidSlotType"
+    # GrayOrRgba fits both (a Mix output into OutputGray: mix_node_single_input)
+    m = g.add_node(Node.new(NodeType.Mix(MixType.Add)))
+    g.connect(m, o, SlotId(0), SlotId(0))
+
+
+def test_ids_names_and_removal():
+    g = NodeGraph.new()
+    a = g.add_node(Node.new(NodeType.OutputRgba("out")))
+    b = g.add_node(Node.new(NodeType.OutputRgba("out")))
+    c = g.add_node(Node.new(NodeType.OutputGray("out")))
+    d = g.add_node(Node.new(NodeType.InputGray("")))
+    assert (a, b, c, d) == (0, 1, 2, 3)
+    names = {int(n.node_id): n.node_type.payload for n in g.nodes}
+    # avoid_name_collision, src/node_graph.rs:141-164; empty names become "untitled"
+    assert names == {0: "out", 1: "out_0", 2: "out_1", 3: "untitled"}
+    assert g.output_ids() == [0, 1, 2] and g.input_ids() == [3]
+    with pytest.raises(TexProError):
+        g.add_node_with_id(Node.with_id(NodeType.Value(1.0), 2))
+    g.add_node_with_id(Node.with_id(NodeType.Value(1.0), 10))
+    v = g.add_node(Node.new(NodeType.Value(2.0)))
+    assert v == 4  # new_id keeps counting from where it was and skips ids in use
+    # remove_node drops the edges too (remove_node test, :773-784)
+    g.connect(10, 2, SlotId(0), SlotId(0))
+    g.remove_node(10)
+    assert not g.edges and 10 not in g.node_ids()
+    with pytest.raises(TexProError) as e:
+        g.disconnect_slot(2, Side.Input, SlotId(0))
+    assert e.value.kind == "SlotNotOccupied"
+
+
+def test_json_import_matches_fixture_and_roundtrips():
+    g = NodeGraph.from_path(graphs.INVERT_JSON)
+    want = json.load(open(graphs.INVERT_JSON))
+    assert json.loads(g.export_json_string()) == want
+    # byte-for-byte the serde_json pretty printing of the fixture
+    assert g.export_json_string() == open(graphs.INVERT_JSON).read().rstrip("\n")
+    # from_path restarts the id counter after the largest id (src/node_graph.rs:36-43)
+    assert g.add_node(Node.new(NodeType.Value(0.0))) == 3948812723
+
+
+def test_json_every_variant_roundtrips(tmp_path):
+    inner = NodeGraph.from_path(graphs.INVERT_JSON)
+    g = NodeGraph.new()
+    nodes = [NodeType.InputGray("a"), NodeType.InputRgba("b"), NodeType.OutputGray("c"), NodeType.OutputRgba("d"),
+             NodeType.Graph(inner), NodeType.Image("dir/some \"file\".png"), NodeType.Embed(7), NodeType.Write("out.png"),
+             NodeType.Value(0.33), NodeType.Mix(MixType.Pow), NodeType.HeightToNormal, NodeType.SeparateRgba,
+             NodeType.CombineRgba]
+    ids = []
+    for i, t in enumerate(nodes):
+        n = Node.new(t)
+        n.resize_policy = [ResizePolicy.MostPixels, ResizePolicy.LeastPixels, ResizePolicy.LargestAxes,
+                           ResizePolicy.SmallestAxes, ResizePolicy.SpecificSlot(SlotId(2)),
+                           ResizePolicy.SpecificSize(Size(640, 480))][i % 6]
+        n.resize_filter = ResizeFilter(i % 5)
+        ids.append(g.add_node(n))
+    g.connect(ids[8], ids[9], SlotId(0), SlotId(1))
+    p = tmp_path / "g.json"
+    g.export_json(str(p))
+    d = json.load(open(p))
+    assert d["nodes"][8]["node_type"] == {"Value": 0.33}
+    assert d["nodes"][10]["node_type"] == "HeightToNormal"
+    assert d["nodes"][4]["node_type"]["Graph"] == json.load(open(graphs.INVERT_JSON))
+    assert d["nodes"][4]["resize_policy"] == {"SpecificSlot": 2}
+    assert d["nodes"][5]["resize_policy"] == {"SpecificSize": {"width": 640, "height": 480}}
+    assert d["edges"] == [{"output_id": 8, "input_id": 9, "output_slot": 0, "input_slot": 1}]
+    g2 = NodeGraph.from_path(str(p))
+    assert g2.export_json_string() == g.export_json_string()
+    assert [repr(n.resize_policy) for n in g2.nodes] == [repr(n.resize_policy) for n in g.nodes]
+
+
+def test_json_errors():
+    with pytest.raises(TexProError) as e:
+        NodeGraph.from_json("{\"nodes\": [")
+    assert e.value.kind == "Io"
+    with pytest.raises(TexProError):
+        NodeGraph.from_json('{"nodes":[{"node_id":1,"node_type":"Bogus","resize_policy":"MostPixels","resize_filter":"Triangle"}],"edges":[]}')
+    with pytest.raises(TexProError):
+        NodeGraph.from_path("/nonexistent/graph.json")
+
+
+def test_set_mix_type_and_clone_independence():
+    g = NodeGraph.new()
+    m = g.add_node(Node.new(NodeType.Mix(MixType.Add)))
+    v = g.add_node(Node.new(NodeType.Value(1.0)))
+    c = g.clone()
+    g.set_mix_type(m, MixType.Divide)
+    assert g.node(m).node_type.payload == MixType.Divide and c.node(m).node_type.payload == MixType.Add
+    with pytest.raises(TexProError):
+        g.set_mix_type(v, MixType.Add)
+
+
+def test_calculate_size_policies_without_pixels():
+    """calculate_size (src/shared.rs:61-139) through the ABI, on constant descriptors
+    (no device work): ties in MostPixels go to the LAST input, in LeastPixels to the FIRST."""
+    from kanter_core_b200._lib import call, kc_edge, kc_image, kc_slot_data
+    lib = _lib.lib
+
+    def img(w, h):
+        im = kc_image()
+        # a constant image needs a context only as an owner tag; NULL is accepted for descriptors
+        pl = C.c_void_p()
+        call("kc_plane_from_value", C.c_void_p(1), w, h, 0.0, C.byref(pl))
+        im.kind = 0
+        im.width, im.height = w, h
+        im.planes[0] = pl
+        return im
+
+    sizes = [(128, 64), (64, 128), (32, 32)]
+    sds = (kc_slot_data * 3)()
+    edges = (kc_edge * 3)()
+    for i, (w, h) in enumerate(sizes):
+        sds[i].node_id, sds[i].slot_id, sds[i].image = 10 + i, 0, img(w, h)
+        edges[i] = kc_edge(10 + i, 99, 0, i)
+
+    def size(policy, slot=0, pw=0, ph=0, n=3):
+        w, h = C.c_uint32(), C.c_uint32()
+        call("kc_calculate_size", sds, n, edges, n, policy, slot, pw, ph, C.byref(w), C.byref(h))
+        return (w.value, h.value)
+
+    assert size(0) == (64, 128)            # MostPixels: tie -> last
+    assert size(1) == (32, 32)             # LeastPixels
+    assert size(1, n=2) == (128, 64)       # LeastPixels: tie -> first
+    assert size(2) == (128, 128)           # LargestAxes
+    assert size(3) == (32, 32)             # SmallestAxes
+    assert size(4, slot=1) == (64, 128)    # SpecificSlot(1)
+    assert size(4, slot=7) == (128, 64)    # absent slot -> lowest connected slot
+    assert size(5, pw=300, ph=200) == (300, 200)
+    assert size(0, n=0) == (1, 1)          # MostPixels with no inputs
