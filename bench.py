@@ -292,14 +292,17 @@ def ours(args, rank, world, local_rank):
         lg.replace_embedded(ib, 1)
         lg.read_rgba(out, SlotId(0), kc.Size(SIZE, SIZE), out=host_out)   # synchronises
 
-    e2e_steps = max(1, min(args.steps, 10))
-    for _ in range(2):
+    e2e_steps = max(1, min(args.steps, 20))
+    for _ in range(3):
         step_e2e()
     barrier()
     tp.synchronize()
+    e2e_step_ms = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
+        ts = time.perf_counter()
         step_e2e()
+        e2e_step_ms.append(round((time.perf_counter() - ts) * 1e3, 3))
     tp.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * e2e_steps * MPIX / e2e_s
@@ -329,7 +332,7 @@ def ours(args, rank, world, local_rank):
                        "parity": parity},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "path": "pinned host f32 planes -> kc_image_from_host_planes -> fused mul/pow/to_u8 kernel -> RGBA8 on host (read_rgba)"},
+                    "steps": e2e_steps, "step_ms_min_median_max": [min(e2e_step_ms), float(np.median(e2e_step_ms)), max(e2e_step_ms)], "path": "pinned host f32 planes -> kc_image_from_host_planes -> fused mul/pow/to_u8 kernel -> RGBA8 on host (read_rgba)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "kc_tape_kernel<%s>" % ("EXACT" if args.math == "exact" else "FAST"),

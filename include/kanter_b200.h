@@ -170,6 +170,8 @@ int32_t kc_context_set_fuse(kc_context* ctx, int32_t fuse);
  * src/transient_buffer.rs:413-420) */
 int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_launches, uint64_t* bytes_live);
 
+/* hand the device buffers the context keeps for reuse back to the driver's pool */
+int32_t kc_context_trim(kc_context* ctx);
 /* per-launch device timing: while on, every kernel the library launches on the
  * context is bracketed by CUDA events on the context's stream.  kind: 0 fused
  * elementwise tape, 1 fill, 2 u8->f32, 3 HeightToNormal, 4 resize vertical,

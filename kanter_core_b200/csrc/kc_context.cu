@@ -125,6 +125,7 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) {
     {
         KcGuard g(ctx);
         cudaStreamSynchronize(ctx->stream);
+        kc_dev_trim(ctx);
         for (auto& kv : ctx->axis_tables) axis_table_free(*kv.second);
         ctx->axis_tables.clear();
         for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
@@ -169,21 +170,60 @@ extern "C" int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_laun
 }
 
 // ---------------------------------------------------------------------------
+// device buffers.  All work of a context is ordered on ONE stream, so a buffer
+// released by the host may be handed out again immediately: whatever still reads
+// it was enqueued earlier on that stream than whatever will write it next.
+// ---------------------------------------------------------------------------
+int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out) {
+    auto it = ctx->free_lists.find(bytes);
+    if (it != ctx->free_lists.end() && !it->second.empty()) {
+        *out = it->second.back();
+        it->second.pop_back();
+        ctx->bytes_cached -= bytes;
+        return KC_OK;
+    }
+    cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
+    if (e != cudaSuccess && ctx->bytes_cached) {  // give the cache back and retry once
+        cudaGetLastError();
+        kc_dev_trim(ctx);
+        e = cudaMallocAsync(out, bytes, ctx->stream);
+    }
+    if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+    return KC_OK;
+}
+
+void kc_dev_free(kc_context* ctx, void* p, size_t bytes) {
+    if (!p) return;
+    ctx->free_lists[bytes].push_back(p);
+    ctx->bytes_cached += bytes;
+}
+
+void kc_dev_trim(kc_context* ctx) {
+    for (auto& kv : ctx->free_lists)
+        for (void* p : kv.second) cudaFreeAsync(p, ctx->stream);
+    ctx->free_lists.clear();
+    ctx->bytes_cached = 0;
+}
+
+// ---------------------------------------------------------------------------
 // planes
 // ---------------------------------------------------------------------------
+static inline size_t plane_alloc_bytes(const kc_plane* p) {
+    // round up to a whole float4 so the vector kernels' last access stays in bounds
+    size_t bytes = ((p->bytes() + 15) / 16) * 16;
+    return bytes ? bytes : 16;
+}
 int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out) {
     auto* p = new kc_plane();
     p->ctx = ctx;
     p->w = w;
     p->h = h;
     p->kind = KC_PLANE_DEVICE;
-    // round up to a whole float4 so the vector kernels' last access stays in bounds
-    size_t bytes = ((p->bytes() + 15) / 16) * 16;
-    if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync((void**)&p->dptr, bytes, ctx->stream);
-    if (e != cudaSuccess) {
+    const size_t bytes = plane_alloc_bytes(p);
+    int32_t rc = kc_dev_alloc(ctx, bytes, (void**)&p->dptr);
+    if (rc != KC_OK) {
         delete p;
-        KC_FAIL(KC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return rc;
     }
     ctx->bytes_live += bytes;
     *out = p;
@@ -230,9 +270,8 @@ void kcp_release(kc_plane* p) {
         if (q->refs.fetch_sub(1, std::memory_order_acq_rel) != 1) continue;
         if (q->kind == KC_PLANE_DEVICE && q->owned && q->dptr) {
             KcGuard g(q->ctx);
-            cudaFreeAsync(q->dptr, q->ctx->stream);
-            size_t bytes = ((q->bytes() + 15) / 16) * 16;
-            if (bytes == 0) bytes = 16;
+            const size_t bytes = plane_alloc_bytes(q);
+            kc_dev_free(q->ctx, q->dptr, bytes);
             q->ctx->bytes_live -= bytes;
         } else if (q->kind == KC_PLANE_EXPR) {
             if (q->a) work.push_back(q->a);
@@ -362,7 +401,8 @@ extern "C" int32_t kc_image_from_u8(kc_context* ctx, const uint8_t* samples, uin
     out->height = h;
     size_t n = (size_t)w * h;
     uint8_t* d_samples = nullptr;
-    KC_CUDA(cudaMallocAsync((void**)&d_samples, n * channels + 16, ctx->stream));
+    const size_t staging = ((n * channels + 15) / 16) * 16 + 16;
+    KC_TRY(kc_dev_alloc(ctx, staging, (void**)&d_samples));
     cudaError_t e = cudaMemcpyAsync(d_samples, samples, n * channels, cudaMemcpyHostToDevice, ctx->stream);
     float* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
     int32_t rc = e == cudaSuccess ? KC_OK : KC_ERR_CUDA;
@@ -375,7 +415,7 @@ extern "C" int32_t kc_image_from_u8(kc_context* ctx, const uint8_t* samples, uin
         }
     }
     if (rc == KC_OK) rc = kck_from_u8(ctx, d_samples, channels, n, ptrs);
-    cudaFreeAsync(d_samples, ctx->stream);
+    kc_dev_free(ctx, d_samples, staging);
     if (rc != KC_OK) {
         kci_release(out);
         if (e != cudaSuccess) kc_set_error("upload failed: %s", cudaGetErrorString(e));
@@ -485,7 +525,8 @@ extern "C" int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t s
     KcGuard g(ctx);
     size_t n = (size_t)in->planes[0]->w * in->planes[0]->h;
     uint32_t* d = nullptr;
-    KC_CUDA(cudaMallocAsync((void**)&d, ((n * 4 + 15) / 16) * 16 + 16, ctx->stream));
+    const size_t staging = ((n * 4 + 15) / 16) * 16 + 16;
+    KC_TRY(kc_dev_alloc(ctx, staging, (void**)&d));
     int32_t rc = kcp_export_rgba8(ctx, in, srgb, d);
     if (rc == KC_OK) {
         cudaError_t e = cudaMemcpyAsync(host_rgba8, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
@@ -495,7 +536,7 @@ extern "C" int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t s
             rc = KC_ERR_CUDA;
         }
     }
-    cudaFreeAsync(d, ctx->stream);
+    kc_dev_free(ctx, d, staging);
     return rc;
 }
 
@@ -555,5 +596,13 @@ extern "C" int32_t kc_context_timing_read(kc_context* ctx, int32_t kind, double*
     ctx->timed.swap(keep);
     if (total_ms) *total_ms = sum;
     if (launches) *launches = n;
+    return KC_OK;
+}
+
+extern "C" int32_t kc_context_trim(kc_context* ctx) {
+    // hand the recycled device buffers back to the driver's pool
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    KcGuard g(ctx);
+    kc_dev_trim(ctx);
     return KC_OK;
 }

@@ -143,6 +143,10 @@ struct kc_context {
     uint64_t run_kernels = 0, run_groups = 0, run_bytes = 0;
     std::map<std::tuple<uint32_t, uint32_t, int>, std::shared_ptr<KcAxisTable>> axis_tables;
     std::atomic<bool> cancel{false};
+    // exact-size recycling of device buffers on top of the stream-ordered pool: a plane freed
+    // by one evaluation is handed to the next one of the same size without touching the driver
+    std::map<size_t, std::vector<void*>> free_lists;
+    uint64_t bytes_cached = 0;
     // optional per-launch device timing (kc_context_set_timing)
     bool timing = false;
     struct TimedLaunch { int kind; cudaEvent_t start, stop; };
@@ -187,6 +191,11 @@ struct KcGuard {
         ctx->mu.unlock();
     }
 };
+
+// ---- device buffers (kc_context.cu): stream-ordered, recycled by exact size ----
+int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out);
+void kc_dev_free(kc_context* ctx, void* p, size_t bytes);
+void kc_dev_trim(kc_context* ctx);
 
 // ---- plane helpers (kc_context.cu) -------------------------------------------
 int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out);

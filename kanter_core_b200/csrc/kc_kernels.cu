@@ -33,7 +33,9 @@ namespace {
 // results need the same algorithm: this is a restatement of it in fp64 with the
 // same tables, polynomial coefficients, evaluation order and special cases.
 // ---------------------------------------------------------------------------
-__constant__ double kPowLogTab[16][2] = {
+// (global memory + __ldg, not __constant__: the index differs per lane and the constant
+// cache would serialise the 16-way divergent lookups; L1 serves them in a few wavefronts)
+__device__ const double kPowLogTab[16][2] = {
     {0x1.661ec79f8f3bep+0, -0x1.efec65b963019p-2}, {0x1.571ed4aaf883dp+0, -0x1.b0b6832d4fca4p-2},
     {0x1.49539f0f010b0p+0, -0x1.7418b0a1fb77bp-2}, {0x1.3c995b0b80385p+0, -0x1.39de91a6dcf7bp-2},
     {0x1.30d190c8864a5p+0, -0x1.01d9bf3f2b631p-2}, {0x1.25e227b0b8ea0p+0, -0x1.97c1d1b3b7af0p-3},
@@ -43,7 +45,7 @@ __constant__ double kPowLogTab[16][2] = {
     {0x1.b2036576afce6p-1, 0x1.e840b4ac4e4d2p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.40645f0c6651cp-2},
     {0x1.886e6037841edp-1, 0x1.88e9c2c1b9ff8p-2},  {0x1.767dcf5534862p-1, 0x1.ce0a44eb17bccp-2}};
 // bits(2^(i/32)) - (i << 47)
-__constant__ unsigned long long kExp2Tab[32] = {
+__device__ const unsigned long long kExp2Tab[32] = {
     0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
     0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
     0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
@@ -114,7 +116,8 @@ __device__ __forceinline__ float kc_pow_exact(float x, float y) {
     const uint32_t top = tmp & 0xff800000u;
     const uint32_t iz = ix - top;
     const int k = (int)top >> 23;
-    const double invc = kPowLogTab[i][0], logc = kPowLogTab[i][1];
+    const double2 tc = __ldg(reinterpret_cast<const double2*>(&kPowLogTab[i][0]));
+    const double invc = tc.x, logc = tc.y;
     const double z = (double)__uint_as_float(iz);
     const double r = fma(z, invc, -1.0);
     const double y0 = __dadd_rn(logc, (double)k);
@@ -137,7 +140,7 @@ __device__ __forceinline__ float kc_pow_exact(float x, float y) {
     const unsigned long long ki = (unsigned long long)__double_as_longlong(kd);
     kd = __dsub_rn(kd, 0x1.8p+47);
     const double rr = __dsub_rn(ylogx, kd);
-    unsigned long long t = kExp2Tab[ki & 31];
+    unsigned long long t = __ldg(&kExp2Tab[ki & 31]);
     t += (ki + sign_bias) << 47;
     const double s = __longlong_as_double((long long)t);
     const double zz = fma(0x1.c6af84b912394p-5, rr, 0x1.ebfce50fac4f3p-3);

@@ -346,7 +346,8 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
         }
     }
     float* tmp = nullptr;
-    KC_CUDA(cudaMallocAsync((void**)&tmp, sizeof(float) * (size_t)sw * dh, ctx->stream));
+    const size_t tmp_bytes = ((sizeof(float) * (size_t)sw * dh + 15) / 16) * 16;
+    KC_TRY(kc_dev_alloc(ctx, tmp_bytes, (void**)&tmp));
     const bool exact = ctx->opts.math_mode == KC_MATH_EXACT;
     {
         dim3 grid((sw + 255) / 256, std::min<uint32_t>(dh, 65535u));
@@ -361,7 +362,7 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
         else kc_resize_h_kernel<false><<<grid, 256, 0, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights);
     }
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(tmp, ctx->stream);
+    kc_dev_free(ctx, tmp, tmp_bytes);
     KC_CUDA(e);
     ctx->kernel_launches += 2;
     ctx->run_kernels += 2;
