@@ -174,126 +174,225 @@ __global__ void __launch_bounds__(256) kc_resize_h_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------
-// Fused V∘H tile kernel for resizes whose tap windows are short (<= FT_MAXT taps
-// per axis: every upsampling, and mild downsampling).  One CTA produces a
-// FT_TW x FT_TH tile of the output: it stages the source patch the tile depends on
-// in shared memory, runs the vertical pass for the tile's rows into a second
-// shared-memory buffer (the unclamped f32 intermediate of the reference, never
-// written to HBM), then each thread owns one output column: its horizontal
-// weights sit in registers and it walks down the tile's rows, so a row of the
-// tile is one coalesced 128-byte store per warp.  Same operation order as the
-// two-pass kernels: vertical taps top to bottom, then horizontal taps left to
-// right, clamp to [0,1] last.
+// Fused V∘H strip kernel for resizes whose tap windows are short (<= FS_MAXT taps
+// per axis: every upsampling, and mild downsampling).
+//
+// A CTA owns a strip of FS_TW output columns and marches down the image in
+// groups of FS_G output rows.  What depends only on the column -- the window
+// and the horizontal weights of each thread's four output columns -- is loaded
+// once and stays in registers for the whole march.  Per group:
+//   (1) the source rows the group needs and the group's vertical taps arrive in
+//       shared memory by cp.async, issued one group ahead (double buffered), so
+//       their latency hides behind the previous group's arithmetic;
+//   (2) vertical pass (the reference's unclamped f32 `tmp`, never in HBM): one
+//       item = two adjacent source columns x one output row, packed FFMA2 (or
+//       FMUL2+FADD2 in EXACT), result stored column-major;
+//   (3) horizontal pass: each thread accumulates 4 columns x 16 rows in
+//       registers, reading the intermediate four rows at a time (LDS.128) and
+//       feeding row pairs to FFMA2 with the tap weight as the broadcast scalar;
+//       when the four columns share one window (always, for integer upsampling
+//       ratios >= 4) every loaded value is used by all four columns;
+//   (4) clamp to [0,1] keeping NaN (image::math::utils::clamp), float4 streaming
+//       stores: one full 2 KiB row segment per CTA per row.
+// Two __syncthreads per 8192 output pixels.  Same operation order as the
+// two-pass kernels: vertical taps top to bottom, horizontal taps left to right
+// starting from +0, clamp last.
 // ---------------------------------------------------------------------------
-constexpr int FT_THREADS = 128;
-constexpr int FT_CPT = 4;                    // consecutive output columns per thread (one float4 store per row)
-constexpr int FT_TW = FT_THREADS * FT_CPT;   // output columns per CTA
-constexpr int FT_TH = 16;                    // output rows per CTA
-constexpr int FT_MAXT = 8;                   // taps per axis this kernel supports
-constexpr int FT_TP = FT_TH + 4;             // pitch of the column-major intermediate: 16-byte aligned, conflict-free
+constexpr int FS_THREADS = 128;
+constexpr int FS_CPT = 4;                    // consecutive output columns per thread (one float4 store per row)
+constexpr int FS_TW = FS_THREADS * FS_CPT;   // output columns per CTA
+constexpr int FS_G = 16;                     // output rows per group
+constexpr int FS_MAXT = 8;                   // taps per axis this kernel supports
+constexpr int FS_TP = FS_G + 4;              // pitch of the column-major intermediate (16-byte aligned rows)
+
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One tap on a pair of pixels.  FAST: FFMA2.  EXACT: the reference rounds the product and
+// the sum separately.  ptxas (12.9, -O1 and up) contracts mul.rn.f32x2 + add.rn.f32x2 -- and
+// even fma(s,w,-0) + fma(acc,1,p) -- into ONE FFMA2 regardless of --fmad=false, so the add is
+// written as fma(acc, one, p) with `one` == 1.0f arriving as a kernel argument the optimiser
+// cannot see through: rn(acc*1 + p) == rn(acc + p) bit for bit, signed zeros included.
+template <bool EXACT>
+__device__ __forceinline__ float2 tap2(float2 acc, float2 s, float w, float one) {
+    const float2 ww = make_float2(w, w);
+    if (EXACT) return __ffma2_rn(acc, make_float2(one, one), __fmul2_rn(s, ww));
+    return __ffma2_rn(s, ww, acc);
+}
+
+// clamp to [0,1]; NaN stays NaN (the reference's clamp is two comparisons)
+__device__ __forceinline__ float clamp01_keep_nan(float a) {
+    float r;
+    asm("min.NaN.f32 %0, %1, 0f3F800000;" : "=f"(r) : "f"(a));
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(r));
+    return r;
+}
+
+struct FsGroupBuf {          // one prefetch stage, in shared memory
+    float wv[FS_MAXT][FS_G];  // vertical weights, tap-major
+    uint32_t vl[FS_G];        // first source row of each output row (absolute)
+    uint32_t vc[FS_G];        // tap count of each output row (0: row past the image)
+};
 
 template <bool EXACT>
-__global__ void __launch_bounds__(FT_THREADS) kc_resize_fused_kernel(const float* __restrict__ src, uint32_t sw, uint32_t sh,
-                                                                     float* __restrict__ dst, uint32_t dw, uint32_t dh,
-                                                                     const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount,
-                                                                     const float* __restrict__ vw, const uint32_t* __restrict__ hleft,
-                                                                     const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
-                                                                     uint32_t pcols, uint32_t prows) {
+__global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
+    const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst, uint32_t dw, uint32_t dh,
+    const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount, const float* __restrict__ vw, uint32_t vtaps,
+    const uint32_t* __restrict__ hleft, const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
+    uint32_t pcols, uint32_t prows, float one) {
     extern __shared__ __align__(16) float fsm[];
-    float* Tm = fsm;                                  // [pcols][FT_TP]   vertical-pass result, column-major
-    float* S = Tm + (size_t)pcols * FT_TP;            // [prows][pcols]   source patch
-    float* Wv = S + (size_t)prows * pcols;            // [FT_TH][FT_MAXT] vertical weights of the tile's rows
-    __shared__ uint32_t vl[FT_TH], vc[FT_TH];
+    float* Tm = fsm;                                              // [pcols][FS_TP] vertical-pass result, column-major
+    float* Sbuf = Tm + (size_t)pcols * FS_TP;                     // [2][prows][pcols] source rows of a group
+    FsGroupBuf* gb = reinterpret_cast<FsGroupBuf*>(Sbuf + 2 * (size_t)prows * pcols);  // [2]
     const int tid = threadIdx.x;
-    const uint32_t ox0 = blockIdx.x * FT_TW, oy0 = blockIdx.y * FT_TH;
-    const uint32_t oxl = min(ox0 + FT_TW, dw) - 1, oyl = min(oy0 + FT_TH, dh) - 1;  // last valid column / row
-    const uint32_t nrow = oyl - oy0 + 1;
-    // this thread's four columns: windows and horizontal weights are requested up front,
-    // so their latency overlaps the patch load and the vertical pass
-    uint32_t left[FT_CPT], cnt[FT_CPT];
-    float w[FT_CPT][FT_MAXT];
+    const uint32_t ox0 = blockIdx.x * FS_TW;
+    const uint32_t oxl = min(ox0 + FS_TW, dw) - 1;                // last valid column of the strip
+    const uint32_t ngroups = (dh + FS_G - 1) / FS_G;
+
+    // ---- per-column state, loaded once --------------------------------------------------
+    uint32_t left[FS_CPT], cnt[FS_CPT];
+    float w[FS_CPT][FS_MAXT];
+    const uint32_t cx0 = __ldg(hleft + ox0), cx1 = __ldg(hleft + oxl) + __ldg(hcount + oxl);
+    const uint32_t ncx = cx1 - cx0;                               // source columns the strip reads
 #pragma unroll
-    for (int c = 0; c < FT_CPT; ++c) {
-        const uint32_t ox = min(ox0 + FT_CPT * tid + c, oxl);
-        left[c] = __ldg(hleft + ox);
+    for (int c = 0; c < FS_CPT; ++c) {
+        const uint32_t ox = min(ox0 + FS_CPT * tid + c, oxl);
+        left[c] = __ldg(hleft + ox) - cx0;
         cnt[c] = __ldg(hcount + ox);
 #pragma unroll
-        for (int j = 0; j < FT_MAXT; ++j) w[c][j] = __ldg(hw + (size_t)min((uint32_t)j, cnt[c] - 1) * dw + ox);
+        for (int j = 0; j < FS_MAXT; ++j) w[c][j] = __ldg(hw + (size_t)min((uint32_t)j, cnt[c] - 1) * dw + ox);
     }
-    // source window of the tile (left[] and left[]+count[] are non-decreasing in o)
-    const uint32_t cx0 = __ldg(hleft + ox0), cx1 = __ldg(hleft + oxl) + __ldg(hcount + oxl);
-    const uint32_t ry0 = __ldg(vleft + oy0), ry1 = __ldg(vleft + oyl) + __ldg(vcount + oyl);
-    const uint32_t ncx = cx1 - cx0, nry = ry1 - ry0;
-    if (tid < FT_TH) {
-        const bool live = (uint32_t)tid < nrow;
-        vl[tid] = live ? vleft[oy0 + tid] - ry0 : 0u;
-        vc[tid] = live ? vcount[oy0 + tid] : 0u;   // rows past the image compute nothing
-    }
-    for (int i = tid; i < (int)nrow * FT_MAXT; i += FT_THREADS) {
-        const int r = i / FT_MAXT, k = i - r * FT_MAXT;
-        Wv[i] = vw[(size_t)k * dh + oy0 + r];  // tap-major table; entries past count are never used
-    }
-    for (uint32_t i = tid; i < nry * ncx; i += FT_THREADS) {
-        const uint32_t r = i / ncx, c = i - r * ncx;
-        S[r * pcols + c] = __ldg(src + (size_t)(ry0 + r) * sw + cx0 + c);
-    }
-    __syncthreads();
-    // vertical pass: Tm[c][r] = sum_i S[vl[r]+i][c] * Wv[r][i]   (all FT_TH rows, dead ones give 0)
-    for (uint32_t i = tid; i < (uint32_t)FT_TH * ncx; i += FT_THREADS) {
-        const uint32_t c = i / FT_TH, r = i - c * FT_TH;
-        const uint32_t l = vl[r], n = vc[r];
-        float acc = 0.0f;
-        for (uint32_t k = 0; k < n; ++k) acc = tap<EXACT>(acc, S[(l + k) * pcols + c], Wv[r * FT_MAXT + k]);
-        Tm[c * FT_TP + r] = acc;
-    }
-    __syncthreads();
-    // horizontal pass: four adjacent output columns per thread, all rows of the tile accumulate
-    // in registers; taps outermost (the per-column tap count is tested once per tap, not per
-    // pixel), the intermediate is read four rows at a time (LDS.128)
-    if (ox0 + FT_CPT * tid > oxl) return;
-    float acc[FT_CPT][FT_TH];
+    const bool shared_window = left[0] == left[1] && left[0] == left[2] && left[0] == left[3] &&
+                               cnt[0] == cnt[1] && cnt[0] == cnt[2] && cnt[0] == cnt[3];
+    const uint32_t oxt = ox0 + FS_CPT * tid;
+    const bool col_live = oxt <= oxl;
+    const bool vec = ((dw & 3u) == 0) && (oxt + 3 <= oxl);
+
+    // source rows [ry0, ry1) of group g
+    auto group_rows = [&](uint32_t g, uint32_t& ry0, uint32_t& ry1) {
+        const uint32_t oy0 = g * FS_G, oyl = min(oy0 + FS_G, dh) - 1;
+        ry0 = __ldg(vleft + oy0);
+        ry1 = __ldg(vleft + oyl) + __ldg(vcount + oyl);
+    };
+    // cp.async everything group g needs into stage b
+    auto prefetch = [&](uint32_t g, int b, uint32_t ry0, uint32_t ry1) {
+        const uint32_t oy0 = g * FS_G;
+        FsGroupBuf& G = gb[b];
+        {
+            const int k = tid / FS_G, r = tid % FS_G;             // FS_THREADS == FS_MAXT * FS_G
+            const uint32_t oy = oy0 + r;
+            if (oy < dh && (uint32_t)k < vtaps) cp_async4(&G.wv[k][r], vw + (size_t)k * dh + oy);
+            if (k == 0) {
+                if (oy < dh) cp_async4(&G.vl[r], vleft + oy);
+                else G.vl[r] = 0u;
+            } else if (k == 1) {
+                if (oy < dh) cp_async4(&G.vc[r], vcount + oy);
+                else G.vc[r] = 0u;                                // rows past the image compute nothing
+            }
+        }
+        float* S = Sbuf + (size_t)b * prows * pcols;
+        const uint32_t nry = ry1 - ry0;
+        for (uint32_t r = 0; r < nry; ++r) {
+            const float* row = src + (size_t)(ry0 + r) * sw + cx0;
+            for (uint32_t c = tid; c < ncx; c += FS_THREADS) cp_async4(S + r * pcols + c, row + c);
+        }
+    };
+
+    uint32_t g = blockIdx.y;
+    if (g >= ngroups) return;
+    uint32_t ry0, ry1;
+    group_rows(g, ry0, ry1);
+    prefetch(g, 0, ry0, ry1);
+    cp_async_commit();
+    int b = 0;
+    for (; g < ngroups; g += gridDim.y) {
+        const uint32_t gn = g + gridDim.y;
+        uint32_t nry0 = 0, nry1 = 0;
+        if (gn < ngroups) group_rows(gn, nry0, nry1);             // consumed after the vertical pass
+        cp_async_wait_all();
+        __syncthreads();                                          // stage b landed; Tm free again
+        const FsGroupBuf& G = gb[b];
+        const float* S = Sbuf + (size_t)b * prows * pcols;
+        // ---- vertical pass: Tm[c][r] = sum_k S[vl[r]-ry0+k][c] * wv[k][r], two columns per item ----
+        const uint32_t npair = (ncx + 1) >> 1;
+        for (uint32_t i = tid; i < npair * FS_G; i += FS_THREADS) {
+            const uint32_t cp = i / FS_G, r = i % FS_G;
+            const uint32_t n = G.vc[r];
+            const float* sp = S + (size_t)(G.vl[r] - ry0) * pcols + 2 * cp;
+            float2 acc = make_float2(0.0f, 0.0f);
+            for (uint32_t k = 0; k < n; ++k) acc = tap2<EXACT>(acc, *reinterpret_cast<const float2*>(sp + (size_t)k * pcols), G.wv[k][r], one);
+            Tm[(2 * cp) * FS_TP + r] = acc.x;
+            Tm[(2 * cp + 1) * FS_TP + r] = acc.y;
+        }
+        if (gn < ngroups) prefetch(gn, b ^ 1, nry0, nry1);
+        cp_async_commit();
+        __syncthreads();                                          // Tm complete
+        // ---- horizontal pass -----------------------------------------------------------------
+        if (col_live) {
+            float2 acc[FS_CPT][FS_G / 2];
 #pragma unroll
-    for (int c = 0; c < FT_CPT; ++c)
+            for (int c = 0; c < FS_CPT; ++c)
 #pragma unroll
-        for (int r = 0; r < FT_TH; ++r) acc[c][r] = 0.0f;
+                for (int q = 0; q < FS_G / 2; ++q) acc[c][q] = make_float2(0.0f, 0.0f);
+            if (shared_window) {
+                const float4* t = reinterpret_cast<const float4*>(Tm + (size_t)left[0] * FS_TP);
 #pragma unroll
-    for (int c = 0; c < FT_CPT; ++c) {
-        const uint32_t l = left[c] - cx0;
+                for (int j = 0; j < FS_MAXT; ++j) {
+                    if ((uint32_t)j < cnt[0]) {
+                        float4 v[FS_G / 4];
 #pragma unroll
-        for (int j = 0; j < FT_MAXT; ++j) {
-            if ((uint32_t)j < cnt[c]) {
-                const float4* t = reinterpret_cast<const float4*>(Tm + (size_t)(l + j) * FT_TP);
+                        for (int q = 0; q < FS_G / 4; ++q) v[q] = t[j * (FS_TP / 4) + q];
 #pragma unroll
-                for (int q = 0; q < FT_TH / 4; ++q) {
-                    const float4 v = t[q];
-                    acc[c][4 * q + 0] = tap<EXACT>(acc[c][4 * q + 0], v.x, w[c][j]);
-                    acc[c][4 * q + 1] = tap<EXACT>(acc[c][4 * q + 1], v.y, w[c][j]);
-                    acc[c][4 * q + 2] = tap<EXACT>(acc[c][4 * q + 2], v.z, w[c][j]);
-                    acc[c][4 * q + 3] = tap<EXACT>(acc[c][4 * q + 3], v.w, w[c][j]);
+                        for (int c = 0; c < FS_CPT; ++c)
+#pragma unroll
+                            for (int q = 0; q < FS_G / 4; ++q) {
+                                acc[c][2 * q] = tap2<EXACT>(acc[c][2 * q], make_float2(v[q].x, v[q].y), w[c][j], one);
+                                acc[c][2 * q + 1] = tap2<EXACT>(acc[c][2 * q + 1], make_float2(v[q].z, v[q].w), w[c][j], one);
+                            }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < FS_CPT; ++c) {
+                    const float4* t = reinterpret_cast<const float4*>(Tm + (size_t)left[c] * FS_TP);
+#pragma unroll
+                    for (int j = 0; j < FS_MAXT; ++j) {
+                        if ((uint32_t)j < cnt[c]) {
+#pragma unroll
+                            for (int q = 0; q < FS_G / 4; ++q) {
+                                const float4 v = t[j * (FS_TP / 4) + q];
+                                acc[c][2 * q] = tap2<EXACT>(acc[c][2 * q], make_float2(v.x, v.y), w[c][j], one);
+                                acc[c][2 * q + 1] = tap2<EXACT>(acc[c][2 * q + 1], make_float2(v.z, v.w), w[c][j], one);
+                            }
+                        }
+                    }
+                }
+            }
+            const uint32_t oy0 = g * FS_G;
+            const uint32_t nrow = min((uint32_t)FS_G, dh - oy0);
+            float* out = dst + (size_t)oy0 * dw + oxt;
+#pragma unroll
+            for (int r = 0; r < FS_G; ++r) {
+                if ((uint32_t)r < nrow) {
+                    float v[FS_CPT];
+#pragma unroll
+                    for (int c = 0; c < FS_CPT; ++c) v[c] = clamp01_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x);
+                    if (vec) {
+                        __stcs(reinterpret_cast<float4*>(out + (size_t)r * dw), make_float4(v[0], v[1], v[2], v[3]));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < FS_CPT; ++c)
+                            if (oxt + c <= oxl) out[(size_t)r * dw + c] = v[c];
+                    }
                 }
             }
         }
-    }
-    const uint32_t oxt = ox0 + FT_CPT * tid;
-    float* out = dst + (size_t)oy0 * dw + oxt;
-    const bool vec = ((dw & 3u) == 0) && (oxt + 3 <= oxl);
-#pragma unroll
-    for (int r = 0; r < FT_TH; ++r) {
-        if ((uint32_t)r < nrow) {
-            float v[FT_CPT];
-#pragma unroll
-            for (int c = 0; c < FT_CPT; ++c) {
-                const float a = acc[c][r];
-                v[c] = a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a);  // image::math::utils::clamp keeps NaN
-            }
-            if (vec) {
-                __stcs(reinterpret_cast<float4*>(out + (size_t)r * dw), make_float4(v[0], v[1], v[2], v[3]));
-            } else {
-#pragma unroll
-                for (int c = 0; c < FT_CPT; ++c)
-                    if (oxt + c <= oxl) out[(size_t)r * dw + c] = v[c];
-            }
-        }
+        ry0 = nry0;
+        ry1 = nry1;
+        b ^= 1;
     }
 }
 
@@ -318,26 +417,35 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
     KC_TRY(get_axis(ctx, sw, dw, filter, th));
     const bool exact_mode = ctx->opts.math_mode == KC_MATH_EXACT;
     static const bool no_fused = getenv("KC_RESIZE_TWO_PASS") != nullptr;
-    if (!no_fused && tv->max_taps <= (uint32_t)FT_MAXT && th->max_taps <= (uint32_t)FT_MAXT) {
-        const uint32_t pcols = max_window(*th, FT_TW) | 1u;  // odd row pitch: no systematic bank conflicts
-        const uint32_t prows = max_window(*tv, FT_TH);
-        const size_t smem = sizeof(float) * ((size_t)prows * pcols + (size_t)pcols * FT_TP + (size_t)FT_TH * FT_MAXT) + 16;
+    if (!no_fused && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT) {
+        // even row pitch (the vertical pass reads column pairs), one spare column for the pair of an odd last column
+        const uint32_t pcols = (max_window(*th, FS_TW) + 2u) & ~1u;
+        const uint32_t prows = max_window(*tv, FS_G);
+        const size_t smem = sizeof(float) * ((size_t)pcols * FS_TP + 2 * (size_t)prows * pcols) + 2 * sizeof(FsGroupBuf);
         if (smem <= 200 * 1024) {
             static bool attr_set = false;
             if (!attr_set) {
-                KC_CUDA(cudaFuncSetAttribute(kc_resize_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                KC_CUDA(cudaFuncSetAttribute(kc_resize_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                KC_CUDA(cudaFuncSetAttribute(kc_resize_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                KC_CUDA(cudaFuncSetAttribute(kc_resize_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
                 attr_set = true;
             }
-            dim3 grid((dw + FT_TW - 1) / FT_TW, (dh + FT_TH - 1) / FT_TH);
-            if (grid.y <= 65535u) {
+            int per_sm = 1;
+            if (exact_mode) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc_resize_strip_kernel<true>, FS_THREADS, smem);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc_resize_strip_kernel<false>, FS_THREADS, smem);
+            per_sm = std::max(per_sm, 1);
+            // one resident wave: strips x row-march lanes ~= SMs x resident CTAs
+            const uint32_t strips = (dw + FS_TW - 1) / FS_TW;
+            const uint32_t ngroups = (dh + FS_G - 1) / FS_G;
+            const uint32_t lanes = std::max<uint32_t>(1u, std::min<uint32_t>(ngroups, (uint32_t)(ctx->sm_count * per_sm) / std::max(strips, 1u)));
+            if (strips <= 65535u * 32768u) {
+                dim3 grid(strips, std::min<uint32_t>(lanes, 65535u));
                 KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
                 if (exact_mode)
-                    kc_resize_fused_kernel<true><<<grid, FT_THREADS, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights,
-                                                                                      th->d_left, th->d_count, th->d_weights, pcols, prows);
+                    kc_resize_strip_kernel<true><<<grid, FS_THREADS, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights, tv->max_taps,
+                                                                                      th->d_left, th->d_count, th->d_weights, pcols, prows, 1.0f);
                 else
-                    kc_resize_fused_kernel<false><<<grid, FT_THREADS, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights,
-                                                                                       th->d_left, th->d_count, th->d_weights, pcols, prows);
+                    kc_resize_strip_kernel<false><<<grid, FS_THREADS, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights, tv->max_taps,
+                                                                                       th->d_left, th->d_count, th->d_weights, pcols, prows, 1.0f);
                 KC_CUDA(cudaGetLastError());
                 ctx->kernel_launches++;
                 ctx->run_kernels++;
