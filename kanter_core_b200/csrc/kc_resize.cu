@@ -185,8 +185,8 @@ __global__ void __launch_bounds__(256) kc_resize_h_kernel(const float* __restric
 //       shared memory by cp.async, issued one group ahead (double buffered), so
 //       their latency hides behind the previous group's arithmetic;
 //   (2) vertical pass (the reference's unclamped f32 `tmp`, never in HBM): one
-//       item = two adjacent source columns x one output row, packed FFMA2 (or
-//       FMUL2+FADD2 in EXACT), result stored column-major;
+//       item = four adjacent source columns (LDS.128) x one output row, two packed
+//       FFMA2 per tap (FMUL2 + FFMA2 in EXACT), result stored column-major;
 //   (3) horizontal pass: each thread accumulates 4 columns x 16 rows in
 //       registers, reading the intermediate four rows at a time (LDS.128) and
 //       feeding row pairs to FFMA2 with the tap weight as the broadcast scalar;
@@ -203,6 +203,7 @@ constexpr int FS_CPT = 4;                    // consecutive output columns per t
 constexpr int FS_TW = FS_THREADS * FS_CPT;   // output columns per CTA
 constexpr int FS_G = 16;                     // output rows per group
 constexpr int FS_MAXT = 8;                   // taps per axis this kernel supports
+constexpr int FS_NE = 6;                     // patch elements per thread kept as a precomputed list
 constexpr int FS_TP = FS_G + 4;              // pitch of the column-major intermediate (16-byte aligned rows)
 
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
@@ -271,14 +272,22 @@ __global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
     const bool col_live = oxt <= oxl;
     const bool vec = ((dw & 3u) == 0) && (oxt + 3 <= oxl);
 
-    // source rows [ry0, ry1) of group g
-    auto group_rows = [&](uint32_t g, uint32_t& ry0, uint32_t& ry1) {
-        const uint32_t oy0 = g * FS_G, oyl = min(oy0 + FS_G, dh) - 1;
-        ry0 = __ldg(vleft + oy0);
-        ry1 = __ldg(vleft + oyl) + __ldg(vcount + oyl);
-    };
+    // The source patch of a group is always `prows` rows x `ncx` columns (first row pulled up
+    // where the window would run past the image), so the patch elements a thread copies are
+    // the same for every group: (row, column) of its first FS_NE elements are worked out once.
+    const uint32_t npatch = prows * ncx;
+    uint32_t soff[FS_NE], goff[FS_NE];    // shared-memory / source offsets (in floats); soff == ~0u: no element
+#pragma unroll
+    for (int i = 0; i < FS_NE; ++i) {
+        const uint32_t e = tid + FS_THREADS * i;
+        const uint32_t r = e / ncx, c = e - r * ncx;
+        soff[i] = e < npatch ? r * pcols + c : 0xffffffffu;
+        goff[i] = r * sw + c;             // a patch spans < 2^32 source floats
+    }
+    // first source row of the patch of group g
+    auto group_row0 = [&](uint32_t g) { return min(__ldg(vleft + g * FS_G), sh - prows); };
     // cp.async everything group g needs into stage b
-    auto prefetch = [&](uint32_t g, int b, uint32_t ry0, uint32_t ry1) {
+    auto prefetch = [&](uint32_t g, int b, uint32_t ry0) {
         const uint32_t oy0 = g * FS_G;
         FsGroupBuf& G = gb[b];
         {
@@ -287,47 +296,60 @@ __global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
             if (oy < dh && (uint32_t)k < vtaps) cp_async4(&G.wv[k][r], vw + (size_t)k * dh + oy);
             if (k == 0) {
                 if (oy < dh) cp_async4(&G.vl[r], vleft + oy);
-                else G.vl[r] = 0u;
+                else G.vl[r] = ry0;
             } else if (k == 1) {
                 if (oy < dh) cp_async4(&G.vc[r], vcount + oy);
                 else G.vc[r] = 0u;                                // rows past the image compute nothing
             }
         }
         float* S = Sbuf + (size_t)b * prows * pcols;
-        const uint32_t nry = ry1 - ry0;
-        for (uint32_t r = 0; r < nry; ++r) {
-            const float* row = src + (size_t)(ry0 + r) * sw + cx0;
-            for (uint32_t c = tid; c < ncx; c += FS_THREADS) cp_async4(S + r * pcols + c, row + c);
+        const float* base = src + (size_t)ry0 * sw + cx0;
+#pragma unroll
+        for (int i = 0; i < FS_NE; ++i) {
+            if (soff[i] != 0xffffffffu) cp_async4(S + soff[i], base + goff[i]);
+        }
+        for (uint32_t e = tid + FS_THREADS * FS_NE; e < npatch; e += FS_THREADS) {   // wide windows only
+            const uint32_t r = e / ncx, c = e - r * ncx;
+            cp_async4(S + r * pcols + c, base + (size_t)r * sw + c);
         }
     };
 
     uint32_t g = blockIdx.y;
     if (g >= ngroups) return;
-    uint32_t ry0, ry1;
-    group_rows(g, ry0, ry1);
-    prefetch(g, 0, ry0, ry1);
+    uint32_t ry0 = group_row0(g);
+    prefetch(g, 0, ry0);
     cp_async_commit();
     int b = 0;
     for (; g < ngroups; g += gridDim.y) {
         const uint32_t gn = g + gridDim.y;
-        uint32_t nry0 = 0, nry1 = 0;
-        if (gn < ngroups) group_rows(gn, nry0, nry1);             // consumed after the vertical pass
+        uint32_t nry0 = 0;
+        if (gn < ngroups) nry0 = group_row0(gn);                  // consumed after the vertical pass
         cp_async_wait_all();
         __syncthreads();                                          // stage b landed; Tm free again
         const FsGroupBuf& G = gb[b];
         const float* S = Sbuf + (size_t)b * prows * pcols;
         // ---- vertical pass: Tm[c][r] = sum_k S[vl[r]-ry0+k][c] * wv[k][r], two columns per item ----
-        const uint32_t npair = (ncx + 1) >> 1;
-        for (uint32_t i = tid; i < npair * FS_G; i += FS_THREADS) {
-            const uint32_t cp = i / FS_G, r = i % FS_G;
+        const uint32_t nquad = (ncx + 3) >> 2;
+        for (uint32_t i = tid; i < nquad * FS_G; i += FS_THREADS) {
+            const uint32_t cq = i / FS_G, r = i % FS_G;
             const uint32_t n = G.vc[r];
-            const float* sp = S + (size_t)(G.vl[r] - ry0) * pcols + 2 * cp;
-            float2 acc = make_float2(0.0f, 0.0f);
-            for (uint32_t k = 0; k < n; ++k) acc = tap2<EXACT>(acc, *reinterpret_cast<const float2*>(sp + (size_t)k * pcols), G.wv[k][r], one);
-            Tm[(2 * cp) * FS_TP + r] = acc.x;
-            Tm[(2 * cp + 1) * FS_TP + r] = acc.y;
+            const float* sp = S + (size_t)(G.vl[r] - ry0) * pcols + 4 * cq;
+            float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int k = 0; k < FS_MAXT; ++k) {
+                if ((uint32_t)k >= n) break;                     // n is warp-uniform away from the image border
+                const float4 v = *reinterpret_cast<const float4*>(sp + k * pcols);
+                const float wk = G.wv[k][r];
+                a0 = tap2<EXACT>(a0, make_float2(v.x, v.y), wk, one);
+                a1 = tap2<EXACT>(a1, make_float2(v.z, v.w), wk, one);
+            }
+            float* t = Tm + (size_t)(4 * cq) * FS_TP + r;
+            t[0] = a0.x;
+            t[FS_TP] = a0.y;
+            t[2 * FS_TP] = a1.x;
+            t[3 * FS_TP] = a1.y;
         }
-        if (gn < ngroups) prefetch(gn, b ^ 1, nry0, nry1);
+        if (gn < ngroups) prefetch(gn, b ^ 1, nry0);
         cp_async_commit();
         __syncthreads();                                          // Tm complete
         // ---- horizontal pass -----------------------------------------------------------------
@@ -374,24 +396,29 @@ __global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
             const uint32_t oy0 = g * FS_G;
             const uint32_t nrow = min((uint32_t)FS_G, dh - oy0);
             float* out = dst + (size_t)oy0 * dw + oxt;
+            if (vec && nrow == (uint32_t)FS_G) {
+                float4* o4 = reinterpret_cast<float4*>(out);
+                const uint32_t dw4 = dw >> 2;
 #pragma unroll
-            for (int r = 0; r < FS_G; ++r) {
-                if ((uint32_t)r < nrow) {
+                for (int r = 0; r < FS_G; ++r) {
                     float v[FS_CPT];
 #pragma unroll
                     for (int c = 0; c < FS_CPT; ++c) v[c] = clamp01_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x);
-                    if (vec) {
-                        __stcs(reinterpret_cast<float4*>(out + (size_t)r * dw), make_float4(v[0], v[1], v[2], v[3]));
-                    } else {
+                    __stcs(o4, make_float4(v[0], v[1], v[2], v[3]));
+                    o4 += dw4;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < FS_G; ++r) {
+                    if ((uint32_t)r < nrow) {
 #pragma unroll
                         for (int c = 0; c < FS_CPT; ++c)
-                            if (oxt + c <= oxl) out[(size_t)r * dw + c] = v[c];
+                            if (oxt + c <= oxl) out[(size_t)r * dw + c] = clamp01_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x);
                     }
                 }
             }
         }
         ry0 = nry0;
-        ry1 = nry1;
         b ^= 1;
     }
 }
@@ -418,8 +445,9 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
     const bool exact_mode = ctx->opts.math_mode == KC_MATH_EXACT;
     static const bool no_fused = getenv("KC_RESIZE_TWO_PASS") != nullptr;
     if (!no_fused && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT) {
-        // even row pitch (the vertical pass reads column pairs), one spare column for the pair of an odd last column
-        const uint32_t pcols = (max_window(*th, FS_TW) + 2u) & ~1u;
+        // row pitch a multiple of 4 floats: the vertical pass reads column quads (LDS.128); the
+        // quad of the last columns may run up to 3 columns past the window
+        const uint32_t pcols = (max_window(*th, FS_TW) + 3u) & ~3u;
         const uint32_t prows = max_window(*tv, FS_G);
         const size_t smem = sizeof(float) * ((size_t)pcols * FS_TP + 2 * (size_t)prows * pcols) + 2 * sizeof(FsGroupBuf);
         if (smem <= 200 * 1024) {
