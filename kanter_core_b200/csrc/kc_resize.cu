@@ -238,8 +238,20 @@ struct FsGroupBuf {          // one prefetch stage, in shared memory
     uint32_t vc[FS_G];        // tap count of each output row (0: row past the image)
 };
 
+// N vertical taps of four adjacent source columns, top to bottom
+template <bool EXACT, int N>
+__device__ __forceinline__ void fs_vtaps(const float* sp, uint32_t pitch, const float* wc, float one, float2& a0, float2& a1) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(sp + k * pitch);
+        const float wk = wc[k * FS_G];
+        a0 = tap2<EXACT>(a0, make_float2(v.x, v.y), wk, one);
+        a1 = tap2<EXACT>(a1, make_float2(v.z, v.w), wk, one);
+    }
+}
+
 template <bool EXACT>
-__global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
+__global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
     const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst, uint32_t dw, uint32_t dh,
     const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount, const float* __restrict__ vw, uint32_t vtaps,
     const uint32_t* __restrict__ hleft, const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
@@ -247,15 +259,17 @@ __global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
     extern __shared__ __align__(16) float fsm[];
     float* Tm = fsm;                                              // [pcols][FS_TP] vertical-pass result, column-major
     float* Sbuf = Tm + (size_t)pcols * FS_TP;                     // [2][prows][pcols] source rows of a group
-    FsGroupBuf* gb = reinterpret_cast<FsGroupBuf*>(Sbuf + 2 * (size_t)prows * pcols);  // [2]
+    float4* Wh = reinterpret_cast<float4*>(Sbuf + 2 * (size_t)prows * pcols);         // [FS_MAXT][FS_THREADS]: tap j of a thread's 4 columns
+    FsGroupBuf* gb = reinterpret_cast<FsGroupBuf*>(Wh + FS_MAXT * FS_THREADS);         // [2]
     const int tid = threadIdx.x;
     const uint32_t ox0 = blockIdx.x * FS_TW;
     const uint32_t oxl = min(ox0 + FS_TW, dw) - 1;                // last valid column of the strip
     const uint32_t ngroups = (dh + FS_G - 1) / FS_G;
 
     // ---- per-column state, loaded once --------------------------------------------------
+    // (the horizontal weights live in shared memory, one float4 per tap per thread, read back
+    // right before use: 32 fewer live registers buys a fourth resident CTA per SM)
     uint32_t left[FS_CPT], cnt[FS_CPT];
-    float w[FS_CPT][FS_MAXT];
     const uint32_t cx0 = __ldg(hleft + ox0), cx1 = __ldg(hleft + oxl) + __ldg(hcount + oxl);
     const uint32_t ncx = cx1 - cx0;                               // source columns the strip reads
 #pragma unroll
@@ -264,7 +278,8 @@ __global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
         left[c] = __ldg(hleft + ox) - cx0;
         cnt[c] = __ldg(hcount + ox);
 #pragma unroll
-        for (int j = 0; j < FS_MAXT; ++j) w[c][j] = __ldg(hw + (size_t)min((uint32_t)j, cnt[c] - 1) * dw + ox);
+        for (int j = 0; j < FS_MAXT; ++j)
+            reinterpret_cast<float*>(Wh + j * FS_THREADS + tid)[c] = __ldg(hw + (size_t)min((uint32_t)j, cnt[c] - 1) * dw + ox);
     }
     const bool shared_window = left[0] == left[1] && left[0] == left[2] && left[0] == left[3] &&
                                cnt[0] == cnt[1] && cnt[0] == cnt[2] && cnt[0] == cnt[3];
@@ -335,13 +350,17 @@ __global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
             const uint32_t n = G.vc[r];
             const float* sp = S + (size_t)(G.vl[r] - ry0) * pcols + 4 * cq;
             float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
-#pragma unroll
-            for (int k = 0; k < FS_MAXT; ++k) {
-                if ((uint32_t)k >= n) break;                     // n is warp-uniform away from the image border
-                const float4 v = *reinterpret_cast<const float4*>(sp + k * pcols);
-                const float wk = G.wv[k][r];
-                a0 = tap2<EXACT>(a0, make_float2(v.x, v.y), wk, one);
-                a1 = tap2<EXACT>(a1, make_float2(v.z, v.w), wk, one);
+            const float* wc = &G.wv[0][r];
+            switch (n) {                                         // straight-line code per tap count
+                case 1: fs_vtaps<EXACT, 1>(sp, pcols, wc, one, a0, a1); break;
+                case 2: fs_vtaps<EXACT, 2>(sp, pcols, wc, one, a0, a1); break;
+                case 3: fs_vtaps<EXACT, 3>(sp, pcols, wc, one, a0, a1); break;
+                case 4: fs_vtaps<EXACT, 4>(sp, pcols, wc, one, a0, a1); break;
+                case 5: fs_vtaps<EXACT, 5>(sp, pcols, wc, one, a0, a1); break;
+                case 6: fs_vtaps<EXACT, 6>(sp, pcols, wc, one, a0, a1); break;
+                case 7: fs_vtaps<EXACT, 7>(sp, pcols, wc, one, a0, a1); break;
+                case 8: fs_vtaps<EXACT, 8>(sp, pcols, wc, one, a0, a1); break;
+                default: break;                                  // 0: row past the image
             }
             float* t = Tm + (size_t)(4 * cq) * FS_TP + r;
             t[0] = a0.x;
@@ -364,6 +383,8 @@ __global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
 #pragma unroll
                 for (int j = 0; j < FS_MAXT; ++j) {
                     if ((uint32_t)j < cnt[0]) {
+                        const float4 w4 = Wh[j * FS_THREADS + tid];
+                        const float w[FS_CPT] = {w4.x, w4.y, w4.z, w4.w};
                         float4 v[FS_G / 4];
 #pragma unroll
                         for (int q = 0; q < FS_G / 4; ++q) v[q] = t[j * (FS_TP / 4) + q];
@@ -371,8 +392,8 @@ __global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
                         for (int c = 0; c < FS_CPT; ++c)
 #pragma unroll
                             for (int q = 0; q < FS_G / 4; ++q) {
-                                acc[c][2 * q] = tap2<EXACT>(acc[c][2 * q], make_float2(v[q].x, v[q].y), w[c][j], one);
-                                acc[c][2 * q + 1] = tap2<EXACT>(acc[c][2 * q + 1], make_float2(v[q].z, v[q].w), w[c][j], one);
+                                acc[c][2 * q] = tap2<EXACT>(acc[c][2 * q], make_float2(v[q].x, v[q].y), w[c], one);
+                                acc[c][2 * q + 1] = tap2<EXACT>(acc[c][2 * q + 1], make_float2(v[q].z, v[q].w), w[c], one);
                             }
                     }
                 }
@@ -383,11 +404,12 @@ __global__ void __launch_bounds__(FS_THREADS, 3) kc_resize_strip_kernel(
 #pragma unroll
                     for (int j = 0; j < FS_MAXT; ++j) {
                         if ((uint32_t)j < cnt[c]) {
+                            const float wj = reinterpret_cast<const float*>(Wh + j * FS_THREADS + tid)[c];
 #pragma unroll
                             for (int q = 0; q < FS_G / 4; ++q) {
                                 const float4 v = t[j * (FS_TP / 4) + q];
-                                acc[c][2 * q] = tap2<EXACT>(acc[c][2 * q], make_float2(v.x, v.y), w[c][j], one);
-                                acc[c][2 * q + 1] = tap2<EXACT>(acc[c][2 * q + 1], make_float2(v.z, v.w), w[c][j], one);
+                                acc[c][2 * q] = tap2<EXACT>(acc[c][2 * q], make_float2(v.x, v.y), wj, one);
+                                acc[c][2 * q + 1] = tap2<EXACT>(acc[c][2 * q + 1], make_float2(v.z, v.w), wj, one);
                             }
                         }
                     }
@@ -449,7 +471,7 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
         // quad of the last columns may run up to 3 columns past the window
         const uint32_t pcols = (max_window(*th, FS_TW) + 3u) & ~3u;
         const uint32_t prows = max_window(*tv, FS_G);
-        const size_t smem = sizeof(float) * ((size_t)pcols * FS_TP + 2 * (size_t)prows * pcols) + 2 * sizeof(FsGroupBuf);
+        const size_t smem = sizeof(float) * ((size_t)pcols * FS_TP + 2 * (size_t)prows * pcols) + sizeof(float4) * FS_MAXT * FS_THREADS + 2 * sizeof(FsGroupBuf);
         if (smem <= 200 * 1024) {
             static bool attr_set = false;
             if (!attr_set) {
