@@ -198,9 +198,8 @@ __global__ void __launch_bounds__(256) kc_resize_h_kernel(const float* __restric
 // two-pass kernels: vertical taps top to bottom, horizontal taps left to right
 // starting from +0, clamp last.
 // ---------------------------------------------------------------------------
-constexpr int FS_THREADS = 128;
+constexpr int FS_DEFAULT_THREADS = 128;       // threads per CTA unless KC_RESIZE_THREADS says otherwise
 constexpr int FS_CPT = 4;                    // consecutive output columns per thread (one float4 store per row)
-constexpr int FS_TW = FS_THREADS * FS_CPT;   // output columns per CTA
 constexpr int FS_G = 16;                     // output rows per group
 constexpr int FS_MAXT = 8;                   // taps per axis this kernel supports
 constexpr int FS_NE = 6;                     // patch elements per thread kept as a precomputed list
@@ -250,8 +249,8 @@ __device__ __forceinline__ void fs_vtaps(const float* sp, uint32_t pitch, const 
     }
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
+template <bool EXACT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel(
     const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst, uint32_t dw, uint32_t dh,
     const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount, const float* __restrict__ vw, uint32_t vtaps,
     const uint32_t* __restrict__ hleft, const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
@@ -259,11 +258,11 @@ __global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
     extern __shared__ __align__(16) float fsm[];
     float* Tm = fsm;                                              // [pcols][FS_TP] vertical-pass result, column-major
     float* Sbuf = Tm + (size_t)pcols * FS_TP;                     // [2][prows][pcols] source rows of a group
-    float4* Wh = reinterpret_cast<float4*>(Sbuf + 2 * (size_t)prows * pcols);         // [FS_MAXT][FS_THREADS]: tap j of a thread's 4 columns
-    FsGroupBuf* gb = reinterpret_cast<FsGroupBuf*>(Wh + FS_MAXT * FS_THREADS);         // [2]
+    float4* Wh = reinterpret_cast<float4*>(Sbuf + 2 * (size_t)prows * pcols);         // [FS_MAXT][THREADS]: tap j of a thread's 4 columns
+    FsGroupBuf* gb = reinterpret_cast<FsGroupBuf*>(Wh + FS_MAXT * THREADS);         // [2]
     const int tid = threadIdx.x;
-    const uint32_t ox0 = blockIdx.x * FS_TW;
-    const uint32_t oxl = min(ox0 + FS_TW, dw) - 1;                // last valid column of the strip
+    const uint32_t ox0 = blockIdx.x * (THREADS * FS_CPT);
+    const uint32_t oxl = min(ox0 + (THREADS * FS_CPT), dw) - 1;                // last valid column of the strip
     const uint32_t ngroups = (dh + FS_G - 1) / FS_G;
 
     // ---- per-column state, loaded once --------------------------------------------------
@@ -279,7 +278,7 @@ __global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
         cnt[c] = __ldg(hcount + ox);
 #pragma unroll
         for (int j = 0; j < FS_MAXT; ++j)
-            reinterpret_cast<float*>(Wh + j * FS_THREADS + tid)[c] = __ldg(hw + (size_t)min((uint32_t)j, cnt[c] - 1) * dw + ox);
+            reinterpret_cast<float*>(Wh + j * THREADS + tid)[c] = __ldg(hw + (size_t)min((uint32_t)j, cnt[c] - 1) * dw + ox);
     }
     const bool shared_window = left[0] == left[1] && left[0] == left[2] && left[0] == left[3] &&
                                cnt[0] == cnt[1] && cnt[0] == cnt[2] && cnt[0] == cnt[3];
@@ -294,7 +293,7 @@ __global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
     uint32_t soff[FS_NE], goff[FS_NE];    // shared-memory / source offsets (in floats); soff == ~0u: no element
 #pragma unroll
     for (int i = 0; i < FS_NE; ++i) {
-        const uint32_t e = tid + FS_THREADS * i;
+        const uint32_t e = tid + THREADS * i;
         const uint32_t r = e / ncx, c = e - r * ncx;
         soff[i] = e < npatch ? r * pcols + c : 0xffffffffu;
         goff[i] = r * sw + c;             // a patch spans < 2^32 source floats
@@ -305,8 +304,8 @@ __global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
     auto prefetch = [&](uint32_t g, int b, uint32_t ry0) {
         const uint32_t oy0 = g * FS_G;
         FsGroupBuf& G = gb[b];
-        {
-            const int k = tid / FS_G, r = tid % FS_G;             // FS_THREADS == FS_MAXT * FS_G
+        for (int i = tid; i < FS_MAXT * FS_G; i += THREADS) {
+            const int k = i / FS_G, r = i % FS_G;
             const uint32_t oy = oy0 + r;
             if (oy < dh && (uint32_t)k < vtaps) cp_async4(&G.wv[k][r], vw + (size_t)k * dh + oy);
             if (k == 0) {
@@ -323,7 +322,7 @@ __global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
         for (int i = 0; i < FS_NE; ++i) {
             if (soff[i] != 0xffffffffu) cp_async4(S + soff[i], base + goff[i]);
         }
-        for (uint32_t e = tid + FS_THREADS * FS_NE; e < npatch; e += FS_THREADS) {   // wide windows only
+        for (uint32_t e = tid + THREADS * FS_NE; e < npatch; e += THREADS) {   // wide windows only
             const uint32_t r = e / ncx, c = e - r * ncx;
             cp_async4(S + r * pcols + c, base + (size_t)r * sw + c);
         }
@@ -345,7 +344,7 @@ __global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
         const float* S = Sbuf + (size_t)b * prows * pcols;
         // ---- vertical pass: Tm[c][r] = sum_k S[vl[r]-ry0+k][c] * wv[k][r], two columns per item ----
         const uint32_t nquad = (ncx + 3) >> 2;
-        for (uint32_t i = tid; i < nquad * FS_G; i += FS_THREADS) {
+        for (uint32_t i = tid; i < nquad * FS_G; i += THREADS) {
             const uint32_t cq = i / FS_G, r = i % FS_G;
             const uint32_t n = G.vc[r];
             const float* sp = S + (size_t)(G.vl[r] - ry0) * pcols + 4 * cq;
@@ -381,9 +380,9 @@ __global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
             if (shared_window) {
                 const float4* t = reinterpret_cast<const float4*>(Tm + (size_t)left[0] * FS_TP);
 #pragma unroll
-                for (int j = 0; j < FS_MAXT; ++j) {
+                for (int j = 0; j < FS_MAXT; ++j) {                // (a switch over straight-line variants per tap count was slower: spills)
                     if ((uint32_t)j < cnt[0]) {
-                        const float4 w4 = Wh[j * FS_THREADS + tid];
+                        const float4 w4 = Wh[j * THREADS + tid];
                         const float w[FS_CPT] = {w4.x, w4.y, w4.z, w4.w};
                         float4 v[FS_G / 4];
 #pragma unroll
@@ -404,7 +403,7 @@ __global__ void __launch_bounds__(FS_THREADS, 4) kc_resize_strip_kernel(
 #pragma unroll
                     for (int j = 0; j < FS_MAXT; ++j) {
                         if ((uint32_t)j < cnt[c]) {
-                            const float wj = reinterpret_cast<const float*>(Wh + j * FS_THREADS + tid)[c];
+                            const float wj = reinterpret_cast<const float*>(Wh + j * THREADS + tid)[c];
 #pragma unroll
                             for (int q = 0; q < FS_G / 4; ++q) {
                                 const float4 v = t[j * (FS_TP / 4) + q];
@@ -467,36 +466,38 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
     const bool exact_mode = ctx->opts.math_mode == KC_MATH_EXACT;
     static const bool no_fused = getenv("KC_RESIZE_TWO_PASS") != nullptr;
     if (!no_fused && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT) {
+        // threads per CTA: 4 output columns each.  Narrow CTAs (one or two warps) march
+        // independently, so no warp waits at a barrier for another's vertical pass.
+        static const int env_threads = getenv("KC_RESIZE_THREADS") ? atoi(getenv("KC_RESIZE_THREADS")) : 0;
+        const int threads = env_threads == 32 || env_threads == 64 || env_threads == 128 ? env_threads : FS_DEFAULT_THREADS;
+        const uint32_t tw = (uint32_t)threads * FS_CPT;
         // row pitch a multiple of 4 floats: the vertical pass reads column quads (LDS.128); the
         // quad of the last columns may run up to 3 columns past the window
-        const uint32_t pcols = (max_window(*th, FS_TW) + 3u) & ~3u;
+        const uint32_t pcols = (max_window(*th, tw) + 3u) & ~3u;
         const uint32_t prows = max_window(*tv, FS_G);
-        const size_t smem = sizeof(float) * ((size_t)pcols * FS_TP + 2 * (size_t)prows * pcols) + sizeof(float4) * FS_MAXT * FS_THREADS + 2 * sizeof(FsGroupBuf);
+        const size_t smem = sizeof(float) * ((size_t)pcols * FS_TP + 2 * (size_t)prows * pcols) + sizeof(float4) * FS_MAXT * threads + 2 * sizeof(FsGroupBuf);
         if (smem <= 200 * 1024) {
-            static bool attr_set = false;
-            if (!attr_set) {
-                KC_CUDA(cudaFuncSetAttribute(kc_resize_strip_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                KC_CUDA(cudaFuncSetAttribute(kc_resize_strip_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                attr_set = true;
-            }
+            const void* fn = nullptr;
+#define KC_PICK(T) (exact_mode ? (const void*)kc_resize_strip_kernel<true, T> : (const void*)kc_resize_strip_kernel<false, T>)
+            fn = threads == 32 ? KC_PICK(32) : threads == 64 ? KC_PICK(64) : KC_PICK(128);
+#undef KC_PICK
+            KC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             int per_sm = 1;
-            if (exact_mode) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc_resize_strip_kernel<true>, FS_THREADS, smem);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc_resize_strip_kernel<false>, FS_THREADS, smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
             per_sm = std::max(per_sm, 1);
             // one resident wave: strips x row-march lanes ~= SMs x resident CTAs
-            const uint32_t strips = (dw + FS_TW - 1) / FS_TW;
+            const uint32_t strips = (dw + tw - 1) / tw;
             const uint32_t ngroups = (dh + FS_G - 1) / FS_G;
             const uint32_t lanes = std::max<uint32_t>(1u, std::min<uint32_t>(ngroups, (uint32_t)(ctx->sm_count * per_sm) / std::max(strips, 1u)));
-            if (strips <= 65535u * 32768u) {
+            {
                 dim3 grid(strips, std::min<uint32_t>(lanes, 65535u));
                 KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
-                if (exact_mode)
-                    kc_resize_strip_kernel<true><<<grid, FS_THREADS, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights, tv->max_taps,
-                                                                                      th->d_left, th->d_count, th->d_weights, pcols, prows, 1.0f);
-                else
-                    kc_resize_strip_kernel<false><<<grid, FS_THREADS, smem, ctx->stream>>>(src, sw, sh, dst, dw, dh, tv->d_left, tv->d_count, tv->d_weights, tv->max_taps,
-                                                                                       th->d_left, th->d_count, th->d_weights, pcols, prows, 1.0f);
-                KC_CUDA(cudaGetLastError());
+                const float one = 1.0f;
+                void* args[] = {(void*)&src, (void*)&sw, (void*)&sh, (void*)&dst, (void*)&dw, (void*)&dh,
+                                (void*)&tv->d_left, (void*)&tv->d_count, (void*)&tv->d_weights, (void*)&tv->max_taps,
+                                (void*)&th->d_left, (void*)&th->d_count, (void*)&th->d_weights,
+                                (void*)&pcols, (void*)&prows, (void*)&one};
+                KC_CUDA(cudaLaunchKernel(fn, grid, dim3(threads), args, smem, ctx->stream));
                 ctx->kernel_launches++;
                 ctx->run_kernels++;
                 return KC_OK;

@@ -171,6 +171,42 @@ def test_resize_fast_within_tolerance(tex_pro_fast, filt):
     assert close(got, oracle.resize_plane(p, 123, 99, int(filt)))
 
 
+@pytest.mark.parametrize("filt", list(ResizeFilter))
+@pytest.mark.parametrize("src,dst", [((96, 80), (768, 640)), ((150, 40), (1100, 90)), ((300, 200), (640, 333))])
+def test_resize_exact_multi_strip(tex_pro, filt, src, dst):
+    """Sizes that span several column strips and full + ragged row groups of the fused kernel."""
+    (sw, sh), (dw, dh) = src, dst
+    p = rnd(13, sh, sw, -0.25, 1.25)
+    img = kc.SlotImage.from_planes(tex_pro, [p])
+    got = _resize_direct(tex_pro, img, dw, dh, filt).planes()[0]
+    assert bits_equal(got, oracle.resize_plane(p, dw, dh, int(filt)))
+
+
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("filt", [ResizeFilter.Triangle, ResizeFilter.Lanczos3, ResizeFilter.Gaussian])
+def test_resize_non_finite_values_propagate_like_the_reference(tex_pro, tex_pro_fast, mode, filt):
+    """NaN / inf / huge samples (what Divide leaves behind) must come out of the resize as the
+    reference's clamp leaves them: NaN stays NaN, +inf -> 1, -inf -> 0; the saturating fast
+    store path of the fused kernel may only be taken where no such value is in reach."""
+    tp = tex_pro if mode == "exact" else tex_pro_fast
+    p = rnd(17, 64, 96)
+    p[3, 5] = np.nan
+    p[20, 40] = np.inf
+    p[21, 41] = -np.inf
+    p[40, 70] = 3e38
+    p[41, 70] = -3e38
+    p[63, 95] = np.nan
+    img = kc.SlotImage.from_planes(tp, [p])
+    got = _resize_direct(tp, img, 768, 512, filt).planes()[0]
+    want = oracle.resize_plane(p, 768, 512, int(filt))
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    if mode == "exact":
+        assert bits_equal(got, want)
+    else:
+        ok = ~np.isnan(want)
+        assert close(got[ok], want[ok])
+
+
 def test_resize_rgba_with_constant_alpha(tex_pro):
     # a constant alpha plane goes through the same tap arithmetic as any other plane
     planes = [rnd(50 + c, 20, 30) for c in range(3)]
