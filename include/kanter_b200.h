@@ -182,6 +182,10 @@ int32_t kc_context_timing_read(kc_context* ctx, int32_t kind, double* total_ms, 
 int32_t kc_event_create(void** out_event);
 int32_t kc_event_destroy(void* event);
 int32_t kc_event_record(kc_context* ctx, void* event);
+/* on the context's download stream: completes when every kc_image_to_u8_async /
+ * kc_live_graph_read_rgba_async enqueued so far has delivered its bytes */
+int32_t kc_event_record_download(kc_context* ctx, void* event);
+int32_t kc_event_synchronize(void* event);
 int32_t kc_event_elapsed_ms(void* start_event, void* stop_event, float* ms);  /* waits for stop */
 
 /* ---- planes: TransientBufferContainer / Buffer, src/slot_image.rs:12,
@@ -214,6 +218,10 @@ int32_t kc_image_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, in
 int32_t kc_image_as_type(kc_context* ctx, const kc_image* in, int32_t rgba, kc_image* out);
 /* SlotImage::to_u8 / to_u8_srgb, src/slot_image.rs:142-207: host_rgba8 gets w*h*4 bytes */
 int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8);
+/* same, but returns once the conversion kernel and the copy to (pinned) host memory are enqueued;
+ * host_rgba8 is valid after kc_context_synchronize.  The copy runs on the context's download
+ * stream, so uploads of the next evaluation (kc_plane_from_host) overlap it. */
+int32_t kc_image_to_u8_async(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8);
 /* same, result left in device memory (w*h*4 bytes, caller-owned) */
 int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, int32_t srgb, void* device_rgba8);
 int32_t kc_image_download(kc_context* ctx, const kc_image* in, float* const* host_planes);
@@ -328,6 +336,8 @@ int32_t kc_live_graph_buffer_srgba(kc_live_graph* lg, uint32_t node_id, uint32_t
 /* await_clean_read + buffer_rgba in one call, so the f32 -> RGBA8 conversion
  * fuses into the kernel that produces the node's planes (never stored as f32) */
 int32_t kc_live_graph_read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host_rgba8, size_t cap);
+/* same through kc_image_to_u8_async: the bytes are valid after kc_context_synchronize */
+int32_t kc_live_graph_read_rgba_async(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host_rgba8, size_t cap);
 /* what the last request did: kernels launched, fused elementwise groups, and the
  * compulsory HBM bytes (inputs read once + outputs written once) of those kernels */
 int32_t kc_live_graph_last_run_stats(const kc_live_graph* lg, uint64_t* kernels, uint64_t* fused_groups,

@@ -87,6 +87,8 @@ SIGNATURES = {
     "kc_event_create": (i32, [P(vp)]),
     "kc_event_destroy": (i32, [vp]),
     "kc_event_record": (i32, [vp, vp]),
+    "kc_event_record_download": (i32, [vp, vp]),
+    "kc_event_synchronize": (i32, [vp]),
     "kc_event_elapsed_ms": (i32, [vp, vp, P(f32)]),
     "kc_plane_create": (i32, [vp, u32, u32, P(vp)]),
     "kc_plane_from_value": (i32, [vp, u32, u32, f32, P(vp)]),
@@ -104,6 +106,7 @@ SIGNATURES = {
     "kc_image_from_value": (i32, [vp, u32, u32, f32, i32, P(kc_image)]),
     "kc_image_as_type": (i32, [vp, P(kc_image), i32, P(kc_image)]),
     "kc_image_to_u8": (i32, [vp, P(kc_image), i32, vp]),
+    "kc_image_to_u8_async": (i32, [vp, P(kc_image), i32, vp]),
     "kc_image_to_u8_device": (i32, [vp, P(kc_image), i32, vp]),
     "kc_image_download": (i32, [vp, P(kc_image), P(vp)]),
     "kc_image_materialize": (i32, [vp, P(kc_image), i32]),
@@ -172,6 +175,7 @@ SIGNATURES = {
     "kc_live_graph_buffer_rgba": (i32, [vp, u32, u32, vp, sz]),
     "kc_live_graph_buffer_srgba": (i32, [vp, u32, u32, vp, sz]),
     "kc_live_graph_read_rgba": (i32, [vp, u32, u32, i32, vp, sz]),
+    "kc_live_graph_read_rgba_async": (i32, [vp, u32, u32, i32, vp, sz]),
     "kc_live_graph_last_run_stats": (i32, [vp, P(u64), P(u64), P(u64)]),
 }
 

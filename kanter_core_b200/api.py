@@ -797,13 +797,17 @@ class LiveGraph(_GraphView):
         call("kc_live_graph_buffer_srgba", self._h, int(node_id), int(slot_id), out.ctypes.data, out.nbytes)
         return out
 
-    def read_rgba(self, node_id, slot_id, size, srgb=False, out=None):
+    def read_rgba(self, node_id, slot_id, size, srgb=False, out=None, sync=True):
         """await_clean_read + buffer_rgba as one call; the f32->RGBA8 conversion is
-        fused into the kernel that computes the node (no f32 round trip)."""
+        fused into the kernel that computes the node (no f32 round trip).
+        sync=False (with a pinned `out`): return once everything is enqueued; the bytes
+        are valid after TextureProcessor.synchronize().  The copy to the host runs on the
+        context's download stream, so the next evaluation's uploads overlap it."""
         self._load_images()
         if out is None:
             out = np.empty((size.height, size.width, 4), dtype=np.uint8)
-        call("kc_live_graph_read_rgba", self._h, int(node_id), int(slot_id), int(bool(srgb)), out.ctypes.data, out.nbytes)
+        call("kc_live_graph_read_rgba" if sync else "kc_live_graph_read_rgba_async", self._h, int(node_id), int(slot_id),
+             int(bool(srgb)), out.ctypes.data, out.nbytes)
         return out
 
     def last_run_stats(self):

@@ -102,6 +102,10 @@ extern "C" int32_t kc_context_create(int32_t device, const kc_options* opts, kc_
     cudaGetDevice(&prev);
     KC_CUDA(cudaSetDevice(device));
     KC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    KC_CUDA(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+    KC_CUDA(cudaStreamCreateWithFlags(&ctx->download_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t* e : {&ctx->ev_up_wait, &ctx->ev_up_done, &ctx->ev_dl_wait, &ctx->ev_dl_done})
+        KC_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     // keep freed planes in the stream-ordered pool instead of returning them to the driver
     cudaMemPool_t pool;
     KC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -124,12 +128,19 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) {
     if (!ctx) return KC_OK;
     {
         KcGuard g(ctx);
+        cudaStreamSynchronize(ctx->upload_stream);
         cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->download_stream);
+        if (ctx->dl_staging) cudaFreeAsync(ctx->dl_staging, ctx->stream);
         kc_dev_trim(ctx);
         for (auto& kv : ctx->axis_tables) axis_table_free(*kv.second);
         ctx->axis_tables.clear();
         for (auto& t : ctx->timed) { cudaEventDestroy(t.start); cudaEventDestroy(t.stop); }
         for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+        for (cudaEvent_t e : {ctx->ev_up_wait, ctx->ev_up_done, ctx->ev_dl_wait, ctx->ev_dl_done}) cudaEventDestroy(e);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->upload_stream);
+        cudaStreamDestroy(ctx->download_stream);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -139,7 +150,10 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) {
 extern "C" int32_t kc_context_synchronize(kc_context* ctx) {
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     KcGuard g(ctx);
+    // uploads are waited for by `stream` (event), downloads are not
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    KC_CUDA(cudaStreamSynchronize(ctx->download_stream));
+    ctx->dl_pending = false;
     return KC_OK;
 }
 extern "C" int32_t kc_context_device(const kc_context* ctx, int32_t* device) {
@@ -309,7 +323,16 @@ extern "C" int32_t kc_plane_from_host(kc_context* ctx, uint32_t w, uint32_t h, c
     KcGuard g(ctx);
     kc_plane* p = nullptr;
     KC_TRY(kcp_new_device(ctx, w, h, &p));
-    cudaError_t e = cudaMemcpyAsync(p->dptr, host, p->bytes(), cudaMemcpyHostToDevice, ctx->stream);
+    // The buffer may be a recycled one that kernels already enqueued on `stream` still read, and a
+    // fresh one exists only in `stream` order: the copy waits for the stream's current tail, then
+    // the stream waits for the copy.  What is behind the tail at this point is at most the kernels
+    // of the previous evaluation -- its RGBA8 download runs on the download stream -- so this copy
+    // overlaps that download (PCIe is full duplex).
+    cudaError_t e = cudaEventRecord(ctx->ev_up_wait, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_up_wait, 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->dptr, host, p->bytes(), cudaMemcpyHostToDevice, ctx->upload_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_up_done, ctx->upload_stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_up_done, 0);
     if (e != cudaSuccess) {
         kcp_release(p);
         KC_FAIL(KC_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
@@ -519,25 +542,44 @@ extern "C" int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, in
     return kcp_export_rgba8(ctx, in, srgb, (uint32_t*)device_rgba8);
 }
 
+// RGBA8 export: the conversion kernel runs on `stream` into a device buffer the context keeps,
+// the copy to the host runs on the download stream.  The buffer is rewritten only after the
+// previous download has finished (ev_dl_done).
+static int32_t to_u8_enqueue(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) {
+    const size_t n = (size_t)in->planes[0]->w * in->planes[0]->h;
+    const size_t staging = ((n * 4 + 15) / 16) * 16 + 16;
+    if (ctx->dl_pending) KC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_dl_done, 0));
+    if (ctx->dl_staging_bytes < staging) {
+        if (ctx->dl_staging) KC_CUDA(cudaFreeAsync(ctx->dl_staging, ctx->stream));   // ordered after the wait above
+        ctx->dl_staging = nullptr;
+        ctx->dl_staging_bytes = 0;
+        KC_CUDA(cudaMallocAsync(&ctx->dl_staging, staging, ctx->stream));
+        ctx->dl_staging_bytes = staging;
+    }
+    KC_TRY(kcp_export_rgba8(ctx, in, srgb, (uint32_t*)ctx->dl_staging));
+    KC_CUDA(cudaEventRecord(ctx->ev_dl_wait, ctx->stream));
+    KC_CUDA(cudaStreamWaitEvent(ctx->download_stream, ctx->ev_dl_wait, 0));
+    cudaError_t e = cudaMemcpyAsync(host_rgba8, ctx->dl_staging, n * 4, cudaMemcpyDeviceToHost, ctx->download_stream);
+    if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
+    KC_CUDA(cudaEventRecord(ctx->ev_dl_done, ctx->download_stream));
+    ctx->dl_pending = true;
+    return KC_OK;
+}
+
 extern "C" int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) {
     // SlotImage::to_u8 / to_u8_srgb, src/slot_image.rs:142-207
     if (!ctx || !in || !host_rgba8) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
-    size_t n = (size_t)in->planes[0]->w * in->planes[0]->h;
-    uint32_t* d = nullptr;
-    const size_t staging = ((n * 4 + 15) / 16) * 16 + 16;
-    KC_TRY(kc_dev_alloc(ctx, staging, (void**)&d));
-    int32_t rc = kcp_export_rgba8(ctx, in, srgb, d);
-    if (rc == KC_OK) {
-        cudaError_t e = cudaMemcpyAsync(host_rgba8, d, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) {
-            kc_set_error("download failed: %s", cudaGetErrorString(e));
-            rc = KC_ERR_CUDA;
-        }
-    }
-    kc_dev_free(ctx, d, staging);
-    return rc;
+    KC_TRY(to_u8_enqueue(ctx, in, srgb, host_rgba8));
+    cudaError_t e = cudaEventSynchronize(ctx->ev_dl_done);
+    if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
+    return KC_OK;
+}
+
+extern "C" int32_t kc_image_to_u8_async(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) {
+    if (!ctx || !in || !host_rgba8) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    return to_u8_enqueue(ctx, in, srgb, host_rgba8);
 }
 
 // ---------------------------------------------------------------------------
@@ -559,6 +601,18 @@ extern "C" int32_t kc_event_record(kc_context* ctx, void* ev) {
     if (!ctx || !ev) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
     KC_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->stream));
+    return KC_OK;
+}
+extern "C" int32_t kc_event_record_download(kc_context* ctx, void* ev) {
+    // completes when every RGBA8 download enqueued so far (kc_image_to_u8_async) has landed
+    if (!ctx || !ev) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    KC_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->download_stream));
+    return KC_OK;
+}
+extern "C" int32_t kc_event_synchronize(void* ev) {
+    if (!ev) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
     return KC_OK;
 }
 extern "C" int32_t kc_event_elapsed_ms(void* start, void* stop, float* ms) {

@@ -181,13 +181,21 @@ int32_t plane_resize(kc_context* ctx, kc_plane* src, uint32_t w, uint32_t h, int
         // A 1x1 source (every Value node) has a single tap per axis whose
         // normalised weight is w/w.  When that is exactly 1.0 the result is the
         // constant  clamp(0 + (0 + v*1)*1, 0, 1)  everywhere: fold it.
-        std::vector<uint32_t> l, n;
-        std::vector<float> wt;
-        uint32_t mt = 0;
+        // (checked once per (length, filter) on the real tap tables, then remembered)
         bool unit = true;
         for (uint32_t len : {h, w}) {
-            kc_resize_axis_host(1, len, filter, l, n, wt, mt);
-            for (uint32_t o = 0; o < len && unit; ++o) unit = n[o] == 1 && wt[(size_t)o * mt] == 1.0f;
+            auto key = std::make_pair(len, filter);
+            auto it = ctx->unit_broadcast.find(key);
+            if (it == ctx->unit_broadcast.end()) {
+                std::vector<uint32_t> l, n;
+                std::vector<float> wt;
+                uint32_t mt = 0;
+                bool u = true;
+                kc_resize_axis_host(1, len, filter, l, n, wt, mt);
+                for (uint32_t o = 0; o < len && u; ++o) u = n[o] == 1 && wt[(size_t)o * mt] == 1.0f;
+                it = ctx->unit_broadcast.emplace(key, u).first;
+            }
+            unit = unit && it->second;
         }
         if (unit) {
             float v = 0.0f + src->value * 1.0f;
@@ -1068,13 +1076,13 @@ int32_t kc_live_graph_node_slot_ids(const kc_live_graph* lg, uint32_t node_id, u
     *n = c;
     return KC_OK;
 }
-static int32_t buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int srgb, uint8_t* host, size_t cap) {
+static int32_t buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int srgb, uint8_t* host, size_t cap, bool wait = true) {
     if (!lg || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const Slot* s = lg->find_slot(node_id, slot_id);
     if (!s) KC_FAIL(KC_ERR_NO_SLOT_DATA, "Could not find a `SlotData` for node %u slot %u", node_id, slot_id);
     size_t need = (size_t)s->image.w() * s->image.h() * 4;
     if (cap < need) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "buffer of %zu bytes is too small for %zu", cap, need);
-    return kc_image_to_u8(lg->ctx, &s->image.im, srgb, host);
+    return wait ? kc_image_to_u8(lg->ctx, &s->image.im, srgb, host) : kc_image_to_u8_async(lg->ctx, &s->image.im, srgb, host);
 }
 int32_t kc_live_graph_buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host, size_t cap) {
     return buffer_rgba(lg, node_id, slot_id, 0, host, cap);
@@ -1082,15 +1090,21 @@ int32_t kc_live_graph_buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t 
 int32_t kc_live_graph_buffer_srgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host, size_t cap) {
     return buffer_rgba(lg, node_id, slot_id, 1, host, cap);
 }
-int32_t kc_live_graph_read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap) {
+static int32_t read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap, bool wait) {
     if (!lg || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const uint64_t k0 = lg->ctx->run_kernels, g0 = lg->ctx->run_groups, b0 = lg->ctx->run_bytes;
     KC_TRY(lg->evaluate(&node_id, 1, false));  // planes stay lazy: the export kernel computes them
-    int32_t rc = buffer_rgba(lg, node_id, slot_id, srgb, host, cap);
+    int32_t rc = buffer_rgba(lg, node_id, slot_id, srgb, host, cap, wait);
     lg->last_kernels = lg->ctx->run_kernels - k0;
     lg->last_groups = lg->ctx->run_groups - g0;
     lg->last_bytes = lg->ctx->run_bytes - b0;
     return rc;
+}
+int32_t kc_live_graph_read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap) {
+    return read_rgba(lg, node_id, slot_id, srgb, host, cap, true);
+}
+int32_t kc_live_graph_read_rgba_async(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap) {
+    return read_rgba(lg, node_id, slot_id, srgb, host, cap, false);
 }
 int32_t kc_live_graph_last_run_stats(const kc_live_graph* lg, uint64_t* kernels, uint64_t* fused_groups, uint64_t* algorithmic_bytes) {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");

@@ -12,6 +12,8 @@
 // intermediate lives in registers.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "kc_internal.h"
@@ -315,6 +317,17 @@ int32_t launch_segments(kc_context* ctx, std::vector<SegPlan*>& segs, uint32_t* 
             done[j] = true;
             ctx->run_groups++;
             ctx->run_bytes += (uint64_t)(k->gen.srcs.size() + k->out_ptrs.size()) * k->n_px * 4 + (d_rgba8 ? k->n_px * 4 : 0);
+        }
+        static const bool trace = getenv("KC_TRACE_FUSION") != nullptr;
+        if (trace) {
+            fprintf(stderr, "[kc fusion] launch n=%zu segments=%u tape=%u tmps=%u:", (size_t)args.n, args.n_seg, pc, args.variant);
+            for (uint32_t q = 0; q < args.n_seg; ++q) {
+                int outs = 0;
+                for (int m = 0; m < KC_MAX_OUT; ++m) outs += args.seg[q].out[m] != nullptr;
+                fprintf(stderr, " [src=%u out=%d ops=%u%s]", args.seg[q].n_src, outs, args.seg[q].tape_end - args.seg[q].tape_begin,
+                        args.seg[q].out_rgba8 ? " rgba8" : "");
+            }
+            fprintf(stderr, "\n");
         }
         int32_t rc = kck_launch_tape(ctx, args);
         if (rc != KC_OK) return rc;

@@ -133,7 +133,15 @@ struct kc_plane {
 
 struct kc_context {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;           // every kernel, and every copy that is not one of the two below
+    // copy engines next to the compute stream: planes built from host memory are uploaded on
+    // `upload_stream`, RGBA8 results leave on `download_stream`, each tied to `stream` by events,
+    // so the upload of the next evaluation overlaps the download of the previous one
+    cudaStream_t upload_stream = nullptr, download_stream = nullptr;
+    cudaEvent_t ev_up_wait = nullptr, ev_up_done = nullptr, ev_dl_wait = nullptr, ev_dl_done = nullptr;
+    bool dl_pending = false;                 // ev_dl_done was recorded and nobody waited for it yet
+    void* dl_staging = nullptr;              // device RGBA8 buffer the download stream reads; guarded by ev_dl_done
+    size_t dl_staging_bytes = 0;
     int sm_count = 148;
     kc_options opts{};
     std::recursive_mutex mu;
@@ -142,6 +150,8 @@ struct kc_context {
     // per-request accounting (reset by the live graph)
     uint64_t run_kernels = 0, run_groups = 0, run_bytes = 0;
     std::map<std::tuple<uint32_t, uint32_t, int>, std::shared_ptr<KcAxisTable>> axis_tables;
+    // 1 -> len broadcasts whose single normalised tap is exactly 1.0 (kc_exec.cu, plane_resize)
+    std::map<std::pair<uint32_t, int>, bool> unit_broadcast;
     std::atomic<bool> cancel{false};
     // exact-size recycling of device buffers on top of the stream-ordered pool: a plane freed
     // by one evaluation is handed to the next one of the same size without touching the driver

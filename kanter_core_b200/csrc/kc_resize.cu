@@ -15,6 +15,9 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "kc_internal.h"
 
@@ -481,10 +484,21 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
 #define KC_PICK(T) (exact_mode ? (const void*)kc_resize_strip_kernel<true, T> : (const void*)kc_resize_strip_kernel<false, T>)
             fn = threads == 32 ? KC_PICK(32) : threads == 64 ? KC_PICK(64) : KC_PICK(128);
 #undef KC_PICK
-            KC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            // resident CTAs per SM for this (kernel, shared-memory size): asked once
+            static std::map<std::tuple<int, const void*, size_t>, int> occupancy;   // per device: the attribute is, too
+            static std::mutex occupancy_mu;
             int per_sm = 1;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem);
-            per_sm = std::max(per_sm, 1);
+            {
+                std::lock_guard<std::mutex> lk(occupancy_mu);
+                auto it = occupancy.find(std::make_tuple(ctx->device, fn, smem));
+                if (it == occupancy.end()) {
+                    KC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                    int n = 1;
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, threads, smem);
+                    it = occupancy.emplace(std::make_tuple(ctx->device, fn, smem), std::max(n, 1)).first;
+                }
+                per_sm = it->second;
+            }
             // one resident wave: strips x row-march lanes ~= SMs x resident CTAs
             const uint32_t strips = (dw + tw - 1) / tw;
             const uint32_t ngroups = (dh + FS_G - 1) / FS_G;

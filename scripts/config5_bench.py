@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: a batch of 32-node graphs (Separate/Mix/HeightToNormal/Resize/
+Combine + nested Graph) at 4096^2, whole graphs sharded over the GPUs of one box
+(independent units, no data-path collective).
+
+    python scripts/config5_bench.py [--gpus N] [--graphs 64] [--size 4096] [--math fast|exact]
+                                    [--distinct 2] [--reps 3] [--no-parity]
+
+One process per GPU (re-executes itself under torchrun for N > 1).  Rank r evaluates graphs
+r, r+N, ...; inputs are resident in HBM (`--distinct` different synthetic input sets per rank,
+graph g uses set g mod distinct); time = CUDA events on the library's stream around the rank's
+whole share, max over ranks.  Prints one JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--graphs", type=int, default=64)
+    ap.add_argument("--size", type=int, default=4096)
+    ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--distinct", type=int, default=2)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--no-parity", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        port = 29500 + os.getpid() % 1000
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+
+    import kanter_core_b200 as kc
+    from kanter_core_b200 import SlotId
+    from kanter_core_b200._lib import call
+    from tests import graphs
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    S = args.size
+    tp = kc.TextureProcessor.new(device=local_rank, math_mode=kc.MATH_FAST if args.math == "fast" else kc.MATH_EXACT)
+    ctx = tp._ctx._h
+    g, out = graphs.config5_graph(S)
+    mine = list(range(rank, args.graphs, world))
+    sets = []
+    for d in range(max(1, args.distinct)):
+        inputs = graphs.config5_inputs(100 + rank * 1000 + d, S)
+        lg = tp.new_live_graph()
+        lg.set_node_graph(g)
+        imgs = [kc.SlotImage.from_planes(tp, planes) for planes in inputs]
+        for eid, img in enumerate(imgs):
+            lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, img), eid)
+        sets.append((lg, imgs, inputs if (rank == 0 and d == 0) else None))
+
+    def run_share():
+        for i, _gid in enumerate(mine):
+            lg, imgs, _ = sets[i % len(sets)]
+            for eid, img in enumerate(imgs):       # "new inputs arrived": everything downstream is dirty again
+                lg.replace_embedded(img, eid)
+            lg.request(out)
+
+    run_share()                                     # warm-up (also builds the resize tap tables)
+    tp.synchronize()
+    stats = sets[0][0].last_run_stats()
+    ev0, ev1 = C.c_void_p(), C.c_void_p()
+    call("kc_event_create", C.byref(ev0))
+    call("kc_event_create", C.byref(ev1))
+    best = None
+    for _ in range(args.reps):
+        barrier()
+        tp.synchronize()
+        t0 = time.perf_counter()
+        call("kc_event_record", ctx, ev0)
+        run_share()
+        call("kc_event_record", ctx, ev1)
+        host_enqueue_s = time.perf_counter() - t0
+        tp.synchronize()
+        ms = C.c_float()
+        call("kc_event_elapsed_ms", ev0, ev1, C.byref(ms))
+        t = max_over_ranks(float(ms.value))
+        best = t if best is None else min(best, t)
+
+    # per-kernel-kind device time of one more pass (events around every launch; rank 0)
+    kinds = {}
+    if rank == 0:
+        ms, n = C.c_double(), C.c_uint64()
+        call("kc_context_set_timing", ctx, 1)
+        call("kc_context_timing_read", ctx, -1, C.byref(ms), C.byref(n))     # forget what came before
+        run_share()
+        tp.synchronize()
+        for kind, name in [(0, "fused_elementwise"), (3, "height_to_normal"), (4, "resize_two_pass_v"), (5, "resize"), (-1, "other")]:
+            call("kc_context_timing_read", ctx, kind, C.byref(ms), C.byref(n))   # returns this kind and forgets it
+            if n.value:
+                kinds[name] = {"ms_per_graph": ms.value / len(mine), "launches_per_graph": n.value / len(mine)}
+        call("kc_context_set_timing", ctx, 0)
+
+    parity = None
+    if rank == 0 and not args.no_parity:
+        lg, _imgs, inputs = sets[0]
+        t0 = time.perf_counter()
+        want = graphs.config5_oracle(g, out, inputs)
+        cpu_s = time.perf_counter() - t0
+        got = lg.slot_data(out, SlotId(0)).image.planes()
+        outside, worst, bit_exact = 0, 0.0, True
+        for c in range(4):
+            w = want[c].astype(np.float64)
+            err = np.abs(got[c].astype(np.float64) - w) - (1e-6 + 1e-5 * np.abs(w))
+            outside += int((err > 0).sum())
+            worst = max(worst, float(np.abs(got[c].astype(np.float64) - w).max()))
+            bit_exact &= bool(np.array_equal(got[c].view(np.uint32), want[c].view(np.uint32)))
+        # EXACT must be bit-identical.  FAST is within 1e-5/1e-6 per operation; through the whole
+        # graph a few pixels per 16.7 M can exceed it where HeightToNormal is ill-conditioned (both
+        # finite differences ~ 0, so a 1e-7 perturbation of the fused pow upstream turns the normal)
+        ok = bit_exact if args.math == "exact" else outside <= 1e-5 * 4 * S * S
+        parity = {"graph": 0, "ok": ok, "bit_exact": bit_exact, "samples_outside_1e-5rel_1e-6abs": outside,
+                  "samples": 4 * S * S, "max_abs_err": worst,
+                  "cpu_oracle_seconds_for_one_graph": cpu_s, "cpu_oracle_mpixel_per_s_one_thread": S * S / 1e6 / cpu_s}
+
+    if rank == 0:
+        mpix = S * S / 1e6
+        peak = 6531.6
+        pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(pk):
+            peak = float(json.load(open(pk))["hbm_gbs"])
+        per_graph_bytes = stats["algorithmic_bytes"]
+        gbs = per_graph_bytes * len(mine) / (best / 1e3) / 1e9    # rank 0's share; all ranks do the same work
+        print(json.dumps({
+            "metric": "graph_eval_mpixel_per_s", "config": "configs[4]: %d x 32-node graphs at %dx%d" % (args.graphs, S, S),
+            "value": args.graphs * mpix / (best / 1e3), "unit": "Mpixel/s", "n_gpus": world, "ms_total": best,
+            "ms_per_graph_per_gpu": best / len(mine), "graphs_per_gpu": len(mine), "math_mode": args.math,
+            "kernels_per_graph": stats["kernels"], "fused_groups_per_graph": stats["fused_groups"],
+            "algorithmic_bytes_per_graph": per_graph_bytes, "achieved_GBs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak,
+            "host_enqueue_ms_last_rep": host_enqueue_s * 1e3, "kernel_time_by_kind": kinds, "scaling": "strong (fixed batch split over GPUs)", "parity": parity}), flush=True)
+    tp.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit("config5: output differs from the CPU oracle beyond the stated bar: %r" % (parity,))
+
+
+if __name__ == "__main__":
+    main()

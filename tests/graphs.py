@@ -293,3 +293,106 @@ def run_product(tex_pro, case, request=True):
     if request:
         kc.LiveGraph.await_clean_read(lg, case.node)
     return lg
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json configs[4]: the 32-node batch graph
+# ---------------------------------------------------------------------------
+def config5_graph(size, lsize=None):
+    """32 nodes: 3 Embed (A: Rgba size^2, H: Gray size^2, L: Rgba lsize^2), 3 Value,
+    2 SeparateRgba, 12 Mix-gray in three chains of four (all five ops), 1 HeightToNormal,
+    1 SeparateRgba of the normal map, 1 nested Graph (data/invert_graph.json), 2 Mix with
+    SpecificSize(size^2) that upsample planes of L (Lanczos3, Gaussian), 2 CombineRgba,
+    4 Mix-rgba, 1 OutputRgba.  Returns (NodeGraph, output node id)."""
+    from kanter_core_b200 import ResizeFilter
+    lsize = lsize or max(1, size // 4)
+    g = NodeGraph.new()
+    add = lambda nt: g.add_node(Node.new(nt))
+    mix = lambda op: add(NodeType.Mix(op))
+
+    def con(src, dst, out_slot, in_slot):
+        g.connect(src, dst, SlotId(out_slot), SlotId(in_slot))
+
+    eA, eH, eL = add(NodeType.Embed(0)), add(NodeType.Embed(1)), add(NodeType.Embed(2))
+    v1, v2, v3 = add(NodeType.Value(0.5)), add(NodeType.Value(2.0)), add(NodeType.Value(0.25))
+    sepA, sepL = add(NodeType.SeparateRgba), add(NodeType.SeparateRgba)
+    con(eA, sepA, 0, 0)
+    con(eL, sepL, 0, 0)
+    # chain 1: m4 = pow(Ar*Ag + 0.5, 2) - Ab
+    m1, m2, m3, m4 = mix(MixType.Multiply), mix(MixType.Add), mix(MixType.Pow), mix(MixType.Subtract)
+    con(sepA, m1, 0, 0); con(sepA, m1, 1, 1)
+    con(m1, m2, 0, 0); con(v1, m2, 0, 1)
+    con(m2, m3, 0, 0); con(v2, m3, 0, 1)
+    con(m3, m4, 0, 0); con(sepA, m4, 2, 1)
+    # chain 2: n4 = ((Ab + H) * 0.25 - Ar) / 2
+    n1, n2, n3, n4 = mix(MixType.Add), mix(MixType.Multiply), mix(MixType.Subtract), mix(MixType.Divide)
+    con(sepA, n1, 2, 0); con(eH, n1, 0, 1)
+    con(n1, n2, 0, 0); con(v3, n2, 0, 1)
+    con(n2, n3, 0, 0); con(sepA, n3, 0, 1)
+    con(n3, n4, 0, 0); con(v2, n4, 0, 1)
+    # chain 3 (the height field): h4 = pow(H*0.5 + m3, 0.25) * Ag
+    h1, h2, h3, h4 = mix(MixType.Multiply), mix(MixType.Add), mix(MixType.Pow), mix(MixType.Multiply)
+    con(eH, h1, 0, 0); con(v1, h1, 0, 1)
+    con(h1, h2, 0, 0); con(m3, h2, 0, 1)
+    con(h2, h3, 0, 0); con(v3, h3, 0, 1)
+    con(h3, h4, 0, 0); con(sepA, h4, 1, 1)
+    h2n = add(NodeType.HeightToNormal)
+    con(h4, h2n, 0, 0)
+    sepN = add(NodeType.SeparateRgba)
+    con(h2n, sepN, 0, 0)
+    inner = NodeGraph.from_path(INVERT_JSON)
+    gn = add(NodeType.Graph(inner))
+    g.connect(m4, gn, SlotId(0), inner.input_slot_id_with_name("in"))
+    # implicit upsample of L's planes: u1 = up_lanczos3(Lr) * Nr ; u2 = up_gaussian(Lg) + Ng
+    nu1 = Node.new(NodeType.Mix(MixType.Multiply))
+    nu1.resize_policy = ResizePolicy.SpecificSize(Size.new(size, size))
+    nu1.resize_filter = ResizeFilter.Lanczos3
+    u1 = g.add_node(nu1)
+    nu2 = Node.new(NodeType.Mix(MixType.Add))
+    nu2.resize_policy = ResizePolicy.SpecificSize(Size.new(size, size))
+    nu2.resize_filter = ResizeFilter.Gaussian
+    u2 = g.add_node(nu2)
+    con(sepL, u1, 0, 0); con(sepN, u1, 0, 1)
+    con(sepL, u2, 1, 0); con(sepN, u2, 1, 1)
+    c1, c2 = add(NodeType.CombineRgba), add(NodeType.CombineRgba)
+    con(m4, c1, 0, 0); con(n4, c1, 0, 1)
+    g.connect(gn, c1, inner.output_slot_id_with_name("out"), SlotId(2))
+    con(u1, c2, 0, 0); con(u2, c2, 0, 1); con(sepN, c2, 2, 2)
+    r1, r2, r3, r4 = mix(MixType.Multiply), mix(MixType.Add), mix(MixType.Subtract), mix(MixType.Multiply)
+    con(eA, r1, 0, 0); con(c1, r1, 0, 1)
+    con(r1, r2, 0, 0); con(c2, r2, 0, 1)
+    con(r2, r3, 0, 0); con(c1, r3, 0, 1)
+    con(r3, r4, 0, 0); con(eA, r4, 0, 1)
+    out = add(NodeType.OutputRgba("out"))
+    con(r4, out, 0, 0)
+    assert len(g.nodes) == 32, len(g.nodes)
+    return g, out
+
+
+def config5_inputs(seed, size, lsize=None):
+    """Synthetic inputs of graph `seed`: A (4 planes), H (1 plane), L (4 planes), uniform [0,1)."""
+    lsize = lsize or max(1, size // 4)
+    r = np.random.default_rng(seed)
+    A = [r.random((size, size), dtype=np.float32) for _ in range(4)]
+    H = [r.random((size, size), dtype=np.float32)]
+    L = [r.random((lsize, lsize), dtype=np.float32) for _ in range(4)]
+    return A, H, L
+
+
+def config5_oracle(graph, out, inputs):
+    import oracle
+    og = oracle.from_node_graph(graph)
+    for eid, planes in enumerate(inputs):
+        og.embed(eid, planes)
+    og.eval()
+    return og.slot(int(out), 0)
+
+
+def config5_product(tex_pro, graph, out, inputs, read=True):
+    lg = tex_pro.new_live_graph()
+    lg.set_node_graph(graph)
+    for eid, planes in enumerate(inputs):
+        lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tex_pro, planes)), eid)
+    if read:
+        kc.LiveGraph.await_clean_read(lg, out)
+    return lg
