@@ -170,6 +170,11 @@ int32_t kc_context_set_fuse(kc_context* ctx, int32_t fuse);
  * src/transient_buffer.rs:413-420) */
 int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_launches, uint64_t* bytes_live);
 
+/* tuning knobs for the sweep scripts (0 = library default): "tile_v", "ctas", "stages",
+ * "src_soft_cap", "resize_threads"; process-wide */
+int32_t kc_debug_set_tuning(const char* key, int32_t value);
+/* (tile float4s per thread, resident CTAs per SM, pipeline stages) of the last fused elementwise launch */
+int32_t kc_debug_last_tile_config(int32_t* v, int32_t* ctas, int32_t* stages);
 /* hand the device buffers the context keeps for reuse back to the driver's pool */
 int32_t kc_context_trim(kc_context* ctx);
 /* per-launch device timing: while on, every kernel the library launches on the

@@ -82,6 +82,8 @@ SIGNATURES = {
     "kc_context_set_fuse": (i32, [vp, i32]),
     "kc_context_stats": (i32, [vp, P(u64), P(u64)]),
     "kc_context_trim": (i32, [vp]),
+    "kc_debug_set_tuning": (i32, [C.c_char_p, i32]),
+    "kc_debug_last_tile_config": (i32, [P(i32), P(i32), P(i32)]),
     "kc_context_set_timing": (i32, [vp, i32]),
     "kc_context_timing_read": (i32, [vp, i32, P(C.c_double), P(u64)]),
     "kc_event_create": (i32, [P(vp)]),

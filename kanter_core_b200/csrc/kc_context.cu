@@ -11,6 +11,9 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cstdlib>
+#include <string>
+
 #include "kc_internal.h"
 
 // ---------------------------------------------------------------------------
@@ -650,6 +653,33 @@ extern "C" int32_t kc_context_timing_read(kc_context* ctx, int32_t kind, double*
     ctx->timed.swap(keep);
     if (total_ms) *total_ms = sum;
     if (launches) *launches = n;
+    return KC_OK;
+}
+
+static int env_int(const char* name) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : 0;
+}
+static KcTuning tuning_from_env() {
+    KcTuning t;
+    t.tile_v = env_int("KC_TILE_V");
+    t.ctas = env_int("KC_CTAS");
+    t.stages = env_int("KC_STAGES");
+    t.src_soft_cap = env_int("KC_SRC_SOFT_CAP");
+    t.resize_threads = env_int("KC_RESIZE_THREADS");
+    return t;
+}
+KcTuning g_kc_tuning = tuning_from_env();
+
+extern "C" int32_t kc_debug_set_tuning(const char* key, int32_t value) {
+    if (!key) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "key is NULL");
+    const std::string k(key);
+    if (k == "tile_v") g_kc_tuning.tile_v = value;
+    else if (k == "ctas") g_kc_tuning.ctas = value;
+    else if (k == "stages") g_kc_tuning.stages = value;
+    else if (k == "src_soft_cap") g_kc_tuning.src_soft_cap = value;
+    else if (k == "resize_threads") g_kc_tuning.resize_threads = value;
+    else KC_FAIL(KC_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
     return KC_OK;
 }
 

@@ -446,7 +446,11 @@ int32_t force_impl(kc_context* ctx, kc_plane* const* roots, size_t n, int pack, 
                 const_roots.push_back(roots[i]);
         if (outs.empty() && const_roots.empty()) return KC_OK;
 
-        // components: outputs whose cones share an expression node or a source plane
+        // components: outputs whose cones share an expression node always go together (else the
+        // node would be computed twice); outputs that only share SOURCE planes are merged -- the
+        // shared planes are then read once -- while the merged kernel keeps few enough sources
+        // for the big-tile configurations of the tile VM (src_soft_cap, see pick_config)
+        const int soft_cap = g_kc_tuning.src_soft_cap > 0 ? std::min(g_kc_tuning.src_soft_cap, KC_MAX_SRC) : KC_SRC_SOFT_CAP;
         const size_t no = outs.size();
         std::vector<std::vector<kc_plane*>> cn(no), cs(no);
         for (size_t i = 0; i < no; ++i) cone_of(outs[i], cn[i], cs[i]);
@@ -458,9 +462,28 @@ int32_t force_impl(kc_context* ctx, kc_plane* const* roots, size_t n, int pack, 
                 if (find((int)i) == find((int)j)) continue;
                 bool share = false;
                 for (kc_plane* p : cn[i]) if (std::find(cn[j].begin(), cn[j].end(), p) != cn[j].end()) { share = true; break; }
-                if (!share) for (kc_plane* p : cs[i]) if (std::find(cs[j].begin(), cs[j].end(), p) != cs[j].end()) { share = true; break; }
                 if (share && outs[i]->w == outs[j]->w && outs[i]->h == outs[j]->h) comp[find((int)j)] = find((int)i);
             }
+        // second pass: source sharing, bounded by the soft cap on the union of sources
+        {
+            auto comp_srcs = [&](int root) {
+                std::vector<kc_plane*> u;
+                for (size_t i = 0; i < no; ++i)
+                    if (find((int)i) == root)
+                        for (kc_plane* p : cs[i]) if (std::find(u.begin(), u.end(), p) == u.end()) u.push_back(p);
+                return u;
+            };
+            for (size_t i = 0; i < no; ++i)
+                for (size_t j = i + 1; j < no; ++j) {
+                    const int ri = find((int)i), rj = find((int)j);
+                    if (ri == rj || outs[i]->w != outs[j]->w || outs[i]->h != outs[j]->h) continue;
+                    std::vector<kc_plane*> ui = comp_srcs(ri), uj = comp_srcs(rj);
+                    size_t shared = 0;
+                    for (kc_plane* p : uj) shared += std::find(ui.begin(), ui.end(), p) != ui.end();
+                    if (shared == 0) continue;
+                    if ((int)(ui.size() + uj.size() - shared) <= soft_cap) comp[rj] = ri;
+                }
+        }
         // one segment per component: the longest prefix of its outputs (topological
         // order) that fits the machine; the rest waits for the next round
         std::vector<std::unique_ptr<SegPlan>> plans;

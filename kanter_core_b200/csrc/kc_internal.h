@@ -44,6 +44,7 @@ void kc_set_error(const char* fmt, ...);
 // temporaries, `acc` the accumulator.  One instruction = op | (arg << 8).
 // arg addresses an operand: 0..7 = S[arg], 8..13 = T[arg-8], 14 = immediate.
 constexpr int KC_MAX_SRC = 8;
+constexpr int KC_SRC_SOFT_CAP = 8;   // default bound for merging outputs that only share sources (kc_fusion.cu)
 constexpr int KC_MAX_TMP = 6;
 constexpr int KC_MAX_OUT = 6;
 constexpr int KC_MAX_TAPE = 96;   // instructions per launch, all segments together
@@ -201,6 +202,18 @@ struct KcGuard {
         ctx->mu.unlock();
     }
 };
+
+// ---- tuning knobs (kc_context.cu): 0 = let the library choose.  Set from the environment
+// (KC_TILE_V, KC_CTAS, KC_STAGES, KC_SRC_SOFT_CAP, KC_RESIZE_THREADS) at load time or through
+// kc_debug_set_tuning; used by the sweep scripts under scripts/ ----------------------------
+struct KcTuning {
+    int tile_v = 0;          // float4s per thread per tile of the fused elementwise kernel (1, 2, 4)
+    int ctas = 0;            // resident CTAs per SM of that kernel (1..3)
+    int stages = 0;          // its pipeline depth (2..4)
+    int src_soft_cap = 0;    // merge independent outputs that only share SOURCES while the union has <= this many
+    int resize_threads = 0;  // threads per CTA of the fused resize kernel (32, 64, 128)
+};
+extern KcTuning g_kc_tuning;
 
 // ---- device buffers (kc_context.cu): stream-ordered, recycled by exact size ----
 int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out);

@@ -537,9 +537,7 @@ struct TvmConfig { int v, ctas, stages; };
 // 4096-pixel tiles beat smaller ones (the dispatch is amortised over 16 pixels per
 // thread), 3 resident CTAs beat 2 beat 1, and 2 stages are as good as 4.
 TvmConfig pick_config(int ns_max, int nt_max, unsigned long long n) {
-    static const int force_v = getenv("KC_TILE_V") ? atoi(getenv("KC_TILE_V")) : 0;
-    static const int force_stages = getenv("KC_STAGES") ? atoi(getenv("KC_STAGES")) : 0;
-    static const int force_ctas = getenv("KC_CTAS") ? atoi(getenv("KC_CTAS")) : 0;
+    const int force_v = g_kc_tuning.tile_v, force_stages = g_kc_tuning.stages, force_ctas = g_kc_tuning.ctas;
     static const TvmConfig order[] = {{4, 3, 0}, {4, 2, 0}, {2, 3, 0}, {2, 2, 0}, {1, 3, 0}, {1, 2, 0}, {4, 1, 0}, {2, 1, 0}, {1, 1, 0}};
     for (int pass = 0; pass < 2; ++pass) {  // pass 0 honours the tuning overrides, pass 1 ignores them
         for (const TvmConfig& c : order) {
@@ -560,12 +558,21 @@ TvmConfig pick_config(int ns_max, int nt_max, unsigned long long n) {
 
 }  // namespace
 
+int g_kc_last_tile_config[3] = {0, 0, 0};
+extern "C" int32_t kc_debug_last_tile_config(int32_t* v, int32_t* ctas, int32_t* stages) {
+    if (v) *v = g_kc_last_tile_config[0];
+    if (ctas) *ctas = g_kc_last_tile_config[1];
+    if (stages) *stages = g_kc_last_tile_config[2];
+    return KC_OK;
+}
+
 int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     if (args.n == 0 || args.n_seg == 0) return KC_OK;
     int ns_max = 0;
     for (uint32_t s = 0; s < args.n_seg; ++s) ns_max = std::max<int>(ns_max, (int)args.seg[s].n_src);
     const int nt_max = (int)args.variant;  // temporaries the tapes touch (set by the planner)
     const TvmConfig c = pick_config(ns_max, nt_max, args.n);
+    g_kc_last_tile_config[0] = c.v; g_kc_last_tile_config[1] = c.ctas; g_kc_last_tile_config[2] = c.stages;
     KcTimed timed(ctx, KC_KERNEL_TAPE);
     int32_t rc;
     const bool exact = ctx->opts.math_mode == KC_MATH_EXACT;

@@ -471,7 +471,7 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
     if (!no_fused && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT) {
         // threads per CTA: 4 output columns each.  Narrow CTAs (one or two warps) march
         // independently, so no warp waits at a barrier for another's vertical pass.
-        static const int env_threads = getenv("KC_RESIZE_THREADS") ? atoi(getenv("KC_RESIZE_THREADS")) : 0;
+        const int env_threads = g_kc_tuning.resize_threads;
         const int threads = env_threads == 32 || env_threads == 64 || env_threads == 128 ? env_threads : FS_DEFAULT_THREADS;
         const uint32_t tw = (uint32_t)threads * FS_CPT;
         // row pitch a multiple of 4 floats: the vertical pass reads column quads (LDS.128); the
