@@ -280,6 +280,29 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
+// resolved instruction word (built by launch_tile_vm from the planner's op | arg << 8):
+//   bits 0-3 op, bit 4 operand is a temporary, bit 5 operand is the immediate,
+//   bits 8.. : operand byte offset inside the stage (sources) or the temporaries' block,
+//              the output index (ST_OUT) or the sRGB flag (PACK_*)
+constexpr uint32_t KC_R_TMP = 1u << 4;
+constexpr uint32_t KC_R_IMM = 1u << 5;
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+#define KC_INPLACE4(INS, A_, X_)                          \
+    do {                                                  \
+        asm(INS : "+f"((A_).x) : "f"((X_).x));            \
+        asm(INS : "+f"((A_).y) : "f"((X_).y));            \
+        asm(INS : "+f"((A_).z) : "f"((X_).z));            \
+        asm(INS : "+f"((A_).w) : "f"((X_).w));            \
+    } while (0)
+
 template <bool EXACT, int V, int MINB>
 __global__ void __launch_bounds__(TVM_THREADS, MINB)
     kc_tile_vm_kernel(const __grid_constant__ KcTapeArgs A, int stages, int ns_max, uint32_t tiles_per_plane, uint32_t total_work) {
@@ -342,25 +365,30 @@ __global__ void __launch_bounds__(TVM_THREADS, MINB)
             }
         }
         // ---- interpret the segment's tape over this tile ---------------------------------
+        // The launch code resolved every operand to a byte offset (KC_R_* below), so decoding an
+        // instruction is: constant-bank load, mask, one add, LDS.128.  The cheap ops update the
+        // accumulator in place (inline PTX with "+f" operands): the compiler then keeps ONE copy
+        // of acc across the switch arms instead of shuffling it through phi moves.
         float4 acc[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t src_addr = smem_u32(sbuf) + (uint32_t)tid * 16u;
+        const uint32_t tmp_addr = smem_u32(tmp_base) + (uint32_t)tid * 16u;
         const uint32_t pc1 = G.tape_end;
         for (uint32_t pc = G.tape_begin; pc < pc1; ++pc) {
             const uint32_t in = A.instr[pc];
-            const uint32_t op = in & 0xffu;
-            const uint32_t arg = (in >> 8) & 0xffu;
+            const uint32_t op = in & 15u;
+            const uint32_t arg = in >> 8;                 // operand byte offset / output index / sRGB flag
             if (op <= TOP_RPOW) {
                 float4 x[V];
-                if (arg == (uint32_t)KC_ARG_IMM) {
+                if (in & KC_R_IMM) {
                     const float v = A.imm[pc];
 #pragma unroll
                     for (int j = 0; j < V; ++j) x[j] = make_float4(v, v, v, v);
                 } else {
-                    const float* base = arg < (uint32_t)KC_ARG_TMP0 ? sbuf + (size_t)arg * TILE_PX : tmp_base + (size_t)(arg - KC_ARG_TMP0) * TILE_PX;
-                    const float4* xp = reinterpret_cast<const float4*>(base) + tid;
+                    const uint32_t addr = ((in & KC_R_TMP) ? tmp_addr : src_addr) + arg;
 #pragma unroll
-                    for (int j = 0; j < V; ++j) x[j] = xp[j * TVM_THREADS];
+                    for (int j = 0; j < V; ++j) x[j] = lds128(addr + (uint32_t)j * (TVM_THREADS * 16u));
                 }
                 switch (op) {
                     case TOP_LD:
@@ -369,19 +397,19 @@ __global__ void __launch_bounds__(TVM_THREADS, MINB)
                         break;
                     case TOP_ADD:
 #pragma unroll
-                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES(__fadd_rn, acc[j], x[j]);
+                        for (int j = 0; j < V; ++j) KC_INPLACE4("add.rn.f32 %0, %0, %1;", acc[j], x[j]);
                         break;
                     case TOP_SUB:
 #pragma unroll
-                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES(__fsub_rn, acc[j], x[j]);
+                        for (int j = 0; j < V; ++j) KC_INPLACE4("sub.rn.f32 %0, %0, %1;", acc[j], x[j]);
                         break;
                     case TOP_RSUB:
 #pragma unroll
-                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES_R(__fsub_rn, acc[j], x[j]);
+                        for (int j = 0; j < V; ++j) KC_INPLACE4("sub.rn.f32 %0, %1, %0;", acc[j], x[j]);
                         break;
                     case TOP_MUL:
 #pragma unroll
-                        for (int j = 0; j < V; ++j) acc[j] = KC_LANES(__fmul_rn, acc[j], x[j]);
+                        for (int j = 0; j < V; ++j) KC_INPLACE4("mul.rn.f32 %0, %0, %1;", acc[j], x[j]);
                         break;
                     case TOP_DIV:
 #pragma unroll
@@ -401,9 +429,8 @@ __global__ void __launch_bounds__(TVM_THREADS, MINB)
                         break;
                 }
             } else if (op == TOP_ST_TMP) {
-                float4* tp = reinterpret_cast<float4*>(tmp_base + (size_t)arg * TILE_PX) + tid;
 #pragma unroll
-                for (int j = 0; j < V; ++j) tp[j * TVM_THREADS] = acc[j];
+                for (int j = 0; j < V; ++j) sts128(tmp_addr + arg + (uint32_t)j * (TVM_THREADS * 16u), acc[j]);
             } else if (op == TOP_ST_OUT) {
                 float* o = G.out[arg] + px0;
                 if (full) {
@@ -526,7 +553,25 @@ int32_t launch_tile_vm(kc_context* ctx, const KcTapeArgs& a, int stages, int ns_
     if (total > 0xffffffffull) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane too large for one launch");
     // persistent grid: one CTA per resident slot, each walks work items w, w+grid, ...
     const uint64_t grid = std::min<uint64_t>(total, (uint64_t)ctx->sm_count * ctas_per_sm);
-    kc_tile_vm_kernel<EXACT, V, MINB><<<(unsigned)grid, TVM_THREADS, smem, ctx->stream>>>(a, stages, ns_max, (uint32_t)tiles, (uint32_t)total);
+    // resolve operands to byte offsets for this tile size (see KC_R_*)
+    KcTapeArgs r = a;
+    uint32_t n_instr = 0;
+    for (uint32_t q = 0; q < a.n_seg; ++q) n_instr = std::max(n_instr, a.seg[q].tape_end);
+    for (uint32_t pc = 0; pc < n_instr; ++pc) {
+        const uint32_t op = a.instr[pc] & 0xffu, arg = (a.instr[pc] >> 8) & 0xffu;
+        uint32_t w = op;
+        if (op <= TOP_RPOW) {
+            if (arg == (uint32_t)KC_ARG_IMM) w |= KC_R_IMM;
+            else if (arg >= (uint32_t)KC_ARG_TMP0) w |= KC_R_TMP | (((arg - KC_ARG_TMP0) * (uint32_t)TILE_PX * 4u) << 8);
+            else w |= (arg * (uint32_t)TILE_PX * 4u) << 8;
+        } else if (op == TOP_ST_TMP) {
+            w |= (arg * (uint32_t)TILE_PX * 4u) << 8;
+        } else {
+            w |= arg << 8;
+        }
+        r.instr[pc] = w;
+    }
+    kc_tile_vm_kernel<EXACT, V, MINB><<<(unsigned)grid, TVM_THREADS, smem, ctx->stream>>>(r, stages, ns_max, (uint32_t)tiles, (uint32_t)total);
     return KC_OK;
 }
 
@@ -546,7 +591,7 @@ TvmConfig pick_config(int ns_max, int nt_max, unsigned long long n) {
             if (c.v > 1 && n <= (unsigned long long)512 * c.v) continue;
             const size_t budget = (size_t)(227 * 1024) / (size_t)c.ctas - 1024 - 128;
             const size_t tile_b = (size_t)4096 * c.v;
-            for (int st = 4; st >= 2; --st) {
+            for (int st = 4; st >= (force_stages == 1 ? 1 : 2); --st) {
                 if (pass == 0 && force_stages && st != force_stages) continue;
                 if (!force_stages && ns_max > 0 && st > 2 && c.ctas >= 2 && (size_t)(st * ns_max + nt_max) * tile_b > budget) continue;
                 if ((size_t)(st * ns_max + nt_max) * tile_b <= budget) return TvmConfig{c.v, c.ctas, ns_max == 0 ? 2 : st};
