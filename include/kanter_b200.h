@@ -170,6 +170,15 @@ int32_t kc_context_set_fuse(kc_context* ctx, int32_t fuse);
  * src/transient_buffer.rs:413-420) */
 int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_launches, uint64_t* bytes_live);
 
+/* ---- PNG codec on the host (zlib), replaces the `image` crate at the three call sites that
+ *      touch files: read_slot_image src/shared.rs:218-261, Image node src/node/image.rs:10-26,
+ *      Write node src/node/write.rs:5-21.  Decoding yields the interleaved 8-bit samples
+ *      `DynamicImage::as_flat_samples_u8` would (1..4 channels); buffers are freed with kc_free. */
+int32_t kc_png_decode(const uint8_t* data, size_t n, uint8_t** samples, uint32_t* w, uint32_t* h, uint32_t* channels);
+int32_t kc_png_decode_file(const char* path, uint8_t** samples, uint32_t* w, uint32_t* h, uint32_t* channels);
+int32_t kc_png_encode(const uint8_t* samples, uint32_t w, uint32_t h, uint32_t channels, uint8_t** png, size_t* n);
+int32_t kc_png_encode_file(const char* path, const uint8_t* samples, uint32_t w, uint32_t h, uint32_t channels);
+
 /* tuning knobs for the sweep scripts (0 = library default): "tile_v", "ctas", "stages",
  * "src_soft_cap", "resize_threads"; process-wide */
 int32_t kc_debug_set_tuning(const char* key, int32_t value);

@@ -82,6 +82,10 @@ SIGNATURES = {
     "kc_context_set_fuse": (i32, [vp, i32]),
     "kc_context_stats": (i32, [vp, P(u64), P(u64)]),
     "kc_context_trim": (i32, [vp]),
+    "kc_png_decode": (i32, [vp, sz, P(vp), P(u32), P(u32), P(u32)]),
+    "kc_png_decode_file": (i32, [C.c_char_p, P(vp), P(u32), P(u32), P(u32)]),
+    "kc_png_encode": (i32, [vp, u32, u32, u32, P(vp), P(sz)]),
+    "kc_png_encode_file": (i32, [C.c_char_p, vp, u32, u32, u32]),
     "kc_debug_set_tuning": (i32, [C.c_char_p, i32]),
     "kc_debug_last_tile_config": (i32, [P(i32), P(i32), P(i32)]),
     "kc_context_set_timing": (i32, [vp, i32]),
@@ -181,7 +185,7 @@ SIGNATURES = {
     "kc_live_graph_last_run_stats": (i32, [vp, P(u64), P(u64), P(u64)]),
 }
 
-_NO_STATUS = {"kc_abi_version"}
+_NO_STATUS = {"kc_abi_version", "kc_free"}
 
 
 class TexProError(Exception):

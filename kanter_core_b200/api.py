@@ -576,6 +576,14 @@ class _Context:
             self._h = None
 
 
+def _is_png(path):
+    try:
+        with open(path, "rb") as f:
+            return f.read(8) == b"\x89PNG\r\n\x1a\n"
+    except OSError:
+        return False
+
+
 def _decode_image(path):
     """Host-side codec for Image nodes (image::open + as_flat_samples_u8,
     src/shared.rs:16-56,241): 8-bit samples, 1..4 channels."""
@@ -724,12 +732,17 @@ class LiveGraph(_GraphView):
         call("kc_live_graph_replace_embedded", self._h, C.byref(image._im), int(esd_id))
 
     def _load_images(self):
-        # the Image node's codec runs on the host side of the boundary
+        # PNG files are decoded by the library itself (kc_png.cu) when the Image node runs; any
+        # other format the `image` crate would have opened is decoded here with Pillow and handed
+        # over as u8 samples
         if not self._scan_images:
             return
         self._scan_images = False
         for n in self.nodes:
             if n.node_type.kind == _lib.NODE_IMAGE and self._images_loaded.get(int(n.node_id)) != n.node_type.payload:
+                if _is_png(n.node_type.payload):
+                    self._images_loaded[int(n.node_id)] = n.node_type.payload
+                    continue
                 try:
                     px = _decode_image(n.node_type.payload)
                 except Exception:

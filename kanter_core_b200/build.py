@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libkanter_b200.so")
-SOURCES = ["kc_context.cu", "kc_kernels.cu", "kc_fusion.cu", "kc_h2n.cu", "kc_resize.cu", "kc_graph.cu", "kc_exec.cu"]
+SOURCES = ["kc_context.cu", "kc_kernels.cu", "kc_fusion.cu", "kc_h2n.cu", "kc_resize.cu", "kc_graph.cu", "kc_exec.cu", "kc_png.cu"]
 HEADERS = ["kc_internal.h", "kc_graph.h", os.path.join("..", "..", "include", "kanter_b200.h")]
 
 NVCC_FLAGS = [
@@ -63,7 +63,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed")
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc_path(), "-shared", "-cudart", "static", "-o", LIB] + objs
+    cmd = [nvcc_path(), "-shared", "-cudart", "static", "-o", LIB] + objs + ["-lz"]
     subprocess.check_call(cmd)
     return LIB
 

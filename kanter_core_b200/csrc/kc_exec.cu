@@ -381,6 +381,15 @@ int32_t process_node(kc_context* ctx, const KcNode& node, const std::vector<Slot
             if (images) {
                 auto it = images->find(node.name);
                 if (it != images->end()) px = &it->second;
+                if (!px) {
+                    // nobody handed in decoded samples: read the file here (read_slot_image,
+                    // src/shared.rs:218-261); PNG is the format the C++ side decodes
+                    ImagePixels dec;
+                    if (kc_png_decode_file_vec(node.name.c_str(), dec.px, dec.w, dec.h, dec.ch) == KC_OK) {
+                        px = &(*images)[node.name];
+                        *px = std::move(dec);
+                    }
+                }
             }
             if (!px) {  // unreadable file => 1x1 magenta
                 Img im;
@@ -410,8 +419,15 @@ int32_t process_node(kc_context* ctx, const KcNode& node, const std::vector<Slot
             push(0, Img(f->image));
             break;
         }
-        case KC_NODE_WRITE:  // src/node/write.rs:5-21: file output belongs to the host application
+        case KC_NODE_WRITE: {  // src/node/write.rs:5-21: save_buffer(path, image.to_u8(), Rgba8); no outputs
+            if (!sd.empty()) {
+                const Img& im = sd[0].image;
+                std::vector<uint8_t> rgba((size_t)im.w() * im.h() * 4);
+                KC_TRY(kc_image_to_u8(ctx, &im.im, 0, rgba.data()));
+                KC_TRY(kc_png_write_file(node.name.c_str(), rgba.data(), im.w(), im.h(), 4));
+            }
             break;
+        }
         case KC_NODE_VALUE:  // src/node/value.rs:14-26
             push(0, img_pixel(ctx, node.value));
             break;

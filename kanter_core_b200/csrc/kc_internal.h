@@ -220,6 +220,11 @@ int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out);
 void kc_dev_free(kc_context* ctx, void* p, size_t bytes);
 void kc_dev_trim(kc_context* ctx);
 
+// ---- PNG codec on the host (kc_png.cu) ------------------------------------------
+int32_t kc_png_decode_vec(const uint8_t* data, size_t n, std::vector<uint8_t>& samples, uint32_t& w, uint32_t& h, uint32_t& ch);
+int32_t kc_png_decode_file_vec(const char* path, std::vector<uint8_t>& samples, uint32_t& w, uint32_t& h, uint32_t& ch);
+int32_t kc_png_write_file(const char* path, const uint8_t* px, uint32_t w, uint32_t h, int ch);
+
 // ---- plane helpers (kc_context.cu) -------------------------------------------
 int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out);
 kc_plane* kcp_new_const(kc_context* ctx, uint32_t w, uint32_t h, float v);

@@ -125,3 +125,47 @@ def test_h2n_on_rgba_input_is_invalid_buffer_count(tex_pro):
     with pytest.raises(kc.TexProError) as ei:
         lg.connect(e, h, SlotId(0), SlotId(0))
     assert ei.value.kind == "InvalidSlotType"
+
+
+def test_write_node_saves_what_the_reference_would(tex_pro, tmp_path):
+    """Image (PNG decoded by the library) -> Mix -> Write: the file holds image.to_u8() as RGBA8
+    (src/node/write.rs:5-21), equal to the oracle's bytes for the same graph."""
+    from PIL import Image as PILImage
+    from kanter_core_b200 import MixType, Node, NodeGraph, NodeType
+    path = str(tmp_path / "written.png")
+    g = NodeGraph.new()
+    i1 = g.add_node(Node.new(NodeType.Image(graphs.IMAGE_1)))
+    i2 = g.add_node(Node.new(NodeType.Image(graphs.IMAGE_2)))
+    m = g.add_node(Node.new(NodeType.Mix(MixType.Multiply)))
+    w = g.add_node(Node.new(NodeType.Write(path)))
+    g.connect(i1, m, SlotId(0), SlotId(0))
+    g.connect(i2, m, SlotId(0), SlotId(1))
+    g.connect(m, w, SlotId(0), SlotId(0))
+    lg = tex_pro.new_live_graph()
+    lg.set_node_graph(g)
+    kc.LiveGraph.await_clean_read(lg, w)
+    got = np.asarray(PILImage.open(path))
+    # the oracle evaluates the graph up to the Mix node (the reference cannot even list a Write
+    # node's slots -- `unimplemented!()`, src/node/node_type.rs -- so its restatement has none)
+    g2 = NodeGraph.new()
+    j1 = g2.add_node(Node.new(NodeType.Image(graphs.IMAGE_1)))
+    j2 = g2.add_node(Node.new(NodeType.Image(graphs.IMAGE_2)))
+    m2 = g2.add_node(Node.new(NodeType.Mix(MixType.Multiply)))
+    g2.connect(j1, m2, SlotId(0), SlotId(0))
+    g2.connect(j2, m2, SlotId(0), SlotId(1))
+    og = graphs.run_oracle(graphs.Case(g2, m2))
+    assert np.array_equal(got, og.buffer_rgba(int(m2), 0))
+
+
+def test_unreadable_image_is_magenta(tex_pro, tmp_path):
+    from kanter_core_b200 import Node, NodeGraph, NodeType
+    bad = tmp_path / "broken.png"
+    bad.write_bytes(b"\x89PNG\r\n\x1a\n garbage")
+    g = NodeGraph.new()
+    i = g.add_node(Node.new(NodeType.Image(str(bad))))
+    o = g.add_node(Node.new(NodeType.OutputRgba("out")))
+    g.connect(i, o, SlotId(0), SlotId(0))
+    lg = tex_pro.new_live_graph()
+    lg.set_node_graph(g)
+    kc.LiveGraph.await_clean_read(lg, o)
+    assert lg.buffer_rgba(o, SlotId(0)).tolist() == [[[255, 0, 255, 255]]]   # src/node/image.rs:13-18
