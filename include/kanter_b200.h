@@ -295,6 +295,10 @@ int32_t kc_graph_connect(kc_graph* g, uint32_t output_id, uint32_t input_id, uin
 int32_t kc_graph_try_connect(kc_graph* g, uint32_t output_id, uint32_t input_id, uint32_t output_slot, uint32_t input_slot); /* try_connect, :394-413 */
 int32_t kc_graph_disconnect_slot(kc_graph* g, uint32_t node_id, int32_t side, uint32_t slot_id);                             /* disconnect_slot, :500-520 */
 int32_t kc_graph_remove_edge(kc_graph* g, const kc_edge* e);                              /* remove_edge, :464-474 */
+int32_t kc_graph_can_connect(const kc_graph* g, uint32_t output_id, uint32_t input_id, uint32_t output_slot, uint32_t input_slot); /* can_connect, :376-393 */
+int32_t kc_graph_connected_edges(const kc_graph* g, uint32_t node_id, int32_t side, uint32_t slot_id, kc_edge* edges, size_t cap, size_t* n); /* :518-537 */
+int32_t kc_graph_new_id(kc_graph* g, uint32_t* out);                                          /* new_id, :86-96 */
+int32_t kc_graph_rename_output_node(kc_graph* g, uint32_t node_id, const char* new_name, char** old_name); /* :232-270; kc_free old_name */
 int32_t kc_graph_node_count(const kc_graph* g, size_t* n);
 int32_t kc_graph_node_at(const kc_graph* g, size_t index, kc_node_desc* out);  /* borrowed name/graph pointers */
 int32_t kc_graph_node(const kc_graph* g, uint32_t node_id, kc_node_desc* out); /* node, :129-135 */
@@ -347,6 +351,15 @@ int32_t kc_live_graph_slot_data_size(const kc_live_graph* lg, uint32_t node_id, 
 int32_t kc_live_graph_node_slot_ids(const kc_live_graph* lg, uint32_t node_id, uint32_t* slot_ids, size_t cap, size_t* n);    /* node_slot_datas, :389-405 */
 int32_t kc_live_graph_buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host_rgba8, size_t cap);   /* buffer_rgba, :93-95 */
 int32_t kc_live_graph_buffer_srgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host_rgba8, size_t cap);  /* try_buffer_srgba's to_u8_srgb, :127-153 */
+/* ---- LiveGraph bookkeeping, src/live_graph.rs (id lists: pass ids == NULL to get the count) ---- */
+int32_t kc_live_graph_changed_consume(kc_live_graph* lg, uint32_t* ids, size_t cap, size_t* n);                 /* changed_consume, :156-160 */
+int32_t kc_live_graph_node_ids_with_state(const kc_live_graph* lg, int32_t state, int32_t without, uint32_t* ids, size_t cap, size_t* n); /* :261-277 */
+int32_t kc_live_graph_get_closest_processable(const kc_live_graph* lg, uint32_t node_id, uint32_t* ids, size_t cap, size_t* n);       /* :279-311 */
+int32_t kc_live_graph_mark(kc_live_graph* lg, uint32_t node_id, int32_t state);   /* request :219-227 / prioritise :229-237: state change only */
+int32_t kc_live_graph_update(kc_live_graph* lg, size_t* n_processed);             /* one engine turn for this graph, src/engine.rs:128-183 */
+int32_t kc_live_graph_remove_edge(kc_live_graph* lg, const kc_edge* e);           /* remove_edge, :551-566 */
+int32_t kc_live_graph_rename_output_node(kc_live_graph* lg, uint32_t node_id, const char* new_name, char** old_name); /* :625-627 */
+int32_t kc_live_graph_new_id(kc_live_graph* lg, uint32_t* out);                   /* new_id, :422-424 */
 /* await_clean_read + buffer_rgba in one call, so the f32 -> RGBA8 conversion
  * fuses into the kernel that produces the node's planes (never stored as f32) */
 int32_t kc_live_graph_read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host_rgba8, size_t cap);

@@ -142,6 +142,10 @@ SIGNATURES = {
     "kc_graph_try_connect": (i32, [vp, u32, u32, u32, u32]),
     "kc_graph_disconnect_slot": (i32, [vp, u32, i32, u32]),
     "kc_graph_remove_edge": (i32, [vp, P(kc_edge)]),
+    "kc_graph_can_connect": (i32, [vp, u32, u32, u32, u32]),
+    "kc_graph_connected_edges": (i32, [vp, u32, i32, u32, P(kc_edge), sz, P(sz)]),
+    "kc_graph_new_id": (i32, [vp, P(u32)]),
+    "kc_graph_rename_output_node": (i32, [vp, u32, C.c_char_p, P(vp)]),
     "kc_graph_node_count": (i32, [vp, P(sz)]),
     "kc_graph_node_at": (i32, [vp, sz, P(kc_node_desc)]),
     "kc_graph_node": (i32, [vp, u32, P(kc_node_desc)]),
@@ -180,6 +184,14 @@ SIGNATURES = {
     "kc_live_graph_node_slot_ids": (i32, [vp, u32, P(u32), sz, P(sz)]),
     "kc_live_graph_buffer_rgba": (i32, [vp, u32, u32, vp, sz]),
     "kc_live_graph_buffer_srgba": (i32, [vp, u32, u32, vp, sz]),
+    "kc_live_graph_changed_consume": (i32, [vp, P(u32), sz, P(sz)]),
+    "kc_live_graph_node_ids_with_state": (i32, [vp, i32, i32, P(u32), sz, P(sz)]),
+    "kc_live_graph_get_closest_processable": (i32, [vp, u32, P(u32), sz, P(sz)]),
+    "kc_live_graph_mark": (i32, [vp, u32, i32]),
+    "kc_live_graph_update": (i32, [vp, P(sz)]),
+    "kc_live_graph_remove_edge": (i32, [vp, P(kc_edge)]),
+    "kc_live_graph_rename_output_node": (i32, [vp, u32, C.c_char_p, P(vp)]),
+    "kc_live_graph_new_id": (i32, [vp, P(u32)]),
     "kc_live_graph_read_rgba": (i32, [vp, u32, u32, i32, vp, sz]),
     "kc_live_graph_read_rgba_async": (i32, [vp, u32, u32, i32, vp, sz]),
     "kc_live_graph_last_run_stats": (i32, [vp, P(u64), P(u64), P(u64)]),

@@ -362,6 +362,28 @@ class _GraphView:
         self.has_node_with_id(node_id)
         return sorted({e.input_id for e in self.edges if e.output_id == node_id})
 
+    def can_connect(self, output_node, input_node, output_slot, input_slot):  # node_graph.rs:376-393
+        call("kc_graph_can_connect", self._graph_handle(), int(output_node), int(input_node), int(output_slot), int(input_slot))
+
+    def connected_edges(self, node_id, side, slot_id):  # node_graph.rs:518-537
+        arr = (kc_edge * 256)()
+        n = C.c_size_t()
+        call("kc_graph_connected_edges", self._graph_handle(), int(node_id), int(side), int(slot_id), arr, 256, C.byref(n))
+        return [Edge(e.output_id, e.input_id, e.output_slot, e.input_slot) for e in arr[:n.value]]
+
+    def get_children_recursive(self, node_id):  # node_graph.rs:566-575 (duplicates kept, like the reference)
+        kids = self.get_children(node_id)
+        out = list(kids)
+        for c in kids:
+            out += self.get_children_recursive(c)
+        return out
+
+    def output_names(self):
+        return [n.node_type.payload for n in self.nodes if n.node_type.is_output()]
+
+    def input_names(self):
+        return [n.node_type.payload for n in self.nodes if n.node_type.is_input()]
+
     def export_json_string(self):
         p = C.c_void_p()
         call("kc_graph_export_json", self._graph_handle(), C.byref(p))
@@ -441,6 +463,19 @@ class NodeGraph(_GraphView):
     def remove_edge(self, edge):
         e = kc_edge(*edge._tuple())
         call("kc_graph_remove_edge", self._h, C.byref(e))
+
+    def new_id(self):  # :86-96
+        out = C.c_uint32()
+        call("kc_graph_new_id", self._h, C.byref(out))
+        return NodeId(out.value)
+
+    def rename_output_node(self, node_id, new_name):  # :232-270, returns the old name
+        p = C.c_void_p()
+        call("kc_graph_rename_output_node", self._h, int(node_id), new_name.encode(), C.byref(p))
+        try:
+            return C.string_at(p).decode("utf-8")
+        finally:
+            _lib.lib.kc_free(p)
 
     def set_mix_type(self, node_id, mix_type):  # :48-63
         n = self.node(node_id)
@@ -764,7 +799,22 @@ class LiveGraph(_GraphView):
         ids = (C.c_uint32 * len(node_ids))(*[int(i) for i in node_ids])
         call("kc_live_graph_request", self._h, ids, len(node_ids))
 
-    prioritise = request
+    # -- the reference's request()/prioritise() only change the node's state and leave the work to
+    #    the engine thread; `request` above does both at once.  These are the two halves:
+    def mark_requested(self, node_id):  # request, :219-227 (state change only)
+        call("kc_live_graph_mark", self._h, int(node_id), int(NodeState.Requested))
+
+    def prioritise(self, node_id):  # :229-237 (state change only)
+        call("kc_live_graph_mark", self._h, int(node_id), int(NodeState.Prioritised))
+
+    def update(self):
+        """One turn of the engine for this graph (src/engine.rs:128-183): evaluates the Requested /
+        Prioritised nodes -- every non-clean node when auto_update is set -- with their dirty
+        ancestors.  Returns how many nodes were wanted."""
+        self._load_images()
+        n = C.c_size_t()
+        call("kc_live_graph_update", self._h, C.byref(n))
+        return n.value
 
     @staticmethod
     def await_clean_read(live_graph, node_id):  # :181-195
@@ -772,7 +822,61 @@ class LiveGraph(_GraphView):
         call("kc_live_graph_await_clean", live_graph._h, int(node_id))
         return live_graph
 
-    await_clean_write = await_clean_read
+    await_clean_write = await_clean_read  # :164-179: same wait, a write guard in the reference
+
+    def _id_list(self, fn, *args):
+        n = C.c_size_t()
+        call(fn, self._h, *args, None, 0, C.byref(n))
+        arr = (C.c_uint32 * max(1, n.value))()
+        call(fn, self._h, *args, arr, n.value, C.byref(n))
+        return [NodeId(arr[i]) for i in range(n.value)]
+
+    def changed_consume(self):  # :156-160
+        return self._id_list("kc_live_graph_changed_consume")
+
+    def node_ids_with_state(self, node_state):  # :270-277
+        return self._id_list("kc_live_graph_node_ids_with_state", int(node_state), 0)
+
+    def node_ids_without_state(self, node_state):  # :261-268
+        return self._id_list("kc_live_graph_node_ids_with_state", int(node_state), 1)
+
+    def get_closest_processable(self, node_id):  # :279-311
+        return self._id_list("kc_live_graph_get_closest_processable", int(node_id))
+
+    def remove_edge(self, edge):  # :551-566
+        e = kc_edge(int(edge.output_id), int(edge.input_id), int(edge.output_slot), int(edge.input_slot))
+        call("kc_live_graph_remove_edge", self._h, C.byref(e))
+        return edge
+
+    def rename_output_node(self, node_id, new_name):  # :625-627, returns the old name
+        p = C.c_void_p()
+        call("kc_live_graph_rename_output_node", self._h, int(node_id), new_name.encode(), C.byref(p))
+        try:
+            return C.string_at(p).decode("utf-8")
+        finally:
+            _lib.lib.kc_free(p)
+
+    def new_id(self):  # :422-424
+        out = C.c_uint32()
+        call("kc_live_graph_new_id", self._h, C.byref(out))
+        return NodeId(out.value)
+
+    def has_node(self, node_id):  # :361-363
+        self.node(node_id)
+
+    def set_node_with_id(self, node_id, node):  # :376-387
+        node.node_id = NodeId(node_id)
+        self.set_node(node)
+
+    def slot_in_memory(self, node_id, slot_id):  # :410-412: planes live in HBM, nothing spills
+        self.slot_data_size(node_id, slot_id)
+        return True
+
+    def try_buffer_rgba(self, node_id, slot_id):  # :98-125 (never blocks here: no spill queue)
+        return self.buffer_rgba(node_id, slot_id)
+
+    def try_buffer_srgba(self, node_id, slot_id):  # :127-153
+        return self.buffer_srgba(node_id, slot_id)
 
     def cancel(self):
         call("kc_live_graph_cancel", self._h)

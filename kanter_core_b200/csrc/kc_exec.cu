@@ -508,6 +508,7 @@ struct kc_live_graph {
     ImageStore own_images;
     ImageStore* images = &own_images;
     std::map<uint32_t, int> state;
+    std::set<uint32_t> changed;   // LiveGraph::changed, live_graph.rs:69: every node whose state or wiring changed since changed_consume
     bool use_cache = false, auto_update = false;
     uint64_t last_kernels = 0, last_groups = 0, last_bytes = 0;
 
@@ -555,6 +556,7 @@ struct kc_live_graph {
             if (!seen.insert(n).second) continue;
             auto it = state.find(n);
             if (it == state.end()) continue;
+            if (it->second != KC_STATE_DIRTY) changed.insert(n);
             it->second = KC_STATE_DIRTY;
             remove_nodes_data(n);
             for (uint32_t c : children(n)) work.push_back(c);
@@ -626,6 +628,7 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
             remove_nodes_data(node.node_id);
             for (Slot& s : out) slot_datas.push_back(std::move(s));
             state[node.node_id] = KC_STATE_CLEAN;
+            changed.insert(node.node_id);
             // free the parents' data once every child of theirs has run, engine.rs:58-75
             // (nodes the caller asked for keep theirs)
             if (!use_cache) {
@@ -931,6 +934,7 @@ int32_t kc_live_graph_add_node(kc_live_graph* lg, const kc_node_desc* node, uint
     uint32_t id = 0;
     KC_TRY(kc_graph_add_node(&lg->graph, node, &id));
     lg->state[id] = KC_STATE_DIRTY;  // add_node_internal, live_graph.rs:445-449
+    lg->changed.insert(id);
     if (out_node_id) *out_node_id = id;
     return KC_OK;
 }
@@ -938,6 +942,7 @@ int32_t kc_live_graph_add_node_with_id(kc_live_graph* lg, const kc_node_desc* no
     if (!lg || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(kc_graph_add_node_with_id(&lg->graph, node));
     lg->state[node->node_id] = KC_STATE_DIRTY;
+    lg->changed.insert(node->node_id);
     return KC_OK;
 }
 int32_t kc_live_graph_remove_node(kc_live_graph* lg, uint32_t node_id) {
@@ -949,7 +954,8 @@ int32_t kc_live_graph_remove_node(kc_live_graph* lg, uint32_t node_id) {
     KC_TRY(kcg_remove_node(lg->graph, node_id, &removed));
     lg->remove_nodes_data(node_id);
     lg->state.erase(node_id);
-    for (uint32_t c : kids) lg->set_dirty(c);
+    lg->changed.insert(node_id);
+    for (uint32_t c : kids) { lg->changed.insert(c); lg->set_dirty(c); }
     return KC_OK;
 }
 int32_t kc_live_graph_connect(kc_live_graph* lg, uint32_t o, uint32_t i, uint32_t os, uint32_t is) {
@@ -957,6 +963,7 @@ int32_t kc_live_graph_connect(kc_live_graph* lg, uint32_t o, uint32_t i, uint32_
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard guard(lg->ctx);
     KC_TRY(kcg_connect(lg->graph, o, i, os, is));
+    lg->changed.insert(i);
     lg->set_dirty(i);
     return KC_OK;
 }
@@ -967,6 +974,7 @@ int32_t kc_live_graph_disconnect_slot(kc_live_graph* lg, uint32_t node_id, int32
     std::vector<kc_edge> removed;
     KC_TRY(kcg_disconnect_slot(lg->graph, node_id, side, slot_id, &removed));
     for (const kc_edge& e : removed) lg->set_dirty(e.input_id);
+    if (side != 0) lg->changed.insert(node_id);   // Side::Output: live_graph.rs:585-589
     return KC_OK;
 }
 int32_t kc_live_graph_set_node(kc_live_graph* lg, const kc_node_desc* node) {
@@ -1044,6 +1052,99 @@ int32_t kc_live_graph_set_image_data_u8(kc_live_graph* lg, uint32_t node_id, con
     lg->set_dirty(node_id);
     return KC_OK;
 }
+// ---- the rest of LiveGraph's bookkeeping surface, src/live_graph.rs ---------------------
+static int32_t copy_ids(const std::vector<uint32_t>& v, uint32_t* ids, size_t cap, size_t* n) {
+    if (!n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    *n = v.size();
+    if (ids)
+        for (size_t i = 0; i < v.size() && i < cap; ++i) ids[i] = v[i];
+    return KC_OK;
+}
+int32_t kc_live_graph_changed_consume(kc_live_graph* lg, uint32_t* ids, size_t cap, size_t* n) {
+    // changed_consume, :156-160.  Call with ids == NULL to size the buffer (nothing is consumed then).
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    std::vector<uint32_t> v(lg->changed.begin(), lg->changed.end());
+    KC_TRY(copy_ids(v, ids, cap, n));
+    if (ids && cap >= v.size()) lg->changed.clear();
+    return KC_OK;
+}
+int32_t kc_live_graph_node_ids_with_state(const kc_live_graph* lg, int32_t state, int32_t without, uint32_t* ids, size_t cap, size_t* n) {
+    // node_ids_with_state / node_ids_without_state, :261-277 (ascending NodeId: BTreeMap order)
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    std::vector<uint32_t> v;
+    for (const auto& kv : lg->state)
+        if ((kv.second == state) != (without != 0)) v.push_back(kv.first);
+    return copy_ids(v, ids, cap, n);
+}
+static void closest_processable(const kc_live_graph* lg, uint32_t id, std::vector<uint32_t>& out) {
+    std::vector<uint32_t> dirty;
+    bool processing = false;
+    for (uint32_t p : lg->parents(id)) {
+        auto it = lg->state.find(p);
+        const int st = it == lg->state.end() ? KC_STATE_CLEAN : it->second;
+        if (st == KC_STATE_PROCESSING || st == KC_STATE_PROCESSING_DIRTY) processing = true;
+        else if (st != KC_STATE_CLEAN) dirty.push_back(p);
+    }
+    if (dirty.empty() && !processing) out.push_back(id);
+    else
+        for (uint32_t p : dirty) closest_processable(lg, p, out);
+}
+int32_t kc_live_graph_get_closest_processable(const kc_live_graph* lg, uint32_t node_id, uint32_t* ids, size_t cap, size_t* n) {
+    // get_closest_processable, :279-311
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!kcg_find(lg->graph, node_id)) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
+    std::vector<uint32_t> v;
+    closest_processable(lg, node_id, v);
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    return copy_ids(v, ids, cap, n);
+}
+int32_t kc_live_graph_mark(kc_live_graph* lg, uint32_t node_id, int32_t state) {
+    // request (:219-227): Dirty -> Requested;  prioritise (:229-237): Dirty | Requested -> Prioritised.
+    // Only the state changes; kc_live_graph_update does the engine's work.
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    auto it = lg->state.find(node_id);
+    if (it == lg->state.end()) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
+    if (state == KC_STATE_REQUESTED) {
+        if (it->second == KC_STATE_DIRTY) it->second = KC_STATE_REQUESTED;
+    } else if (state == KC_STATE_PRIORITISED) {
+        if (it->second == KC_STATE_DIRTY || it->second == KC_STATE_REQUESTED) it->second = KC_STATE_PRIORITISED;
+    } else {
+        KC_FAIL(KC_ERR_INVALID_ARGUMENT, "only Requested and Prioritised can be marked");
+    }
+    return KC_OK;
+}
+int32_t kc_live_graph_update(kc_live_graph* lg, size_t* n_processed) {
+    // one turn of the engine's loop for this graph (src/engine.rs:128-183): with auto_update every
+    // node that is not Clean is wanted, otherwise the Requested and Prioritised ones; they and
+    // their dirty ancestors are evaluated
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    std::vector<uint32_t> want;
+    for (const auto& kv : lg->state) {
+        const bool w = lg->auto_update ? kv.second != KC_STATE_CLEAN : (kv.second == KC_STATE_REQUESTED || kv.second == KC_STATE_PRIORITISED);
+        if (w) want.push_back(kv.first);
+    }
+    if (n_processed) *n_processed = want.size();
+    if (want.empty()) return KC_OK;
+    return lg->evaluate(want.data(), want.size(), true);
+}
+int32_t kc_live_graph_remove_edge(kc_live_graph* lg, const kc_edge* e) {
+    // remove_edge, :551-566: the input node and everything downstream become dirty and lose their data
+    if (!lg || !e) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard guard(lg->ctx);
+    KC_TRY(kc_graph_remove_edge(&lg->graph, e));
+    lg->set_dirty(e->input_id);
+    return KC_OK;
+}
+int32_t kc_live_graph_rename_output_node(kc_live_graph* lg, uint32_t node_id, const char* new_name, char** old_name) {
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    return kc_graph_rename_output_node(&lg->graph, node_id, new_name, old_name);   // :625-627
+}
+int32_t kc_live_graph_new_id(kc_live_graph* lg, uint32_t* out) {
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    return kc_graph_new_id(&lg->graph, out);   // :422-424
+}
+
 int32_t kc_live_graph_request(kc_live_graph* lg, const uint32_t* node_ids, size_t n) {
     if (!lg || (n && !node_ids)) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     return lg->evaluate(node_ids, n, true);

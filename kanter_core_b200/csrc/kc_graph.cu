@@ -671,6 +671,63 @@ int32_t kc_graph_try_connect(kc_graph* g, uint32_t o, uint32_t i, uint32_t os, u
     g->edges.push_back(kc_edge{o, i, os, is});
     return KC_OK;
 }
+int32_t kc_graph_can_connect(const kc_graph* g, uint32_t o, uint32_t i, uint32_t os, uint32_t is) {
+    // NodeGraph::can_connect, src/node_graph.rs:376-393
+    if (!g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    const KcNode* on = kcg_find(*g, o);
+    const KcNode* in = kcg_find(*g, i);
+    if (!on || !in) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no such node");
+    int t = 0;
+    KC_TRY(slot_type_lookup(kcg_output_slots(*on), os, &t));
+    KC_TRY(slot_type_lookup(kcg_input_slots(*in), is, &t));
+    for (const kc_edge& e : g->edges)
+        if (e.input_id == i && e.input_slot == is) KC_FAIL(KC_ERR_SLOT_OCCUPIED, "slot %u of node %u is occupied", is, i);
+    return KC_OK;
+}
+int32_t kc_graph_connected_edges(const kc_graph* g, uint32_t node_id, int32_t side, uint32_t slot_id, kc_edge* edges, size_t cap, size_t* n) {
+    // NodeGraph::connected_edges, src/node_graph.rs:518-537 (side 0 = Input, 1 = Output)
+    if (!g || !n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!kcg_find(*g, node_id)) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
+    size_t k = 0;
+    for (const kc_edge& e : g->edges) {
+        const bool hit = side == 0 ? (e.input_id == node_id && e.input_slot == slot_id) : (e.output_id == node_id && e.output_slot == slot_id);
+        if (!hit) continue;
+        if (edges && k < cap) edges[k] = e;
+        ++k;
+    }
+    *n = k;
+    if (k == 0) KC_FAIL(KC_ERR_SLOT_NOT_OCCUPIED, "slot %u of node %u has no edges", slot_id, node_id);
+    return KC_OK;
+}
+int32_t kc_graph_new_id(kc_graph* g, uint32_t* out) {
+    // NodeGraph::new_id, src/node_graph.rs:86-96
+    if (!g || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = new_id(*g);
+    return KC_OK;
+}
+int32_t kc_graph_rename_output_node(kc_graph* g, uint32_t node_id, const char* new_name, char** old_name) {
+    // NodeGraph::rename_output_node, src/node_graph.rs:232-270: the new name is de-collided
+    // against the OTHER output names; returns the old name (kc_free it)
+    if (!g || !new_name) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcNode* node = kcg_find(*g, node_id);
+    if (!node) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
+    if (!kcg_is_output(node->type)) KC_FAIL(KC_ERR_INVALID_NODE_TYPE, "node %u is not an output node", node_id);
+    std::vector<std::string> names;
+    bool skipped = false;
+    for (const KcNode& m : g->nodes) {
+        if (!kcg_is_output(m.type)) continue;
+        if (!skipped && m.name == node->name) { skipped = true; continue; }   // remove the first occurrence of the old name
+        names.push_back(m.name);
+    }
+    const std::string old = node->name;
+    node->name = avoid_name_collision(names, new_name);
+    if (old_name) {
+        *old_name = (char*)malloc(old.size() + 1);
+        if (!*old_name) KC_FAIL(KC_ERR_GENERIC, "out of memory");
+        memcpy(*old_name, old.c_str(), old.size() + 1);
+    }
+    return KC_OK;
+}
 int32_t kc_graph_disconnect_slot(kc_graph* g, uint32_t node_id, int32_t side, uint32_t slot_id) {
     if (!g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     return kcg_disconnect_slot(*g, node_id, side, slot_id, nullptr);

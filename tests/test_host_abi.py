@@ -257,3 +257,43 @@ def test_calculate_size_policies_without_pixels():
     assert size(4, slot=7) == (128, 64)    # absent slot -> lowest connected slot
     assert size(5, pw=300, ph=200) == (300, 200)
     assert size(0, n=0) == (1, 1)          # MostPixels with no inputs
+
+
+def test_node_graph_bookkeeping_surface():
+    """can_connect / connected_edges / new_id / rename_output_node, src/node_graph.rs:86-96,232-270,376-393,518-537."""
+    import kanter_core_b200 as kc
+    from kanter_core_b200 import MixType, Node, NodeGraph, NodeType, Side, SlotId
+    g = NodeGraph.new()
+    a = g.add_node(Node.new(NodeType.Value(0.5)))
+    b = g.add_node(Node.new(NodeType.Value(0.25)))
+    m = g.add_node(Node.new(NodeType.Mix(MixType.Add)))
+    o1 = g.add_node(Node.new(NodeType.OutputGray("out")))
+    o2 = g.add_node(Node.new(NodeType.OutputGray("out")))        # de-collided on insert
+    assert g.output_names() == ["out", "out_0"]
+    g.can_connect(a, m, SlotId(0), SlotId(0))
+    g.connect(a, m, SlotId(0), SlotId(0))
+    with pytest.raises(kc.TexProError) as e:
+        g.can_connect(b, m, SlotId(0), SlotId(0))
+    assert e.value.kind == "SlotOccupied"
+    with pytest.raises(kc.TexProError) as e:
+        g.can_connect(b, m, SlotId(0), SlotId(7))
+    assert e.value.kind == "InvalidSlotId"
+    g.connect(b, m, SlotId(0), SlotId(1))
+    g.connect(m, o1, SlotId(0), SlotId(0))
+    g.connect(m, o2, SlotId(0), SlotId(0))
+    out_edges = g.connected_edges(m, Side.Output, SlotId(0))
+    assert sorted(int(x.input_id) for x in out_edges) == sorted([int(o1), int(o2)])
+    assert [int(x.output_id) for x in g.connected_edges(m, Side.Input, SlotId(1))] == [int(b)]
+    with pytest.raises(kc.TexProError) as e:
+        g.connected_edges(a, Side.Input, SlotId(0))
+    assert e.value.kind == "SlotNotOccupied"
+    assert g.rename_output_node(o2, "out") == "out_0"            # collides with o1's name again
+    assert g.output_names() == ["out", "out_0"]
+    assert g.rename_output_node(o2, "normal") == "out_0"
+    assert g.output_names() == ["out", "normal"]
+    with pytest.raises(kc.TexProError) as e:
+        g.rename_output_node(m, "x")
+    assert e.value.kind == "InvalidNodeType"
+    nid = g.new_id()
+    assert int(nid) not in [int(n) for n in g.node_ids()]
+    assert sorted(int(x) for x in g.get_children_recursive(a)) == sorted([int(m), int(o1), int(o2)])
