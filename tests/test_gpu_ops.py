@@ -123,6 +123,46 @@ def test_height_to_normal_exact(tex_pro, shape):
     assert np.array_equal(got[3], np.ones((h, w), np.float32))
 
 
+@pytest.mark.parametrize("case", ["flat", "tiny_steps", "huge", "mixed_scales", "signed", "big_random", "smooth"])
+def test_height_to_normal_exact_adversarial(tex_pro, case):
+    """EXACT HeightToNormal = the oracle bit for bit on inputs that exercise both the written-out
+    div/sqrt sequences (differences 0 or in [2^-20, 4]) and the guarded IEEE fallback (differences
+    tiny, denormal, huge, infinite)."""
+    r = np.random.default_rng(21)
+    h, w = 96, 256                      # w % 4 == 0: the vector kernel
+    if case == "flat":
+        hgt = np.full((h, w), 0.375, np.float32)
+        hgt[10:20, 30:60] = 0.5         # a plateau: zero differences inside, steps on its rim
+    elif case == "tiny_steps":
+        base = r.random((h, w), dtype=np.float32)
+        step = np.float32(2.0) ** r.integers(-40, -15, (h, w)).astype(np.float32)   # straddles 2^-20
+        hgt = (base + step).astype(np.float32)
+        hgt[::3] = base[::3]
+        hgt[5, :] = np.float32(1e-42)   # denormals
+        hgt[6, :] = 0.0
+    elif case == "huge":
+        hgt = (r.random((h, w), dtype=np.float32) * np.float32(1e30)).astype(np.float32)
+        hgt[7, 9] = np.inf
+        hgt[50, 100] = np.float32(3e38)
+    elif case == "mixed_scales":
+        hgt = (r.random((h, w), dtype=np.float32) * (np.float32(2.0) ** r.integers(-30, 6, (h, w)).astype(np.float32))).astype(np.float32)
+    elif case == "signed":
+        hgt = (r.random((h, w), dtype=np.float32) * 8 - 4).astype(np.float32)         # differences up to 8: both paths
+    elif case == "big_random":
+        h, w = 512, 1024
+        hgt = r.random((h, w), dtype=np.float32)
+    else:
+        yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+        hgt = (0.5 + 0.25 * np.sin(xx / 17.0) * np.cos(yy / 11.0)).astype(np.float32)
+    img = kc.SlotImage.from_planes(tex_pro, [hgt])
+    with np.errstate(all="ignore"):
+        want = oracle.height_to_normal(hgt)
+    got = kc.SlotImage(tex_pro._ctx, _h2n_direct(tex_pro, img)).planes()
+    for c_ in range(3):
+        assert bits_equal(got[c_], want[c_]), "channel %d: %d samples differ" % (
+            c_, int((got[c_].view(np.uint32) != want[c_].view(np.uint32)).sum()))
+
+
 def _h2n_direct(tp, img):
     import ctypes as C
     from kanter_core_b200._lib import call, kc_image
