@@ -194,10 +194,11 @@ __device__ __forceinline__ float kc_pow(float a, float b) {
 //   ((v.clamp(0,1) * 255.).min(255.)) as u8
 // Rust's clamp keeps NaN, min(NaN,255) = 255, `as u8` truncates and saturates.
 __device__ __forceinline__ uint32_t kc_to_u8(float v) {
-    float c = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
-    float m = __fmul_rn(c, 255.0f);
-    m = (m != m) ? 255.0f : fminf(m, 255.0f);
-    return __float2uint_rz(m);
+    // clamp that keeps NaN (min.NaN / max.NaN), then the ordinary min drops it: NaN -> 255
+    float c;
+    asm("min.NaN.f32 %0, %1, 0f3F800000;" : "=f"(c) : "f"(v));
+    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(c) : "f"(c));
+    return __float2uint_rz(fminf(__fmul_rn(c, 255.0f), 255.0f));
 }
 // srgb_to_linear, src/slot_data.rs:100-109, applied to the clamped value (:173-176)
 template <bool EXACT>
@@ -500,6 +501,15 @@ __global__ void __launch_bounds__(256) kc_fill_kernel(float* __restrict__ dst, s
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[4 * nvec + threadIdx.x] = v;
 }
 
+// byte / 255.0f, correctly rounded, without the generic div.rn expansion: q = b*y, q += (b - 255 q)*y
+// with y = RN(1/255).  All 256 inputs are checked against the oracle's `as f32 / 255.` by
+// tests/test_gpu_ops.py::test_u8_roundtrip_every_value.
+__device__ __forceinline__ float kc_u8_over_255(uint32_t byte) {
+    const float a = (float)byte, y = 0x1.010102p-8f;
+    const float q = __fmul_rn(a, y);
+    return __fmaf_rn(__fmaf_rn(-255.0f, q, a), y, q);
+}
+
 // deconstruct_image, src/shared.rs:27-33: plane_c[i] = samples[i*C + c] as f32 / 255.
 // One thread converts 4 consecutive pixels: it reads 4*C bytes and writes one
 // float4 per channel plane.
@@ -520,7 +530,7 @@ __global__ void __launch_bounds__(256) kc_from_u8_kernel(const uint8_t* __restri
 #pragma unroll
         for (int b = 0; b < 4 * C; ++b) {
             const uint32_t byte = (wds[b >> 2] >> (8 * (b & 3))) & 0xffu;
-            vals[b / C][b % C] = __fdiv_rn((float)byte, 255.0f);
+            vals[b / C][b % C] = kc_u8_over_255(byte);
         }
 #pragma unroll
         for (int c = 0; c < C; ++c)
@@ -648,7 +658,7 @@ int32_t kck_fill(kc_context* ctx, float* dst, size_t n, float v) {
 int32_t kck_from_u8(kc_context* ctx, const uint8_t* d_samples, uint32_t channels, size_t n,
                     float* const planes[4]) {
     if (n == 0) return KC_OK;
-    const int grid = grid_for(ctx, (n + 3) >> 2, 256, 8);
+    const int grid = grid_for(ctx, (n + 3) >> 2, 256, 5);   // 5 CTAs of 256 threads are resident per SM: one wave
     KcTimed timed(ctx, KC_KERNEL_FROM_U8);
     switch (channels) {
         case 1: kc_from_u8_kernel<1><<<grid, 256, 0, ctx->stream>>>(d_samples, n, planes[0], planes[1], planes[2], planes[3]); break;
