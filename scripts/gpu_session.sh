@@ -17,7 +17,7 @@ full() {  # name kernel-regex skip math only
       python scripts/kernel_bench.py --math $4 --only $5 --reps 2 > $O/${TAG}_ncu_$1.log 2>&1
 }
 full tilevm_cfg2_fast kc_tile_vm 3 fast config2_fused
-full resize_lanczos3_fast kc_resize_fused 3 fast resize_lanczos3_1024
+full resize_lanczos3_fast kc_resize_strip 3 fast resize_lanczos3_1024
 full h2n_fast kc_h2n_vec 3 fast height_to_normal
 full h2n_exact kc_h2n_vec 3 exact height_to_normal
 full to_u8_rgba kc_tile_vm 3 fast to_u8_rgba
