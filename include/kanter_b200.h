@@ -261,6 +261,10 @@ int32_t kc_height_to_normal_strip(kc_context* ctx, const kc_image* strip, kc_pla
 int32_t kc_plane_copy_rows(kc_context* ctx, kc_plane* dst, uint32_t dst_row, kc_plane* src, uint32_t src_row, uint32_t rows);
 /* resize_buffers' per-plane imageops::resize, src/shared.rs:155-201 */
 int32_t kc_resize(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, int32_t filter, kc_image* out);
+/* rows [row_begin, row_begin + row_count) of that result (out is w x row_count): the share of one GPU when
+ * a resize is tiled over GPUs by output rows; bit-identical to the same rows of kc_resize */
+int32_t kc_resize_rows(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, int32_t filter,
+                       uint32_t row_begin, uint32_t row_count, kc_image* out);
 /* separate_rgba::process / combine_rgba::process (plane aliasing),
  * src/node/separate_rgba.rs:38-69, src/node/combine_rgba.rs:14-97.
  * in may be NULL; channels[i] may be NULL. */

@@ -123,6 +123,7 @@ SIGNATURES = {
     "kc_height_to_normal_strip": (i32, [vp, P(kc_image), vp, u32, P(kc_image)]),
     "kc_plane_copy_rows": (i32, [vp, vp, u32, vp, u32, u32]),
     "kc_resize": (i32, [vp, P(kc_image), u32, u32, i32, P(kc_image)]),
+    "kc_resize_rows": (i32, [vp, P(kc_image), u32, u32, i32, u32, u32, P(kc_image)]),
     "kc_separate_rgba": (i32, [vp, P(kc_image), P(kc_image)]),
     "kc_combine_rgba": (i32, [vp, P(P(kc_image)), P(kc_image)]),
     "kc_calculate_size": (i32, [P(kc_slot_data), sz, P(kc_edge), sz, i32, u32, u32, u32, P(u32), P(u32)]),

@@ -175,7 +175,11 @@ int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullp
 }
 
 // one plane through imageops::resize; returns a new reference
-int32_t plane_resize(kc_context* ctx, kc_plane* src, uint32_t w, uint32_t h, int filter, kc_plane** out) {
+// rows [row0, row0 + nrows) of the w x h resize (the whole image by default)
+int32_t plane_resize(kc_context* ctx, kc_plane* src, uint32_t w, uint32_t h, int filter, kc_plane** out,
+                     uint32_t row0 = 0, uint32_t nrows = 0xffffffffu) {
+    if (nrows == 0xffffffffu) nrows = h;
+    if (row0 > h || nrows > h - row0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "rows [%u, %u) are outside the %u-row result", row0, row0 + nrows, h);
     if (filter < KC_FILTER_NEAREST || filter > KC_FILTER_LANCZOS3) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad filter %d", filter);
     if (src->kind == KC_PLANE_CONST && src->w == 1 && src->h == 1) {
         // A 1x1 source (every Value node) has a single tap per axis whose
@@ -201,14 +205,14 @@ int32_t plane_resize(kc_context* ctx, kc_plane* src, uint32_t w, uint32_t h, int
             float v = 0.0f + src->value * 1.0f;
             v = 0.0f + v * 1.0f;
             v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
-            *out = kcp_new_const(ctx, w, h, v);
+            *out = kcp_new_const(ctx, w, nrows, v);
             return KC_OK;
         }
     }
     KC_TRY(kcp_force(ctx, &src, 1));
     kc_plane* dst = nullptr;
-    KC_TRY(kcp_new_device(ctx, w, h, &dst));
-    int32_t rc = kck_resize_plane(ctx, src->dptr, src->w, src->h, dst->dptr, w, h, filter);
+    KC_TRY(kcp_new_device(ctx, w, nrows, &dst));
+    int32_t rc = kck_resize_plane_rows(ctx, src->dptr, src->w, src->h, dst->dptr, w, h, filter, row0, nrows);
     if (rc != KC_OK) {
         kcp_release(dst);
         return rc;
@@ -218,8 +222,10 @@ int32_t plane_resize(kc_context* ctx, kc_plane* src, uint32_t w, uint32_t h, int
     return KC_OK;
 }
 
-int32_t img_resize(kc_context* ctx, const Img& in, uint32_t w, uint32_t h, int filter, Img& out) {
-    if (in.w() == w && in.h() == h) {
+int32_t img_resize(kc_context* ctx, const Img& in, uint32_t w, uint32_t h, int filter, Img& out,
+                   uint32_t row0 = 0, uint32_t nrows = 0xffffffffu) {
+    if (nrows == 0xffffffffu) nrows = h;
+    if (in.w() == w && in.h() == h && row0 == 0 && nrows == h) {
         out = in;
         return KC_OK;
     }
@@ -235,7 +241,7 @@ int32_t img_resize(kc_context* ctx, const Img& in, uint32_t w, uint32_t h, int f
             continue;
         }
         kc_plane* p = nullptr;
-        KC_TRY(plane_resize(ctx, in.im.planes[c], w, h, filter, &p));
+        KC_TRY(plane_resize(ctx, in.im.planes[c], w, h, filter, &p, row0, nrows));
         res.set(c, p);
     }
     out = std::move(res);
@@ -782,6 +788,19 @@ int32_t kc_resize(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, i
     KcGuard g(ctx);
     Img res;
     KC_TRY(img_resize(ctx, borrow(in), w, h, filter, res));
+    *out = res.release();
+    return KC_OK;
+}
+
+int32_t kc_resize_rows(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, int32_t filter, uint32_t row_begin,
+                       uint32_t row_count, kc_image* out) {
+    // the strip [row_begin, row_begin + row_count) of kc_resize(in, w, h): what one GPU of a
+    // row-sharded resize computes; bit-identical to those rows of the whole result
+    if (!ctx || !in || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KC_TRY(check_image(in, "resize"));
+    KcGuard g(ctx);
+    Img res;
+    KC_TRY(img_resize(ctx, borrow(in), w, h, filter, res, row_begin, row_count));
     *out = res.release();
     return KC_OK;
 }

@@ -257,6 +257,8 @@ int32_t kck_height_to_normal(kc_context* ctx, const float* hgt, uint32_t w, uint
                              const float* halo, float* r, float* g, float* b);
 int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst,
                          uint32_t dw, uint32_t dh, int filter);
+int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,
+                              uint32_t dh, int filter, uint32_t row0, uint32_t nrows);
 // host-side weight table exactly as image 0.24.0 computes it (kc_resize.cu)
 void kc_resize_axis_host(uint32_t src_len, uint32_t dst_len, int filter, std::vector<uint32_t>& left,
                          std::vector<uint32_t>& count, std::vector<float>& weights, uint32_t& max_taps);

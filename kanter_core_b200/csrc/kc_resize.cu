@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
     const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst, uint32_t dw, uint32_t dh,
     const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount, const float* __restrict__ vw, uint32_t vtaps,
     const uint32_t* __restrict__ hleft, const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
-    uint32_t pcols, uint32_t prows, float one) {
+    uint32_t pcols, uint32_t prows, float one, uint32_t row0, uint32_t nrows) {
+    // rows [row0, row0 + nrows) of the dw x dh result are produced; dst holds just those rows
     extern __shared__ __align__(16) float fsm[];
     float* Tm = fsm;                                              // [pcols][FS_TP] vertical-pass result, column-major
     float* Sbuf = Tm + (size_t)pcols * FS_TP;                     // [2][prows][pcols] source rows of a group
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
     const int tid = threadIdx.x;
     const uint32_t ox0 = blockIdx.x * (THREADS * FS_CPT);
     const uint32_t oxl = min(ox0 + (THREADS * FS_CPT), dw) - 1;                // last valid column of the strip
-    const uint32_t ngroups = (dh + FS_G - 1) / FS_G;
+    const uint32_t ngroups = (nrows + FS_G - 1) / FS_G;
 
     // ---- per-column state, loaded once --------------------------------------------------
     // (the horizontal weights live in shared memory, one float4 per tap per thread, read back
@@ -302,20 +303,21 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
         goff[i] = r * sw + c;             // a patch spans < 2^32 source floats
     }
     // first source row of the patch of group g
-    auto group_row0 = [&](uint32_t g) { return min(__ldg(vleft + g * FS_G), sh - prows); };
+    auto group_row0 = [&](uint32_t g) { return min(__ldg(vleft + row0 + g * FS_G), sh - prows); };
     // cp.async everything group g needs into stage b
     auto prefetch = [&](uint32_t g, int b, uint32_t ry0) {
-        const uint32_t oy0 = g * FS_G;
+        const uint32_t ly0 = g * FS_G;                            // first row of the group inside the window
         FsGroupBuf& G = gb[b];
         for (int i = tid; i < FS_MAXT * FS_G; i += THREADS) {
             const int k = i / FS_G, r = i % FS_G;
-            const uint32_t oy = oy0 + r;
-            if (oy < dh && (uint32_t)k < vtaps) cp_async4(&G.wv[k][r], vw + (size_t)k * dh + oy);
+            const bool live = ly0 + r < nrows;
+            const uint32_t oy = row0 + ly0 + r;                   // row of the full result: indexes the tap tables
+            if (live && (uint32_t)k < vtaps) cp_async4(&G.wv[k][r], vw + (size_t)k * dh + oy);
             if (k == 0) {
-                if (oy < dh) cp_async4(&G.vl[r], vleft + oy);
+                if (live) cp_async4(&G.vl[r], vleft + oy);
                 else G.vl[r] = ry0;
             } else if (k == 1) {
-                if (oy < dh) cp_async4(&G.vc[r], vcount + oy);
+                if (live) cp_async4(&G.vc[r], vcount + oy);
                 else G.vc[r] = 0u;                                // rows past the image compute nothing
             }
         }
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
                 }
             }
             const uint32_t oy0 = g * FS_G;
-            const uint32_t nrow = min((uint32_t)FS_G, dh - oy0);
+            const uint32_t nrow = min((uint32_t)FS_G, nrows - oy0);
             float* out = dst + (size_t)oy0 * dw + oxt;
             if (vec && nrow == (uint32_t)FS_G) {
                 float4* o4 = reinterpret_cast<float4*>(out);
@@ -457,11 +459,30 @@ uint32_t max_window(const KcAxisTable& t, uint32_t tile) {
     return mx;
 }
 
+// the same for tiles that may start at any output index (row windows of a strip)
+uint32_t max_window_sliding(const KcAxisTable& t, uint32_t tile) {
+    uint32_t mx = 0;
+    for (uint32_t o0 = 0; o0 < t.dst_len; ++o0) {
+        const uint32_t ol = std::min(o0 + tile, t.dst_len) - 1;
+        mx = std::max(mx, t.h_left[ol] + t.h_count[ol] - t.h_left[o0]);
+    }
+    return mx;
+}
+
 }  // namespace
 
 int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,
                          uint32_t dh, int filter) {
-    if (dw == 0 || dh == 0) return KC_OK;
+    return kck_resize_plane_rows(ctx, src, sw, sh, dst, dw, dh, filter, 0, dh);
+}
+
+// rows [row0, row0 + nrows) of the dw x dh resize of src, written to dst (dw x nrows).  A GPU that
+// owns a horizontal strip of the result calls this with its rows: it needs the source rows
+// [left(row0), right(row0 + nrows - 1)) only -- for an upsample, simply the whole (small) source.
+int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,
+                              uint32_t dh, int filter, uint32_t row0, uint32_t nrows) {
+    if (dw == 0 || dh == 0 || nrows == 0) return KC_OK;
+    if (row0 > dh || nrows > dh - row0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "rows [%u, %u) are outside the %u-row result", row0, row0 + nrows, dh);
     if (sw == 0 || sh == 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "cannot resize an empty plane");
     std::shared_ptr<KcAxisTable> tv, th;
     KC_TRY(get_axis(ctx, sh, dh, filter, tv));
@@ -477,7 +498,7 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
         // row pitch a multiple of 4 floats: the vertical pass reads column quads (LDS.128); the
         // quad of the last columns may run up to 3 columns past the window
         const uint32_t pcols = (max_window(*th, tw) + 3u) & ~3u;
-        const uint32_t prows = max_window(*tv, FS_G);
+        const uint32_t prows = max_window_sliding(*tv, FS_G);   // groups start at row0 + 16 k: any alignment
         const size_t smem = sizeof(float) * ((size_t)pcols * FS_TP + 2 * (size_t)prows * pcols) + sizeof(float4) * FS_MAXT * threads + 2 * sizeof(FsGroupBuf);
         if (smem <= 200 * 1024) {
             const void* fn = nullptr;
@@ -501,7 +522,7 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
             }
             // one resident wave: strips x row-march lanes ~= SMs x resident CTAs
             const uint32_t strips = (dw + tw - 1) / tw;
-            const uint32_t ngroups = (dh + FS_G - 1) / FS_G;
+            const uint32_t ngroups = (nrows + FS_G - 1) / FS_G;
             const uint32_t lanes = std::max<uint32_t>(1u, std::min<uint32_t>(ngroups, (uint32_t)(ctx->sm_count * per_sm) / std::max(strips, 1u)));
             {
                 dim3 grid(strips, std::min<uint32_t>(lanes, 65535u));
@@ -510,13 +531,26 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
                 void* args[] = {(void*)&src, (void*)&sw, (void*)&sh, (void*)&dst, (void*)&dw, (void*)&dh,
                                 (void*)&tv->d_left, (void*)&tv->d_count, (void*)&tv->d_weights, (void*)&tv->max_taps,
                                 (void*)&th->d_left, (void*)&th->d_count, (void*)&th->d_weights,
-                                (void*)&pcols, (void*)&prows, (void*)&one};
+                                (void*)&pcols, (void*)&prows, (void*)&one, (void*)&row0, (void*)&nrows};
                 KC_CUDA(cudaLaunchKernel(fn, grid, dim3(threads), args, smem, ctx->stream));
                 ctx->kernel_launches++;
                 ctx->run_kernels++;
                 return KC_OK;
             }
         }
+    }
+    if (row0 != 0 || nrows != dh) {
+        // long windows (downsampling): resize the whole plane with the two-pass kernels, keep the rows
+        float* full = nullptr;
+        const size_t full_bytes = ((sizeof(float) * (size_t)dw * dh + 15) / 16) * 16;
+        KC_TRY(kc_dev_alloc(ctx, full_bytes, (void**)&full));
+        int32_t rc = kck_resize_plane_rows(ctx, src, sw, sh, full, dw, dh, filter, 0, dh);
+        if (rc == KC_OK) {
+            cudaError_t e = cudaMemcpyAsync(dst, full + (size_t)row0 * dw, sizeof(float) * (size_t)dw * nrows, cudaMemcpyDeviceToDevice, ctx->stream);
+            if (e != cudaSuccess) { kc_set_error("row copy failed: %s", cudaGetErrorString(e)); rc = KC_ERR_CUDA; }
+        }
+        kc_dev_free(ctx, full, full_bytes);
+        return rc;
     }
     float* tmp = nullptr;
     const size_t tmp_bytes = ((sizeof(float) * (size_t)sw * dh + 15) / 16) * 16;

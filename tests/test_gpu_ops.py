@@ -247,6 +247,29 @@ def test_resize_non_finite_values_propagate_like_the_reference(tex_pro, tex_pro_
         assert close(got[ok], want[ok])
 
 
+@pytest.mark.parametrize("filt", [ResizeFilter.Nearest, ResizeFilter.Triangle, ResizeFilter.Lanczos3])
+@pytest.mark.parametrize("src,dst,parts", [((64, 48), (512, 384), 3), ((100, 70), (333, 211), 4), ((256, 256), (100, 77), 2)])
+def test_resize_row_strips_equal_whole_image(tex_pro, filt, src, dst, parts):
+    """kc_resize_rows: the row strips a row-sharded resize hands to each GPU are the
+    rows of the whole result, bit for bit, at strip boundaries that are not multiples of the
+    kernel's 16-row groups; the last case takes the two-pass (downsampling) route."""
+    import ctypes as C
+    from kanter_core_b200._lib import call, kc_image
+    (sw, sh), (dw, dh) = src, dst
+    p = rnd(31, sh, sw, -0.25, 1.25)
+    img = kc.SlotImage.from_planes(tex_pro, [p])
+    whole = _resize_direct(tex_pro, img, dw, dh, filt).planes()[0]
+    assert bits_equal(whole, oracle.resize_plane(p, dw, dh, int(filt)))
+    bounds = [dh * k // parts for k in range(parts + 1)]
+    bounds[1] += 5                      # ragged on purpose
+    for r0, r1 in zip(bounds[:-1], bounds[1:]):
+        out = kc_image()
+        call("kc_resize_rows", tex_pro._ctx._h, C.byref(img._im), dw, dh, int(filt), r0, r1 - r0, C.byref(out))
+        strip = kc.SlotImage(tex_pro._ctx, out).planes()[0]
+        assert strip.shape == (r1 - r0, dw)
+        assert bits_equal(strip, whole[r0:r1]), (r0, r1)
+
+
 def test_resize_rgba_with_constant_alpha(tex_pro):
     # a constant alpha plane goes through the same tap arithmetic as any other plane
     planes = [rnd(50 + c, 20, 30) for c in range(3)]
