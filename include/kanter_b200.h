@@ -256,6 +256,20 @@ int32_t kc_height_to_normal(kc_context* ctx, const kc_image* in, kc_image* out);
  * (wrapping_sample_subtract, src/node/process_shared.rs:52-60).  Bit-identical to the
  * corresponding rows of kc_height_to_normal on the whole image. */
 int32_t kc_height_to_normal_strip(kc_context* ctx, const kc_image* strip, kc_plane* halo_row, uint32_t full_height, kc_image* out);
+/* ---- halo rows through peer memory (one process per GPU; SURVEY.md section 8e: "NVLink peer copies only for
+ *      halo exchange").  The GPU that owns the strip above publishes its last row into a mailbox in its own
+ *      HBM; the GPU below maps the mailbox with CUDA IPC and its HeightToNormal kernel waits for the step's
+ *      flag and reads the row straight out of peer memory.  Steps count 1, 2, 3, ...; a mailbox holds two. */
+typedef struct kc_halo_link kc_halo_link;
+int32_t kc_halo_outbox_create(kc_context* ctx, uint32_t width, kc_halo_link** out);
+int32_t kc_halo_outbox_handle(const kc_halo_link* outbox, uint8_t handle[64]);              /* cudaIpcMemHandle_t bytes: send to the rank below */
+int32_t kc_halo_inbox_open(kc_context* ctx, const uint8_t handle[64], uint32_t width, kc_halo_link** out);
+int32_t kc_halo_inbox_local(kc_context* ctx, const kc_halo_link* outbox, kc_halo_link** out); /* same process: ring of one rank, tests */
+int32_t kc_halo_publish(kc_halo_link* outbox, kc_plane* plane, uint32_t row, uint64_t step);
+int32_t kc_height_to_normal_strip_peer(kc_context* ctx, const kc_image* strip, const kc_halo_link* inbox, uint64_t step,
+                                       uint32_t full_height, kc_image* out);
+int32_t kc_halo_timeouts(kc_context* ctx, uint32_t* count);   /* waits that gave up after 2 s; 0 in a healthy run */
+int32_t kc_halo_link_destroy(kc_halo_link* link);
 /* device-to-device copy of whole rows between planes of equal width (halo rows; works
  * across devices with peer access: one cudaMemcpyAsync over NVLink) */
 int32_t kc_plane_copy_rows(kc_context* ctx, kc_plane* dst, uint32_t dst_row, kc_plane* src, uint32_t src_row, uint32_t rows);

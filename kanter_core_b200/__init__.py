@@ -8,6 +8,6 @@ from ._lib import MATH_EXACT, MATH_FAST, TexProError, lib  # noqa: F401
 from .api import (  # noqa: F401
     Edge, EmbeddedSlotDataId, LiveGraph, MixType, Node, NodeGraph, NodeId, NodeState, NodeType,
     ResizeFilter, ResizePolicy, Side, Size, Slot, SlotData, SlotId, SlotImage, SlotType,
-    TextureProcessor, copy_rows, empty_gray, free_pinned, graph_to_dict, height_to_normal,
-    height_to_normal_strip, mix, pinned_empty, resize, wrap_device_plane,
+    HaloLink, TextureProcessor, copy_rows, empty_gray, free_pinned, graph_to_dict, halo_timeouts, height_to_normal,
+    height_to_normal_strip, height_to_normal_strip_peer, mix, pinned_empty, resize, wrap_device_plane,
 )

@@ -121,6 +121,14 @@ SIGNATURES = {
     "kc_mix": (i32, [vp, i32, P(kc_image), P(kc_image), P(kc_image)]),
     "kc_height_to_normal": (i32, [vp, P(kc_image), P(kc_image)]),
     "kc_height_to_normal_strip": (i32, [vp, P(kc_image), vp, u32, P(kc_image)]),
+    "kc_halo_outbox_create": (i32, [vp, u32, P(vp)]),
+    "kc_halo_outbox_handle": (i32, [vp, vp]),
+    "kc_halo_inbox_open": (i32, [vp, vp, u32, P(vp)]),
+    "kc_halo_inbox_local": (i32, [vp, vp, P(vp)]),
+    "kc_halo_publish": (i32, [vp, vp, u32, u64]),
+    "kc_height_to_normal_strip_peer": (i32, [vp, P(kc_image), vp, u64, u32, P(kc_image)]),
+    "kc_halo_timeouts": (i32, [vp, P(u32)]),
+    "kc_halo_link_destroy": (i32, [vp]),
     "kc_plane_copy_rows": (i32, [vp, vp, u32, vp, u32, u32]),
     "kc_resize": (i32, [vp, P(kc_image), u32, u32, i32, P(kc_image)]),
     "kc_resize_rows": (i32, [vp, P(kc_image), u32, u32, i32, u32, u32, P(kc_image)]),

@@ -957,6 +957,58 @@ def height_to_normal_strip(tex_pro, strip, halo_row, full_height):
     return SlotImage(tex_pro._ctx, out)
 
 
+class HaloLink:
+    """A halo mailbox in peer memory (kc_halo_*): `outbox(tp, width)` on the GPU that owns the strip
+    above, `.handle()` -> 64 bytes for the rank below, `HaloLink.open(tp, handle, width)` there."""
+
+    def __init__(self, tex_pro, handle):
+        self._tp, self._h = tex_pro, handle
+
+    @staticmethod
+    def outbox(tex_pro, width):
+        h = C.c_void_p()
+        call("kc_halo_outbox_create", tex_pro._ctx._h, int(width), C.byref(h))
+        return HaloLink(tex_pro, h)
+
+    def handle(self):
+        buf = (C.c_uint8 * 64)()
+        call("kc_halo_outbox_handle", self._h, buf)
+        return bytes(buf)
+
+    @staticmethod
+    def open(tex_pro, handle_bytes, width):
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle_bytes)
+        h = C.c_void_p()
+        call("kc_halo_inbox_open", tex_pro._ctx._h, buf, int(width), C.byref(h))
+        return HaloLink(tex_pro, h)
+
+    def local_inbox(self):
+        h = C.c_void_p()
+        call("kc_halo_inbox_local", self._tp._ctx._h, self._h, C.byref(h))
+        return HaloLink(self._tp, h)
+
+    def publish(self, image, row, step, plane=0):
+        call("kc_halo_publish", self._h, image._im.planes[plane], int(row), int(step))
+
+    def close(self):
+        if self._h:
+            _lib.lib.kc_halo_link_destroy(self._h)
+            self._h = None
+
+
+def height_to_normal_strip_peer(tex_pro, strip, inbox, step, full_height):
+    """HeightToNormal on a strip whose halo row the kernel reads from the mailbox of the GPU above."""
+    out = kc_image()
+    call("kc_height_to_normal_strip_peer", tex_pro._ctx._h, C.byref(strip._im), inbox._h, int(step), int(full_height), C.byref(out))
+    return SlotImage(tex_pro._ctx, out)
+
+
+def halo_timeouts(tex_pro):
+    n = C.c_uint32()
+    call("kc_halo_timeouts", tex_pro._ctx._h, C.byref(n))
+    return n.value
+
+
 def resize(tex_pro, image, size, resize_filter):
     """imageops::resize per plane, src/shared.rs:155-201."""
     out = kc_image()

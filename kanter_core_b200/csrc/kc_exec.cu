@@ -150,7 +150,8 @@ int32_t img_mix(kc_context* ctx, int mix_type, const Img* left, const Img* right
 
 // height_to_normal::process, src/node/height_to_normal.rs:16-77.  halo/h_full: strip mode
 // (rows [y0, y0+h) of an image h_full tall; halo = the row above the strip, w x 1).
-int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullptr, uint32_t h_full = 0) {
+int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullptr, uint32_t h_full = 0,
+                const kc_halo_link* inbox = nullptr, uint64_t step = 0) {
     if (in.rgba()) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "HeightToNormal needs a Gray input");
     kc_plane* src = in.im.planes[0];
     KC_TRY(kcp_force(ctx, &src, 1));
@@ -167,8 +168,15 @@ int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullp
         res.set(c, p);
     }
     res.set(3, kcp_new_const(ctx, src->w, src->h, 1.0f));  // from_buffers_rgb, slot_image.rs:90-102
-    KC_TRY(kck_height_to_normal(ctx, src->dptr, src->w, src->h, h_full, halo ? halo->dptr : nullptr, res.im.planes[0]->dptr,
-                                res.im.planes[1]->dptr, res.im.planes[2]->dptr));
+    const float* halo_ptr = halo ? halo->dptr : nullptr;
+    const unsigned long long* peer_flag = nullptr;
+    if (inbox) {
+        if (kck_halo_width(inbox) != src->w) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "mailbox is %u wide, the strip %u", kck_halo_width(inbox), src->w);
+        KC_TRY(kck_halo_read_args(inbox, step, &halo_ptr, &peer_flag));
+    }
+    KC_TRY(kck_height_to_normal(ctx, src->dptr, src->w, src->h, h_full, halo_ptr, res.im.planes[0]->dptr,
+                                res.im.planes[1]->dptr, res.im.planes[2]->dptr, peer_flag, step));
+    if (inbox) KC_TRY(kck_halo_ack(ctx, inbox, step));   // stream-ordered after the kernel that read the row
     ctx->run_bytes += (uint64_t)src->bytes() * 4;
     out = std::move(res);
     return KC_OK;
@@ -766,6 +774,20 @@ int32_t kc_height_to_normal_strip(kc_context* ctx, const kc_image* strip, kc_pla
     KcGuard g(ctx);
     Img res;
     KC_TRY(img_h2n(ctx, borrow(strip), res, halo_row, full_height));
+    *out = res.release();
+    return KC_OK;
+}
+
+int32_t kc_height_to_normal_strip_peer(kc_context* ctx, const kc_image* strip, const kc_halo_link* inbox, uint64_t step,
+                                       uint32_t full_height, kc_image* out) {
+    // as kc_height_to_normal_strip, with the halo row read by the kernel itself from the mailbox
+    // of the GPU above (kc_halo_*): no copy of the row, no host synchronisation
+    if (!ctx || !strip || !inbox || !out || step == 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad argument");
+    KC_TRY(check_image(strip, "height_to_normal_strip_peer"));
+    if (full_height < strip->planes[0]->h) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "full height smaller than the strip");
+    KcGuard g(ctx);
+    Img res;
+    KC_TRY(img_h2n(ctx, borrow(strip), res, nullptr, full_height, inbox, step));
     *out = res.release();
     return KC_OK;
 }

@@ -254,7 +254,13 @@ int32_t kck_from_u8(kc_context* ctx, const uint8_t* d_samples, uint32_t channels
 // h_full/halo: for a horizontal strip of a taller image, the full height and the row above
 // the strip (NULL halo + h_full == h: the whole image, toroidal wrap)
 int32_t kck_height_to_normal(kc_context* ctx, const float* hgt, uint32_t w, uint32_t h, uint32_t h_full,
-                             const float* halo, float* r, float* g, float* b);
+                             const float* halo, float* r, float* g, float* b,
+                             const unsigned long long* peer_flag = nullptr, unsigned long long peer_step = 0);
+// halo mailboxes in peer memory (kc_h2n.cu)
+struct kc_halo_link;
+int32_t kck_halo_read_args(const kc_halo_link* inbox, uint64_t step, const float** halo, const unsigned long long** flag);
+int32_t kck_halo_ack(kc_context* ctx, const kc_halo_link* inbox, uint64_t step);
+uint32_t kck_halo_width(const kc_halo_link* l);
 int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst,
                          uint32_t dw, uint32_t dh, int filter);
 int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,

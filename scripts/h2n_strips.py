@@ -6,9 +6,11 @@ tiled across the GPUs of one box as horizontal strips with one halo row per stri
         --master-port 29511 scripts/h2n_strips.py [--size 8192] [--steps 20] [--math fast|exact]
 
 One process per GPU.  Each rank owns rows [y0, y1) of the height map in its own HBM.
-Per step: the last row of every strip goes to the rank below it (NCCL send/recv of
-w*4 bytes over NVLink; rank N-1's row wraps to rank 0), then every rank runs the strip
-kernel.  No collective on the data path.  Rank 0 prints one JSON line; `value` is the
+Per step (--halo peer, default): every rank publishes the last row of its strip into a mailbox in
+its own HBM and runs the strip kernel, whose first rows wait for the flag of the mailbox of the
+rank above (mapped once through CUDA IPC) and read the halo row straight out of peer memory over
+NVLink -- no copy, no NCCL, no host synchronisation.  --halo nccl is the earlier send/recv path.
+No collective on the data path either way.  Rank 0 prints one JSON line; `value` is the
 whole image's Mpixel/s (strong scaling: the image is fixed, the strips shrink).
 """
 import argparse
@@ -29,6 +31,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="peer: the kernel reads the row from the neighbour's mailbox over NVLink (CUDA IPC); nccl: send/recv per step")
     args = ap.parse_args()
 
     import torch
@@ -63,7 +67,26 @@ def main():
     send_t = torch.empty(W, dtype=torch.float32, device="cuda")
     send_img = kc.wrap_device_plane(tp, send_t.data_ptr(), W, 1)
 
+    # peer mode: my mailbox holds MY last row; the rank below maps it.  Handles travel once, at setup.
+    outbox = inbox = None
+    if args.halo == "peer":
+        outbox = kc.HaloLink.outbox(tp, W)
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, outbox.handle())
+            inbox = kc.HaloLink.open(tp, handles[(rank - 1) % world], W)
+        else:
+            inbox = outbox.local_inbox()
+    counter = [0]
+
+    def step_peer():
+        counter[0] += 1
+        outbox.publish(strip, (y1 - y0) - 1, counter[0])          # stream-ordered; waits (on the GPU) for the reader's ack of step-2
+        return kc.height_to_normal_strip_peer(tp, strip, inbox, counter[0], H), None
+
     def step():
+        if args.halo == "peer":
+            return step_peer()
         # 1. my last row -> staging (device-to-device, on the library's stream)
         kc.copy_rows(tp, send_img, 0, strip, (y1 - y0) - 1, 1)
         tp.synchronize()
@@ -114,8 +137,15 @@ def main():
             "strip_kernel_ms_max_over_ranks": kernel_ms,
             "strip_kernel_GBs_per_gpu": (y1 - y0) * W * 16 / (kernel_ms / 1e3) / 1e9,
             "halo_bytes_per_boundary": W * 4, "math_mode": args.math,
+            "halo": "kernel reads the neighbour's mailbox over NVLink (CUDA IPC mapping), no host sync per step" if args.halo == "peer" else "NCCL send/recv + host sync per step",
+            "halo_wait_timeouts": kc.halo_timeouts(tp) if args.halo == "peer" else None,
             "parity": "rows 0..7 (wrapped halo from the last strip) vs CPU oracle: %s" % ("bit-exact" if args.math == "exact" else "within 1e-5 rel / 1e-6 abs"),
         }), flush=True)
+    if world > 1:
+        dist.barrier()          # nobody unmaps a mailbox a neighbour may still be reading
+    for l in (inbox, outbox):
+        if l is not None:
+            l.close()
     tp.close()
     if world > 1:
         dist.destroy_process_group()

@@ -383,6 +383,31 @@ def test_height_to_normal_strips_equal_whole_image(tex_pro, h, w, parts):
             assert bits_equal(got[c], want[c][y0:y1]), (r, c)
 
 
+@pytest.mark.parametrize("h,w,parts", [(64, 64, 2), (100, 128, 3), (256, 512, 4)])
+def test_height_to_normal_strips_with_peer_mailboxes(tex_pro, h, w, parts):
+    """The halo row read by the kernel from a mailbox (kc_halo_*), every "rank" emulated in one
+    process on one stream: publish always precedes the reading kernel in stream order, so
+    nothing ever waits (what the multi-process run does across GPUs is the same data path through
+    a CUDA-IPC mapping).  Three steps with different data exercise both slots and the ack."""
+    from kanter_core_b200 import dist as kdist
+    strips = [kdist.strip_rows(h, r, parts) for r in range(parts)]
+    boxes = [kc.HaloLink.outbox(tex_pro, w) for _ in range(parts)]
+    inboxes = [boxes[(r - 1) % parts].local_inbox() for r in range(parts)]
+    for step in (1, 2, 3):
+        hgt = rnd(40 + step, h, w)
+        want = oracle.height_to_normal(hgt)
+        imgs = [kc.SlotImage.from_planes(tex_pro, [hgt[y0:y1]]) for (y0, y1) in strips]
+        for r, (y0, y1) in enumerate(strips):
+            boxes[r].publish(imgs[r], (y1 - y0) - 1, step)
+        for r, (y0, y1) in enumerate(strips):
+            got = kc.height_to_normal_strip_peer(tex_pro, imgs[r], inboxes[r], step, h).planes()
+            for c in range(3):
+                assert bits_equal(got[c], want[c][y0:y1]), (step, r, c)
+    assert kc.halo_timeouts(tex_pro) == 0
+    for l in inboxes + boxes:
+        l.close()
+
+
 def test_ops_module_functions(tex_pro):
     A, B = rnd(31, 20, 24), rnd(32, 20, 24)
     ia, ib = kc.SlotImage.from_planes(tex_pro, [A]), kc.SlotImage.from_planes(tex_pro, [B])
