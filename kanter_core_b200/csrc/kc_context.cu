@@ -123,6 +123,10 @@ static void axis_table_free(KcAxisTable& t) {
     if (t.d_left) cudaFree(t.d_left);
     if (t.d_count) cudaFree(t.d_count);
     if (t.d_weights) cudaFree(t.d_weights);
+    if (t.d_march_w) cudaFree(t.d_march_w);
+    if (t.d_march_o) cudaFree(t.d_march_o);
+    t.d_march_w = nullptr;
+    t.d_march_o = nullptr;
     t.d_left = t.d_count = nullptr;
     t.d_weights = nullptr;
 }

@@ -98,6 +98,12 @@ struct KcAxisTable {
     float* d_weights = nullptr;
     std::vector<uint32_t> h_left, h_count;
     std::vector<float> h_weights;  // [dst_len][max_taps] on the host
+    // marching tables for long windows (downsampling), built on first use (kc_resize.cu):
+    // for every SOURCE index r and ring slot s = o mod 8: the weight of r in the one output o of that
+    // slot whose window holds r (NaN: none), and the output that is complete after r (-1: none)
+    int march_state = 0;           // 0 not built, 1 usable, -1 this axis cannot march (falls back)
+    float* d_march_w = nullptr;    // [src_len][8]
+    int32_t* d_march_o = nullptr;  // [src_len][8]
 };
 
 // ---- planes -------------------------------------------------------------------

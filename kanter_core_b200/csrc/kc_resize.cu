@@ -449,6 +449,112 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
     }
 }
 
+// ---------------------------------------------------------------------------
+// Vertical pass for LONG windows (downsampling: 6 R + 1 taps for a ratio R with Lanczos3), as
+// a march over the SOURCE rows.  The two-pass kernel above reads every source row once per
+// output row whose window holds it (~6x, all of it L2 traffic); here a thread owns four
+// columns, streams the source rows of its CTA's output range exactly once and keeps the up to
+// eight output rows in flight in registers: output o lives in ring slot o mod 8 (windows of o
+// and o + 8 never overlap), so for a source row the host-built table gives, per slot, the tap
+// weight (NaN: the row is in no window of that slot) and the output that is complete after it.
+// Each output still sums its taps top to bottom starting from +0: the reference's order.
+// ---------------------------------------------------------------------------
+constexpr int VM_THREADS = 128;
+constexpr int VM_SLOTS = 8;
+constexpr int VM_ROWS_PER_CTA = 32;   // output rows per CTA (its source range overlaps the neighbours' by one window)
+
+template <bool EXACT>
+__device__ __forceinline__ void vm_tap4(float4& a, const float4& v, float w) {
+    if (EXACT) {
+        a.x = __fadd_rn(a.x, __fmul_rn(v.x, w)); a.y = __fadd_rn(a.y, __fmul_rn(v.y, w));
+        a.z = __fadd_rn(a.z, __fmul_rn(v.z, w)); a.w = __fadd_rn(a.w, __fmul_rn(v.w, w));
+    } else {                                               // two packed FFMA2 instead of four FFMA
+        const float2 ww = make_float2(w, w);
+        const float2 lo = __ffma2_rn(make_float2(v.x, v.y), ww, make_float2(a.x, a.y));
+        const float2 hi = __ffma2_rn(make_float2(v.z, v.w), ww, make_float2(a.z, a.w));
+        a = make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(VM_THREADS) kc_resize_v_march_kernel(const float4* __restrict__ src, uint32_t sw4, float4* __restrict__ tmp,
+                                                                       uint32_t dh, const uint32_t* __restrict__ vleft,
+                                                                       const uint32_t* __restrict__ vcount, const float4* __restrict__ mw,
+                                                                       const int4* __restrict__ mo, uint32_t rows_per_cta) {
+    extern __shared__ __align__(16) float4 vm_sm[];        // the tables of this CTA's source rows: [rows][2] weights, [rows][2] retire ids
+    const uint32_t x4 = blockIdx.x * VM_THREADS + threadIdx.x;
+    const uint32_t oyA = blockIdx.y * rows_per_cta, oyB = min(oyA + rows_per_cta, dh);
+    const uint32_t r0 = __ldg(vleft + oyA), r1 = __ldg(vleft + oyB - 1) + __ldg(vcount + oyB - 1);
+    const uint32_t nr = r1 - r0;
+    float4* sw_ = vm_sm;
+    int4* so_ = reinterpret_cast<int4*>(vm_sm + 2 * (size_t)nr);
+    for (uint32_t i = threadIdx.x; i < 2 * nr; i += VM_THREADS) {
+        sw_[i] = __ldg(mw + 2 * (size_t)r0 + i);
+        so_[i] = __ldg(mo + 2 * (size_t)r0 + i);
+    }
+    __syncthreads();
+    if (x4 >= sw4) return;
+    float4 acc[VM_SLOTS];
+#pragma unroll
+    for (int s = 0; s < VM_SLOTS; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* col = src + x4;
+    constexpr int U = 8;                                   // source rows whose loads are in flight together
+    for (uint32_t rb = 0; rb < nr; rb += U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = __ldg(col + (size_t)(r0 + min(rb + u, nr - 1)) * sw4);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t r = rb + u;                     // relative to r0
+            if (r >= nr) break;                            // uniform
+            const float4 wa = sw_[2 * r], wb = sw_[2 * r + 1];
+            const float w[VM_SLOTS] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int s = 0; s < VM_SLOTS; ++s)
+                if (w[s] == w[s]) vm_tap4<EXACT>(acc[s], v[u], w[s]);
+            const int4 oa = so_[2 * r], ob = so_[2 * r + 1];
+            const int o[VM_SLOTS] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+            // "no output completes here" is every entry -1: the AND of all eight keeps its sign bit
+            if ((oa.x & oa.y & oa.z & oa.w & ob.x & ob.y & ob.z & ob.w) < 0) continue;
+#pragma unroll
+            for (int s = 0; s < VM_SLOTS; ++s)
+                if (o[s] >= 0) {
+                    if ((uint32_t)o[s] >= oyA && (uint32_t)o[s] < oyB) tmp[(size_t)o[s] * sw4 + x4] = acc[s];
+                    acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+        }
+    }
+}
+
+// host: the marching tables of an axis; false when some source index sits in more than one
+// window of a ring slot, or a real weight is NaN (the sentinel) -- the caller then falls back
+int32_t build_march_tables(kc_context* ctx, KcAxisTable& t) {
+    if (t.march_state != 0) return KC_OK;
+    t.march_state = -1;
+    const uint32_t S = t.src_len, D = t.dst_len;
+    std::vector<float> w((size_t)S * VM_SLOTS, nanf(""));
+    std::vector<int32_t> o((size_t)S * VM_SLOTS, -1);
+    for (uint32_t oy = 0; oy < D; ++oy) {
+        const int s = (int)(oy % VM_SLOTS);
+        const uint32_t l = t.h_left[oy], n = t.h_count[oy];
+        for (uint32_t k = 0; k < n; ++k) {
+            const float wk = t.h_weights[(size_t)oy * t.max_taps + k];
+            float& cell = w[(size_t)(l + k) * VM_SLOTS + s];
+            if (wk != wk || cell == cell) return KC_OK;        // NaN weight, or the slot is taken: cannot march
+            cell = wk;
+        }
+        if (o[(size_t)(l + n - 1) * VM_SLOTS + s] >= 0) return KC_OK;
+        o[(size_t)(l + n - 1) * VM_SLOTS + s] = (int32_t)oy;
+    }
+    KC_CUDA(cudaMalloc((void**)&t.d_march_w, w.size() * sizeof(float)));
+    KC_CUDA(cudaMalloc((void**)&t.d_march_o, o.size() * sizeof(int32_t)));
+    KC_CUDA(cudaMemcpyAsync(t.d_march_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    KC_CUDA(cudaMemcpyAsync(t.d_march_o, o.data(), o.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));           // the vectors go out of scope
+    t.march_state = 1;
+    return KC_OK;
+}
+
 // largest source window any tile of FT_T output elements touches along one axis
 uint32_t max_window(const KcAxisTable& t, uint32_t tile) {
     uint32_t mx = 0;
@@ -556,7 +662,40 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
     const size_t tmp_bytes = ((sizeof(float) * (size_t)sw * dh + 15) / 16) * 16;
     KC_TRY(kc_dev_alloc(ctx, tmp_bytes, (void**)&tmp));
     const bool exact = ctx->opts.math_mode == KC_MATH_EXACT;
-    {
+    bool marched = false;
+    static const bool no_march = getenv("KC_RESIZE_NO_MARCH") != nullptr;
+    if (!no_march && (sw & 3u) == 0 && tv->max_taps > (uint32_t)FS_MAXT) {
+        KC_TRY(build_march_tables(ctx, *tv));
+        if (tv->march_state == 1) {
+            // output rows per CTA: as many as keep the tables of its source range within 64 KiB of shared memory
+            uint32_t rows = VM_ROWS_PER_CTA;
+            auto range = [&](uint32_t rpc) {
+                uint32_t mx = 0;
+                for (uint32_t a = 0; a < dh; a += rpc) {
+                    const uint32_t bb = std::min(a + rpc, dh) - 1;
+                    mx = std::max(mx, tv->h_left[bb] + tv->h_count[bb] - tv->h_left[a]);
+                }
+                return mx;
+            };
+            while (rows > 1 && (size_t)range(rows) * 64 > 64 * 1024) rows >>= 1;
+            const size_t smem = (size_t)range(rows) * 64;
+            const uint32_t gy = (dh + rows - 1) / rows;
+            if (smem <= 64 * 1024 && gy <= 65535u) {
+                static bool attr_set = false;
+                if (!attr_set) {
+                    KC_CUDA(cudaFuncSetAttribute(kc_resize_v_march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                    KC_CUDA(cudaFuncSetAttribute(kc_resize_v_march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+                    attr_set = true;
+                }
+                dim3 grid(((sw >> 2) + VM_THREADS - 1) / VM_THREADS, gy);
+                KcTimed timed(ctx, KC_KERNEL_RESIZE_V);
+                if (exact) kc_resize_v_march_kernel<true><<<grid, VM_THREADS, smem, ctx->stream>>>((const float4*)src, sw >> 2, (float4*)tmp, dh, tv->d_left, tv->d_count, (const float4*)tv->d_march_w, (const int4*)tv->d_march_o, rows);
+                else kc_resize_v_march_kernel<false><<<grid, VM_THREADS, smem, ctx->stream>>>((const float4*)src, sw >> 2, (float4*)tmp, dh, tv->d_left, tv->d_count, (const float4*)tv->d_march_w, (const int4*)tv->d_march_o, rows);
+                marched = true;
+            }
+        }
+    }
+    if (!marched) {
         dim3 grid((sw + 255) / 256, std::min<uint32_t>(dh, 65535u));
         KcTimed timed(ctx, KC_KERNEL_RESIZE_V);
         if (exact) kc_resize_v_kernel<true><<<grid, 256, 0, ctx->stream>>>(src, sw, tmp, dh, tv->d_left, tv->d_count, tv->d_weights);

@@ -270,6 +270,23 @@ def test_resize_row_strips_equal_whole_image(tex_pro, filt, src, dst, parts):
         assert bits_equal(strip, whole[r0:r1]), (r0, r1)
 
 
+@pytest.mark.parametrize("filt", list(ResizeFilter))
+@pytest.mark.parametrize("src,dst", [((512, 384), (64, 50)), ((1000, 700), (37, 91)), ((64, 640), (64, 80)),
+                                     ((256, 2048), (300, 100)), ((36, 300), (8, 7))])
+def test_resize_downsample_exact(tex_pro, filt, src, dst):
+    """Long windows: the source-marching vertical pass (ring of eight output rows in registers)
+    and the horizontal pass over its intermediate, bit for bit against the oracle; the last case
+    has width % 4 != 0 and stays on the per-output kernels."""
+    (sw, sh), (dw, dh) = src, dst
+    p = rnd(19, sh, sw, -0.25, 1.25)
+    if filt == ResizeFilter.Lanczos3:
+        p[sh // 2, sw // 3] = np.nan          # a NaN sample must reach exactly the outputs whose windows hold it
+        p[sh // 3, sw // 2] = np.inf
+    img = kc.SlotImage.from_planes(tex_pro, [p])
+    got = _resize_direct(tex_pro, img, dw, dh, filt).planes()[0]
+    assert bits_equal(got, oracle.resize_plane(p, dw, dh, int(filt)))
+
+
 def test_resize_rgba_with_constant_alpha(tex_pro):
     # a constant alpha plane goes through the same tap arithmetic as any other plane
     planes = [rnd(50 + c, 20, 30) for c in range(3)]
