@@ -184,6 +184,13 @@ int32_t kc_png_encode_file(const char* path, const uint8_t* samples, uint32_t w,
 int32_t kc_debug_set_tuning(const char* key, int32_t value);
 /* (tile float4s per thread, resident CTAs per SM, pipeline stages) of the last fused elementwise launch */
 int32_t kc_debug_last_tile_config(int32_t* v, int32_t* ctas, int32_t* stages);
+/* ---- spill queue: TransientBufferQueue, src/transient_buffer.rs:250-411 + TextureProcessor::memory_threshold,
+ *      src/texture_processor.rs:19.  Above `bytes` of live planes in HBM the least recently used ones move to
+ *      pinned host memory (the reference writes them to disk) and come back when something reads them.
+ *      0 = no limit (the default: 180 GB of HBM). */
+int32_t kc_context_set_memory_threshold(kc_context* ctx, uint64_t bytes);
+int32_t kc_context_spill_stats(const kc_context* ctx, uint64_t* bytes_spilled, uint64_t* spills, uint64_t* reloads);
+int32_t kc_plane_in_memory(const kc_plane* p, int32_t* in_memory);   /* TransientBufferContainer::in_memory */
 /* hand the device buffers the context keeps for reuse back to the driver's pool */
 int32_t kc_context_trim(kc_context* ctx);
 /* per-launch device timing: while on, every kernel the library launches on the
@@ -365,6 +372,7 @@ int32_t kc_live_graph_await_clean(kc_live_graph* lg, uint32_t node_id);
 int32_t kc_live_graph_cancel(kc_live_graph* lg);                              /* Node.cancel / shutdown flags, src/node/process_shared.rs:67-69 */
 int32_t kc_live_graph_node_state(const kc_live_graph* lg, uint32_t node_id, int32_t* state); /* node_state, :243-249 */
 int32_t kc_live_graph_slot_data(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, kc_image* out);   /* slot_data, :415-420 (retains) */
+int32_t kc_live_graph_slot_in_memory(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t* in_memory); /* :410-412 */
 int32_t kc_live_graph_slot_data_size(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint32_t* w, uint32_t* h); /* :407-409 */
 int32_t kc_live_graph_node_slot_ids(const kc_live_graph* lg, uint32_t node_id, uint32_t* slot_ids, size_t cap, size_t* n);    /* node_slot_datas, :389-405 */
 int32_t kc_live_graph_buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host_rgba8, size_t cap);   /* buffer_rgba, :93-95 */

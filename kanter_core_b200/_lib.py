@@ -82,6 +82,10 @@ SIGNATURES = {
     "kc_context_set_fuse": (i32, [vp, i32]),
     "kc_context_stats": (i32, [vp, P(u64), P(u64)]),
     "kc_context_trim": (i32, [vp]),
+    "kc_context_set_memory_threshold": (i32, [vp, u64]),
+    "kc_context_spill_stats": (i32, [vp, P(u64), P(u64), P(u64)]),
+    "kc_plane_in_memory": (i32, [vp, P(i32)]),
+    "kc_live_graph_slot_in_memory": (i32, [vp, u32, u32, P(i32)]),
     "kc_png_decode": (i32, [vp, sz, P(vp), P(u32), P(u32), P(u32)]),
     "kc_png_decode_file": (i32, [C.c_char_p, P(vp), P(u32), P(u32), P(u32)]),
     "kc_png_encode": (i32, [vp, u32, u32, u32, P(vp), P(sz)]),

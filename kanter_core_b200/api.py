@@ -664,6 +664,16 @@ class TextureProcessor:
     def synchronize(self):
         call("kc_context_synchronize", self._ctx._h)
 
+    def set_memory_threshold(self, nbytes):
+        """TextureProcessor::memory_threshold (src/texture_processor.rs:19): above this many bytes of live
+        planes the least recently used ones are spilled (here: to pinned host memory); 0 = no limit."""
+        call("kc_context_set_memory_threshold", self._ctx._h, int(nbytes))
+
+    def spill_stats(self):
+        b, s, r = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        call("kc_context_spill_stats", self._ctx._h, C.byref(b), C.byref(s), C.byref(r))
+        return {"bytes_spilled": b.value, "spills": s.value, "reloads": r.value}
+
     def stats(self):
         k, b = C.c_uint64(), C.c_uint64()
         call("kc_context_stats", self._ctx._h, C.byref(k), C.byref(b))
@@ -868,9 +878,10 @@ class LiveGraph(_GraphView):
         node.node_id = NodeId(node_id)
         self.set_node(node)
 
-    def slot_in_memory(self, node_id, slot_id):  # :410-412: planes live in HBM, nothing spills
-        self.slot_data_size(node_id, slot_id)
-        return True
+    def slot_in_memory(self, node_id, slot_id):  # :410-412: False while a plane sits in the spill queue's host memory
+        v = C.c_int32()
+        call("kc_live_graph_slot_in_memory", self._h, int(node_id), int(slot_id), C.byref(v))
+        return bool(v.value)
 
     def try_buffer_rgba(self, node_id, slot_id):  # :98-125 (never blocks here: no spill queue)
         return self.buffer_rgba(node_id, slot_id)

@@ -224,6 +224,14 @@ void kc_dev_trim(kc_context* ctx) {
         for (void* p : kv.second) cudaFreeAsync(p, ctx->stream);
     ctx->free_lists.clear();
     ctx->bytes_cached = 0;
+    bool any = false;
+    for (auto& kv : ctx->host_free_lists) any |= !kv.second.empty();
+    if (any) {
+        cudaStreamSynchronize(ctx->stream);   // copies out of / into these buffers may still be in flight
+        for (auto& kv : ctx->host_free_lists)
+            for (void* p : kv.second) cudaFreeHost(p);
+        ctx->host_free_lists.clear();
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -247,7 +255,130 @@ int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out) 
         return rc;
     }
     ctx->bytes_live += bytes;
+    p->last_use = ++ctx->use_tick;
+    ctx->resident.push_back(p);
+    if (ctx->bytes_live > ctx->memory_threshold) {
+        ++p->pins;                       // never the plane being handed out
+        rc = kc_enforce_threshold(ctx);
+        --p->pins;
+        if (rc != KC_OK) { kcp_release(p); return rc; }
+    }
     *out = p;
+    return KC_OK;
+}
+
+// ---------------------------------------------------------------------------
+// spill queue.  Everything here is ordered on the context's compute stream: the device-to-host copy
+// of a spill is enqueued before the device buffer goes back to the recycler, the host-to-device
+// copy of a reload before anything that reads the plane, and host buffers are recycled, never
+// freed, while the context lives -- so no call in this section has to wait for the GPU.
+// ---------------------------------------------------------------------------
+static void resident_remove(kc_context* ctx, kc_plane* p) {
+    auto it = std::find(ctx->resident.begin(), ctx->resident.end(), p);
+    if (it != ctx->resident.end()) { *it = ctx->resident.back(); ctx->resident.pop_back(); }
+}
+void kcp_touch(kc_plane* p) {
+    if (p && p->ctx) p->last_use = ++p->ctx->use_tick;
+}
+float* kcp_take_storage(kc_plane* p) {
+    float* d = p->dptr;
+    resident_remove(p->ctx, p);
+    p->dptr = nullptr;
+    p->owned = false;
+    return d;
+}
+void kcp_adopt_storage(kc_plane* p, float* dptr) {
+    p->kind = KC_PLANE_DEVICE;
+    p->dptr = dptr;
+    p->owned = true;
+    p->last_use = ++p->ctx->use_tick;
+    p->ctx->resident.push_back(p);
+}
+static int32_t host_alloc(kc_context* ctx, size_t bytes, void** out) {
+    auto it = ctx->host_free_lists.find(bytes);
+    if (it != ctx->host_free_lists.end() && !it->second.empty()) {
+        *out = it->second.back();
+        it->second.pop_back();
+        return KC_OK;
+    }
+    KC_CUDA(cudaMallocHost(out, bytes));
+    return KC_OK;
+}
+static int32_t spill_one(kc_context* ctx, kc_plane* p) {
+    const size_t bytes = plane_alloc_bytes(p);
+    void* h = nullptr;
+    KC_TRY(host_alloc(ctx, bytes, &h));
+    cudaError_t e = cudaMemcpyAsync(h, p->dptr, p->bytes(), cudaMemcpyDeviceToHost, ctx->stream);
+    if (e != cudaSuccess) {
+        ctx->host_free_lists[bytes].push_back(h);
+        KC_FAIL(KC_ERR_CUDA, "spill copy failed: %s", cudaGetErrorString(e));
+    }
+    kc_dev_free(ctx, p->dptr, bytes);
+    resident_remove(ctx, p);
+    p->dptr = nullptr;
+    p->host_copy = (float*)h;
+    p->kind = KC_PLANE_SPILLED;
+    ctx->bytes_live -= bytes;
+    ctx->bytes_spilled += bytes;
+    ctx->n_spills++;
+    return KC_OK;
+}
+int32_t kc_enforce_threshold(kc_context* ctx) {
+    while (ctx->bytes_live > ctx->memory_threshold) {
+        kc_plane* victim = nullptr;
+        for (kc_plane* q : ctx->resident)
+            if (q->pins == 0 && q->owned && q->dptr && (!victim || q->last_use < victim->last_use)) victim = q;
+        if (!victim) break;              // everything left is in use right now
+        KC_TRY(spill_one(ctx, victim));
+    }
+    return KC_OK;
+}
+int32_t kcp_reload(kc_context* ctx, kc_plane* p) {
+    if (p->kind != KC_PLANE_SPILLED) return KC_OK;
+    const size_t bytes = plane_alloc_bytes(p);
+    void* d = nullptr;
+    KC_TRY(kc_dev_alloc(ctx, bytes, &d));
+    cudaError_t e = cudaMemcpyAsync(d, p->host_copy, p->bytes(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+        kc_dev_free(ctx, d, bytes);
+        KC_FAIL(KC_ERR_CUDA, "reload copy failed: %s", cudaGetErrorString(e));
+    }
+    ctx->host_free_lists[bytes].push_back(p->host_copy);   // reusable at once: later copies into it are stream-ordered after this one
+    p->host_copy = nullptr;
+    p->dptr = (float*)d;
+    p->kind = KC_PLANE_DEVICE;
+    p->last_use = ++ctx->use_tick;
+    ctx->resident.push_back(p);
+    ctx->bytes_live += bytes;
+    ctx->bytes_spilled -= bytes;
+    ctx->n_reloads++;
+    if (ctx->bytes_live > ctx->memory_threshold) {
+        ++p->pins;
+        int32_t rc = kc_enforce_threshold(ctx);
+        --p->pins;
+        return rc;
+    }
+    return KC_OK;
+}
+
+extern "C" int32_t kc_context_set_memory_threshold(kc_context* ctx, uint64_t bytes) {
+    // TextureProcessor::memory_threshold, src/texture_processor.rs:19; 0 = no limit
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    KcGuard g(ctx);
+    ctx->memory_threshold = bytes ? bytes : UINT64_MAX;
+    return kc_enforce_threshold(ctx);
+}
+extern "C" int32_t kc_context_spill_stats(const kc_context* ctx, uint64_t* bytes_spilled, uint64_t* spills, uint64_t* reloads) {
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (bytes_spilled) *bytes_spilled = ctx->bytes_spilled;
+    if (spills) *spills = ctx->n_spills;
+    if (reloads) *reloads = ctx->n_reloads;
+    return KC_OK;
+}
+extern "C" int32_t kc_plane_in_memory(const kc_plane* p, int32_t* in_memory) {
+    // TransientBufferContainer::in_memory: constants and lazy planes hold no pixels, so they count as resident
+    if (!p || !in_memory) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    *in_memory = p->kind != KC_PLANE_SPILLED;
     return KC_OK;
 }
 
@@ -293,7 +424,13 @@ void kcp_release(kc_plane* p) {
             KcGuard g(q->ctx);
             const size_t bytes = plane_alloc_bytes(q);
             kc_dev_free(q->ctx, q->dptr, bytes);
+            resident_remove(q->ctx, q);
             q->ctx->bytes_live -= bytes;
+        } else if (q->kind == KC_PLANE_SPILLED && q->host_copy) {
+            KcGuard g(q->ctx);
+            const size_t bytes = plane_alloc_bytes(q);
+            q->ctx->host_free_lists[bytes].push_back(q->host_copy);
+            q->ctx->bytes_spilled -= bytes;
         } else if (q->kind == KC_PLANE_EXPR) {
             if (q->a) work.push_back(q->a);
             if (q->b) work.push_back(q->b);
@@ -390,13 +527,16 @@ extern "C" int32_t kc_plane_device_ptr(kc_plane* p, void** device_ptr) {
     if (!p || !device_ptr) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(p->ctx);
     KC_TRY(kcp_force(p->ctx, &p, 1));
+    ++p->pins;   // a raw pointer has left the library: this plane is never spilled again
     *device_ptr = p->dptr;
     return KC_OK;
 }
 extern "C" int32_t kc_plane_upload(kc_plane* p, const float* host) {
     if (!p || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
-    if (p->kind != KC_PLANE_DEVICE) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane has no device storage");
+    if (p->kind != KC_PLANE_DEVICE && p->kind != KC_PLANE_SPILLED) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane has no device storage");
     KcGuard g(p->ctx);
+    KC_TRY(kcp_reload(p->ctx, p));
+    kcp_touch(p);
     KC_CUDA(cudaMemcpyAsync(p->dptr, host, p->bytes(), cudaMemcpyHostToDevice, p->ctx->stream));
     return KC_OK;
 }
@@ -435,11 +575,12 @@ extern "C" int32_t kc_image_from_u8(kc_context* ctx, const uint8_t* samples, uin
     KC_TRY(kc_dev_alloc(ctx, staging, (void**)&d_samples));
     cudaError_t e = cudaMemcpyAsync(d_samples, samples, n * channels, cudaMemcpyHostToDevice, ctx->stream);
     float* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
+    KcPin pin;   // the planes allocated first stay in HBM while the later ones are allocated
     int32_t rc = e == cudaSuccess ? KC_OK : KC_ERR_CUDA;
     for (uint32_t c = 0; c < 4 && rc == KC_OK; ++c) {
         if (c < channels) {
             rc = kcp_new_device(ctx, w, h, &out->planes[c]);
-            if (rc == KC_OK) ptrs[c] = out->planes[c]->dptr;
+            if (rc == KC_OK) { ptrs[c] = out->planes[c]->dptr; pin.add(out->planes[c]); }
         } else {
             out->planes[c] = kcp_new_const(ctx, w, h, c == 3 ? 1.0f : 0.0f);
         }

@@ -154,10 +154,13 @@ int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullp
                 const kc_halo_link* inbox = nullptr, uint64_t step = 0) {
     if (in.rgba()) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "HeightToNormal needs a Gray input");
     kc_plane* src = in.im.planes[0];
+    KcPin pin;   // source, halo and the planes already allocated stay in HBM until the kernel is enqueued
     KC_TRY(kcp_force(ctx, &src, 1));
+    pin.add(src);
     if (halo) {
         if (halo->w != src->w || halo->h != 1) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "halo row must be %u x 1", src->w);
         KC_TRY(kcp_force(ctx, &halo, 1));
+        pin.add(halo);
     }
     if (h_full == 0) h_full = src->h;
     Img res;
@@ -165,6 +168,7 @@ int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullp
     for (int c = 0; c < 3; ++c) {
         kc_plane* p = nullptr;
         KC_TRY(kcp_new_device(ctx, src->w, src->h, &p));
+        pin.add(p);
         res.set(c, p);
     }
     res.set(3, kcp_new_const(ctx, src->w, src->h, 1.0f));  // from_buffers_rgb, slot_image.rs:90-102
@@ -218,6 +222,8 @@ int32_t plane_resize(kc_context* ctx, kc_plane* src, uint32_t w, uint32_t h, int
         }
     }
     KC_TRY(kcp_force(ctx, &src, 1));
+    KcPin pin;
+    pin.add(src);
     kc_plane* dst = nullptr;
     KC_TRY(kcp_new_device(ctx, w, nrows, &dst));
     int32_t rc = kck_resize_plane_rows(ctx, src->dptr, src->w, src->h, dst->dptr, w, h, filter, row0, nrows);
@@ -674,13 +680,15 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
             if (requested.count(s.node_id) || use_cache)
                 for (int c = 0; c < kci_nplanes(&s.image.im); ++c) {
                     kc_plane* p = s.image.im.planes[c];
-                    if (p->kind != KC_PLANE_DEVICE && std::find(roots.begin(), roots.end(), p) == roots.end()) roots.push_back(p);
+                    // lazy and constant planes become pixels; spilled ones stay where they are until somebody reads them
+                    if (p->kind != KC_PLANE_DEVICE && p->kind != KC_PLANE_SPILLED && std::find(roots.begin(), roots.end(), p) == roots.end()) roots.push_back(p);
                 }
         if (!roots.empty()) KC_TRY(kcp_force(ctx, roots.data(), roots.size()));
     }
     last_kernels = ctx->run_kernels - k0;
     last_groups = ctx->run_groups - g0;
     last_bytes = ctx->run_bytes - b0;
+    if (ctx->bytes_live > ctx->memory_threshold) KC_TRY(kc_enforce_threshold(ctx));   // nothing is pinned any more
     return KC_OK;
 }
 
@@ -794,10 +802,14 @@ int32_t kc_height_to_normal_strip_peer(kc_context* ctx, const kc_image* strip, c
 
 int32_t kc_plane_copy_rows(kc_context* ctx, kc_plane* dst, uint32_t dst_row, kc_plane* src, uint32_t src_row, uint32_t rows) {
     if (!ctx || !dst || !src) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
-    if (dst->kind != KC_PLANE_DEVICE) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "destination has no device storage");
+    if (dst->kind != KC_PLANE_DEVICE && dst->kind != KC_PLANE_SPILLED) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "destination has no device storage");
     if (dst->w != src->w || dst_row + rows > dst->h || src_row + rows > src->h) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "row range out of bounds");
     KcGuard g(ctx);
+    KcPin pin;
+    KC_TRY(kcp_reload(dst->ctx, dst));
+    pin.add(dst);
     KC_TRY(kcp_force(ctx, &src, 1));
+    pin.add(src);
     // a peer copy when the planes live on different devices (NVLink), a plain one otherwise
     KC_CUDA(cudaMemcpyAsync(dst->dptr + (size_t)dst_row * dst->w, src->dptr + (size_t)src_row * src->w,
                             sizeof(float) * (size_t)rows * src->w, cudaMemcpyDefault, ctx->stream));
@@ -1213,6 +1225,16 @@ int32_t kc_live_graph_slot_data(const kc_live_graph* lg, uint32_t node_id, uint3
     if (!s) KC_FAIL(KC_ERR_NO_SLOT_DATA, "Could not find a `SlotData` for node %u slot %u", node_id, slot_id);
     *out = s->image.im;
     kci_retain(out);
+    return KC_OK;
+}
+int32_t kc_live_graph_slot_in_memory(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t* in_memory) {
+    // LiveGraph::slot_in_memory, src/live_graph.rs:410-412 -> SlotImage::in_memory: every plane resident
+    if (!lg || !in_memory) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    const Slot* s = lg->find_slot(node_id, slot_id);
+    if (!s) KC_FAIL(KC_ERR_NO_SLOT_DATA, "Could not find a `SlotData` for node %u slot %u", node_id, slot_id);
+    int all = 1;
+    for (int c = 0; c < kci_nplanes(&s->image.im); ++c) all &= s->image.im.planes[c]->kind != KC_PLANE_SPILLED;
+    *in_memory = all;
     return KC_OK;
 }
 int32_t kc_live_graph_slot_data_size(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint32_t* w, uint32_t* h) {

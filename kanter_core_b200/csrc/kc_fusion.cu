@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 
 #include "kc_internal.h"
 
@@ -272,9 +273,7 @@ bool gen_segment(SegPlan& k, int pack, kc_plane* const* pack_planes, int srgb) {
 int32_t alloc_plane_storage(kc_context* ctx, kc_plane* like, float** out) {
     kc_plane* tmp = nullptr;
     KC_TRY(kcp_new_device(ctx, like->w, like->h, &tmp));
-    *out = tmp->dptr;
-    tmp->owned = false;  // the storage is adopted by the caller
-    tmp->dptr = nullptr;
+    *out = kcp_take_storage(tmp);  // the storage is adopted by the caller (kcp_adopt_storage)
     delete tmp;
     return KC_OK;
 }
@@ -282,6 +281,9 @@ int32_t alloc_plane_storage(kc_context* ctx, kc_plane* like, float** out) {
 // Launch a set of generated, mutually independent segments: grouped by pixel
 // count, up to KC_MAX_SEG per launch.
 int32_t launch_segments(kc_context* ctx, std::vector<SegPlan*>& segs, uint32_t* d_rgba8) {
+    KcPin pin;   // allocating the outputs may push the spill queue over its threshold: the sources stay
+    for (SegPlan* k : segs)
+        for (kc_plane* sp : k->gen.srcs) { pin.add(sp); kcp_touch(sp); }
     for (SegPlan* k : segs) {
         for (kc_plane* o : k->outs) {
             float* d = nullptr;
@@ -337,9 +339,7 @@ int32_t launch_segments(kc_context* ctx, std::vector<SegPlan*>& segs, uint32_t* 
         for (size_t m = 0; m < k->outs.size(); ++m) {
             kc_plane* o = k->outs[m];
             kc_plane *a = o->a, *b = o->b;
-            o->kind = KC_PLANE_DEVICE;
-            o->dptr = k->out_ptrs[m];
-            o->owned = true;
+            kcp_adopt_storage(o, k->out_ptrs[m]);
             o->a = o->b = nullptr;
             if (a) kcp_release(a);
             if (b) kcp_release(b);
@@ -407,10 +407,38 @@ void cone_of(kc_plane* o, std::vector<kc_plane*>& nodes, std::vector<kc_plane*>&
     }
 }
 
+// With a memory threshold in force: bring every spilled plane under the roots back into HBM and pin
+// every pixel-holding leaf, so that nothing this evaluation still has to read can be pushed out by
+// the allocations it makes (the pins go away with the caller's KcPin).
+int32_t reload_and_pin_leaves(kc_context* ctx, kc_plane* const* roots, size_t n, KcPin& pin) {
+    std::vector<kc_plane*> st(std::make_reverse_iterator(roots + n), std::make_reverse_iterator(roots)), seen;   // roots are visited (and stamped) in order
+    while (!st.empty()) {
+        kc_plane* p = st.back();
+        st.pop_back();
+        if (!p || std::find(seen.begin(), seen.end(), p) != seen.end()) continue;
+        seen.push_back(p);
+        if (p->kind == KC_PLANE_DEVICE) {
+            pin.add(p);
+            kcp_touch(p);
+        } else if (p->kind == KC_PLANE_SPILLED) {
+            pin.add(p);                 // pinned first: the reload's own threshold pass must not pick it
+            KC_TRY(kcp_reload(ctx, p));
+        } else if (p->kind == KC_PLANE_EXPR) {
+            st.push_back(p->a);
+            st.push_back(p->b);
+        }
+    }
+    return KC_OK;
+}
+
 int32_t force_impl(kc_context* ctx, kc_plane* const* roots, size_t n, int pack, int srgb, uint32_t* d_rgba8, int depth) {
     static std::atomic<int> mark_serial{MARK_BASE};
     if (depth > 64) KC_FAIL(KC_ERR_GENERIC, "fusion planner: recursion too deep");
+    KcPin leaves;
+    const bool spilling = ctx->memory_threshold != UINT64_MAX || ctx->bytes_spilled != 0;
     for (int round = 0; round < 100000; ++round) {
+        // every round: planes materialised by the previous one are leaves now
+        if (spilling) KC_TRY(reload_and_pin_leaves(ctx, roots, n, leaves));
         Cone c;
         collect(roots, n, ++mark_serial, c);
         bool changed = false;
@@ -535,7 +563,15 @@ int32_t force_impl(kc_context* ctx, kc_plane* const* roots, size_t n, int pack, 
 }  // namespace
 
 int32_t kcp_force(kc_context* ctx, kc_plane* const* roots, size_t n) {
-    return force_impl(ctx, roots, n, 0, 0, nullptr, 0);
+    int32_t rc = force_impl(ctx, roots, n, 0, 0, nullptr, 0);
+    // the evaluation held its operands in HBM (pins); now that they are released the queue may settle --
+    // except for the planes the caller asked for: it is about to read them
+    if (rc == KC_OK && ctx->bytes_live > ctx->memory_threshold) {
+        KcPin keep;
+        for (size_t i = 0; i < n; ++i) keep.add(roots[i]);
+        rc = kc_enforce_threshold(ctx);
+    }
+    return rc;
 }
 
 int32_t kcp_export_rgba8(kc_context* ctx, const kc_image* img, int srgb, uint32_t* d_out) {
@@ -543,5 +579,7 @@ int32_t kcp_export_rgba8(kc_context* ctx, const kc_image* img, int srgb, uint32_
     // whatever still has to be computed for this image.
     const int np = kci_nplanes(img);
     kc_plane* roots[4] = {img->planes[0], img->planes[1], img->planes[2], img->planes[3]};
-    return force_impl(ctx, roots, (size_t)np, np == 4 ? 1 : 2, srgb, d_out, 0);
+    int32_t rc = force_impl(ctx, roots, (size_t)np, np == 4 ? 1 : 2, srgb, d_out, 0);
+    if (rc == KC_OK && ctx->bytes_live > ctx->memory_threshold) rc = kc_enforce_threshold(ctx);
+    return rc;
 }

@@ -107,7 +107,8 @@ struct KcAxisTable {
 };
 
 // ---- planes -------------------------------------------------------------------
-enum KcPlaneKind { KC_PLANE_DEVICE = 0, KC_PLANE_CONST = 1, KC_PLANE_EXPR = 2 };
+// SPILLED: pixels moved to pinned host memory by the spill queue (kc_context.cu); forcing the plane brings them back
+enum KcPlaneKind { KC_PLANE_DEVICE = 0, KC_PLANE_CONST = 1, KC_PLANE_EXPR = 2, KC_PLANE_SPILLED = 3 };
 
 struct kc_plane {
     std::atomic<int> refs{1};
@@ -117,6 +118,10 @@ struct kc_plane {
     // DEVICE
     float* dptr = nullptr;
     bool owned = true;
+    // spill queue: host copy while SPILLED, recency stamp, and a pin count held while a launch is being assembled
+    float* host_copy = nullptr;
+    uint64_t last_use = 0;
+    int pins = 0;
     // CONST
     float value = 0.0f;
     // EXPR: a lazily evaluated  a (op) b ; operands are retained
@@ -154,6 +159,12 @@ struct kc_context {
     std::recursive_mutex mu;
     uint64_t kernel_launches = 0;
     uint64_t bytes_live = 0;
+    // spill queue (TransientBufferQueue, src/transient_buffer.rs:250-411): above `memory_threshold` bytes of
+    // live planes the least recently used ones move to pinned host memory and come back on access
+    uint64_t memory_threshold = UINT64_MAX;
+    uint64_t use_tick = 0, bytes_spilled = 0, n_spills = 0, n_reloads = 0;
+    std::vector<kc_plane*> resident;                       // owned DEVICE planes, candidates for spilling
+    std::map<size_t, std::vector<void*>> host_free_lists;  // pinned host buffers kept for reuse
     // per-request accounting (reset by the live graph)
     uint64_t run_kernels = 0, run_groups = 0, run_bytes = 0;
     std::map<std::tuple<uint32_t, uint32_t, int>, std::shared_ptr<KcAxisTable>> axis_tables;
@@ -230,6 +241,18 @@ void kc_dev_trim(kc_context* ctx);
 int32_t kc_png_decode_vec(const uint8_t* data, size_t n, std::vector<uint8_t>& samples, uint32_t& w, uint32_t& h, uint32_t& ch);
 int32_t kc_png_decode_file_vec(const char* path, std::vector<uint8_t>& samples, uint32_t& w, uint32_t& h, uint32_t& ch);
 int32_t kc_png_write_file(const char* path, const uint8_t* px, uint32_t w, uint32_t h, int ch);
+
+// ---- spill queue (kc_context.cu) ---------------------------------------------------
+void kcp_touch(kc_plane* p);                       // mark as most recently used
+void kcp_adopt_storage(kc_plane* p, float* dptr);  // p becomes an owned DEVICE plane over storage taken from kcp_take_storage
+float* kcp_take_storage(kc_plane* p);              // detach p's device storage (p is about to be deleted)
+int32_t kcp_reload(kc_context* ctx, kc_plane* p);  // SPILLED -> DEVICE
+int32_t kc_enforce_threshold(kc_context* ctx);     // spill unpinned LRU planes until bytes_live <= memory_threshold
+struct KcPin {                                     // keeps planes in HBM while a launch that reads/writes them is assembled
+    std::vector<kc_plane*> v;
+    void add(kc_plane* p) { if (p) { ++p->pins; v.push_back(p); } }
+    ~KcPin() { for (kc_plane* p : v) --p->pins; }
+};
 
 // ---- plane helpers (kc_context.cu) -------------------------------------------
 int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out);
