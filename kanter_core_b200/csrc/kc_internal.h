@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <set>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -171,6 +172,8 @@ struct kc_context {
     // 1 -> len broadcasts whose single normalised tap is exactly 1.0 (kc_exec.cu, plane_resize)
     std::map<std::pair<uint32_t, int>, bool> unit_broadcast;
     std::atomic<bool> cancel{false};
+    // kernels whose dynamic shared-memory limit has been raised on THIS device (the attribute is per device)
+    std::set<const void*> smem_attr_done;
     // exact-size recycling of device buffers on top of the stream-ordered pool: a plane freed
     // by one evaluation is handed to the next one of the same size without touching the driver
     std::map<size_t, std::vector<void*>> free_lists;
@@ -231,6 +234,15 @@ struct KcTuning {
     int resize_threads = 0;  // threads per CTA of the fused resize kernel (32, 64, 128)
 };
 extern KcTuning g_kc_tuning;
+
+// raise a kernel's dynamic shared-memory limit once per context (= per device)
+inline int32_t kc_ensure_smem_attr(kc_context* ctx, const void* fn, int bytes) {
+    if (ctx->smem_attr_done.count(fn)) return KC_OK;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) { kc_set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return KC_ERR_CUDA; }
+    ctx->smem_attr_done.insert(fn);
+    return KC_OK;
+}
 
 // ---- device buffers (kc_context.cu): stream-ordered, recycled by exact size ----
 int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out);

@@ -553,11 +553,7 @@ template <bool EXACT, int V, int MINB>
 int32_t launch_tile_vm(kc_context* ctx, const KcTapeArgs& a, int stages, int ns_max, int nt_max, int ctas_per_sm) {
     constexpr int TILE_PX = 1024 * V;
     const size_t smem = 128 + (size_t)(stages * ns_max + nt_max) * TILE_PX * 4;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        KC_CUDA(cudaFuncSetAttribute(kc_tile_vm_kernel<EXACT, V, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    KC_TRY(kc_ensure_smem_attr(ctx, (const void*)kc_tile_vm_kernel<EXACT, V, MINB>, 227 * 1024));
     const uint64_t tiles = (a.n + TILE_PX - 1) / TILE_PX;
     const uint64_t total = tiles * a.n_seg;
     if (total > 0xffffffffull) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane too large for one launch");

@@ -681,12 +681,7 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
             const size_t smem = (size_t)range(rows) * 64;
             const uint32_t gy = (dh + rows - 1) / rows;
             if (smem <= 64 * 1024 && gy <= 65535u) {
-                static bool attr_set = false;
-                if (!attr_set) {
-                    KC_CUDA(cudaFuncSetAttribute(kc_resize_v_march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                    KC_CUDA(cudaFuncSetAttribute(kc_resize_v_march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-                    attr_set = true;
-                }
+                KC_TRY(kc_ensure_smem_attr(ctx, exact ? (const void*)kc_resize_v_march_kernel<true> : (const void*)kc_resize_v_march_kernel<false>, 64 * 1024));
                 dim3 grid(((sw >> 2) + VM_THREADS - 1) / VM_THREADS, gy);
                 KcTimed timed(ctx, KC_KERNEL_RESIZE_V);
                 if (exact) kc_resize_v_march_kernel<true><<<grid, VM_THREADS, smem, ctx->stream>>>((const float4*)src, sw >> 2, (float4*)tmp, dh, tv->d_left, tv->d_count, (const float4*)tv->d_march_w, (const int4*)tv->d_march_o, rows);

@@ -247,3 +247,48 @@ def test_rename_output_and_misc(tex_pro):
     assert [e.output_id for e in lg.connected_edges(o1, Side.Input, SlotId(0))] == [v]
     lg.request(o1)
     assert lg.try_buffer_rgba(o1, SlotId(0)).reshape(-1).tolist() == [127, 127, 127, 255]
+
+
+def test_concurrent_threads_share_one_context(tex_pro):
+    """process_node is called from up to num_cpus engine threads at once in the reference
+    (src/engine.rs:288-296); here eight host threads drive their own LiveGraphs on ONE context
+    (ctypes drops the GIL inside every call) and every result must be its own."""
+    import threading
+    import oracle
+    errors = []
+
+    def worker(k):
+        try:
+            r = np.random.default_rng(900 + k)
+            for it in range(6):
+                A = r.random((96, 160), dtype=np.float32)
+                B = r.random((96, 160), dtype=np.float32)
+                lg = tex_pro.new_live_graph()
+                lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tex_pro, [A])), 0)
+                lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tex_pro, [B])), 1)
+                a = lg.add_node(Node.new(NodeType.Embed(0)))
+                b = lg.add_node(Node.new(NodeType.Embed(1)))
+                m = lg.add_node(Node.new(NodeType.Mix(MixType(k % 5))))
+                h = lg.add_node(Node.new(NodeType.HeightToNormal))
+                lg.connect(a, m, SlotId(0), SlotId(0))
+                lg.connect(b, m, SlotId(0), SlotId(1))
+                lg.connect(m, h, SlotId(0), SlotId(0))
+                LiveGraph.await_clean_read(lg, h)
+                got = lg.slot_data(h, SlotId(0)).image.planes()
+                with np.errstate(all="ignore"):
+                    want = oracle.height_to_normal(oracle.mix_plane(k % 5, A, B))
+                for c in range(3):
+                    same = np.array_equal(np.isnan(got[c]), np.isnan(want[c])) and np.array_equal(
+                        got[c][~np.isnan(got[c])].view(np.uint32), want[c][~np.isnan(want[c])].view(np.uint32))
+                    if not same:
+                        errors.append((k, it, c))
+                lg.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
