@@ -234,6 +234,14 @@ int32_t kc_image_from_u8(kc_context* ctx, const uint8_t* samples, uint32_t w, ui
 int32_t kc_image_from_host_planes(kc_context* ctx, int32_t kind, uint32_t w, uint32_t h,
                                   const float* const* planes, kc_image* out);
 /* SlotImage::from_value, src/slot_image.rs:28-64 */
+/* deferred upload: the planes stay in the caller's pinned memory until something reads them (then they go up on
+ * the upload stream); a plane no node reads -- the alpha of an image that only feeds Mix -- never crosses PCIe.
+ * The host memory must stay valid and unchanged until the context has been synchronised after the last use. */
+int32_t kc_plane_from_host_deferred(kc_context* ctx, uint32_t w, uint32_t h, const float* host, kc_plane** out);
+int32_t kc_image_from_host_planes_deferred(kc_context* ctx, int32_t kind, uint32_t w, uint32_t h,
+                                           const float* const* planes, kc_image* out);
+/* bytes copied host->device and device->host on behalf of the caller since the context was created */
+int32_t kc_context_transfer_stats(const kc_context* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 int32_t kc_image_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, int32_t rgba, kc_image* out);
 /* SlotImage::as_type, src/slot_image.rs:212-256 */
 int32_t kc_image_as_type(kc_context* ctx, const kc_image* in, int32_t rgba, kc_image* out);

@@ -82,6 +82,9 @@ SIGNATURES = {
     "kc_context_set_fuse": (i32, [vp, i32]),
     "kc_context_stats": (i32, [vp, P(u64), P(u64)]),
     "kc_context_trim": (i32, [vp]),
+    "kc_plane_from_host_deferred": (i32, [vp, u32, u32, vp, P(vp)]),
+    "kc_image_from_host_planes_deferred": (i32, [vp, i32, u32, u32, P(vp), P(kc_image)]),
+    "kc_context_transfer_stats": (i32, [vp, P(u64), P(u64)]),
     "kc_context_set_memory_threshold": (i32, [vp, u64]),
     "kc_context_spill_stats": (i32, [vp, P(u64), P(u64), P(u64)]),
     "kc_plane_in_memory": (i32, [vp, P(i32)]),

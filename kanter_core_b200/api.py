@@ -509,16 +509,23 @@ class SlotImage:
         return SlotImage(tex_pro._ctx, im)
 
     @staticmethod
-    def from_planes(tex_pro, planes, sync=True):
+    def from_planes(tex_pro, planes, sync=True, deferred=False):
         """planes: one (Gray) or four (Rgba) float32 arrays of shape (h, w).  With
         sync=False the copies are only enqueued: the arrays (pinned, see
-        pinned_empty) must stay alive and unchanged until the stream has passed them."""
+        pinned_empty) must stay alive and unchanged until the stream has passed them.
+        deferred=True: nothing is copied now; each plane goes up (on the upload stream) when
+        something first reads it, and a plane nobody reads never crosses PCIe."""
         arrs = [np.ascontiguousarray(p, dtype=np.float32) for p in planes]
         if len(arrs) not in (1, 4):
             raise TexProError(4, "need 1 or 4 planes")
         h, w = arrs[0].shape
         ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
         im = kc_image()
+        if deferred:
+            call("kc_image_from_host_planes_deferred", tex_pro._ctx._h, 1 if len(arrs) == 4 else 0, w, h, ptrs, C.byref(im))
+            img = SlotImage(tex_pro._ctx, im)
+            img._keep = arrs                                 # the planes read from these arrays later
+            return img
         call("kc_image_from_host_planes", tex_pro._ctx._h, 1 if len(arrs) == 4 else 0, w, h, ptrs, C.byref(im))
         if sync:
             call("kc_context_synchronize", tex_pro._ctx._h)  # the host arrays may go away after this returns
@@ -668,6 +675,11 @@ class TextureProcessor:
         """TextureProcessor::memory_threshold (src/texture_processor.rs:19): above this many bytes of live
         planes the least recently used ones are spilled (here: to pinned host memory); 0 = no limit."""
         call("kc_context_set_memory_threshold", self._ctx._h, int(nbytes))
+
+    def transfer_stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        call("kc_context_transfer_stats", self._ctx._h, C.byref(a), C.byref(b))
+        return {"h2d_bytes": a.value, "d2h_bytes": b.value}
 
     def spill_stats(self):
         b, s, r = C.c_uint64(), C.c_uint64(), C.c_uint64()

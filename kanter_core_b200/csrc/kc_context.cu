@@ -321,6 +321,7 @@ static int32_t spill_one(kc_context* ctx, kc_plane* p) {
     ctx->bytes_live -= bytes;
     ctx->bytes_spilled += bytes;
     ctx->n_spills++;
+    ctx->planes_on_host++;
     return KC_OK;
 }
 int32_t kc_enforce_threshold(kc_context* ctx) {
@@ -338,20 +339,36 @@ int32_t kcp_reload(kc_context* ctx, kc_plane* p) {
     const size_t bytes = plane_alloc_bytes(p);
     void* d = nullptr;
     KC_TRY(kc_dev_alloc(ctx, bytes, &d));
-    cudaError_t e = cudaMemcpyAsync(d, p->host_copy, p->bytes(), cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e;
+    if (p->host_borrowed) {
+        // a deferred upload: the caller's pinned memory -> HBM on the upload stream, ordered like kc_plane_from_host
+        e = cudaEventRecord(ctx->ev_up_wait, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->upload_stream, ctx->ev_up_wait, 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d, p->host_copy, p->bytes(), cudaMemcpyHostToDevice, ctx->upload_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_up_done, ctx->upload_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_up_done, 0);
+    } else {
+        e = cudaMemcpyAsync(d, p->host_copy, p->bytes(), cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e != cudaSuccess) {
         kc_dev_free(ctx, d, bytes);
         KC_FAIL(KC_ERR_CUDA, "reload copy failed: %s", cudaGetErrorString(e));
     }
-    ctx->host_free_lists[bytes].push_back(p->host_copy);   // reusable at once: later copies into it are stream-ordered after this one
+    if (p->host_borrowed) {
+        p->host_borrowed = false;
+        ctx->bytes_h2d += p->bytes();
+    } else {
+        ctx->host_free_lists[bytes].push_back(p->host_copy);   // reusable at once: later copies into it are stream-ordered after this one
+        ctx->bytes_spilled -= bytes;
+        ctx->n_reloads++;
+    }
     p->host_copy = nullptr;
     p->dptr = (float*)d;
     p->kind = KC_PLANE_DEVICE;
     p->last_use = ++ctx->use_tick;
     ctx->resident.push_back(p);
     ctx->bytes_live += bytes;
-    ctx->bytes_spilled -= bytes;
-    ctx->n_reloads++;
+    ctx->planes_on_host--;
     if (ctx->bytes_live > ctx->memory_threshold) {
         ++p->pins;
         int32_t rc = kc_enforce_threshold(ctx);
@@ -428,9 +445,12 @@ void kcp_release(kc_plane* p) {
             q->ctx->bytes_live -= bytes;
         } else if (q->kind == KC_PLANE_SPILLED && q->host_copy) {
             KcGuard g(q->ctx);
-            const size_t bytes = plane_alloc_bytes(q);
-            q->ctx->host_free_lists[bytes].push_back(q->host_copy);
-            q->ctx->bytes_spilled -= bytes;
+            if (!q->host_borrowed) {
+                const size_t bytes = plane_alloc_bytes(q);
+                q->ctx->host_free_lists[bytes].push_back(q->host_copy);
+                q->ctx->bytes_spilled -= bytes;
+            }
+            q->ctx->planes_on_host--;
         } else if (q->kind == KC_PLANE_EXPR) {
             if (q->a) work.push_back(q->a);
             if (q->b) work.push_back(q->b);
@@ -481,7 +501,33 @@ extern "C" int32_t kc_plane_from_host(kc_context* ctx, uint32_t w, uint32_t h, c
         kcp_release(p);
         KC_FAIL(KC_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
     }
+    ctx->bytes_h2d += p->bytes();
     *out = p;
+    return KC_OK;
+}
+
+extern "C" int32_t kc_plane_from_host_deferred(kc_context* ctx, uint32_t w, uint32_t h, const float* host, kc_plane** out) {
+    // The pixels stay in the caller's (pinned) memory until something reads the plane; a plane nobody
+    // reads -- the alpha of an image that only goes through Mix, say -- never crosses PCIe.  `host` must
+    // stay valid and unchanged until the context has been synchronised after the plane's last use.
+    if (!ctx || !out || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard g(ctx);
+    auto* p = new kc_plane();
+    p->ctx = ctx;
+    p->w = w;
+    p->h = h;
+    p->kind = KC_PLANE_SPILLED;
+    p->host_copy = const_cast<float*>(host);
+    p->host_borrowed = true;
+    ctx->planes_on_host++;
+    *out = p;
+    return KC_OK;
+}
+extern "C" int32_t kc_context_transfer_stats(const kc_context* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    // bytes copied host->device (plane uploads, u8 samples) and device->host (plane / RGBA8 downloads) so far
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (h2d_bytes) *h2d_bytes = ctx->bytes_h2d;
+    if (d2h_bytes) *d2h_bytes = ctx->bytes_d2h;
     return KC_OK;
 }
 
@@ -551,6 +597,7 @@ extern "C" int32_t kc_plane_download(kc_plane* p, float* host) {
     KC_TRY(kcp_force(p->ctx, &p, 1));
     KC_CUDA(cudaMemcpyAsync(host, p->dptr, p->bytes(), cudaMemcpyDeviceToHost, p->ctx->stream));
     KC_CUDA(cudaStreamSynchronize(p->ctx->stream));
+    p->ctx->bytes_d2h += p->bytes();
     return KC_OK;
 }
 
@@ -574,6 +621,7 @@ extern "C" int32_t kc_image_from_u8(kc_context* ctx, const uint8_t* samples, uin
     const size_t staging = ((n * channels + 15) / 16) * 16 + 16;
     KC_TRY(kc_dev_alloc(ctx, staging, (void**)&d_samples));
     cudaError_t e = cudaMemcpyAsync(d_samples, samples, n * channels, cudaMemcpyHostToDevice, ctx->stream);
+    ctx->bytes_h2d += n * channels;
     float* ptrs[4] = {nullptr, nullptr, nullptr, nullptr};
     KcPin pin;   // the planes allocated first stay in HBM while the later ones are allocated
     int32_t rc = e == cudaSuccess ? KC_OK : KC_ERR_CUDA;
@@ -605,6 +653,24 @@ extern "C" int32_t kc_image_from_host_planes(kc_context* ctx, int32_t kind, uint
     int np = kci_nplanes(out);
     for (int c = 0; c < np; ++c) {
         int32_t rc = kc_plane_from_host(ctx, w, h, planes[c], &out->planes[c]);
+        if (rc != KC_OK) {
+            kci_release(out);
+            return rc;
+        }
+    }
+    return KC_OK;
+}
+
+extern "C" int32_t kc_image_from_host_planes_deferred(kc_context* ctx, int32_t kind, uint32_t w, uint32_t h,
+                                                      const float* const* planes, kc_image* out) {
+    if (!ctx || !planes || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    kci_clear(out);
+    out->kind = kind == KC_IMAGE_RGBA ? KC_IMAGE_RGBA : KC_IMAGE_GRAY;
+    out->width = w;
+    out->height = h;
+    int np = kci_nplanes(out);
+    for (int c = 0; c < np; ++c) {
+        int32_t rc = kc_plane_from_host_deferred(ctx, w, h, planes[c], &out->planes[c]);
         if (rc != KC_OK) {
             kci_release(out);
             return rc;
@@ -662,6 +728,7 @@ extern "C" int32_t kc_image_download(kc_context* ctx, const kc_image* in, float*
             for (size_t i = 0; i < n; ++i) host_planes[c][i] = p->value;
         } else {
             KC_CUDA(cudaMemcpyAsync(host_planes[c], p->dptr, p->bytes(), cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->bytes_d2h += p->bytes();
         }
     }
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -696,6 +763,12 @@ extern "C" int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, in
 static int32_t to_u8_enqueue(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) {
     const size_t n = (size_t)in->planes[0]->w * in->planes[0]->h;
     const size_t staging = ((n * 4 + 15) / 16) * 16 + 16;
+    // deferred inputs start their uploads BEFORE the compute stream is made to wait for the previous
+    // download: an upload waits for the compute stream's tail, and that wait must not be part of it
+    {
+        kc_plane* roots[4] = {in->planes[0], in->planes[1], in->planes[2], in->planes[3]};
+        KC_TRY(kcp_prefetch_leaves(ctx, roots, (size_t)kci_nplanes(in)));
+    }
     if (ctx->dl_pending) KC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_dl_done, 0));
     if (ctx->dl_staging_bytes < staging) {
         if (ctx->dl_staging) KC_CUDA(cudaFreeAsync(ctx->dl_staging, ctx->stream));   // ordered after the wait above
@@ -711,6 +784,7 @@ static int32_t to_u8_enqueue(kc_context* ctx, const kc_image* in, int32_t srgb, 
     if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
     KC_CUDA(cudaEventRecord(ctx->ev_dl_done, ctx->download_stream));
     ctx->dl_pending = true;
+    ctx->bytes_d2h += n * 4;
     return KC_OK;
 }
 

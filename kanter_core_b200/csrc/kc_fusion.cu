@@ -435,7 +435,7 @@ int32_t force_impl(kc_context* ctx, kc_plane* const* roots, size_t n, int pack, 
     static std::atomic<int> mark_serial{MARK_BASE};
     if (depth > 64) KC_FAIL(KC_ERR_GENERIC, "fusion planner: recursion too deep");
     KcPin leaves;
-    const bool spilling = ctx->memory_threshold != UINT64_MAX || ctx->bytes_spilled != 0;
+    const bool spilling = ctx->memory_threshold != UINT64_MAX || ctx->planes_on_host != 0;
     for (int round = 0; round < 100000; ++round) {
         // every round: planes materialised by the previous one are leaves now
         if (spilling) KC_TRY(reload_and_pin_leaves(ctx, roots, n, leaves));
@@ -561,6 +561,13 @@ int32_t force_impl(kc_context* ctx, kc_plane* const* roots, size_t n, int pack, 
 }
 
 }  // namespace
+
+int32_t kcp_prefetch_leaves(kc_context* ctx, kc_plane* const* roots, size_t n) {
+    // start the uploads of every host-resident plane under the roots now (they are reloaded, not pinned)
+    if (ctx->planes_on_host == 0) return KC_OK;
+    KcPin scratch;
+    return reload_and_pin_leaves(ctx, roots, n, scratch);
+}
 
 int32_t kcp_force(kc_context* ctx, kc_plane* const* roots, size_t n) {
     int32_t rc = force_impl(ctx, roots, n, 0, 0, nullptr, 0);

@@ -121,6 +121,7 @@ struct kc_plane {
     bool owned = true;
     // spill queue: host copy while SPILLED, recency stamp, and a pin count held while a launch is being assembled
     float* host_copy = nullptr;
+    bool host_borrowed = false;   // host_copy is the caller's (pinned) memory: a plane whose upload is deferred until somebody reads it
     uint64_t last_use = 0;
     int pins = 0;
     // CONST
@@ -164,6 +165,8 @@ struct kc_context {
     // live planes the least recently used ones move to pinned host memory and come back on access
     uint64_t memory_threshold = UINT64_MAX;
     uint64_t use_tick = 0, bytes_spilled = 0, n_spills = 0, n_reloads = 0;
+    uint64_t planes_on_host = 0;              // spilled + deferred planes alive: evaluations must look for them
+    uint64_t bytes_h2d = 0, bytes_d2h = 0;    // what crossed PCIe on behalf of the caller (kc_context_transfer_stats)
     std::vector<kc_plane*> resident;                       // owned DEVICE planes, candidates for spilling
     std::map<size_t, std::vector<void*>> host_free_lists;  // pinned host buffers kept for reuse
     // per-request accounting (reset by the live graph)
@@ -259,6 +262,7 @@ void kcp_touch(kc_plane* p);                       // mark as most recently used
 void kcp_adopt_storage(kc_plane* p, float* dptr);  // p becomes an owned DEVICE plane over storage taken from kcp_take_storage
 float* kcp_take_storage(kc_plane* p);              // detach p's device storage (p is about to be deleted)
 int32_t kcp_reload(kc_context* ctx, kc_plane* p);  // SPILLED -> DEVICE
+int32_t kcp_prefetch_leaves(kc_context* ctx, kc_plane* const* roots, size_t n);  // kc_fusion.cu: reload every host-resident leaf under roots
 int32_t kc_enforce_threshold(kc_context* ctx);     // spill unpinned LRU planes until bytes_live <= memory_threshold
 struct KcPin {                                     // keeps planes in HBM while a launch that reads/writes them is assembled
     std::vector<kc_plane*> v;

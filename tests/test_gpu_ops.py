@@ -473,3 +473,40 @@ def test_pipelined_async_read_matches_sync(tex_pro):
             kc.free_pinned(p)
     for p in outs:
         kc.free_pinned(p)
+
+
+def test_deferred_host_planes_upload_only_what_is_read(tex_pro):
+    """from_planes(deferred=True): planes stay in pinned host memory until an evaluation reads them;
+    Mix(rgba) never reads alpha, so 6 of 8 planes are uploaded, and the result is unchanged."""
+    tp = tex_pro
+    S = 128
+    A = [kc.pinned_empty((S, S)) for _ in range(4)]
+    B = [kc.pinned_empty((S, S)) for _ in range(4)]
+    for i, p in enumerate(A + B):
+        p[...] = rnd(500 + i, S, S)
+    out = kc.pinned_empty((S, S, 4), np.uint8)
+    lg = tp.new_live_graph()
+    lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tp, A, deferred=True)), 0)
+    lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tp, B, deferred=True)), 1)
+    a = lg.add_node(Node.new(NodeType.Embed(0)))
+    b = lg.add_node(Node.new(NodeType.Embed(1)))
+    m = lg.add_node(Node.new(NodeType.Mix(MixType.Multiply)))
+    o = lg.add_node(Node.new(NodeType.OutputRgba("out")))
+    lg.connect(a, m, SlotId(0), SlotId(0))
+    lg.connect(b, m, SlotId(0), SlotId(1))
+    lg.connect(m, o, SlotId(0), SlotId(0))
+    x0 = tp.transfer_stats()
+    lg.read_rgba(o, SlotId(0), Size(S, S), out=out)
+    x1 = tp.transfer_stats()
+    assert x1["h2d_bytes"] - x0["h2d_bytes"] == 6 * S * S * 4
+    assert x1["d2h_bytes"] - x0["d2h_bytes"] == S * S * 4
+    planes = [oracle.mix_plane(2, A[c], B[c]) for c in range(3)] + [np.ones((S, S), np.float32)]
+    assert np.array_equal(out, oracle.to_u8(planes, False))
+    # reading a deferred plane directly uploads just that plane
+    img = kc.SlotImage.from_planes(tp, A, deferred=True)
+    assert np.array_equal(img.planes()[3], A[3])
+    x2 = tp.transfer_stats()
+    assert x2["h2d_bytes"] - x1["h2d_bytes"] == 4 * S * S * 4
+    tp.synchronize()
+    for p in A + B + [out]:
+        kc.free_pinned(p)
