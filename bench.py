@@ -353,6 +353,10 @@ def ours(args, rank, world, local_rank):
         except Exception:
             traffic = None
 
+    tv, tc_, ts_ = C.c_int32(), C.c_int32(), C.c_int32()
+    call("kc_debug_last_tile_config", C.byref(tv), C.byref(tc_), C.byref(ts_))
+    mode_name = "EXACT" if args.math == "exact" else "FAST"
+    kernel_name = ("kc_jit_entry = kc_tile_vm_body<%s> specialised for this tape with NVRTC" % mode_name) if tv.value < 0 else ("kc_tile_vm_kernel<%s> (tape interpreter)" % mode_name)
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -367,7 +371,7 @@ def ours(args, rank, world, local_rank):
                     "steps": e2e_steps, "step_ms_min_median_max": [min(e2e_step_ms), float(np.median(e2e_step_ms)), max(e2e_step_ms)], "path": "8 pinned host f32 planes per step -> deferred upload of the 6 planes the graph reads (upload stream) -> fused mul/pow/to_u8 kernel -> RGBA8 on pinned host (read_rgba, download stream); steps pipelined one deep; bytes as counted by the library"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "kc_tile_vm_kernel<%s>" % ("EXACT" if args.math == "exact" else "FAST"),
+                         "traffic": traffic, "kernel": kernel_name,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms,
                          "launches_timed": int(kn.value), "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0},

@@ -886,6 +886,7 @@ static KcTuning tuning_from_env() {
     t.stages = env_int("KC_STAGES");
     t.src_soft_cap = env_int("KC_SRC_SOFT_CAP");
     t.resize_threads = env_int("KC_RESIZE_THREADS");
+    t.jit = env_int("KC_JIT");
     return t;
 }
 KcTuning g_kc_tuning = tuning_from_env();
@@ -898,6 +899,7 @@ extern "C" int32_t kc_debug_set_tuning(const char* key, int32_t value) {
     else if (k == "stages") g_kc_tuning.stages = value;
     else if (k == "src_soft_cap") g_kc_tuning.src_soft_cap = value;
     else if (k == "resize_threads") g_kc_tuning.resize_threads = value;
+    else if (k == "jit") g_kc_tuning.jit = value;
     else KC_FAIL(KC_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
     return KC_OK;
 }

@@ -16,10 +16,10 @@ full() {  # name kernel-regex skip math only
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -f -o $O/prof_$1_${TAG} \
       python scripts/kernel_bench.py --math $4 --only $5 --reps 2 > $O/${TAG}_ncu_$1.log 2>&1
 }
-full tilevm_cfg2_fast kc_tile_vm 3 fast config2_fused
+full tilevm_cfg2_fast "kc_tile_vm|kc_jit_entry" 3 fast config2_fused
 full resize_lanczos3_fast kc_resize_strip 3 fast resize_lanczos3_1024
 full h2n_fast kc_h2n_vec 3 fast height_to_normal
 full h2n_exact kc_h2n_vec 3 exact height_to_normal
-full to_u8_rgba kc_tile_vm 3 fast to_u8_rgba
+full to_u8_rgba "kc_tile_vm|kc_jit_entry" 3 fast to_u8_rgba
 full from_u8 kc_from_u8 2 fast from_u8
 tail -3 $O/${TAG}_pytest.log; tail -c 600 $O/${TAG}_bench.log; cat $O/${TAG}_kernels_fast.log
