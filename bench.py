@@ -349,7 +349,8 @@ def ours(args, rank, world, local_rank):
     tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("tape_kernel_%s" % args.math, {}).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = (tj.get("fused_kernel_%s_specialised" % args.math) or tj.get("tape_kernel_%s" % args.math, {})).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
 
