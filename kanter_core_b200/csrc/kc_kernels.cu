@@ -1,22 +1,19 @@
-// kc_kernels.cu — the elementwise device kernels.
+// kc_kernels.cu — the elementwise device kernels and their launch code.
 //
-//  * kc_tape_kernel: ONE kernel for every chain/tree of per-pixel node work:
+//  * kc_tile_vm_kernel: ONE kernel for every chain/tree of per-pixel node work:
 //    Mix add/subtract/multiply/divide/pow (src/node/mix.rs:136-302), the
 //    Rgba->Gray average of SlotImage::as_type (src/slot_image.rs:242-253),
 //    constant fills (SlotImage::from_value, :28-64) and the f32->RGBA8 export of
-//    SlotImage::to_u8 / to_u8_srgb (:142-207).  It interprets a short op tape
-//    (kc_internal.h) over float4s of pixels with sources, temporaries and the
-//    accumulator all in registers, so a fused group reads each source plane once
-//    and writes each result plane once; intermediates never touch HBM.
-//    blockIdx.y selects one of up to four independent segments (e.g. the R, G
-//    and B expression chains of an Rgba graph), each thread interprets its
-//    segment's tape once for V float4s at a time.
+//    SlotImage::to_u8 / to_u8_srgb (:142-207).  Persistent CTAs walk (segment, tile)
+//    work items -- up to four independent segments per launch, e.g. the R, G and B
+//    chains of an Rgba graph -- with the source tiles arriving by TMA bulk copies;
+//    a fused group reads each source plane once and writes each result plane once,
+//    intermediates never touch HBM.  The device code lives in kc_tile_vm.cuh (shared
+//    with the NVRTC-specialised variant, kc_jit.cu); here the body is instantiated
+//    with the tape interpreter, and kck_launch_tape picks the configuration and the
+//    variant.
 //  * kc_from_u8_kernel: deconstruct_image's u8/255 de-interleave (src/shared.rs:16-56).
 //  * kc_fill_kernel: materialise a constant plane.
-//
-// HBM-bound streaming work: 16-byte coalesced accesses, streaming cache hints
-// (every byte is touched once), all source loads of a pixel group issued before
-// the first use, grid.x = SM count x resident CTAs (grid-stride inside).
 #include <cstdlib>
 
 #include "kc_internal.h"
