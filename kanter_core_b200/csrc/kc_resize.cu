@@ -449,6 +449,62 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
     }
 }
 
+// horizontal_sample for LONG windows.  One CTA = 256 adjacent outputs x HT_ROWS rows: the stretch of
+// the intermediate those outputs read is staged in shared memory with coalesced loads (index i
+// lives at i + i/32, so the stride-R reads of neighbouring outputs spread over the banks), and a
+// thread walks its window ONCE for all the rows -- each tap weight is fetched once per HT_ROWS
+// outputs and the rows are independent accumulation chains.  Same tap order and clamp as
+// kc_resize_h_kernel.
+constexpr int HT_ROWS = 8;
+
+template <bool EXACT>
+__global__ void __launch_bounds__(256) kc_resize_h_tile_kernel(const float* __restrict__ tmp, uint32_t sw, float* __restrict__ dst, uint32_t dw,
+                                                               uint32_t dh, const uint32_t* __restrict__ left, const uint32_t* __restrict__ count,
+                                                               const float* __restrict__ wh, uint32_t pitch) {
+    extern __shared__ __align__(16) float htile[];                 // [HT_ROWS][pitch]
+    const uint32_t ox0 = blockIdx.x * 256, oxl = min(ox0 + 256, dw) - 1;
+    const uint32_t y0 = blockIdx.y * HT_ROWS, nrow = min((uint32_t)HT_ROWS, dh - y0);
+    const uint32_t c0 = __ldg(left + ox0), ncol = __ldg(left + oxl) + __ldg(count + oxl) - c0;
+    // staging: the loads of all HT_ROWS rows of a column are in flight together (the intermediate comes from L2)
+    for (uint32_t i = threadIdx.x; i < ncol; i += 256) {
+        float v[HT_ROWS];
+#pragma unroll
+        for (int r = 0; r < HT_ROWS; ++r) v[r] = __ldg(tmp + (size_t)(y0 + min((uint32_t)r, nrow - 1)) * sw + c0 + i);
+        const uint32_t si = i + (i >> 5);
+#pragma unroll
+        for (int r = 0; r < HT_ROWS; ++r) htile[(size_t)r * pitch + si] = v[r];
+    }
+    __syncthreads();
+    const uint32_t ox = ox0 + threadIdx.x;
+    if (ox > oxl) return;
+    const uint32_t l = __ldg(left + ox) - c0, n = __ldg(count + ox);
+    float acc[HT_ROWS];
+#pragma unroll
+    for (int r = 0; r < HT_ROWS; ++r) acc[r] = 0.0f;
+    const float* wp = wh + ox;
+    constexpr int WB = 8;                                          // tap weights fetched WB at a time
+    for (uint32_t j0 = 0; j0 < n; j0 += WB) {
+        float w[WB];
+#pragma unroll
+        for (int k = 0; k < WB; ++k) w[k] = __ldg(wp + (size_t)min(j0 + k, n - 1) * dw);
+#pragma unroll
+        for (int k = 0; k < WB; ++k) {
+            if (j0 + k < n) {
+                const uint32_t i = l + j0 + k;
+                const float* sp = htile + i + (i >> 5);
+#pragma unroll
+                for (int r = 0; r < HT_ROWS; ++r) acc[r] = tap<EXACT>(acc[r], sp[(size_t)r * pitch], w[k]);   // rows past nrow: duplicates, never stored
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < HT_ROWS; ++r)
+        if ((uint32_t)r < nrow) {
+            const float a = acc[r];
+            dst[(size_t)(y0 + r) * dw + ox] = a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a);   // image::math::utils::clamp keeps NaN
+        }
+}
+
 // ---------------------------------------------------------------------------
 // Vertical pass for LONG windows (downsampling: 6 R + 1 taps for a ratio R with Lanczos3), as
 // a march over the SOURCE rows.  The two-pass kernel above reads every source row once per
@@ -696,7 +752,17 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
         if (exact) kc_resize_v_kernel<true><<<grid, 256, 0, ctx->stream>>>(src, sw, tmp, dh, tv->d_left, tv->d_count, tv->d_weights);
         else kc_resize_v_kernel<false><<<grid, 256, 0, ctx->stream>>>(src, sw, tmp, dh, tv->d_left, tv->d_count, tv->d_weights);
     }
-    {
+    const uint32_t hwin = max_window(*th, 256);
+    const uint32_t hpitch = hwin + (hwin >> 5) + 1;
+    const size_t hsmem = sizeof(float) * (size_t)HT_ROWS * hpitch;
+    const uint32_t hgy = (dh + HT_ROWS - 1) / HT_ROWS;
+    if (!no_march && th->max_taps > (uint32_t)FS_MAXT && hsmem <= 96 * 1024 && hgy <= 65535u) {
+        KC_TRY(kc_ensure_smem_attr(ctx, exact ? (const void*)kc_resize_h_tile_kernel<true> : (const void*)kc_resize_h_tile_kernel<false>, 96 * 1024));
+        dim3 grid((dw + 255) / 256, hgy);
+        KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
+        if (exact) kc_resize_h_tile_kernel<true><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, hpitch);
+        else kc_resize_h_tile_kernel<false><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, hpitch);
+    } else {
         dim3 grid((dw + 255) / 256, std::min<uint32_t>(dh, 65535u));
         KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
         if (exact) kc_resize_h_kernel<true><<<grid, 256, 0, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights);
