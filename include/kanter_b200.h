@@ -182,7 +182,11 @@ int32_t kc_png_encode_file(const char* path, const uint8_t* samples, uint32_t w,
 /* tuning knobs for the sweep scripts (0 = library default): "tile_v", "ctas", "stages",
  * "src_soft_cap", "resize_threads"; process-wide */
 int32_t kc_debug_set_tuning(const char* key, int32_t value);
-/* (tile float4s per thread, resident CTAs per SM, pipeline stages) of the last fused elementwise launch */
+/* NVRTC-only check of the kernel generator (kc_jit.cu): compiles the specialised kernel of a one-segment tape
+ * (planner words op | arg << 8) for sm_100a; needs no GPU */
+int32_t kc_debug_jit_compile(const uint32_t* instr, uint32_t n_instr, int32_t exact, int32_t v, int32_t ctas, size_t* cubin_bytes);
+/* (tile float4s per thread, resident CTAs per SM, pipeline stages) of the last fused elementwise launch; V < 0: the
+ * specialised kernel ran */
 int32_t kc_debug_last_tile_config(int32_t* v, int32_t* ctas, int32_t* stages);
 /* ---- spill queue: TransientBufferQueue, src/transient_buffer.rs:250-411 + TextureProcessor::memory_threshold,
  *      src/texture_processor.rs:19.  Above `bytes` of live planes in HBM the least recently used ones move to

@@ -297,3 +297,28 @@ def test_node_graph_bookkeeping_surface():
     nid = g.new_id()
     assert int(nid) not in [int(n) for n in g.node_ids()]
     assert sorted(int(x) for x in g.get_children_recursive(a)) == sorted([int(m), int(o1), int(o2)])
+
+
+def test_kernel_generator_compiles_with_nvrtc():
+    """kc_jit.cu: the device code embedded in the library (kc_tape.h + kc_tile_vm.cuh) plus the
+    straight-line program generated from a tape compile for sm_100a with NVRTC -- no GPU involved.
+    Tapes: every arithmetic op on source / temporary / immediate operands, stores, both exports."""
+    import ctypes as C
+    from kanter_core_b200._lib import call
+    LD, ADD, SUB, RSUB, MUL, DIV, RDIV, POW, RPOW, ST_TMP, ST_OUT, PACK_RGBA, PACK_GRAY = range(13)
+    S = lambda k: k          # source k
+    T = lambda j: 8 + j      # temporary j
+    IMM = 14
+    w = lambda op, arg=0: op | (arg << 8)
+    tapes = {
+        "all_ops": [w(LD, S(0)), w(ADD, S(1)), w(SUB, IMM), w(RSUB, S(2)), w(ST_TMP, 0), w(MUL, S(3)), w(DIV, T(0)), w(RDIV, IMM),
+                    w(POW, S(1)), w(RPOW, T(0)), w(ST_OUT, 0), w(LD, T(0)), w(ST_OUT, 1)],
+        "export_rgba": [w(LD, S(0)), w(ST_TMP, 0), w(LD, S(1)), w(ST_TMP, 1), w(LD, S(2)), w(MUL, S(3)), w(ST_TMP, 2), w(LD, IMM), w(PACK_RGBA, 1)],
+        "export_gray": [w(LD, S(0)), w(POW, IMM), w(PACK_GRAY, 0)],
+    }
+    for name, tape in tapes.items():
+        arr = (C.c_uint32 * len(tape))(*tape)
+        for exact, v, ctas in ((1, 4, 3), (0, 1, 2)):
+            n = C.c_size_t()
+            call("kc_debug_jit_compile", arr, len(tape), exact, v, ctas, C.byref(n))
+            assert n.value > 10000, (name, exact, v)
