@@ -965,6 +965,34 @@ def mix(tex_pro, mix_type, left, right):
     return SlotImage(tex_pro._ctx, out)
 
 
+def process_node(tex_pro, node, slot_datas, edges, embedded_slot_datas=(), input_slot_datas=()):
+    """`process_node`, src/node/node_type.rs:213-248 -- THE seam the backend sits behind: one node,
+    the SlotData of its connected inputs (slot_datas[i] arrived over edges[i]), the graph's embedded
+    and input slot data; returns the node's output SlotDatas.  `embedded_slot_datas`: iterable of
+    (embedded id, SlotData)."""
+    d, keep = node._desc()
+    n = len(slot_datas)
+    if n != len(edges):
+        raise TexProError(101, "edges.len() != slot_datas.len()")
+    sd = (_lib.kc_slot_data * max(1, n))()
+    ed = (kc_edge * max(1, n))()
+    for i, (s_, e_) in enumerate(zip(slot_datas, edges)):
+        sd[i].node_id, sd[i].slot_id, sd[i].image = int(s_.node_id), int(s_.slot_id), s_.image._im
+        ed[i] = kc_edge(int(e_.output_id), int(e_.input_id), int(e_.output_slot), int(e_.input_slot))
+    emb = list(embedded_slot_datas)
+    em = (_lib.kc_embedded_slot_data * max(1, len(emb)))()
+    for i, (eid, s_) in enumerate(emb):
+        em[i].slot_data_id, em[i].slot_id, em[i].image = int(eid), int(s_.slot_id), s_.image._im
+    ins = list(input_slot_datas)
+    isd = (_lib.kc_slot_data * max(1, len(ins)))()
+    for i, s_ in enumerate(ins):
+        isd[i].node_id, isd[i].slot_id, isd[i].image = int(s_.node_id), int(s_.slot_id), s_.image._im
+    out = (_lib.kc_slot_data * 8)()
+    n_out = C.c_size_t()
+    call("kc_process_node", tex_pro._ctx._h, C.byref(d), sd, n, em, len(emb), isd, len(ins), ed, n, out, 8, C.byref(n_out))
+    return [SlotData(NodeId(out[i].node_id), SlotId(out[i].slot_id), SlotImage(tex_pro._ctx, out[i].image)) for i in range(n_out.value)]
+
+
 def height_to_normal(tex_pro, image):
     """height_to_normal::process, src/node/height_to_normal.rs:16-77."""
     out = kc_image()
