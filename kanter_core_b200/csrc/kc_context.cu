@@ -714,6 +714,8 @@ extern "C" int32_t kc_image_release(kc_image* img) {
 
 extern "C" int32_t kc_image_download(kc_context* ctx, const kc_image* in, float* const* host_planes) {
     if (!ctx || !in || !host_planes) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    for (int c = 0; c < kci_nplanes(in); ++c)
+        if (!in->planes[c] || !host_planes[c]) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "image has no plane %d (released?) or no destination for it", c);
     KcGuard g(ctx);
     int np = kci_nplanes(in);
     // one fused launch for whatever is still lazy, then the copies
@@ -761,6 +763,8 @@ extern "C" int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, in
 // the copy to the host runs on the download stream.  The buffer is rewritten only after the
 // previous download has finished (ev_dl_done).
 static int32_t to_u8_enqueue(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) {
+    for (int c = 0; c < kci_nplanes(in); ++c)
+        if (!in->planes[c]) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "image has no plane %d (released?)", c);
     const size_t n = (size_t)in->planes[0]->w * in->planes[0]->h;
     const size_t staging = ((n * 4 + 15) / 16) * 16 + 16;
     // deferred inputs start their uploads BEFORE the compute stream is made to wait for the previous

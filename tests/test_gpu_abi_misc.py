@@ -1,0 +1,120 @@
+"""The plane / image level of the C ABI called directly (no Python mirror in between): plane life
+cycle and reference counts, uploads and downloads, Separate / Combine as pure aliasing, the
+asynchronous RGBA8 export, context accessors."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import kanter_core_b200 as kc
+import oracle
+from kanter_core_b200._lib import call, kc_image, lib
+
+pytestmark = pytest.mark.gpu
+
+
+def rnd(seed, h, w):
+    return np.random.default_rng(seed).random((h, w), dtype=np.float32)
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def test_plane_life_cycle(tex_pro):
+    ctx = tex_pro._ctx._h
+    a, b = rnd(1, 20, 30), rnd(2, 20, 30)
+    p = C.c_void_p()
+    call("kc_plane_from_host", ctx, 30, 20, fptr(a), C.byref(p))
+    w, h = C.c_uint32(), C.c_uint32()
+    call("kc_plane_size", p, C.byref(w), C.byref(h))
+    assert (w.value, h.value) == (30, 20)
+    out = np.empty_like(a)
+    call("kc_plane_download", p, fptr(out))
+    assert np.array_equal(out, a)
+    call("kc_plane_retain", p)
+    call("kc_plane_release", p)                      # still one reference left
+    q = C.c_void_p()
+    call("kc_plane_create", ctx, 30, 20, C.byref(q))
+    call("kc_plane_upload", q, fptr(b))
+    call("kc_plane_download", q, fptr(out))
+    assert np.array_equal(out, b)
+    d = C.c_void_p()
+    call("kc_plane_from_host_deferred", ctx, 30, 20, fptr(a), C.byref(d))
+    inmem = C.c_int32(1)
+    call("kc_plane_in_memory", d, C.byref(inmem))
+    assert inmem.value == 0                          # still in the caller's memory
+    call("kc_plane_download", d, fptr(out))
+    assert np.array_equal(out, a)
+    call("kc_plane_in_memory", d, C.byref(inmem))
+    assert inmem.value == 1
+    for x in (p, q, d):
+        call("kc_plane_release", x)
+    with pytest.raises(kc.TexProError):
+        call("kc_plane_from_host", ctx, 30, 20, None, C.byref(p))
+    assert lib.kc_last_error()                       # thread-local message of the failure above
+
+
+def test_separate_combine_alias_planes_and_image_download(tex_pro):
+    ctx = tex_pro._ctx._h
+    P = [rnd(10 + c, 12, 9) for c in range(4)]
+    img = kc.SlotImage.from_planes(tex_pro, P)
+    parts = (kc_image * 4)()
+    k0 = tex_pro.stats()["kernel_launches"]
+    call("kc_separate_rgba", ctx, C.byref(img._im), parts)
+    for c in range(4):
+        assert parts[c].kind == 0 and parts[c].planes[0] == img._im.planes[c]        # the very same plane objects
+    chans = (C.POINTER(kc_image) * 4)(C.pointer(parts[3]), None, C.pointer(parts[0]), None)
+    comb = kc_image()
+    call("kc_combine_rgba", ctx, chans, C.byref(comb))
+    assert comb.kind == 1 and comb.planes[0] == img._im.planes[3] and comb.planes[2] == img._im.planes[0]
+    assert tex_pro.stats()["kernel_launches"] == k0
+    extra = kc_image()
+    C.memmove(C.byref(extra), C.byref(comb), C.sizeof(kc_image))
+    call("kc_image_retain", C.byref(extra))          # a second owner of the same planes ...
+    call("kc_image_release", C.byref(extra))         # ... gives its references back (release also clears the struct)
+    assert not any(extra.planes[c] for c in range(4))
+    outs = [np.empty((12, 9), np.float32) for _ in range(4)]
+    ptrs = (C.c_void_p * 4)(*[o.ctypes.data for o in outs])
+    call("kc_image_download", ctx, C.byref(comb), ptrs)
+    assert np.array_equal(outs[0], P[3]) and np.array_equal(outs[2], P[0])
+    assert not outs[1].any() and np.array_equal(outs[3], np.ones((12, 9), np.float32))  # missing G -> 0, missing A -> 1
+    call("kc_image_release", C.byref(comb))
+    for c in range(4):
+        call("kc_image_release", C.byref(parts[c]))
+
+
+def test_async_export_and_context_accessors(tex_pro):
+    ctx = tex_pro._ctx._h
+    dev, stream = C.c_int32(-1), C.c_void_p()
+    call("kc_context_device", ctx, C.byref(dev))
+    call("kc_context_stream", ctx, C.byref(stream))
+    assert dev.value == 0 and stream.value
+    P = [rnd(30 + c, 64, 64) for c in range(4)]
+    img = kc.SlotImage.from_planes(tex_pro, P)
+    host = kc.pinned_empty((64, 64, 4), np.uint8)
+    call("kc_image_to_u8_async", ctx, C.byref(img._im), 0, host.ctypes.data)
+    call("kc_context_synchronize", ctx)
+    assert np.array_equal(host, oracle.to_u8(P, False))
+    kc.free_pinned(host)
+    call("kc_context_trim", ctx)                     # recycled buffers go back to the driver; everything still works
+    assert np.array_equal(img.planes()[1], P[1])
+
+
+def test_clear_input_slot_data(tex_pro):
+    from kanter_core_b200 import Node, NodeType, SlotData, SlotId
+    H = rnd(40, 8, 8)
+    lg = tex_pro.new_live_graph()
+    i = lg.add_node(Node.new(NodeType.InputGray("in")))
+    o = lg.add_node(Node.new(NodeType.OutputGray("out")))
+    lg.connect(i, o, SlotId(0), SlotId(0))
+    lg.add_input_slot_data(SlotData.new(i, 0, kc.SlotImage.from_planes(tex_pro, [H])))
+    kc.LiveGraph.await_clean_read(lg, o)
+    assert np.array_equal(lg.slot_data(o, SlotId(0)).image.planes()[0], H)
+    call("kc_live_graph_clear_input_slot_data", lg._h)
+    assert lg.node_state(i) == kc.NodeState.Dirty and lg.node_state(o) == kc.NodeState.Dirty
+    # an Input node without data yields no buffers (src/node/input_gray.rs:7-16) -> InvalidBufferCount
+    # (node_type.rs:124-137; the reference's engine shuts down on it, src/engine.rs:104-120)
+    with pytest.raises(kc.TexProError) as e:
+        lg.request(o)
+    assert e.value.kind == "InvalidBufferCount"
