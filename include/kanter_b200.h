@@ -216,7 +216,9 @@ int32_t kc_event_elapsed_ms(void* start_event, void* stop_event, float* ms);  /*
 /* ---- planes: TransientBufferContainer / Buffer, src/slot_image.rs:12,
  *      src/transient_buffer.rs:188-247 --------------------------------------- */
 int32_t kc_plane_create(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out);          /* uninitialised */
-int32_t kc_plane_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, kc_plane** out); /* vec![v; n], kept as a descriptor until pixels are needed */
+/* vec![v; n], kept as a descriptor until pixels are needed.  ctx may be NULL for a descriptor that is
+ * only ever measured (kc_plane_size, kc_calculate_size): no device is touched. */
+int32_t kc_plane_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, kc_plane** out);
 int32_t kc_plane_from_host(kc_context* ctx, uint32_t w, uint32_t h, const float* host, kc_plane** out);
 /* adopt caller-owned device memory (16-byte aligned, w*h floats); never freed by the library */
 int32_t kc_plane_wrap_device(kc_context* ctx, uint32_t w, uint32_t h, void* device_ptr, kc_plane** out);

@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libkanter_b200.so")
+# KANTER_B200_LIB: load another build of the same library (the AddressSanitizer build, scripts/README.md)
+LIB_PATH = os.environ.get("KANTER_B200_LIB") or os.path.join(HERE, "libkanter_b200.so")
 
 # ---- enums (include/kanter_b200.h) ------------------------------------------
 KC_OK = 0

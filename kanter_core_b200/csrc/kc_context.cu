@@ -133,6 +133,7 @@ static void axis_table_free(KcAxisTable& t) {
 
 extern "C" int32_t kc_context_destroy(kc_context* ctx) {
     if (!ctx) return KC_OK;
+    if (ctx->closed) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "the context was destroyed already");
     {
         KcGuard g(ctx);
         cudaStreamSynchronize(ctx->upload_stream);
@@ -149,8 +150,14 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) {
         cudaStreamDestroy(ctx->upload_stream);
         cudaStreamDestroy(ctx->download_stream);
         cudaStreamDestroy(ctx->stream);
+        ctx->timed.clear();
+        ctx->event_pool.clear();
+        ctx->dl_staging = nullptr;
+        ctx->stream = ctx->upload_stream = ctx->download_stream = nullptr;
+        ctx->ev_up_wait = ctx->ev_up_done = ctx->ev_dl_wait = ctx->ev_dl_done = nullptr;
+        ctx->closed = true;
     }
-    delete ctx;
+    kc_ctx_unref(ctx);   // planes and live graphs still alive keep the bookkeeping until they are released
     return KC_OK;
 }
 
@@ -196,6 +203,7 @@ extern "C" int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_laun
 // it was enqueued earlier on that stream than whatever will write it next.
 // ---------------------------------------------------------------------------
 int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out) {
+    if (ctx->closed) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "the context was destroyed");
     auto it = ctx->free_lists.find(bytes);
     if (it != ctx->free_lists.end() && !it->second.empty()) {
         *out = it->second.back();
@@ -215,6 +223,10 @@ int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out) {
 
 void kc_dev_free(kc_context* ctx, void* p, size_t bytes) {
     if (!p) return;
+    if (ctx->closed) {   // a plane that outlived its context: the streams are gone, free synchronously
+        cudaFree(p);
+        return;
+    }
     ctx->free_lists[bytes].push_back(p);
     ctx->bytes_cached += bytes;
 }
@@ -243,15 +255,14 @@ static inline size_t plane_alloc_bytes(const kc_plane* p) {
     return bytes ? bytes : 16;
 }
 int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out) {
-    auto* p = new kc_plane();
-    p->ctx = ctx;
+    auto* p = kcp_alloc(ctx);
     p->w = w;
     p->h = h;
     p->kind = KC_PLANE_DEVICE;
     const size_t bytes = plane_alloc_bytes(p);
     int32_t rc = kc_dev_alloc(ctx, bytes, (void**)&p->dptr);
     if (rc != KC_OK) {
-        delete p;
+        kcp_dealloc(p);
         return rc;
     }
     ctx->bytes_live += bytes;
@@ -400,8 +411,7 @@ extern "C" int32_t kc_plane_in_memory(const kc_plane* p, int32_t* in_memory) {
 }
 
 kc_plane* kcp_new_const(kc_context* ctx, uint32_t w, uint32_t h, float v) {
-    auto* p = new kc_plane();
-    p->ctx = ctx;
+    auto* p = kcp_alloc(ctx);
     p->w = w;
     p->h = h;
     p->kind = KC_PLANE_CONST;
@@ -410,8 +420,7 @@ kc_plane* kcp_new_const(kc_context* ctx, uint32_t w, uint32_t h, float v) {
 }
 
 kc_plane* kcp_new_expr(kc_context* ctx, int op, kc_plane* a, kc_plane* b) {
-    auto* p = new kc_plane();
-    p->ctx = ctx;
+    auto* p = kcp_alloc(ctx);
     // constants broadcast; the size comes from whichever side has pixels
     const kc_plane* sz = (a->kind != KC_PLANE_CONST) ? a : b;
     p->w = sz->w;
@@ -447,7 +456,8 @@ void kcp_release(kc_plane* p) {
             KcGuard g(q->ctx);
             if (!q->host_borrowed) {
                 const size_t bytes = plane_alloc_bytes(q);
-                q->ctx->host_free_lists[bytes].push_back(q->host_copy);
+                if (q->ctx->closed) cudaFreeHost(q->host_copy);
+                else q->ctx->host_free_lists[bytes].push_back(q->host_copy);
                 q->ctx->bytes_spilled -= bytes;
             }
             q->ctx->planes_on_host--;
@@ -455,7 +465,7 @@ void kcp_release(kc_plane* p) {
             if (q->a) work.push_back(q->a);
             if (q->b) work.push_back(q->b);
         }
-        delete q;
+        kcp_dealloc(q);
     }
 }
 
@@ -477,7 +487,8 @@ extern "C" int32_t kc_plane_create(kc_context* ctx, uint32_t w, uint32_t h, kc_p
 }
 
 extern "C" int32_t kc_plane_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, kc_plane** out) {
-    if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    // ctx may be NULL: a descriptor that is only measured (kc_plane_size, kc_calculate_size) needs no device
+    if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = kcp_new_const(ctx, w, h, v);
     return KC_OK;
 }
@@ -512,8 +523,7 @@ extern "C" int32_t kc_plane_from_host_deferred(kc_context* ctx, uint32_t w, uint
     // stay valid and unchanged until the context has been synchronised after the plane's last use.
     if (!ctx || !out || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
-    auto* p = new kc_plane();
-    p->ctx = ctx;
+    auto* p = kcp_alloc(ctx);
     p->w = w;
     p->h = h;
     p->kind = KC_PLANE_SPILLED;
@@ -534,8 +544,7 @@ extern "C" int32_t kc_context_transfer_stats(const kc_context* ctx, uint64_t* h2
 extern "C" int32_t kc_plane_wrap_device(kc_context* ctx, uint32_t w, uint32_t h, void* device_ptr, kc_plane** out) {
     if (!ctx || !out || !device_ptr) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (((uintptr_t)device_ptr & 15) != 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "device pointer must be 16-byte aligned");
-    auto* p = new kc_plane();
-    p->ctx = ctx;
+    auto* p = kcp_alloc(ctx);
     p->w = w;
     p->h = h;
     p->kind = KC_PLANE_DEVICE;

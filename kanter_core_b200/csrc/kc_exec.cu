@@ -943,6 +943,7 @@ int32_t kc_live_graph_create(kc_context* ctx, kc_live_graph** out) {
     if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     auto* lg = new kc_live_graph();
     lg->ctx = ctx;
+    kc_ctx_ref(ctx);
     *out = lg;
     return KC_OK;
 }
@@ -956,7 +957,9 @@ int32_t kc_live_graph_destroy(kc_live_graph* lg) {
         for (auto& e : lg->embeds) kci_release(&e.image);
         lg->embeds.clear();
     }
+    kc_context* ctx = lg->ctx;
     delete lg;
+    kc_ctx_unref(ctx);
     return KC_OK;
 }
 int32_t kc_live_graph_set_node_graph(kc_live_graph* lg, const kc_graph* g) {

@@ -98,6 +98,12 @@ struct kc_plane {
 };
 
 struct kc_context {
+    // Planes and live graphs point back at their context.  Each of them, and the caller's own
+    // handle, holds one count; kc_context_destroy releases the device side at once (`closed`)
+    // and the struct itself goes with the last count, so images and graphs that outlive the
+    // context -- the reference's SlotImages outlive its Engine -- can still be released.
+    std::atomic<int> handles{1};
+    bool closed = false;
     int device = 0;
     cudaStream_t stream = nullptr;           // every kernel, and every copy that is not one of the two below
     // copy engines next to the compute stream: planes built from host memory are uploaded on
@@ -164,10 +170,15 @@ struct KcTimed {
 };
 
 // RAII device selection + context lock
-struct KcGuard {
+inline void kc_ctx_ref(kc_context* c) { c->handles.fetch_add(1, std::memory_order_relaxed); }
+inline void kc_ctx_unref(kc_context* c) {
+    if (c->handles.fetch_sub(1, std::memory_order_acq_rel) == 1) delete c;
+}
+struct KcGuard {   // holds a count of its own: the last plane may go while the lock is held
     kc_context* ctx;
     int prev = -1;
     explicit KcGuard(kc_context* c) : ctx(c) {
+        kc_ctx_ref(ctx);
         ctx->mu.lock();
         cudaGetDevice(&prev);
         if (prev != ctx->device) cudaSetDevice(ctx->device);
@@ -175,8 +186,23 @@ struct KcGuard {
     ~KcGuard() {
         if (prev >= 0 && prev != ctx->device) cudaSetDevice(prev);
         ctx->mu.unlock();
+        kc_ctx_unref(ctx);
     }
+    KcGuard(const KcGuard&) = delete;
+    KcGuard& operator=(const KcGuard&) = delete;
 };
+// every kc_plane is made and unmade here (the context count goes with it)
+inline kc_plane* kcp_alloc(kc_context* ctx) {
+    auto* p = new kc_plane();
+    p->ctx = ctx;
+    if (ctx) kc_ctx_ref(ctx);   // NULL: a constant descriptor that belongs to no context (kc_plane_from_value)
+    return p;
+}
+inline void kcp_dealloc(kc_plane* p) {
+    kc_context* c = p->ctx;
+    delete p;
+    if (c) kc_ctx_unref(c);
+}
 
 // ---- tuning knobs (kc_context.cu): 0 = let the library choose.  Set from the environment
 // (KC_TILE_V, KC_CTAS, KC_STAGES, KC_SRC_SOFT_CAP, KC_RESIZE_THREADS) at load time or through
@@ -219,10 +245,18 @@ float* kcp_take_storage(kc_plane* p);              // detach p's device storage 
 int32_t kcp_reload(kc_context* ctx, kc_plane* p);  // SPILLED -> DEVICE
 int32_t kcp_prefetch_leaves(kc_context* ctx, kc_plane* const* roots, size_t n);  // kc_fusion.cu: reload every host-resident leaf under roots
 int32_t kc_enforce_threshold(kc_context* ctx);     // spill unpinned LRU planes until bytes_live <= memory_threshold
-struct KcPin {                                     // keeps planes in HBM while a launch that reads/writes them is assembled
+void kcp_retain(kc_plane* p);
+void kcp_release(kc_plane* p);
+// Keeps planes in HBM while a launch that reads/writes them is assembled.  A pin is also a reference:
+// the launch's outputs drop their operands once it is enqueued, and a source that only the
+// expression held would otherwise be gone before the pin is.
+struct KcPin {
     std::vector<kc_plane*> v;
-    void add(kc_plane* p) { if (p) { ++p->pins; v.push_back(p); } }
-    ~KcPin() { for (kc_plane* p : v) --p->pins; }
+    void add(kc_plane* p) { if (p) { kcp_retain(p); ++p->pins; v.push_back(p); } }
+    ~KcPin() { for (kc_plane* p : v) { --p->pins; kcp_release(p); } }
+    KcPin() = default;
+    KcPin(const KcPin&) = delete;
+    KcPin& operator=(const KcPin&) = delete;
 };
 
 // ---- plane helpers (kc_context.cu) -------------------------------------------

@@ -118,3 +118,27 @@ def test_clear_input_slot_data(tex_pro):
     with pytest.raises(kc.TexProError) as e:
         lg.request(o)
     assert e.value.kind == "InvalidBufferCount"
+
+
+def test_images_and_graphs_may_outlive_their_context():
+    """The reference's SlotImages and LiveGraphs are Arc-owned and outlive the Engine;
+    here planes and live graphs keep the context's bookkeeping alive, so releasing them
+    after kc_context_destroy is legal, and using them for new work is an error."""
+    ctx = C.c_void_p()
+    call("kc_context_create", 0, None, C.byref(ctx))
+    a = np.random.default_rng(0).random((64, 48), dtype=np.float32)
+    im = kc_image()
+    ptrs = (C.c_void_p * 4)(a.ctypes.data, 0, 0, 0)
+    call("kc_image_from_host_planes", ctx, 0, 48, 64, ptrs, C.byref(im))
+    lazy = kc_image()
+    call("kc_mix", ctx, 2, C.byref(im), C.byref(im), C.byref(lazy))     # an unevaluated expression over `im`
+    lg = C.c_void_p()
+    call("kc_live_graph_create", ctx, C.byref(lg))
+    call("kc_context_destroy", ctx)
+    out = np.empty((64, 48), np.float32)
+    optrs = (C.c_void_p * 4)(out.ctypes.data, 0, 0, 0)
+    with pytest.raises(kc.TexProError):
+        call("kc_image_download", ctx, C.byref(lazy), optrs)                   # needs a new plane: refused
+    call("kc_image_release", C.byref(lazy))
+    call("kc_image_release", C.byref(im))
+    call("kc_live_graph_destroy", lg)                                          # the last handle: the context goes here

@@ -1,0 +1,237 @@
+"""Seeded random node graphs, every slot of every node compared bit for bit with
+the CPU oracle (EXACT mode), and within the stated tolerance in FAST mode.
+
+The hand-written tests pin each operator; this one pins the planner: which nodes
+fuse into one tape, how many sources a tape reads, temporaries, broadcast of 1x1
+values, implicit resizes in the middle of a fused chain, Gray/Rgba coercion, fan-out
+of one plane into several consumers, nested evaluation order.
+"""
+import numpy as np
+import pytest
+
+import kanter_core_b200 as kc
+import oracle
+from kanter_core_b200 import MixType, Node, NodeType, ResizeFilter, ResizePolicy, Size, SlotId
+from kanter_core_b200._lib import call
+
+from .test_gpu_ops import ABS, REL, bits_equal
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [(64, 64), (96, 64), (50, 70), (33, 17), (128, 128), (1, 1), (7, 200)]
+POLICIES = [ResizePolicy.MostPixels, ResizePolicy.LeastPixels, ResizePolicy.LargestAxes, ResizePolicy.SmallestAxes]
+MIX = list(MixType)
+
+
+def random_graph(seed, n_ops, h2n=True, typed=True):
+    """-> (NodeGraph, {embed id: planes}).  Every op node takes its inputs from earlier
+    nodes, so the graph is a DAG.  With `typed` the generator tracks which outputs carry
+    Gray and which Rgba data and only makes connections the operators accept at run time
+    (HeightToNormal and CombineRgba read Gray, SeparateRgba reads Rgba, outputs read their
+    own kind); without it only the static slot types are respected and some graphs fail
+    to evaluate - in the reference as well."""
+    r = np.random.default_rng(seed)
+    g = kc.NodeGraph.new()
+    embeds = {}
+    outs = []  # (node id, output slot, kind of the data "gray" | "rgba", static slot type "gray" | "rgba" | "any")
+
+    def add(nt, policy=None, filt=None):
+        n = Node.new(nt)
+        if policy is not None:
+            n.resize_policy = policy
+        if filt is not None:
+            n.resize_filter = filt
+        return g.add_node(n)
+
+    for eid in range(int(r.integers(2, 5))):
+        w, h = [z for z in SIZES if z != (1, 1)][int(r.integers(len(SIZES) - 1))]
+        nplanes = 4 if r.random() < 0.5 else 1
+        lo, hi = (-0.5, 1.5) if r.random() < 0.3 else (0.0, 1.0)
+        embeds[eid] = [(r.random((h, w), dtype=np.float32) * np.float32(hi - lo) + np.float32(lo)).astype(np.float32)
+                       for _ in range(nplanes)]
+        outs.append((add(NodeType.Embed(eid)), 0, "rgba" if nplanes == 4 else "gray", "rgba"))  # node_type.rs:186-188
+    for _ in range(int(r.integers(1, 3))):
+        outs.append((add(NodeType.Value(float(np.float32(r.random() * 2.0)))), 0, "gray", "gray"))
+
+    def policy(connected):
+        p = r.random()
+        if p < 0.55 or not connected:
+            return POLICIES[int(r.integers(len(POLICIES)))]
+        if p < 0.75:
+            return ResizePolicy.SpecificSlot(SlotId(connected[int(r.integers(len(connected)))]))
+        w, h = SIZES[int(r.integers(len(SIZES)))]
+        return ResizePolicy.SpecificSize(Size.new(w, h))
+
+    def pick(want=None):
+        pool = [o for o in outs if not typed or want is None or (o[2] == want and o[3] in (want, "any"))]
+        return pool[int(r.integers(len(pool)))] if pool else None
+
+    def build(nt, filt, sources):
+        """sources: {input slot: picked output}.  The policy is drawn knowing which slots
+        are connected; edges the static slot types refuse (untyped mode) are left out."""
+        n = add(nt, policy(sorted(sources)), filt)
+        kinds = {}
+        for in_slot, (src, s, kind, _) in sources.items():
+            try:
+                g.connect(src, n, SlotId(s), SlotId(in_slot))
+                kinds[in_slot] = kind
+            except kc.TexProError:
+                assert not typed
+        return n, kinds
+
+    for _ in range(n_ops):
+        p = r.random()
+        filt = list(ResizeFilter)[int(r.integers(len(ResizeFilter)))]
+        if p < 0.55:
+            src = {0: pick()}
+            if r.random() < 0.9:
+                src[1] = pick()
+            if r.random() < 0.05:
+                del src[0]           # right side only: zeros op right (mix.rs:77-83)
+            n, kinds = build(NodeType.Mix(MIX[int(r.integers(len(MIX)))]), filt, src)
+            if kinds:
+                outs.append((n, 0, kinds.get(0) or kinds[1], "any"))
+        elif p < 0.70:
+            one = pick("rgba")
+            if one:
+                n, kinds = build(NodeType.SeparateRgba, filt, {0: one})
+                if kinds:
+                    outs.extend((n, s, "gray", "gray") for s in range(4))
+        elif p < 0.85:
+            src = {s: pick("gray") for s in range(4) if r.random() < 0.8}
+            src = {s: o for s, o in src.items() if o}
+            n, kinds = build(NodeType.CombineRgba, filt, src)
+            outs.append((n, 0, "rgba", "rgba"))
+        elif h2n:
+            one = pick("gray")
+            n, kinds = build(NodeType.HeightToNormal, filt, {0: one}) if one else (None, None)
+            if kinds:
+                outs.append((n, 0, "rgba", "rgba"))
+    for k in range(int(r.integers(1, 4))):
+        rgba = r.random() < 0.5
+        one = pick("rgba" if rgba else "gray")
+        if one:
+            nt = NodeType.OutputRgba("o%d" % k) if rgba else NodeType.OutputGray("o%d" % k)
+            n = add(nt)
+            try:
+                g.connect(one[0], n, SlotId(one[1]), SlotId(0))
+            except kc.TexProError:
+                assert not typed
+    return g, embeds
+
+
+def evaluate_both(tp, graph, embeds, use_cache=True):
+    """use_cache (src/live_graph.rs:72) keeps every node's slot data; without it the live
+    graph drops a parent's data once its children are clean, as the reference does."""
+    og = oracle.from_node_graph(graph)
+    for eid, planes in embeds.items():
+        og.embed(eid, planes)
+    og.eval()
+    lg = tp.new_live_graph()
+    lg.use_cache = use_cache
+    lg.set_node_graph(graph)
+    for eid, planes in embeds.items():
+        lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tp, planes)), eid)
+    if use_cache:
+        for n in graph.nodes:        # nodes no output depends on are evaluated only when asked for
+            kc.LiveGraph.await_clean_read(lg, n.node_id)
+    return og, lg
+
+
+def each_slot(og, lg, graph):
+    for n in graph.nodes:
+        nid = int(n.node_id)
+        if not lg.use_cache:         # ask node by node; whatever was dropped is evaluated again
+            kc.LiveGraph.await_clean_read(lg, n.node_id)
+        for s in og.slot_ids(nid):
+            yield nid, n, s, og.slot(nid, s), lg.slot_data(n.node_id, SlotId(s)).image.planes()
+
+
+def describe(graph, nid):
+    ins = [(int(e.output_id), int(e.output_slot), int(e.input_slot)) for e in graph.edges if int(e.input_id) == nid]
+    return "node %d inputs(out node, out slot, in slot)=%s" % (nid, ins)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_graph_exact(tex_pro, seed):
+    graph, embeds = random_graph(1000 + seed, n_ops=6 + seed % 17)
+    og, lg = evaluate_both(tex_pro, graph, embeds, use_cache=seed % 2 == 0)
+    checked = 0
+    for nid, n, s, want, got in each_slot(og, lg, graph):
+        assert len(got) == len(want), (describe(graph, nid), n.node_type, s)
+        for c in range(len(want)):
+            assert bits_equal(got[c], want[c]), (describe(graph, nid), n.node_type, s, c, got[c].shape, want[c].shape)
+        checked += 1
+    assert checked >= len(embeds)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_graph_exact_specialised_kernels(tex_pro, seed):
+    """The same comparison with every tape compiled to its own kernel (KC_JIT=1 policy)."""
+    call("kc_debug_set_tuning", b"jit", 1)
+    try:
+        graph, embeds = random_graph(2000 + seed, n_ops=8 + seed)
+        og, lg = evaluate_both(tex_pro, graph, embeds)
+        for nid, n, s, want, got in each_slot(og, lg, graph):
+            for c in range(len(want)):
+                assert bits_equal(got[c], want[c]), (describe(graph, nid), n.node_type, s, c)
+    finally:
+        call("kc_debug_set_tuning", b"jit", 0)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_graph_that_may_not_evaluate(tex_pro, seed):
+    """Connections checked against the static slot types only: Gray data behind an Rgba
+    slot, Rgba into HeightToNormal, SpecificSlot naming an empty slot ...  Where the
+    reference's evaluation fails, this one has to fail as well (no made-up pixels); where
+    it succeeds, every slot matches bit for bit."""
+    graph, embeds = random_graph(4000 + seed, n_ops=6 + seed % 17, typed=False)
+    og = oracle.from_node_graph(graph)
+    for eid, planes in embeds.items():
+        og.embed(eid, planes)
+    try:
+        og.eval()
+    except oracle.OracleError:
+        lg = tex_pro.new_live_graph()
+        lg.set_node_graph(graph)
+        for eid, planes in embeds.items():
+            lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tex_pro, planes)), eid)
+        with pytest.raises(kc.TexProError):
+            for n in graph.nodes:
+                kc.LiveGraph.await_clean_read(lg, n.node_id)
+        return
+    og, lg = evaluate_both(tex_pro, graph, embeds)
+    for nid, n, s, want, got in each_slot(og, lg, graph):
+        assert len(got) == len(want), (describe(graph, nid), n.node_type, s)
+        for c in range(len(want)):
+            assert bits_equal(got[c], want[c]), (describe(graph, nid), n.node_type, s, c)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_graph_fast_tracks_the_oracle(tex_pro_fast, seed):
+    """FAST mode through whole graphs.  The per-operator tolerance (1e-5 rel / 1e-6 abs,
+    test_gpu_ops.py) cannot hold sample for sample across a chain: one Subtract that
+    cancels followed by a Divide amplifies a 4e-7 difference without bound.  What a
+    planner mistake in the FAST instantiations would look like is a gross error over
+    whole planes, so the check is: at least 99% of every plane's finite samples are
+    within 100x the per-operator tolerance, relative to the larger of the sample and the
+    node's largest input magnitude.  No HeightToNormal (test_config5 bounds it)."""
+    graph, embeds = random_graph(3000 + seed, n_ops=6 + seed, h2n=False)
+    og, lg = evaluate_both(tex_pro_fast, graph, embeds)
+    mags = {}
+    for nid, n, s, want, got in each_slot(og, lg, graph):
+        fin = [np.abs(p[np.isfinite(p)]) for p in want]
+        mags[(nid, s)] = max([float(f.max()) for f in fin if f.size] or [0.0])
+    for nid, n, s, want, got in each_slot(og, lg, graph):
+        scale = max([mags.get((int(e.output_id), int(e.output_slot)), 0.0) for e in graph.edges
+                     if int(e.input_id) == nid] or [0.0])
+        scale = min(scale, 1e30)
+        for c in range(len(want)):
+            a, b = got[c].astype(np.float64), want[c].astype(np.float64)
+            assert a.shape == b.shape
+            fin = np.isfinite(a) & np.isfinite(b)
+            err = np.abs(a[fin] - b[fin])
+            bound = 100.0 * (ABS + REL * np.maximum(np.abs(b[fin]), scale))
+            bad = int((err > bound).sum())
+            assert bad <= max(1, int(fin.sum()) // 100), (describe(graph, nid), n.node_type, s, c, bad, float(err.max()))
+            assert int((np.isfinite(a) != np.isfinite(b)).sum()) <= max(1, a.size // 100)  # inf/NaN in the same places

@@ -228,9 +228,9 @@ def test_calculate_size_policies_without_pixels():
 
     def img(w, h):
         im = kc_image()
-        # a constant image needs a context only as an owner tag; NULL is accepted for descriptors
+        # a descriptor that is only measured belongs to no context
         pl = C.c_void_p()
-        call("kc_plane_from_value", C.c_void_p(1), w, h, 0.0, C.byref(pl))
+        call("kc_plane_from_value", None, w, h, 0.0, C.byref(pl))
         im.kind = 0
         im.width, im.height = w, h
         im.planes[0] = pl
