@@ -497,8 +497,8 @@ class SlotImage:
 
     def __del__(self):
         im = getattr(self, "_im", None)
-        if im is not None and self._ctx is not None and self._ctx._h:
-            _lib.lib.kc_image_release(C.byref(im))
+        if im is not None and _lib is not None and _lib.lib is not None:
+            _lib.lib.kc_image_release(C.byref(im))   # legal after the context was closed: planes keep its bookkeeping alive
             self._im = None
 
     # constructors
@@ -721,8 +721,8 @@ class LiveGraph(_GraphView):
         self._scan_images = False   # set when the graph may have gained an Image node
 
     def close(self):
-        if getattr(self, "_h", None) and self._ctx._h:
-            _lib.lib.kc_live_graph_destroy(self._h)
+        if getattr(self, "_h", None) and _lib is not None and _lib.lib is not None:
+            _lib.lib.kc_live_graph_destroy(self._h)   # legal after the context was closed
         self._h = None
 
     def __del__(self):

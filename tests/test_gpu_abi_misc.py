@@ -142,3 +142,16 @@ def test_images_and_graphs_may_outlive_their_context():
     call("kc_image_release", C.byref(lazy))
     call("kc_image_release", C.byref(im))
     call("kc_live_graph_destroy", lg)                                          # the last handle: the context goes here
+
+
+def test_python_objects_released_after_close():
+    tp = kc.TextureProcessor.new()
+    img = kc.SlotImage.from_planes(tp, [rnd(3, 16, 16)])
+    lg = tp.new_live_graph()
+    n = lg.add_node(kc.Node.new(kc.NodeType.Value(0.5)))
+    kc.LiveGraph.await_clean_read(lg, n)
+    held = lg.slot_data(n, kc.SlotId(0)).image
+    tp.close()
+    del img, held, lg            # releases run against a closed context: no leak, no crash
+    import gc
+    gc.collect()
