@@ -235,3 +235,47 @@ def test_random_graph_fast_tracks_the_oracle(tex_pro_fast, seed):
             bad = int((err > bound).sum())
             assert bad <= max(1, int(fin.sum()) // 100), (describe(graph, nid), n.node_type, s, c, bad, float(err.max()))
             assert int((np.isfinite(a) != np.isfinite(b)).sum()) <= max(1, a.size // 100)  # inf/NaN in the same places
+
+
+def test_threads_share_one_context(tex_pro):
+    """The reference's engine evaluates live graphs on worker threads (src/engine.rs:200-307)
+    that share the TextureProcessor.  Here: eight threads, each with its own live graph on the
+    same context (ctypes drops the GIL around every call), three rounds each; every slot still
+    matches the oracle bit for bit."""
+    import threading
+    cases = [random_graph(5000 + i, n_ops=8 + i) for i in range(8)]
+    wants = []
+    for graph, embeds in cases:
+        og = oracle.from_node_graph(graph)
+        for eid, planes in embeds.items():
+            og.embed(eid, planes)
+        og.eval()
+        wants.append({(int(n.node_id), s): og.slot(int(n.node_id), s) for n in graph.nodes for s in og.slot_ids(int(n.node_id))})
+    errors = []
+
+    def work(i):
+        try:
+            graph, embeds = cases[i]
+            for _ in range(3):
+                lg = tex_pro.new_live_graph()
+                lg.use_cache = True
+                lg.set_node_graph(graph)
+                for eid, planes in embeds.items():
+                    lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tex_pro, planes)), eid)
+                for n in graph.nodes:
+                    kc.LiveGraph.await_clean_read(lg, n.node_id)
+                for (nid, s), want in wants[i].items():
+                    got = lg.slot_data(kc.NodeId(nid), SlotId(s)).image.planes()
+                    assert len(got) == len(want)
+                    for c in range(len(want)):
+                        assert bits_equal(got[c], want[c]), (i, nid, s, c)
+                lg.close()
+        except BaseException as e:  # noqa: BLE001 - reported in the main thread
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(cases))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
