@@ -158,6 +158,10 @@ int32_t kc_host_free(void* p);
  *      src/texture_processor.rs:34-56 (engine + transient-buffer queue) ------ */
 void kc_options_default(kc_options* o);
 int32_t kc_context_create(int32_t device, const kc_options* opts, kc_context** out);
+/* Waits for the streams, then frees the streams, the buffer cache and the spill buffers.  Planes,
+ * images and live graphs made from the context may be released AFTER this call (the reference's
+ * Arc-owned SlotImages outlive its Engine the same way); every other use of them fails with
+ * KC_ERR_INVALID_ARGUMENT, and `ctx` itself must not be passed to anything again. */
 int32_t kc_context_destroy(kc_context* ctx);
 int32_t kc_context_synchronize(kc_context* ctx);
 int32_t kc_context_device(const kc_context* ctx, int32_t* device);
