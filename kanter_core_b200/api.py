@@ -778,6 +778,13 @@ class LiveGraph(_GraphView):
         call("kc_live_graph_set_node", self._h, C.byref(d))
         self._scan_images |= node.node_type.kind == _lib.NODE_IMAGE
 
+    def set_mix_type(self, node_id, mix_type):  # node_mut(..).node_type = Mix(..), :369-374: the node becomes dirty
+        n = self.node(node_id)
+        if n.node_type.kind != _lib.NODE_MIX:
+            raise TexProError(5, "node %d is not a Mix node" % node_id)
+        n.node_type = NodeType.Mix(mix_type)
+        self.set_node(n)
+
     def add_input_slot_data(self, slot_data):  # :347-350
         call("kc_live_graph_add_input_slot_data", self._h, int(slot_data.node_id), int(slot_data.slot_id), C.byref(slot_data.image._im))
 
