@@ -23,13 +23,16 @@ POLICIES = [ResizePolicy.MostPixels, ResizePolicy.LeastPixels, ResizePolicy.Larg
 MIX = list(MixType)
 
 
-def random_graph(seed, n_ops, h2n=True, typed=True):
+def random_graph(seed, n_ops, h2n=True, typed=True, inputs=None, nested=True):
     """-> (NodeGraph, {embed id: planes}).  Every op node takes its inputs from earlier
     nodes, so the graph is a DAG.  With `typed` the generator tracks which outputs carry
     Gray and which Rgba data and only makes connections the operators accept at run time
     (HeightToNormal and CombineRgba read Gray, SeparateRgba reads Rgba, outputs read their
     own kind); without it only the static slot types are respected and some graphs fail
-    to evaluate - in the reference as well."""
+    to evaluate - in the reference as well.  `inputs` (a list of "gray" | "rgba") makes the
+    graph an inner one: InputGray / InputRgba nodes "i0", "i1", .. instead of Embed nodes.
+    With `nested`, some operators are Graph nodes holding such an inner graph.  The named
+    outputs and their kinds are left in `graph.fuzz_outputs`."""
     r = np.random.default_rng(seed)
     g = kc.NodeGraph.new()
     embeds = {}
@@ -43,7 +46,10 @@ def random_graph(seed, n_ops, h2n=True, typed=True):
             n.resize_filter = filt
         return g.add_node(n)
 
-    for eid in range(int(r.integers(2, 5))):
+    for k, kind in enumerate(inputs or []):
+        nt = NodeType.InputRgba("i%d" % k) if kind == "rgba" else NodeType.InputGray("i%d" % k)
+        outs.append((add(nt), 0, kind, kind))
+    for eid in range(int(r.integers(2, 5)) if inputs is None else 0):
         w, h = [z for z in SIZES if z != (1, 1)][int(r.integers(len(SIZES) - 1))]
         nplanes = 4 if r.random() < 0.5 else 1
         lo, hi = (-0.5, 1.5) if r.random() < 0.3 else (0.0, 1.0)
@@ -82,6 +88,19 @@ def random_graph(seed, n_ops, h2n=True, typed=True):
     for _ in range(n_ops):
         p = r.random()
         filt = list(ResizeFilter)[int(r.integers(len(ResizeFilter)))]
+        if nested and typed and inputs is None and r.random() < 0.12:
+            # a Graph node: inner inputs take outer sources of their kind, inner outputs become sources
+            want = ["rgba" if r.random() < 0.5 else "gray" for _ in range(int(r.integers(1, 4)))]
+            srcs = [pick(k) for k in want]
+            if all(srcs):
+                inner = random_graph(int(r.integers(1 << 30)), int(r.integers(2, 7)), h2n=h2n, inputs=want)
+                if inner.fuzz_outputs:
+                    n = add(NodeType.Graph(inner), None, filt)
+                    for k, (src, sl, _, _) in enumerate(srcs):
+                        g.connect(src, n, SlotId(sl), inner.input_slot_id_with_name("i%d" % k))
+                    for name, kind in inner.fuzz_outputs:
+                        outs.append((n, int(inner.output_slot_id_with_name(name)), kind, kind))
+                    continue
         if p < 0.55:
             src = {0: pick()}
             if r.random() < 0.9:
@@ -107,6 +126,7 @@ def random_graph(seed, n_ops, h2n=True, typed=True):
             n, kinds = build(NodeType.HeightToNormal, filt, {0: one}) if one else (None, None)
             if kinds:
                 outs.append((n, 0, "rgba", "rgba"))
+    g.fuzz_outputs = []
     for k in range(int(r.integers(1, 4))):
         rgba = r.random() < 0.5
         one = pick("rgba" if rgba else "gray")
@@ -115,9 +135,10 @@ def random_graph(seed, n_ops, h2n=True, typed=True):
             n = add(nt)
             try:
                 g.connect(one[0], n, SlotId(one[1]), SlotId(0))
+                g.fuzz_outputs.append(("o%d" % k, "rgba" if rgba else "gray"))
             except kc.TexProError:
                 assert not typed
-    return g, embeds
+    return (g, embeds) if inputs is None else g
 
 
 def evaluate_both(tp, graph, embeds, use_cache=True):

@@ -44,6 +44,12 @@ def data_kinds(lg, embeds):
             elif k == 11:
                 for s in range(4):
                     kinds[(nid, s)] = "gray"
+            elif k == 4:     # a nested graph: one output slot per inner Output node, typed by it
+                inner = n.node_type.payload
+                for m in inner.nodes:
+                    if m.node_type.kind in (2, 3):
+                        slot = int(inner.output_slot_id_with_name(m.node_type.payload))
+                        kinds[(nid, slot)] = "gray" if m.node_type.kind == 2 else "rgba"
             else:
                 kinds[(nid, -1)] = "sink"      # outputs: nothing reads them
         assert len(later) < len(todo), "cycle"
@@ -62,8 +68,10 @@ def descendants(edges, nid):
     return out
 
 
-def static_type(lg, nid):
+def static_type(lg, nid, slot, kinds):
     k = lg.node(nid).node_type.kind
+    if k == 4:
+        return kinds[(nid, slot)]
     return {6: "rgba", 8: "gray", 9: "any", 10: "rgba", 11: "gray", 12: "rgba"}.get(k)
 
 
@@ -137,7 +145,7 @@ def test_edits_keep_every_requested_slot_exact(tex_pro, seed):
             need_static = "gray" if lg.node(e.input_id).node_type.kind == 12 else None
             below = descendants(edges, e.input_id)
             pool = [(nid, s) for (nid, s), k in kinds.items()
-                    if k == want and nid not in below and (need_static is None or static_type(lg, nid) in ("gray", "any"))]
+                    if k == want and nid not in below and (need_static is None or static_type(lg, nid, s, kinds) in ("gray", "any"))]
             if not pool:
                 continue
             src = pool[int(r.integers(len(pool)))]
