@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <new>
+#include <stdexcept>
 #include <vector>
 
 #include "kc_internal.h"
@@ -71,7 +73,7 @@ struct Header {
     int samples_per_px() const { return color == 0 ? 1 : color == 2 ? 3 : color == 3 ? 1 : color == 4 ? 2 : 4; }
 };
 
-int32_t decode(const uint8_t* data, size_t n, std::vector<uint8_t>& out, uint32_t& W, uint32_t& H, uint32_t& CH) {
+int32_t decode_impl(const uint8_t* data, size_t n, std::vector<uint8_t>& out, uint32_t& W, uint32_t& H, uint32_t& CH) {
     if (n < 8 || memcmp(data, kSig, 8) != 0) KC_FAIL(KC_ERR_IMAGE, "not a PNG file");
     Header hd;
     bool have_hdr = false, have_trns = false;
@@ -122,6 +124,9 @@ int32_t decode(const uint8_t* data, size_t n, std::vector<uint8_t>& out, uint32_
             const size_t ph = (hd.h > (uint32_t)ay[i]) ? (hd.h - ay[i] + ady[i] - 1) / ady[i] : 0;
             if (pw && ph) total += ph * (stride_of(pw) + 1);
         }
+    // deflate expands by at most 1032:1, so a header that promises more pixels than the IDAT
+    // bytes could ever inflate to is rejected before anything of that size is allocated
+    if (total > idat.size() * 1032 + 1024) KC_FAIL(KC_ERR_IMAGE, "PNG header promises more data than its IDAT chunks can hold");
     std::vector<uint8_t> raw(total);
     uLongf got = (uLongf)total;
     if (uncompress(raw.data(), &got, idat.data(), (uLong)idat.size()) != Z_OK || got != total) KC_FAIL(KC_ERR_IMAGE, "PNG data does not inflate to the image size");
@@ -218,6 +223,17 @@ void chunk(std::vector<uint8_t>& f, const char* type, const uint8_t* body, size_
     f.insert(f.end(), type, type + 4);
     if (len) f.insert(f.end(), body, body + len);
     put32(f, (uint32_t)crc32(0, &f[at], (uInt)(4 + len)));
+}
+
+// files come from outside: running out of memory on one is an error code, not an exception through the C ABI
+int32_t decode(const uint8_t* data, size_t n, std::vector<uint8_t>& out, uint32_t& W, uint32_t& H, uint32_t& CH) {
+    try {
+        return decode_impl(data, n, out, W, H, CH);
+    } catch (const std::bad_alloc&) {
+        KC_FAIL(KC_ERR_IMAGE, "out of memory while decoding a PNG");
+    } catch (const std::length_error&) {
+        KC_FAIL(KC_ERR_IMAGE, "PNG too large to decode");
+    }
 }
 
 // RGBA8 (or any `ch` bytes per pixel) -> PNG; filter per scanline by the minimum-sum-of-

@@ -138,6 +138,15 @@ def test_rejects_what_the_reference_cannot_take(tmp_path):
     assert e.value.kind == "Io"
 
 
+def test_header_that_promises_terabytes_is_rejected_before_allocating():
+    good = bytearray(enc(np.zeros((3, 3, 4), np.uint8)))
+    good[16:24] = struct.pack(">II", 1 << 30, 1 << 30)                      # IHDR width, height
+    good[29:33] = struct.pack(">I", zlib.crc32(bytes(good[12:29])) & 0xffffffff)  # keep the IHDR checksum valid
+    with pytest.raises(TexProError) as e:
+        dec_mem(bytes(good))
+    assert e.value.kind == "Image"
+
+
 def test_encode_file(tmp_path):
     a = np.random.default_rng(4).integers(0, 256, (12, 10, 4), dtype=np.uint8)
     path = str(tmp_path / "out.png")
