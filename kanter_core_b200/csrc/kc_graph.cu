@@ -259,6 +259,7 @@ namespace {
 struct JVal {
     enum T { NUL, BOOL, NUM, STR, ARR, OBJ } t = NUL;
     double num = 0;
+    bool is_int = false;   // the token had no fraction and no exponent (serde takes u32 fields only from those)
     bool b = false;
     std::string str;
     std::vector<JVal> arr;
@@ -274,6 +275,7 @@ struct JParser {
     const char* p;
     const char* end;
     bool ok = true;
+    int depth = 0;         // serde_json refuses documents nested deeper than 128
     void ws() { while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
     bool lit(const char* s) {
         size_t n = strlen(s);
@@ -282,12 +284,47 @@ struct JParser {
     }
     JVal parse() {
         JVal v;
+        if (++depth > 128) ok = false;
+        if (ok) parse_into(v);
+        --depth;
+        return v;
+    }
+    // -?(0|[1-9][0-9]*)(.[0-9]+)?([eE][+-]?[0-9]+)? and nothing strtod would take beyond that (inf, nan, hex, +1, .5)
+    bool number(JVal& v) {
+        const char* q = p;
+        if (q < end && *q == '-') ++q;
+        if (q >= end || *q < '0' || *q > '9') return false;
+        if (*q == '0') ++q;
+        else while (q < end && *q >= '0' && *q <= '9') ++q;
+        bool integral = true;
+        if (q < end && *q == '.') {
+            integral = false;
+            ++q;
+            if (q >= end || *q < '0' || *q > '9') return false;
+            while (q < end && *q >= '0' && *q <= '9') ++q;
+        }
+        if (q < end && (*q == 'e' || *q == 'E')) {
+            integral = false;
+            ++q;
+            if (q < end && (*q == '+' || *q == '-')) ++q;
+            if (q >= end || *q < '0' || *q > '9') return false;
+            while (q < end && *q >= '0' && *q <= '9') ++q;
+        }
+        const std::string tok(p, q);
+        v.t = JVal::NUM;
+        v.num = strtod(tok.c_str(), nullptr);
+        v.is_int = integral;
+        if (!std::isfinite(v.num)) return false;   // serde_json: "number out of range"
+        p = q;
+        return true;
+    }
+    void parse_into(JVal& v) {
         ws();
-        if (p >= end) { ok = false; return v; }
+        if (p >= end) { ok = false; return; }
         if (*p == '{') {
             v.t = JVal::OBJ;
             ++p; ws();
-            if (p < end && *p == '}') { ++p; return v; }
+            if (p < end && *p == '}') { ++p; return; }
             while (ok) {
                 ws();
                 JVal k = parse_string();
@@ -304,7 +341,7 @@ struct JParser {
         } else if (*p == '[') {
             v.t = JVal::ARR;
             ++p; ws();
-            if (p < end && *p == ']') { ++p; return v; }
+            if (p < end && *p == ']') { ++p; return; }
             while (ok) {
                 v.arr.push_back(parse());
                 ws();
@@ -317,14 +354,7 @@ struct JParser {
         } else if (lit("true")) { v.t = JVal::BOOL; v.b = true; }
         else if (lit("false")) { v.t = JVal::BOOL; v.b = false; }
         else if (lit("null")) { v.t = JVal::NUL; }
-        else {
-            char* e = nullptr;
-            v.t = JVal::NUM;
-            v.num = strtod(p, &e);
-            if (e == p) ok = false;
-            p = e;
-        }
-        return v;
+        else if (!number(v)) ok = false;
     }
     JVal parse_string() {
         JVal v;
@@ -376,14 +406,21 @@ int index_of(const char* const* names, int n, const std::string& s) {
 
 int32_t graph_from_jval(const JVal& root, kc_graph& g);
 
+// a u32 field: serde takes it only from a non-negative integer token that fits
+bool to_u32(const JVal* j, uint32_t& out) {
+    if (!j || j->t != JVal::NUM || !j->is_int || j->num < 0.0 || j->num > 4294967295.0) return false;
+    out = (uint32_t)j->num;
+    return true;
+}
+
 int32_t node_from_jval(const JVal& j, KcNode& n) {
     if (j.t != JVal::OBJ) KC_FAIL(KC_ERR_IO, "json: node is not an object");
     const JVal* id = j.get("node_id");
     const JVal* ty = j.get("node_type");
     const JVal* pol = j.get("resize_policy");
     const JVal* fil = j.get("resize_filter");
-    if (!id || id->t != JVal::NUM || !ty || !pol || !fil) KC_FAIL(KC_ERR_IO, "json: node is missing a field");
-    n.node_id = (uint32_t)id->num;
+    if (!id || !ty || !pol || !fil) KC_FAIL(KC_ERR_IO, "json: node is missing a field");
+    if (!to_u32(id, n.node_id)) KC_FAIL(KC_ERR_IO, "json: node_id is not a u32");
     // node_type: "Variant" for unit variants, {"Variant": payload} otherwise
     std::string variant;
     const JVal* payload = nullptr;
@@ -405,8 +442,7 @@ int32_t node_from_jval(const JVal& j, KcNode& n) {
             break;
         }
         case KC_NODE_EMBED:
-            if (!payload || payload->t != JVal::NUM) KC_FAIL(KC_ERR_IO, "json: Embed needs an id");
-            n.embed_id = (uint32_t)payload->num;
+            if (!to_u32(payload, n.embed_id)) KC_FAIL(KC_ERR_IO, "json: Embed needs an id (u32)");
             break;
         case KC_NODE_VALUE:
             if (!payload || payload->t != JVal::NUM) KC_FAIL(KC_ERR_IO, "json: Value needs a number");
@@ -425,13 +461,10 @@ int32_t node_from_jval(const JVal& j, KcNode& n) {
     } else if (pol->t == JVal::OBJ && pol->obj.size() == 1) {
         const std::string& k = pol->obj[0].first;
         const JVal& v = pol->obj[0].second;
-        if (k == "SpecificSlot" && v.t == JVal::NUM) {
+        if (k == "SpecificSlot" && to_u32(&v, n.policy_slot)) {
             n.policy = KC_POLICY_SPECIFIC_SLOT;
-            n.policy_slot = (uint32_t)v.num;
-        } else if (k == "SpecificSize" && v.t == JVal::OBJ && v.get("width") && v.get("height")) {
+        } else if (k == "SpecificSize" && v.t == JVal::OBJ && to_u32(v.get("width"), n.policy_w) && to_u32(v.get("height"), n.policy_h)) {
             n.policy = KC_POLICY_SPECIFIC_SIZE;
-            n.policy_w = (uint32_t)v.get("width")->num;
-            n.policy_h = (uint32_t)v.get("height")->num;
         } else KC_FAIL(KC_ERR_IO, "json: bad resize_policy");
     } else KC_FAIL(KC_ERR_IO, "json: bad resize_policy");
     if (fil->t != JVal::STR) KC_FAIL(KC_ERR_IO, "json: bad resize_filter");
@@ -453,9 +486,11 @@ int32_t graph_from_jval(const JVal& root, kc_graph& g) {
         g.nodes.push_back(std::move(n));
     }
     for (const JVal& j : edges->arr) {
-        const JVal *a = j.get("output_id"), *b = j.get("input_id"), *c = j.get("output_slot"), *d = j.get("input_slot");
-        if (!a || !b || !c || !d) KC_FAIL(KC_ERR_IO, "json: edge is missing a field");
-        g.edges.push_back(kc_edge{(uint32_t)a->num, (uint32_t)b->num, (uint32_t)c->num, (uint32_t)d->num});
+        kc_edge e{};
+        if (j.t != JVal::OBJ || !to_u32(j.get("output_id"), e.output_id) || !to_u32(j.get("input_id"), e.input_id) ||
+            !to_u32(j.get("output_slot"), e.output_slot) || !to_u32(j.get("input_slot"), e.input_slot))
+            KC_FAIL(KC_ERR_IO, "json: an edge needs output_id, input_id, output_slot, input_slot (u32)");
+        g.edges.push_back(e);
     }
     // NodeGraph::from_path, :36-43: the id counter restarts after the largest id
     uint32_t mx = 0;

@@ -207,6 +207,20 @@ def test_json_errors():
         NodeGraph.from_json('{"nodes":[{"node_id":1,"node_type":"Bogus","resize_policy":"MostPixels","resize_filter":"Triangle"}],"edges":[]}')
     with pytest.raises(TexProError):
         NodeGraph.from_path("/nonexistent/graph.json")
+    # what serde_json refuses is refused here: numbers outside f64, tokens that are not JSON numbers,
+    # u32 fields that are negative / fractional / too large, nesting deeper than 128
+    node = '{"node_id":%s,"node_type":{"Value":%s},"resize_policy":"MostPixels","resize_filter":"Triangle"}'
+    doc = '{"nodes":[' + node + '],"edges":[%s]}'
+    assert len(NodeGraph.from_json(doc % ("7", "0.5", "")).nodes) == 1
+    for nid, val, edge in (("7", "1e999", ""), ("7", "inf", ""), ("7", "+1", ""), ("7", ".5", ""), ("7", "0x10", ""),
+                           ("-1", "0.5", ""), ("1.5", "0.5", ""), ("4294967296", "0.5", ""), ('"7"', "0.5", ""),
+                           ("7", "0.5", '{"output_id":7,"input_id":"x","output_slot":0,"input_slot":0}'),
+                           ("7", "0.5", "7")):
+        with pytest.raises(TexProError) as e:
+            NodeGraph.from_json(doc % (nid, val, edge))
+        assert e.value.kind == "Io", (nid, val, edge)
+    with pytest.raises(TexProError):
+        NodeGraph.from_json("[" * 100000)
 
 
 def test_set_mix_type_and_clone_independence():
