@@ -238,6 +238,10 @@ def ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    # the tape became hot during these steps and its specialised kernel is being compiled in the
+    # background (no stall in a caller's loop): the warm-up ends when that kernel is in use
+    kc.jit_wait()
+    step_resident()
     tp.synchronize()
     stats = lg.last_run_stats()
     # the timed region is milliseconds long: keep the GPU under the very same load for about
@@ -322,6 +326,8 @@ def ours(args, rank, world, local_rank):
 
     e2e_steps = max(1, min(args.steps, 20))
     run_e2e(3)
+    kc.jit_wait()        # the fused RGBA8-export tape of this path, same as above
+    run_e2e(2)
     barrier()
     tp.synchronize()
     stamps = []

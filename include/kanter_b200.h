@@ -192,6 +192,10 @@ int32_t kc_debug_jit_compile(const uint32_t* instr, uint32_t n_instr, int32_t ex
 /* (tile float4s per thread, resident CTAs per SM, pipeline stages) of the last fused elementwise launch; V < 0: the
  * specialised kernel ran */
 int32_t kc_debug_last_tile_config(int32_t* v, int32_t* ctas, int32_t* stages);
+/* Under the automatic policy a hot tape is compiled on a background thread while the interpreter keeps serving it
+ * (no stall in the caller's loop; KC_JIT_SYNC=1 compiles in the launching thread instead).  This waits until no
+ * compile is running, at most timeout_ms; *still_running = compiles left.  Benchmarks call it to end their warm-up. */
+int32_t kc_debug_jit_wait(int32_t timeout_ms, int32_t* still_running);
 /* ---- spill queue: TransientBufferQueue, src/transient_buffer.rs:250-411 + TextureProcessor::memory_threshold,
  *      src/texture_processor.rs:19.  Above `bytes` of live planes in HBM the least recently used ones move to
  *      pinned host memory (the reference writes them to disk) and come back when something reads them.

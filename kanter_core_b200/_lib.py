@@ -97,6 +97,7 @@ SIGNATURES = {
     "kc_debug_set_tuning": (i32, [C.c_char_p, i32]),
     "kc_debug_last_tile_config": (i32, [P(i32), P(i32), P(i32)]),
     "kc_debug_jit_compile": (i32, [P(u32), u32, i32, i32, i32, P(sz)]),
+    "kc_debug_jit_wait": (i32, [i32, P(i32)]),
     "kc_context_set_timing": (i32, [vp, i32]),
     "kc_context_timing_read": (i32, [vp, i32, P(C.c_double), P(u64)]),
     "kc_event_create": (i32, [P(vp)]),

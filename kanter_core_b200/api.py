@@ -618,6 +618,15 @@ class _Context:
             self._h = None
 
 
+def jit_wait(timeout_ms=60000):
+    """Hot tapes are compiled in the background (kc_jit.cu); wait until no compile is running.
+    Returns the number still running.  Benchmarks call it at the end of their warm-up, then
+    run one more untimed step so the finished kernel is loaded before anything is timed."""
+    n = C.c_int32()
+    call("kc_debug_jit_wait", int(timeout_ms), C.byref(n))
+    return n.value
+
+
 def _is_png(path):
     try:
         with open(path, "rb") as f:

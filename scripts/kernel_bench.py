@@ -38,6 +38,8 @@ class Timer:
     def run(self, fn, reps, warm=3):
         for _ in range(warm):
             fn()
+        kc.jit_wait()          # a hot tape is compiled in the background: measure the kernel that serves it from then on
+        fn()
         self.tp.synchronize()
         ms, n = C.c_double(), C.c_uint64()
         call("kc_context_set_timing", self.ctx, 1)

@@ -22,6 +22,7 @@ from kanter_core_b200._lib import call, kc_image  # noqa: E402
 def main():
     tp = kc.TextureProcessor.new(math_mode=kc.MATH_FAST)
     ctx = tp._ctx._h
+    call("kc_debug_set_tuning", b"jit", -1)     # this sweep is about the interpreter kernel's configurations
     S = 4096
     r = np.random.default_rng(5)
     planes = [kc.SlotImage.from_planes(tp, [r.random((S, S), dtype=np.float32)]) for _ in range(8)]

@@ -86,3 +86,36 @@ def test_fast_mode_within_tolerance(tex_pro_fast, jit_always):
         want = oracle.mix_plane(4, oracle.mix_plane(2, A[c], B[c]), B[c]).astype(np.float64)
         assert (np.abs(got[c].astype(np.float64) - want) <= 1e-6 + 1e-5 * np.abs(want)).all()
     assert _specialised_kernel_ran()
+
+
+def test_automatic_policy_compiles_in_the_background(tex_pro_fast):
+    """A tape that keeps coming back on a large plane is compiled on a background thread: the
+    launches meanwhile are served by the interpreter (no stall), the specialised kernel takes
+    over once it is ready, and both give the same pixels."""
+    import time
+    tp = tex_pro_fast
+    s = 1024
+    r = np.random.default_rng(11)
+    planes = [r.random((s, s), dtype=np.float32) + np.float32(0.25) for _ in range(3)]
+    imgs = [kc.SlotImage.from_planes(tp, [p]) for p in planes]
+
+    def evaluate():
+        # a tape no other test uses: ((a * b) / c - a) * c  -- five ops, 1 Mpx
+        x = kc.mix(tp, MixType.Multiply, imgs[0], imgs[1])
+        x = kc.mix(tp, MixType.Divide, x, imgs[2])
+        x = kc.mix(tp, MixType.Subtract, x, imgs[0])
+        x = kc.mix(tp, MixType.Multiply, x, imgs[2])
+        return x.planes()[0]
+
+    t0 = time.perf_counter()
+    first = [evaluate() for _ in range(3)]                 # the third sighting starts the compile
+    stall = time.perf_counter() - t0
+    assert not _specialised_kernel_ran()                   # ... and is still served by the interpreter
+    assert stall < 0.5, "the launching thread waited for NVRTC (%.2f s)" % stall
+    assert kc.jit_wait(60000) == 0
+    after = evaluate()
+    assert _specialised_kernel_ran()
+    want = ((planes[0] * planes[1]) / planes[2] - planes[0]) * planes[2]
+    for got in first + [after]:
+        assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+    assert np.array_equal(first[0], after)                 # no pow in this tape: FAST == EXACT arithmetic, same bits
