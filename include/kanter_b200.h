@@ -21,6 +21,8 @@
  *    back to the host synchronise that stream, nothing else does.
  *  - there is no CPU fallback: without a usable sm_100 device
  *    kc_context_create fails with KC_ERR_CUDA.
+ *  - nothing unwinds through this boundary: a C++ exception inside the library
+ *    (host memory running out included) comes back as KC_ERR_GENERIC.
  */
 #ifndef KANTER_B200_H
 #define KANTER_B200_H

@@ -28,6 +28,12 @@ void kc_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int32_t kc_fail_exception(const char* what) {
+    if (what) kc_set_error("internal error: %s", what);
+    else kc_set_error("out of host memory");
+    return KC_ERR_GENERIC;
+}
+
 extern "C" const char* kc_last_error(void) { return g_err; }
 extern "C" int32_t kc_abi_version(void) { return KC_ABI_VERSION; }
 extern "C" void kc_free(void* p) { free(p); }
@@ -62,15 +68,15 @@ extern "C" const char* kc_error_string(int32_t code) {
     }
 }
 
-extern "C" int32_t kc_host_alloc(size_t bytes, void** out) {
+extern "C" int32_t kc_host_alloc(size_t bytes, void** out) try {
     if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "kc_host_alloc: out is NULL");
     KC_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
     return KC_OK;
-}
-extern "C" int32_t kc_host_free(void* p) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_host_free(void* p) try {
     if (p) KC_CUDA(cudaFreeHost(p));
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 // ---------------------------------------------------------------------------
 // context
@@ -82,7 +88,7 @@ extern "C" void kc_options_default(kc_options* o) {
     o->fuse = 1;
 }
 
-extern "C" int32_t kc_context_create(int32_t device, const kc_options* opts, kc_context** out) {
+extern "C" int32_t kc_context_create(int32_t device, const kc_options* opts, kc_context** out) try {
     if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "kc_context_create: out is NULL");
     *out = nullptr;
     int n = 0;
@@ -117,7 +123,7 @@ extern "C" int32_t kc_context_create(int32_t device, const kc_options* opts, kc_
     cudaSetDevice(prev);
     *out = ctx;
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 static void axis_table_free(KcAxisTable& t) {
     if (t.d_left) cudaFree(t.d_left);
@@ -131,7 +137,7 @@ static void axis_table_free(KcAxisTable& t) {
     t.d_weights = nullptr;
 }
 
-extern "C" int32_t kc_context_destroy(kc_context* ctx) {
+extern "C" int32_t kc_context_destroy(kc_context* ctx) try {
     if (!ctx) return KC_OK;
     if (ctx->closed) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "the context was destroyed already");
     {
@@ -159,9 +165,9 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) {
     }
     kc_ctx_unref(ctx);   // planes and live graphs still alive keep the bookkeeping until they are released
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_context_synchronize(kc_context* ctx) {
+extern "C" int32_t kc_context_synchronize(kc_context* ctx) try {
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     KcGuard g(ctx);
     // uploads are waited for by `stream` (event), downloads are not
@@ -169,40 +175,40 @@ extern "C" int32_t kc_context_synchronize(kc_context* ctx) {
     KC_CUDA(cudaStreamSynchronize(ctx->download_stream));
     ctx->dl_pending = false;
     return KC_OK;
-}
-extern "C" int32_t kc_context_device(const kc_context* ctx, int32_t* device) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_device(const kc_context* ctx, int32_t* device) try {
     if (!ctx || !device) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *device = ctx->device;
     return KC_OK;
-}
-extern "C" int32_t kc_context_stream(const kc_context* ctx, void** stream) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_stream(const kc_context* ctx, void** stream) try {
     if (!ctx || !stream) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *stream = (void*)ctx->stream;
     return KC_OK;
-}
-extern "C" int32_t kc_context_set_math_mode(kc_context* ctx, int32_t mode) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_set_math_mode(kc_context* ctx, int32_t mode) try {
     if (!ctx || (mode != KC_MATH_EXACT && mode != KC_MATH_FAST)) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad math mode");
     ctx->opts.math_mode = mode;
     return KC_OK;
-}
-extern "C" int32_t kc_context_set_fuse(kc_context* ctx, int32_t fuse) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_set_fuse(kc_context* ctx, int32_t fuse) try {
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     ctx->opts.fuse = fuse ? 1 : 0;
     return KC_OK;
-}
-extern "C" int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_launches, uint64_t* bytes_live) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_launches, uint64_t* bytes_live) try {
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     if (kernel_launches) *kernel_launches = ctx->kernel_launches;
     if (bytes_live) *bytes_live = ctx->bytes_live;
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 // ---------------------------------------------------------------------------
 // device buffers.  All work of a context is ordered on ONE stream, so a buffer
 // released by the host may be handed out again immediately: whatever still reads
 // it was enqueued earlier on that stream than whatever will write it next.
 // ---------------------------------------------------------------------------
-int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out) {
+int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out) try {
     if (ctx->closed) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "the context was destroyed");
     auto it = ctx->free_lists.find(bytes);
     if (it != ctx->free_lists.end() && !it->second.empty()) {
@@ -219,7 +225,7 @@ int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out) {
     }
     if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "cudaMallocAsync(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 void kc_dev_free(kc_context* ctx, void* p, size_t bytes) {
     if (!p) return;
@@ -335,7 +341,7 @@ static int32_t spill_one(kc_context* ctx, kc_plane* p) {
     ctx->planes_on_host++;
     return KC_OK;
 }
-int32_t kc_enforce_threshold(kc_context* ctx) {
+int32_t kc_enforce_threshold(kc_context* ctx) try {
     while (ctx->bytes_live > ctx->memory_threshold) {
         kc_plane* victim = nullptr;
         for (kc_plane* q : ctx->resident)
@@ -344,7 +350,7 @@ int32_t kc_enforce_threshold(kc_context* ctx) {
         KC_TRY(spill_one(ctx, victim));
     }
     return KC_OK;
-}
+} KC_ABI_CATCH
 int32_t kcp_reload(kc_context* ctx, kc_plane* p) {
     if (p->kind != KC_PLANE_SPILLED) return KC_OK;
     const size_t bytes = plane_alloc_bytes(p);
@@ -389,26 +395,26 @@ int32_t kcp_reload(kc_context* ctx, kc_plane* p) {
     return KC_OK;
 }
 
-extern "C" int32_t kc_context_set_memory_threshold(kc_context* ctx, uint64_t bytes) {
+extern "C" int32_t kc_context_set_memory_threshold(kc_context* ctx, uint64_t bytes) try {
     // TextureProcessor::memory_threshold, src/texture_processor.rs:19; 0 = no limit
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     KcGuard g(ctx);
     ctx->memory_threshold = bytes ? bytes : UINT64_MAX;
     return kc_enforce_threshold(ctx);
-}
-extern "C" int32_t kc_context_spill_stats(const kc_context* ctx, uint64_t* bytes_spilled, uint64_t* spills, uint64_t* reloads) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_spill_stats(const kc_context* ctx, uint64_t* bytes_spilled, uint64_t* spills, uint64_t* reloads) try {
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     if (bytes_spilled) *bytes_spilled = ctx->bytes_spilled;
     if (spills) *spills = ctx->n_spills;
     if (reloads) *reloads = ctx->n_reloads;
     return KC_OK;
-}
-extern "C" int32_t kc_plane_in_memory(const kc_plane* p, int32_t* in_memory) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_plane_in_memory(const kc_plane* p, int32_t* in_memory) try {
     // TransientBufferContainer::in_memory: constants and lazy planes hold no pixels, so they count as resident
     if (!p || !in_memory) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *in_memory = p->kind != KC_PLANE_SPILLED;
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 kc_plane* kcp_new_const(kc_context* ctx, uint32_t w, uint32_t h, float v) {
     auto* p = kcp_alloc(ctx);
@@ -480,20 +486,20 @@ void kci_release(kc_image* im) {
     }
 }
 
-extern "C" int32_t kc_plane_create(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out) {
+extern "C" int32_t kc_plane_create(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out) try {
     if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
     return kcp_new_device(ctx, w, h, out);
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_plane_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, kc_plane** out) {
+extern "C" int32_t kc_plane_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, kc_plane** out) try {
     // ctx may be NULL: a descriptor that is only measured (kc_plane_size, kc_calculate_size) needs no device
     if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = kcp_new_const(ctx, w, h, v);
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_plane_from_host(kc_context* ctx, uint32_t w, uint32_t h, const float* host, kc_plane** out) {
+extern "C" int32_t kc_plane_from_host(kc_context* ctx, uint32_t w, uint32_t h, const float* host, kc_plane** out) try {
     if (!ctx || !out || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
     kc_plane* p = nullptr;
@@ -515,9 +521,9 @@ extern "C" int32_t kc_plane_from_host(kc_context* ctx, uint32_t w, uint32_t h, c
     ctx->bytes_h2d += p->bytes();
     *out = p;
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_plane_from_host_deferred(kc_context* ctx, uint32_t w, uint32_t h, const float* host, kc_plane** out) {
+extern "C" int32_t kc_plane_from_host_deferred(kc_context* ctx, uint32_t w, uint32_t h, const float* host, kc_plane** out) try {
     // The pixels stay in the caller's (pinned) memory until something reads the plane; a plane nobody
     // reads -- the alpha of an image that only goes through Mix, say -- never crosses PCIe.  `host` must
     // stay valid and unchanged until the context has been synchronised after the plane's last use.
@@ -532,16 +538,16 @@ extern "C" int32_t kc_plane_from_host_deferred(kc_context* ctx, uint32_t w, uint
     ctx->planes_on_host++;
     *out = p;
     return KC_OK;
-}
-extern "C" int32_t kc_context_transfer_stats(const kc_context* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_transfer_stats(const kc_context* ctx, uint64_t* h2d_bytes, uint64_t* d2h_bytes) try {
     // bytes copied host->device (plane uploads, u8 samples) and device->host (plane / RGBA8 downloads) so far
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     if (h2d_bytes) *h2d_bytes = ctx->bytes_h2d;
     if (d2h_bytes) *d2h_bytes = ctx->bytes_d2h;
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_plane_wrap_device(kc_context* ctx, uint32_t w, uint32_t h, void* device_ptr, kc_plane** out) {
+extern "C" int32_t kc_plane_wrap_device(kc_context* ctx, uint32_t w, uint32_t h, void* device_ptr, kc_plane** out) try {
     if (!ctx || !out || !device_ptr) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (((uintptr_t)device_ptr & 15) != 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "device pointer must be 16-byte aligned");
     auto* p = kcp_alloc(ctx);
@@ -552,41 +558,41 @@ extern "C" int32_t kc_plane_wrap_device(kc_context* ctx, uint32_t w, uint32_t h,
     p->owned = false;
     *out = p;
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_plane_retain(kc_plane* p) {
+extern "C" int32_t kc_plane_retain(kc_plane* p) try {
     if (!p) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane is NULL");
     kcp_retain(p);
     return KC_OK;
-}
-extern "C" int32_t kc_plane_release(kc_plane* p) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_plane_release(kc_plane* p) try {
     if (!p) return KC_OK;
     kc_context* ctx = p->ctx;
     KcGuard g(ctx);
     kcp_release(p);
     return KC_OK;
-}
-extern "C" int32_t kc_plane_size(const kc_plane* p, uint32_t* w, uint32_t* h) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_plane_size(const kc_plane* p, uint32_t* w, uint32_t* h) try {
     if (!p) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane is NULL");
     if (w) *w = p->w;
     if (h) *h = p->h;
     return KC_OK;
-}
-extern "C" int32_t kc_plane_is_constant(const kc_plane* p, int32_t* is_const, float* value) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_plane_is_constant(const kc_plane* p, int32_t* is_const, float* value) try {
     if (!p) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane is NULL");
     if (is_const) *is_const = p->kind == KC_PLANE_CONST;
     if (value) *value = p->kind == KC_PLANE_CONST ? p->value : 0.0f;
     return KC_OK;
-}
-extern "C" int32_t kc_plane_device_ptr(kc_plane* p, void** device_ptr) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_plane_device_ptr(kc_plane* p, void** device_ptr) try {
     if (!p || !device_ptr) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(p->ctx);
     KC_TRY(kcp_force(p->ctx, &p, 1));
     ++p->pins;   // a raw pointer has left the library: this plane is never spilled again
     *device_ptr = p->dptr;
     return KC_OK;
-}
-extern "C" int32_t kc_plane_upload(kc_plane* p, const float* host) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_plane_upload(kc_plane* p, const float* host) try {
     if (!p || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (p->kind != KC_PLANE_DEVICE && p->kind != KC_PLANE_SPILLED) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "plane has no device storage");
     KcGuard g(p->ctx);
@@ -594,8 +600,8 @@ extern "C" int32_t kc_plane_upload(kc_plane* p, const float* host) {
     kcp_touch(p);
     KC_CUDA(cudaMemcpyAsync(p->dptr, host, p->bytes(), cudaMemcpyHostToDevice, p->ctx->stream));
     return KC_OK;
-}
-extern "C" int32_t kc_plane_download(kc_plane* p, float* host) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_plane_download(kc_plane* p, float* host) try {
     if (!p || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (p->kind == KC_PLANE_CONST) {  // a descriptor: fill on the host, no device work
         size_t n = p->count();
@@ -608,13 +614,13 @@ extern "C" int32_t kc_plane_download(kc_plane* p, float* host) {
     KC_CUDA(cudaStreamSynchronize(p->ctx->stream));
     p->ctx->bytes_d2h += p->bytes();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 // ---------------------------------------------------------------------------
 // images
 // ---------------------------------------------------------------------------
 extern "C" int32_t kc_image_from_u8(kc_context* ctx, const uint8_t* samples, uint32_t w, uint32_t h,
-                                    uint32_t channels, kc_image* out) {
+                                    uint32_t channels, kc_image* out) try {
     // deconstruct_image, src/shared.rs:16-56: u8/255 per sample, channels dealt
     // round-robin, absent colour planes 0.0, absent alpha 1.0.  read_slot_image
     // (:218-261) always ends up with four planes, i.e. an Rgba image.
@@ -650,10 +656,10 @@ extern "C" int32_t kc_image_from_u8(kc_context* ctx, const uint8_t* samples, uin
         return rc;
     }
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 extern "C" int32_t kc_image_from_host_planes(kc_context* ctx, int32_t kind, uint32_t w, uint32_t h,
-                                             const float* const* planes, kc_image* out) {
+                                             const float* const* planes, kc_image* out) try {
     if (!ctx || !planes || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     kci_clear(out);
     out->kind = kind == KC_IMAGE_RGBA ? KC_IMAGE_RGBA : KC_IMAGE_GRAY;
@@ -668,10 +674,10 @@ extern "C" int32_t kc_image_from_host_planes(kc_context* ctx, int32_t kind, uint
         }
     }
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 extern "C" int32_t kc_image_from_host_planes_deferred(kc_context* ctx, int32_t kind, uint32_t w, uint32_t h,
-                                                      const float* const* planes, kc_image* out) {
+                                                      const float* const* planes, kc_image* out) try {
     if (!ctx || !planes || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     kci_clear(out);
     out->kind = kind == KC_IMAGE_RGBA ? KC_IMAGE_RGBA : KC_IMAGE_GRAY;
@@ -686,9 +692,9 @@ extern "C" int32_t kc_image_from_host_planes_deferred(kc_context* ctx, int32_t k
         }
     }
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_image_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, int32_t rgba, kc_image* out) {
+extern "C" int32_t kc_image_from_value(kc_context* ctx, uint32_t w, uint32_t h, float v, int32_t rgba, kc_image* out) try {
     // SlotImage::from_value, src/slot_image.rs:28-64: alpha is 1.0 whatever v is
     if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     kci_clear(out);
@@ -703,14 +709,14 @@ extern "C" int32_t kc_image_from_value(kc_context* ctx, uint32_t w, uint32_t h, 
         out->planes[0] = kcp_new_const(ctx, w, h, v);
     }
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_image_retain(const kc_image* img) {
+extern "C" int32_t kc_image_retain(const kc_image* img) try {
     if (!img) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "image is NULL");
     kci_retain(img);
     return KC_OK;
-}
-extern "C" int32_t kc_image_release(kc_image* img) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_image_release(kc_image* img) try {
     if (!img) return KC_OK;
     kc_context* ctx = nullptr;
     for (int c = 0; c < 4; ++c)
@@ -719,9 +725,9 @@ extern "C" int32_t kc_image_release(kc_image* img) {
     KcGuard g(ctx);
     kci_release(img);
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_image_download(kc_context* ctx, const kc_image* in, float* const* host_planes) {
+extern "C" int32_t kc_image_download(kc_context* ctx, const kc_image* in, float* const* host_planes) try {
     if (!ctx || !in || !host_planes) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     for (int c = 0; c < kci_nplanes(in); ++c)
         if (!in->planes[c] || !host_planes[c]) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "image has no plane %d (released?) or no destination for it", c);
@@ -744,9 +750,9 @@ extern "C" int32_t kc_image_download(kc_context* ctx, const kc_image* in, float*
     }
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_image_materialize(kc_context* ctx, const kc_image* in, int32_t include_constants) {
+extern "C" int32_t kc_image_materialize(kc_context* ctx, const kc_image* in, int32_t include_constants) try {
     // make the image's planes real pixels in HBM with one fused launch (lazy
     // expression planes always; constant descriptors only on request)
     if (!ctx || !in) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -759,14 +765,14 @@ extern "C" int32_t kc_image_materialize(kc_context* ctx, const kc_image* in, int
         if (want && std::find(roots.begin(), roots.end(), p) == roots.end()) roots.push_back(p);
     }
     return roots.empty() ? KC_OK : kcp_force(ctx, roots.data(), roots.size());
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, int32_t srgb, void* device_rgba8) {
+extern "C" int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, int32_t srgb, void* device_rgba8) try {
     if (!ctx || !in || !device_rgba8) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (((uintptr_t)device_rgba8 & 15) != 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "device pointer must be 16-byte aligned");
     KcGuard g(ctx);
     return kcp_export_rgba8(ctx, in, srgb, (uint32_t*)device_rgba8);
-}
+} KC_ABI_CATCH
 
 // RGBA8 export: the conversion kernel runs on `stream` into a device buffer the context keeps,
 // the copy to the host runs on the download stream.  The buffer is rewritten only after the
@@ -801,7 +807,7 @@ static int32_t to_u8_enqueue(kc_context* ctx, const kc_image* in, int32_t srgb, 
     return KC_OK;
 }
 
-extern "C" int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) {
+extern "C" int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) try {
     // SlotImage::to_u8 / to_u8_srgb, src/slot_image.rs:142-207
     if (!ctx || !in || !host_rgba8) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
@@ -809,63 +815,63 @@ extern "C" int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t s
     cudaError_t e = cudaEventSynchronize(ctx->ev_dl_done);
     if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_image_to_u8_async(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) {
+extern "C" int32_t kc_image_to_u8_async(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) try {
     if (!ctx || !in || !host_rgba8) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
     return to_u8_enqueue(ctx, in, srgb, host_rgba8);
-}
+} KC_ABI_CATCH
 
 // ---------------------------------------------------------------------------
 // device-side timing on the context's stream (what bench.py uses: CUDA events
 // recorded on the stream the kernels are launched on)
 // ---------------------------------------------------------------------------
-extern "C" int32_t kc_event_create(void** out) {
+extern "C" int32_t kc_event_create(void** out) try {
     if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "out is NULL");
     cudaEvent_t e;
     KC_CUDA(cudaEventCreate(&e));
     *out = (void*)e;
     return KC_OK;
-}
-extern "C" int32_t kc_event_destroy(void* ev) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_event_destroy(void* ev) try {
     if (ev) KC_CUDA(cudaEventDestroy((cudaEvent_t)ev));
     return KC_OK;
-}
-extern "C" int32_t kc_event_record(kc_context* ctx, void* ev) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_event_record(kc_context* ctx, void* ev) try {
     if (!ctx || !ev) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
     KC_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->stream));
     return KC_OK;
-}
-extern "C" int32_t kc_event_record_download(kc_context* ctx, void* ev) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_event_record_download(kc_context* ctx, void* ev) try {
     // completes when every RGBA8 download enqueued so far (kc_image_to_u8_async) has landed
     if (!ctx || !ev) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
     KC_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->download_stream));
     return KC_OK;
-}
-extern "C" int32_t kc_event_synchronize(void* ev) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_event_synchronize(void* ev) try {
     if (!ev) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_CUDA(cudaEventSynchronize((cudaEvent_t)ev));
     return KC_OK;
-}
-extern "C" int32_t kc_event_elapsed_ms(void* start, void* stop, float* ms) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_event_elapsed_ms(void* start, void* stop, float* ms) try {
     if (!start || !stop || !ms) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
     KC_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 // per-launch kernel timing: every kernel this library launches on the context is
 // bracketed by two events on the context's stream while timing is on
-extern "C" int32_t kc_context_set_timing(kc_context* ctx, int32_t on) {
+extern "C" int32_t kc_context_set_timing(kc_context* ctx, int32_t on) try {
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     KcGuard g(ctx);
     ctx->timing = on != 0;
     return KC_OK;
-}
-extern "C" int32_t kc_context_timing_read(kc_context* ctx, int32_t kind, double* total_ms, uint64_t* launches) {
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_timing_read(kc_context* ctx, int32_t kind, double* total_ms, uint64_t* launches) try {
     // waits for the stream, sums the launches of `kind` (-1: all kinds) recorded so far and forgets them
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     KcGuard g(ctx);
@@ -886,7 +892,7 @@ extern "C" int32_t kc_context_timing_read(kc_context* ctx, int32_t kind, double*
     if (total_ms) *total_ms = sum;
     if (launches) *launches = n;
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 static int env_int(const char* name) {
     const char* v = getenv(name);
@@ -904,7 +910,7 @@ static KcTuning tuning_from_env() {
 }
 KcTuning g_kc_tuning = tuning_from_env();
 
-extern "C" int32_t kc_debug_set_tuning(const char* key, int32_t value) {
+extern "C" int32_t kc_debug_set_tuning(const char* key, int32_t value) try {
     if (!key) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "key is NULL");
     const std::string k(key);
     if (k == "tile_v") g_kc_tuning.tile_v = value;
@@ -915,12 +921,12 @@ extern "C" int32_t kc_debug_set_tuning(const char* key, int32_t value) {
     else if (k == "jit") g_kc_tuning.jit = value;
     else KC_FAIL(KC_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-extern "C" int32_t kc_context_trim(kc_context* ctx) {
+extern "C" int32_t kc_context_trim(kc_context* ctx) try {
     // hand the recycled device buffers back to the driver's pool
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     KcGuard g(ctx);
     kc_dev_trim(ctx);
     return KC_OK;
-}
+} KC_ABI_CATCH

@@ -744,7 +744,7 @@ int32_t check_image(const kc_image* im, const char* what) {
 // ---------------------------------------------------------------------------
 extern "C" {
 
-int32_t kc_image_as_type(kc_context* ctx, const kc_image* in, int32_t rgba, kc_image* out) {
+int32_t kc_image_as_type(kc_context* ctx, const kc_image* in, int32_t rgba, kc_image* out) try {
     if (!ctx || !in || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(check_image(in, "as_type"));
     KcGuard g(ctx);
@@ -752,9 +752,9 @@ int32_t kc_image_as_type(kc_context* ctx, const kc_image* in, int32_t rgba, kc_i
     KC_TRY(img_as_type(ctx, borrow(in), rgba != 0, res));
     *out = res.release();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-int32_t kc_mix(kc_context* ctx, int32_t mix_type, const kc_image* left, const kc_image* right, kc_image* out) {
+int32_t kc_mix(kc_context* ctx, int32_t mix_type, const kc_image* left, const kc_image* right, kc_image* out) try {
     if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(check_image(left, "mix left"));
     KC_TRY(check_image(right, "mix right"));
@@ -763,9 +763,9 @@ int32_t kc_mix(kc_context* ctx, int32_t mix_type, const kc_image* left, const kc
     KC_TRY(img_mix(ctx, mix_type, left ? &l : nullptr, right ? &r : nullptr, res));
     *out = res.release();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-int32_t kc_height_to_normal(kc_context* ctx, const kc_image* in, kc_image* out) {
+int32_t kc_height_to_normal(kc_context* ctx, const kc_image* in, kc_image* out) try {
     if (!ctx || !in || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(check_image(in, "height_to_normal"));
     KcGuard g(ctx);
@@ -773,9 +773,9 @@ int32_t kc_height_to_normal(kc_context* ctx, const kc_image* in, kc_image* out) 
     KC_TRY(img_h2n(ctx, borrow(in), res));
     *out = res.release();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-int32_t kc_height_to_normal_strip(kc_context* ctx, const kc_image* strip, kc_plane* halo_row, uint32_t full_height, kc_image* out) {
+int32_t kc_height_to_normal_strip(kc_context* ctx, const kc_image* strip, kc_plane* halo_row, uint32_t full_height, kc_image* out) try {
     if (!ctx || !strip || !halo_row || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(check_image(strip, "height_to_normal_strip"));
     if (full_height < strip->planes[0]->h) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "full height smaller than the strip");
@@ -784,10 +784,10 @@ int32_t kc_height_to_normal_strip(kc_context* ctx, const kc_image* strip, kc_pla
     KC_TRY(img_h2n(ctx, borrow(strip), res, halo_row, full_height));
     *out = res.release();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 int32_t kc_height_to_normal_strip_peer(kc_context* ctx, const kc_image* strip, const kc_halo_link* inbox, uint64_t step,
-                                       uint32_t full_height, kc_image* out) {
+                                       uint32_t full_height, kc_image* out) try {
     // as kc_height_to_normal_strip, with the halo row read by the kernel itself from the mailbox
     // of the GPU above (kc_halo_*): no copy of the row, no host synchronisation
     if (!ctx || !strip || !inbox || !out || step == 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad argument");
@@ -798,9 +798,9 @@ int32_t kc_height_to_normal_strip_peer(kc_context* ctx, const kc_image* strip, c
     KC_TRY(img_h2n(ctx, borrow(strip), res, nullptr, full_height, inbox, step));
     *out = res.release();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-int32_t kc_plane_copy_rows(kc_context* ctx, kc_plane* dst, uint32_t dst_row, kc_plane* src, uint32_t src_row, uint32_t rows) {
+int32_t kc_plane_copy_rows(kc_context* ctx, kc_plane* dst, uint32_t dst_row, kc_plane* src, uint32_t src_row, uint32_t rows) try {
     if (!ctx || !dst || !src) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (dst->kind != KC_PLANE_DEVICE && dst->kind != KC_PLANE_SPILLED) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "destination has no device storage");
     if (dst->w != src->w || dst_row + rows > dst->h || src_row + rows > src->h) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "row range out of bounds");
@@ -814,9 +814,9 @@ int32_t kc_plane_copy_rows(kc_context* ctx, kc_plane* dst, uint32_t dst_row, kc_
     KC_CUDA(cudaMemcpyAsync(dst->dptr + (size_t)dst_row * dst->w, src->dptr + (size_t)src_row * src->w,
                             sizeof(float) * (size_t)rows * src->w, cudaMemcpyDefault, ctx->stream));
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-int32_t kc_resize(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, int32_t filter, kc_image* out) {
+int32_t kc_resize(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, int32_t filter, kc_image* out) try {
     if (!ctx || !in || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(check_image(in, "resize"));
     KcGuard g(ctx);
@@ -824,10 +824,10 @@ int32_t kc_resize(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, i
     KC_TRY(img_resize(ctx, borrow(in), w, h, filter, res));
     *out = res.release();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 int32_t kc_resize_rows(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t h, int32_t filter, uint32_t row_begin,
-                       uint32_t row_count, kc_image* out) {
+                       uint32_t row_count, kc_image* out) try {
     // the strip [row_begin, row_begin + row_count) of kc_resize(in, w, h): what one GPU of a
     // row-sharded resize computes; bit-identical to those rows of the whole result
     if (!ctx || !in || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -837,9 +837,9 @@ int32_t kc_resize_rows(kc_context* ctx, const kc_image* in, uint32_t w, uint32_t
     KC_TRY(img_resize(ctx, borrow(in), w, h, filter, res, row_begin, row_count));
     *out = res.release();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-int32_t kc_separate_rgba(kc_context* ctx, const kc_image* in, kc_image out[4]) {
+int32_t kc_separate_rgba(kc_context* ctx, const kc_image* in, kc_image out[4]) try {
     if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(check_image(in, "separate_rgba"));
     KcGuard g(ctx);
@@ -850,9 +850,9 @@ int32_t kc_separate_rgba(kc_context* ctx, const kc_image* in, kc_image out[4]) {
         out[c] = im.release();
     }
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-int32_t kc_combine_rgba(kc_context* ctx, const kc_image* const channels[4], kc_image* out) {
+int32_t kc_combine_rgba(kc_context* ctx, const kc_image* const channels[4], kc_image* out) try {
     if (!ctx || !channels || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard g(ctx);
     KcNode node;
@@ -876,11 +876,11 @@ int32_t kc_combine_rgba(kc_context* ctx, const kc_image* const channels[4], kc_i
     KC_TRY(process_node(ctx, node, in, edges, none, no_inputs, nullptr, res));
     *out = res[0].image.release();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 int32_t kc_calculate_size(const kc_slot_data* slot_datas, size_t n_slot_datas, const kc_edge* edges, size_t n_edges,
                           int32_t policy, uint32_t policy_slot, uint32_t policy_w, uint32_t policy_h, uint32_t* out_w,
-                          uint32_t* out_h) {
+                          uint32_t* out_h) try {
     if (!out_w || !out_h || (n_slot_datas && !slot_datas) || (n_edges && !edges)) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     std::vector<Slot> sd;
     for (size_t i = 0; i < n_slot_datas; ++i) {
@@ -898,12 +898,12 @@ int32_t kc_calculate_size(const kc_slot_data* slot_datas, size_t n_slot_datas, c
     *out_w = s.w;
     *out_h = s.h;
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 int32_t kc_process_node(kc_context* ctx, const kc_node_desc* node, const kc_slot_data* slot_datas, size_t n_slot_datas,
                         const kc_embedded_slot_data* embedded, size_t n_embedded, const kc_slot_data* input_slot_datas,
                         size_t n_input_slot_datas, const kc_edge* edges, size_t n_edges, kc_slot_data* out, size_t out_cap,
-                        size_t* n_out) {
+                        size_t* n_out) try {
     if (!ctx || !node || !n_out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (n_slot_datas != n_edges) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "edges.len() != slot_datas.len()");  // assert_eq!, node_type.rs:221-226
     KcGuard g(ctx);
@@ -934,20 +934,20 @@ int32_t kc_process_node(kc_context* ctx, const kc_node_desc* node, const kc_slot
         out[i].image = res[i].image.release();
     }
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 // ---------------------------------------------------------------------------
 // C ABI: LiveGraph
 // ---------------------------------------------------------------------------
-int32_t kc_live_graph_create(kc_context* ctx, kc_live_graph** out) {
+int32_t kc_live_graph_create(kc_context* ctx, kc_live_graph** out) try {
     if (!ctx || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     auto* lg = new kc_live_graph();
     lg->ctx = ctx;
     kc_ctx_ref(ctx);
     *out = lg;
     return KC_OK;
-}
-int32_t kc_live_graph_destroy(kc_live_graph* lg) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_destroy(kc_live_graph* lg) try {
     if (!lg) return KC_OK;
     {
         KcGuard g(lg->ctx);
@@ -961,31 +961,31 @@ int32_t kc_live_graph_destroy(kc_live_graph* lg) {
     delete lg;
     kc_ctx_unref(ctx);
     return KC_OK;
-}
-int32_t kc_live_graph_set_node_graph(kc_live_graph* lg, const kc_graph* g) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_set_node_graph(kc_live_graph* lg, const kc_graph* g) try {
     if (!lg || !g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard guard(lg->ctx);
     lg->graph = *g;
     lg->reset_states();
     lg->slot_datas.clear();
     return KC_OK;
-}
-int32_t kc_live_graph_node_graph(const kc_live_graph* lg, const kc_graph** out) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_node_graph(const kc_live_graph* lg, const kc_graph** out) try {
     if (!lg || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = &lg->graph;
     return KC_OK;
-}
-int32_t kc_live_graph_set_use_cache(kc_live_graph* lg, int32_t v) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_set_use_cache(kc_live_graph* lg, int32_t v) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     lg->use_cache = v != 0;
     return KC_OK;
-}
-int32_t kc_live_graph_set_auto_update(kc_live_graph* lg, int32_t v) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_set_auto_update(kc_live_graph* lg, int32_t v) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     lg->auto_update = v != 0;
     return KC_OK;
-}
-int32_t kc_live_graph_add_node(kc_live_graph* lg, const kc_node_desc* node, uint32_t* out_node_id) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_add_node(kc_live_graph* lg, const kc_node_desc* node, uint32_t* out_node_id) try {
     if (!lg || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     uint32_t id = 0;
     KC_TRY(kc_graph_add_node(&lg->graph, node, &id));
@@ -993,15 +993,15 @@ int32_t kc_live_graph_add_node(kc_live_graph* lg, const kc_node_desc* node, uint
     lg->changed.insert(id);
     if (out_node_id) *out_node_id = id;
     return KC_OK;
-}
-int32_t kc_live_graph_add_node_with_id(kc_live_graph* lg, const kc_node_desc* node) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_add_node_with_id(kc_live_graph* lg, const kc_node_desc* node) try {
     if (!lg || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(kc_graph_add_node_with_id(&lg->graph, node));
     lg->state[node->node_id] = KC_STATE_DIRTY;
     lg->changed.insert(node->node_id);
     return KC_OK;
-}
-int32_t kc_live_graph_remove_node(kc_live_graph* lg, uint32_t node_id) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_remove_node(kc_live_graph* lg, uint32_t node_id) try {
     // LiveGraph::remove_node, live_graph.rs:451-475
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard guard(lg->ctx);
@@ -1013,8 +1013,8 @@ int32_t kc_live_graph_remove_node(kc_live_graph* lg, uint32_t node_id) {
     lg->changed.insert(node_id);
     for (uint32_t c : kids) { lg->changed.insert(c); lg->set_dirty(c); }
     return KC_OK;
-}
-int32_t kc_live_graph_connect(kc_live_graph* lg, uint32_t o, uint32_t i, uint32_t os, uint32_t is) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_connect(kc_live_graph* lg, uint32_t o, uint32_t i, uint32_t os, uint32_t is) try {
     // LiveGraph::connect, live_graph.rs:487-511
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard guard(lg->ctx);
@@ -1022,8 +1022,8 @@ int32_t kc_live_graph_connect(kc_live_graph* lg, uint32_t o, uint32_t i, uint32_
     lg->changed.insert(i);
     lg->set_dirty(i);
     return KC_OK;
-}
-int32_t kc_live_graph_disconnect_slot(kc_live_graph* lg, uint32_t node_id, int32_t side, uint32_t slot_id) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_disconnect_slot(kc_live_graph* lg, uint32_t node_id, int32_t side, uint32_t slot_id) try {
     // LiveGraph::disconnect_slot, live_graph.rs:577-603
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard guard(lg->ctx);
@@ -1032,16 +1032,16 @@ int32_t kc_live_graph_disconnect_slot(kc_live_graph* lg, uint32_t node_id, int32
     for (const kc_edge& e : removed) lg->set_dirty(e.input_id);
     if (side != 0) lg->changed.insert(node_id);   // Side::Output: live_graph.rs:585-589
     return KC_OK;
-}
-int32_t kc_live_graph_set_node(kc_live_graph* lg, const kc_node_desc* node) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_set_node(kc_live_graph* lg, const kc_node_desc* node) try {
     // node_mut / set_node_with_id, live_graph.rs:369-387: the node and its children become dirty
     if (!lg || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard guard(lg->ctx);
     KC_TRY(kc_graph_set_node(&lg->graph, node));
     lg->set_dirty(node->node_id);
     return KC_OK;
-}
-int32_t kc_live_graph_add_input_slot_data(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, const kc_image* image) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_add_input_slot_data(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, const kc_image* image) try {
     if (!lg || !image) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(check_image(image, "add_input_slot_data"));
     KcGuard guard(lg->ctx);
@@ -1053,16 +1053,16 @@ int32_t kc_live_graph_add_input_slot_data(kc_live_graph* lg, uint32_t node_id, u
     for (const KcNode& n : lg->graph.nodes)
         if (kcg_is_input(n.type)) lg->set_dirty(n.node_id);
     return KC_OK;
-}
-int32_t kc_live_graph_clear_input_slot_data(kc_live_graph* lg) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_clear_input_slot_data(kc_live_graph* lg) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard guard(lg->ctx);
     lg->inputs.clear();
     for (const KcNode& n : lg->graph.nodes)
         if (kcg_is_input(n.type)) lg->set_dirty(n.node_id);
     return KC_OK;
-}
-int32_t kc_live_graph_embed_slot_data_with_id(kc_live_graph* lg, const kc_image* image, uint32_t slot_id, uint32_t embed_id) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_embed_slot_data_with_id(kc_live_graph* lg, const kc_image* image, uint32_t slot_id, uint32_t embed_id) try {
     // embed_slot_data_with_id, live_graph.rs:324-341
     if (!lg || !image) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(check_image(image, "embed_slot_data_with_id"));
@@ -1075,8 +1075,8 @@ int32_t kc_live_graph_embed_slot_data_with_id(kc_live_graph* lg, const kc_image*
     kci_retain(&e.image);
     lg->embeds.push_back(e);
     return KC_OK;
-}
-int32_t kc_live_graph_replace_embedded(kc_live_graph* lg, const kc_image* image, uint32_t embed_id) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_replace_embedded(kc_live_graph* lg, const kc_image* image, uint32_t embed_id) try {
     if (!lg || !image) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(check_image(image, "replace_embedded"));
     KcGuard guard(lg->ctx);
@@ -1090,9 +1090,9 @@ int32_t kc_live_graph_replace_embedded(kc_live_graph* lg, const kc_image* image,
             return KC_OK;
         }
     KC_FAIL(KC_ERR_INVALID_SLOT_ID, "no embedded slot data with id %u", embed_id);
-}
+} KC_ABI_CATCH
 int32_t kc_live_graph_set_image_data_u8(kc_live_graph* lg, uint32_t node_id, const uint8_t* samples, uint32_t w, uint32_t h,
-                                        uint32_t channels) {
+                                        uint32_t channels) try {
     if (!lg || !samples) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (channels < 1 || channels > 4) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "channels must be 1..4");
     KcGuard guard(lg->ctx);
@@ -1107,7 +1107,7 @@ int32_t kc_live_graph_set_image_data_u8(kc_live_graph* lg, uint32_t node_id, con
     px.have_upload = false;
     lg->set_dirty(node_id);
     return KC_OK;
-}
+} KC_ABI_CATCH
 // ---- the rest of LiveGraph's bookkeeping surface, src/live_graph.rs ---------------------
 static int32_t copy_ids(const std::vector<uint32_t>& v, uint32_t* ids, size_t cap, size_t* n) {
     if (!n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -1116,22 +1116,22 @@ static int32_t copy_ids(const std::vector<uint32_t>& v, uint32_t* ids, size_t ca
         for (size_t i = 0; i < v.size() && i < cap; ++i) ids[i] = v[i];
     return KC_OK;
 }
-int32_t kc_live_graph_changed_consume(kc_live_graph* lg, uint32_t* ids, size_t cap, size_t* n) {
+int32_t kc_live_graph_changed_consume(kc_live_graph* lg, uint32_t* ids, size_t cap, size_t* n) try {
     // changed_consume, :156-160.  Call with ids == NULL to size the buffer (nothing is consumed then).
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     std::vector<uint32_t> v(lg->changed.begin(), lg->changed.end());
     KC_TRY(copy_ids(v, ids, cap, n));
     if (ids && cap >= v.size()) lg->changed.clear();
     return KC_OK;
-}
-int32_t kc_live_graph_node_ids_with_state(const kc_live_graph* lg, int32_t state, int32_t without, uint32_t* ids, size_t cap, size_t* n) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_node_ids_with_state(const kc_live_graph* lg, int32_t state, int32_t without, uint32_t* ids, size_t cap, size_t* n) try {
     // node_ids_with_state / node_ids_without_state, :261-277 (ascending NodeId: BTreeMap order)
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     std::vector<uint32_t> v;
     for (const auto& kv : lg->state)
         if ((kv.second == state) != (without != 0)) v.push_back(kv.first);
     return copy_ids(v, ids, cap, n);
-}
+} KC_ABI_CATCH
 static void closest_processable(const kc_live_graph* lg, uint32_t id, std::vector<uint32_t>& out) {
     std::vector<uint32_t> dirty;
     bool processing = false;
@@ -1145,7 +1145,7 @@ static void closest_processable(const kc_live_graph* lg, uint32_t id, std::vecto
     else
         for (uint32_t p : dirty) closest_processable(lg, p, out);
 }
-int32_t kc_live_graph_get_closest_processable(const kc_live_graph* lg, uint32_t node_id, uint32_t* ids, size_t cap, size_t* n) {
+int32_t kc_live_graph_get_closest_processable(const kc_live_graph* lg, uint32_t node_id, uint32_t* ids, size_t cap, size_t* n) try {
     // get_closest_processable, :279-311
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!kcg_find(lg->graph, node_id)) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
@@ -1154,8 +1154,8 @@ int32_t kc_live_graph_get_closest_processable(const kc_live_graph* lg, uint32_t 
     std::sort(v.begin(), v.end());
     v.erase(std::unique(v.begin(), v.end()), v.end());
     return copy_ids(v, ids, cap, n);
-}
-int32_t kc_live_graph_mark(kc_live_graph* lg, uint32_t node_id, int32_t state) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_mark(kc_live_graph* lg, uint32_t node_id, int32_t state) try {
     // request (:219-227): Dirty -> Requested;  prioritise (:229-237): Dirty | Requested -> Prioritised.
     // Only the state changes; kc_live_graph_update does the engine's work.
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -1169,8 +1169,8 @@ int32_t kc_live_graph_mark(kc_live_graph* lg, uint32_t node_id, int32_t state) {
         KC_FAIL(KC_ERR_INVALID_ARGUMENT, "only Requested and Prioritised can be marked");
     }
     return KC_OK;
-}
-int32_t kc_live_graph_update(kc_live_graph* lg, size_t* n_processed) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_update(kc_live_graph* lg, size_t* n_processed) try {
     // one turn of the engine's loop for this graph (src/engine.rs:128-183): with auto_update every
     // node that is not Clean is wanted, otherwise the Requested and Prioritised ones; they and
     // their dirty ancestors are evaluated
@@ -1183,54 +1183,54 @@ int32_t kc_live_graph_update(kc_live_graph* lg, size_t* n_processed) {
     if (n_processed) *n_processed = want.size();
     if (want.empty()) return KC_OK;
     return lg->evaluate(want.data(), want.size(), true);
-}
-int32_t kc_live_graph_remove_edge(kc_live_graph* lg, const kc_edge* e) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_remove_edge(kc_live_graph* lg, const kc_edge* e) try {
     // remove_edge, :551-566: the input node and everything downstream become dirty and lose their data
     if (!lg || !e) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcGuard guard(lg->ctx);
     KC_TRY(kc_graph_remove_edge(&lg->graph, e));
     lg->set_dirty(e->input_id);
     return KC_OK;
-}
-int32_t kc_live_graph_rename_output_node(kc_live_graph* lg, uint32_t node_id, const char* new_name, char** old_name) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_rename_output_node(kc_live_graph* lg, uint32_t node_id, const char* new_name, char** old_name) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     return kc_graph_rename_output_node(&lg->graph, node_id, new_name, old_name);   // :625-627
-}
-int32_t kc_live_graph_new_id(kc_live_graph* lg, uint32_t* out) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_new_id(kc_live_graph* lg, uint32_t* out) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     return kc_graph_new_id(&lg->graph, out);   // :422-424
-}
+} KC_ABI_CATCH
 
-int32_t kc_live_graph_request(kc_live_graph* lg, const uint32_t* node_ids, size_t n) {
+int32_t kc_live_graph_request(kc_live_graph* lg, const uint32_t* node_ids, size_t n) try {
     if (!lg || (n && !node_ids)) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     return lg->evaluate(node_ids, n, true);
-}
-int32_t kc_live_graph_await_clean(kc_live_graph* lg, uint32_t node_id) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_await_clean(kc_live_graph* lg, uint32_t node_id) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KC_TRY(lg->evaluate(&node_id, 1, true));
     return kc_context_synchronize(lg->ctx);
-}
-int32_t kc_live_graph_cancel(kc_live_graph* lg) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_cancel(kc_live_graph* lg) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     lg->ctx->cancel.store(true);
     return KC_OK;
-}
-int32_t kc_live_graph_node_state(const kc_live_graph* lg, uint32_t node_id, int32_t* state) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_node_state(const kc_live_graph* lg, uint32_t node_id, int32_t* state) try {
     if (!lg || !state) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     auto it = lg->state.find(node_id);
     if (it == lg->state.end()) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
     *state = it->second;
     return KC_OK;
-}
-int32_t kc_live_graph_slot_data(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, kc_image* out) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_slot_data(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, kc_image* out) try {
     if (!lg || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const Slot* s = lg->find_slot(node_id, slot_id);
     if (!s) KC_FAIL(KC_ERR_NO_SLOT_DATA, "Could not find a `SlotData` for node %u slot %u", node_id, slot_id);
     *out = s->image.im;
     kci_retain(out);
     return KC_OK;
-}
-int32_t kc_live_graph_slot_in_memory(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t* in_memory) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_slot_in_memory(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t* in_memory) try {
     // LiveGraph::slot_in_memory, src/live_graph.rs:410-412 -> SlotImage::in_memory: every plane resident
     if (!lg || !in_memory) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const Slot* s = lg->find_slot(node_id, slot_id);
@@ -1239,16 +1239,16 @@ int32_t kc_live_graph_slot_in_memory(const kc_live_graph* lg, uint32_t node_id, 
     for (int c = 0; c < kci_nplanes(&s->image.im); ++c) all &= s->image.im.planes[c]->kind != KC_PLANE_SPILLED;
     *in_memory = all;
     return KC_OK;
-}
-int32_t kc_live_graph_slot_data_size(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint32_t* w, uint32_t* h) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_slot_data_size(const kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint32_t* w, uint32_t* h) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const Slot* s = lg->find_slot(node_id, slot_id);
     if (!s) KC_FAIL(KC_ERR_NO_SLOT_DATA, "Could not find a `SlotData` for node %u slot %u", node_id, slot_id);
     if (w) *w = s->image.w();
     if (h) *h = s->image.h();
     return KC_OK;
-}
-int32_t kc_live_graph_node_slot_ids(const kc_live_graph* lg, uint32_t node_id, uint32_t* slot_ids, size_t cap, size_t* n) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_node_slot_ids(const kc_live_graph* lg, uint32_t node_id, uint32_t* slot_ids, size_t cap, size_t* n) try {
     if (!lg || !n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     size_t c = 0;
     for (const Slot& s : lg->slot_datas)
@@ -1258,7 +1258,7 @@ int32_t kc_live_graph_node_slot_ids(const kc_live_graph* lg, uint32_t node_id, u
         }
     *n = c;
     return KC_OK;
-}
+} KC_ABI_CATCH
 static int32_t buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int srgb, uint8_t* host, size_t cap, bool wait = true) {
     if (!lg || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const Slot* s = lg->find_slot(node_id, slot_id);
@@ -1267,12 +1267,12 @@ static int32_t buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id
     if (cap < need) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "buffer of %zu bytes is too small for %zu", cap, need);
     return wait ? kc_image_to_u8(lg->ctx, &s->image.im, srgb, host) : kc_image_to_u8_async(lg->ctx, &s->image.im, srgb, host);
 }
-int32_t kc_live_graph_buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host, size_t cap) {
+int32_t kc_live_graph_buffer_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host, size_t cap) try {
     return buffer_rgba(lg, node_id, slot_id, 0, host, cap);
-}
-int32_t kc_live_graph_buffer_srgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host, size_t cap) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_buffer_srgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, uint8_t* host, size_t cap) try {
     return buffer_rgba(lg, node_id, slot_id, 1, host, cap);
-}
+} KC_ABI_CATCH
 static int32_t read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap, bool wait) {
     if (!lg || !host) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const uint64_t k0 = lg->ctx->run_kernels, g0 = lg->ctx->run_groups, b0 = lg->ctx->run_bytes;
@@ -1283,18 +1283,18 @@ static int32_t read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, 
     lg->last_bytes = lg->ctx->run_bytes - b0;
     return rc;
 }
-int32_t kc_live_graph_read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap) {
+int32_t kc_live_graph_read_rgba(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap) try {
     return read_rgba(lg, node_id, slot_id, srgb, host, cap, true);
-}
-int32_t kc_live_graph_read_rgba_async(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_read_rgba_async(kc_live_graph* lg, uint32_t node_id, uint32_t slot_id, int32_t srgb, uint8_t* host, size_t cap) try {
     return read_rgba(lg, node_id, slot_id, srgb, host, cap, false);
-}
-int32_t kc_live_graph_last_run_stats(const kc_live_graph* lg, uint64_t* kernels, uint64_t* fused_groups, uint64_t* algorithmic_bytes) {
+} KC_ABI_CATCH
+int32_t kc_live_graph_last_run_stats(const kc_live_graph* lg, uint64_t* kernels, uint64_t* fused_groups, uint64_t* algorithmic_bytes) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (kernels) *kernels = lg->last_kernels;
     if (fused_groups) *fused_groups = lg->last_groups;
     if (algorithmic_bytes) *algorithmic_bytes = lg->last_bytes;
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 }  // extern "C"

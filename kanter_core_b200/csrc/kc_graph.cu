@@ -628,71 +628,71 @@ std::string kcg_to_json(const kc_graph& g) {
 // ---------------------------------------------------------------------------
 extern "C" {
 
-int32_t kc_graph_create(kc_graph** out) {
+int32_t kc_graph_create(kc_graph** out) try {
     if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "out is NULL");
     *out = new kc_graph();
     return KC_OK;
-}
-int32_t kc_graph_destroy(kc_graph* g) {
+} KC_ABI_CATCH
+int32_t kc_graph_destroy(kc_graph* g) try {
     delete g;
     return KC_OK;
-}
-int32_t kc_graph_clone(const kc_graph* g, kc_graph** out) {
+} KC_ABI_CATCH
+int32_t kc_graph_clone(const kc_graph* g, kc_graph** out) try {
     if (!g || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = new kc_graph(*g);
     return KC_OK;
-}
-int32_t kc_graph_from_json(const char* text, kc_graph** out) {
+} KC_ABI_CATCH
+int32_t kc_graph_from_json(const char* text, kc_graph** out) try {
     if (!text || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     auto g = std::make_unique<kc_graph>();
     KC_TRY(kcg_parse_json(text, *g));
     *out = g.release();
     return KC_OK;
-}
-int32_t kc_graph_from_path(const char* path, kc_graph** out) {
+} KC_ABI_CATCH
+int32_t kc_graph_from_path(const char* path, kc_graph** out) try {
     if (!path || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     std::ifstream f(path, std::ios::binary);
     if (!f) KC_FAIL(KC_ERR_IO, "cannot open '%s'", path);
     std::stringstream ss;
     ss << f.rdbuf();
     return kc_graph_from_json(ss.str().c_str(), out);
-}
-int32_t kc_graph_export_json(const kc_graph* g, char** out_text) {
+} KC_ABI_CATCH
+int32_t kc_graph_export_json(const kc_graph* g, char** out_text) try {
     if (!g || !out_text) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     std::string s = kcg_to_json(*g);
     *out_text = (char*)malloc(s.size() + 1);
     if (!*out_text) KC_FAIL(KC_ERR_GENERIC, "out of memory");
     memcpy(*out_text, s.c_str(), s.size() + 1);
     return KC_OK;
-}
-int32_t kc_graph_export_json_path(const kc_graph* g, const char* path) {
+} KC_ABI_CATCH
+int32_t kc_graph_export_json_path(const kc_graph* g, const char* path) try {
     if (!g || !path) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     std::ofstream f(path, std::ios::binary);
     if (!f) KC_FAIL(KC_ERR_IO, "cannot create '%s'", path);
     f << kcg_to_json(*g);
     return f.good() ? KC_OK : KC_ERR_IO;
-}
-int32_t kc_graph_add_node(kc_graph* g, const kc_node_desc* node, uint32_t* out_node_id) {
+} KC_ABI_CATCH
+int32_t kc_graph_add_node(kc_graph* g, const kc_node_desc* node, uint32_t* out_node_id) try {
     if (!g || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcNode n;
     kcg_from_desc(*node, n);
     return kcg_add_node(*g, std::move(n), out_node_id);
-}
-int32_t kc_graph_add_node_with_id(kc_graph* g, const kc_node_desc* node) {
+} KC_ABI_CATCH
+int32_t kc_graph_add_node_with_id(kc_graph* g, const kc_node_desc* node) try {
     if (!g || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcNode n;
     kcg_from_desc(*node, n);
     return kcg_add_node_with_id(*g, std::move(n));
-}
-int32_t kc_graph_remove_node(kc_graph* g, uint32_t node_id) {
+} KC_ABI_CATCH
+int32_t kc_graph_remove_node(kc_graph* g, uint32_t node_id) try {
     if (!g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     return kcg_remove_node(*g, node_id, nullptr);
-}
-int32_t kc_graph_connect(kc_graph* g, uint32_t o, uint32_t i, uint32_t os, uint32_t is) {
+} KC_ABI_CATCH
+int32_t kc_graph_connect(kc_graph* g, uint32_t o, uint32_t i, uint32_t os, uint32_t is) try {
     if (!g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     return kcg_connect(*g, o, i, os, is);
-}
-int32_t kc_graph_try_connect(kc_graph* g, uint32_t o, uint32_t i, uint32_t os, uint32_t is) {
+} KC_ABI_CATCH
+int32_t kc_graph_try_connect(kc_graph* g, uint32_t o, uint32_t i, uint32_t os, uint32_t is) try {
     // NodeGraph::try_connect + can_connect, :376-413 (no slot-type check there)
     if (!g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const KcNode* on = kcg_find(*g, o);
@@ -705,8 +705,8 @@ int32_t kc_graph_try_connect(kc_graph* g, uint32_t o, uint32_t i, uint32_t os, u
         if (e.input_id == i && e.input_slot == is) KC_FAIL(KC_ERR_SLOT_OCCUPIED, "slot %u of node %u is occupied", is, i);
     g->edges.push_back(kc_edge{o, i, os, is});
     return KC_OK;
-}
-int32_t kc_graph_can_connect(const kc_graph* g, uint32_t o, uint32_t i, uint32_t os, uint32_t is) {
+} KC_ABI_CATCH
+int32_t kc_graph_can_connect(const kc_graph* g, uint32_t o, uint32_t i, uint32_t os, uint32_t is) try {
     // NodeGraph::can_connect, src/node_graph.rs:376-393
     if (!g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const KcNode* on = kcg_find(*g, o);
@@ -718,8 +718,8 @@ int32_t kc_graph_can_connect(const kc_graph* g, uint32_t o, uint32_t i, uint32_t
     for (const kc_edge& e : g->edges)
         if (e.input_id == i && e.input_slot == is) KC_FAIL(KC_ERR_SLOT_OCCUPIED, "slot %u of node %u is occupied", is, i);
     return KC_OK;
-}
-int32_t kc_graph_connected_edges(const kc_graph* g, uint32_t node_id, int32_t side, uint32_t slot_id, kc_edge* edges, size_t cap, size_t* n) {
+} KC_ABI_CATCH
+int32_t kc_graph_connected_edges(const kc_graph* g, uint32_t node_id, int32_t side, uint32_t slot_id, kc_edge* edges, size_t cap, size_t* n) try {
     // NodeGraph::connected_edges, src/node_graph.rs:518-537 (side 0 = Input, 1 = Output)
     if (!g || !n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!kcg_find(*g, node_id)) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
@@ -733,14 +733,14 @@ int32_t kc_graph_connected_edges(const kc_graph* g, uint32_t node_id, int32_t si
     *n = k;
     if (k == 0) KC_FAIL(KC_ERR_SLOT_NOT_OCCUPIED, "slot %u of node %u has no edges", slot_id, node_id);
     return KC_OK;
-}
-int32_t kc_graph_new_id(kc_graph* g, uint32_t* out) {
+} KC_ABI_CATCH
+int32_t kc_graph_new_id(kc_graph* g, uint32_t* out) try {
     // NodeGraph::new_id, src/node_graph.rs:86-96
     if (!g || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = new_id(*g);
     return KC_OK;
-}
-int32_t kc_graph_rename_output_node(kc_graph* g, uint32_t node_id, const char* new_name, char** old_name) {
+} KC_ABI_CATCH
+int32_t kc_graph_rename_output_node(kc_graph* g, uint32_t node_id, const char* new_name, char** old_name) try {
     // NodeGraph::rename_output_node, src/node_graph.rs:232-270: the new name is de-collided
     // against the OTHER output names; returns the old name (kc_free it)
     if (!g || !new_name) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -762,12 +762,12 @@ int32_t kc_graph_rename_output_node(kc_graph* g, uint32_t node_id, const char* n
         memcpy(*old_name, old.c_str(), old.size() + 1);
     }
     return KC_OK;
-}
-int32_t kc_graph_disconnect_slot(kc_graph* g, uint32_t node_id, int32_t side, uint32_t slot_id) {
+} KC_ABI_CATCH
+int32_t kc_graph_disconnect_slot(kc_graph* g, uint32_t node_id, int32_t side, uint32_t slot_id) try {
     if (!g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     return kcg_disconnect_slot(*g, node_id, side, slot_id, nullptr);
-}
-int32_t kc_graph_remove_edge(kc_graph* g, const kc_edge* e) {
+} KC_ABI_CATCH
+int32_t kc_graph_remove_edge(kc_graph* g, const kc_edge* e) try {
     if (!g || !e) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     for (size_t i = 0; i < g->edges.size(); ++i) {
         const kc_edge& c = g->edges[i];
@@ -777,26 +777,26 @@ int32_t kc_graph_remove_edge(kc_graph* g, const kc_edge* e) {
         }
     }
     KC_FAIL(KC_ERR_INVALID_EDGE, "no such edge");
-}
-int32_t kc_graph_node_count(const kc_graph* g, size_t* n) {
+} KC_ABI_CATCH
+int32_t kc_graph_node_count(const kc_graph* g, size_t* n) try {
     if (!g || !n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *n = g->nodes.size();
     return KC_OK;
-}
-int32_t kc_graph_node_at(const kc_graph* g, size_t index, kc_node_desc* out) {
+} KC_ABI_CATCH
+int32_t kc_graph_node_at(const kc_graph* g, size_t index, kc_node_desc* out) try {
     if (!g || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (index >= g->nodes.size()) KC_FAIL(KC_ERR_INVALID_NODE_ID, "node index out of range");
     kcg_to_desc(g->nodes[index], *out);
     return KC_OK;
-}
-int32_t kc_graph_node(const kc_graph* g, uint32_t node_id, kc_node_desc* out) {
+} KC_ABI_CATCH
+int32_t kc_graph_node(const kc_graph* g, uint32_t node_id, kc_node_desc* out) try {
     if (!g || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     const KcNode* n = kcg_find(*g, node_id);
     if (!n) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
     kcg_to_desc(*n, *out);
     return KC_OK;
-}
-int32_t kc_graph_set_node(kc_graph* g, const kc_node_desc* node) {
+} KC_ABI_CATCH
+int32_t kc_graph_set_node(kc_graph* g, const kc_node_desc* node) try {
     if (!g || !node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcNode* n = kcg_find(*g, node->node_id);
     if (!n) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node->node_id);
@@ -804,18 +804,18 @@ int32_t kc_graph_set_node(kc_graph* g, const kc_node_desc* node) {
     kcg_from_desc(*node, tmp);
     *n = std::move(tmp);
     return KC_OK;
-}
-int32_t kc_graph_edge_count(const kc_graph* g, size_t* n) {
+} KC_ABI_CATCH
+int32_t kc_graph_edge_count(const kc_graph* g, size_t* n) try {
     if (!g || !n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *n = g->edges.size();
     return KC_OK;
-}
-int32_t kc_graph_edge_at(const kc_graph* g, size_t index, kc_edge* out) {
+} KC_ABI_CATCH
+int32_t kc_graph_edge_at(const kc_graph* g, size_t index, kc_edge* out) try {
     if (!g || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (index >= g->edges.size()) KC_FAIL(KC_ERR_INVALID_EDGE, "edge index out of range");
     *out = g->edges[index];
     return KC_OK;
-}
+} KC_ABI_CATCH
 static int32_t slot_id_with_name(const kc_graph* g, const char* name, bool input, uint32_t* slot_id) {
     if (!g || !name || !slot_id) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     for (const KcNode& n : g->nodes)
@@ -825,12 +825,12 @@ static int32_t slot_id_with_name(const kc_graph* g, const char* name, bool input
         }
     KC_FAIL(KC_ERR_INVALID_NAME, "no %s node named '%s'", input ? "input" : "output", name);
 }
-int32_t kc_graph_input_slot_id_with_name(const kc_graph* g, const char* name, uint32_t* slot_id) {
+int32_t kc_graph_input_slot_id_with_name(const kc_graph* g, const char* name, uint32_t* slot_id) try {
     return slot_id_with_name(g, name, true, slot_id);
-}
-int32_t kc_graph_output_slot_id_with_name(const kc_graph* g, const char* name, uint32_t* slot_id) {
+} KC_ABI_CATCH
+int32_t kc_graph_output_slot_id_with_name(const kc_graph* g, const char* name, uint32_t* slot_id) try {
     return slot_id_with_name(g, name, false, slot_id);
-}
+} KC_ABI_CATCH
 static int32_t ids_of(const kc_graph* g, bool input, uint32_t* ids, size_t cap, size_t* n) {
     if (!g || !n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     size_t c = 0;
@@ -845,7 +845,7 @@ static int32_t ids_of(const kc_graph* g, bool input, uint32_t* ids, size_t cap, 
 int32_t kc_graph_output_ids(const kc_graph* g, uint32_t* ids, size_t cap, size_t* n) { return ids_of(g, false, ids, cap, n); }
 int32_t kc_graph_input_ids(const kc_graph* g, uint32_t* ids, size_t cap, size_t* n) { return ids_of(g, true, ids, cap, n); }
 
-static int32_t slots_out(const std::vector<KcSlotInfo>& v, kc_slot* slots, size_t cap, size_t* n) {
+static int32_t slots_out(const std::vector<KcSlotInfo>& v, kc_slot* slots, size_t cap, size_t* n) try {
     if (!n) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     *n = v.size();
     for (size_t i = 0; i < v.size() && i < cap && slots; ++i) {
@@ -855,18 +855,18 @@ static int32_t slots_out(const std::vector<KcSlotInfo>& v, kc_slot* slots, size_
         slots[i].slot_type = v[i].slot_type;
     }
     return KC_OK;
-}
-int32_t kc_node_input_slots(const kc_node_desc* node, kc_slot* slots, size_t cap, size_t* n) {
+} KC_ABI_CATCH
+int32_t kc_node_input_slots(const kc_node_desc* node, kc_slot* slots, size_t cap, size_t* n) try {
     if (!node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcNode k;
     kcg_from_desc(*node, k);
     return slots_out(kcg_input_slots(k), slots, cap, n);
-}
-int32_t kc_node_output_slots(const kc_node_desc* node, kc_slot* slots, size_t cap, size_t* n) {
+} KC_ABI_CATCH
+int32_t kc_node_output_slots(const kc_node_desc* node, kc_slot* slots, size_t cap, size_t* n) try {
     if (!node) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     KcNode k;
     kcg_from_desc(*node, k);
     return slots_out(kcg_output_slots(k), slots, cap, n);
-}
+} KC_ABI_CATCH
 
 }  // extern "C"

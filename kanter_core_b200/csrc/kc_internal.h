@@ -12,6 +12,8 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <new>
+#include <stdexcept>
 #include <tuple>
 #include <vector>
 
@@ -38,6 +40,14 @@ void kc_set_error(const char* fmt, ...);
         int32_t rc__ = (expr);    \
         if (rc__ != KC_OK) return rc__; \
     } while (0)
+
+// Nothing may unwind through the C ABI (the caller is Rust): every int32_t entry point is a function-try-block
+// that ends in this.  Host memory running out, or any other C++ exception, becomes KC_ERR_GENERIC.
+int32_t kc_fail_exception(const char* what);
+#define KC_ABI_CATCH                                                              \
+    catch (const std::bad_alloc&) { return kc_fail_exception(nullptr); }          \
+    catch (const std::exception& e__) { return kc_fail_exception(e__.what()); }   \
+    catch (...) { return kc_fail_exception("unknown exception"); }
 
 #include "kc_tape.h"
 

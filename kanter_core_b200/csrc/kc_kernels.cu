@@ -146,12 +146,12 @@ TvmConfig pick_config(int ns_max, int nt_max, unsigned long long n) {
 }  // namespace
 
 int g_kc_last_tile_config[3] = {0, 0, 0};
-extern "C" int32_t kc_debug_last_tile_config(int32_t* v, int32_t* ctas, int32_t* stages) {
+extern "C" int32_t kc_debug_last_tile_config(int32_t* v, int32_t* ctas, int32_t* stages) try {
     if (v) *v = g_kc_last_tile_config[0];
     if (ctas) *ctas = g_kc_last_tile_config[1];
     if (stages) *stages = g_kc_last_tile_config[2];
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     if (args.n == 0 || args.n_seg == 0) return KC_OK;

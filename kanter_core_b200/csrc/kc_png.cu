@@ -301,15 +301,15 @@ int32_t read_file(const char* path, std::vector<uint8_t>& data) {
 
 }  // namespace
 
-int32_t kc_png_decode_vec(const uint8_t* data, size_t n, std::vector<uint8_t>& samples, uint32_t& w, uint32_t& h, uint32_t& ch) {
+int32_t kc_png_decode_vec(const uint8_t* data, size_t n, std::vector<uint8_t>& samples, uint32_t& w, uint32_t& h, uint32_t& ch) try {
     return decode(data, n, samples, w, h, ch);
-}
-int32_t kc_png_decode_file_vec(const char* path, std::vector<uint8_t>& samples, uint32_t& w, uint32_t& h, uint32_t& ch) {
+} KC_ABI_CATCH
+int32_t kc_png_decode_file_vec(const char* path, std::vector<uint8_t>& samples, uint32_t& w, uint32_t& h, uint32_t& ch) try {
     std::vector<uint8_t> data;
     KC_TRY(read_file(path, data));
     return decode(data.data(), data.size(), samples, w, h, ch);
-}
-int32_t kc_png_write_file(const char* path, const uint8_t* px, uint32_t w, uint32_t h, int ch) {
+} KC_ABI_CATCH
+int32_t kc_png_write_file(const char* path, const uint8_t* px, uint32_t w, uint32_t h, int ch) try {
     std::vector<uint8_t> f;
     KC_TRY(encode(px, w, h, ch, f));
     FILE* fp = fopen(path, "wb");
@@ -317,11 +317,11 @@ int32_t kc_png_write_file(const char* path, const uint8_t* px, uint32_t w, uint3
     const size_t put = fwrite(f.data(), 1, f.size(), fp);
     if (fclose(fp) != 0 || put != f.size()) KC_FAIL(KC_ERR_IO, "short write on %s", path);
     return KC_OK;
-}
+} KC_ABI_CATCH
 
 extern "C" {
 
-int32_t kc_png_decode(const uint8_t* data, size_t n, uint8_t** samples, uint32_t* w, uint32_t* h, uint32_t* channels) {
+int32_t kc_png_decode(const uint8_t* data, size_t n, uint8_t** samples, uint32_t* w, uint32_t* h, uint32_t* channels) try {
     if (!data || !samples || !w || !h || !channels) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     std::vector<uint8_t> v;
     KC_TRY(decode(data, n, v, *w, *h, *channels));
@@ -329,16 +329,16 @@ int32_t kc_png_decode(const uint8_t* data, size_t n, uint8_t** samples, uint32_t
     if (!*samples) KC_FAIL(KC_ERR_GENERIC, "out of memory");
     memcpy(*samples, v.data(), v.size());
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-int32_t kc_png_decode_file(const char* path, uint8_t** samples, uint32_t* w, uint32_t* h, uint32_t* channels) {
+int32_t kc_png_decode_file(const char* path, uint8_t** samples, uint32_t* w, uint32_t* h, uint32_t* channels) try {
     if (!path) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "path is NULL");
     std::vector<uint8_t> data;
     KC_TRY(read_file(path, data));
     return kc_png_decode(data.data(), data.size(), samples, w, h, channels);
-}
+} KC_ABI_CATCH
 
-int32_t kc_png_encode(const uint8_t* samples, uint32_t w, uint32_t h, uint32_t channels, uint8_t** png, size_t* n) {
+int32_t kc_png_encode(const uint8_t* samples, uint32_t w, uint32_t h, uint32_t channels, uint8_t** png, size_t* n) try {
     if (!samples || !png || !n || channels < 1 || channels > 4) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad argument");
     std::vector<uint8_t> f;
     KC_TRY(encode(samples, w, h, (int)channels, f));
@@ -347,11 +347,11 @@ int32_t kc_png_encode(const uint8_t* samples, uint32_t w, uint32_t h, uint32_t c
     memcpy(*png, f.data(), f.size());
     *n = f.size();
     return KC_OK;
-}
+} KC_ABI_CATCH
 
-int32_t kc_png_encode_file(const char* path, const uint8_t* samples, uint32_t w, uint32_t h, uint32_t channels) {
+int32_t kc_png_encode_file(const char* path, const uint8_t* samples, uint32_t w, uint32_t h, uint32_t channels) try {
     if (!path || !samples || channels < 1 || channels > 4) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad argument");
     return kc_png_write_file(path, samples, w, h, (int)channels);
-}
+} KC_ABI_CATCH
 
 }  // extern "C"
