@@ -187,7 +187,15 @@ template <bool EXACT>
 __device__ __forceinline__ uint32_t kc_to_u8_srgb(float v) {
     float c = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
     float l;
-    if (c <= 0.0f) l = c;
+    if (!EXACT) {
+        // FAST (+-1 LSB of the exact bytes): branch-free, reciprocal multiplies, and the curve's argument
+        // ((c + .055) / 1.055 in (0.09, 1]) needs none of the general pow's range handling: 2^(2.4 * lg2 t)
+        const float t = (c + 0.055f) * (1.0f / 1.055f);
+        float lg, p;
+        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(t));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(2.4f * lg));
+        l = c <= 0.04045f ? c * (1.0f / 12.92f) : p;    // NaN compares false and comes out of lg2/ex2 as NaN
+    } else if (c <= 0.0f) l = c;
     else if (c <= 0.04045f) l = __fdiv_rn(c, 12.92f);
     else l = kc_pow<EXACT>(__fdiv_rn(__fadd_rn(c, 0.055f), 1.055f), 2.4f);
     float m = __fmul_rn(l, 255.0f);

@@ -318,6 +318,25 @@ def test_to_u8(tex_pro, srgb, shape):
     assert np.array_equal(g.to_u8(srgb), oracle.to_u8(P[:1], srgb))
 
 
+@pytest.mark.parametrize("srgb", [False, True])
+def test_to_u8_fast_within_one_lsb(tex_pro_fast, srgb):
+    # FAST export: the plain bytes are identical, the sRGB curve (SFU lg2/ex2, reciprocal multiplies) within 1 LSB;
+    # every 8-bit level and both sides of the curve's knee (0.04045) are in the input
+    h, w = 96, 128
+    P = [rnd(70 + c, h, w, -0.25, 1.25) for c in range(4)]
+    P[0].flat[:256] = np.arange(256, dtype=np.float32) / np.float32(255.0)
+    P[1].flat[:6] = [0.04045, np.nextafter(np.float32(0.04045), np.float32(1)), 0.0404, 0.0, 1.0, np.nan]
+    img = kc.SlotImage.from_planes(tex_pro_fast, P)
+    got, want = img.to_u8(srgb).astype(np.int32), oracle.to_u8(P, srgb).astype(np.int32)
+    if srgb:
+        assert np.abs(got - want).max() <= 1
+        assert (got != want).mean() < 0.01
+    else:
+        assert np.array_equal(got, want)
+    g = kc.SlotImage.from_planes(tex_pro_fast, P[:1])
+    assert np.abs(g.to_u8(srgb).astype(np.int32) - oracle.to_u8(P[:1], srgb).astype(np.int32)).max() <= (1 if srgb else 0)
+
+
 @pytest.mark.parametrize("ch", [1, 2, 3, 4])
 @pytest.mark.parametrize("shape", [(1, 1), (5, 7), (64, 64), (33, 31)])
 def test_from_u8(tex_pro, ch, shape):
