@@ -96,7 +96,11 @@ typedef struct kc_live_graph kc_live_graph;  /* LiveGraph, src/live_graph.rs:63-
 typedef struct kc_options {
     int32_t math_mode;        /* KC_MATH_*            (default KC_MATH_EXACT) */
     int32_t fuse;             /* 1: fuse chains of elementwise nodes into one kernel (default 1) */
-    int32_t reserved[6];
+    /* 0 (default): the second (horizontal) pass of a resize clamps to [0,1], as image-0.24's
+     * horizontal_sample does for f32.  No golden of the reference pins that clamp, so it
+     * can be switched off: 1 leaves overshoot (Lanczos3, CatmullRom) and out-of-range inputs as they are. */
+    int32_t resize_unclamped;
+    int32_t reserved[5];
 } kc_options;
 
 /* SlotImage, src/slot_image.rs:16-19.  planes[1..3] are NULL for Gray.  A
@@ -171,6 +175,7 @@ int32_t kc_context_device(const kc_context* ctx, int32_t* device);
 int32_t kc_context_stream(const kc_context* ctx, void** stream);
 int32_t kc_context_set_math_mode(kc_context* ctx, int32_t mode);
 int32_t kc_context_set_fuse(kc_context* ctx, int32_t fuse);
+int32_t kc_context_set_resize_unclamped(kc_context* ctx, int32_t unclamped);   /* kc_options.resize_unclamped */
 /* counters: kernels launched by this library on the context since creation,
  * bytes currently held by live planes (TransientBufferQueue::bytes_memory,
  * src/transient_buffer.rs:413-420) */

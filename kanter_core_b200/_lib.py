@@ -28,7 +28,7 @@ SIDE_INPUT, SIDE_OUTPUT = 0, 1
 
 
 class kc_options(C.Structure):
-    _fields_ = [("math_mode", C.c_int32), ("fuse", C.c_int32), ("reserved", C.c_int32 * 6)]
+    _fields_ = [("math_mode", C.c_int32), ("fuse", C.c_int32), ("resize_unclamped", C.c_int32), ("reserved", C.c_int32 * 5)]
 
 
 class kc_image(C.Structure):
@@ -81,6 +81,7 @@ SIGNATURES = {
     "kc_context_stream": (i32, [vp, P(vp)]),
     "kc_context_set_math_mode": (i32, [vp, i32]),
     "kc_context_set_fuse": (i32, [vp, i32]),
+    "kc_context_set_resize_unclamped": (i32, [vp, i32]),
     "kc_context_stats": (i32, [vp, P(u64), P(u64)]),
     "kc_context_trim": (i32, [vp]),
     "kc_plane_from_host_deferred": (i32, [vp, u32, u32, vp, P(vp)]),

@@ -674,6 +674,10 @@ class TextureProcessor:
     def set_math_mode(self, mode):
         call("kc_context_set_math_mode", self._ctx._h, int(mode))
 
+    def set_resize_clamp(self, clamp):
+        """The [0,1] clamp of a resize's second pass (image-0.24 semantics, on by default; no reference golden pins it)."""
+        call("kc_context_set_resize_unclamped", self._ctx._h, int(not clamp))
+
     def set_fuse(self, fuse):
         call("kc_context_set_fuse", self._ctx._h, int(bool(fuse)))
 

@@ -196,6 +196,11 @@ extern "C" int32_t kc_context_set_fuse(kc_context* ctx, int32_t fuse) try {
     ctx->opts.fuse = fuse ? 1 : 0;
     return KC_OK;
 } KC_ABI_CATCH
+extern "C" int32_t kc_context_set_resize_unclamped(kc_context* ctx, int32_t unclamped) try {
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    ctx->opts.resize_unclamped = unclamped ? 1 : 0;
+    return KC_OK;
+} KC_ABI_CATCH
 extern "C" int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_launches, uint64_t* bytes_live) try {
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     if (kernel_launches) *kernel_launches = ctx->kernel_launches;

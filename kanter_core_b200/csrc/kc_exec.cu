@@ -216,7 +216,7 @@ int32_t plane_resize(kc_context* ctx, kc_plane* src, uint32_t w, uint32_t h, int
         if (unit) {
             float v = 0.0f + src->value * 1.0f;
             v = 0.0f + v * 1.0f;
-            v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
+            if (!ctx->opts.resize_unclamped) v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);
             *out = kcp_new_const(ctx, w, nrows, v);
             return KC_OK;
         }

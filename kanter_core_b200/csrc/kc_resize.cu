@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(256) kc_resize_v_kernel(const float* __restric
 template <bool EXACT>
 __global__ void __launch_bounds__(256) kc_resize_h_kernel(const float* __restrict__ tmp, uint32_t sw, float* __restrict__ dst,
                                                           uint32_t dw, uint32_t dh, const uint32_t* __restrict__ left,
-                                                          const uint32_t* __restrict__ count, const float* __restrict__ wh) {
+                                                          const uint32_t* __restrict__ count, const float* __restrict__ wh, float clo, float chi) {
     const uint32_t ox = blockIdx.x * blockDim.x + threadIdx.x;
     if (ox >= dw) return;
     const uint32_t l = left[ox], n = count[ox];
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) kc_resize_h_kernel(const float* __restric
         float acc = 0.0f;
         for (uint32_t j = 0; j < n; ++j) acc = tap<EXACT>(acc, __ldg(row + j), wh[(size_t)j * dw + ox]);
         // image::math::utils::clamp keeps NaN
-        acc = acc < 0.0f ? 0.0f : (acc > 1.0f ? 1.0f : acc);
+        acc = acc < clo ? clo : (acc > chi ? chi : acc);
         __stcs(dst + (size_t)y * dw + ox, acc);
     }
 }
@@ -226,11 +226,12 @@ __device__ __forceinline__ float2 tap2(float2 acc, float2 s, float w, float one)
     return __ffma2_rn(s, ww, acc);
 }
 
-// clamp to [0,1]; NaN stays NaN (the reference's clamp is two comparisons)
-__device__ __forceinline__ float clamp01_keep_nan(float a) {
+// clamp to [lo, hi] = [0, 1]; NaN stays NaN (the reference's clamp is two comparisons).  The bounds are kernel
+// arguments: (-inf, +inf) when the caller switched the clamp off (kc_options.resize_unclamped), which makes both no-ops.
+__device__ __forceinline__ float clamp_keep_nan(float a, float lo, float hi) {
     float r;
-    asm("min.NaN.f32 %0, %1, 0f3F800000;" : "=f"(r) : "f"(a));
-    asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(r));
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(hi));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(r), "f"(lo));
     return r;
 }
 
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
     const float* __restrict__ src, uint32_t sw, uint32_t sh, float* __restrict__ dst, uint32_t dw, uint32_t dh,
     const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount, const float* __restrict__ vw, uint32_t vtaps,
     const uint32_t* __restrict__ hleft, const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
-    uint32_t pcols, uint32_t prows, float one, uint32_t row0, uint32_t nrows) {
+    uint32_t pcols, uint32_t prows, float one, uint32_t row0, uint32_t nrows, float clo, float chi) {
     // rows [row0, row0 + nrows) of the dw x dh result are produced; dst holds just those rows
     extern __shared__ __align__(16) float fsm[];
     float* Tm = fsm;                                              // [pcols][FS_TP] vertical-pass result, column-major
@@ -429,7 +430,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
                 for (int r = 0; r < FS_G; ++r) {
                     float v[FS_CPT];
 #pragma unroll
-                    for (int c = 0; c < FS_CPT; ++c) v[c] = clamp01_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x);
+                    for (int c = 0; c < FS_CPT; ++c) v[c] = clamp_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi);
                     __stcs(o4, make_float4(v[0], v[1], v[2], v[3]));
                     o4 += dw4;
                 }
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
                     if ((uint32_t)r < nrow) {
 #pragma unroll
                         for (int c = 0; c < FS_CPT; ++c)
-                            if (oxt + c <= oxl) out[(size_t)r * dw + c] = clamp01_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x);
+                            if (oxt + c <= oxl) out[(size_t)r * dw + c] = clamp_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi);
                     }
                 }
             }
@@ -460,7 +461,7 @@ constexpr int HT_ROWS = 8;
 template <bool EXACT>
 __global__ void __launch_bounds__(256) kc_resize_h_tile_kernel(const float* __restrict__ tmp, uint32_t sw, float* __restrict__ dst, uint32_t dw,
                                                                uint32_t dh, const uint32_t* __restrict__ left, const uint32_t* __restrict__ count,
-                                                               const float* __restrict__ wh, uint32_t pitch) {
+                                                               const float* __restrict__ wh, uint32_t pitch, float clo, float chi) {
     extern __shared__ __align__(16) float htile[];                 // [HT_ROWS][pitch]
     const uint32_t ox0 = blockIdx.x * 256, oxl = min(ox0 + 256, dw) - 1;
     const uint32_t y0 = blockIdx.y * HT_ROWS, nrow = min((uint32_t)HT_ROWS, dh - y0);
@@ -501,7 +502,7 @@ __global__ void __launch_bounds__(256) kc_resize_h_tile_kernel(const float* __re
     for (int r = 0; r < HT_ROWS; ++r)
         if ((uint32_t)r < nrow) {
             const float a = acc[r];
-            dst[(size_t)(y0 + r) * dw + ox] = a < 0.0f ? 0.0f : (a > 1.0f ? 1.0f : a);   // image::math::utils::clamp keeps NaN
+            dst[(size_t)(y0 + r) * dw + ox] = a < clo ? clo : (a > chi ? chi : a);   // image::math::utils::clamp keeps NaN
         }
 }
 
@@ -650,6 +651,8 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
     KC_TRY(get_axis(ctx, sh, dh, filter, tv));
     KC_TRY(get_axis(ctx, sw, dw, filter, th));
     const bool exact_mode = ctx->opts.math_mode == KC_MATH_EXACT;
+    // the [0,1] clamp of image-0.24's horizontal pass (unpinned by the reference's goldens: switchable)
+    const float clo = ctx->opts.resize_unclamped ? -INFINITY : 0.0f, chi = ctx->opts.resize_unclamped ? INFINITY : 1.0f;
     static const bool no_fused = getenv("KC_RESIZE_TWO_PASS") != nullptr;
     if (!no_fused && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT) {
         // threads per CTA: 4 output columns each.  Narrow CTAs (one or two warps) march
@@ -693,7 +696,7 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
                 void* args[] = {(void*)&src, (void*)&sw, (void*)&sh, (void*)&dst, (void*)&dw, (void*)&dh,
                                 (void*)&tv->d_left, (void*)&tv->d_count, (void*)&tv->d_weights, (void*)&tv->max_taps,
                                 (void*)&th->d_left, (void*)&th->d_count, (void*)&th->d_weights,
-                                (void*)&pcols, (void*)&prows, (void*)&one, (void*)&row0, (void*)&nrows};
+                                (void*)&pcols, (void*)&prows, (void*)&one, (void*)&row0, (void*)&nrows, (void*)&clo, (void*)&chi};
                 KC_CUDA(cudaLaunchKernel(fn, grid, dim3(threads), args, smem, ctx->stream));
                 ctx->kernel_launches++;
                 ctx->run_kernels++;
@@ -760,13 +763,13 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
         KC_TRY(kc_ensure_smem_attr(ctx, exact ? (const void*)kc_resize_h_tile_kernel<true> : (const void*)kc_resize_h_tile_kernel<false>, 96 * 1024));
         dim3 grid((dw + 255) / 256, hgy);
         KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
-        if (exact) kc_resize_h_tile_kernel<true><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, hpitch);
-        else kc_resize_h_tile_kernel<false><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, hpitch);
+        if (exact) kc_resize_h_tile_kernel<true><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, hpitch, clo, chi);
+        else kc_resize_h_tile_kernel<false><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, hpitch, clo, chi);
     } else {
         dim3 grid((dw + 255) / 256, std::min<uint32_t>(dh, 65535u));
         KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
-        if (exact) kc_resize_h_kernel<true><<<grid, 256, 0, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights);
-        else kc_resize_h_kernel<false><<<grid, 256, 0, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights);
+        if (exact) kc_resize_h_kernel<true><<<grid, 256, 0, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, clo, chi);
+        else kc_resize_h_kernel<false><<<grid, 256, 0, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, clo, chi);
     }
     cudaError_t e = cudaGetLastError();
     kc_dev_free(ctx, tmp, tmp_bytes);

@@ -529,3 +529,33 @@ def test_deferred_host_planes_upload_only_what_is_read(tex_pro):
     tp.synchronize()
     for p in A + B + [out]:
         kc.free_pinned(p)
+
+
+@pytest.mark.parametrize("filt", [ResizeFilter.Lanczos3, ResizeFilter.CatmullRom, ResizeFilter.Triangle])
+@pytest.mark.parametrize("sizes", [((40, 36), (131, 97)), ((257, 260), (64, 60)), ((1, 1), (32, 32))])
+def test_resize_clamp_is_switchable(tex_pro, filt, sizes):
+    """The [0,1] clamp of the second resize pass is the one arithmetic step of image-0.24 that no
+    reference golden pins, so it can be switched off: the clamped result is then
+    exactly clamp(unclamped), overshoot and out-of-range inputs survive, and the default is on."""
+    (sh, sw), (dh, dw) = sizes
+    src = rnd(123, sh, sw, -0.5, 1.5)
+    if src.size > 4:
+        src[::5, ::3] = 1.0
+        src[1::5, 1::3] = 0.0          # hard edges: Lanczos3 / CatmullRom overshoot
+    else:
+        src[0, 0] = 1.3
+    img = kc.SlotImage.from_planes(tex_pro, [src])
+    clamped = kc.resize(tex_pro, img, Size(dw, dh), filt).planes()[0]
+    assert bits_equal(clamped, oracle.resize_plane(src, dw, dh, int(filt)))
+    tex_pro.set_resize_clamp(False)
+    try:
+        free = kc.resize(tex_pro, img, Size(dw, dh), filt).planes()[0]
+        v = kc.SlotImage.from_value(tex_pro, Size(1, 1), 1.75, False)
+        assert kc.resize(tex_pro, v, Size(8, 8), filt).planes()[0][3, 3] == np.float32(1.75)     # the folded broadcast too
+    finally:
+        tex_pro.set_resize_clamp(True)
+    if dh >= sh:                         # an upsample keeps the input's range (and overshoots); a 4x downsample averages it away
+        assert free.max() > 1.0 and (src.size == 1 or free.min() < 0.0)
+    assert bits_equal(np.clip(free, np.float32(0), np.float32(1)), clamped)
+    v = kc.SlotImage.from_value(tex_pro, Size(1, 1), 1.75, False)
+    assert kc.resize(tex_pro, v, Size(8, 8), filt).planes()[0][3, 3] == np.float32(1.0)
