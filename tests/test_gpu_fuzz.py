@@ -300,3 +300,26 @@ def test_threads_share_one_context(tex_pro):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("threshold", [16, 64 * 1024, 1 << 20])
+@pytest.mark.parametrize("seed", range(10))
+def test_random_graph_exact_under_memory_pressure(tex_pro, seed, threshold):
+    """The same graphs with the spill queue squeezed (src/transient_buffer.rs:250-411): with a
+    threshold of 16 B, 64 KiB or 1 MiB nearly every plane leaves HBM as soon as nothing pins it and
+    comes back when a kernel needs it.  Results do not change, and planes really moved."""
+    graph, embeds = random_graph(8000 + seed, n_ops=8 + seed)
+    before = tex_pro.spill_stats()
+    tex_pro.set_memory_threshold(threshold)
+    try:
+        og, lg = evaluate_both(tex_pro, graph, embeds, use_cache=seed % 2 == 0)
+        for nid, n, s, want, got in each_slot(og, lg, graph):
+            assert len(got) == len(want)
+            for c in range(len(want)):
+                assert bits_equal(got[c], want[c]), (describe(graph, nid), n.node_type, s, c)
+        lg.close()
+    finally:
+        tex_pro.set_memory_threshold(0)            # 0: no limit
+    after = tex_pro.spill_stats()
+    if threshold == 16:
+        assert after["spills"] > before["spills"] and after["reloads"] > before["reloads"]
