@@ -23,7 +23,7 @@ POLICIES = [ResizePolicy.MostPixels, ResizePolicy.LeastPixels, ResizePolicy.Larg
 MIX = list(MixType)
 
 
-def random_graph(seed, n_ops, h2n=True, typed=True, inputs=None, nested=True):
+def random_graph(seed, n_ops, h2n=True, typed=True, inputs=None, nested=True, sizes=None):
     """-> (NodeGraph, {embed id: planes}).  Every op node takes its inputs from earlier
     nodes, so the graph is a DAG.  With `typed` the generator tracks which outputs carry
     Gray and which Rgba data and only makes connections the operators accept at run time
@@ -34,6 +34,7 @@ def random_graph(seed, n_ops, h2n=True, typed=True, inputs=None, nested=True):
     With `nested`, some operators are Graph nodes holding such an inner graph.  The named
     outputs and their kinds are left in `graph.fuzz_outputs`."""
     r = np.random.default_rng(seed)
+    SIZES = sizes or globals()["SIZES"]
     g = kc.NodeGraph.new()
     embeds = {}
     outs = []  # (node id, output slot, kind of the data "gray" | "rgba", static slot type "gray" | "rgba" | "any")
@@ -93,7 +94,7 @@ def random_graph(seed, n_ops, h2n=True, typed=True, inputs=None, nested=True):
             want = ["rgba" if r.random() < 0.5 else "gray" for _ in range(int(r.integers(1, 4)))]
             srcs = [pick(k) for k in want]
             if all(srcs):
-                inner = random_graph(int(r.integers(1 << 30)), int(r.integers(2, 7)), h2n=h2n, inputs=want)
+                inner = random_graph(int(r.integers(1 << 30)), int(r.integers(2, 7)), h2n=h2n, inputs=want, sizes=sizes)
                 if inner.fuzz_outputs:
                     n = add(NodeType.Graph(inner), None, filt)
                     for k, (src, sl, _, _) in enumerate(srcs):
@@ -323,3 +324,37 @@ def test_random_graph_exact_under_memory_pressure(tex_pro, seed, threshold):
     after = tex_pro.spill_stats()
     if threshold == 16:
         assert after["spills"] > before["spills"] and after["reloads"] > before["reloads"]
+
+
+BIG = [(1500, 1100), (2048, 1024), (1031, 997), (640, 2200), (1024, 1024), (1, 1), (3000, 500)]
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_graph_exact_at_megapixel_sizes(tex_pro, seed):
+    """Planes of 1-2 Mpx with ragged edges: many tiles per plane, tails that are not a multiple
+    of a float4 or of a tile, resizes between unrelated sizes in both directions (short- and
+    long-window kernels), and tapes hot enough for the automatic specialisation to kick in
+    (the graph is evaluated four times; the background compile is waited for in between)."""
+    graph, embeds = random_graph(9000 + seed, n_ops=7 + seed, sizes=BIG)
+    og = oracle.from_node_graph(graph)
+    for eid, planes in embeds.items():
+        og.embed(eid, planes)
+    og.eval()
+    lg = tex_pro.new_live_graph()
+    lg.use_cache = True
+    lg.set_node_graph(graph)
+    for eid, planes in embeds.items():
+        lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, kc.SlotImage.from_planes(tex_pro, planes)), eid)
+    for rounds in range(4):
+        if rounds:
+            for eid, planes in embeds.items():            # "new" pixels: everything downstream is dirty again
+                lg.replace_embedded(kc.SlotImage.from_planes(tex_pro, planes), eid)
+        if rounds == 3:
+            kc.jit_wait()
+        for n in graph.nodes:
+            kc.LiveGraph.await_clean_read(lg, n.node_id)
+    for nid, n, s, want, got in each_slot(og, lg, graph):
+        assert len(got) == len(want)
+        for c in range(len(want)):
+            assert bits_equal(got[c], want[c]), (describe(graph, nid), n.node_type, s, c, got[c].shape)
+    lg.close()
