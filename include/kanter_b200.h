@@ -164,6 +164,10 @@ int32_t kc_host_free(void* p);
  *      src/texture_processor.rs:34-56 (engine + transient-buffer queue) ------ */
 void kc_options_default(kc_options* o);
 int32_t kc_context_create(int32_t device, const kc_options* opts, kc_context** out);
+/* the same, with the caller's CUDA stream (a cudaStream_t; it must belong to `device` and outlive the context)
+ * as the stream every kernel is enqueued on: evaluations are ordered with the caller's other work on that stream.
+ * Uploads from host memory and RGBA8 downloads still use the context's two copy streams, tied in by events. */
+int32_t kc_context_create_on_stream(int32_t device, const kc_options* opts, void* cuda_stream, kc_context** out);
 /* Waits for the streams, then frees the streams, the buffer cache and the spill buffers.  Planes,
  * images and live graphs made from the context may be released AFTER this call (the reference's
  * Arc-owned SlotImages outlive its Engine the same way); every other use of them fails with

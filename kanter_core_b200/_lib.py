@@ -75,6 +75,7 @@ SIGNATURES = {
     "kc_host_free": (i32, [vp]),
     "kc_options_default": (None, [P(kc_options)]),
     "kc_context_create": (i32, [i32, P(kc_options), P(vp)]),
+    "kc_context_create_on_stream": (i32, [i32, P(kc_options), vp, P(vp)]),
     "kc_context_destroy": (i32, [vp]),
     "kc_context_synchronize": (i32, [vp]),
     "kc_context_device": (i32, [vp, P(i32)]),

@@ -604,13 +604,16 @@ class SlotData:  # src/slot_data.rs:35-39
 
 
 class _Context:
-    def __init__(self, device, math_mode, fuse):
+    def __init__(self, device, math_mode, fuse, cuda_stream=None):
         o = kc_options()
         _lib.lib.kc_options_default(C.byref(o))
         o.math_mode = int(math_mode)
         o.fuse = int(bool(fuse))
         self._h = C.c_void_p()
-        call("kc_context_create", int(device), C.byref(o), C.byref(self._h))
+        if cuda_stream is None:
+            call("kc_context_create", int(device), C.byref(o), C.byref(self._h))
+        else:   # the caller's stream, e.g. torch.cuda.Stream().cuda_stream
+            call("kc_context_create_on_stream", int(device), C.byref(o), C.c_void_p(int(cuda_stream)), C.byref(self._h))
 
     def close(self):
         if self._h:
@@ -654,9 +657,9 @@ class TextureProcessor:
     the CUDA context/stream/plane pool that replace the engine and
     transient-buffer threads."""
 
-    def __init__(self, memory_threshold=None, device=0, math_mode=_lib.MATH_EXACT, fuse=True):
+    def __init__(self, memory_threshold=None, device=0, math_mode=_lib.MATH_EXACT, fuse=True, cuda_stream=None):
         self.memory_threshold = memory_threshold
-        self._ctx = _Context(device, math_mode, fuse)
+        self._ctx = _Context(device, math_mode, fuse, cuda_stream)
         self._live_graphs = []
 
     @staticmethod

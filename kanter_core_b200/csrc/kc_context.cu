@@ -88,7 +88,7 @@ extern "C" void kc_options_default(kc_options* o) {
     o->fuse = 1;
 }
 
-extern "C" int32_t kc_context_create(int32_t device, const kc_options* opts, kc_context** out) try {
+static int32_t context_create(int32_t device, const kc_options* opts, cudaStream_t external, bool have_external, kc_context** out) {
     if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "kc_context_create: out is NULL");
     *out = nullptr;
     int n = 0;
@@ -109,20 +109,46 @@ extern "C" int32_t kc_context_create(int32_t device, const kc_options* opts, kc_
     if (opts) ctx->opts = *opts;
     int prev = 0;
     cudaGetDevice(&prev);
-    KC_CUDA(cudaSetDevice(device));
-    KC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    KC_CUDA(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
-    KC_CUDA(cudaStreamCreateWithFlags(&ctx->download_stream, cudaStreamNonBlocking));
-    for (cudaEvent_t* e : {&ctx->ev_up_wait, &ctx->ev_up_done, &ctx->ev_dl_wait, &ctx->ev_dl_done})
-        KC_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    // keep freed planes in the stream-ordered pool instead of returning them to the driver
-    cudaMemPool_t pool;
-    KC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-    uint64_t thr = UINT64_MAX;
-    KC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    auto setup = [&]() -> int32_t {
+        KC_CUDA(cudaSetDevice(device));
+        if (have_external) {
+            ctx->stream = external;          // the caller's stream: kernels are ordered with the caller's own work; never destroyed here
+            ctx->own_stream = false;
+        } else {
+            KC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        }
+        KC_CUDA(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+        KC_CUDA(cudaStreamCreateWithFlags(&ctx->download_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t* ev : {&ctx->ev_up_wait, &ctx->ev_up_done, &ctx->ev_dl_wait, &ctx->ev_dl_done})
+            KC_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+        // keep freed planes in the stream-ordered pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        KC_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thr = UINT64_MAX;
+        KC_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        return KC_OK;
+    };
+    const int32_t rc = setup();
     cudaSetDevice(prev);
+    if (rc != KC_OK) {   // whatever was created so far goes again
+        if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+        if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+        if (ctx->download_stream) cudaStreamDestroy(ctx->download_stream);
+        for (cudaEvent_t ev : {ctx->ev_up_wait, ctx->ev_up_done, ctx->ev_dl_wait, ctx->ev_dl_done})
+            if (ev) cudaEventDestroy(ev);
+        delete ctx;
+        return rc;
+    }
     *out = ctx;
     return KC_OK;
+}
+extern "C" int32_t kc_context_create(int32_t device, const kc_options* opts, kc_context** out) try {
+    return context_create(device, opts, nullptr, false, out);
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_create_on_stream(int32_t device, const kc_options* opts, void* cuda_stream, kc_context** out) try {
+    // every kernel of the context is enqueued on the caller's stream (NULL: the legacy default stream),
+    // so the evaluation is ordered with the caller's other CUDA work without events in between
+    return context_create(device, opts, (cudaStream_t)cuda_stream, true, out);
 } KC_ABI_CATCH
 
 static void axis_table_free(KcAxisTable& t) {
@@ -155,7 +181,7 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) try {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamDestroy(ctx->upload_stream);
         cudaStreamDestroy(ctx->download_stream);
-        cudaStreamDestroy(ctx->stream);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
         ctx->timed.clear();
         ctx->event_pool.clear();
         ctx->dl_staging = nullptr;

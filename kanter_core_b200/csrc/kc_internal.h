@@ -116,6 +116,7 @@ struct kc_context {
     bool closed = false;
     int device = 0;
     cudaStream_t stream = nullptr;           // every kernel, and every copy that is not one of the two below
+    bool own_stream = true;                  // false: the caller's stream (kc_context_create_on_stream)
     // copy engines next to the compute stream: planes built from host memory are uploaded on
     // `upload_stream`, RGBA8 results leave on `download_stream`, each tied to `stream` by events,
     // so the upload of the next evaluation overlaps the download of the previous one

@@ -155,3 +155,35 @@ def test_python_objects_released_after_close():
     del img, held, lg            # releases run against a closed context: no leak, no crash
     import gc
     gc.collect()
+
+
+def test_context_on_the_callers_stream():
+    """kc_context_create_on_stream: the library's kernels go onto a stream the caller owns (here a
+    torch stream), so they are ordered with the caller's own work on it and a torch event recorded
+    after the call covers them."""
+    import torch
+    s = torch.cuda.Stream()
+    tp = kc.TextureProcessor.new(cuda_stream=s.cuda_stream)
+    st = C.c_void_p()
+    call("kc_context_stream", tp._ctx._h, C.byref(st))
+    assert (st.value or 0) == s.cuda_stream
+    n = 1024
+    a, b = rnd(5, n, n), rnd(6, n, n)
+    # a torch tensor produced on the same stream, wrapped as a plane without a copy, consumed by the library
+    with torch.cuda.stream(s):
+        ta = torch.from_numpy(a).cuda(non_blocking=False)
+        ta = ta * 2.0                                            # caller's own kernel on s
+    A = kc.wrap_device_plane(tp, ta.data_ptr(), n, n)
+    B = kc.SlotImage.from_planes(tp, [b])
+    out = kc.mix(tp, kc.MixType.Add, A, B)
+    call("kc_image_materialize", tp._ctx._h, C.byref(out._im), 0)   # enqueued on s, after the torch kernel
+    done = torch.cuda.Event()
+    done.record(s)
+    done.synchronize()
+    got = out.planes()[0]
+    assert np.array_equal(got, oracle.mix_plane(0, (a * np.float32(2.0)).astype(np.float32), b))
+    del A, B, out
+    tp.close()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):                                  # the stream is still the caller's, and usable
+        assert float((ta + 1).sum()) > 0
