@@ -28,6 +28,17 @@ void kc_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+std::atomic<uint64_t> g_kc_hp_ns[KC_HP_COUNT], g_kc_hp_calls[KC_HP_COUNT];
+bool g_kc_hp_on = getenv("KC_HOST_PROFILE") != nullptr;
+static void host_profile_report() {
+    static const char* names[KC_HP_COUNT] = {"evaluate", "process_node", "kcp_force", "launch_segments", "kck_launch_tape", "plane_resize", "img_h2n"};
+    fprintf(stderr, "[kc host profile] stage: calls, total ms, us per call (stages nest: evaluate > process_node, kcp_force > launch_segments > kck_launch_tape)\n");
+    for (int i = 0; i < KC_HP_COUNT; ++i) {
+        const uint64_t c = g_kc_hp_calls[i].load(), ns = g_kc_hp_ns[i].load();
+        if (c) fprintf(stderr, "[kc host profile] %-16s %8llu  %9.3f  %8.2f\n", names[i], (unsigned long long)c, ns / 1e6, ns / 1e3 / c);
+    }
+}
+
 int32_t kc_fail_exception(const char* what) {
     if (what) kc_set_error("internal error: %s", what);
     else kc_set_error("out of host memory");
@@ -189,6 +200,7 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) try {
         ctx->ev_up_wait = ctx->ev_up_done = ctx->ev_dl_wait = ctx->ev_dl_done = nullptr;
         ctx->closed = true;
     }
+    if (g_kc_hp_on) host_profile_report();
     kc_ctx_unref(ctx);   // planes and live graphs still alive keep the bookkeeping until they are released
     return KC_OK;
 } KC_ABI_CATCH

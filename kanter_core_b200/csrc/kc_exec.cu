@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstring>
 #include <set>
+#include <unordered_map>
 
 #include "kc_graph.h"
 
@@ -153,6 +154,7 @@ int32_t img_mix(kc_context* ctx, int mix_type, const Img* left, const Img* right
 int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullptr, uint32_t h_full = 0,
                 const kc_halo_link* inbox = nullptr, uint64_t step = 0) {
     if (in.rgba()) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "HeightToNormal needs a Gray input");
+    KcHostTimer hp(KC_HP_H2N);
     kc_plane* src = in.im.planes[0];
     KcPin pin;   // source, halo and the planes already allocated stay in HBM until the kernel is enqueued
     KC_TRY(kcp_force(ctx, &src, 1));
@@ -191,6 +193,7 @@ int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullp
 int32_t plane_resize(kc_context* ctx, kc_plane* src, uint32_t w, uint32_t h, int filter, kc_plane** out,
                      uint32_t row0 = 0, uint32_t nrows = 0xffffffffu) {
     if (nrows == 0xffffffffu) nrows = h;
+    KcHostTimer hp(KC_HP_RESIZE);
     if (row0 > h || nrows > h - row0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "rows [%u, %u) are outside the %u-row result", row0, row0 + nrows, h);
     if (filter < KC_FILTER_NEAREST || filter > KC_FILTER_LANCZOS3) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad filter %d", filter);
     if (src->kind == KC_PLANE_CONST && src->w == 1 && src->h == 1) {
@@ -592,72 +595,108 @@ struct kc_live_graph {
 
 int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool materialise) {
     KcGuard guard(ctx);
+    KcHostTimer hp(KC_HP_EVALUATE);
     ctx->cancel.store(false);
     const uint64_t k0 = ctx->run_kernels, g0 = ctx->run_groups, b0 = ctx->run_bytes;
     std::set<uint32_t> requested(ids, ids + n_ids);
     for (uint32_t id : requested)
         if (!kcg_find(graph, id)) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", id);
 
+    // An index of the graph as it stands, built once per call: positions of the nodes, each node's incoming
+    // edges (in edge order), parents and children.  The loops below touch each edge a constant number of times.
+    const size_t N = graph.nodes.size();
+    std::unordered_map<uint32_t, int> pos;
+    pos.reserve(N * 2);
+    for (size_t i = 0; i < N; ++i) pos.emplace(graph.nodes[i].node_id, (int)i);   // first node wins, as kcg_find does
+    std::vector<std::vector<int>> in_edges(N), par(N), chi(N);
+    for (size_t j = 0; j < graph.edges.size(); ++j) {
+        const kc_edge& e = graph.edges[j];
+        auto ci = pos.find(e.input_id), pi = pos.find(e.output_id);
+        if (ci == pos.end()) continue;
+        in_edges[ci->second].push_back((int)j);
+        if (pi == pos.end()) continue;                    // an edge from a node that is gone: no dependency, no data either
+        if (std::find(par[ci->second].begin(), par[ci->second].end(), pi->second) == par[ci->second].end()) par[ci->second].push_back(pi->second);
+        if (std::find(chi[pi->second].begin(), chi[pi->second].end(), ci->second) == chi[pi->second].end()) chi[pi->second].push_back(ci->second);
+    }
+    std::vector<int*> st(N);                              // the nodes' states (map nodes do not move)
+    for (size_t i = 0; i < N; ++i) st[i] = &state[graph.nodes[i].node_id];
+    std::vector<char> is_req(N, 0), in_todo(N, 0);
+    for (uint32_t id : requested) is_req[pos[id]] = 1;
+
     // 1. which nodes must run: requested nodes and their ancestors that are not
     //    Clean, or Clean but whose data has been freed (engine.rs:253-262)
-    std::set<uint32_t> todo;
+    size_t remaining = 0;
     {
-        std::vector<uint32_t> work(requested.begin(), requested.end());
+        std::vector<char> with_data(N, 0);
+        for (const Slot& s : slot_datas) {
+            auto it = pos.find(s.node_id);
+            if (it != pos.end()) with_data[it->second] = 1;
+        }
+        std::vector<int> work;
+        for (size_t i = 0; i < N; ++i)
+            if (is_req[i]) work.push_back((int)i);
         while (!work.empty()) {
-            uint32_t id = work.back();
+            const int i = work.back();
             work.pop_back();
-            if (todo.count(id)) continue;
-            if (state[id] == KC_STATE_CLEAN && has_data(id)) continue;
-            todo.insert(id);
-            for (uint32_t p : parents(id)) work.push_back(p);
+            if (in_todo[i]) continue;
+            if (*st[i] == KC_STATE_CLEAN && with_data[i]) continue;
+            in_todo[i] = 1;
+            ++remaining;
+            for (int p : par[i]) work.push_back(p);
         }
     }
-    for (uint32_t id : todo)
-        if (state[id] == KC_STATE_CLEAN) state[id] = KC_STATE_DIRTY;
-    for (uint32_t id : requested)
-        if (state[id] != KC_STATE_CLEAN) state[id] = KC_STATE_REQUESTED;
+    for (size_t i = 0; i < N; ++i)
+        if (in_todo[i] && *st[i] == KC_STATE_CLEAN) *st[i] = KC_STATE_DIRTY;
+    for (size_t i = 0; i < N; ++i)
+        if (is_req[i] && *st[i] != KC_STATE_CLEAN) *st[i] = KC_STATE_REQUESTED;
 
     // 2. run them in dependency order (ties: position in the node vector)
-    size_t remaining = todo.size();
     int32_t rc = KC_OK;
+    std::vector<kc_edge> ne;
+    std::vector<Slot> in, out;
     while (remaining > 0 && rc == KC_OK) {
         bool progressed = false;
-        for (const KcNode& node : graph.nodes) {
-            if (!todo.count(node.node_id) || state[node.node_id] == KC_STATE_CLEAN) continue;
+        for (size_t i = 0; i < N; ++i) {
+            if (!in_todo[i] || *st[i] == KC_STATE_CLEAN) continue;
+            const KcNode& node = graph.nodes[i];
             bool ready = true;
-            for (const kc_edge& e : graph.edges)
-                if (e.input_id == node.node_id && kcg_find(graph, e.output_id) && state[e.output_id] != KC_STATE_CLEAN) ready = false;
+            for (int p : par[i])
+                if (*st[p] != KC_STATE_CLEAN) { ready = false; break; }
             if (!ready) continue;
             if (ctx->cancel.load()) { rc = KC_ERR_CANCELED; kc_set_error("evaluation canceled"); break; }
-            state[node.node_id] = KC_STATE_PROCESSING;
+            *st[i] = KC_STATE_PROCESSING;
             // gather the inputs in graph-edge order, engine.rs:217-262
-            std::vector<kc_edge> ne;
-            std::vector<Slot> in;
-            for (const kc_edge& e : graph.edges) {
-                if (e.input_id != node.node_id) continue;
+            ne.clear();
+            in.clear();
+            for (int j : in_edges[i]) {
+                const kc_edge& e = graph.edges[j];
                 const Slot* f = find_slot(e.output_id, e.output_slot);
                 if (!f) { rc = KC_ERR_NO_SLOT_DATA; kc_set_error("node %u has no data in slot %u", e.output_id, e.output_slot); break; }
                 ne.push_back(e);
                 in.push_back(*f);
             }
             if (rc != KC_OK) break;
-            std::vector<Slot> out;
-            rc = process_node(ctx, node, in, ne, embeds, inputs, images, out);
+            out.clear();
+            {
+                KcHostTimer hp_node(KC_HP_PROCESS_NODE);
+                rc = process_node(ctx, node, in, ne, embeds, inputs, images, out);
+            }
             if (rc != KC_OK) break;
             in.clear();
             remove_nodes_data(node.node_id);
             for (Slot& s : out) slot_datas.push_back(std::move(s));
-            state[node.node_id] = KC_STATE_CLEAN;
+            out.clear();
+            *st[i] = KC_STATE_CLEAN;
             changed.insert(node.node_id);
             // free the parents' data once every child of theirs has run, engine.rs:58-75
             // (nodes the caller asked for keep theirs)
             if (!use_cache) {
-                for (uint32_t p : parents(node.node_id)) {
-                    if (requested.count(p)) continue;
+                for (int p : par[i]) {
+                    if (is_req[p]) continue;
                     bool all = true;
-                    for (uint32_t c : children(p))
-                        if (state[c] != KC_STATE_CLEAN && state[c] != KC_STATE_PROCESSING) all = false;
-                    if (all) remove_nodes_data(p);
+                    for (int c : chi[p])
+                        if (*st[c] != KC_STATE_CLEAN && *st[c] != KC_STATE_PROCESSING) { all = false; break; }
+                    if (all) remove_nodes_data(graph.nodes[p].node_id);
                 }
             }
             --remaining;
@@ -668,9 +707,11 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
             kc_set_error("the graph has a cycle; %zu nodes can never become clean", remaining);
         }
     }
+    in.clear();
+    out.clear();
     if (rc != KC_OK) {
-        for (uint32_t id : todo)
-            if (state[id] != KC_STATE_CLEAN) { state[id] = KC_STATE_DIRTY; remove_nodes_data(id); }
+        for (size_t i = 0; i < N; ++i)
+            if (in_todo[i] && *st[i] != KC_STATE_CLEAN) { *st[i] = KC_STATE_DIRTY; remove_nodes_data(graph.nodes[i].node_id); }
         return rc;
     }
     // 3. the requested nodes' planes become real pixels, in as few kernels as possible

@@ -281,6 +281,7 @@ int32_t alloc_plane_storage(kc_context* ctx, kc_plane* like, float** out) {
 // Launch a set of generated, mutually independent segments: grouped by pixel
 // count, up to KC_MAX_SEG per launch.
 int32_t launch_segments(kc_context* ctx, std::vector<SegPlan*>& segs, uint32_t* d_rgba8) {
+    KcHostTimer hp(KC_HP_LAUNCH_SEGMENTS);
     KcPin pin;   // allocating the outputs may push the spill queue over its threshold: the sources stay
     for (SegPlan* k : segs)
         for (kc_plane* sp : k->gen.srcs) { pin.add(sp); kcp_touch(sp); }
@@ -570,6 +571,7 @@ int32_t kcp_prefetch_leaves(kc_context* ctx, kc_plane* const* roots, size_t n) {
 }
 
 int32_t kcp_force(kc_context* ctx, kc_plane* const* roots, size_t n) {
+    KcHostTimer hp(KC_HP_FORCE);
     int32_t rc = force_impl(ctx, roots, n, 0, 0, nullptr, 0);
     // the evaluation held its operands in HBM (pins); now that they are released the queue may settle --
     // except for the planes the caller asked for: it is about to read them

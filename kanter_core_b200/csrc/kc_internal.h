@@ -12,6 +12,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <chrono>
 #include <new>
 #include <stdexcept>
 #include <tuple>
@@ -214,6 +215,21 @@ inline void kcp_dealloc(kc_plane* p) {
     delete p;
     if (c) kc_ctx_unref(c);
 }
+
+// ---- host-side profile (KC_HOST_PROFILE=1): wall time of the evaluator's stages, printed when a context is destroyed
+enum { KC_HP_EVALUATE = 0, KC_HP_PROCESS_NODE, KC_HP_FORCE, KC_HP_LAUNCH_SEGMENTS, KC_HP_LAUNCH_TAPE, KC_HP_RESIZE, KC_HP_H2N, KC_HP_COUNT };
+extern std::atomic<uint64_t> g_kc_hp_ns[KC_HP_COUNT], g_kc_hp_calls[KC_HP_COUNT];
+extern bool g_kc_hp_on;
+struct KcHostTimer {
+    int k;
+    std::chrono::steady_clock::time_point t0;
+    explicit KcHostTimer(int kind) : k(kind) { if (g_kc_hp_on) t0 = std::chrono::steady_clock::now(); }
+    ~KcHostTimer() {
+        if (!g_kc_hp_on) return;
+        g_kc_hp_ns[k] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+        g_kc_hp_calls[k]++;
+    }
+};
 
 // ---- tuning knobs (kc_context.cu): 0 = let the library choose.  Set from the environment
 // (KC_TILE_V, KC_CTAS, KC_STAGES, KC_SRC_SOFT_CAP, KC_RESIZE_THREADS) at load time or through

@@ -155,6 +155,7 @@ extern "C" int32_t kc_debug_last_tile_config(int32_t* v, int32_t* ctas, int32_t*
 
 int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     if (args.n == 0 || args.n_seg == 0) return KC_OK;
+    KcHostTimer hp(KC_HP_LAUNCH_TAPE);
     int ns_max = 0;
     for (uint32_t s = 0; s < args.n_seg; ++s) ns_max = std::max<int>(ns_max, (int)args.seg[s].n_src);
     const int nt_max = (int)args.variant;  // temporaries the tapes touch (set by the planner)
