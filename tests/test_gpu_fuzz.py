@@ -358,3 +358,36 @@ def test_random_graph_exact_at_megapixel_sizes(tex_pro, seed):
         for c in range(len(want)):
             assert bits_equal(got[c], want[c]), (describe(graph, nid), n.node_type, s, c, got[c].shape)
     lg.close()
+
+
+def test_contexts_on_separate_threads_do_not_interfere():
+    """Four contexts, one thread each, no lock in common: what they share inside the library (the
+    cache of specialised kernels, occupancy and attribute caches, the planner's stamps) is
+    process-wide state that has to hold up."""
+    import threading
+    errors = []
+
+    def work(i):
+        tp = None
+        try:
+            tp = kc.TextureProcessor.new(math_mode=kc.MATH_EXACT)
+            for rep in range(3):
+                graph, embeds = random_graph(9500 + 10 * i + rep, n_ops=8 + i)
+                og, lg = evaluate_both(tp, graph, embeds)
+                for nid, n, s, want, got in each_slot(og, lg, graph):
+                    assert len(got) == len(want)
+                    for c in range(len(want)):
+                        assert bits_equal(got[c], want[c]), (i, rep, nid, s, c)
+                lg.close()
+        except BaseException as e:  # noqa: BLE001 - reported in the main thread
+            errors.append((i, repr(e)))
+        finally:
+            if tp is not None:
+                tp.close()
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
