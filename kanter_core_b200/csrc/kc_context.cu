@@ -298,6 +298,7 @@ void kc_dev_trim(kc_context* ctx) {
 // ---------------------------------------------------------------------------
 // planes
 // ---------------------------------------------------------------------------
+static void resident_add(kc_context* ctx, kc_plane* p);
 static inline size_t plane_alloc_bytes(const kc_plane* p) {
     // round up to a whole float4 so the vector kernels' last access stays in bounds
     size_t bytes = ((p->bytes() + 15) / 16) * 16;
@@ -316,7 +317,7 @@ int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out) 
     }
     ctx->bytes_live += bytes;
     p->last_use = ++ctx->use_tick;
-    ctx->resident.push_back(p);
+    resident_add(ctx, p);
     if (ctx->bytes_live > ctx->memory_threshold) {
         ++p->pins;                       // never the plane being handed out
         rc = kc_enforce_threshold(ctx);
@@ -333,9 +334,20 @@ int32_t kcp_new_device(kc_context* ctx, uint32_t w, uint32_t h, kc_plane** out) 
 // copy of a reload before anything that reads the plane, and host buffers are recycled, never
 // freed, while the context lives -- so no call in this section has to wait for the GPU.
 // ---------------------------------------------------------------------------
+// the list of spill candidates; each plane knows its position, so joining and leaving are O(1)
+// (a context with a thousand live planes releases dozens per evaluation)
+static void resident_add(kc_context* ctx, kc_plane* p) {
+    p->resident_idx = (int)ctx->resident.size();
+    ctx->resident.push_back(p);
+}
 static void resident_remove(kc_context* ctx, kc_plane* p) {
-    auto it = std::find(ctx->resident.begin(), ctx->resident.end(), p);
-    if (it != ctx->resident.end()) { *it = ctx->resident.back(); ctx->resident.pop_back(); }
+    const int i = p->resident_idx;
+    if (i < 0 || (size_t)i >= ctx->resident.size() || ctx->resident[i] != p) return;
+    kc_plane* last = ctx->resident.back();
+    ctx->resident[i] = last;
+    last->resident_idx = i;
+    ctx->resident.pop_back();
+    p->resident_idx = -1;
 }
 void kcp_touch(kc_plane* p) {
     if (p && p->ctx) p->last_use = ++p->ctx->use_tick;
@@ -352,7 +364,7 @@ void kcp_adopt_storage(kc_plane* p, float* dptr) {
     p->dptr = dptr;
     p->owned = true;
     p->last_use = ++p->ctx->use_tick;
-    p->ctx->resident.push_back(p);
+    resident_add(p->ctx, p);
 }
 static int32_t host_alloc(kc_context* ctx, size_t bytes, void** out) {
     auto it = ctx->host_free_lists.find(bytes);
@@ -426,7 +438,7 @@ int32_t kcp_reload(kc_context* ctx, kc_plane* p) {
     p->dptr = (float*)d;
     p->kind = KC_PLANE_DEVICE;
     p->last_use = ++ctx->use_tick;
-    ctx->resident.push_back(p);
+    resident_add(ctx, p);
     ctx->bytes_live += bytes;
     ctx->planes_on_host--;
     if (ctx->bytes_live > ctx->memory_threshold) {

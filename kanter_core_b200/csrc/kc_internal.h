@@ -87,6 +87,7 @@ struct kc_plane {
     bool host_borrowed = false;   // host_copy is the caller's (pinned) memory: a plane whose upload is deferred until somebody reads it
     uint64_t last_use = 0;
     int pins = 0;
+    int resident_idx = -1;        // position in ctx->resident while the plane owns device storage
     // CONST
     float value = 0.0f;
     // EXPR: a lazily evaluated  a (op) b ; operands are retained
