@@ -727,7 +727,8 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
         KC_TRY(build_march_tables(ctx, *tv));
         if (tv->march_state == 1) {
             // output rows per CTA: as many as keep the tables of its source range within 64 KiB of shared memory
-            uint32_t rows = VM_ROWS_PER_CTA;
+            static const int env_rows = getenv("KC_VM_ROWS") ? atoi(getenv("KC_VM_ROWS")) : 0;
+            uint32_t rows = env_rows > 0 ? (uint32_t)env_rows : (uint32_t)VM_ROWS_PER_CTA;
             auto range = [&](uint32_t rpc) {
                 uint32_t mx = 0;
                 for (uint32_t a = 0; a < dh; a += rpc) {
