@@ -456,32 +456,44 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
 // thread walks its window ONCE for all the rows -- each tap weight is fetched once per HT_ROWS
 // outputs and the rows are independent accumulation chains.  Same tap order and clamp as
 // kc_resize_h_kernel.
-constexpr int HT_ROWS = 8;
+constexpr int HT_ROWS_MAX = 8;
 
-template <bool EXACT>
+// ROWS rows of a 256-output tile per CTA; eight loads per thread are in flight during staging whatever ROWS is.
+template <bool EXACT, int ROWS>
 __global__ void __launch_bounds__(256) kc_resize_h_tile_kernel(const float* __restrict__ tmp, uint32_t sw, float* __restrict__ dst, uint32_t dw,
                                                                uint32_t dh, const uint32_t* __restrict__ left, const uint32_t* __restrict__ count,
                                                                const float* __restrict__ wh, uint32_t pitch, float clo, float chi) {
-    extern __shared__ __align__(16) float htile[];                 // [HT_ROWS][pitch]
+    extern __shared__ __align__(16) float htile[];                 // [ROWS][pitch]
     const uint32_t ox0 = blockIdx.x * 256, oxl = min(ox0 + 256, dw) - 1;
-    const uint32_t y0 = blockIdx.y * HT_ROWS, nrow = min((uint32_t)HT_ROWS, dh - y0);
+    const uint32_t y0 = blockIdx.y * ROWS, nrow = min((uint32_t)ROWS, dh - y0);
     const uint32_t c0 = __ldg(left + ox0), ncol = __ldg(left + oxl) + __ldg(count + oxl) - c0;
-    // staging: the loads of all HT_ROWS rows of a column are in flight together (the intermediate comes from L2)
-    for (uint32_t i = threadIdx.x; i < ncol; i += 256) {
-        float v[HT_ROWS];
+    // staging: eight loads per thread in flight together (ROWS rows of CB columns; the intermediate comes from L2)
+    constexpr int CB = 8 / ROWS;
+    for (uint32_t i0 = threadIdx.x; i0 < ncol; i0 += 256 * CB) {
+        float v[CB][ROWS];
 #pragma unroll
-        for (int r = 0; r < HT_ROWS; ++r) v[r] = __ldg(tmp + (size_t)(y0 + min((uint32_t)r, nrow - 1)) * sw + c0 + i);
-        const uint32_t si = i + (i >> 5);
+        for (int cb = 0; cb < CB; ++cb) {
+            const uint32_t i = min(i0 + 256u * cb, ncol - 1);
 #pragma unroll
-        for (int r = 0; r < HT_ROWS; ++r) htile[(size_t)r * pitch + si] = v[r];
+            for (int r = 0; r < ROWS; ++r) v[cb][r] = __ldg(tmp + (size_t)(y0 + min((uint32_t)r, nrow - 1)) * sw + c0 + i);
+        }
+#pragma unroll
+        for (int cb = 0; cb < CB; ++cb) {
+            const uint32_t i = i0 + 256u * cb;
+            if (i < ncol) {
+                const uint32_t si = i + (i >> 5);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) htile[(size_t)r * pitch + si] = v[cb][r];
+            }
+        }
     }
     __syncthreads();
     const uint32_t ox = ox0 + threadIdx.x;
     if (ox > oxl) return;
     const uint32_t l = __ldg(left + ox) - c0, n = __ldg(count + ox);
-    float acc[HT_ROWS];
+    float acc[ROWS];
 #pragma unroll
-    for (int r = 0; r < HT_ROWS; ++r) acc[r] = 0.0f;
+    for (int r = 0; r < ROWS; ++r) acc[r] = 0.0f;
     const float* wp = wh + ox;
     constexpr int WB = 8;                                          // tap weights fetched WB at a time
     for (uint32_t j0 = 0; j0 < n; j0 += WB) {
@@ -494,12 +506,12 @@ __global__ void __launch_bounds__(256) kc_resize_h_tile_kernel(const float* __re
                 const uint32_t i = l + j0 + k;
                 const float* sp = htile + i + (i >> 5);
 #pragma unroll
-                for (int r = 0; r < HT_ROWS; ++r) acc[r] = tap<EXACT>(acc[r], sp[(size_t)r * pitch], w[k]);   // rows past nrow: duplicates, never stored
+                for (int r = 0; r < ROWS; ++r) acc[r] = tap<EXACT>(acc[r], sp[(size_t)r * pitch], w[k]);   // rows past nrow: duplicates, never stored
             }
         }
     }
 #pragma unroll
-    for (int r = 0; r < HT_ROWS; ++r)
+    for (int r = 0; r < ROWS; ++r)
         if ((uint32_t)r < nrow) {
             const float a = acc[r];
             dst[(size_t)(y0 + r) * dw + ox] = a < clo ? clo : (a > chi ? chi : a);   // image::math::utils::clamp keeps NaN
@@ -758,14 +770,23 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
     }
     const uint32_t hwin = max_window(*th, 256);
     const uint32_t hpitch = hwin + (hwin >> 5) + 1;
-    const size_t hsmem = sizeof(float) * (size_t)HT_ROWS * hpitch;
-    const uint32_t hgy = (dh + HT_ROWS - 1) / HT_ROWS;
+    // rows per CTA: measured on 8192x1024 -> 1024x1024 (Lanczos3): 8 rows 0.0323 ms, 4 rows 0.0307 ms, 2 rows 0.0332 ms
+    // (KC_HT_ROWS overrides for sweeps)
+    static const int env_ht = getenv("KC_HT_ROWS") ? atoi(getenv("KC_HT_ROWS")) : 0;
+    const int ht_rows = (env_ht == 2 || env_ht == 4 || env_ht == 8) ? env_ht : 4;
+    const size_t hsmem = sizeof(float) * (size_t)ht_rows * hpitch;
+    const uint32_t hgy = (dh + ht_rows - 1) / ht_rows;
     if (!no_march && th->max_taps > (uint32_t)FS_MAXT && hsmem <= 96 * 1024 && hgy <= 65535u) {
-        KC_TRY(kc_ensure_smem_attr(ctx, exact ? (const void*)kc_resize_h_tile_kernel<true> : (const void*)kc_resize_h_tile_kernel<false>, 96 * 1024));
+        const void* fn = nullptr;
+#define KC_HT(R) (exact ? (const void*)kc_resize_h_tile_kernel<true, R> : (const void*)kc_resize_h_tile_kernel<false, R>)
+        fn = ht_rows == 8 ? KC_HT(8) : ht_rows == 4 ? KC_HT(4) : KC_HT(2);
+#undef KC_HT
+        KC_TRY(kc_ensure_smem_attr(ctx, fn, 96 * 1024));
         dim3 grid((dw + 255) / 256, hgy);
         KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
-        if (exact) kc_resize_h_tile_kernel<true><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, hpitch, clo, chi);
-        else kc_resize_h_tile_kernel<false><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, hpitch, clo, chi);
+        void* hargs[] = {(void*)&tmp, (void*)&sw, (void*)&dst, (void*)&dw, (void*)&dh, (void*)&th->d_left, (void*)&th->d_count,
+                         (void*)&th->d_weights, (void*)&hpitch, (void*)&clo, (void*)&chi};
+        cudaLaunchKernel(fn, grid, dim3(256), hargs, hsmem, ctx->stream);   // a failure is picked up below, after tmp is handed back
     } else {
         dim3 grid((dw + 255) / 256, std::min<uint32_t>(dh, 65535u));
         KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
