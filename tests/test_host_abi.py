@@ -55,6 +55,24 @@ def test_no_gpu_means_loud_failure_not_fallback():
     assert "ERR Cuda" in out, out
 
 
+def test_entry_points_that_need_no_device():
+    """Argument checking and the process-wide helpers answer without a GPU."""
+    from kanter_core_b200._lib import TexProError, call, lib
+    n = C.c_int32(-1)
+    call("kc_debug_jit_wait", 10, C.byref(n))                     # nothing is compiling
+    assert n.value == 0
+    for fn, args in (("kc_context_set_resize_unclamped", (None, 1)), ("kc_context_set_math_mode", (None, 0)),
+                     ("kc_context_synchronize", (None,)), ("kc_live_graph_create", (None, None))):
+        with pytest.raises(TexProError) as e:
+            call(fn, *args)
+        assert e.value.code == 101, fn                           # KC_ERR_INVALID_ARGUMENT, not a crash
+    ctx = C.c_void_p()
+    with pytest.raises(TexProError) as e:                         # a caller-owned stream does not conjure a device either
+        call("kc_context_create_on_stream", 0, None, None, C.byref(ctx))
+    assert e.value.kind == "Cuda" and not ctx.value
+    assert lib.kc_context_destroy(None) == 0                      # destroying nothing is fine
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "kanter_core_b200")
     for dirpath, _, files in os.walk(pkg):
