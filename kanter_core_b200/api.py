@@ -532,15 +532,18 @@ class SlotImage:
         return SlotImage(tex_pro._ctx, im)
 
     @staticmethod
-    def from_u8(tex_pro, samples):
-        """Decoded interleaved u8 samples, shape (h, w) or (h, w, c): deconstruct_image, src/shared.rs:16-56."""
+    def from_u8(tex_pro, samples, sync=True):
+        """Decoded interleaved u8 samples, shape (h, w) or (h, w, c): deconstruct_image, src/shared.rs:16-56.
+        sync=False: returns once the copy and the conversion are enqueued (the samples must then be in
+        pinned memory and stay untouched until the context has been synchronised)."""
         a = np.ascontiguousarray(samples, dtype=np.uint8)
         if a.ndim == 2:
             a = a[:, :, None]
         h, w, c = a.shape
         im = kc_image()
         call("kc_image_from_u8", tex_pro._ctx._h, a.ctypes.data, w, h, c, C.byref(im))
-        call("kc_context_synchronize", tex_pro._ctx._h)
+        if sync:
+            call("kc_context_synchronize", tex_pro._ctx._h)
         return SlotImage(tex_pro._ctx, im)
 
     def is_rgba(self):
