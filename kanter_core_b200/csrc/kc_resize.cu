@@ -456,7 +456,6 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
 // thread walks its window ONCE for all the rows -- each tap weight is fetched once per HT_ROWS
 // outputs and the rows are independent accumulation chains.  Same tap order and clamp as
 // kc_resize_h_kernel.
-constexpr int HT_ROWS_MAX = 8;
 
 // ROWS rows of a 256-output tile per CTA; eight loads per thread are in flight during staging whatever ROWS is.
 template <bool EXACT, int ROWS>
