@@ -16,7 +16,7 @@ if [ "$1" = build ]; then
             -c kanter_core_b200/csrc/$s.cu -o $OUT/$s.o &
     done
     wait
-    nvcc -shared -cudart static -o $OUT/libkanter_b200.so $OUT/*.o -lz -ldl -Xcompiler -fsanitize=address
+    nvcc -shared -cudart static -Wno-deprecated-gpu-targets -o $OUT/libkanter_b200.so $OUT/*.o -lz -ldl -Xcompiler -fsanitize=address
     echo $OUT/libkanter_b200.so
 else
     shift || true
