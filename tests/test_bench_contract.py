@@ -34,3 +34,35 @@ def test_reference_arm_other_ranks_exit_quietly():
     p = run({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2", "MASTER_ADDR": "127.0.0.1", "MASTER_PORT": "29599"})
     assert p.returncode == 0
     assert not [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_own_arm_prints_one_contract_line():
+    """bench.py on the GPU (short run): every key the contract names, the launch count it claims,
+    the byte counts of the end-to-end path as the library counted them."""
+    p = subprocess.run([sys.executable, "bench.py", "--steps", "5", "--warmup", "3"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert "impl" not in d and d["metric"] == "graph_eval_mpixel_per_s" and d["steps"] == 5 and d["warmup"] >= 3
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
+    assert d["config"]["workload"].startswith("configs[1]") and "model" not in d["config"]
+    assert d["gpu_launches"] == 5                                   # one fused kernel per step
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and 0.3 < r["frac"] <= 1.05 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 6 * 4096 * 4096 * 4 and e["d2h_bytes_per_step"] == 4096 * 4096 * 4
+    assert 0 < e["value"] < d["value"]
+    assert e["u8_inputs"]["h2d_bytes_per_step"] == 2 * 4096 * 4096 * 4
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
