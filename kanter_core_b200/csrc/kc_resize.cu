@@ -457,42 +457,39 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
 // outputs and the rows are independent accumulation chains.  Same tap order and clamp as
 // kc_resize_h_kernel.
 
-// ROWS rows of a 256-output tile per CTA; eight loads per thread are in flight during staging whatever ROWS is.
-template <bool EXACT, int ROWS>
+// Four rows of a 256-output tile per CTA.  The stretch of the intermediate those outputs read is staged in shared
+// memory TRANSPOSED -- one 16-byte slot per source column holding its four rows -- so a tap costs one LDS.128 and
+// four FMAs (the row-major layout needed four LDS and the index arithmetic four times over: 14.6 M warp
+// instructions for 8192x1024 -> 1024x1024, issue slots 59 % busy).  A spare slot after every eight columns
+// spreads the stride-R reads of adjacent outputs over the banks.
+constexpr int HT_ROWS = 4;
+__device__ __forceinline__ uint32_t ht_slot(uint32_t i) { return i + (i >> 3); }
+
+template <bool EXACT>
 __global__ void __launch_bounds__(256) kc_resize_h_tile_kernel(const float* __restrict__ tmp, uint32_t sw, float* __restrict__ dst, uint32_t dw,
                                                                uint32_t dh, const uint32_t* __restrict__ left, const uint32_t* __restrict__ count,
-                                                               const float* __restrict__ wh, uint32_t pitch, float clo, float chi) {
-    extern __shared__ __align__(16) float htile[];                 // [ROWS][pitch]
+                                                               const float* __restrict__ wh, float clo, float chi) {
+    extern __shared__ __align__(16) float4 htile4[];               // [ht_slot(ncol)] x (4 rows)
     const uint32_t ox0 = blockIdx.x * 256, oxl = min(ox0 + 256, dw) - 1;
-    const uint32_t y0 = blockIdx.y * ROWS, nrow = min((uint32_t)ROWS, dh - y0);
+    const uint32_t y0 = blockIdx.y * HT_ROWS, nrow = min((uint32_t)HT_ROWS, dh - y0);
     const uint32_t c0 = __ldg(left + ox0), ncol = __ldg(left + oxl) + __ldg(count + oxl) - c0;
-    // staging: eight loads per thread in flight together (ROWS rows of CB columns; the intermediate comes from L2)
-    constexpr int CB = 8 / ROWS;
-    for (uint32_t i0 = threadIdx.x; i0 < ncol; i0 += 256 * CB) {
-        float v[CB][ROWS];
-#pragma unroll
-        for (int cb = 0; cb < CB; ++cb) {
-            const uint32_t i = min(i0 + 256u * cb, ncol - 1);
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r) v[cb][r] = __ldg(tmp + (size_t)(y0 + min((uint32_t)r, nrow - 1)) * sw + c0 + i);
-        }
-#pragma unroll
-        for (int cb = 0; cb < CB; ++cb) {
-            const uint32_t i = i0 + 256u * cb;
-            if (i < ncol) {
-                const uint32_t si = i + (i >> 5);
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) htile[(size_t)r * pitch + si] = v[cb][r];
-            }
-        }
+    const float* r0 = tmp + (size_t)y0 * sw + c0;
+    const float* r1 = tmp + (size_t)(y0 + min(1u, nrow - 1)) * sw + c0;   // rows past nrow: duplicates, never stored
+    const float* r2 = tmp + (size_t)(y0 + min(2u, nrow - 1)) * sw + c0;
+    const float* r3 = tmp + (size_t)(y0 + min(3u, nrow - 1)) * sw + c0;
+    // staging: eight loads per thread in flight together (two columns x four rows; the intermediate comes from L2)
+    for (uint32_t i0 = threadIdx.x; i0 < ncol; i0 += 512) {
+        const uint32_t ia = i0, ib = min(i0 + 256u, ncol - 1);
+        const float4 va = make_float4(__ldg(r0 + ia), __ldg(r1 + ia), __ldg(r2 + ia), __ldg(r3 + ia));
+        const float4 vb = make_float4(__ldg(r0 + ib), __ldg(r1 + ib), __ldg(r2 + ib), __ldg(r3 + ib));
+        htile4[ht_slot(ia)] = va;
+        if (i0 + 256u < ncol) htile4[ht_slot(i0 + 256u)] = vb;
     }
     __syncthreads();
     const uint32_t ox = ox0 + threadIdx.x;
     if (ox > oxl) return;
     const uint32_t l = __ldg(left + ox) - c0, n = __ldg(count + ox);
-    float acc[ROWS];
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) acc[r] = 0.0f;
+    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const float* wp = wh + ox;
     constexpr int WB = 8;                                          // tap weights fetched WB at a time
     for (uint32_t j0 = 0; j0 < n; j0 += WB) {
@@ -502,19 +499,18 @@ __global__ void __launch_bounds__(256) kc_resize_h_tile_kernel(const float* __re
 #pragma unroll
         for (int k = 0; k < WB; ++k) {
             if (j0 + k < n) {
-                const uint32_t i = l + j0 + k;
-                const float* sp = htile + i + (i >> 5);
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) acc[r] = tap<EXACT>(acc[r], sp[(size_t)r * pitch], w[k]);   // rows past nrow: duplicates, never stored
+                const float4 sv = htile4[ht_slot(l + j0 + k)];
+                acc.x = tap<EXACT>(acc.x, sv.x, w[k]);
+                acc.y = tap<EXACT>(acc.y, sv.y, w[k]);
+                acc.z = tap<EXACT>(acc.z, sv.z, w[k]);
+                acc.w = tap<EXACT>(acc.w, sv.w, w[k]);
             }
         }
     }
+    const float a[HT_ROWS] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-        if ((uint32_t)r < nrow) {
-            const float a = acc[r];
-            dst[(size_t)(y0 + r) * dw + ox] = a < clo ? clo : (a > chi ? chi : a);   // image::math::utils::clamp keeps NaN
-        }
+    for (int r = 0; r < HT_ROWS; ++r)
+        if ((uint32_t)r < nrow) dst[(size_t)(y0 + r) * dw + ox] = a[r] < clo ? clo : (a[r] > chi ? chi : a[r]);   // image::math::utils::clamp keeps NaN
 }
 
 // ---------------------------------------------------------------------------
@@ -768,24 +764,14 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
         else kc_resize_v_kernel<false><<<grid, 256, 0, ctx->stream>>>(src, sw, tmp, dh, tv->d_left, tv->d_count, tv->d_weights);
     }
     const uint32_t hwin = max_window(*th, 256);
-    const uint32_t hpitch = hwin + (hwin >> 5) + 1;
-    // rows per CTA: measured on 8192x1024 -> 1024x1024 (Lanczos3): 8 rows 0.0323 ms, 4 rows 0.0307 ms, 2 rows 0.0332 ms
-    // (KC_HT_ROWS overrides for sweeps)
-    static const int env_ht = getenv("KC_HT_ROWS") ? atoi(getenv("KC_HT_ROWS")) : 0;
-    const int ht_rows = (env_ht == 2 || env_ht == 4 || env_ht == 8) ? env_ht : 4;
-    const size_t hsmem = sizeof(float) * (size_t)ht_rows * hpitch;
-    const uint32_t hgy = (dh + ht_rows - 1) / ht_rows;
+    const size_t hsmem = sizeof(float4) * ((size_t)hwin + (hwin >> 3) + 2);
+    const uint32_t hgy = (dh + HT_ROWS - 1) / HT_ROWS;
     if (!no_march && th->max_taps > (uint32_t)FS_MAXT && hsmem <= 96 * 1024 && hgy <= 65535u) {
-        const void* fn = nullptr;
-#define KC_HT(R) (exact ? (const void*)kc_resize_h_tile_kernel<true, R> : (const void*)kc_resize_h_tile_kernel<false, R>)
-        fn = ht_rows == 8 ? KC_HT(8) : ht_rows == 4 ? KC_HT(4) : KC_HT(2);
-#undef KC_HT
-        KC_TRY(kc_ensure_smem_attr(ctx, fn, 96 * 1024));
+        KC_TRY(kc_ensure_smem_attr(ctx, exact ? (const void*)kc_resize_h_tile_kernel<true> : (const void*)kc_resize_h_tile_kernel<false>, 96 * 1024));
         dim3 grid((dw + 255) / 256, hgy);
         KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
-        void* hargs[] = {(void*)&tmp, (void*)&sw, (void*)&dst, (void*)&dw, (void*)&dh, (void*)&th->d_left, (void*)&th->d_count,
-                         (void*)&th->d_weights, (void*)&hpitch, (void*)&clo, (void*)&chi};
-        cudaLaunchKernel(fn, grid, dim3(256), hargs, hsmem, ctx->stream);   // a failure is picked up below, after tmp is handed back
+        if (exact) kc_resize_h_tile_kernel<true><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, clo, chi);
+        else kc_resize_h_tile_kernel<false><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, clo, chi);
     } else {
         dim3 grid((dw + 255) / 256, std::min<uint32_t>(dh, 65535u));
         KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
