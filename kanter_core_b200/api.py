@@ -26,10 +26,16 @@ class NodeId(int):
     def __repr__(self):
         return "NodeId(%d)" % int(self)
 
+    def as_usize(self):
+        return int(self)
+
 
 class SlotId(int):
     def __repr__(self):
         return "SlotId(%d)" % int(self)
+
+    def as_usize(self):
+        return int(self)
 
 
 class EmbeddedSlotDataId(int):  # src/node/embed.rs:13-14
@@ -384,6 +390,24 @@ class _GraphView:
     def input_names(self):
         return [n.node_type.payload for n in self.nodes if n.node_type.is_input()]
 
+    def input_nodes(self):  # node_graph.rs:191-196
+        return [n for n in self.nodes if n.node_type.is_input()]
+
+    def output_nodes(self):  # :198-203
+        return [n for n in self.nodes if n.node_type.is_output()]
+
+    def edge_indices_node(self, node_id):  # :351-361
+        self.has_node_with_id(node_id)
+        return [i for i, e in enumerate(self.edges) if e.output_id == node_id or e.input_id == node_id]
+
+    def edge_indices_slot(self, node_id, side, slot_id):  # :364-374
+        if int(side) == int(Side.Input):
+            return [i for i, e in enumerate(self.edges) if e.input_id == node_id and e.input_slot == slot_id]
+        return [i for i, e in enumerate(self.edges) if e.output_id == node_id and e.output_slot == slot_id]
+
+    def slot_occupied(self, node_id, side, slot_id):  # :449-460
+        return bool(self.edge_indices_slot(node_id, side, slot_id))
+
     def export_json_string(self):
         p = C.c_void_p()
         call("kc_graph_export_json", self._graph_handle(), C.byref(p))
@@ -477,6 +501,14 @@ class NodeGraph(_GraphView):
         finally:
             _lib.lib.kc_free(p)
 
+    def set_image_node_path(self, node_id, path):  # :65-83: only an Image node takes a path
+        n = self.node(node_id)
+        if n.node_type.kind != _lib.NODE_IMAGE:
+            raise TexProError(5, "node %d is not an Image node" % node_id)
+        n.node_type = NodeType.Image(str(path))
+        d, keep = n._desc()
+        call("kc_graph_set_node", self._h, C.byref(d))
+
     def set_mix_type(self, node_id, mix_type):  # :48-63
         n = self.node(node_id)
         if n.node_type.kind != _lib.NODE_MIX:
@@ -546,6 +578,33 @@ class SlotImage:
             call("kc_context_synchronize", tex_pro._ctx._h)
         return SlotImage(tex_pro._ctx, im)
 
+    @staticmethod
+    def from_buffers_rgba(tex_pro, buffers):  # :66-88: exactly four planes
+        if len(buffers) != 4:
+            raise TexProError(4, "from_buffers_rgba needs 4 buffers, got %d" % len(buffers))
+        return SlotImage.from_planes(tex_pro, list(buffers))
+
+    @staticmethod
+    def from_buffers_rgb(tex_pro, buffers):  # :90-102: three planes and an alpha of 1.0
+        if len(buffers) != 3:
+            raise TexProError(4, "from_buffers_rgb needs 3 buffers, got %d" % len(buffers))
+        b = [np.ascontiguousarray(x, dtype=np.float32) for x in buffers]
+        return SlotImage.from_planes(tex_pro, b + [np.ones_like(b[0])])
+
+    def from_self(self):  # :104-114: the planes are immutable, so a copy is another reference
+        im = kc_image()
+        C.memmove(C.byref(im), C.byref(self._im), C.sizeof(kc_image))
+        call("kc_image_retain", C.byref(im))
+        return SlotImage(self._ctx, im)
+
+    def in_memory(self):  # SlotData::in_memory, src/slot_data.rs:70-78: no plane sits in the spill queue's host memory
+        for c in range(4 if self.is_rgba() else 1):
+            v = C.c_int32()
+            call("kc_plane_in_memory", self._im.planes[c], C.byref(v))
+            if not v.value:
+                return False
+        return True
+
     def is_rgba(self):
         return self._im.kind == _lib.IMAGE_RGBA
 
@@ -604,6 +663,12 @@ class SlotData:  # src/slot_data.rs:35-39
 
     def size(self):
         return self.image.size()
+
+    def from_self(self):  # :62-64: a new SlotData over the same (immutable, shared) planes
+        return SlotData(self.node_id, self.slot_id, self.image.from_self())
+
+    def in_memory(self):  # :70-78
+        return self.image.in_memory()
 
 
 class _Context:
@@ -676,6 +741,23 @@ class TextureProcessor:
 
     def push_live_graph(self, live_graph):  # :65-69
         self._live_graphs.append(live_graph)
+
+    def live_graph(self):  # :71-73
+        return self._live_graphs
+
+    @staticmethod
+    def buffer_rgba(live_graph, node_id, slot_id):  # :75-81: await_clean_write(..).buffer_rgba(..)
+        return LiveGraph.await_clean_write(live_graph, node_id).buffer_rgba(node_id, slot_id)
+
+    @staticmethod
+    def await_slot_data_size(live_graph, node_id, slot_id):  # :91-105: prioritise the node, wait for its slot, return the size
+        return LiveGraph.await_clean_read(live_graph, node_id).slot_data_size(node_id, slot_id)
+
+    def processing_node_count(self):  # :107-109: nodes being processed right now; evaluation here is synchronous per request
+        return 0
+
+    def set_max_processing_nodes(self, count):  # :111-114: a limit on concurrent node threads; there are none to limit
+        self._max_processing_nodes = int(count)
 
     def set_math_mode(self, mode):
         call("kc_context_set_math_mode", self._ctx._h, int(mode))
@@ -871,6 +953,7 @@ class LiveGraph(_GraphView):
         return live_graph
 
     await_clean_write = await_clean_read  # :164-179: same wait, a write guard in the reference
+
 
     def _id_list(self, fn, *args):
         n = C.c_size_t()

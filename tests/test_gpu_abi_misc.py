@@ -187,3 +187,31 @@ def test_context_on_the_callers_stream():
     torch.cuda.synchronize()
     with torch.cuda.stream(s):                                  # the stream is still the caller's, and usable
         assert float((ta + 1).sum()) > 0
+
+
+def test_remaining_reference_surface(tex_pro):
+    """SlotImage::from_buffers_rgb/rgba, from_self, SlotData::in_memory/from_self, TextureProcessor::buffer_rgba and
+    await_slot_data_size (src/slot_image.rs:66-114, src/slot_data.rs:62-78, src/texture_processor.rs:75-105)."""
+    r, g, b, a = (rnd(50 + k, 12, 10) for k in range(4))
+    rgb = kc.SlotImage.from_buffers_rgb(tex_pro, [r, g, b])
+    got = rgb.planes()
+    assert rgb.is_rgba() and np.array_equal(got[0], r) and np.array_equal(got[2], b) and np.array_equal(got[3], np.ones_like(r))
+    rgba = kc.SlotImage.from_buffers_rgba(tex_pro, [r, g, b, a])
+    assert np.array_equal(rgba.planes()[3], a)
+    for bad, n in ((kc.SlotImage.from_buffers_rgb, 4), (kc.SlotImage.from_buffers_rgba, 3)):
+        with pytest.raises(kc.TexProError) as e:
+            bad(tex_pro, [r] * n)
+        assert e.value.kind == "InvalidBufferCount"
+    twin = rgba.from_self()
+    assert np.array_equal(twin.planes()[1], g) and twin.in_memory()
+    sd = kc.SlotData.new(3, 1, rgba).from_self()
+    assert int(sd.node_id) == 3 and int(sd.slot_id) == 1 and sd.in_memory() and sd.size() == kc.Size(10, 12)
+    lg = tex_pro.new_live_graph()
+    v = lg.add_node(kc.Node.new(kc.NodeType.Value(0.5)))
+    o = lg.add_node(kc.Node.new(kc.NodeType.OutputGray("o")))
+    lg.connect(v, o, kc.SlotId(0), kc.SlotId(0))
+    assert kc.TextureProcessor.await_slot_data_size(lg, o, kc.SlotId(0)) == kc.Size(1, 1)
+    px = np.asarray(kc.TextureProcessor.buffer_rgba(lg, o, kc.SlotId(0))).reshape(-1)
+    assert list(px[:4]) == [127, 127, 127, 255]            # read_dirty_read's known answer for Value(0.5)
+    assert tex_pro.processing_node_count() == 0
+    tex_pro.set_max_processing_nodes(4)

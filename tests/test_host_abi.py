@@ -354,3 +354,27 @@ def test_kernel_generator_compiles_with_nvrtc():
             n = C.c_size_t()
             call("kc_debug_jit_compile", arr, len(tape), exact, v, ctas, C.byref(n))
             assert n.value > 10000, (name, exact, v)
+
+
+def test_graph_queries_of_the_reference_surface():
+    """edge_indices_node / edge_indices_slot / slot_occupied / input_nodes / output_nodes /
+    set_image_node_path (src/node_graph.rs:65-83,191-203,351-374,449-460)."""
+    g = NodeGraph.new()
+    i = g.add_node(Node.new(NodeType.InputGray("in")))
+    im = g.add_node(Node.new(NodeType.Image("a.png")))
+    m = g.add_node(Node.new(NodeType.Mix(MixType.Add)))
+    o = g.add_node(Node.new(NodeType.OutputGray("out")))
+    g.connect(i, m, SlotId(0), SlotId(0))
+    g.connect(im, m, SlotId(0), SlotId(1))
+    g.connect(m, o, SlotId(0), SlotId(0))
+    assert g.edge_indices_node(m) == [0, 1, 2] and g.edge_indices_node(i) == [0]
+    assert g.edge_indices_slot(m, Side.Input, SlotId(1)) == [1] and g.edge_indices_slot(m, Side.Output, SlotId(0)) == [2]
+    assert g.slot_occupied(m, Side.Input, SlotId(0)) and not g.slot_occupied(o, Side.Output, SlotId(0))
+    assert [int(n.node_id) for n in g.input_nodes()] == [int(i)] and [int(n.node_id) for n in g.output_nodes()] == [int(o)]
+    with pytest.raises(TexProError):
+        g.edge_indices_node(kc.NodeId(77))
+    g.set_image_node_path(im, "b.png")
+    assert g.node(im).node_type.payload == "b.png"
+    with pytest.raises(TexProError):
+        g.set_image_node_path(m, "c.png")
+    assert kc.NodeId(5).as_usize() == 5 and SlotId(3).as_usize() == 3
