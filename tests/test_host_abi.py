@@ -378,3 +378,25 @@ def test_graph_queries_of_the_reference_surface():
     with pytest.raises(TexProError):
         g.set_image_node_path(m, "c.png")
     assert kc.NodeId(5).as_usize() == 5 and SlotId(3).as_usize() == 3
+
+
+def test_image_handles_without_a_device():
+    """SlotImage::from_self / SlotData::from_self / in_memory (src/slot_image.rs:104-114, src/slot_data.rs:62-78) on
+    constant descriptors, which need no device: a copy is another reference on the same immutable planes."""
+    from kanter_core_b200._lib import call, kc_image
+    im = kc_image()
+    im.kind, im.width, im.height = 1, 7, 5
+    for c in range(4):
+        pl = C.c_void_p()
+        call("kc_plane_from_value", None, 7, 5, 0.25 * c, C.byref(pl))
+        im.planes[c] = pl
+    img = kc.SlotImage(None, im)
+    assert img.is_rgba() and img.size() == Size(7, 5) and img.in_memory()
+    twin = img.from_self()
+    assert twin._im.planes[2] == img._im.planes[2]              # the same plane object, one more reference
+    sd = kc.SlotData.new(4, 2, img).from_self()
+    assert (int(sd.node_id), int(sd.slot_id)) == (4, 2) and sd.in_memory() and sd.size() == Size(7, 5)
+    v, is_c = C.c_float(), C.c_int32()
+    del img, twin                                               # two of the three references go; the plane must survive
+    call("kc_plane_is_constant", sd.image._im.planes[3], C.byref(is_c), C.byref(v))
+    assert is_c.value == 1 and v.value == 0.75
