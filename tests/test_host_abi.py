@@ -400,3 +400,9 @@ def test_image_handles_without_a_device():
     del img, twin                                               # two of the three references go; the plane must survive
     call("kc_plane_is_constant", sd.image._im.planes[3], C.byref(is_c), C.byref(v))
     assert is_c.value == 1 and v.value == 0.75
+    import numpy as np
+    a = np.zeros((2, 2), np.float32)
+    for make, n in ((kc.SlotImage.from_buffers_rgb, 4), (kc.SlotImage.from_buffers_rgba, 3)):   # src/slot_image.rs:66-69,90-93
+        with pytest.raises(TexProError) as e:
+            make(None, [a] * n)
+        assert e.value.kind == "InvalidBufferCount"
