@@ -67,3 +67,30 @@ def test_oracle_resize_weights_triangle_upsample():
     for f in range(5):
         l, c, ww = oracle.resize_weights(1, 256, f)
         assert (c == 1).all() and (ww[:, 0] == 1.0).all() and (l == 0).all()
+
+
+@pytest.mark.parametrize("filt, pil_filter", [(1, "BILINEAR"), (2, "BICUBIC"), (4, "LANCZOS")])
+@pytest.mark.parametrize("dst", [(120, 156), (20, 26), (57, 33), (40, 52)])
+def test_oracle_resize_agrees_with_an_independent_implementation(filt, pil_filter, dst):
+    """No golden of the reference pins CatmullRom / Lanczos3 pixels or Triangle downsampling,
+    and the image crate itself cannot be built here.  Pillow's resampler is an independent implementation
+    of the same separable design (window = support x max(ratio, 1) around the pixel centre, weights
+    normalised by their sum, BICUBIC with a = -0.5 = CatmullRom): on f32 data kept inside [0, 1] the
+    oracle agrees with it to float rounding, up-, down- and mixed-sampling.  This pins the arithmetic of
+    the restated algorithm (windows, kernels, normalisation), not its bits."""
+    import numpy as np
+    from PIL import Image
+    import oracle
+    r = np.random.default_rng(5)
+    k = np.outer(np.hanning(9), np.hanning(9)).astype(np.float64)
+    noise = r.random((48, 60))
+    smooth = np.zeros((40, 52))
+    for dy in range(9):
+        for dx in range(9):
+            smooth += k[dy, dx] * noise[dy:dy + 40, dx:dx + 52]
+    src = (0.2 + 0.6 * (smooth - smooth.min()) / (smooth.max() - smooth.min())).astype(np.float32)
+    dh, dw = dst
+    got = oracle.resize_plane(src, dw, dh, filt)
+    want = np.asarray(Image.fromarray(src, mode="F").resize((dw, dh), getattr(Image, pil_filter)), dtype=np.float32)
+    assert got.shape == want.shape
+    assert float(np.abs(got - want).max()) < 2e-6
