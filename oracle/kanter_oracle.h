@@ -14,7 +14,10 @@
  * [0,1] clamp of the resize's horizontal pass: the reference delegates those to
  * the un-vendored third-party crate image 0.24.0 (Cargo.lock:237-240) and has
  * no golden that exercises them; the oracle restates that crate's published
- * algorithm (imageops/sample.rs).
+ * algorithm (imageops/sample.rs).  Independent evidence short of a pin:
+ * Triangle, CatmullRom and Lanczos3 agree with Pillow's resampler (another
+ * implementation of the same separable design) to float rounding, up- and
+ * down-sampling (tests/test_oracle_goldens.py).
  */
 #ifndef KANTER_ORACLE_H
 #define KANTER_ORACLE_H
