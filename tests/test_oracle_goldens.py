@@ -94,3 +94,59 @@ def test_oracle_resize_agrees_with_an_independent_implementation(filt, pil_filte
     want = np.asarray(Image.fromarray(src, mode="F").resize((dw, dh), getattr(Image, pil_filter)), dtype=np.float32)
     assert got.shape == want.shape
     assert float(np.abs(got - want).max()) < 2e-6
+
+
+@pytest.mark.parametrize("filt", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("dst", [(90, 31), (13, 77), (40, 52)])
+def test_oracle_resize_against_the_formula_in_float64(filt, dst):
+    """The documented algorithm of image 0.24's sample.rs written out a second time, in
+    numpy float64 with the centres and windows in float32 as the crate computes them: the C++ oracle
+    (f32 accumulation) must agree to rounding for all five filters, Gaussian and Nearest included."""
+    import numpy as np
+    import oracle
+    f32 = np.float32
+
+    def kernel(x):
+        a = abs(x)
+        if filt == 0:
+            return 1.0
+        if filt == 1:
+            return max(0.0, 1.0 - a)
+        if filt == 2:   # bc_cubic, B = 0, C = 0.5
+            if a < 1:
+                return ((12 - 6 * 0.5) * a ** 3 + (-18 + 6 * 0.5) * a ** 2 + 6) / 6
+            if a < 2:
+                return ((-6 * 0.5) * a ** 3 + (30 * 0.5) * a ** 2 + (-48 * 0.5) * a + 24 * 0.5) / 6
+            return 0.0
+        if filt == 3:   # gaussian(x, r = 0.5), not truncated at the support
+            return float(np.exp(-x * x / (2 * 0.25)) / (np.sqrt(2 * np.pi) * 0.5))
+        if a >= 3:
+            return 0.0
+        s = lambda t: 1.0 if t == 0 else float(np.sin(np.pi * t) / (np.pi * t))
+        return s(x) * s(x / 3)
+
+    support = [0.0, 1.0, 2.0, 3.0, 3.0][filt]
+
+    def axis(src_len, new_len):
+        ratio = f32(src_len) / f32(new_len)
+        sratio = max(ratio, f32(1.0))
+        ssup = f32(support) * sratio
+        out = []
+        for o in range(new_len):
+            c = (f32(o) + f32(0.5)) * ratio
+            left = int(min(max(np.floor(c - ssup), 0), src_len - 1))
+            right = int(min(max(np.ceil(c + ssup), left + 1), src_len))
+            c = c - f32(0.5)
+            w = np.array([kernel((f32(i) - c) / sratio) for i in range(left, right)], dtype=np.float64)
+            out.append((left, w / w.sum()))
+        return out
+
+    r = np.random.default_rng(8)
+    src = (0.1 + 0.8 * r.random((40, 52))).astype(np.float32)
+    dh, dw = dst
+    tmp = np.stack([sum(wk * src[l + k].astype(np.float64) for k, wk in enumerate(w)) for l, w in axis(40, dh)])
+    want = np.stack([sum(wk * tmp[:, l + k] for k, wk in enumerate(w)) for l, w in axis(52, dw)], axis=1)
+    want = np.clip(want, 0.0, 1.0)
+    got = oracle.resize_plane(src, dw, dh, filt)
+    assert got.shape == want.shape
+    assert float(np.abs(got - want).max()) < 5e-6
