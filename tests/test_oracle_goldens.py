@@ -150,3 +150,29 @@ def test_oracle_resize_against_the_formula_in_float64(filt, dst):
     got = oracle.resize_plane(src, dw, dh, filt)
     assert got.shape == want.shape
     assert float(np.abs(got - want).max()) < 5e-6
+
+
+def test_oracle_height_to_normal_against_the_formula_in_float64():
+    """height_to_normal::process (src/node/height_to_normal.rs:16-77) written out in numpy float64:
+    tangent (1/W, 0, h - left), bitangent (0, 1/H, up - h), both normalised, their cross product
+    normalised, * 0.5 + 0.5, with the toroidal wrap of wrapping_sample_subtract.  The golden pins the
+    oracle at 8-bit precision only; this pins its f32 planes to rounding."""
+    import numpy as np
+    import oracle
+    r = np.random.default_rng(9)
+    h, w = 37, 53
+    hgt = r.random((h, w)).astype(np.float32)
+    H = hgt.astype(np.float64)
+    left = np.roll(H, 1, axis=1)
+    up = np.roll(H, 1, axis=0)
+    t = np.stack([np.full_like(H, 1.0 / w), np.zeros_like(H), H - left], axis=-1)
+    b = np.stack([np.zeros_like(H), np.full_like(H, 1.0 / h), up - H], axis=-1)
+    t /= np.linalg.norm(t, axis=-1, keepdims=True)
+    b /= np.linalg.norm(b, axis=-1, keepdims=True)
+    n = np.cross(t, b)
+    n /= np.linalg.norm(n, axis=-1, keepdims=True)
+    want = n * 0.5 + 0.5
+    got = oracle.height_to_normal(hgt)
+    assert len(got) == 3                                       # R, G, B; the node adds the alpha of 1.0
+    for c in range(3):
+        assert float(np.abs(got[c].astype(np.float64) - want[..., c]).max()) < 2e-6, c
