@@ -176,3 +176,29 @@ def test_oracle_height_to_normal_against_the_formula_in_float64():
     assert len(got) == 3                                       # R, G, B; the node adds the alpha of 1.0
     for c in range(3):
         assert float(np.abs(got[c].astype(np.float64) - want[..., c]).max()) < 2e-6, c
+
+
+def test_oracle_mix_and_gray_average_are_plain_f32_arithmetic():
+    """mix.rs:136-302 and SlotImage::as_type (slot_image.rs:242-253) are single IEEE f32 operations per
+    sample: the oracle equals numpy's float32 arithmetic bit for bit (pow goes through libm's powf and is
+    compared to rounding), including 0/0, x/0 and negative bases."""
+    import numpy as np
+    import oracle
+    r = np.random.default_rng(10)
+    a = (r.random((33, 47)) * 3 - 1).astype(np.float32)
+    b = (r.random((33, 47)) * 3 - 1).astype(np.float32)
+    a[0, :4] = [0.0, 1.0, -2.0, 0.0]
+    b[0, :4] = [0.0, 0.0, 0.5, 3.0]
+    with np.errstate(all="ignore"):
+        for op, fn in ((0, np.add), (1, np.subtract), (2, np.multiply), (3, np.divide)):
+            got, want = oracle.mix_plane(op, a, b), fn(a, b)
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+            assert np.array_equal(got[~np.isnan(got)].view(np.uint32), want[~np.isnan(want)].view(np.uint32)), op
+        got = oracle.mix_plane(4, a, b).astype(np.float64)
+        want = np.power(a.astype(np.float64), b.astype(np.float64))
+        fin = np.isfinite(want) & np.isfinite(got)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert (np.abs(got[fin] - want[fin]) <= 1.5e-7 * np.abs(want[fin]) + 1e-45).all()
+        assert got[0, 0] == 1.0                                   # 0^0 = 1 (pinned by pow_node_*.png too)
+    g = oracle.rgb_to_gray(a, b, a)
+    assert np.array_equal(g.view(np.uint32), (((a + b) + a) / np.float32(3.0)).view(np.uint32))
