@@ -202,3 +202,25 @@ def test_oracle_mix_and_gray_average_are_plain_f32_arithmetic():
         assert got[0, 0] == 1.0                                   # 0^0 = 1 (pinned by pow_node_*.png too)
     g = oracle.rgb_to_gray(a, b, a)
     assert np.array_equal(g.view(np.uint32), (((a + b) + a) / np.float32(3.0)).view(np.uint32))
+
+
+def test_oracle_srgb_export_against_the_formula_in_float64():
+    """SlotImage::to_u8_srgb (src/slot_image.rs:172-207) + srgb_to_linear (src/slot_data.rs:100-109): no test of the
+    reference calls it, so the oracle's bytes are checked against the formula in float64 - equal except where
+    the f32 result sits within rounding of a truncation boundary, and then one level apart."""
+    import numpy as np
+    import oracle
+    r = np.random.default_rng(11)
+    P = [(r.random((64, 80)) * 1.4 - 0.2).astype(np.float32) for _ in range(4)]
+    P[0].flat[:256] = np.arange(256, dtype=np.float32) / np.float32(255.0)
+    got = oracle.to_u8(P, True).astype(np.int32)
+    want = np.empty_like(got)
+    for c in range(4):
+        v = np.clip(P[c].astype(np.float64), 0.0, 1.0)
+        if c < 3:
+            v = np.where(v <= 0.0, v, np.where(v <= np.float64(np.float32(0.04045)), v / np.float64(np.float32(12.92)),
+                                               ((v + np.float64(np.float32(0.055))) / np.float64(np.float32(1.055))) ** 2.4))
+        want[..., c] = np.minimum(v * 255.0, 255.0).astype(np.int32)
+    assert np.abs(got - want).max() <= 1
+    assert (got != want).mean() < 1e-3
+    assert np.array_equal(got[..., 3], want[..., 3])             # alpha stays linear
