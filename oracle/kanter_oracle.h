@@ -9,7 +9,9 @@
  *
  * Parity status: PINNED for everything the reference's own goldens exercise
  * (all 22 golden checks of tests/integration_tests.rs reproduce byte-exactly,
- * see tests/test_oracle_goldens.py).  UNPINNED for the Nearest / CatmullRom /
+ * see tests/test_oracle_goldens.py).  UNPINNED for the sRGB export (to_u8_srgb:
+ * no test of the reference calls it; checked against the formula in float64),
+ * for the Nearest / CatmullRom /
  * Gaussian / Lanczos3 resize filters, for Triangle down-sampling and for the
  * [0,1] clamp of the resize's horizontal pass: the reference delegates those to
  * the un-vendored third-party crate image 0.24.0 (Cargo.lock:237-240) and has
