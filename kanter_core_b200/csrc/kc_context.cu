@@ -212,7 +212,7 @@ extern "C" int32_t kc_context_synchronize(kc_context* ctx) try {
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
     KC_CUDA(cudaStreamSynchronize(ctx->download_stream));
     ctx->dl_pending = false;
-    return KC_OK;
+    return kck_halo_check_timeouts(ctx);
 } KC_ABI_CATCH
 extern "C" int32_t kc_context_device(const kc_context* ctx, int32_t* device) try {
     if (!ctx || !device) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
@@ -623,6 +623,10 @@ extern "C" int32_t kc_plane_retain(kc_plane* p) try {
 extern "C" int32_t kc_plane_release(kc_plane* p) try {
     if (!p) return KC_OK;
     kc_context* ctx = p->ctx;
+    if (!ctx) {             // a context-less constant descriptor (kc_plane_from_value(NULL, ..)): no device state to guard
+        kcp_release(p);
+        return KC_OK;
+    }
     KcGuard g(ctx);
     kcp_release(p);
     return KC_OK;
@@ -668,7 +672,7 @@ extern "C" int32_t kc_plane_download(kc_plane* p, float* host) try {
     KC_CUDA(cudaMemcpyAsync(host, p->dptr, p->bytes(), cudaMemcpyDeviceToHost, p->ctx->stream));
     KC_CUDA(cudaStreamSynchronize(p->ctx->stream));
     p->ctx->bytes_d2h += p->bytes();
-    return KC_OK;
+    return kck_halo_check_timeouts(p->ctx);
 } KC_ABI_CATCH
 
 // ---------------------------------------------------------------------------
@@ -776,7 +780,10 @@ extern "C" int32_t kc_image_release(kc_image* img) try {
     kc_context* ctx = nullptr;
     for (int c = 0; c < 4; ++c)
         if (img->planes[c]) ctx = img->planes[c]->ctx;
-    if (!ctx) return KC_OK;
+    if (!ctx) {             // only context-less constant descriptors (or nothing): release them all the same
+        kci_release(img);
+        return KC_OK;
+    }
     KcGuard g(ctx);
     kci_release(img);
     return KC_OK;
@@ -804,7 +811,7 @@ extern "C" int32_t kc_image_download(kc_context* ctx, const kc_image* in, float*
         }
     }
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
-    return KC_OK;
+    return kck_halo_check_timeouts(ctx);
 } KC_ABI_CATCH
 
 extern "C" int32_t kc_image_materialize(kc_context* ctx, const kc_image* in, int32_t include_constants) try {
@@ -869,7 +876,7 @@ extern "C" int32_t kc_image_to_u8(kc_context* ctx, const kc_image* in, int32_t s
     KC_TRY(to_u8_enqueue(ctx, in, srgb, host_rgba8));
     cudaError_t e = cudaEventSynchronize(ctx->ev_dl_done);
     if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
-    return KC_OK;
+    return kck_halo_check_timeouts(ctx);
 } KC_ABI_CATCH
 
 extern "C" int32_t kc_image_to_u8_async(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) try {

@@ -129,20 +129,16 @@ int32_t img_mix(kc_context* ctx, int mix_type, const Img* left, const Img* right
         return KC_OK;
     }
     const int np = l.rgba() ? 3 : 1;
-    for (int c = 0; c < np; ++c) {
-        const kc_plane *a = l.im.planes[c], *b = r.im.planes[c];
-        if (a->kind != KC_PLANE_CONST && b->kind != KC_PLANE_CONST && (a->w != b->w || a->h != b->h))
-            KC_FAIL(KC_ERR_GENERIC, "mix: operand sizes differ (%ux%u vs %ux%u); resize first", a->w, a->h, b->w, b->h);
-    }
+    // The result has the LEFT image's size (ImageBuffer::from_fn(size.width, ..), :140) and the reference reads
+    // pixel (x, y) of BOTH operands -- get_pixel panics out of bounds -- so every operand plane, constant
+    // descriptors included, must have exactly that size: an error here, never a read past a smaller buffer.
+    for (int c = 0; c < np; ++c)
+        for (const kc_plane* q : {(const kc_plane*)l.im.planes[c], (const kc_plane*)r.im.planes[c]})
+            if (q->w != l.w() || q->h != l.h())
+                KC_FAIL(KC_ERR_GENERIC, "mix: operand sizes differ (%ux%u vs %ux%u); resize first", l.w(), l.h(), q->w, q->h);
     Img res;
     res.im.kind = l.rgba() ? KC_IMAGE_RGBA : KC_IMAGE_GRAY;
-    for (int c = 0; c < np; ++c) {
-        kc_plane* p = lazy_op(ctx, mix_type, l.im.planes[c], r.im.planes[c]);
-        // the result has the LEFT image's size (ImageBuffer::from_fn(size.width, ..), :140)
-        p->w = l.w();
-        p->h = l.h();
-        res.set(c, p);
-    }
+    for (int c = 0; c < np; ++c) res.set(c, lazy_op(ctx, mix_type, l.im.planes[c], r.im.planes[c]));
     if (l.rgba()) res.set(3, kcp_new_const(ctx, l.w(), l.h(), 1.0f));  // :203-212
     KC_TRY(force_if_eager(ctx, res));
     out = std::move(res);
@@ -844,7 +840,9 @@ int32_t kc_height_to_normal_strip_peer(kc_context* ctx, const kc_image* strip, c
 int32_t kc_plane_copy_rows(kc_context* ctx, kc_plane* dst, uint32_t dst_row, kc_plane* src, uint32_t src_row, uint32_t rows) try {
     if (!ctx || !dst || !src) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (dst->kind != KC_PLANE_DEVICE && dst->kind != KC_PLANE_SPILLED) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "destination has no device storage");
-    if (dst->w != src->w || dst_row + rows > dst->h || src_row + rows > src->h) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "row range out of bounds");
+    // row + rows is not formed: it wraps in 32 bits (dst_row = 0xffffffff, rows = 2 used to pass)
+    if (dst->w != src->w || dst_row > dst->h || rows > dst->h - dst_row || src_row > src->h || rows > src->h - src_row)
+        KC_FAIL(KC_ERR_INVALID_ARGUMENT, "row range out of bounds");
     KcGuard g(ctx);
     KcPin pin;
     KC_TRY(kcp_reload(dst->ctx, dst));

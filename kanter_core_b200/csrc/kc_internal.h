@@ -157,6 +157,10 @@ struct kc_context {
     struct TimedLaunch { int kind; cudaEvent_t start, stop; };
     std::vector<TimedLaunch> timed;
     std::vector<cudaEvent_t> event_pool;
+    // peer halo mailboxes (kc_h2n.cu): once a context has waited on a peer's flag, every synchronising call
+    // checks the device's time-out counter and fails instead of handing back a strip computed from a stale row
+    bool halo_used = false;
+    uint32_t halo_timeouts_seen = 0;
 };
 
 // kernel kinds for kc_context_timing_read
@@ -323,6 +327,8 @@ struct kc_halo_link;
 int32_t kck_halo_read_args(const kc_halo_link* inbox, uint64_t step, const float** halo, const unsigned long long** flag);
 int32_t kck_halo_ack(kc_context* ctx, const kc_halo_link* inbox, uint64_t step);
 uint32_t kck_halo_width(const kc_halo_link* l);
+// after a synchronisation of ctx->stream: KC_ERR_CUDA if a wait on a peer's flag gave up since the last check
+int32_t kck_halo_check_timeouts(kc_context* ctx);
 int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst,
                          uint32_t dw, uint32_t dh, int filter);
 int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,

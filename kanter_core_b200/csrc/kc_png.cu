@@ -67,6 +67,9 @@ bool unfilter(uint8_t* raw, size_t h, size_t stride, size_t bpp) {
     return true;
 }
 
+constexpr uint32_t kMaxPngSide = 1u << 16;
+constexpr uint64_t kMaxPngBytes = 1ull << 30;
+
 struct Header {
     uint32_t w = 0, h = 0;
     int depth = 0, color = 0, interlace = 0;
@@ -104,6 +107,10 @@ int32_t decode_impl(const uint8_t* data, size_t n, std::vector<uint8_t>& out, ui
         p += 12 + (size_t)len;
     }
     if (!have_hdr || hd.w == 0 || hd.h == 0) KC_FAIL(KC_ERR_IMAGE, "PNG without a valid IHDR");
+    // The header comes from outside: bound it BEFORE any arithmetic on it.  With both sides <= 2^16 and <= 8 bytes
+    // per pixel every product below fits 64 bits; the byte cap (a 16384^2 RGBA8 image) also bounds what a
+    // maximally compressed stream may ask us to allocate.
+    if (hd.w > kMaxPngSide || hd.h > kMaxPngSide) KC_FAIL(KC_ERR_IMAGE, "PNG is %u x %u: sides above %u are refused", hd.w, hd.h, kMaxPngSide);
     if (hd.depth == 16) KC_FAIL(KC_ERR_IMAGE, "16-bit PNG: the reference only takes 8-bit samples (as_flat_samples_u8)");
     const bool depth_ok = (hd.color == 0 && (hd.depth == 1 || hd.depth == 2 || hd.depth == 4 || hd.depth == 8)) ||
                           (hd.color == 3 && (hd.depth == 1 || hd.depth == 2 || hd.depth == 4 || hd.depth == 8)) ||
@@ -124,6 +131,7 @@ int32_t decode_impl(const uint8_t* data, size_t n, std::vector<uint8_t>& out, ui
             const size_t ph = (hd.h > (uint32_t)ay[i]) ? (hd.h - ay[i] + ady[i] - 1) / ady[i] : 0;
             if (pw && ph) total += ph * (stride_of(pw) + 1);
         }
+    if (total > kMaxPngBytes || (uint64_t)hd.w * hd.h * 4 > kMaxPngBytes) KC_FAIL(KC_ERR_IMAGE, "PNG of %u x %u exceeds the decoder's %llu-byte limit", hd.w, hd.h, (unsigned long long)kMaxPngBytes);
     // deflate expands by at most 1032:1, so a header that promises more pixels than the IDAT
     // bytes could ever inflate to is rejected before anything of that size is allocated
     if (total > idat.size() * 1032 + 1024) KC_FAIL(KC_ERR_IMAGE, "PNG header promises more data than its IDAT chunks can hold");

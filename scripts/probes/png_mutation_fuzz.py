@@ -101,8 +101,14 @@ def main():
             cs = chunks(bytes(d))
             pos = cs[int(r.integers(len(cs)))][0]
             d[pos:pos + 4] = struct.pack(">I", int(r.integers(1 << 32)) if r.random() < 0.5 else int(r.integers(64)))
-        else:                             # huge dimensions with a valid checksum
-            d[16:24] = struct.pack(">II", int(r.integers(1, 1 << 31)), int(r.integers(1, 1 << 31)))
+        else:                             # huge dimensions with a valid checksum; powers of two (2^31 x 2^31 wraps
+            #                               h * (stride + 1) to 2 GiB in 64 bits) and sides just past the decoder's cap
+            if r.random() < 0.5:
+                wh = (1 << int(r.integers(12, 33)), 1 << int(r.integers(12, 33)))
+                wh = tuple(min(v, 0xffffffff) + int(r.integers(-1, 2)) * (v < (1 << 32)) for v in wh)
+            else:
+                wh = (int(r.integers(1, 1 << 31)), int(r.integers(1, 1 << 31)))
+            d[16:24] = struct.pack(">II", max(0, wh[0]) & 0xffffffff, max(0, wh[1]) & 0xffffffff)
             d = bytearray(fix_crcs(bytes(d)))
         rc = decode(bytes(d))
         ok += rc == 0

@@ -215,3 +215,32 @@ def test_remaining_reference_surface(tex_pro):
     assert list(px[:4]) == [127, 127, 127, 255]            # read_dirty_read's known answer for Value(0.5)
     assert tex_pro.processing_node_count() == 0
     tex_pro.set_max_processing_nodes(4)
+
+
+def test_mix_rejects_operands_of_another_size_whatever_their_kind(tex_pro):
+    """kc_mix through the ABI: the reference reads pixel (x, y) of both operands for every pixel of the LEFT image
+    (src/node/mix.rs:136-192, get_pixel panics out of bounds).  A constant left of 64x64 with a 16x16 device or lazy
+    right used to launch a 64x64 kernel over the 16x16 buffer (advisor finding, round 1)."""
+    from kanter_core_b200 import MixType, Size
+    from kanter_core_b200._lib import TexProError
+    small = kc.SlotImage.from_planes(tex_pro, [np.full((16, 16), 0.5, np.float32)])
+    big_const = kc.SlotImage.from_value(tex_pro, Size(64, 64), 0.25, False)
+    lazy_small = kc.mix(tex_pro, MixType.Add, small, small)
+    for l, r in ((big_const, small), (big_const, lazy_small), (small, big_const), (lazy_small, big_const)):
+        with pytest.raises(TexProError):
+            kc.mix(tex_pro, MixType.Multiply, l, r)
+    same = kc.SlotImage.from_value(tex_pro, Size(16, 16), 0.25, False)
+    got = kc.mix(tex_pro, MixType.Multiply, same, lazy_small).planes()[0]
+    assert np.array_equal(got, np.full((16, 16), 0.25, np.float32))
+
+
+def test_copy_rows_bounds_do_not_wrap(tex_pro):
+    """dst_row + rows was formed in 32 bits: 0xffffffff + 2 passed the check (advisor finding, round 1)."""
+    from kanter_core_b200._lib import TexProError
+    a = kc.SlotImage.from_planes(tex_pro, [np.zeros((8, 8), np.float32)])
+    b = kc.empty_gray(tex_pro, 8, 8)
+    for args in ((0xffffffff, 0, 2), (0, 0xffffffff, 2), (7, 0, 2), (0, 7, 2), (9, 0, 0), (0, 0, 0xffffffff)):
+        with pytest.raises(TexProError):
+            kc.copy_rows(tex_pro, b, args[0], a, args[1], args[2])
+    kc.copy_rows(tex_pro, b, 6, a, 0, 2)
+    kc.copy_rows(tex_pro, b, 8, a, 8, 0)      # an empty range at the end is legal

@@ -7,6 +7,7 @@ import pytest
 import kanter_core_b200 as kc
 import oracle
 from kanter_core_b200 import MixType, Node, NodeType, ResizeFilter, ResizePolicy, Size, SlotId
+from kanter_core_b200._lib import TexProError
 
 pytestmark = pytest.mark.gpu
 
@@ -442,6 +443,28 @@ def test_height_to_normal_strips_with_peer_mailboxes(tex_pro, h, w, parts):
     assert kc.halo_timeouts(tex_pro) == 0
     for l in inboxes + boxes:
         l.close()
+
+
+def test_a_halo_row_that_never_arrives_is_an_error_not_a_stale_result():
+    """A peer that never publishes: the kernel's wait gives up after 2 s (never a hang) and the NEXT synchronising
+    call fails -- the strip was computed from whatever the mailbox held (advisor finding, round 1)."""
+    tp = kc.TextureProcessor.new()
+    try:
+        box = kc.HaloLink.outbox(tp, 64)
+        inbox = box.local_inbox()
+        img = kc.SlotImage.from_planes(tp, [rnd(77, 16, 64)])
+        out = kc.height_to_normal_strip_peer(tp, img, inbox, 1, 32)      # nobody published step 1
+        with pytest.raises(TexProError):
+            tp.synchronize()
+        tp.synchronize()                                                 # reported once; the context stays usable
+        box.publish(img, 15, 2)
+        kc.height_to_normal_strip_peer(tp, img, inbox, 2, 32).planes()
+        assert kc.halo_timeouts(tp) == 1
+        del out
+        inbox.close()
+        box.close()
+    finally:
+        tp.close()
 
 
 def test_ops_module_functions(tex_pro):

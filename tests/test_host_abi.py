@@ -406,3 +406,24 @@ def test_image_handles_without_a_device():
         with pytest.raises(TexProError) as e:
             make(None, [a] * n)
         assert e.value.kind == "InvalidBufferCount"
+
+
+def test_context_less_constant_planes_can_be_released():
+    """kc_plane_from_value(ctx = NULL) is documented as legal; releasing such a plane (or an image made only of
+    them) used to dereference the NULL context / return early without releasing (advisor finding, round 1)."""
+    from kanter_core_b200._lib import call, kc_image
+    pl = C.c_void_p()
+    call("kc_plane_from_value", None, 3, 2, 0.5, C.byref(pl))
+    call("kc_plane_retain", pl)
+    call("kc_plane_release", pl)
+    call("kc_plane_release", pl)            # last reference: the descriptor is gone, no context touched
+    call("kc_plane_release", None)          # NULL stays a no-op
+    im = kc_image()
+    im.kind, im.width, im.height = 1, 3, 2
+    for c in range(4):
+        p = C.c_void_p()
+        call("kc_plane_from_value", None, 3, 2, 0.25 * c, C.byref(p))
+        im.planes[c] = p
+    call("kc_image_release", C.byref(im))
+    assert all(not im.planes[c] for c in range(4)), "the handles must be cleared once released"
+    call("kc_image_release", C.byref(im))   # releasing an empty image is a no-op

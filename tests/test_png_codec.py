@@ -147,6 +147,30 @@ def test_header_that_promises_terabytes_is_rejected_before_allocating():
     assert e.value.kind == "Image"
 
 
+@pytest.mark.parametrize("w,h", [(1 << 31, 1 << 31), (1 << 31, 1), (1, 1 << 31), ((1 << 16) + 1, 3), (1 << 16, 1 << 16), (0xffffffff, 0xffffffff)])
+def test_header_sizes_that_wrap_64_bit_arithmetic_are_refused(w, h):
+    """w = h = 2^31 made h * (stride + 1) wrap to 2 GiB and the pixel buffer to 0 bytes (advisor finding, round 1):
+    the header is now bounded before any arithmetic, and a 9 MB stream of zeros behind it must not be walked."""
+    good = bytearray(enc(np.zeros((3, 3, 4), np.uint8)))
+    good[16:24] = struct.pack(">II", w, h)
+    good[29:33] = struct.pack(">I", zlib.crc32(bytes(good[12:29])) & 0xffffffff)
+    with pytest.raises(TexProError) as e:
+        dec_mem(bytes(good))
+    assert e.value.kind == "Image"
+    # the same header in front of a stream that really inflates to 2 GiB of zeros (what the wrapped total asked for)
+    if (w, h) == (1 << 31, 1 << 31):
+        z = zlib.compressobj(9)
+        body = b"".join(z.compress(bytes(1 << 24)) for _ in range(128)) + z.flush()
+        ihdr = struct.pack(">II", w, h) + bytes([8, 6, 0, 0, 0])
+
+        def chunk(t, b):
+            return struct.pack(">I", len(b)) + t + b + struct.pack(">I", zlib.crc32(t + b) & 0xffffffff)
+        bomb = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", ihdr) + chunk(b"IDAT", body) + chunk(b"IEND", b"")
+        with pytest.raises(TexProError) as e:
+            dec_mem(bomb)
+        assert e.value.kind == "Image"
+
+
 def test_encode_file(tmp_path):
     a = np.random.default_rng(4).integers(0, 256, (12, 10, 4), dtype=np.uint8)
     path = str(tmp_path / "out.png")
