@@ -212,6 +212,12 @@ int32_t kc_debug_jit_wait(int32_t timeout_ms, int32_t* still_running);
  *      pinned host memory (the reference writes them to disk) and come back when something reads them.
  *      0 = no limit (the default: 180 GB of HBM). */
 int32_t kc_context_set_memory_threshold(kc_context* ctx, uint64_t bytes);
+/* ---- priority admission: ProcessPackManager, src/process_pack.rs:33-96 + PriorityPropagator, src/priority.rs:101-127.
+ *      An engine turn (kc_live_graph_update_turn, and every turn kc_live_graph_await_clean takes on an auto_update graph)
+ *      admits at most this many closest-processable nodes, highest PROPAGATED priority first.
+ *      set_max_processing_nodes, src/texture_processor.rs:111-114; default = the host's logical CPUs (num_cpus::get()). */
+int32_t kc_context_set_max_processing_nodes(kc_context* ctx, size_t count);
+int32_t kc_context_max_processing_nodes(const kc_context* ctx, size_t* count);
 int32_t kc_context_spill_stats(const kc_context* ctx, uint64_t* bytes_spilled, uint64_t* spills, uint64_t* reloads);
 int32_t kc_plane_in_memory(const kc_plane* p, int32_t* in_memory);   /* TransientBufferContainer::in_memory */
 /* hand the device buffers the context keeps for reuse back to the driver's pool */
@@ -361,6 +367,10 @@ int32_t kc_graph_node_count(const kc_graph* g, size_t* n);
 int32_t kc_graph_node_at(const kc_graph* g, size_t index, kc_node_desc* out);  /* borrowed name/graph pointers */
 int32_t kc_graph_node(const kc_graph* g, uint32_t node_id, kc_node_desc* out); /* node, :129-135 */
 int32_t kc_graph_set_node(kc_graph* g, const kc_node_desc* node);              /* replace the node with node->node_id */
+/* Node.priority (src/node/mod.rs:120): Priority::set_priority / priority / propagated_priority, src/priority.rs:33-45.
+ * `propagated` is the value PriorityPropagator::update leaves behind: max(own, children's propagated). */
+int32_t kc_graph_set_node_priority(kc_graph* g, uint32_t node_id, int8_t priority);
+int32_t kc_graph_node_priority(const kc_graph* g, uint32_t node_id, int8_t* priority, int8_t* propagated);
 int32_t kc_graph_edge_count(const kc_graph* g, size_t* n);
 int32_t kc_graph_edge_at(const kc_graph* g, size_t index, kc_edge* out);
 int32_t kc_graph_input_slot_id_with_name(const kc_graph* g, const char* name, uint32_t* slot_id);   /* :285-290 */
@@ -416,6 +426,11 @@ int32_t kc_live_graph_node_ids_with_state(const kc_live_graph* lg, int32_t state
 int32_t kc_live_graph_get_closest_processable(const kc_live_graph* lg, uint32_t node_id, uint32_t* ids, size_t cap, size_t* n);       /* :279-311 */
 int32_t kc_live_graph_mark(kc_live_graph* lg, uint32_t node_id, int32_t state);   /* request :219-227 / prioritise :229-237: state change only */
 int32_t kc_live_graph_update(kc_live_graph* lg, size_t* n_processed);             /* one engine turn for this graph, src/engine.rs:128-183 */
+/* ONE engine turn with priority admission (src/engine.rs:128-307 + src/process_pack.rs:33-96): the closest processable
+ * ancestors of the wanted nodes, at most max_processing_nodes of them, highest propagated priority first; the ids of the
+ * nodes that ran come back in that order (admitted == NULL: just the count). */
+int32_t kc_live_graph_update_turn(kc_live_graph* lg, uint32_t* admitted, size_t cap, size_t* n_admitted);
+int32_t kc_live_graph_set_priority(kc_live_graph* lg, uint32_t node_id, int8_t priority);   /* node(id)?.priority.set_priority(v) */
 int32_t kc_live_graph_remove_edge(kc_live_graph* lg, const kc_edge* e);           /* remove_edge, :551-566 */
 int32_t kc_live_graph_rename_output_node(kc_live_graph* lg, uint32_t node_id, const char* new_name, char** old_name); /* :625-627 */
 int32_t kc_live_graph_new_id(kc_live_graph* lg, uint32_t* out);                   /* new_id, :422-424 */

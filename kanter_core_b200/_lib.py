@@ -90,6 +90,12 @@ SIGNATURES = {
     "kc_context_transfer_stats": (i32, [vp, P(u64), P(u64)]),
     "kc_context_set_memory_threshold": (i32, [vp, u64]),
     "kc_context_spill_stats": (i32, [vp, P(u64), P(u64), P(u64)]),
+    "kc_context_set_max_processing_nodes": (i32, [vp, sz]),
+    "kc_context_max_processing_nodes": (i32, [vp, P(sz)]),
+    "kc_graph_set_node_priority": (i32, [vp, u32, C.c_int8]),
+    "kc_graph_node_priority": (i32, [vp, u32, P(C.c_int8), P(C.c_int8)]),
+    "kc_live_graph_update_turn": (i32, [vp, P(u32), sz, P(sz)]),
+    "kc_live_graph_set_priority": (i32, [vp, u32, C.c_int8]),
     "kc_plane_in_memory": (i32, [vp, P(i32)]),
     "kc_live_graph_slot_in_memory": (i32, [vp, u32, u32, P(i32)]),
     "kc_png_decode": (i32, [vp, sz, P(vp), P(u32), P(u32), P(u32)]),

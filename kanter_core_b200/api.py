@@ -186,6 +186,33 @@ class Slot:  # src/node/mod.rs:223-238
         return "Slot(%r, %d, %s)" % (self.name, self.slot_id, self.slot_type.name)
 
 
+class Priority:
+    """`struct Priority`, src/priority.rs:11-45.  On a node that lives in a graph the value is the graph's (the
+    reference shares an Arc<Priority> between the node and the engine); on a free-standing node it travels with
+    the node into add_node."""
+
+    def __init__(self, value=0, owner=None, node_id=None):
+        self._value, self._owner, self._node_id = int(value), owner, node_id
+
+    def set_priority(self, val):  # :33-37
+        val = int(val)
+        if not -128 <= val <= 127:
+            raise ValueError("priority is an i8")
+        self._value = val
+        if self._owner is not None:
+            self._owner._set_priority(self._node_id, val)
+
+    def priority(self):  # :43-45
+        if self._owner is not None:
+            return self._owner._priority(self._node_id)[0]
+        return self._value
+
+    def propagated_priority(self):  # :39-41, after PriorityPropagator::update (:101-127)
+        if self._owner is not None:
+            return self._owner._priority(self._node_id)[1]
+        return self._value
+
+
 class Node:
     """`struct Node`, src/node/mod.rs:114-123."""
 
@@ -194,6 +221,7 @@ class Node:
         self.node_type = node_type
         self.resize_policy = ResizePolicy.default()
         self.resize_filter = ResizeFilter.default()
+        self.priority = Priority()
 
     new = staticmethod(lambda node_type: Node(node_type))
     with_id = staticmethod(lambda node_type, node_id: Node(node_type, node_id))
@@ -328,7 +356,17 @@ class _GraphView:
     def node(self, node_id):
         d = kc_node_desc()
         call("kc_graph_node", self._graph_handle(), int(node_id), C.byref(d))
-        return Node._from_desc(d)
+        n = Node._from_desc(d)
+        n.priority = Priority(0, self, int(node_id))   # node(id)?.priority.set_priority(v) reaches the graph's node
+        return n
+
+    def _priority(self, node_id):
+        own, prop = C.c_int8(), C.c_int8()
+        call("kc_graph_node_priority", self._graph_handle(), int(node_id), C.byref(own), C.byref(prop))
+        return own.value, prop.value
+
+    def _set_priority(self, node_id, val):
+        call("kc_graph_set_node_priority", self._graph_handle(), int(node_id), int(val))
 
     def has_node_with_id(self, node_id):
         self.node(node_id)
@@ -465,11 +503,15 @@ class NodeGraph(_GraphView):
         d, keep = node._desc()
         out = C.c_uint32()
         call("kc_graph_add_node", self._h, C.byref(d), C.byref(out))
+        if node.priority.priority():
+            self._set_priority(out.value, node.priority.priority())
         return NodeId(out.value)
 
     def add_node_with_id(self, node):  # :339-348
         d, keep = node._desc()
         call("kc_graph_add_node_with_id", self._h, C.byref(d))
+        if node.priority.priority():
+            self._set_priority(int(node.node_id), node.priority.priority())
 
     def remove_node(self, node_id):
         call("kc_graph_remove_node", self._h, int(node_id))
@@ -756,8 +798,13 @@ class TextureProcessor:
     def processing_node_count(self):  # :107-109: nodes being processed right now; evaluation here is synchronous per request
         return 0
 
-    def set_max_processing_nodes(self, count):  # :111-114: a limit on concurrent node threads; there are none to limit
-        self._max_processing_nodes = int(count)
+    def set_max_processing_nodes(self, count):  # :111-114 -> ProcessPackManager::max_count: nodes admitted per engine turn
+        call("kc_context_set_max_processing_nodes", self._ctx._h, int(count))
+
+    def max_processing_nodes(self):
+        n = C.c_size_t()
+        call("kc_context_max_processing_nodes", self._ctx._h, C.byref(n))
+        return n.value
 
     def set_math_mode(self, mode):
         call("kc_context_set_math_mode", self._ctx._h, int(mode))
@@ -857,12 +904,19 @@ class LiveGraph(_GraphView):
         out = C.c_uint32()
         call("kc_live_graph_add_node", self._h, C.byref(d), C.byref(out))
         self._scan_images |= node.node_type.kind == _lib.NODE_IMAGE
+        if node.priority.priority():
+            self._set_priority(out.value, node.priority.priority())
         return NodeId(out.value)
 
     def add_node_with_id(self, node):
         d, keep = node._desc()
         call("kc_live_graph_add_node_with_id", self._h, C.byref(d))
         self._scan_images |= node.node_type.kind == _lib.NODE_IMAGE
+        if node.priority.priority():
+            self._set_priority(int(node.node_id), node.priority.priority())
+
+    def _set_priority(self, node_id, val):
+        call("kc_live_graph_set_priority", self._h, int(node_id), int(val))
 
     def remove_node(self, node_id):
         call("kc_live_graph_remove_node", self._h, int(node_id))
@@ -945,6 +999,16 @@ class LiveGraph(_GraphView):
         n = C.c_size_t()
         call("kc_live_graph_update", self._h, C.byref(n))
         return n.value
+
+    def update_turn(self):
+        """ONE engine turn with priority admission (src/engine.rs:128-307, src/process_pack.rs:33-96): at most
+        `set_max_processing_nodes` closest-processable nodes run, highest propagated priority first.  Returns
+        their ids in the order they ran."""
+        self._load_images()
+        arr = (C.c_uint32 * 4096)()
+        n = C.c_size_t()
+        call("kc_live_graph_update_turn", self._h, arr, 4096, C.byref(n))
+        return [NodeId(arr[i]) for i in range(min(n.value, 4096))]
 
     @staticmethod
     def await_clean_read(live_graph, node_id):  # :181-195

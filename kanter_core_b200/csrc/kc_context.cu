@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <string>
 
+#include <thread>
+
 #include "kc_internal.h"
 
 // ---------------------------------------------------------------------------
@@ -116,6 +118,7 @@ static int32_t context_create(int32_t device, const kc_options* opts, cudaStream
     auto* ctx = new kc_context();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->max_processing_nodes = std::max(1u, std::thread::hardware_concurrency());   // num_cpus::get(), src/process_pack.rs:27
     kc_options_default(&ctx->opts);
     if (opts) ctx->opts = *opts;
     int prev = 0;
@@ -456,6 +459,18 @@ extern "C" int32_t kc_context_set_memory_threshold(kc_context* ctx, uint64_t byt
     KcGuard g(ctx);
     ctx->memory_threshold = bytes ? bytes : UINT64_MAX;
     return kc_enforce_threshold(ctx);
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_set_max_processing_nodes(kc_context* ctx, size_t count) try {
+    // TextureProcessor::set_max_processing_nodes, src/texture_processor.rs:111-114 -> ProcessPackManager::max_count
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    KcGuard g(ctx);
+    ctx->max_processing_nodes = count ? count : 1;
+    return KC_OK;
+} KC_ABI_CATCH
+extern "C" int32_t kc_context_max_processing_nodes(const kc_context* ctx, size_t* count) try {
+    if (!ctx || !count) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    *count = ctx->max_processing_nodes;
+    return KC_OK;
 } KC_ABI_CATCH
 extern "C" int32_t kc_context_spill_stats(const kc_context* ctx, uint64_t* bytes_spilled, uint64_t* spills, uint64_t* reloads) try {
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");

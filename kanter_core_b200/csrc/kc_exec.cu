@@ -587,7 +587,78 @@ struct kc_live_graph {
     }
 
     int32_t evaluate(const uint32_t* ids, size_t n_ids, bool materialise);
+    // one turn of the engine with priority admission (engine.rs:128-307 + process_pack.rs:33-96)
+    int32_t turn(std::vector<uint32_t>& admitted);
 };
+
+// An index of the graph as it stands, built once per call: positions of the nodes, each node's incoming
+// edges (in edge order), parents and children.  The loops that use it touch each edge a constant number of times.
+struct KcGraphIndex {
+    size_t N = 0;
+    std::unordered_map<uint32_t, int> pos;
+    std::vector<std::vector<int>> in_edges, par, chi;
+    std::vector<int*> st;                                 // the nodes' states (map nodes do not move)
+    std::vector<int8_t> prio;                             // propagated priorities; empty when every priority is 0
+    explicit KcGraphIndex(kc_live_graph& lg) {
+        const kc_graph& graph = lg.graph;
+        N = graph.nodes.size();
+        pos.reserve(N * 2);
+        for (size_t i = 0; i < N; ++i) pos.emplace(graph.nodes[i].node_id, (int)i);   // first node wins, as kcg_find does
+        in_edges.resize(N); par.resize(N); chi.resize(N);
+        for (size_t j = 0; j < graph.edges.size(); ++j) {
+            const kc_edge& e = graph.edges[j];
+            auto ci = pos.find(e.input_id), pi = pos.find(e.output_id);
+            if (ci == pos.end()) continue;
+            in_edges[ci->second].push_back((int)j);
+            if (pi == pos.end()) continue;                    // an edge from a node that is gone: no dependency, no data either
+            if (std::find(par[ci->second].begin(), par[ci->second].end(), pi->second) == par[ci->second].end()) par[ci->second].push_back(pi->second);
+            if (std::find(chi[pi->second].begin(), chi[pi->second].end(), ci->second) == chi[pi->second].end()) chi[pi->second].push_back(ci->second);
+        }
+        st.resize(N);
+        for (size_t i = 0; i < N; ++i) st[i] = &lg.state[graph.nodes[i].node_id];
+        bool any = false;
+        for (size_t i = 0; i < N && !any; ++i) any = graph.nodes[i].priority != 0;
+        if (any) kcg_propagated_priorities(graph, prio);
+    }
+};
+
+// process one ready node: gather its inputs in graph-edge order (engine.rs:217-262), call process_node, store the
+// results, mark it Clean and free the parents' data once every child of theirs has run (engine.rs:58-75; nodes the
+// caller asked for keep theirs)
+static int32_t run_ready_node(kc_live_graph& lg, const KcGraphIndex& ix, size_t i, const std::vector<char>& keep) {
+    kc_context* ctx = lg.ctx;
+    const KcNode& node = lg.graph.nodes[i];
+    *ix.st[i] = KC_STATE_PROCESSING;
+    std::vector<kc_edge> ne;
+    std::vector<Slot> in, out;
+    for (int j : ix.in_edges[i]) {
+        const kc_edge& e = lg.graph.edges[j];
+        const Slot* f = lg.find_slot(e.output_id, e.output_slot);
+        if (!f) KC_FAIL(KC_ERR_NO_SLOT_DATA, "node %u has no data in slot %u", e.output_id, e.output_slot);
+        ne.push_back(e);
+        in.push_back(*f);
+    }
+    {
+        KcHostTimer hp_node(KC_HP_PROCESS_NODE);
+        KC_TRY(process_node(ctx, node, in, ne, lg.embeds, lg.inputs, lg.images, out));
+    }
+    in.clear();
+    lg.remove_nodes_data(node.node_id);
+    for (Slot& s : out) lg.slot_datas.push_back(std::move(s));
+    out.clear();
+    *ix.st[i] = KC_STATE_CLEAN;
+    lg.changed.insert(node.node_id);
+    if (!lg.use_cache) {
+        for (int p : ix.par[i]) {
+            if (keep[p]) continue;
+            bool all = true;
+            for (int c : ix.chi[p])
+                if (*ix.st[c] != KC_STATE_CLEAN && *ix.st[c] != KC_STATE_PROCESSING) { all = false; break; }
+            if (all) lg.remove_nodes_data(lg.graph.nodes[p].node_id);
+        }
+    }
+    return KC_OK;
+}
 
 int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool materialise) {
     KcGuard guard(ctx);
@@ -598,24 +669,11 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
     for (uint32_t id : requested)
         if (!kcg_find(graph, id)) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", id);
 
-    // An index of the graph as it stands, built once per call: positions of the nodes, each node's incoming
-    // edges (in edge order), parents and children.  The loops below touch each edge a constant number of times.
-    const size_t N = graph.nodes.size();
-    std::unordered_map<uint32_t, int> pos;
-    pos.reserve(N * 2);
-    for (size_t i = 0; i < N; ++i) pos.emplace(graph.nodes[i].node_id, (int)i);   // first node wins, as kcg_find does
-    std::vector<std::vector<int>> in_edges(N), par(N), chi(N);
-    for (size_t j = 0; j < graph.edges.size(); ++j) {
-        const kc_edge& e = graph.edges[j];
-        auto ci = pos.find(e.input_id), pi = pos.find(e.output_id);
-        if (ci == pos.end()) continue;
-        in_edges[ci->second].push_back((int)j);
-        if (pi == pos.end()) continue;                    // an edge from a node that is gone: no dependency, no data either
-        if (std::find(par[ci->second].begin(), par[ci->second].end(), pi->second) == par[ci->second].end()) par[ci->second].push_back(pi->second);
-        if (std::find(chi[pi->second].begin(), chi[pi->second].end(), ci->second) == chi[pi->second].end()) chi[pi->second].push_back(ci->second);
-    }
-    std::vector<int*> st(N);                              // the nodes' states (map nodes do not move)
-    for (size_t i = 0; i < N; ++i) st[i] = &state[graph.nodes[i].node_id];
+    KcGraphIndex ix(*this);
+    const size_t N = ix.N;
+    auto& pos = ix.pos;
+    auto& par = ix.par;
+    auto& st = ix.st;
     std::vector<char> is_req(N, 0), in_todo(N, 0);
     for (uint32_t id : requested) is_req[pos[id]] = 1;
 
@@ -646,65 +704,45 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
     for (size_t i = 0; i < N; ++i)
         if (is_req[i] && *st[i] != KC_STATE_CLEAN) *st[i] = KC_STATE_REQUESTED;
 
-    // 2. run them in dependency order (ties: position in the node vector)
+    // 2. run them in dependency order.  Among the nodes that are ready, the one with the highest PROPAGATED
+    //    priority goes first (PriorityPropagator + ProcessPackManager order the engine's work the same way,
+    //    src/priority.rs:101-127, src/process_pack.rs:33-96); ties, and the common case of no priorities at all:
+    //    position in the node vector.
     int32_t rc = KC_OK;
-    std::vector<kc_edge> ne;
-    std::vector<Slot> in, out;
     while (remaining > 0 && rc == KC_OK) {
         bool progressed = false;
-        for (size_t i = 0; i < N; ++i) {
-            if (!in_todo[i] || *st[i] == KC_STATE_CLEAN) continue;
-            const KcNode& node = graph.nodes[i];
-            bool ready = true;
+        auto ready = [&](size_t i) {
+            if (!in_todo[i] || *st[i] == KC_STATE_CLEAN) return false;
             for (int p : par[i])
-                if (*st[p] != KC_STATE_CLEAN) { ready = false; break; }
-            if (!ready) continue;
-            if (ctx->cancel.load()) { rc = KC_ERR_CANCELED; kc_set_error("evaluation canceled"); break; }
-            *st[i] = KC_STATE_PROCESSING;
-            // gather the inputs in graph-edge order, engine.rs:217-262
-            ne.clear();
-            in.clear();
-            for (int j : in_edges[i]) {
-                const kc_edge& e = graph.edges[j];
-                const Slot* f = find_slot(e.output_id, e.output_slot);
-                if (!f) { rc = KC_ERR_NO_SLOT_DATA; kc_set_error("node %u has no data in slot %u", e.output_id, e.output_slot); break; }
-                ne.push_back(e);
-                in.push_back(*f);
+                if (*st[p] != KC_STATE_CLEAN) return false;
+            return true;
+        };
+        if (ix.prio.empty()) {
+            for (size_t i = 0; i < N; ++i) {
+                if (!ready(i)) continue;
+                if (ctx->cancel.load()) { rc = KC_ERR_CANCELED; kc_set_error("evaluation canceled"); break; }
+                rc = run_ready_node(*this, ix, i, is_req);
+                if (rc != KC_OK) break;
+                --remaining;
+                progressed = true;
             }
-            if (rc != KC_OK) break;
-            out.clear();
-            {
-                KcHostTimer hp_node(KC_HP_PROCESS_NODE);
-                rc = process_node(ctx, node, in, ne, embeds, inputs, images, out);
+        } else {
+            int best = -1;
+            for (size_t i = 0; i < N; ++i)
+                if (ready(i) && (best < 0 || ix.prio[i] > ix.prio[best])) best = (int)i;
+            if (best >= 0) {
+                if (ctx->cancel.load()) { rc = KC_ERR_CANCELED; kc_set_error("evaluation canceled"); break; }
+                rc = run_ready_node(*this, ix, (size_t)best, is_req);
+                if (rc != KC_OK) break;
+                --remaining;
+                progressed = true;
             }
-            if (rc != KC_OK) break;
-            in.clear();
-            remove_nodes_data(node.node_id);
-            for (Slot& s : out) slot_datas.push_back(std::move(s));
-            out.clear();
-            *st[i] = KC_STATE_CLEAN;
-            changed.insert(node.node_id);
-            // free the parents' data once every child of theirs has run, engine.rs:58-75
-            // (nodes the caller asked for keep theirs)
-            if (!use_cache) {
-                for (int p : par[i]) {
-                    if (is_req[p]) continue;
-                    bool all = true;
-                    for (int c : chi[p])
-                        if (*st[c] != KC_STATE_CLEAN && *st[c] != KC_STATE_PROCESSING) { all = false; break; }
-                    if (all) remove_nodes_data(graph.nodes[p].node_id);
-                }
-            }
-            --remaining;
-            progressed = true;
         }
         if (rc == KC_OK && !progressed) {
             rc = KC_ERR_NODE_DIRTY;
             kc_set_error("the graph has a cycle; %zu nodes can never become clean", remaining);
         }
     }
-    in.clear();
-    out.clear();
     if (rc != KC_OK) {
         for (size_t i = 0; i < N; ++i)
             if (in_todo[i] && *st[i] != KC_STATE_CLEAN) { *st[i] = KC_STATE_DIRTY; remove_nodes_data(graph.nodes[i].node_id); }
@@ -726,6 +764,84 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
     last_groups = ctx->run_groups - g0;
     last_bytes = ctx->run_bytes - b0;
     if (ctx->bytes_live > ctx->memory_threshold) KC_TRY(kc_enforce_threshold(ctx));   // nothing is pinned any more
+    return KC_OK;
+}
+
+// One turn of the engine's loop for this graph, src/engine.rs:128-307: the wanted nodes (Requested / Prioritised,
+// or every node that is not Clean with auto_update) are traced back to their closest processable ancestors
+// (live_graph.rs:279-311); those candidates are admitted in order of PROPAGATED priority, at most
+// `max_processing_nodes` of them (ProcessPackManager::update, src/process_pack.rs:33-96: packs sorted ascending,
+// popped from the end -- among equal priorities the later node id goes first, which is what Rust's sort does for the
+// short vectors involved), and each admitted node is processed.  The reference hands them to threads and collects
+// the results on later turns; here a node is done when its turn ends, so nothing is ever pre-empted.
+int32_t kc_live_graph::turn(std::vector<uint32_t>& admitted) {
+    KcGuard guard(ctx);
+    admitted.clear();
+    ctx->cancel.store(false);
+    KcGraphIndex ix(*this);
+    const size_t N = ix.N;
+    std::vector<char> wanted(N, 0), cand(N, 0);
+    size_t n_wanted = 0;
+    for (size_t i = 0; i < N; ++i) {
+        const int s = *ix.st[i];
+        const bool w = auto_update ? (s != KC_STATE_CLEAN && s != KC_STATE_PROCESSING && s != KC_STATE_PROCESSING_DIRTY)
+                                   : (s == KC_STATE_REQUESTED || s == KC_STATE_PRIORITISED);
+        wanted[i] = w;
+        n_wanted += w;
+    }
+    if (n_wanted == 0) return KC_OK;
+    // get_closest_processable: a wanted node whose parents are all Clean is a candidate, otherwise its dirty parents are asked
+    std::vector<char> seen(N, 0);
+    std::vector<int> work;
+    for (size_t i = 0; i < N; ++i)
+        if (wanted[i]) work.push_back((int)i);
+    while (!work.empty()) {
+        const int i = work.back();
+        work.pop_back();
+        if (seen[i]) continue;
+        seen[i] = 1;
+        bool processing = false, dirty = false;
+        for (int p : ix.par[i]) {
+            const int ps = *ix.st[p];
+            if (ps == KC_STATE_PROCESSING || ps == KC_STATE_PROCESSING_DIRTY) processing = true;
+            else if (ps != KC_STATE_CLEAN) { dirty = true; work.push_back(p); }
+        }
+        if (!dirty && !processing) cand[i] = 1;
+    }
+    std::vector<int> order;
+    for (size_t i = 0; i < N; ++i)
+        if (cand[i]) order.push_back((int)i);
+    auto prio = [&](int i) { return ix.prio.empty() ? (int8_t)0 : ix.prio[i]; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        if (prio(a) != prio(b)) return prio(a) > prio(b);
+        return graph.nodes[a].node_id > graph.nodes[b].node_id;
+    });
+    const size_t cap = std::max<size_t>(1, ctx->max_processing_nodes);
+    if (order.size() > cap) order.resize(cap);
+    // a parent's data goes once all its children ran, except for nodes somebody asked for explicitly
+    std::vector<char> keep(N, 0);
+    for (size_t i = 0; i < N; ++i) keep[i] = *ix.st[i] == KC_STATE_REQUESTED || *ix.st[i] == KC_STATE_PRIORITISED;
+    std::vector<kc_plane*> roots;
+    for (int i : order) {
+        if (ctx->cancel.load()) KC_FAIL(KC_ERR_CANCELED, "evaluation canceled");
+        const bool was_wanted = wanted[i];
+        int32_t rc = run_ready_node(*this, ix, (size_t)i, keep);
+        if (rc != KC_OK) {
+            *ix.st[i] = KC_STATE_DIRTY;
+            remove_nodes_data(graph.nodes[i].node_id);
+            return rc;
+        }
+        admitted.push_back(graph.nodes[i].node_id);
+        if (was_wanted)   // what the caller waits for becomes real pixels, like every buffer the reference's nodes produce
+            for (const Slot& s : slot_datas)
+                if (s.node_id == graph.nodes[i].node_id)
+                    for (int c = 0; c < kci_nplanes(&s.image.im); ++c) {
+                        kc_plane* p = s.image.im.planes[c];
+                        if (p->kind != KC_PLANE_DEVICE && p->kind != KC_PLANE_SPILLED && std::find(roots.begin(), roots.end(), p) == roots.end()) roots.push_back(p);
+                    }
+    }
+    if (!roots.empty()) KC_TRY(kcp_force(ctx, roots.data(), roots.size()));
+    if (ctx->bytes_live > ctx->memory_threshold) KC_TRY(kc_enforce_threshold(ctx));
     return KC_OK;
 }
 
@@ -1245,9 +1361,40 @@ int32_t kc_live_graph_request(kc_live_graph* lg, const uint32_t* node_ids, size_
     return lg->evaluate(node_ids, n, true);
 } KC_ABI_CATCH
 int32_t kc_live_graph_await_clean(kc_live_graph* lg, uint32_t node_id) try {
+    // LiveGraph::await_clean_read / await_clean_write, src/live_graph.rs:164-195: prioritise the node and wait until
+    // it is Clean.  With auto_update the reference's engine keeps working on EVERY node that is not clean while the
+    // caller waits, admitting them by priority, so that is what happens here: engine turns until the node is Clean.
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (lg->auto_update) {
+        auto it = lg->state.find(node_id);
+        if (it == lg->state.end()) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
+        if (it->second == KC_STATE_DIRTY || it->second == KC_STATE_REQUESTED) it->second = KC_STATE_PRIORITISED;
+        std::vector<uint32_t> admitted;
+        while (lg->state[node_id] != KC_STATE_CLEAN) {
+            KC_TRY(lg->turn(admitted));
+            if (admitted.empty()) KC_FAIL(KC_ERR_NODE_DIRTY, "node %u can never become clean (cycle, or an input that is gone)", node_id);
+        }
+        return kc_context_synchronize(lg->ctx);
+    }
     KC_TRY(lg->evaluate(&node_id, 1, true));
     return kc_context_synchronize(lg->ctx);
+} KC_ABI_CATCH
+int32_t kc_live_graph_update_turn(kc_live_graph* lg, uint32_t* admitted, size_t cap, size_t* n_admitted) try {
+    // ONE turn of the engine with priority admission (kc_live_graph::turn): at most kc_context_set_max_processing_nodes
+    // nodes are processed, highest propagated priority first; their ids come back in the order they ran
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    std::vector<uint32_t> v;
+    KC_TRY(lg->turn(v));
+    if (n_admitted) *n_admitted = v.size();
+    if (admitted)
+        for (size_t i = 0; i < v.size() && i < cap; ++i) admitted[i] = v[i];
+    return KC_OK;
+} KC_ABI_CATCH
+int32_t kc_live_graph_set_priority(kc_live_graph* lg, uint32_t node_id, int8_t priority) try {
+    // live_graph.node(id)?.priority.set_priority(v), src/priority.rs:33-37; scheduling state: nothing becomes dirty
+    if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcGuard guard(lg->ctx);
+    return kc_graph_set_node_priority(&lg->graph, node_id, priority);
 } KC_ABI_CATCH
 int32_t kc_live_graph_cancel(kc_live_graph* lg) try {
     if (!lg) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");

@@ -131,6 +131,27 @@ void kcg_to_desc(const KcNode& n, kc_node_desc& d) {
     d.resize_filter = n.filter;
 }
 
+void kcg_propagated_priorities(const kc_graph& g, std::vector<int8_t>& out) {
+    const size_t N = g.nodes.size();
+    out.resize(N);
+    for (size_t i = 0; i < N; ++i) out[i] = g.nodes[i].priority;
+    bool any = false;
+    for (size_t i = 0; i < N && !any; ++i) any = out[i] != 0;
+    if (!any || g.edges.empty()) return;
+    std::map<uint32_t, size_t> pos;
+    for (size_t i = 0; i < N; ++i) pos.emplace(g.nodes[i].node_id, i);
+    // relax parent >= child until nothing moves: at most N sweeps on a DAG, and a cycle cannot raise anything forever
+    for (size_t sweep = 0; sweep <= N; ++sweep) {
+        bool moved = false;
+        for (const kc_edge& e : g.edges) {
+            auto p = pos.find(e.output_id), c = pos.find(e.input_id);
+            if (p == pos.end() || c == pos.end()) continue;
+            if (out[c->second] > out[p->second]) { out[p->second] = out[c->second]; moved = true; }
+        }
+        if (!moved) break;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // node management: src/node_graph.rs:81-96,141-197,332-348
 // ---------------------------------------------------------------------------
@@ -802,7 +823,29 @@ int32_t kc_graph_set_node(kc_graph* g, const kc_node_desc* node) try {
     if (!n) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node->node_id);
     KcNode tmp;
     kcg_from_desc(*node, tmp);
+    tmp.priority = n->priority;        // engine state stays with the node (the reference keeps the Arc<Priority>)
     *n = std::move(tmp);
+    return KC_OK;
+} KC_ABI_CATCH
+int32_t kc_graph_set_node_priority(kc_graph* g, uint32_t node_id, int8_t priority) try {
+    // Priority::set_priority, src/priority.rs:33-37
+    if (!g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    KcNode* n = kcg_find(*g, node_id);
+    if (!n) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
+    n->priority = priority;
+    return KC_OK;
+} KC_ABI_CATCH
+int32_t kc_graph_node_priority(const kc_graph* g, uint32_t node_id, int8_t* priority, int8_t* propagated) try {
+    // Priority::priority / propagated_priority after PriorityPropagator::update, src/priority.rs:39-45,101-127
+    if (!g) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
+    const KcNode* n = kcg_find(*g, node_id);
+    if (!n) KC_FAIL(KC_ERR_INVALID_NODE_ID, "no node %u", node_id);
+    if (priority) *priority = n->priority;
+    if (propagated) {
+        std::vector<int8_t> prop;
+        kcg_propagated_priorities(*g, prop);
+        *propagated = prop[(size_t)(n - g->nodes.data())];
+    }
     return KC_OK;
 } KC_ABI_CATCH
 int32_t kc_graph_edge_count(const kc_graph* g, size_t* n) try {

@@ -20,6 +20,7 @@ struct KcNode {
     int policy = KC_POLICY_MOST_PIXELS;
     uint32_t policy_slot = 0, policy_w = 0, policy_h = 0;
     int filter = KC_FILTER_TRIANGLE;
+    int8_t priority = 0;               // Node.priority (src/node/mod.rs:120, src/priority.rs:11-15): engine state, not serialised
 };
 
 struct kc_graph {
@@ -48,6 +49,11 @@ int32_t kcg_add_node_with_id(kc_graph& g, KcNode node);
 int32_t kcg_connect(kc_graph& g, uint32_t out_id, uint32_t in_id, uint32_t out_slot, uint32_t in_slot);
 int32_t kcg_disconnect_slot(kc_graph& g, uint32_t node_id, int side, uint32_t slot_id, std::vector<kc_edge>* removed);
 int32_t kcg_remove_node(kc_graph& g, uint32_t node_id, std::vector<kc_edge>* removed);
+
+// PriorityPropagator::update, src/priority.rs:101-127, as its fixed point: a node's propagated priority is the
+// largest of its own and its children's propagated priorities ("a node that has a high priority needs all its
+// parents to have the same high priority").  out[i] belongs to g.nodes[i].
+void kcg_propagated_priorities(const kc_graph& g, std::vector<int8_t>& out);
 
 int32_t kcg_parse_json(const std::string& text, kc_graph& out);
 std::string kcg_to_json(const kc_graph& g);

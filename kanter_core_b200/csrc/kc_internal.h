@@ -146,6 +146,9 @@ struct kc_context {
     // 1 -> len broadcasts whose single normalised tap is exactly 1.0 (kc_exec.cu, plane_resize)
     std::map<std::pair<uint32_t, int>, bool> unit_broadcast;
     std::atomic<bool> cancel{false};
+    // ProcessPackManager::max_count (src/process_pack.rs:27, set_max_processing_nodes src/texture_processor.rs:111-114):
+    // how many nodes one engine turn admits; num_cpus::get() by default
+    size_t max_processing_nodes = 1;
     // kernels whose dynamic shared-memory limit has been raised on THIS device (the attribute is per device)
     std::set<const void*> smem_attr_done;
     // exact-size recycling of device buffers on top of the stream-ordered pool: a plane freed

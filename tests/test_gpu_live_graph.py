@@ -292,3 +292,95 @@ def test_concurrent_threads_share_one_context(tex_pro):
     for t in threads:
         t.join()
     assert not errors, errors[:5]
+
+
+# ---- priority admission: tests/integration_tests.rs:414-492 ------------------------------------
+def _priority_internal(max_processing, large_priority):
+    """`priority_internal`: a Value feeding three resizing Mix nodes of an auto_update graph, one of them with its own
+    priority; the test waits for that one and reports whether it became clean BEFORE both of the others."""
+    SIZE_LARGE = SIZE_SMALL = 400
+    tp = kc.TextureProcessor.new()
+    try:
+        tp.set_max_processing_nodes(max_processing)
+        lg = tp.new_live_graph()
+        value_node = lg.add_node(Node.new(NodeType.Value(0.5)))
+
+        def sized(size):
+            n = Node.new(NodeType.Mix(MixType.default()))
+            n.resize_filter = ResizeFilter.Nearest
+            n.resize_policy = ResizePolicy.SpecificSize(Size(size, size))
+            return n
+        resize_small_1 = lg.add_node(sized(SIZE_SMALL))
+        resize_small_2 = lg.add_node(sized(SIZE_SMALL))
+        resize_large = lg.add_node(sized(SIZE_LARGE))
+        lg.node(resize_large).priority.set_priority(large_priority)
+        lg.connect(value_node, resize_small_1, SlotId(0), SlotId(0))
+        lg.connect(value_node, resize_large, SlotId(0), SlotId(0))
+        lg.connect(value_node, resize_small_2, SlotId(0), SlotId(0))
+        lg.auto_update = True
+        LiveGraph.await_clean_read(lg, resize_large)
+        assert lg.slot_data_size(resize_large, SlotId(0)) == Size(SIZE_LARGE, SIZE_LARGE)
+        both_small_clean = (lg.node_state(resize_small_1) == NodeState.Clean and lg.node_state(resize_small_2) == NodeState.Clean)
+        return not both_small_clean
+    finally:
+        tp.close()
+
+
+def test_priority():  # :414-419
+    assert not _priority_internal(2, -1)
+    assert _priority_internal(1, 1)
+    assert _priority_internal(2, 1)
+
+
+def test_engine_turns_admit_by_propagated_priority(tex_pro):
+    """One engine turn = the closest processable ancestors of what is wanted, at most max_processing_nodes of them,
+    highest PROPAGATED priority first (src/process_pack.rs:33-96, src/priority.rs:101-127): a low-priority root runs
+    early when a high-priority node hangs below it."""
+    before = tex_pro.max_processing_nodes()
+    tex_pro.set_max_processing_nodes(1)
+    try:
+        lg = tex_pro.new_live_graph()
+        a = lg.add_node(Node.new(NodeType.Value(0.25)))
+        b = lg.add_node(Node.new(NodeType.Value(0.5)))
+        c = lg.add_node(Node.new(NodeType.Value(0.75)))
+        ma = lg.add_node(Node.new(NodeType.Mix(MixType.Add)))
+        mb = lg.add_node(Node.new(NodeType.Mix(MixType.Add)))
+        mc = lg.add_node(Node.new(NodeType.Mix(MixType.Add)))
+        for v, m in ((a, ma), (b, mb), (c, mc)):
+            lg.connect(v, m, SlotId(0), SlotId(0))
+        lg.node(a).priority.set_priority(-5)
+        lg.node(ma).priority.set_priority(9)          # a's propagated priority becomes 9
+        lg.node(mb).priority.set_priority(3)
+        assert lg.node(a).priority.propagated_priority() == 9 and lg.node(a).priority.priority() == -5
+        lg.auto_update = True
+        ran = []
+        while True:
+            t = lg.update_turn()
+            if not t:
+                break
+            assert len(t) == 1
+            ran += t
+        assert ran == [a, ma, b, mb, c, mc]
+        assert lg.node_ids_without_state(NodeState.Clean) == []
+        assert lg.slot_data(ma, SlotId(0)).image.planes()[0].tolist() == [[0.25]]
+        # two per turn: the two best candidates of each turn, best first
+        tex_pro.set_max_processing_nodes(2)
+        for n in (a, b, c):
+            lg.set_node(lg.node(n))                    # node_mut: the node and everything below become dirty
+        assert lg.update_turn() == [a, b]              # candidates a (9), b (3), c (0)
+        assert lg.update_turn() == [ma, mb]            # candidates ma (9), mb (3), c (0)
+        assert lg.update_turn() == [c]
+        assert lg.update_turn() == [mc]
+        assert lg.update_turn() == []
+        # without auto_update only what was requested (and its ancestors) is wanted
+        lg.auto_update = False
+        for n in (a, b, c):
+            lg.set_node(lg.node(n))
+        lg.mark_requested(mc)
+        assert lg.update_turn() == [c] and lg.update_turn() == [mc] and lg.update_turn() == []
+        assert lg.node_state(ma) == NodeState.Dirty
+        # a full request honours the same order among ready nodes
+        lg.request_many([ma, mb, mc])
+        assert lg.node_ids_without_state(NodeState.Clean) == []
+    finally:
+        tex_pro.set_max_processing_nodes(before)

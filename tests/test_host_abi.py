@@ -427,3 +427,46 @@ def test_context_less_constant_planes_can_be_released():
     call("kc_image_release", C.byref(im))
     assert all(not im.planes[c] for c in range(4)), "the handles must be cleared once released"
     call("kc_image_release", C.byref(im))   # releasing an empty image is a no-op
+
+
+def test_propagate_priority():
+    """The reference's unit test `propagate_priority` (src/priority.rs:181-245) on the C++ graph model:
+
+         1---2---+
+                 4---5          own priorities 3, -10, 8, 5, 0
+             3---+
+
+    a node that has a high priority needs all its parents to have the same high priority."""
+    from kanter_core_b200 import MixType, Node, NodeGraph, NodeType, SlotId
+    g = NodeGraph.new()
+    own = [3, -10, 8, 5, 0]
+    ids = []
+    for v in own:
+        nid = g.add_node(Node.new(NodeType.Mix(MixType.default())))
+        g.node(nid).priority.set_priority(v)
+        ids.append(nid)
+    n1, n2, n3, n4, n5 = ids
+    g.connect(n1, n2, SlotId(0), SlotId(0))
+    g.connect(n2, n4, SlotId(0), SlotId(0))
+    g.connect(n3, n4, SlotId(0), SlotId(1))
+    g.connect(n4, n5, SlotId(0), SlotId(0))
+    want = {n1: 5, n2: 5, n3: 8, n4: 5, n5: 0}      # assert_priority(node, expected) x 5, :215-238
+    for nid, v in zip(ids, own):
+        p = g.node(nid).priority
+        assert p.priority() == v
+        assert p.propagated_priority() == want[nid], nid
+    # the reference pops its priority-sorted list: 3 (8), then 4, 1, 2 by propagated 5, then 5 (0): same order here
+    order = sorted(ids, key=lambda n: g.node(n).priority.propagated_priority(), reverse=True)
+    assert order[0] == n3 and order[-1] == n5
+    # lowering node 4 lets its ancestors fall back to their own priorities; a priority set on a free node travels
+    g.node(n4).priority.set_priority(-20)
+    assert [g.node(n).priority.propagated_priority() for n in ids] == [3, 0, 8, 0, 0]
+    fresh = Node.new(NodeType.Value(1.0))
+    fresh.priority.set_priority(7)
+    f = g.add_node(fresh)
+    assert g.node(f).priority.priority() == 7
+    # set_node replaces the node's data, not its scheduling state; clones keep it; JSON does not carry it (#[serde(skip)])
+    node = g.node(n3)
+    node.resize_filter = kc.ResizeFilter.Nearest
+    assert g.clone().node(n3).priority.priority() == 8
+    assert NodeGraph.from_json(g.export_json_string()).node(n3).priority.priority() == 0
