@@ -6,6 +6,7 @@
 // (size policy + resize pre-pass), src/node/*.rs (node bodies), src/live_graph.rs
 // and src/engine.rs:34-307 (state machine, scheduling, parent-data freeing).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <unordered_map>
@@ -153,7 +154,13 @@ int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullp
     KcHostTimer hp(KC_HP_H2N);
     kc_plane* src = in.im.planes[0];
     KcPin pin;   // source, halo and the planes already allocated stay in HBM until the kernel is enqueued
-    KC_TRY(kcp_force(ctx, &src, 1));
+    {
+        // the stencil differentiates: whatever per-pixel expression feeds it is evaluated in EXACT arithmetic even in
+        // FAST mode (see kc_context::exact_scope); KC_FAST_STENCIL_INPUTS=1 switches this off for A/B measurements
+        static const bool fast_inputs = getenv("KC_FAST_STENCIL_INPUTS") != nullptr;
+        KcExactScope exact_cone(ctx, !fast_inputs);
+        KC_TRY(kcp_force(ctx, &src, 1));
+    }
     pin.add(src);
     if (halo) {
         if (halo->w != src->w || halo->h != 1) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "halo row must be %u x 1", src->w);

@@ -162,6 +162,11 @@ struct kc_context {
     std::vector<cudaEvent_t> event_pool;
     // peer halo mailboxes (kc_h2n.cu): once a context has waited on a peer's flag, every synchronising call
     // checks the device's time-out counter and fails instead of handing back a strip computed from a stale row
+    // > 0 while the operand cone of a stencil is being evaluated (KcExactScope): the tape kernels then use the
+    // EXACT arithmetic whatever opts.math_mode says.  HeightToNormal differentiates its input -- on a smooth
+    // 4096-wide map an input error e becomes an output error of about e * W / 2 -- so the 4e-7 of FAST pow would
+    // leave the north star's 1e-5 / 1e-6; bit-identical inputs keep FAST HeightToNormal inside it.
+    int exact_scope = 0;
     bool halo_used = false;
     uint32_t halo_timeouts_seen = 0;
 };
@@ -187,6 +192,16 @@ struct KcTimed {
     ~KcTimed() {
         if (stop) cudaEventRecord(stop, ctx->stream);
     }
+};
+
+inline bool kc_tape_exact(const kc_context* ctx) { return ctx->opts.math_mode == KC_MATH_EXACT || ctx->exact_scope > 0; }
+struct KcExactScope {
+    kc_context* ctx;
+    bool on;
+    explicit KcExactScope(kc_context* c, bool enable = true) : ctx(c), on(enable) { if (on) ++ctx->exact_scope; }
+    ~KcExactScope() { if (on) --ctx->exact_scope; }
+    KcExactScope(const KcExactScope&) = delete;
+    KcExactScope& operator=(const KcExactScope&) = delete;
 };
 
 // RAII device selection + context lock

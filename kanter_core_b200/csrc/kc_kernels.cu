@@ -163,7 +163,7 @@ int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     g_kc_last_tile_config[0] = c.v; g_kc_last_tile_config[1] = c.ctas; g_kc_last_tile_config[2] = c.stages;
     KcTimed timed(ctx, KC_KERNEL_TAPE);
     int32_t rc;
-    const bool exact = ctx->opts.math_mode == KC_MATH_EXACT;
+    const bool exact = kc_tape_exact(ctx);   // EXACT mode, or the operand cone of a stencil (KcExactScope)
     {
         // a kernel specialised for this tape (kc_jit.cu): its temporaries are registers, so the launch
         // configuration is chosen for zero shared-memory temporaries, V bounded by the register budget

@@ -141,10 +141,9 @@ def main():
             outside += int((err > 0).sum())
             worst = max(worst, float(np.abs(got[c].astype(np.float64) - w).max()))
             bit_exact &= bool(np.array_equal(got[c].view(np.uint32), want[c].view(np.uint32)))
-        # EXACT must be bit-identical.  FAST is within 1e-5/1e-6 per operation; through the whole
-        # graph a few pixels per 16.7 M can exceed it where HeightToNormal is ill-conditioned (both
-        # finite differences ~ 0, so a 1e-7 perturbation of the fused pow upstream turns the normal)
-        ok = bit_exact if args.math == "exact" else outside <= 1e-5 * 4 * S * S
+        # EXACT must be bit-identical; FAST must have EVERY sample within 1e-5 rel / 1e-6 abs (the expression
+        # that feeds HeightToNormal is evaluated in exact arithmetic for that: kc_context::exact_scope)
+        ok = bit_exact if args.math == "exact" else outside == 0
         parity = {"graph": 0, "ok": ok, "bit_exact": bit_exact, "samples_outside_1e-5rel_1e-6abs": outside,
                   "samples": 4 * S * S, "max_abs_err": worst,
                   "cpu_oracle_seconds_for_one_graph": cpu_s, "cpu_oracle_mpixel_per_s_one_thread": S * S / 1e6 / cpu_s}

@@ -369,10 +369,30 @@ def config5_graph(size, lsize=None):
     return g, out
 
 
-def config5_inputs(seed, size, lsize=None):
-    """Synthetic inputs of graph `seed`: A (4 planes), H (1 plane), L (4 planes), uniform [0,1)."""
+def smooth_plane(seed, h, w):
+    """A smooth height map in [0.05, 0.95]: a sum of five low-frequency sines (SURVEY.md section 8d, config 3's
+    "sum-of-sines variant").  Neighbouring pixels differ by ~1e-3 / (w / 256) or less, the case in which HeightToNormal
+    amplifies any error of its input by ~w / 2."""
+    r = np.random.default_rng(seed)
+    y, x = np.meshgrid(np.arange(h, dtype=np.float64) / h, np.arange(w, dtype=np.float64) / w, indexing="ij")
+    acc = np.zeros((h, w), np.float64)
+    for _ in range(5):
+        fx, fy = r.integers(1, 5, 2)
+        acc += r.uniform(0.3, 1.0) * np.sin(2 * np.pi * (fx * x + fy * y) + r.uniform(0, 2 * np.pi))
+    acc = (acc - acc.min()) / (acc.max() - acc.min())
+    return (0.05 + 0.9 * acc).astype(np.float32)
+
+
+def config5_inputs(seed, size, lsize=None, smooth=False):
+    """Synthetic inputs of graph `seed`: A (4 planes), H (1 plane), L (4 planes), uniform [0,1);
+    smooth=True: A and H are smooth sum-of-sines maps (so is the height field the graph derives from them)."""
     lsize = lsize or max(1, size // 4)
     r = np.random.default_rng(seed)
+    if smooth:
+        A = [smooth_plane(seed * 10 + c, size, size) for c in range(4)]
+        H = [smooth_plane(seed * 10 + 4, size, size)]
+        L = [r.random((lsize, lsize), dtype=np.float32) for _ in range(4)]
+        return A, H, L
     A = [r.random((size, size), dtype=np.float32) for _ in range(4)]
     H = [r.random((size, size), dtype=np.float32)]
     L = [r.random((lsize, lsize), dtype=np.float32) for _ in range(4)]
