@@ -13,8 +13,14 @@ N > 1: one process per GPU (torchrun); every rank evaluates its own graph on its
 inputs (independent texture graphs, SURVEY.md section 8e: no data-path collective); the
 only communication is the barrier and the max-over-ranks of the device time.
 
+The same JSON line carries a `workloads` block with the other BASELINE.json configurations
+(bench_workloads.py): HeightToNormal 8192^2 (FAST + EXACT; strips with a peer-memory halo at
+N > 1), Resize Lanczos3/Gaussian 1024^2 -> 8192^2 RGBA (row strips at N > 1), the batch of 64
+32-node graphs at 4096^2 split over the ranks, and one 8192^2 RGBA Mix graph -- each with its
+ms, algorithmic bytes, roofline fraction and a parity sample against the CPU oracle.
+
 --impl reference times the CPU restatement of the reference engine (oracle/, the Rust
-crate cannot be built here) on the host cores.
+crate cannot be built here) on every host core the process may use, --steps/--warmup as given.
 """
 import argparse
 import json
@@ -76,28 +82,37 @@ def cpu_threads():
         return max(1, os.cpu_count() or 1)
 
 
+CPU_BAND_ROWS = 1024     # the bounded sample: a 1024-row band (1/4) of the 4096^2 images per graph copy
+
+
 def run_cpu(steps, warmup):
     """Copies of the graph evaluated concurrently, one thread per ready node (the
     reference engine's only parallelism, src/engine.rs:288, src/process_pack.rs:27);
-    every node's pixel loop is single-threaded as in the reference."""
-    A, B = make_inputs(1), make_inputs(2)
+    every node's pixel loop is single-threaded as in the reference.  Each step evaluates
+    one copy per host thread on a CPU_BAND_ROWS-row band of the inputs (the graph is purely
+    per-pixel, so a band costs exactly its share of the image): ~0.15 s per step, so that
+    --steps 200 still ends within a minute, and 8 GB of planes at 32 threads."""
+    rows = CPU_BAND_ROWS
+    A = [p[:rows] for p in make_inputs(1)]
+    B = [p[:rows] for p in make_inputs(2)]
     g = oracle_graph(A, B)
-    threads = min(cpu_threads(), 16)     # 0.5 GiB of intermediates per in-flight copy
+    threads = cpu_threads()              # every core the process may run on (sched_getaffinity)
     copies = threads
+    band_mpix = rows * SIZE / 1e6
     for _ in range(warmup):
-        g.eval_batch_seconds(1, 1)
+        g.eval_batch_seconds(copies, threads)
     total = 0.0
     for _ in range(steps):
         total += g.eval_batch_seconds(copies, threads)
-    value = copies * steps * MPIX / total
-    return value, total / steps * 1e3, threads, "%d steps x %d concurrent copies of the full %dx%d graph, one thread per copy" % (steps, copies, SIZE, SIZE)
+    value = copies * steps * band_mpix / total
+    return value, total / steps * 1e3, threads, ("%d steps x %d concurrent copies of the graph on a %d-row band (%d/%d) of the %dx%d images, one thread per copy, all %d cores of sched_getaffinity"
+                                                 % (steps, copies, rows, rows, SIZE, SIZE, SIZE, threads))
 
 
 def reference_arm(args, rank):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 3))
-    warm = 1 if args.warmup > 0 else 0
+    steps, warm = max(1, args.steps), max(0, args.warmup)     # the driver's --steps / --warmup, as given
     value, ms, threads, sample = run_cpu(steps, warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -399,17 +414,34 @@ def ours(args, rank, world, local_rank):
         e2e_u8 = {"unavailable": "another rank failed"}
 
     peak, peak_src = peaks()
+    workloads = None
+    if not args.no_workloads:
+        import bench_workloads as bw
+
+        def gather(obj):
+            outl = [None] * world
+            dist.all_gather_object(outl, obj)
+            return outl
+        env = bw.Env(kc, tp, rank, world, barrier, max_over_ranks, peak, gather if dist is not None else None)
+        workloads = bw.run_all(env, max(3, min(args.steps, 10)))
+        tp.set_math_mode(math_mode)
     alg_bytes = stats["algorithmic_bytes"] / max(1, stats["kernels"]) if stats["kernels"] else 0
     avg_kernel_ms = kms.value / max(1, kn.value)
     achieved = alg_bytes / (avg_kernel_ms / 1e3) / 1e9 if avg_kernel_ms > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tpath):
+    # DRAM bytes per launch of the dominant kernel: from the newest ncu --set full capture of this same command
+    # (profiles/traffic_rNN.json names the capture file it was read from); a profiler cannot run inside the bench
+    traffic, traffic_src = None, None
+    import glob
+    for tpath in sorted(glob.glob(os.path.join(ROOT, "profiles", "traffic_r*.json")), reverse=True):
         try:
             tj = json.load(open(tpath))
-            traffic = (tj.get("fused_kernel_%s_specialised" % args.math) or tj.get("tape_kernel_%s" % args.math, {})).get("dram_bytes_per_launch")
+            ent = tj.get("fused_kernel_%s_specialised" % args.math) or tj.get("tape_kernel_%s" % args.math, {})
+            if ent.get("dram_bytes_per_launch"):
+                traffic = ent["dram_bytes_per_launch"]
+                traffic_src = "%s (%s)" % (os.path.relpath(tpath, ROOT), ent.get("capture", tj.get("capture", "ncu --set full")))
+                break
         except Exception:
-            traffic = None
+            continue
 
     tv, tc_, ts_ = C.c_int32(), C.c_int32(), C.c_int32()
     call("kc_debug_last_tile_config", C.byref(tv), C.byref(tc_), C.byref(ts_))
@@ -429,11 +461,13 @@ def ours(args, rank, world, local_rank):
                     "steps": e2e_steps, "step_ms_min_median_max": [min(e2e_step_ms), float(np.median(e2e_step_ms)), max(e2e_step_ms)], "u8_inputs": e2e_u8, "path": "8 pinned host f32 planes per step -> deferred upload of the 6 planes the graph reads (upload stream) -> fused mul/pow/to_u8 kernel -> RGBA8 on pinned host (read_rgba, download stream); steps pipelined one deep; bytes as counted by the library"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": kernel_name,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": avg_kernel_ms,
                          "launches_timed": int(kn.value), "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
         }
+        if workloads is not None:
+            line["workloads"] = workloads
         if world == 1 and not args.no_cpu:
             v, _ms, threads, sample = run_cpu(1, 0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
@@ -455,6 +489,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-workloads", action="store_true", help="headline only: skip the `workloads` block (configs[2..4], 8192^2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

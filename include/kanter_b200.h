@@ -157,8 +157,14 @@ const char* kc_last_error(void);
 const char* kc_error_string(int32_t code);  /* Display for TexProError, src/error.rs:37-64 */
 void kc_free(void* p);                      /* frees memory the library malloc'ed for the caller */
 /* pinned host staging memory for uploads/downloads */
-int32_t kc_host_alloc(size_t bytes, void** out);
+int32_t kc_host_alloc(size_t bytes, void** out);          /* on the NUMA node of the current CUDA device, where the host tells */
 int32_t kc_host_free(void* p);
+/* NUMA placement (no reference counterpart; it is what the 8-GPU end-to-end curve hangs on): page-locked memory on the
+ * node `device` is attached to (mmap + mbind + cudaHostRegister; plain cudaHostAlloc when the topology is unknown or
+ * KC_NO_NUMA is set), the topology as seen from here, and moving the calling thread next to the device. */
+int32_t kc_host_alloc_near_device(int32_t device, size_t bytes, void** out);   /* free with kc_host_free */
+int32_t kc_numa_info(int32_t device, int32_t* device_node, int32_t* thread_node, int32_t* nodes);
+int32_t kc_bind_thread_near_device(int32_t device, int32_t* bound);
 
 /* ---- context: replaces TextureProcessor's worker threads,
  *      src/texture_processor.rs:34-56 (engine + transient-buffer queue) ------ */

@@ -73,6 +73,9 @@ SIGNATURES = {
     "kc_free": (None, [vp]),
     "kc_host_alloc": (i32, [sz, P(vp)]),
     "kc_host_free": (i32, [vp]),
+    "kc_host_alloc_near_device": (i32, [i32, sz, P(vp)]),
+    "kc_numa_info": (i32, [i32, P(i32), P(i32), P(i32)]),
+    "kc_bind_thread_near_device": (i32, [i32, P(i32)]),
     "kc_options_default": (None, [P(kc_options)]),
     "kc_context_create": (i32, [i32, P(kc_options), P(vp)]),
     "kc_context_create_on_stream": (i32, [i32, P(kc_options), vp, P(vp)]),

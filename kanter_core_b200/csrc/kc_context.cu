@@ -83,12 +83,13 @@ extern "C" const char* kc_error_string(int32_t code) {
 
 extern "C" int32_t kc_host_alloc(size_t bytes, void** out) try {
     if (!out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "kc_host_alloc: out is NULL");
-    KC_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
-    return KC_OK;
+    // on the NUMA node of the CURRENT device (kc_numa.cu); plain cudaHostAlloc where the topology is unknown
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return kc_host_alloc_on_node(kc_device_numa_node(dev), bytes, out);
 } KC_ABI_CATCH
 extern "C" int32_t kc_host_free(void* p) try {
-    if (p) KC_CUDA(cudaFreeHost(p));
-    return KC_OK;
+    return kc_host_release(p);
 } KC_ABI_CATCH
 
 // ---------------------------------------------------------------------------
@@ -293,7 +294,7 @@ void kc_dev_trim(kc_context* ctx) {
     if (any) {
         cudaStreamSynchronize(ctx->stream);   // copies out of / into these buffers may still be in flight
         for (auto& kv : ctx->host_free_lists)
-            for (void* p : kv.second) cudaFreeHost(p);
+            for (void* p : kv.second) kc_host_release(p);
         ctx->host_free_lists.clear();
     }
 }
@@ -376,8 +377,7 @@ static int32_t host_alloc(kc_context* ctx, size_t bytes, void** out) {
         it->second.pop_back();
         return KC_OK;
     }
-    KC_CUDA(cudaMallocHost(out, bytes));
-    return KC_OK;
+    return kc_host_alloc_on_node(kc_device_numa_node(ctx->device), bytes, out);   // spilled planes stay near their GPU
 }
 static int32_t spill_one(kc_context* ctx, kc_plane* p) {
     const size_t bytes = plane_alloc_bytes(p);
@@ -532,7 +532,7 @@ void kcp_release(kc_plane* p) {
             KcGuard g(q->ctx);
             if (!q->host_borrowed) {
                 const size_t bytes = plane_alloc_bytes(q);
-                if (q->ctx->closed) cudaFreeHost(q->host_copy);
+                if (q->ctx->closed) kc_host_release(q->host_copy);
                 else q->ctx->host_free_lists[bytes].push_back(q->host_copy);
                 q->ctx->bytes_spilled -= bytes;
             }
@@ -983,6 +983,10 @@ static KcTuning tuning_from_env() {
     t.src_soft_cap = env_int("KC_SRC_SOFT_CAP");
     t.resize_threads = env_int("KC_RESIZE_THREADS");
     t.jit = env_int("KC_JIT");
+    t.resize_tma = getenv("KC_RESIZE_NO_TMA") ? -1 : 0;
+    t.resize_g = env_int("KC_RESIZE_G");
+    t.resize_rc = env_int("KC_RESIZE_RC");
+    t.resize_minb = env_int("KC_RESIZE_MINB");
     return t;
 }
 KcTuning g_kc_tuning = tuning_from_env();
@@ -996,6 +1000,10 @@ extern "C" int32_t kc_debug_set_tuning(const char* key, int32_t value) try {
     else if (k == "src_soft_cap") g_kc_tuning.src_soft_cap = value;
     else if (k == "resize_threads") g_kc_tuning.resize_threads = value;
     else if (k == "jit") g_kc_tuning.jit = value;
+    else if (k == "resize_tma") g_kc_tuning.resize_tma = value;
+    else if (k == "resize_g") g_kc_tuning.resize_g = value;
+    else if (k == "resize_rc") g_kc_tuning.resize_rc = value;
+    else if (k == "resize_minb") g_kc_tuning.resize_minb = value;
     else KC_FAIL(KC_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
     return KC_OK;
 } KC_ABI_CATCH

@@ -60,6 +60,9 @@ struct KcAxisTable {
     uint32_t* d_left = nullptr;
     uint32_t* d_count = nullptr;
     float* d_weights = nullptr;
+    // the same three arrays as ONE 2-D table of 32-bit words, [2 + max_taps][dst_len]: row 0 = left, row 1 = count,
+    // rows 2.. = the weights tap by tap -- the TMA resize kernel fetches a group's slice of it with one tensor load
+    uint32_t* d_vtab = nullptr;
     std::vector<uint32_t> h_left, h_count;
     std::vector<float> h_weights;  // [dst_len][max_taps] on the host
     // marching tables for long windows (downsampling), built on first use (kc_resize.cu):
@@ -264,6 +267,10 @@ struct KcTuning {
     int src_soft_cap = 0;    // merge independent outputs that only share SOURCES while the union has <= this many
     int resize_threads = 0;  // threads per CTA of the fused resize kernel (32, 64, 128)
     int jit = 0;             // per-tape specialisation of the fused kernel: 0 auto (hot, long tapes on large planes), 1 always, -1 never
+    int resize_tma = 0;      // fused upsample kernel with tensor-map loads/stores: 0 auto (on), -1 off (the cp.async / STG kernel)
+    int resize_g = 0;        // its output rows per group (8, 16)
+    int resize_rc = 0;       // rows per accumulator chunk of its horizontal pass (4, 8, 16)
+    int resize_minb = 0;     // resident CTAs per SM it is compiled for (6, 8; groups of 8 rows only)
 };
 extern KcTuning g_kc_tuning;
 // kc_jit.cu
@@ -282,6 +289,11 @@ inline int32_t kc_ensure_smem_attr(kc_context* ctx, const void* fn, int bytes) {
 int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out);
 void kc_dev_free(kc_context* ctx, void* p, size_t bytes);
 void kc_dev_trim(kc_context* ctx);
+
+// ---- NUMA placement of pinned host memory (kc_numa.cu) ---------------------------------
+int kc_device_numa_node(int device);                                  // -1: unknown
+int32_t kc_host_alloc_on_node(int node, size_t bytes, void** out);    // page-locked; node < 0: wherever cudaHostAlloc puts it
+int32_t kc_host_release(void* p);                                     // frees either kind
 
 // ---- PNG codec on the host (kc_png.cu) ------------------------------------------
 int32_t kc_png_decode_vec(const uint8_t* data, size_t n, std::vector<uint8_t>& samples, uint32_t& w, uint32_t& h, uint32_t& ch);

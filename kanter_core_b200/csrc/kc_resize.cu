@@ -15,9 +15,13 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 #include "kc_internal.h"
 
@@ -130,10 +134,45 @@ int32_t get_axis(kc_context* ctx, uint32_t src_len, uint32_t dst_len, int filter
     KC_CUDA(cudaMemcpyAsync(t->d_left, t->h_left.data(), sizeof(uint32_t) * dst_len, cudaMemcpyHostToDevice, ctx->stream));
     KC_CUDA(cudaMemcpyAsync(t->d_count, t->h_count.data(), sizeof(uint32_t) * dst_len, cudaMemcpyHostToDevice, ctx->stream));
     KC_CUDA(cudaMemcpyAsync(t->d_weights, wt.data(), sizeof(float) * wt.size(), cudaMemcpyHostToDevice, ctx->stream));
+    {
+        std::vector<uint32_t> vt((size_t)(2 + t->max_taps) * dst_len);
+        memcpy(vt.data(), t->h_left.data(), sizeof(uint32_t) * dst_len);
+        memcpy(vt.data() + dst_len, t->h_count.data(), sizeof(uint32_t) * dst_len);
+        memcpy(vt.data() + 2 * (size_t)dst_len, wt.data(), sizeof(float) * wt.size());
+        KC_CUDA(cudaMalloc((void**)&t->d_vtab, sizeof(uint32_t) * vt.size()));
+        KC_CUDA(cudaMemcpyAsync(t->d_vtab, vt.data(), sizeof(uint32_t) * vt.size(), cudaMemcpyHostToDevice, ctx->stream));
+        KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->axis_tables[key] = t;
     out = t;
     return KC_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+PFN_cuTensorMapEncodeTiled tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled fn = []() -> PFN_cuTensorMapEncodeTiled {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (PFN_cuTensorMapEncodeTiled)p;
+    }();
+    return fn;
+}
+
+// a row-major [rows][cols] array of 32-bit words with a [box_rows][box_cols] box; out-of-bounds elements read as zero
+bool make_tensor_map_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint32_t box_cols, uint32_t box_rows) {
+    PFN_cuTensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 4};
+    const cuuint32_t box[2] = {box_cols, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <bool EXACT>
@@ -450,6 +489,248 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
     }
 }
 
+
+template <bool EXACT, int N, int G>
+__device__ __forceinline__ void ft_vtaps(const float* sp, uint32_t pitch, const float* wc, float one, float2& a0, float2& a1) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(sp + k * pitch);
+        const float wk = wc[k * G];
+        a0 = tap2<EXACT>(a0, make_float2(v.x, v.y), wk, one);
+        a1 = tap2<EXACT>(a1, make_float2(v.z, v.w), wk, one);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The same fused V∘H march with TMA on both sides (the default for every upsample of a plane whose
+// widths are multiples of four): what changes is who moves the bytes.
+//   in : per group ONE 2-D tensor-map load of the source patch (cp.async.bulk.tensor, UTMALDG: prows x pcols,
+//        out-of-bounds columns arrive as zeros) and ONE of the group's slice of the vertical table
+//        ([left | count | tap 0 .. tap n-1] x G rows), both completing on an mbarrier, issued one whole group
+//        ahead by thread 0 -- no per-thread cp.async, no address arithmetic in the other 127 threads;
+//   out: the horizontal pass leaves the clamped G x 512 tile in shared memory (conflict-free STS.128) and thread 0
+//        hands it to the TMA as two 2-D tensor stores (UTMASTG) that clip at the right and bottom edges themselves,
+//        so there is no ragged-tail code and no warp holds 64 accumulators while 16 STG.128 drain.
+// The horizontal pass works on RC rows at a time (RC x 4 accumulators), the tap weights come from L1 (__ldg of the
+// tap-major table: the same 16 KiB every group): ~half the registers of the kernel above, twice the resident warps.
+// Arithmetic, operation order and clamp are those of kc_resize_strip_kernel, bit for bit.
+// ---------------------------------------------------------------------------
+constexpr int FT_THREADS = 128;
+constexpr int FT_TW = FT_THREADS * FS_CPT;      // 512 output columns per CTA
+constexpr int FT_HALF = 256;                    // columns per tensor store (a box side is at most 256 elements)
+
+__device__ __forceinline__ uint32_t ft_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ft_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ft_smem(bar)), "r"(count));
+}
+__device__ __forceinline__ void ft_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ft_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ft_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FT_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FT_DONE;\n"
+        "bra FT_WAIT;\n"
+        "FT_DONE:\n"
+        "}\n" ::"r"(ft_smem(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void ft_tma_load_2d(void* dst, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(ft_smem(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(ft_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void ft_tma_store_2d(const CUtensorMap* map, uint32_t c0, uint32_t c1, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(ft_smem(src)) : "memory");
+}
+
+struct FtLayout {   // byte offsets into dynamic shared memory (host and device agree through this)
+    uint32_t tm, s, s_stage, vt, vt_stage, o, total;
+    __host__ __device__ FtLayout(uint32_t pcols, uint32_t prows, uint32_t vrows, int G) {
+        auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
+        uint32_t p = 128;                                   // two mbarriers live in the first 16 bytes
+        tm = p; p += up(pcols * (uint32_t)(G + 4) * 4u);
+        s_stage = up(prows * pcols * 4u);
+        s = p; p += 2 * s_stage;
+        vt_stage = up(vrows * (uint32_t)G * 4u);
+        vt = p; p += 2 * vt_stage;
+        o = p; p += 2u * (uint32_t)G * FT_HALF * 4u;
+        total = p;
+    }
+};
+
+template <bool EXACT, int G, int RC, int MINB>
+__global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
+    const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_vtab, const __grid_constant__ CUtensorMap tm_dst,
+    uint32_t sh, uint32_t dw, const uint32_t* __restrict__ vleft, uint32_t vtaps,
+    const uint32_t* __restrict__ hleft, const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
+    uint32_t pcols, uint32_t prows, float one, uint32_t row0, uint32_t nrows, float clo, float chi) {
+    static_assert(G % RC == 0 && RC % 4 == 0, "row chunks are whole float4s");
+    constexpr int TP = G + 4;                                       // pitch of the column-major intermediate
+    extern __shared__ __align__(128) unsigned char ftm[];
+    const FtLayout L(pcols, prows, vtaps + 2, G);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(ftm);
+    float* Tm = reinterpret_cast<float*>(ftm + L.tm);
+    const int tid = threadIdx.x;
+    const uint32_t ox0 = blockIdx.x * FT_TW;
+    const uint32_t oxl = min(ox0 + FT_TW, dw) - 1;
+    const uint32_t ngroups = (nrows + G - 1) / G;
+    uint32_t g = blockIdx.y;
+    if (g >= ngroups) return;
+
+    if (tid == 0) {
+        ft_mbar_init(&mbar[0], 1);
+        ft_mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- per-column state, loaded once ----
+    const uint32_t cx0 = __ldg(hleft + ox0), cx1 = __ldg(hleft + oxl) + __ldg(hcount + oxl);
+    const uint32_t ncx = cx1 - cx0;
+    const uint32_t oxt = ox0 + FS_CPT * tid;
+    const bool col_live = oxt <= oxl;                               // dw % 4 == 0: a live thread owns four real columns
+    uint32_t left[FS_CPT], cnt[FS_CPT];
+#pragma unroll
+    for (int c = 0; c < FS_CPT; ++c) {
+        const uint32_t ox = min(oxt + c, oxl);
+        left[c] = __ldg(hleft + ox) - cx0;
+        cnt[c] = __ldg(hcount + ox);
+    }
+    const bool shared_window = left[0] == left[1] && left[0] == left[2] && left[0] == left[3] &&
+                               cnt[0] == cnt[1] && cnt[0] == cnt[2] && cnt[0] == cnt[3];
+    const uint32_t cmax = max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3]));
+    const float4* hw4 = reinterpret_cast<const float4*>(hw + (col_live ? oxt : ox0));   // tap j of my four columns: hw4[j * dw/4]
+    const uint32_t dw4 = dw >> 2;
+    const uint32_t stage_bytes = prows * pcols * 4u + (vtaps + 2) * (uint32_t)G * 4u;
+
+    auto group_row0 = [&](uint32_t gg) { return min(__ldg(vleft + row0 + gg * G), sh - prows); };
+    auto issue = [&](uint32_t gg, int b, uint32_t ry) {               // thread 0 only
+        ft_mbar_expect_tx(&mbar[b], stage_bytes);
+        ft_tma_load_2d(ftm + L.s + b * L.s_stage, &tm_src, cx0, ry, &mbar[b]);
+        ft_tma_load_2d(ftm + L.vt + b * L.vt_stage, &tm_vtab, row0 + gg * G, 0u, &mbar[b]);
+    };
+    __syncthreads();                                                  // the barriers are initialised
+    uint32_t ry0 = group_row0(g);
+    if (tid == 0) issue(g, 0, ry0);
+    uint32_t phase = 0;                                               // bit b: parity stage b completes with next
+    int b = 0;
+    for (; g < ngroups; g += gridDim.y) {
+        const uint32_t gn = g + gridDim.y;
+        uint32_t nry0 = 0;
+        if (gn < ngroups) {
+            nry0 = group_row0(gn);
+            if (tid == 0) issue(gn, b ^ 1, nry0);                     // stage b^1 was drained before the last barrier of the previous group
+        }
+        ft_mbar_wait(&mbar[b], (phase >> b) & 1u);
+        phase ^= 1u << b;
+        const float* S = reinterpret_cast<const float*>(ftm + L.s + b * L.s_stage);
+        const uint32_t* VT = reinterpret_cast<const uint32_t*>(ftm + L.vt + b * L.vt_stage);   // [2 + vtaps][G]
+        const float* WV = reinterpret_cast<const float*>(VT + 2 * G);
+        const uint32_t live_rows = min((uint32_t)G, nrows - g * G);   // rows past the strip compute nothing (their table rows may be real)
+        // ---- vertical pass: Tm[c][r] = sum_k S[vl[r]-ry0+k][c] * wv[k][r] ----
+        const uint32_t nquad = (ncx + 3) >> 2;
+        for (uint32_t i = tid; i < nquad * G; i += FT_THREADS) {
+            const uint32_t cq = i / G, r = i % G;
+            const uint32_t n = r < live_rows ? VT[G + r] : 0u;
+            const float* sp = S + (size_t)(VT[r] - ry0) * pcols + 4 * cq;
+            float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+            const float* wc = WV + r;
+            switch (n) {
+                case 1: ft_vtaps<EXACT, 1, G>(sp, pcols, wc, one, a0, a1); break;
+                case 2: ft_vtaps<EXACT, 2, G>(sp, pcols, wc, one, a0, a1); break;
+                case 3: ft_vtaps<EXACT, 3, G>(sp, pcols, wc, one, a0, a1); break;
+                case 4: ft_vtaps<EXACT, 4, G>(sp, pcols, wc, one, a0, a1); break;
+                case 5: ft_vtaps<EXACT, 5, G>(sp, pcols, wc, one, a0, a1); break;
+                case 6: ft_vtaps<EXACT, 6, G>(sp, pcols, wc, one, a0, a1); break;
+                case 7: ft_vtaps<EXACT, 7, G>(sp, pcols, wc, one, a0, a1); break;
+                case 8: ft_vtaps<EXACT, 8, G>(sp, pcols, wc, one, a0, a1); break;
+                default: break;
+            }
+            float* t = Tm + (size_t)(4 * cq) * TP + r;
+            t[0] = a0.x;
+            t[TP] = a0.y;
+            t[2 * TP] = a1.x;
+            t[3 * TP] = a1.y;
+        }
+        // the tensor stores of the previous group must have READ the staging tile before it is overwritten
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();                                              // Tm complete, stage b drained, staging tile free
+        // ---- horizontal pass, RC rows at a time ----
+        if (col_live) {
+            float* O = reinterpret_cast<float*>(ftm + L.o) + (tid >= FT_HALF / FS_CPT ? (size_t)G * FT_HALF : 0) + FS_CPT * (tid & (FT_HALF / FS_CPT - 1));
+#pragma unroll 1
+            for (int rc = 0; rc < G; rc += RC) {
+                float2 acc[FS_CPT][RC / 2];
+#pragma unroll
+                for (int c = 0; c < FS_CPT; ++c)
+#pragma unroll
+                    for (int q = 0; q < RC / 2; ++q) acc[c][q] = make_float2(0.0f, 0.0f);
+                if (shared_window) {
+                    const float4* t = reinterpret_cast<const float4*>(Tm + (size_t)left[0] * TP + rc);
+#pragma unroll
+                    for (int j = 0; j < FS_MAXT; ++j) {
+                        if ((uint32_t)j < cnt[0]) {
+                            const float4 w4 = __ldg(hw4 + (size_t)j * dw4);
+                            const float w[FS_CPT] = {w4.x, w4.y, w4.z, w4.w};
+                            float4 v[RC / 4];
+#pragma unroll
+                            for (int q = 0; q < RC / 4; ++q) v[q] = t[j * (TP / 4) + q];
+#pragma unroll
+                            for (int c = 0; c < FS_CPT; ++c)
+#pragma unroll
+                                for (int q = 0; q < RC / 4; ++q) {
+                                    acc[c][2 * q] = tap2<EXACT>(acc[c][2 * q], make_float2(v[q].x, v[q].y), w[c], one);
+                                    acc[c][2 * q + 1] = tap2<EXACT>(acc[c][2 * q + 1], make_float2(v[q].z, v[q].w), w[c], one);
+                                }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < FS_MAXT; ++j) {
+                        if ((uint32_t)j < cmax) {
+                            const float4 w4 = __ldg(hw4 + (size_t)j * dw4);   // taps past a column's count are zero padding in the table, and skipped below
+                            const float w[FS_CPT] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int c = 0; c < FS_CPT; ++c) {
+                                if ((uint32_t)j < cnt[c]) {
+                                    const float4* t = reinterpret_cast<const float4*>(Tm + (size_t)(left[c] + j) * TP + rc);
+#pragma unroll
+                                    for (int q = 0; q < RC / 4; ++q) {
+                                        const float4 v = t[q];
+                                        acc[c][2 * q] = tap2<EXACT>(acc[c][2 * q], make_float2(v.x, v.y), w[c], one);
+                                        acc[c][2 * q + 1] = tap2<EXACT>(acc[c][2 * q + 1], make_float2(v.z, v.w), w[c], one);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < RC; ++r) {
+                    float v[FS_CPT];
+#pragma unroll
+                    for (int c = 0; c < FS_CPT; ++c) v[c] = clamp_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi);
+                    *reinterpret_cast<float4*>(O + (size_t)(rc + r) * FT_HALF) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile must be visible to the TMA (async proxy)
+        __syncthreads();                                              // staging tile complete; Tm free for the next group
+        if (tid == 0) {
+            const float* O = reinterpret_cast<const float*>(ftm + L.o);
+            ft_tma_store_2d(&tm_dst, ox0, g * G, O);                  // rows and columns past the result are clipped by the TMA
+            if (ox0 + FT_HALF < dw) ft_tma_store_2d(&tm_dst, ox0 + FT_HALF, g * G, O + (size_t)G * FT_HALF);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ry0 = nry0;
+        b ^= 1;
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the reads of the last stores
+}
+
 // horizontal_sample for LONG windows.  One CTA = 256 adjacent outputs x HT_ROWS rows: the stretch of
 // the intermediate those outputs read is staged in shared memory with coalesced loads (index i
 // lives at i + i/32, so the stride-R reads of neighbouring outputs spread over the banks), and a
@@ -661,6 +942,58 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
     // the [0,1] clamp of image-0.24's horizontal pass (unpinned by the reference's goldens: switchable)
     const float clo = ctx->opts.resize_unclamped ? -INFINITY : 0.0f, chi = ctx->opts.resize_unclamped ? INFINITY : 1.0f;
     static const bool no_fused = getenv("KC_RESIZE_TWO_PASS") != nullptr;
+    // ---- TMA variant: tensor-map loads of the source patch and the vertical table, tensor-map stores of the result ----
+    const bool no_tma = g_kc_tuning.resize_tma <= 0;   // TEMPORARY: opt-in (resize_tma = 1) until the kernel is green on the GPU
+    if (!no_fused && !no_tma && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT && (sw & 3u) == 0 && (dw & 3u) == 0 &&
+        dw >= (uint32_t)FT_TW && nrows >= 16 && (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && tensor_map_encoder()) {
+        // rows per group / rows per accumulator chunk / CTAs per SM: tuning knobs (kc_debug_set_tuning, scripts/resize_sweep.py)
+        const int minb = g_kc_tuning.resize_minb == 8 ? 8 : 6;
+        const int G = g_kc_tuning.resize_g == 16 ? 16 : 8;
+        const int RC = g_kc_tuning.resize_rc == 4 ? 4 : (g_kc_tuning.resize_rc == 16 && G == 16) ? 16 : 8;
+        const uint32_t pcols = (max_window(*th, (uint32_t)FT_TW) + 3u) & ~3u;
+        const uint32_t prows = max_window_sliding(*tv, (uint32_t)G);
+        const uint32_t vrows = tv->max_taps + 2;
+        const FtLayout L(pcols, prows, vrows, G);
+        if (pcols <= 256 && prows <= 256 && pcols <= sw && prows <= sh && L.total <= 200 * 1024) {
+            CUtensorMap m_src, m_vt, m_dst;
+            if (make_tensor_map_2d(&m_src, src, sw, sh, pcols, prows) && make_tensor_map_2d(&m_vt, tv->d_vtab, dh, vrows, (uint32_t)G, vrows) &&
+                make_tensor_map_2d(&m_dst, dst, dw, nrows, (uint32_t)FT_HALF, (uint32_t)G)) {
+                const void* fn = nullptr;
+#define KC_FT(E) (G == 8 ? (RC == 4 ? (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 4, 8> : (const void*)kc_resize_tma_kernel<E, 8, 4, 6>)  \
+                                    : (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 8, 8> : (const void*)kc_resize_tma_kernel<E, 8, 8, 6>)) \
+                         : (RC == 4 ? (const void*)kc_resize_tma_kernel<E, 16, 4, 4> : RC == 8 ? (const void*)kc_resize_tma_kernel<E, 16, 8, 4> : (const void*)kc_resize_tma_kernel<E, 16, 16, 4>))
+                fn = exact_mode ? KC_FT(true) : KC_FT(false);
+#undef KC_FT
+                static std::map<std::tuple<int, const void*, size_t>, int> occ;
+                static std::mutex occ_mu;
+                int per_sm = 1;
+                {
+                    std::lock_guard<std::mutex> lk(occ_mu);
+                    auto it = occ.find(std::make_tuple(ctx->device, fn, (size_t)L.total));
+                    if (it == occ.end()) {
+                        KC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+                        int n = 1;
+                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, FT_THREADS, L.total);
+                        it = occ.emplace(std::make_tuple(ctx->device, fn, (size_t)L.total), std::max(n, 1)).first;
+                    }
+                    per_sm = it->second;
+                }
+                const uint32_t strips = (dw + FT_TW - 1) / FT_TW;
+                const uint32_t ngroups = (nrows + G - 1) / G;
+                const uint32_t lanes = std::max<uint32_t>(1u, std::min<uint32_t>(ngroups, (uint32_t)(ctx->sm_count * per_sm) / std::max(strips, 1u)));
+                dim3 grid(strips, std::min<uint32_t>(lanes, 65535u));
+                KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
+                const float one = 1.0f;
+                void* args[] = {(void*)&m_src, (void*)&m_vt, (void*)&m_dst, (void*)&sh, (void*)&dw, (void*)&tv->d_left, (void*)&tv->max_taps,
+                                (void*)&th->d_left, (void*)&th->d_count, (void*)&th->d_weights, (void*)&pcols, (void*)&prows, (void*)&one,
+                                (void*)&row0, (void*)&nrows, (void*)&clo, (void*)&chi};
+                KC_CUDA(cudaLaunchKernel(fn, grid, dim3(FT_THREADS), args, L.total, ctx->stream));
+                ctx->kernel_launches++;
+                ctx->run_kernels++;
+                return KC_OK;
+            }
+        }
+    }
     if (!no_fused && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT) {
         // threads per CTA: 4 output columns each.  Narrow CTAs (one or two warps) march
         // independently, so no warp waits at a barrier for another's vertical pass.

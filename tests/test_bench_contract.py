@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def run(env_extra):
     env = dict(os.environ, **env_extra)
-    return subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "0"],
+    return subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--steps", "4", "--warmup", "2"],
                           cwd=ROOT, env=env, capture_output=True, text=True, timeout=300)
 
 
@@ -22,10 +22,12 @@ def test_reference_arm_prints_one_contract_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "graph_eval_mpixel_per_s" and d["unit"] == "Mpixel/s"
-    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["value"] > 0
+    assert d["steps"] == 4 and d["warmup"] == 2          # --steps / --warmup are honoured as given (same_steps with our arm)
     assert d["config"]["workload"].startswith("configs[1]")
     cb = d["cpu_baseline"]
-    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert cb["kind"] in ("port", "reference") and cb["sample"] and cb["value"] == d["value"]
+    assert cb["cores"] == len(os.sched_getaffinity(0))   # every core the process may run on, no cap
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
 
@@ -67,3 +69,18 @@ def test_own_arm_prints_one_contract_line():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # the other BASELINE configs ride in the same line, each with ms, bytes, a roofline fraction and a parity verdict
+    w = d["workloads"]
+    assert set(w) == {"height_to_normal_8192", "resize_1024_to_8192_rgba", "graphs32_batch64_4096", "mix_rgba_8192"}
+    for mode in ("fast", "exact"):
+        e = w["height_to_normal_8192"][mode]
+        assert e["ms"] > 0 and 0.2 < e["roofline"]["frac"] <= 1.05 and e["parity"]["ok"] is True, e
+    assert w["height_to_normal_8192"]["exact"]["parity"]["bit_exact"] is True
+    for filt in ("lanczos3", "gaussian"):
+        e = w["resize_1024_to_8192_rgba"][filt]
+        assert e["ms"] > 0 and 0.2 < e["roofline"]["frac"] <= 1.05 and e["parity"]["ok"] is True, e
+    g = w["graphs32_batch64_4096"]
+    assert g["graphs"] == 64 and g["kernels_per_graph"] < 32 and 0.2 < g["roofline"]["frac"] <= 1.05
+    assert g["parity"]["ok"] is True and g["parity"]["samples_outside_1e-5rel_1e-6abs"] == 0, g["parity"]
+    m = w["mix_rgba_8192"]
+    assert m["pixels"] == 8192 * 8192 and 0.3 < m["roofline"]["frac"] <= 1.05 and m["parity"]["ok"] is True, m

@@ -223,6 +223,43 @@ def test_resize_exact_multi_strip(tex_pro, filt, src, dst):
     assert bits_equal(got, oracle.resize_plane(p, dw, dh, int(filt)))
 
 
+def _set_resize_knobs(**kw):
+    from kanter_core_b200._lib import call
+    for k in ("resize_tma", "resize_g", "resize_rc", "resize_minb"):
+        call("kc_debug_set_tuning", k.encode(), int(kw.get(k, 0)))
+
+
+@pytest.mark.parametrize("knobs", [dict(resize_tma=-1), dict(resize_tma=1, resize_g=8, resize_rc=4, resize_minb=6), dict(resize_tma=1, resize_g=8, resize_rc=4, resize_minb=8),
+                                   dict(resize_tma=1, resize_g=8, resize_rc=8, resize_minb=6), dict(resize_tma=1, resize_g=8, resize_rc=8, resize_minb=8),
+                                   dict(resize_tma=1, resize_g=16, resize_rc=4), dict(resize_tma=1, resize_g=16, resize_rc=8), dict(resize_tma=1, resize_g=16, resize_rc=16)],
+                         ids=lambda k: "-".join("%s%d" % (a.split("_")[1], b) for a, b in k.items()))
+@pytest.mark.parametrize("filt", [ResizeFilter.Nearest, ResizeFilter.Triangle, ResizeFilter.CatmullRom, ResizeFilter.Gaussian, ResizeFilter.Lanczos3])
+def test_resize_tensor_map_kernel_every_variant_bit_exact(tex_pro, filt, knobs):
+    """The fused upsample kernel with tensor-map loads and stores (kc_resize_tma_kernel: every compiled combination of
+    rows per group / rows per accumulator chunk / CTAs per SM) and the cp.async/STG kernel it replaces, bit for bit
+    against the oracle: sizes with ragged right edges (dw % 512 != 0), ragged bottom groups, non-integer ratios
+    (no shared windows), strips that start at odd rows, NaN / inf / out-of-range samples."""
+    import ctypes as C
+    from kanter_core_b200._lib import call, kc_image
+    _set_resize_knobs(**knobs)
+    try:
+        for (sw, sh), (dw, dh) in (((96, 80), (768, 640)), ((300, 200), (640, 333)), ((128, 64), (1024 + 512 + 4, 515)), ((64, 40), (520, 47))):
+            p = rnd(13 + sw, sh, sw, -0.25, 1.25)
+            p[sh // 2, sw // 3] = np.nan
+            p[sh // 3, sw // 2] = np.inf
+            p[1, 1] = -np.inf
+            img = kc.SlotImage.from_planes(tex_pro, [p])
+            want = oracle.resize_plane(p, dw, dh, int(filt))
+            got = _resize_direct(tex_pro, img, dw, dh, filt).planes()[0]
+            assert bits_equal(got, want), ((sw, sh), (dw, dh))
+            r0, nr = 7, dh - 18                  # a strip that starts and ends off the group grid
+            out = kc_image()
+            call("kc_resize_rows", tex_pro._ctx._h, C.byref(img._im), dw, dh, int(filt), r0, nr, C.byref(out))
+            assert bits_equal(kc.SlotImage(tex_pro._ctx, out).planes()[0], want[r0:r0 + nr]), ("strip", (sw, sh), (dw, dh))
+    finally:
+        _set_resize_knobs()
+
+
 @pytest.mark.parametrize("mode", ["exact", "fast"])
 @pytest.mark.parametrize("filt", [ResizeFilter.Triangle, ResizeFilter.Lanczos3, ResizeFilter.Gaussian])
 def test_resize_non_finite_values_propagate_like_the_reference(tex_pro, tex_pro_fast, mode, filt):
