@@ -214,6 +214,19 @@ def ours(args, rank, world, local_rank):
         return float(t.item())
 
     math_mode = kc.MATH_FAST if args.math == "fast" else kc.MATH_EXACT
+    # NUMA: this rank's host thread moves next to its GPU (where the cpuset allows) BEFORE any pinned buffer is
+    # allocated or filled; the pinned buffers themselves are placed on the GPU's node by the library (kc_numa.cu)
+    numa = {"device_node": None, "thread_node_before": None, "thread_node": None, "nodes": None, "thread_moved": False}
+    try:
+        dn, tn, nn, moved = C.c_int32(-1), C.c_int32(-1), C.c_int32(0), C.c_int32(0)
+        call("kc_numa_info", local_rank, C.byref(dn), C.byref(tn), C.byref(nn))
+        numa["thread_node_before"] = tn.value
+        if not args.no_numa:
+            call("kc_bind_thread_near_device", local_rank, C.byref(moved))
+        call("kc_numa_info", local_rank, C.byref(dn), C.byref(tn), C.byref(nn))
+        numa.update(device_node=dn.value, thread_node=tn.value, nodes=nn.value, thread_moved=bool(moved.value))
+    except Exception as ex:  # noqa: BLE001 - placement is best effort
+        numa["error"] = repr(ex)[:120]
     tp = kc.TextureProcessor.new(device=local_rank, math_mode=math_mode)
     ctx = tp._ctx._h
 
@@ -413,6 +426,40 @@ def ours(args, rank, world, local_rank):
     elif e2e_u8 is None:
         e2e_u8 = {"unavailable": "another rank failed"}
 
+    # ---- the PCIe ceiling of this box, all ranks at once: plain cudaMemcpyAsync out of / into the same kind of pinned memory ----
+    pcie = None
+    try:
+        probe = kc.pinned_empty((64 << 20,), np.uint8)                    # 64 MiB: one plane
+        probe[...] = 1
+        res = {}
+        for name, direction in (("h2d", 0), ("d2h", 1), ("both", 2)):
+            barrier()
+            a, b = C.c_double(), C.c_double()
+            call("kc_context_pcie_probe", ctx, probe.ctypes.data, probe.nbytes, 12, direction, C.byref(a), C.byref(b))
+            res[name] = (a.value, b.value)
+        kc.free_pinned(probe)
+        mine = [res["h2d"][0], res["d2h"][1], res["both"][0], res["both"][1]]
+    except Exception as ex:  # noqa: BLE001
+        mine = [0.0, 0.0, 0.0, 0.0]
+        numa["probe_error"] = repr(ex)[:160]
+    if dist is not None:
+        allv = [None] * world
+        dist.all_gather_object(allv, (mine, numa))
+    else:
+        allv = [(mine, numa)]
+    if rank == 0:
+        per = [v[0] for v in allv]
+        pcie = {"probe": "12 x 64 MiB plain cudaMemcpyAsync per rank from/to NUMA-placed pinned memory, every rank at once (barrier), CUDA events",
+                "per_rank_h2d_GBs": [round(p[0], 1) for p in per], "per_rank_d2h_GBs": [round(p[1], 1) for p in per],
+                "aggregate_h2d_GBs": round(sum(p[0] for p in per), 1), "aggregate_d2h_GBs": round(sum(p[1] for p in per), 1),
+                "aggregate_duplex_GBs": round(sum(p[2] + p[3] for p in per), 1),
+                "e2e_bytes_per_step_per_rank": int(h2d + d2h),
+                "e2e_aggregate_GBs": round(world * (h2d + d2h) * e2e_steps / e2e_s / 1e9, 1),
+                "numa": [v[1] for v in allv]}
+        ceiling = sum(p[2] + p[3] for p in per)
+        if ceiling > 0:
+            pcie["e2e_fraction_of_duplex_ceiling"] = round(pcie["e2e_aggregate_GBs"] / ceiling, 3)
+
     peak, peak_src = peaks()
     workloads = None
     if not args.no_workloads:
@@ -466,6 +513,8 @@ def ours(args, rank, world, local_rank):
                          "launches_timed": int(kn.value), "peak_source": peak_src,
                          "frac_of_nominal_8TBs": achieved / 8000.0},
         }
+        if pcie is not None:
+            line["pcie"] = pcie
         if workloads is not None:
             line["workloads"] = workloads
         if world == 1 and not args.no_cpu:
@@ -489,6 +538,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-numa", action="store_true", help="leave the host thread where the launcher put it (A/B of the NUMA placement; KC_NO_NUMA=1 also disables the memory placement)")
     ap.add_argument("--no-workloads", action="store_true", help="headline only: skip the `workloads` block (configs[2..4], 8192^2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

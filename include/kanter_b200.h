@@ -165,6 +165,9 @@ int32_t kc_host_free(void* p);
 int32_t kc_host_alloc_near_device(int32_t device, size_t bytes, void** out);   /* free with kc_host_free */
 int32_t kc_numa_info(int32_t device, int32_t* device_node, int32_t* thread_node, int32_t* nodes);
 int32_t kc_bind_thread_near_device(int32_t device, int32_t* bound);
+/* the PCIe ceiling next to it: `reps` plain cudaMemcpyAsync copies of `bytes` between pinned_host and a scratch device buffer,
+ * timed with events; direction 0 host->device, 1 device->host, 2 both at once (half the buffer each way) */
+int32_t kc_context_pcie_probe(kc_context* ctx, void* pinned_host, size_t bytes, int32_t reps, int32_t direction, double* h2d_gbs, double* d2h_gbs);
 
 /* ---- context: replaces TextureProcessor's worker threads,
  *      src/texture_processor.rs:34-56 (engine + transient-buffer queue) ------ */

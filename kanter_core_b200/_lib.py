@@ -76,6 +76,7 @@ SIGNATURES = {
     "kc_host_alloc_near_device": (i32, [i32, sz, P(vp)]),
     "kc_numa_info": (i32, [i32, P(i32), P(i32), P(i32)]),
     "kc_bind_thread_near_device": (i32, [i32, P(i32)]),
+    "kc_context_pcie_probe": (i32, [vp, vp, sz, i32, i32, P(C.c_double), P(C.c_double)]),
     "kc_options_default": (None, [P(kc_options)]),
     "kc_context_create": (i32, [i32, P(kc_options), P(vp)]),
     "kc_context_create_on_stream": (i32, [i32, P(kc_options), vp, P(vp)]),

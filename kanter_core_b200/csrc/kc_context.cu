@@ -172,6 +172,8 @@ static void axis_table_free(KcAxisTable& t) {
     if (t.d_weights) cudaFree(t.d_weights);
     if (t.d_march_w) cudaFree(t.d_march_w);
     if (t.d_march_o) cudaFree(t.d_march_o);
+    if (t.d_vtab) cudaFree(t.d_vtab);
+    t.d_vtab = nullptr;
     t.d_march_w = nullptr;
     t.d_march_o = nullptr;
     t.d_left = t.d_count = nullptr;
@@ -187,6 +189,7 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) try {
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->download_stream);
         if (ctx->dl_staging) cudaFreeAsync(ctx->dl_staging, ctx->stream);
+        if (ctx->d_halo_timeouts) { cudaFree(ctx->d_halo_timeouts); ctx->d_halo_timeouts = nullptr; }
         kc_dev_trim(ctx);
         for (auto& kv : ctx->axis_tables) axis_table_free(*kv.second);
         ctx->axis_tables.clear();
@@ -1004,7 +1007,46 @@ extern "C" int32_t kc_debug_set_tuning(const char* key, int32_t value) try {
     else if (k == "resize_g") g_kc_tuning.resize_g = value;
     else if (k == "resize_rc") g_kc_tuning.resize_rc = value;
     else if (k == "resize_minb") g_kc_tuning.resize_minb = value;
+    else if (k == "resize_store") g_kc_tuning.resize_store = value;
     else KC_FAIL(KC_ERR_INVALID_ARGUMENT, "unknown tuning key '%s'", key);
+    return KC_OK;
+} KC_ABI_CATCH
+
+extern "C" int32_t kc_context_pcie_probe(kc_context* ctx, void* pinned_host, size_t bytes, int32_t reps, int32_t direction,
+                                         double* h2d_gbs, double* d2h_gbs) try {
+    // Plain cudaMemcpyAsync between `pinned_host` and a scratch device buffer, `reps` copies of `bytes` each way, timed
+    // with events: the PCIe ceiling the end-to-end number is judged against.  direction: 0 host->device, 1 device->host,
+    // 2 both at once (upload and download streams, full duplex).
+    if (!ctx || !pinned_host || bytes == 0 || reps <= 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad argument");
+    KcGuard g(ctx);
+    void *d_up = nullptr, *d_dn = nullptr;
+    KC_CUDA(cudaMalloc(&d_up, bytes));
+    if (cudaMalloc(&d_dn, bytes) != cudaSuccess) { cudaFree(d_up); KC_FAIL(KC_ERR_CUDA, "probe buffer allocation failed"); }
+    cudaEvent_t e[4];
+    for (auto& ev : e) cudaEventCreate(&ev);
+    cudaStreamSynchronize(ctx->stream);
+    const bool up = direction == 0 || direction == 2, dn = direction == 1 || direction == 2;
+    // the second half of the host buffer receives the downloads when both directions run, so they do not share pages
+    char* h_dn = (char*)pinned_host + (direction == 2 ? bytes / 2 : 0);
+    const size_t n_up = direction == 2 ? bytes / 2 : bytes, n_dn = n_up;
+    cudaError_t err = cudaSuccess;
+    if (up) cudaEventRecord(e[0], ctx->upload_stream);
+    if (dn) cudaEventRecord(e[2], ctx->download_stream);
+    for (int i = 0; i < reps && err == cudaSuccess; ++i) {
+        if (up) err = cudaMemcpyAsync(d_up, pinned_host, n_up, cudaMemcpyHostToDevice, ctx->upload_stream);
+        if (dn && err == cudaSuccess) err = cudaMemcpyAsync(h_dn, d_dn, n_dn, cudaMemcpyDeviceToHost, ctx->download_stream);
+    }
+    if (up) cudaEventRecord(e[1], ctx->upload_stream);
+    if (dn) cudaEventRecord(e[3], ctx->download_stream);
+    cudaStreamSynchronize(ctx->upload_stream);
+    cudaStreamSynchronize(ctx->download_stream);
+    float ms = 0;
+    if (h2d_gbs) { *h2d_gbs = 0; if (up && cudaEventElapsedTime(&ms, e[0], e[1]) == cudaSuccess && ms > 0) *h2d_gbs = (double)n_up * reps / (ms / 1e3) / 1e9; }
+    if (d2h_gbs) { *d2h_gbs = 0; if (dn && cudaEventElapsedTime(&ms, e[2], e[3]) == cudaSuccess && ms > 0) *d2h_gbs = (double)n_dn * reps / (ms / 1e3) / 1e9; }
+    for (auto& ev : e) cudaEventDestroy(ev);
+    cudaFree(d_up);
+    cudaFree(d_dn);
+    KC_CUDA(err);
     return KC_OK;
 } KC_ABI_CATCH
 

@@ -170,6 +170,7 @@ struct kc_context {
     // 4096-wide map an input error e becomes an output error of about e * W / 2 -- so the 4e-7 of FAST pow would
     // leave the north star's 1e-5 / 1e-6; bit-identical inputs keep FAST HeightToNormal inside it.
     int exact_scope = 0;
+    unsigned int* d_halo_timeouts = nullptr;   // device counter of waits that gave up (this context's kernels only)
     bool halo_used = false;
     uint32_t halo_timeouts_seen = 0;
 };
@@ -270,6 +271,7 @@ struct KcTuning {
     int resize_tma = 0;      // fused upsample kernel with tensor-map loads/stores: 0 auto (on), -1 off (the cp.async / STG kernel)
     int resize_g = 0;        // its output rows per group (8, 16)
     int resize_rc = 0;       // rows per accumulator chunk of its horizontal pass (4, 8, 16)
+    int resize_store = 0;    // 0: one tensor store per G x 256 half of the block's tile; 1: every warp stores its own RC x 128 tiles
     int resize_minb = 0;     // resident CTAs per SM it is compiled for (6, 8; groups of 8 rows only)
 };
 extern KcTuning g_kc_tuning;

@@ -490,12 +490,12 @@ __global__ void __launch_bounds__(THREADS, 512 / THREADS) kc_resize_strip_kernel
 }
 
 
-template <bool EXACT, int N, int G>
+template <bool EXACT, int N, int WP>
 __device__ __forceinline__ void ft_vtaps(const float* sp, uint32_t pitch, const float* wc, float one, float2& a0, float2& a1) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const float4 v = *reinterpret_cast<const float4*>(sp + k * pitch);
-        const float wk = wc[k * G];
+        const float wk = wc[k * WP];
         a0 = tap2<EXACT>(a0, make_float2(v.x, v.y), wk, one);
         a1 = tap2<EXACT>(a1, make_float2(v.z, v.w), wk, one);
     }
@@ -508,16 +508,18 @@ __device__ __forceinline__ void ft_vtaps(const float* sp, uint32_t pitch, const 
 //        out-of-bounds columns arrive as zeros) and ONE of the group's slice of the vertical table
 //        ([left | count | tap 0 .. tap n-1] x G rows), both completing on an mbarrier, issued one whole group
 //        ahead by thread 0 -- no per-thread cp.async, no address arithmetic in the other 127 threads;
-//   out: the horizontal pass leaves the clamped G x 512 tile in shared memory (conflict-free STS.128) and thread 0
-//        hands it to the TMA as two 2-D tensor stores (UTMASTG) that clip at the right and bottom edges themselves,
-//        so there is no ragged-tail code and no warp holds 64 accumulators while 16 STG.128 drain.
+//   out: each warp leaves its clamped RC x 128 tile in shared memory (conflict-free STS.128) and its lane 0 hands it to
+//        the TMA as a 2-D tensor store (UTMASTG) that clips at the right and bottom edges itself: no ragged-tail code,
+//        no warp holding 64 accumulators while 16 STG.128 drain, and -- the tiles being double-buffered per warp --
+//        no block-wide wait for a store: ONE __syncthreads per group (the intermediate is double-buffered too).
 // The horizontal pass works on RC rows at a time (RC x 4 accumulators), the tap weights come from L1 (__ldg of the
 // tap-major table: the same 16 KiB every group): ~half the registers of the kernel above, twice the resident warps.
 // Arithmetic, operation order and clamp are those of kc_resize_strip_kernel, bit for bit.
 // ---------------------------------------------------------------------------
 constexpr int FT_THREADS = 128;
 constexpr int FT_TW = FT_THREADS * FS_CPT;      // 512 output columns per CTA
-constexpr int FT_HALF = 256;                    // columns per tensor store (a box side is at most 256 elements)
+constexpr int FT_WARP_COLS = 32 * FS_CPT;       // 128: the columns one warp computes (and, with WARP_STORE, stages and stores itself)
+constexpr int FT_HALF = 256;                    // columns per block-wide tensor store (a box side is at most 256 elements)
 
 __device__ __forceinline__ uint32_t ft_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ft_mbar_init(uint64_t* bar, uint32_t count) {
@@ -544,26 +546,36 @@ __device__ __forceinline__ void ft_tma_load_2d(void* dst, const CUtensorMap* map
                  "l"(map), "r"(c0), "r"(c1), "r"(ft_smem(bar))
                  : "memory");
 }
-__device__ __forceinline__ void ft_tma_store_2d(const CUtensorMap* map, uint32_t c0, uint32_t c1, const void* src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1), "r"(ft_smem(src)) : "memory");
+__device__ __forceinline__ void ft_tma_store_2d(const CUtensorMap* map, uint32_t c0, uint32_t c1, const void* src, uint64_t policy) {
+    // evict-first in L2, like the st.global.cs of the other kernels: the result is a pure stream nobody re-reads soon
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(ft_smem(src)), "l"(policy)
+                 : "memory");
 }
 
 struct FtLayout {   // byte offsets into dynamic shared memory (host and device agree through this)
-    uint32_t tm, s, s_stage, vt, vt_stage, o, total;
-    __host__ __device__ FtLayout(uint32_t pcols, uint32_t prows, uint32_t vrows, int G) {
+    uint32_t tm, tm_buf, s, s_stage, vt, vt_stage, o, o_buf, total;
+    __host__ __device__ FtLayout(uint32_t pcols, uint32_t prows, uint32_t vrows, int G, int RC, bool warp_store) {
         auto up = [](uint32_t x) { return (x + 127u) & ~127u; };
         uint32_t p = 128;                                   // two mbarriers live in the first 16 bytes
-        tm = p; p += up(pcols * (uint32_t)(G + 4) * 4u);
+        tm_buf = up(pcols * (uint32_t)(G + 4) * 4u);
+        tm = p; p += 2 * tm_buf;                            // the intermediate of this group and of the previous one
         s_stage = up(prows * pcols * 4u);
         s = p; p += 2 * s_stage;
-        vt_stage = up(vrows * (uint32_t)G * 4u);
+        vt_stage = up(vrows * (uint32_t)(G + 4) * 4u);      // G + 4 columns: the slice starts at the 16-byte boundary below its first row
         vt = p; p += 2 * vt_stage;
-        o = p; p += 2u * (uint32_t)G * FT_HALF * 4u;
+        if (warp_store) {
+            o_buf = (uint32_t)RC * FT_WARP_COLS * 4u;       // one warp's RC x 128 result tile
+            o = p; p += (FT_THREADS / 32) * 2u * o_buf;     // two per warp
+        } else {
+            o_buf = (uint32_t)G * FT_HALF * 4u;             // half of the block's G x 512 result tile: one tensor store
+            o = p; p += 2u * o_buf;
+        }
         total = p;
     }
 };
 
-template <bool EXACT, int G, int RC, int MINB>
+template <bool EXACT, int G, int RC, int MINB, bool WARP_STORE>
 __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
     const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_vtab, const __grid_constant__ CUtensorMap tm_dst,
     uint32_t sh, uint32_t dw, const uint32_t* __restrict__ vleft, uint32_t vtaps,
@@ -571,11 +583,13 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
     uint32_t pcols, uint32_t prows, float one, uint32_t row0, uint32_t nrows, float clo, float chi) {
     static_assert(G % RC == 0 && RC % 4 == 0, "row chunks are whole float4s");
     constexpr int TP = G + 4;                                       // pitch of the column-major intermediate
+    constexpr int VP = G + 4;                                       // pitch of the vertical-table slice (see issue())
     extern __shared__ __align__(128) unsigned char ftm[];
-    const FtLayout L(pcols, prows, vtaps + 2, G);
+    const FtLayout L(pcols, prows, vtaps + 2, G, RC, WARP_STORE);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(ftm);
-    float* Tm = reinterpret_cast<float*>(ftm + L.tm);
-    const int tid = threadIdx.x;
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ox0 = blockIdx.x * FT_TW;
     const uint32_t oxl = min(ox0 + FT_TW, dw) - 1;
     const uint32_t ngroups = (nrows + G - 1) / G;
@@ -588,10 +602,13 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // ---- per-column state, loaded once ----
-    const uint32_t cx0 = __ldg(hleft + ox0), cx1 = __ldg(hleft + oxl) + __ldg(hcount + oxl);
+    // A tensor-map box must START on a 16-byte boundary of global memory (an unaligned innermost coordinate is an
+    // illegal-instruction fault): the patch begins at the multiple of four columns at or below the strip's first source column
+    const uint32_t cx0 = __ldg(hleft + ox0) & ~3u, cx1 = __ldg(hleft + oxl) + __ldg(hcount + oxl);
     const uint32_t ncx = cx1 - cx0;
     const uint32_t oxt = ox0 + FS_CPT * tid;
     const bool col_live = oxt <= oxl;                               // dw % 4 == 0: a live thread owns four real columns
+    const bool warp_live = ox0 + (uint32_t)warp * FT_WARP_COLS <= oxl;
     uint32_t left[FS_CPT], cnt[FS_CPT];
 #pragma unroll
     for (int c = 0; c < FS_CPT; ++c) {
@@ -604,49 +621,52 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
     const uint32_t cmax = max(max(cnt[0], cnt[1]), max(cnt[2], cnt[3]));
     const float4* hw4 = reinterpret_cast<const float4*>(hw + (col_live ? oxt : ox0));   // tap j of my four columns: hw4[j * dw/4]
     const uint32_t dw4 = dw >> 2;
-    const uint32_t stage_bytes = prows * pcols * 4u + (vtaps + 2) * (uint32_t)G * 4u;
+    const uint32_t stage_bytes = prows * pcols * 4u + (vtaps + 2) * (uint32_t)VP * 4u;
+    float* Ow = reinterpret_cast<float*>(ftm + L.o + (uint32_t)warp * 2u * L.o_buf);   // this warp's two result tiles
 
     auto group_row0 = [&](uint32_t gg) { return min(__ldg(vleft + row0 + gg * G), sh - prows); };
     auto issue = [&](uint32_t gg, int b, uint32_t ry) {               // thread 0 only
         ft_mbar_expect_tx(&mbar[b], stage_bytes);
         ft_tma_load_2d(ftm + L.s + b * L.s_stage, &tm_src, cx0, ry, &mbar[b]);
-        ft_tma_load_2d(ftm + L.vt + b * L.vt_stage, &tm_vtab, row0 + gg * G, 0u, &mbar[b]);
+        ft_tma_load_2d(ftm + L.vt + b * L.vt_stage, &tm_vtab, (row0 + gg * G) & ~3u, 0u, &mbar[b]);   // same rule: aligned start, G + 4 wide
     };
     __syncthreads();                                                  // the barriers are initialised
     uint32_t ry0 = group_row0(g);
     if (tid == 0) issue(g, 0, ry0);
     uint32_t phase = 0;                                               // bit b: parity stage b completes with next
+    uint32_t chunk = 0;                                               // result tiles this warp has handed to the TMA
     int b = 0;
     for (; g < ngroups; g += gridDim.y) {
         const uint32_t gn = g + gridDim.y;
         uint32_t nry0 = 0;
         if (gn < ngroups) {
             nry0 = group_row0(gn);
-            if (tid == 0) issue(gn, b ^ 1, nry0);                     // stage b^1 was drained before the last barrier of the previous group
+            if (tid == 0) issue(gn, b ^ 1, nry0);                     // stage b^1 was drained before the barrier of the previous group
         }
         ft_mbar_wait(&mbar[b], (phase >> b) & 1u);
         phase ^= 1u << b;
         const float* S = reinterpret_cast<const float*>(ftm + L.s + b * L.s_stage);
-        const uint32_t* VT = reinterpret_cast<const uint32_t*>(ftm + L.vt + b * L.vt_stage);   // [2 + vtaps][G]
-        const float* WV = reinterpret_cast<const float*>(VT + 2 * G);
+        const uint32_t* VT = reinterpret_cast<const uint32_t*>(ftm + L.vt + b * L.vt_stage) + ((row0 + g * G) & 3u);   // [2 + vtaps][VP], this group's first row
+        const float* WV = reinterpret_cast<const float*>(VT + 2 * VP);
+        float* Tm = reinterpret_cast<float*>(ftm + L.tm + b * L.tm_buf);   // the other one may still be read by a slower warp's horizontal pass
         const uint32_t live_rows = min((uint32_t)G, nrows - g * G);   // rows past the strip compute nothing (their table rows may be real)
         // ---- vertical pass: Tm[c][r] = sum_k S[vl[r]-ry0+k][c] * wv[k][r] ----
         const uint32_t nquad = (ncx + 3) >> 2;
         for (uint32_t i = tid; i < nquad * G; i += FT_THREADS) {
             const uint32_t cq = i / G, r = i % G;
-            const uint32_t n = r < live_rows ? VT[G + r] : 0u;
+            const uint32_t n = r < live_rows ? VT[VP + r] : 0u;
             const float* sp = S + (size_t)(VT[r] - ry0) * pcols + 4 * cq;
             float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
             const float* wc = WV + r;
             switch (n) {
-                case 1: ft_vtaps<EXACT, 1, G>(sp, pcols, wc, one, a0, a1); break;
-                case 2: ft_vtaps<EXACT, 2, G>(sp, pcols, wc, one, a0, a1); break;
-                case 3: ft_vtaps<EXACT, 3, G>(sp, pcols, wc, one, a0, a1); break;
-                case 4: ft_vtaps<EXACT, 4, G>(sp, pcols, wc, one, a0, a1); break;
-                case 5: ft_vtaps<EXACT, 5, G>(sp, pcols, wc, one, a0, a1); break;
-                case 6: ft_vtaps<EXACT, 6, G>(sp, pcols, wc, one, a0, a1); break;
-                case 7: ft_vtaps<EXACT, 7, G>(sp, pcols, wc, one, a0, a1); break;
-                case 8: ft_vtaps<EXACT, 8, G>(sp, pcols, wc, one, a0, a1); break;
+                case 1: ft_vtaps<EXACT, 1, VP>(sp, pcols, wc, one, a0, a1); break;
+                case 2: ft_vtaps<EXACT, 2, VP>(sp, pcols, wc, one, a0, a1); break;
+                case 3: ft_vtaps<EXACT, 3, VP>(sp, pcols, wc, one, a0, a1); break;
+                case 4: ft_vtaps<EXACT, 4, VP>(sp, pcols, wc, one, a0, a1); break;
+                case 5: ft_vtaps<EXACT, 5, VP>(sp, pcols, wc, one, a0, a1); break;
+                case 6: ft_vtaps<EXACT, 6, VP>(sp, pcols, wc, one, a0, a1); break;
+                case 7: ft_vtaps<EXACT, 7, VP>(sp, pcols, wc, one, a0, a1); break;
+                case 8: ft_vtaps<EXACT, 8, VP>(sp, pcols, wc, one, a0, a1); break;
                 default: break;
             }
             float* t = Tm + (size_t)(4 * cq) * TP + r;
@@ -655,12 +675,11 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
             t[2 * TP] = a1.x;
             t[3 * TP] = a1.y;
         }
-        // the tensor stores of the previous group must have READ the staging tile before it is overwritten
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        __syncthreads();                                              // Tm complete, stage b drained, staging tile free
+        // block-wide stores: the two tensor stores of the previous group must have READ the tile before it is overwritten
+        if (!WARP_STORE && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncthreads();                                              // Tm complete, stage b drained (the ONE barrier per group with WARP_STORE)
         // ---- horizontal pass, RC rows at a time ----
-        if (col_live) {
-            float* O = reinterpret_cast<float*>(ftm + L.o) + (tid >= FT_HALF / FS_CPT ? (size_t)G * FT_HALF : 0) + FS_CPT * (tid & (FT_HALF / FS_CPT - 1));
+        if (warp_live) {
 #pragma unroll 1
             for (int rc = 0; rc < G; rc += RC) {
                 float2 acc[FS_CPT][RC / 2];
@@ -708,27 +727,52 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
                         }
                     }
                 }
+                if (WARP_STORE) {
+                    // each warp stages and stores its own RC x 128 tile; the store issued two tiles ago must have READ this buffer
+                    if (lane == 0 && chunk >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    float* O = Ow + (chunk & 1u) * (size_t)(RC * FT_WARP_COLS) + FS_CPT * lane;
 #pragma unroll
-                for (int r = 0; r < RC; ++r) {
-                    float v[FS_CPT];
+                    for (int r = 0; r < RC; ++r) {
+                        float v[FS_CPT];
 #pragma unroll
-                    for (int c = 0; c < FS_CPT; ++c) v[c] = clamp_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi);
-                    *reinterpret_cast<float4*>(O + (size_t)(rc + r) * FT_HALF) = make_float4(v[0], v[1], v[2], v[3]);
+                        for (int c = 0; c < FS_CPT; ++c) v[c] = clamp_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi);
+                        *reinterpret_cast<float4*>(O + (size_t)r * FT_WARP_COLS) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile must be visible to the TMA (async proxy)
+                    __syncwarp();
+                    if (lane == 0) {                                      // rows and columns past the result are clipped by the TMA
+                        ft_tma_store_2d(&tm_dst, ox0 + (uint32_t)warp * FT_WARP_COLS, g * G + rc, Ow + (chunk & 1u) * (size_t)(RC * FT_WARP_COLS), policy);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++chunk;
+                } else {
+                    // the block's G x 512 tile as two G x 256 halves: thread t owns columns 4t .. 4t+3
+                    float* O = reinterpret_cast<float*>(ftm + L.o) + (tid >= FT_HALF / FS_CPT ? (size_t)G * FT_HALF : 0) + FS_CPT * (tid & (FT_HALF / FS_CPT - 1));
+#pragma unroll
+                    for (int r = 0; r < RC; ++r) {
+                        float v[FS_CPT];
+#pragma unroll
+                        for (int c = 0; c < FS_CPT; ++c) v[c] = clamp_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi);
+                        *reinterpret_cast<float4*>(O + (size_t)(rc + r) * FT_HALF) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
                 }
             }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile must be visible to the TMA (async proxy)
-        __syncthreads();                                              // staging tile complete; Tm free for the next group
-        if (tid == 0) {
-            const float* O = reinterpret_cast<const float*>(ftm + L.o);
-            ft_tma_store_2d(&tm_dst, ox0, g * G, O);                  // rows and columns past the result are clipped by the TMA
-            if (ox0 + FT_HALF < dw) ft_tma_store_2d(&tm_dst, ox0 + FT_HALF, g * G, O + (size_t)G * FT_HALF);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (!WARP_STORE) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile must be visible to the TMA (async proxy)
+            __syncthreads();                                              // tile complete
+            if (tid == 0) {
+                const float* O = reinterpret_cast<const float*>(ftm + L.o);
+                ft_tma_store_2d(&tm_dst, ox0, g * G, O, policy);          // rows and columns past the result are clipped by the TMA
+                if (ox0 + FT_HALF < dw) ft_tma_store_2d(&tm_dst, ox0 + FT_HALF, g * G, O + (size_t)G * FT_HALF, policy);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
         }
         ry0 = nry0;
         b ^= 1;
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the reads of the last stores
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the reads of the last stores
 }
 
 // horizontal_sample for LONG windows.  One CTA = 256 adjacent outputs x HT_ROWS rows: the stretch of
@@ -947,22 +991,31 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
     if (!no_fused && !no_tma && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT && (sw & 3u) == 0 && (dw & 3u) == 0 &&
         dw >= (uint32_t)FT_TW && nrows >= 16 && (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && tensor_map_encoder()) {
         // rows per group / rows per accumulator chunk / CTAs per SM: tuning knobs (kc_debug_set_tuning, scripts/resize_sweep.py)
-        const int minb = g_kc_tuning.resize_minb == 8 ? 8 : 6;
+        const int minb = g_kc_tuning.resize_minb == 8 ? 8 : g_kc_tuning.resize_minb == 4 ? 4 : 6;
         const int G = g_kc_tuning.resize_g == 16 ? 16 : 8;
         const int RC = g_kc_tuning.resize_rc == 4 ? 4 : (g_kc_tuning.resize_rc == 16 && G == 16) ? 16 : 8;
-        const uint32_t pcols = (max_window(*th, (uint32_t)FT_TW) + 3u) & ~3u;
+        uint32_t pcols = 0;                                 // widest patch of any strip, from the 16-byte boundary below its first column
+        for (uint32_t o0 = 0; o0 < dw; o0 += (uint32_t)FT_TW) {
+            const uint32_t ol = std::min(o0 + (uint32_t)FT_TW, dw) - 1;
+            pcols = std::max(pcols, th->h_left[ol] + th->h_count[ol] - (th->h_left[o0] & ~3u));
+        }
+        pcols = (pcols + 3u) & ~3u;
         const uint32_t prows = max_window_sliding(*tv, (uint32_t)G);
         const uint32_t vrows = tv->max_taps + 2;
-        const FtLayout L(pcols, prows, vrows, G);
+        const bool warp_store = g_kc_tuning.resize_store == 1;     // 0: the block stores G x 256 halves (default), 1: each warp stores its RC x 128 tiles
+        const FtLayout L(pcols, prows, vrows, G, RC, warp_store);
         if (pcols <= 256 && prows <= 256 && pcols <= sw && prows <= sh && L.total <= 200 * 1024) {
             CUtensorMap m_src, m_vt, m_dst;
-            if (make_tensor_map_2d(&m_src, src, sw, sh, pcols, prows) && make_tensor_map_2d(&m_vt, tv->d_vtab, dh, vrows, (uint32_t)G, vrows) &&
-                make_tensor_map_2d(&m_dst, dst, dw, nrows, (uint32_t)FT_HALF, (uint32_t)G)) {
+            if (make_tensor_map_2d(&m_src, src, sw, sh, pcols, prows) && make_tensor_map_2d(&m_vt, tv->d_vtab, dh, vrows, (uint32_t)G + 4u, vrows) &&
+                make_tensor_map_2d(&m_dst, dst, dw, nrows, warp_store ? (uint32_t)FT_WARP_COLS : (uint32_t)FT_HALF, warp_store ? (uint32_t)RC : (uint32_t)G)) {
                 const void* fn = nullptr;
-#define KC_FT(E) (G == 8 ? (RC == 4 ? (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 4, 8> : (const void*)kc_resize_tma_kernel<E, 8, 4, 6>)  \
-                                    : (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 8, 8> : (const void*)kc_resize_tma_kernel<E, 8, 8, 6>)) \
-                         : (RC == 4 ? (const void*)kc_resize_tma_kernel<E, 16, 4, 4> : RC == 8 ? (const void*)kc_resize_tma_kernel<E, 16, 8, 4> : (const void*)kc_resize_tma_kernel<E, 16, 16, 4>))
+#define KC_FT2(E, W) (G == 8 ? (RC == 4 ? (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 4, 8, W> : (const void*)kc_resize_tma_kernel<E, 8, 4, 6, W>)   \
+                                        : (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 8, 8, W> : (const void*)kc_resize_tma_kernel<E, 8, 8, 6, W>))  \
+                             : (RC == 4 ? (minb >= 6 ? (const void*)kc_resize_tma_kernel<E, 16, 4, 6, W> : (const void*)kc_resize_tma_kernel<E, 16, 4, 4, W>)  \
+                                        : RC == 8 ? (const void*)kc_resize_tma_kernel<E, 16, 8, 4, W> : (const void*)kc_resize_tma_kernel<E, 16, 16, 4, W>))
+#define KC_FT(E) (warp_store ? KC_FT2(E, true) : KC_FT2(E, false))
                 fn = exact_mode ? KC_FT(true) : KC_FT(false);
+#undef KC_FT2
 #undef KC_FT
                 static std::map<std::tuple<int, const void*, size_t>, int> occ;
                 static std::mutex occ_mu;

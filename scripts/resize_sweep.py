@@ -39,7 +39,7 @@ def main():
     L = kc.SlotImage.from_planes(tp, [np.random.default_rng(4).random((S, S), dtype=np.float32)])
 
     def set_knobs(**kw):
-        for k in ("resize_tma", "resize_g", "resize_rc", "resize_minb", "resize_threads"):
+        for k in ("resize_tma", "resize_g", "resize_rc", "resize_minb", "resize_threads", "resize_store"):
             call("kc_debug_set_tuning", k.encode(), int(kw.get(k, 0)))
 
     def time_filter(filt):
@@ -66,8 +66,9 @@ def main():
         for rc in (4, 8, 16):
             if rc > g:
                 continue
-            for mb in ((6, 8) if g == 8 else (6,)):
-                variants.append(("tma_G%d_RC%d_MINB%d" % (g, rc, mb), dict(resize_tma=1, resize_g=g, resize_rc=rc, resize_minb=mb)))
+            for mb in ((6, 8) if g == 8 else ((4, 6) if rc == 4 else (4,))):
+                for st in (0, 1):
+                    variants.append(("tma_%s_G%d_RC%d_MINB%d" % ("warp" if st else "block", g, rc, mb), dict(resize_tma=1, resize_g=g, resize_rc=rc, resize_minb=mb, resize_store=st)))
     rows = []
     alg = D * D * 4 + S * S * 4
     for name, kw in variants:
