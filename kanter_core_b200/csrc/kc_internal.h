@@ -269,9 +269,9 @@ struct KcTuning {
     int resize_threads = 0;  // threads per CTA of the fused resize kernel (32, 64, 128)
     int jit = 0;             // per-tape specialisation of the fused kernel: 0 auto (hot, long tapes on large planes), 1 always, -1 never
     int resize_tma = 0;      // fused upsample kernel with tensor-map loads/stores: 0 auto (on), -1 off (the cp.async / STG kernel)
-    int resize_g = 0;        // its output rows per group (8, 16)
+    int resize_g = 0;        // its output rows per group (8, 16; default 16)
     int resize_rc = 0;       // rows per accumulator chunk of its horizontal pass (4, 8, 16)
-    int resize_store = 0;    // 0: one tensor store per G x 256 half of the block's tile; 1: every warp stores its own RC x 128 tiles
+    int resize_store = 0;    // 0 auto (every warp stores its own RC x 128 tiles); -1: one tensor store per G x 256 half of the block's tile
     int resize_minb = 0;     // resident CTAs per SM it is compiled for (6, 8; groups of 8 rows only)
 };
 extern KcTuning g_kc_tuning;

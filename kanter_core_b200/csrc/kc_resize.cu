@@ -553,6 +553,16 @@ __device__ __forceinline__ void ft_tma_store_2d(const CUtensorMap* map, uint32_t
                  : "memory");
 }
 
+// clamp to [lo, hi]; `sat`: the bounds are [0, 1] and a is known to be a number, so one saturating add does it
+__device__ __forceinline__ float ft_clamp(float a, float lo, float hi, bool sat) {
+    if (sat) {
+        float r;
+        asm("add.rn.sat.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(a));
+        return r;
+    }
+    return clamp_keep_nan(a, lo, hi);
+}
+
 struct FtLayout {   // byte offsets into dynamic shared memory (host and device agree through this)
     uint32_t tm, tm_buf, s, s_stage, vt, vt_stage, o, o_buf, total;
     __host__ __device__ FtLayout(uint32_t pcols, uint32_t prows, uint32_t vrows, int G, int RC, bool warp_store) {
@@ -587,6 +597,11 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
     extern __shared__ __align__(128) unsigned char ftm[];
     const FtLayout L(pcols, prows, vtaps + 2, G, RC, WARP_STORE);
     uint64_t* mbar = reinterpret_cast<uint64_t*>(ftm);
+    // nonfinite[i % 3]: some thread saw a NaN or an infinity in the intermediate of the i-th group this block processes.  A group
+    // without any takes the one-instruction clamp below.  Three flags: the one of group i + 2 is cleared between the barriers
+    // of groups i and i + 1, when nobody can be writing it.
+    volatile uint32_t* nonfinite = reinterpret_cast<volatile uint32_t*>(ftm + 16);
+    const bool unit_clamp = clo == 0.0f && chi == 1.0f;              // image-0.24's clamp; (-inf, +inf) when the caller switched it off
     uint64_t policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -600,6 +615,7 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
         ft_mbar_init(&mbar[0], 1);
         ft_mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        nonfinite[0] = nonfinite[1] = nonfinite[2] = 0u;
     }
     // ---- per-column state, loaded once ----
     // A tensor-map box must START on a 16-byte boundary of global memory (an unaligned innermost coordinate is an
@@ -635,6 +651,7 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
     if (tid == 0) issue(g, 0, ry0);
     uint32_t phase = 0;                                               // bit b: parity stage b completes with next
     uint32_t chunk = 0;                                               // result tiles this warp has handed to the TMA
+    uint32_t it = 0;                                                  // groups this block has processed, mod 3
     int b = 0;
     for (; g < ngroups; g += gridDim.y) {
         const uint32_t gn = g + gridDim.y;
@@ -674,10 +691,21 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
             t[TP] = a0.y;
             t[2 * TP] = a1.x;
             t[3 * TP] = a1.y;
+            // NaN-propagating maximum of the four magnitudes: anything but a finite number raises the group's flag
+            float m0, m1;
+            asm("max.NaN.f32 %0, %1, %2;" : "=f"(m0) : "f"(fabsf(a0.x)), "f"(fabsf(a0.y)));
+            asm("max.NaN.f32 %0, %1, %2;" : "=f"(m1) : "f"(fabsf(a1.x)), "f"(fabsf(a1.y)));
+            asm("max.NaN.f32 %0, %1, %2;" : "=f"(m0) : "f"(m0), "f"(m1));
+            if (!(m0 <= 3.402823466e+38f)) nonfinite[it] = 1u;
         }
         // block-wide stores: the two tensor stores of the previous group must have READ the tile before it is overwritten
         if (!WARP_STORE && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();                                              // Tm complete, stage b drained (the ONE barrier per group with WARP_STORE)
+        // Every intermediate finite => every horizontal sum is a number (an overflow gives +-inf, never inf - inf), and
+        // clamp(x, 0, 1) of a number is ONE saturating add of +0 (FADD.SAT) instead of min.NaN + max.NaN: rn(x + 0) == x,
+        // -0 cannot occur (the sums start from +0).  A group that holds a NaN or an infinity keeps the two-instruction clamp.
+        const bool sat = unit_clamp && nonfinite[it] == 0u;
+        if (tid == 0) nonfinite[it == 0 ? 2 : it - 1] = 0u;           // == (it + 2) % 3: next used two barriers from here
         // ---- horizontal pass, RC rows at a time ----
         if (warp_live) {
 #pragma unroll 1
@@ -736,7 +764,7 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
                     for (int r = 0; r < RC; ++r) {
                         float v[FS_CPT];
 #pragma unroll
-                        for (int c = 0; c < FS_CPT; ++c) v[c] = clamp_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi);
+                        for (int c = 0; c < FS_CPT; ++c) v[c] = ft_clamp((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi, sat);
                         *reinterpret_cast<float4*>(O + (size_t)r * FT_WARP_COLS) = make_float4(v[0], v[1], v[2], v[3]);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile must be visible to the TMA (async proxy)
@@ -753,7 +781,7 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
                     for (int r = 0; r < RC; ++r) {
                         float v[FS_CPT];
 #pragma unroll
-                        for (int c = 0; c < FS_CPT; ++c) v[c] = clamp_keep_nan((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi);
+                        for (int c = 0; c < FS_CPT; ++c) v[c] = ft_clamp((r & 1) ? acc[c][r >> 1].y : acc[c][r >> 1].x, clo, chi, sat);
                         *reinterpret_cast<float4*>(O + (size_t)(rc + r) * FT_HALF) = make_float4(v[0], v[1], v[2], v[3]);
                     }
                 }
@@ -771,6 +799,7 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
         }
         ry0 = nry0;
         b ^= 1;
+        it = it == 2 ? 0 : it + 1;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the reads of the last stores
 }
@@ -987,22 +1016,16 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
     const float clo = ctx->opts.resize_unclamped ? -INFINITY : 0.0f, chi = ctx->opts.resize_unclamped ? INFINITY : 1.0f;
     static const bool no_fused = getenv("KC_RESIZE_TWO_PASS") != nullptr;
     // ---- TMA variant: tensor-map loads of the source patch and the vertical table, tensor-map stores of the result ----
-    const bool no_tma = g_kc_tuning.resize_tma <= 0;   // TEMPORARY: opt-in (resize_tma = 1) until the kernel is green on the GPU
+    const bool no_tma = g_kc_tuning.resize_tma < 0;
     if (!no_fused && !no_tma && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT && (sw & 3u) == 0 && (dw & 3u) == 0 &&
-        dw >= (uint32_t)FT_TW && nrows >= 16 && (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && tensor_map_encoder()) {
+        dw >= (uint32_t)FT_TW && nrows >= 32 && (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && tensor_map_encoder()) {
         // rows per group / rows per accumulator chunk / CTAs per SM: tuning knobs (kc_debug_set_tuning, scripts/resize_sweep.py)
-        const int minb = g_kc_tuning.resize_minb == 8 ? 8 : g_kc_tuning.resize_minb == 4 ? 4 : 6;
-        const int G = g_kc_tuning.resize_g == 16 ? 16 : 8;
-        const int RC = g_kc_tuning.resize_rc == 4 ? 4 : (g_kc_tuning.resize_rc == 16 && G == 16) ? 16 : 8;
-        uint32_t pcols = 0;                                 // widest patch of any strip, from the 16-byte boundary below its first column
-        for (uint32_t o0 = 0; o0 < dw; o0 += (uint32_t)FT_TW) {
-            const uint32_t ol = std::min(o0 + (uint32_t)FT_TW, dw) - 1;
-            pcols = std::max(pcols, th->h_left[ol] + th->h_count[ol] - (th->h_left[o0] & ~3u));
-        }
-        pcols = (pcols + 3u) & ~3u;
-        const uint32_t prows = max_window_sliding(*tv, (uint32_t)G);
-        const uint32_t vrows = tv->max_taps + 2;
-        const bool warp_store = g_kc_tuning.resize_store == 1;     // 0: the block stores G x 256 halves (default), 1: each warp stores its RC x 128 tiles
+        // defaults from profiles/resize_sweep_r02_{fast,exact}.json: every warp stores its own tiles; FAST 16-row groups in
+        // 4-row chunks, EXACT (twice the floating-point instructions per tap) 32-row groups in 8-row chunks
+        const int G = g_kc_tuning.resize_g == 8 ? 8 : g_kc_tuning.resize_g == 32 ? 32 : g_kc_tuning.resize_g == 16 ? 16 : (exact_mode ? 32 : 16);
+        const int minb = g_kc_tuning.resize_minb == 8 ? 8 : g_kc_tuning.resize_minb == 6 ? 6 : g_kc_tuning.resize_minb == 4 ? 4 : (G >= 16 ? 4 : 6);
+        const int RC = g_kc_tuning.resize_rc == 8 ? 8 : (g_kc_tuning.resize_rc == 16 && G == 16) ? 16 : g_kc_tuning.resize_rc == 4 ? 4 : (exact_mode ? 8 : 4);
+        const bool warp_store = g_kc_tuning.resize_store >= 0;     // default: each warp stores its RC x 128 tiles; -1: the block stores G x 256 halves
         const FtLayout L(pcols, prows, vrows, G, RC, warp_store);
         if (pcols <= 256 && prows <= 256 && pcols <= sw && prows <= sh && L.total <= 200 * 1024) {
             CUtensorMap m_src, m_vt, m_dst;
@@ -1011,8 +1034,9 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
                 const void* fn = nullptr;
 #define KC_FT2(E, W) (G == 8 ? (RC == 4 ? (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 4, 8, W> : (const void*)kc_resize_tma_kernel<E, 8, 4, 6, W>)   \
                                         : (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 8, 8, W> : (const void*)kc_resize_tma_kernel<E, 8, 8, 6, W>))  \
-                             : (RC == 4 ? (minb >= 6 ? (const void*)kc_resize_tma_kernel<E, 16, 4, 6, W> : (const void*)kc_resize_tma_kernel<E, 16, 4, 4, W>)  \
-                                        : RC == 8 ? (const void*)kc_resize_tma_kernel<E, 16, 8, 4, W> : (const void*)kc_resize_tma_kernel<E, 16, 16, 4, W>))
+                      : G == 16 ? (RC == 4 ? (minb >= 6 ? (const void*)kc_resize_tma_kernel<E, 16, 4, 6, W> : (const void*)kc_resize_tma_kernel<E, 16, 4, 4, W>)  \
+                                        : RC == 8 ? (const void*)kc_resize_tma_kernel<E, 16, 8, 4, W> : (const void*)kc_resize_tma_kernel<E, 16, 16, 4, W>)    \
+                                : (RC == 4 ? (const void*)kc_resize_tma_kernel<E, 32, 4, 4, W> : (const void*)kc_resize_tma_kernel<E, 32, 8, 4, W>))
 #define KC_FT(E) (warp_store ? KC_FT2(E, true) : KC_FT2(E, false))
                 fn = exact_mode ? KC_FT(true) : KC_FT(false);
 #undef KC_FT2

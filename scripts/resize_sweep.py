@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--src", type=int, default=1024)
     ap.add_argument("--dst", type=int, default=8192)
+    ap.add_argument("--all", action="store_true", help="every compiled variant (default: the shortlist)")
     args = ap.parse_args()
     tp = kc.TextureProcessor.new(math_mode=kc.MATH_FAST if args.math == "fast" else kc.MATH_EXACT)
     ctx = tp._ctx._h
@@ -62,13 +63,17 @@ def main():
         return ms.value / args.reps
 
     variants = [("strip_r01_128thr", dict(resize_tma=-1)), ("strip_r01_64thr", dict(resize_tma=-1, resize_threads=64))]
-    for g in (8, 16):
-        for rc in (4, 8, 16):
-            if rc > g:
-                continue
-            for mb in ((6, 8) if g == 8 else ((4, 6) if rc == 4 else (4,))):
-                for st in (0, 1):
-                    variants.append(("tma_%s_G%d_RC%d_MINB%d" % ("warp" if st else "block", g, rc, mb), dict(resize_tma=1, resize_g=g, resize_rc=rc, resize_minb=mb, resize_store=st)))
+    if args.all:
+        for g in (8, 16, 32):
+            for rc in (4, 8, 16):
+                if rc > g or (g == 32 and rc == 16):
+                    continue
+                for mb in ((6, 8) if g == 8 else ((4, 6) if (rc == 4 and g == 16) else (4,))):
+                    for st in (-1, 1):
+                        variants.append(("tma_%s_G%d_RC%d_MINB%d" % ("warp" if st > 0 else "block", g, rc, mb), dict(resize_tma=1, resize_g=g, resize_rc=rc, resize_minb=mb, resize_store=st)))
+    else:
+        for g, rc, mb, st in ((16, 4, 4, 1), (16, 8, 4, 1), (32, 4, 4, 1), (32, 8, 4, 1), (32, 4, 4, -1), (32, 8, 4, -1), (16, 8, 4, -1)):
+            variants.append(("tma_%s_G%d_RC%d_MINB%d" % ("warp" if st > 0 else "block", g, rc, mb), dict(resize_tma=1, resize_g=g, resize_rc=rc, resize_minb=mb, resize_store=st)))
     rows = []
     alg = D * D * 4 + S * S * 4
     for name, kw in variants:

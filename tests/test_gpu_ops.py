@@ -229,12 +229,13 @@ def _set_resize_knobs(**kw):
         call("kc_debug_set_tuning", k.encode(), int(kw.get(k, 0)))
 
 
-@pytest.mark.parametrize("knobs", [dict(resize_tma=-1), dict(resize_tma=1, resize_g=8, resize_rc=4, resize_minb=6), dict(resize_tma=1, resize_g=8, resize_rc=4, resize_minb=8),
-                                   dict(resize_tma=1, resize_g=8, resize_rc=8, resize_minb=6), dict(resize_tma=1, resize_g=8, resize_rc=8, resize_minb=8),
-                                   dict(resize_tma=1, resize_g=16, resize_rc=4, resize_minb=4), dict(resize_tma=1, resize_g=16, resize_rc=4, resize_minb=6),
-                                   dict(resize_tma=1, resize_g=16, resize_rc=8), dict(resize_tma=1, resize_g=16, resize_rc=16),
-                                   dict(resize_tma=1, resize_g=8, resize_rc=8, resize_store=1), dict(resize_tma=1, resize_g=16, resize_rc=4, resize_store=1),
-                                   dict(resize_tma=1, resize_g=16, resize_rc=8, resize_store=1)],
+@pytest.mark.parametrize("knobs", [dict(resize_tma=-1), dict(resize_store=-1, resize_g=8, resize_rc=4, resize_minb=6), dict(resize_store=-1, resize_g=8, resize_rc=4, resize_minb=8),
+                                   dict(resize_store=-1, resize_g=8, resize_rc=8, resize_minb=6), dict(resize_store=-1, resize_g=8, resize_rc=8, resize_minb=8),
+                                   dict(resize_store=-1, resize_g=16, resize_rc=4, resize_minb=4), dict(resize_store=-1, resize_g=16, resize_rc=4, resize_minb=6),
+                                   dict(resize_store=-1, resize_g=16, resize_rc=8), dict(resize_store=-1, resize_g=16, resize_rc=16),
+                                   dict(resize_g=8, resize_rc=8), dict(resize_g=8, resize_rc=4, resize_minb=8), dict(resize_g=16, resize_rc=4),
+                                   dict(resize_g=16, resize_rc=8), dict(resize_g=16, resize_rc=16), dict(resize_g=32, resize_rc=4), dict(resize_g=32, resize_rc=8),
+                                   dict(resize_store=-1, resize_g=32, resize_rc=8)],
                          ids=lambda k: "-".join("%s%d" % (a.split("_")[1], b) for a, b in k.items()))
 @pytest.mark.parametrize("filt", [ResizeFilter.Nearest, ResizeFilter.Triangle, ResizeFilter.CatmullRom, ResizeFilter.Gaussian, ResizeFilter.Lanczos3])
 def test_resize_tensor_map_kernel_every_variant_bit_exact(tex_pro, filt, knobs):
