@@ -1025,6 +1025,14 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
         const int G = g_kc_tuning.resize_g == 8 ? 8 : g_kc_tuning.resize_g == 32 ? 32 : g_kc_tuning.resize_g == 16 ? 16 : (exact_mode ? 32 : 16);
         const int minb = g_kc_tuning.resize_minb == 8 ? 8 : g_kc_tuning.resize_minb == 6 ? 6 : g_kc_tuning.resize_minb == 4 ? 4 : (G >= 16 ? 4 : 6);
         const int RC = g_kc_tuning.resize_rc == 8 ? 8 : (g_kc_tuning.resize_rc == 16 && G == 16) ? 16 : g_kc_tuning.resize_rc == 4 ? 4 : (exact_mode ? 8 : 4);
+        uint32_t pcols = 0;                                 // widest patch of any strip, from the 16-byte boundary below its first column
+        for (uint32_t o0 = 0; o0 < dw; o0 += (uint32_t)FT_TW) {
+            const uint32_t ol = std::min(o0 + (uint32_t)FT_TW, dw) - 1;
+            pcols = std::max(pcols, th->h_left[ol] + th->h_count[ol] - (th->h_left[o0] & ~3u));
+        }
+        pcols = (pcols + 3u) & ~3u;
+        const uint32_t prows = max_window_sliding(*tv, (uint32_t)G);
+        const uint32_t vrows = tv->max_taps + 2;
         const bool warp_store = g_kc_tuning.resize_store >= 0;     // default: each warp stores its RC x 128 tiles; -1: the block stores G x 256 halves
         const FtLayout L(pcols, prows, vrows, G, RC, warp_store);
         if (pcols <= 256 && prows <= 256 && pcols <= sw && prows <= sh && L.total <= 200 * 1024) {
