@@ -151,11 +151,10 @@ def wl_height_to_normal(env, steps, size=8192):
     def step():
         if env.world == 1:
             return kc.height_to_normal(tp, st["strip"])
-        counter[0] += 1
-        st["outbox"].publish(st["strip"], (y1 - y0) - 1, counter[0])
-        return kc.height_to_normal_strip_peer(tp, st["strip"], st["inbox"], counter[0], H)
+        counter[0] += 1     # ONE launch: the stencil kernel publishes my last row, reads the neighbour's and acknowledges it
+        return kc.height_to_normal_strip_exchange(tp, st["strip"], st["outbox"], st["inbox"], counter[0], H)
 
-    out = {"workload": "configs[2]: HeightToNormal %dx%d Gray -> RGBA%s" % (W, H, "" if env.world == 1 else ", %d horizontal strips, halo row read from the neighbour's mailbox over NVLink (CUDA IPC), no collective" % env.world),
+    out = {"workload": "configs[2]: HeightToNormal %dx%d Gray -> RGBA%s" % (W, H, "" if env.world == 1 else ", %d horizontal strips; one launch per strip and step: the stencil kernel publishes its last row, reads the row above from the neighbour's mailbox over NVLink (CUDA IPC) and acknowledges it; no collective" % env.world),
            "scaling": "strong" if env.world > 1 else "single GPU", "pixels": H * W,
            "algorithmic_bytes": H * W * 16, "algorithmic_bytes_note": "4 B read + 12 B written per pixel; the alpha plane stays a constant descriptor (20 B/px if a caller insists on alpha pixels)",
            "reference": "src/node/height_to_normal.rs:16-77"}

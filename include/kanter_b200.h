@@ -323,6 +323,10 @@ int32_t kc_halo_inbox_local(kc_context* ctx, const kc_halo_link* outbox, kc_halo
 int32_t kc_halo_publish(kc_halo_link* outbox, kc_plane* plane, uint32_t row, uint64_t step);
 int32_t kc_height_to_normal_strip_peer(kc_context* ctx, const kc_image* strip, const kc_halo_link* inbox, uint64_t step,
                                        uint32_t full_height, kc_image* out);
+/* the whole exchange of a step in ONE launch: the stencil kernel publishes the strip's last row into `outbox`, reads the row
+ * above out of `inbox` and acknowledges it there (no kc_halo_publish, no separate ack) */
+int32_t kc_height_to_normal_strip_exchange(kc_context* ctx, const kc_image* strip, kc_halo_link* outbox, const kc_halo_link* inbox,
+                                           uint64_t step, uint32_t full_height, kc_image* out);
 int32_t kc_halo_timeouts(kc_context* ctx, uint32_t* count);   /* waits that gave up after 2 s; 0 in a healthy run */
 int32_t kc_halo_link_destroy(kc_halo_link* link);
 /* device-to-device copy of whole rows between planes of equal width (halo rows; works

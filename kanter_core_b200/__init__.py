@@ -9,5 +9,5 @@ from .api import (  # noqa: F401
     Edge, EmbeddedSlotDataId, LiveGraph, MixType, Node, NodeGraph, NodeId, NodeState, NodeType, Priority,
     ResizeFilter, ResizePolicy, Side, Size, Slot, SlotData, SlotId, SlotImage, SlotType,
     HaloLink, TextureProcessor, copy_rows, empty_gray, free_pinned, graph_to_dict, halo_timeouts, height_to_normal,
-    height_to_normal_strip, height_to_normal_strip_peer, jit_wait, mix, pinned_empty, process_node, resize, wrap_device_plane,
+    height_to_normal_strip, height_to_normal_strip_exchange, height_to_normal_strip_peer, jit_wait, mix, pinned_empty, process_node, resize, wrap_device_plane,
 )

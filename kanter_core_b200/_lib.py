@@ -149,6 +149,7 @@ SIGNATURES = {
     "kc_halo_inbox_local": (i32, [vp, vp, P(vp)]),
     "kc_halo_publish": (i32, [vp, vp, u32, u64]),
     "kc_height_to_normal_strip_peer": (i32, [vp, P(kc_image), vp, u64, u32, P(kc_image)]),
+    "kc_height_to_normal_strip_exchange": (i32, [vp, P(kc_image), vp, vp, u64, u32, P(kc_image)]),
     "kc_halo_timeouts": (i32, [vp, P(u32)]),
     "kc_halo_link_destroy": (i32, [vp]),
     "kc_plane_copy_rows": (i32, [vp, vp, u32, vp, u32, u32]),

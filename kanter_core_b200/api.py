@@ -1206,10 +1206,12 @@ class HaloLink:
         call("kc_halo_inbox_open", tex_pro._ctx._h, buf, int(width), C.byref(h))
         return HaloLink(tex_pro, h)
 
-    def local_inbox(self):
+    def local_inbox(self, tex_pro=None):
+        """The same mailbox seen from the reading side inside one process; tex_pro: the reader's context (default: the owner's)."""
+        tp = tex_pro or self._tp
         h = C.c_void_p()
-        call("kc_halo_inbox_local", self._tp._ctx._h, self._h, C.byref(h))
-        return HaloLink(self._tp, h)
+        call("kc_halo_inbox_local", tp._ctx._h, self._h, C.byref(h))
+        return HaloLink(tp, h)
 
     def publish(self, image, row, step, plane=0):
         call("kc_halo_publish", self._h, image._im.planes[plane], int(row), int(step))
@@ -1224,6 +1226,14 @@ def height_to_normal_strip_peer(tex_pro, strip, inbox, step, full_height):
     """HeightToNormal on a strip whose halo row the kernel reads from the mailbox of the GPU above."""
     out = kc_image()
     call("kc_height_to_normal_strip_peer", tex_pro._ctx._h, C.byref(strip._im), inbox._h, int(step), int(full_height), C.byref(out))
+    return SlotImage(tex_pro._ctx, out)
+
+
+def height_to_normal_strip_exchange(tex_pro, strip, outbox, inbox, step, full_height):
+    """One launch per step: the stencil kernel publishes the strip's last row into `outbox`, reads the row above out of
+    `inbox` (the neighbour's mailbox, peer memory) and acknowledges it there."""
+    out = kc_image()
+    call("kc_height_to_normal_strip_exchange", tex_pro._ctx._h, C.byref(strip._im), outbox._h, inbox._h, int(step), int(full_height), C.byref(out))
     return SlotImage(tex_pro._ctx, out)
 
 

@@ -149,7 +149,7 @@ int32_t img_mix(kc_context* ctx, int mix_type, const Img* left, const Img* right
 // height_to_normal::process, src/node/height_to_normal.rs:16-77.  halo/h_full: strip mode
 // (rows [y0, y0+h) of an image h_full tall; halo = the row above the strip, w x 1).
 int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullptr, uint32_t h_full = 0,
-                const kc_halo_link* inbox = nullptr, uint64_t step = 0) {
+                const kc_halo_link* inbox = nullptr, uint64_t step = 0, const kc_halo_link* outbox = nullptr) {
     if (in.rgba()) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "HeightToNormal needs a Gray input");
     KcHostTimer hp(KC_HP_H2N);
     kc_plane* src = in.im.planes[0];
@@ -183,9 +183,10 @@ int32_t img_h2n(kc_context* ctx, const Img& in, Img& out, kc_plane* halo = nullp
         if (kck_halo_width(inbox) != src->w) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "mailbox is %u wide, the strip %u", kck_halo_width(inbox), src->w);
         KC_TRY(kck_halo_read_args(inbox, step, &halo_ptr, &peer_flag));
     }
+    if (outbox && kck_halo_width(outbox) != src->w) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "outbox is %u wide, the strip %u", kck_halo_width(outbox), src->w);
     KC_TRY(kck_height_to_normal(ctx, src->dptr, src->w, src->h, h_full, halo_ptr, res.im.planes[0]->dptr,
-                                res.im.planes[1]->dptr, res.im.planes[2]->dptr, peer_flag, step));
-    if (inbox) KC_TRY(kck_halo_ack(ctx, inbox, step));   // stream-ordered after the kernel that read the row
+                                res.im.planes[1]->dptr, res.im.planes[2]->dptr, peer_flag, step, outbox, outbox ? inbox : nullptr));
+    if (inbox && !outbox) KC_TRY(kck_halo_ack(ctx, inbox, step));   // stream-ordered after the kernel that read the row (the fused exchange acknowledges itself)
     ctx->run_bytes += (uint64_t)src->bytes() * 4;
     out = std::move(res);
     return KC_OK;
@@ -251,7 +252,47 @@ int32_t img_resize(kc_context* ctx, const Img& in, uint32_t w, uint32_t h, int f
     }
     Img res;
     res.im.kind = in.im.kind;
-    for (int c = 0; c < kci_nplanes(&in.im); ++c) {
+    const int np = kci_nplanes(&in.im);
+    // The planes that need pixels (not an alias of an earlier channel, not a 1x1 constant that folds) go through ONE launch
+    // of the tensor-map kernel when it takes the configuration: same tables, grid.z = plane.
+    if (np > 1 && filter >= KC_FILTER_NEAREST && filter <= KC_FILTER_LANCZOS3 && row0 <= h && nrows <= h - row0) {
+        std::vector<int> batch;
+        for (int c = 0; c < np; ++c) {
+            bool alias = false;
+            for (int d = 0; d < c; ++d) alias |= in.im.planes[d] == in.im.planes[c];
+            const kc_plane* p = in.im.planes[c];
+            if (!alias && !(p->kind == KC_PLANE_CONST && p->w == 1 && p->h == 1)) batch.push_back(c);
+        }
+        if (batch.size() > 1) {
+            KcHostTimer hp(KC_HP_RESIZE);
+            std::vector<kc_plane*> srcs;
+            for (int c : batch) srcs.push_back(in.im.planes[c]);
+            KC_TRY(kcp_force(ctx, srcs.data(), srcs.size()));        // one fused launch for whatever is still lazy
+            KcPin pin;
+            for (kc_plane* p : srcs) pin.add(p);
+            std::vector<kc_plane*> dsts(batch.size(), nullptr);
+            std::vector<const float*> sp;
+            std::vector<float*> dp;
+            int32_t rc = KC_OK;
+            for (size_t i = 0; i < batch.size() && rc == KC_OK; ++i) {
+                rc = kcp_new_device(ctx, w, nrows, &dsts[i]);
+                if (rc == KC_OK) { pin.add(dsts[i]); sp.push_back(srcs[i]->dptr); dp.push_back(dsts[i]->dptr); }
+            }
+            bool done = false;
+            if (rc == KC_OK) rc = kck_resize_planes_rows_batched(ctx, sp.data(), dp.data(), (int)batch.size(), in.w(), in.h(), w, h, filter, row0, nrows, &done);
+            if (rc != KC_OK || !done) {
+                for (kc_plane* p : dsts) if (p) kcp_release(p);
+                if (rc != KC_OK) return rc;
+            } else {
+                for (size_t i = 0; i < batch.size(); ++i) {
+                    ctx->run_bytes += (uint64_t)srcs[i]->bytes() + dsts[i]->bytes();
+                    res.set(batch[i], dsts[i]);
+                }
+            }
+        }
+    }
+    for (int c = 0; c < np; ++c) {
+        if (res.im.planes[c]) continue;                        // resized by the batched launch above
         // planes shared between channels (Gray -> Rgba aliasing) are resized once
         int same = -1;
         for (int d = 0; d < c; ++d)
@@ -956,6 +997,22 @@ int32_t kc_height_to_normal_strip_peer(kc_context* ctx, const kc_image* strip, c
     KcGuard g(ctx);
     Img res;
     KC_TRY(img_h2n(ctx, borrow(strip), res, nullptr, full_height, inbox, step));
+    *out = res.release();
+    return KC_OK;
+} KC_ABI_CATCH
+
+int32_t kc_height_to_normal_strip_exchange(kc_context* ctx, const kc_image* strip, kc_halo_link* outbox, const kc_halo_link* inbox, uint64_t step,
+                                           uint32_t full_height, kc_image* out) try {
+    // One launch per step: the stencil kernel itself publishes the strip's last row into `outbox` (for the GPU below),
+    // reads the row above out of `inbox` (the mailbox of the GPU above, peer memory) and acknowledges it there.
+    if (!ctx || !strip || !outbox || !inbox || !out || step == 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "bad argument");
+    KC_TRY(check_image(strip, "height_to_normal_strip_exchange"));
+    if (full_height < strip->planes[0]->h) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "full height smaller than the strip");
+    if ((strip->planes[0]->w & 3u) != 0) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "the fused exchange needs a width that is a multiple of 4");
+    KcGuard g(ctx);
+    ctx->halo_used = true;
+    Img res;
+    KC_TRY(img_h2n(ctx, borrow(strip), res, nullptr, full_height, inbox, step, outbox));
     *out = res.release();
     return KC_OK;
 } KC_ABI_CATCH

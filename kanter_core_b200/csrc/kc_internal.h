@@ -351,11 +351,14 @@ int32_t kck_from_u8(kc_context* ctx, const uint8_t* d_samples, uint32_t channels
                     float* const planes[4]);
 // h_full/halo: for a horizontal strip of a taller image, the full height and the row above
 // the strip (NULL halo + h_full == h: the whole image, toroidal wrap)
-int32_t kck_height_to_normal(kc_context* ctx, const float* hgt, uint32_t w, uint32_t h, uint32_t h_full,
-                             const float* halo, float* r, float* g, float* b,
-                             const unsigned long long* peer_flag = nullptr, unsigned long long peer_step = 0);
 // halo mailboxes in peer memory (kc_h2n.cu)
 struct kc_halo_link;
+// publish_to / ack_to: the fused exchange -- the kernel also publishes the strip's last row into `publish_to` and
+// acknowledges the halo it read in `ack_to` (kc_height_to_normal_strip_exchange)
+int32_t kck_height_to_normal(kc_context* ctx, const float* hgt, uint32_t w, uint32_t h, uint32_t h_full,
+                             const float* halo, float* r, float* g, float* b,
+                             const unsigned long long* peer_flag = nullptr, unsigned long long peer_step = 0,
+                             const kc_halo_link* publish_to = nullptr, const kc_halo_link* ack_to = nullptr);
 int32_t kck_halo_read_args(const kc_halo_link* inbox, uint64_t step, const float** halo, const unsigned long long** flag);
 int32_t kck_halo_ack(kc_context* ctx, const kc_halo_link* inbox, uint64_t step);
 uint32_t kck_halo_width(const kc_halo_link* l);
@@ -365,6 +368,9 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
                          uint32_t dw, uint32_t dh, int filter);
 int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,
                               uint32_t dh, int filter, uint32_t row0, uint32_t nrows);
+// up to four planes of one geometry in one launch; *done = false: not a configuration the tensor-map kernel takes
+int32_t kck_resize_planes_rows_batched(kc_context* ctx, const float* const* srcs, float* const* dsts, int n, uint32_t sw, uint32_t sh,
+                                       uint32_t dw, uint32_t dh, int filter, uint32_t row0, uint32_t nrows, bool* done);
 // host-side weight table exactly as image 0.24.0 computes it (kc_resize.cu)
 void kc_resize_axis_host(uint32_t src_len, uint32_t dst_len, int filter, std::vector<uint32_t>& left,
                          std::vector<uint32_t>& count, std::vector<float>& weights, uint32_t& max_taps);

@@ -563,6 +563,13 @@ __device__ __forceinline__ float ft_clamp(float a, float lo, float hi, bool sat)
     return clamp_keep_nan(a, lo, hi);
 }
 
+// the planes of one launch (blockIdx.z picks one): an RGBA image resizes in ONE launch, with the same tables for every plane
+constexpr int FT_MAX_PLANES = 4;
+struct FtPlaneMaps {
+    CUtensorMap src[FT_MAX_PLANES];
+    CUtensorMap dst[FT_MAX_PLANES];
+};
+
 struct FtLayout {   // byte offsets into dynamic shared memory (host and device agree through this)
     uint32_t tm, tm_buf, s, s_stage, vt, vt_stage, o, o_buf, total;
     __host__ __device__ FtLayout(uint32_t pcols, uint32_t prows, uint32_t vrows, int G, int RC, bool warp_store) {
@@ -587,7 +594,7 @@ struct FtLayout {   // byte offsets into dynamic shared memory (host and device 
 
 template <bool EXACT, int G, int RC, int MINB, bool WARP_STORE>
 __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
-    const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_vtab, const __grid_constant__ CUtensorMap tm_dst,
+    const __grid_constant__ FtPlaneMaps pm, const __grid_constant__ CUtensorMap tm_vtab,
     uint32_t sh, uint32_t dw, const uint32_t* __restrict__ vleft, uint32_t vtaps,
     const uint32_t* __restrict__ hleft, const uint32_t* __restrict__ hcount, const float* __restrict__ hw,
     uint32_t pcols, uint32_t prows, float one, uint32_t row0, uint32_t nrows, float clo, float chi) {
@@ -643,7 +650,7 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
     auto group_row0 = [&](uint32_t gg) { return min(__ldg(vleft + row0 + gg * G), sh - prows); };
     auto issue = [&](uint32_t gg, int b, uint32_t ry) {               // thread 0 only
         ft_mbar_expect_tx(&mbar[b], stage_bytes);
-        ft_tma_load_2d(ftm + L.s + b * L.s_stage, &tm_src, cx0, ry, &mbar[b]);
+        ft_tma_load_2d(ftm + L.s + b * L.s_stage, &pm.src[blockIdx.z], cx0, ry, &mbar[b]);
         ft_tma_load_2d(ftm + L.vt + b * L.vt_stage, &tm_vtab, (row0 + gg * G) & ~3u, 0u, &mbar[b]);   // same rule: aligned start, G + 4 wide
     };
     __syncthreads();                                                  // the barriers are initialised
@@ -770,7 +777,7 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tile must be visible to the TMA (async proxy)
                     __syncwarp();
                     if (lane == 0) {                                      // rows and columns past the result are clipped by the TMA
-                        ft_tma_store_2d(&tm_dst, ox0 + (uint32_t)warp * FT_WARP_COLS, g * G + rc, Ow + (chunk & 1u) * (size_t)(RC * FT_WARP_COLS), policy);
+                        ft_tma_store_2d(&pm.dst[blockIdx.z], ox0 + (uint32_t)warp * FT_WARP_COLS, g * G + rc, Ow + (chunk & 1u) * (size_t)(RC * FT_WARP_COLS), policy);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     ++chunk;
@@ -792,8 +799,8 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
             __syncthreads();                                              // tile complete
             if (tid == 0) {
                 const float* O = reinterpret_cast<const float*>(ftm + L.o);
-                ft_tma_store_2d(&tm_dst, ox0, g * G, O, policy);          // rows and columns past the result are clipped by the TMA
-                if (ox0 + FT_HALF < dw) ft_tma_store_2d(&tm_dst, ox0 + FT_HALF, g * G, O + (size_t)G * FT_HALF, policy);
+                ft_tma_store_2d(&pm.dst[blockIdx.z], ox0, g * G, O, policy);          // rows and columns past the result are clipped by the TMA
+                if (ox0 + FT_HALF < dw) ft_tma_store_2d(&pm.dst[blockIdx.z], ox0 + FT_HALF, g * G, O + (size_t)G * FT_HALF, policy);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             }
         }
@@ -816,6 +823,35 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
 // four FMAs (the row-major layout needed four LDS and the index arithmetic four times over: 14.6 M warp
 // instructions for 8192x1024 -> 1024x1024, issue slots 59 % busy).  A spare slot after every eight columns
 // spreads the stride-R reads of adjacent outputs over the banks.
+// L2 residency control for the long-window path.  The 256 MiB source is a pure stream (evict-first) EXCEPT the rows two
+// neighbouring blocks both need (the window overlap at a chunk boundary, ~15 % of the source): the lower block reads them
+// first, at its start, and marks them evict-last so that they are still in L2 when the upper block gets to them at its end
+// -- without that every overlap row came out of DRAM twice (dram__bytes_read 1.15 x the source, profiles/ncu_full_resize_down_v_r01).
+// The 32 MiB intermediate is written evict-last as well and read back evict-first by the horizontal pass: it never leaves L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ float4 ld_nc_hint4(const float4* a, uint64_t policy) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ float ld_nc_hint(const float* a, uint64_t policy) {
+    float v;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(a), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ void st_hint4(float4* a, const float4& v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(policy) : "memory");
+}
+
 constexpr int HT_ROWS = 4;
 __device__ __forceinline__ uint32_t ht_slot(uint32_t i) { return i + (i >> 3); }
 
@@ -831,11 +867,13 @@ __global__ void __launch_bounds__(256) kc_resize_h_tile_kernel(const float* __re
     const float* r1 = tmp + (size_t)(y0 + min(1u, nrow - 1)) * sw + c0;   // rows past nrow: duplicates, never stored
     const float* r2 = tmp + (size_t)(y0 + min(2u, nrow - 1)) * sw + c0;
     const float* r3 = tmp + (size_t)(y0 + min(3u, nrow - 1)) * sw + c0;
-    // staging: eight loads per thread in flight together (two columns x four rows; the intermediate comes from L2)
+    // staging: eight loads per thread in flight together (two columns x four rows).  The intermediate sits in L2 (the vertical
+    // march wrote it evict-last); this is its last use, so the reads demote it again (evict-first)
+    const uint64_t pol = l2_policy_evict_first();
     for (uint32_t i0 = threadIdx.x; i0 < ncol; i0 += 512) {
         const uint32_t ia = i0, ib = min(i0 + 256u, ncol - 1);
-        const float4 va = make_float4(__ldg(r0 + ia), __ldg(r1 + ia), __ldg(r2 + ia), __ldg(r3 + ia));
-        const float4 vb = make_float4(__ldg(r0 + ib), __ldg(r1 + ib), __ldg(r2 + ib), __ldg(r3 + ib));
+        const float4 va = make_float4(ld_nc_hint(r0 + ia, pol), ld_nc_hint(r1 + ia, pol), ld_nc_hint(r2 + ia, pol), ld_nc_hint(r3 + ia, pol));
+        const float4 vb = make_float4(ld_nc_hint(r0 + ib, pol), ld_nc_hint(r1 + ib, pol), ld_nc_hint(r2 + ib, pol), ld_nc_hint(r3 + ib, pol));
         htile4[ht_slot(ia)] = va;
         if (i0 + 256u < ncol) htile4[ht_slot(i0 + 256u)] = vb;
     }
@@ -904,6 +942,10 @@ __global__ void __launch_bounds__(VM_THREADS) kc_resize_v_march_kernel(const flo
     const uint32_t oyA = blockIdx.y * rows_per_cta, oyB = min(oyA + rows_per_cta, dh);
     const uint32_t r0 = __ldg(vleft + oyA), r1 = __ldg(vleft + oyB - 1) + __ldg(vcount + oyB - 1);
     const uint32_t nr = r1 - r0;
+    // rows [r0, r_shared) are also the LAST rows of the block above: keep them in L2 for it
+    const uint32_t r_shared = oyA == 0 ? r0 : min(r1, __ldg(vleft + oyA - 1) + __ldg(vcount + oyA - 1));
+    const uint32_t n_shared = r_shared > r0 ? r_shared - r0 : 0u;
+    const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
     float4* sw_ = vm_sm;
     int4* so_ = reinterpret_cast<int4*>(vm_sm + 2 * (size_t)nr);
     for (uint32_t i = threadIdx.x; i < 2 * nr; i += VM_THREADS) {
@@ -920,7 +962,10 @@ __global__ void __launch_bounds__(VM_THREADS) kc_resize_v_march_kernel(const flo
     for (uint32_t rb = 0; rb < nr; rb += U) {
         float4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = __ldg(col + (size_t)(r0 + min(rb + u, nr - 1)) * sw4);
+        for (int u = 0; u < U; ++u) {
+            const uint32_t rr = min(rb + u, nr - 1);
+            v[u] = ld_nc_hint4(col + (size_t)(r0 + rr) * sw4, rr < n_shared ? pol_keep : pol_stream);
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const uint32_t r = rb + u;                     // relative to r0
@@ -937,7 +982,7 @@ __global__ void __launch_bounds__(VM_THREADS) kc_resize_v_march_kernel(const flo
 #pragma unroll
             for (int s = 0; s < VM_SLOTS; ++s)
                 if (o[s] >= 0) {
-                    if ((uint32_t)o[s] >= oyA && (uint32_t)o[s] < oyB) tmp[(size_t)o[s] * sw4 + x4] = acc[s];
+                    if ((uint32_t)o[s] >= oyA && (uint32_t)o[s] < oyB) st_hint4(tmp + (size_t)o[s] * sw4 + x4, acc[s], pol_keep);
                     acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
         }
@@ -1003,6 +1048,90 @@ int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_
 // rows [row0, row0 + nrows) of the dw x dh resize of src, written to dst (dw x nrows).  A GPU that
 // owns a horizontal strip of the result calls this with its rows: it needs the source rows
 // [left(row0), right(row0 + nrows - 1)) only -- for an upsample, simply the whole (small) source.
+// Up to four planes of the same geometry in ONE launch of the tensor-map kernel (grid.z = plane).  *done = false: the
+// configuration is not one that kernel takes (the caller resizes plane by plane).
+int32_t kck_resize_planes_rows_batched(kc_context* ctx, const float* const* srcs, float* const* dsts, int n, uint32_t sw, uint32_t sh,
+                                       uint32_t dw, uint32_t dh, int filter, uint32_t row0, uint32_t nrows, bool* done) {
+    *done = false;
+    if (n < 1 || n > FT_MAX_PLANES || dw == 0 || dh == 0 || nrows == 0 || sw == 0 || sh == 0 || row0 > dh || nrows > dh - row0) return KC_OK;
+    std::shared_ptr<KcAxisTable> tv, th;
+    KC_TRY(get_axis(ctx, sh, dh, filter, tv));
+    KC_TRY(get_axis(ctx, sw, dw, filter, th));
+    const bool exact_mode = ctx->opts.math_mode == KC_MATH_EXACT;
+    const float clo = ctx->opts.resize_unclamped ? -INFINITY : 0.0f, chi = ctx->opts.resize_unclamped ? INFINITY : 1.0f;
+    static const bool no_fused = getenv("KC_RESIZE_TWO_PASS") != nullptr;
+    const bool no_tma = g_kc_tuning.resize_tma < 0;
+    uintptr_t align = 0;
+    for (int i = 0; i < n; ++i) align |= (uintptr_t)srcs[i] | (uintptr_t)dsts[i];
+    if (no_fused || no_tma || tv->max_taps > (uint32_t)FS_MAXT || th->max_taps > (uint32_t)FS_MAXT || (sw & 3u) != 0 || (dw & 3u) != 0 ||
+        dw < (uint32_t)FT_TW || nrows < 32 || (align & 15u) != 0 || !tensor_map_encoder())
+        return KC_OK;
+    // rows per group / rows per accumulator chunk / CTAs per SM: tuning knobs (kc_debug_set_tuning, scripts/resize_sweep.py);
+    // defaults from profiles/resize_sweep_r02_{fast,exact}.json: every warp stores its own tiles; FAST 16-row groups in
+    // 4-row chunks, EXACT (twice the floating-point instructions per tap) 32-row groups in 8-row chunks
+    const int G = g_kc_tuning.resize_g == 8 ? 8 : g_kc_tuning.resize_g == 32 ? 32 : g_kc_tuning.resize_g == 16 ? 16 : (exact_mode ? 32 : 16);
+    const int minb = g_kc_tuning.resize_minb == 8 ? 8 : g_kc_tuning.resize_minb == 6 ? 6 : g_kc_tuning.resize_minb == 4 ? 4 : (G >= 16 ? 4 : 6);
+    const int RC = g_kc_tuning.resize_rc == 8 ? 8 : (g_kc_tuning.resize_rc == 16 && G == 16) ? 16 : g_kc_tuning.resize_rc == 4 ? 4 : (exact_mode ? 8 : 4);
+    uint32_t pcols = 0;                                 // widest patch of any strip, from the 16-byte boundary below its first column
+    for (uint32_t o0 = 0; o0 < dw; o0 += (uint32_t)FT_TW) {
+        const uint32_t ol = std::min(o0 + (uint32_t)FT_TW, dw) - 1;
+        pcols = std::max(pcols, th->h_left[ol] + th->h_count[ol] - (th->h_left[o0] & ~3u));
+    }
+    pcols = (pcols + 3u) & ~3u;
+    const uint32_t prows = max_window_sliding(*tv, (uint32_t)G);
+    const uint32_t vrows = tv->max_taps + 2;
+    const bool warp_store = g_kc_tuning.resize_store >= 0;     // default: each warp stores its RC x 128 tiles; -1: the block stores G x 256 halves
+    const FtLayout L(pcols, prows, vrows, G, RC, warp_store);
+    if (!(pcols <= 256 && prows <= 256 && pcols <= sw && prows <= sh && L.total <= 200 * 1024)) return KC_OK;
+    FtPlaneMaps pm;
+    CUtensorMap m_vt;
+    memset(&pm, 0, sizeof pm);
+    if (!make_tensor_map_2d(&m_vt, tv->d_vtab, dh, vrows, (uint32_t)G + 4u, vrows)) return KC_OK;
+    for (int i = 0; i < n; ++i)
+        if (!make_tensor_map_2d(&pm.src[i], srcs[i], sw, sh, pcols, prows) ||
+            !make_tensor_map_2d(&pm.dst[i], dsts[i], dw, nrows, warp_store ? (uint32_t)FT_WARP_COLS : (uint32_t)FT_HALF, warp_store ? (uint32_t)RC : (uint32_t)G))
+            return KC_OK;
+    const void* fn = nullptr;
+#define KC_FT2(E, W) (G == 8 ? (RC == 4 ? (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 4, 8, W> : (const void*)kc_resize_tma_kernel<E, 8, 4, 6, W>)   \
+                                        : (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 8, 8, W> : (const void*)kc_resize_tma_kernel<E, 8, 8, 6, W>))  \
+                      : G == 16 ? (RC == 4 ? (minb >= 6 ? (const void*)kc_resize_tma_kernel<E, 16, 4, 6, W> : (const void*)kc_resize_tma_kernel<E, 16, 4, 4, W>)  \
+                                        : RC == 8 ? (const void*)kc_resize_tma_kernel<E, 16, 8, 4, W> : (const void*)kc_resize_tma_kernel<E, 16, 16, 4, W>)    \
+                                : (RC == 4 ? (const void*)kc_resize_tma_kernel<E, 32, 4, 4, W> : (const void*)kc_resize_tma_kernel<E, 32, 8, 4, W>))
+#define KC_FT(E) (warp_store ? KC_FT2(E, true) : KC_FT2(E, false))
+    fn = exact_mode ? KC_FT(true) : KC_FT(false);
+#undef KC_FT2
+#undef KC_FT
+    static std::map<std::tuple<int, const void*, size_t>, int> occ;
+    static std::mutex occ_mu;
+    int per_sm = 1;
+    {
+        std::lock_guard<std::mutex> lk(occ_mu);
+        auto it = occ.find(std::make_tuple(ctx->device, fn, (size_t)L.total));
+        if (it == occ.end()) {
+            KC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            int nb = 1;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, FT_THREADS, L.total);
+            it = occ.emplace(std::make_tuple(ctx->device, fn, (size_t)L.total), std::max(nb, 1)).first;
+        }
+        per_sm = it->second;
+    }
+    // one resident wave over all the planes: strips x row-march lanes x planes ~= SMs x resident CTAs
+    const uint32_t strips = (dw + FT_TW - 1) / FT_TW;
+    const uint32_t ngroups = (nrows + G - 1) / G;
+    const uint32_t lanes = std::max<uint32_t>(1u, std::min<uint32_t>(ngroups, (uint32_t)(ctx->sm_count * per_sm) / std::max(strips * (uint32_t)n, 1u)));
+    dim3 grid(strips, std::min<uint32_t>(lanes, 65535u), (unsigned)n);
+    KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
+    const float one = 1.0f;
+    void* args[] = {(void*)&pm, (void*)&m_vt, (void*)&sh, (void*)&dw, (void*)&tv->d_left, (void*)&tv->max_taps,
+                    (void*)&th->d_left, (void*)&th->d_count, (void*)&th->d_weights, (void*)&pcols, (void*)&prows, (void*)&one,
+                    (void*)&row0, (void*)&nrows, (void*)&clo, (void*)&chi};
+    KC_CUDA(cudaLaunchKernel(fn, grid, dim3(FT_THREADS), args, L.total, ctx->stream));
+    ctx->kernel_launches++;
+    ctx->run_kernels++;
+    *done = true;
+    return KC_OK;
+}
+
 int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,
                               uint32_t dh, int filter, uint32_t row0, uint32_t nrows) {
     if (dw == 0 || dh == 0 || nrows == 0) return KC_OK;
@@ -1015,69 +1144,11 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
     // the [0,1] clamp of image-0.24's horizontal pass (unpinned by the reference's goldens: switchable)
     const float clo = ctx->opts.resize_unclamped ? -INFINITY : 0.0f, chi = ctx->opts.resize_unclamped ? INFINITY : 1.0f;
     static const bool no_fused = getenv("KC_RESIZE_TWO_PASS") != nullptr;
-    // ---- TMA variant: tensor-map loads of the source patch and the vertical table, tensor-map stores of the result ----
-    const bool no_tma = g_kc_tuning.resize_tma < 0;
-    if (!no_fused && !no_tma && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT && (sw & 3u) == 0 && (dw & 3u) == 0 &&
-        dw >= (uint32_t)FT_TW && nrows >= 32 && (((uintptr_t)src | (uintptr_t)dst) & 15u) == 0 && tensor_map_encoder()) {
-        // rows per group / rows per accumulator chunk / CTAs per SM: tuning knobs (kc_debug_set_tuning, scripts/resize_sweep.py)
-        // defaults from profiles/resize_sweep_r02_{fast,exact}.json: every warp stores its own tiles; FAST 16-row groups in
-        // 4-row chunks, EXACT (twice the floating-point instructions per tap) 32-row groups in 8-row chunks
-        const int G = g_kc_tuning.resize_g == 8 ? 8 : g_kc_tuning.resize_g == 32 ? 32 : g_kc_tuning.resize_g == 16 ? 16 : (exact_mode ? 32 : 16);
-        const int minb = g_kc_tuning.resize_minb == 8 ? 8 : g_kc_tuning.resize_minb == 6 ? 6 : g_kc_tuning.resize_minb == 4 ? 4 : (G >= 16 ? 4 : 6);
-        const int RC = g_kc_tuning.resize_rc == 8 ? 8 : (g_kc_tuning.resize_rc == 16 && G == 16) ? 16 : g_kc_tuning.resize_rc == 4 ? 4 : (exact_mode ? 8 : 4);
-        uint32_t pcols = 0;                                 // widest patch of any strip, from the 16-byte boundary below its first column
-        for (uint32_t o0 = 0; o0 < dw; o0 += (uint32_t)FT_TW) {
-            const uint32_t ol = std::min(o0 + (uint32_t)FT_TW, dw) - 1;
-            pcols = std::max(pcols, th->h_left[ol] + th->h_count[ol] - (th->h_left[o0] & ~3u));
-        }
-        pcols = (pcols + 3u) & ~3u;
-        const uint32_t prows = max_window_sliding(*tv, (uint32_t)G);
-        const uint32_t vrows = tv->max_taps + 2;
-        const bool warp_store = g_kc_tuning.resize_store >= 0;     // default: each warp stores its RC x 128 tiles; -1: the block stores G x 256 halves
-        const FtLayout L(pcols, prows, vrows, G, RC, warp_store);
-        if (pcols <= 256 && prows <= 256 && pcols <= sw && prows <= sh && L.total <= 200 * 1024) {
-            CUtensorMap m_src, m_vt, m_dst;
-            if (make_tensor_map_2d(&m_src, src, sw, sh, pcols, prows) && make_tensor_map_2d(&m_vt, tv->d_vtab, dh, vrows, (uint32_t)G + 4u, vrows) &&
-                make_tensor_map_2d(&m_dst, dst, dw, nrows, warp_store ? (uint32_t)FT_WARP_COLS : (uint32_t)FT_HALF, warp_store ? (uint32_t)RC : (uint32_t)G)) {
-                const void* fn = nullptr;
-#define KC_FT2(E, W) (G == 8 ? (RC == 4 ? (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 4, 8, W> : (const void*)kc_resize_tma_kernel<E, 8, 4, 6, W>)   \
-                                        : (minb == 8 ? (const void*)kc_resize_tma_kernel<E, 8, 8, 8, W> : (const void*)kc_resize_tma_kernel<E, 8, 8, 6, W>))  \
-                      : G == 16 ? (RC == 4 ? (minb >= 6 ? (const void*)kc_resize_tma_kernel<E, 16, 4, 6, W> : (const void*)kc_resize_tma_kernel<E, 16, 4, 4, W>)  \
-                                        : RC == 8 ? (const void*)kc_resize_tma_kernel<E, 16, 8, 4, W> : (const void*)kc_resize_tma_kernel<E, 16, 16, 4, W>)    \
-                                : (RC == 4 ? (const void*)kc_resize_tma_kernel<E, 32, 4, 4, W> : (const void*)kc_resize_tma_kernel<E, 32, 8, 4, W>))
-#define KC_FT(E) (warp_store ? KC_FT2(E, true) : KC_FT2(E, false))
-                fn = exact_mode ? KC_FT(true) : KC_FT(false);
-#undef KC_FT2
-#undef KC_FT
-                static std::map<std::tuple<int, const void*, size_t>, int> occ;
-                static std::mutex occ_mu;
-                int per_sm = 1;
-                {
-                    std::lock_guard<std::mutex> lk(occ_mu);
-                    auto it = occ.find(std::make_tuple(ctx->device, fn, (size_t)L.total));
-                    if (it == occ.end()) {
-                        KC_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-                        int n = 1;
-                        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, fn, FT_THREADS, L.total);
-                        it = occ.emplace(std::make_tuple(ctx->device, fn, (size_t)L.total), std::max(n, 1)).first;
-                    }
-                    per_sm = it->second;
-                }
-                const uint32_t strips = (dw + FT_TW - 1) / FT_TW;
-                const uint32_t ngroups = (nrows + G - 1) / G;
-                const uint32_t lanes = std::max<uint32_t>(1u, std::min<uint32_t>(ngroups, (uint32_t)(ctx->sm_count * per_sm) / std::max(strips, 1u)));
-                dim3 grid(strips, std::min<uint32_t>(lanes, 65535u));
-                KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
-                const float one = 1.0f;
-                void* args[] = {(void*)&m_src, (void*)&m_vt, (void*)&m_dst, (void*)&sh, (void*)&dw, (void*)&tv->d_left, (void*)&tv->max_taps,
-                                (void*)&th->d_left, (void*)&th->d_count, (void*)&th->d_weights, (void*)&pcols, (void*)&prows, (void*)&one,
-                                (void*)&row0, (void*)&nrows, (void*)&clo, (void*)&chi};
-                KC_CUDA(cudaLaunchKernel(fn, grid, dim3(FT_THREADS), args, L.total, ctx->stream));
-                ctx->kernel_launches++;
-                ctx->run_kernels++;
-                return KC_OK;
-            }
-        }
+    // ---- tensor-map loads of the source patch and the vertical table, tensor-map stores of the result ----
+    {
+        bool done = false;
+        KC_TRY(kck_resize_planes_rows_batched(ctx, &src, &dst, 1, sw, sh, dw, dh, filter, row0, nrows, &done));
+        if (done) return KC_OK;
     }
     if (!no_fused && tv->max_taps <= (uint32_t)FS_MAXT && th->max_taps <= (uint32_t)FS_MAXT) {
         // threads per CTA: 4 output columns each.  Narrow CTAs (one or two warps) march

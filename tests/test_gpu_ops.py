@@ -329,6 +329,41 @@ def test_resize_downsample_exact(tex_pro, filt, src, dst):
     assert bits_equal(got, oracle.resize_plane(p, dw, dh, int(filt)))
 
 
+@pytest.mark.parametrize("filt", [ResizeFilter.Triangle, ResizeFilter.Lanczos3])
+def test_resize_rgba_planes_in_one_launch(tex_pro, filt):
+    """An RGBA image whose planes all need pixels goes through ONE launch of the tensor-map kernel (grid.z = plane): every
+    plane bit-identical to the oracle's per-plane resize, a Gray->Rgba image (three aliases of one plane + a constant alpha)
+    still resizes its plane once, and kc_resize_rows of an RGBA image equals the rows of the whole result."""
+    import ctypes as C
+    from kanter_core_b200._lib import call, kc_image
+    sw, sh, dw, dh = 96, 80, 768, 640
+    planes = [rnd(70 + c, sh, sw, -0.25, 1.25) for c in range(4)]
+    img = kc.SlotImage.from_planes(tex_pro, planes)
+    k0 = tex_pro.stats()["kernel_launches"]
+    got = kc.resize(tex_pro, img, Size(dw, dh), filt)
+    assert tex_pro.stats()["kernel_launches"] - k0 == 1
+    gp = got.planes()
+    want = [oracle.resize_plane(p, dw, dh, int(filt)) for p in planes]
+    for c in range(4):
+        assert bits_equal(gp[c], want[c]), c
+    out = kc_image()
+    call("kc_resize_rows", tex_pro._ctx._h, C.byref(img._im), dw, dh, int(filt), 37, 300, C.byref(out))
+    sp = kc.SlotImage(tex_pro._ctx, out).planes()
+    for c in range(4):
+        assert bits_equal(sp[c], want[c][37:337]), c
+    # lazy planes are forced by one fused launch first, then resized by one more
+    lazy = kc.mix(tex_pro, MixType.Add, img, img)
+    k0 = tex_pro.stats()["kernel_launches"]
+    lp = kc.resize(tex_pro, lazy, Size(dw, dh), filt).planes()
+    assert tex_pro.stats()["kernel_launches"] - k0 == 2
+    for c in range(3):
+        assert bits_equal(lp[c], oracle.resize_plane(oracle.mix_plane(0, planes[c], planes[c]), dw, dh, int(filt))), c
+    gray = kc.SlotImage.from_planes(tex_pro, [planes[0]]).as_type(True)
+    gg = kc.resize(tex_pro, gray, Size(dw, dh), filt)
+    assert gg.same_plane(0, gg, 1) and gg.same_plane(0, gg, 2)
+    assert bits_equal(gg.planes()[0], want[0])
+
+
 def test_resize_rgba_with_constant_alpha(tex_pro):
     # a constant alpha plane goes through the same tap arithmetic as any other plane
     planes = [rnd(50 + c, 20, 30) for c in range(3)]
@@ -484,6 +519,39 @@ def test_height_to_normal_strips_with_peer_mailboxes(tex_pro, h, w, parts):
     assert kc.halo_timeouts(tex_pro) == 0
     for l in inboxes + boxes:
         l.close()
+
+
+@pytest.mark.parametrize("h,w,parts", [(64, 64, 1), (64, 128, 2), (100, 256, 3), (512, 1024, 4), (4096, 4096, 2)])
+def test_height_to_normal_strip_exchange_in_one_launch(h, w, parts):
+    """kc_height_to_normal_strip_exchange: publish + stencil + acknowledge in ONE kernel per strip and step.  Every
+    "rank" is a context of its own (its own stream) in this process, all launched back to back: strip r waits inside
+    its kernel for the row strip r-1 publishes from inside ITS kernel -- rank 0 for the last rank's, launched after it
+    (the wrap) -- so the kernels really overlap and the flags really order them.  parts = 1: a GPU reading its own
+    mailbox, which only works because the publishing blocks are scheduled first.  Four steps: both slots, the acks."""
+    from kanter_core_b200 import dist as kdist
+    tps = [kc.TextureProcessor.new() for _ in range(parts)]
+    try:
+        strips = [kdist.strip_rows(h, r, parts) for r in range(parts)]
+        boxes = [kc.HaloLink.outbox(tps[r], w) for r in range(parts)]
+        inboxes = [boxes[(r - 1) % parts].local_inbox(tps[r]) for r in range(parts)]    # same process: the mailbox is aliased, not IPC-mapped
+        for step in (1, 2, 3, 4):
+            hgt = rnd(60 + step, h, w)
+            want = oracle.height_to_normal(hgt)
+            imgs = [kc.SlotImage.from_planes(tps[r], [hgt[y0:y1]]) for r, (y0, y1) in enumerate(strips)]
+            for tp in tps:
+                tp.synchronize()
+            outs = [kc.height_to_normal_strip_exchange(tps[r], imgs[r], boxes[r], inboxes[r], step, h) for r in range(parts)]
+            for r, (y0, y1) in enumerate(strips):
+                got = outs[r].planes()
+                for c in range(3):
+                    assert bits_equal(got[c], want[c][y0:y1]), (step, r, c)
+        for tp in tps:
+            assert kc.halo_timeouts(tp) == 0
+        for l in inboxes + boxes:
+            l.close()
+    finally:
+        for tp in tps:
+            tp.close()
 
 
 def test_a_halo_row_that_never_arrives_is_an_error_not_a_stale_result():
