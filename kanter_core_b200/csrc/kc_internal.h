@@ -346,7 +346,6 @@ void kci_release(kc_image* im);
 
 // ---- kernel launchers (defined in the .cu files) -----------------------------
 int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args);
-int32_t kck_fill(kc_context* ctx, float* dst, size_t n, float v);
 int32_t kck_from_u8(kc_context* ctx, const uint8_t* d_samples, uint32_t channels, size_t n,
                     float* const planes[4]);
 // h_full/halo: for a horizontal strip of a taller image, the full height and the row above

@@ -13,7 +13,7 @@
 //    with the tape interpreter, and kck_launch_tape picks the configuration and the
 //    variant.
 //  * kc_from_u8_kernel: deconstruct_image's u8/255 de-interleave (src/shared.rs:16-56).
-//  * kc_fill_kernel: materialise a constant plane.
+//  (constant planes somebody insists on seeing as pixels are a two-instruction fill segment of the tape kernel: no kernel of their own)
 #include <cstdlib>
 
 #include "kc_internal.h"
@@ -26,15 +26,6 @@ template <bool EXACT, int V, int MINB>
 __global__ void __launch_bounds__(TVM_THREADS, MINB)
     kc_tile_vm_kernel(const __grid_constant__ KcTapeArgs A, int stages, int ns_max, uint32_t tiles_per_plane, uint32_t total_work) {
     kc_tile_vm_body<EXACT, V, KcInterp>(A, stages, ns_max, tiles_per_plane, total_work);
-}
-
-__global__ void __launch_bounds__(256) kc_fill_kernel(float* __restrict__ dst, size_t n, float v) {
-    const size_t nvec = n >> 2;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    const float4 v4 = make_float4(v, v, v, v);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride)
-        __stcs(reinterpret_cast<float4*>(dst) + i, v4);
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[4 * nvec + threadIdx.x] = v;
 }
 
 // byte / 255.0f, correctly rounded, without the generic div.rn expansion: q = b*y, q += (b - 255 q)*y
@@ -185,17 +176,6 @@ int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     else rc = exact ? KC_TVM(true, 1) : KC_TVM(false, 1);
 #undef KC_TVM
     KC_TRY(rc);
-    KC_CUDA(cudaGetLastError());
-    ctx->kernel_launches++;
-    ctx->run_kernels++;
-    return KC_OK;
-}
-
-int32_t kck_fill(kc_context* ctx, float* dst, size_t n, float v) {
-    if (n == 0) return KC_OK;
-    const int grid = grid_for(ctx, (n + 3) >> 2, 256, 8);
-    KcTimed timed(ctx, KC_KERNEL_FILL);
-    kc_fill_kernel<<<grid, 256, 0, ctx->stream>>>(dst, n, v);
     KC_CUDA(cudaGetLastError());
     ctx->kernel_launches++;
     ctx->run_kernels++;

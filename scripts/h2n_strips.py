@@ -31,8 +31,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
-                    help="peer: the kernel reads the row from the neighbour's mailbox over NVLink (CUDA IPC); nccl: send/recv per step")
+    ap.add_argument("--halo", default="peer", choices=["peer", "peer3", "nccl"],
+                    help="peer: ONE launch per step -- the stencil kernel publishes its last row, reads the neighbour's mailbox over NVLink (CUDA IPC) and acknowledges; "
+                         "peer3: round 1's three launches (publish, stencil, ack); nccl: send/recv + host sync per step")
     args = ap.parse_args()
 
     import torch
@@ -69,7 +70,7 @@ def main():
 
     # peer mode: my mailbox holds MY last row; the rank below maps it.  Handles travel once, at setup.
     outbox = inbox = None
-    if args.halo == "peer":
+    if args.halo in ("peer", "peer3"):
         outbox = kc.HaloLink.outbox(tp, W)
         if world > 1:
             handles = [None] * world
@@ -81,11 +82,13 @@ def main():
 
     def step_peer():
         counter[0] += 1
+        if args.halo == "peer":
+            return kc.height_to_normal_strip_exchange(tp, strip, outbox, inbox, counter[0], H), None
         outbox.publish(strip, (y1 - y0) - 1, counter[0])          # stream-ordered; waits (on the GPU) for the reader's ack of step-2
         return kc.height_to_normal_strip_peer(tp, strip, inbox, counter[0], H), None
 
     def step():
-        if args.halo == "peer":
+        if args.halo in ("peer", "peer3"):
             return step_peer()
         # 1. my last row -> staging (device-to-device, on the library's stream)
         kc.copy_rows(tp, send_img, 0, strip, (y1 - y0) - 1, 1)
@@ -137,8 +140,9 @@ def main():
             "strip_kernel_ms_max_over_ranks": kernel_ms,
             "strip_kernel_GBs_per_gpu": (y1 - y0) * W * 16 / (kernel_ms / 1e3) / 1e9,
             "halo_bytes_per_boundary": W * 4, "math_mode": args.math,
-            "halo": "kernel reads the neighbour's mailbox over NVLink (CUDA IPC mapping), no host sync per step" if args.halo == "peer" else "NCCL send/recv + host sync per step",
-            "halo_wait_timeouts": kc.halo_timeouts(tp) if args.halo == "peer" else None,
+            "halo": {"peer": "one launch per step: the stencil kernel publishes, reads the neighbour's mailbox over NVLink (CUDA IPC mapping) and acknowledges; no host sync",
+                     "peer3": "publish kernel + stencil kernel reading the neighbour's mailbox + ack kernel; no host sync", "nccl": "NCCL send/recv + host sync per step"}[args.halo],
+            "halo_wait_timeouts": kc.halo_timeouts(tp) if args.halo != "nccl" else None,
             "parity": "rows 0..7 (wrapped halo from the last strip) vs CPU oracle: %s" % ("bit-exact" if args.math == "exact" else "within 1e-5 rel / 1e-6 abs"),
         }), flush=True)
     if world > 1:

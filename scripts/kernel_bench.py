@@ -155,6 +155,22 @@ def main():
             kc.SlotImage(tp._ctx, o)
         record("resize_%s_1024_to_8192_plane" % filt.name.lower(), "src/shared.rs:155-201 (image 0.24.0 imageops::resize)",
                8192 * 8192, 4 + 4 / 64.0, rs, reps=10)
+    L4 = kc.SlotImage.from_planes(tp, [rnd(40 + c, 1024, 1024) for c in range(4)])
+    for filt in (ResizeFilter.Lanczos3, ResizeFilter.Gaussian):
+        def rs4(filt=filt):
+            o = kc_image()
+            call("kc_resize", tp._ctx._h, C.byref(L4._im), 8192, 8192, int(filt), C.byref(o))
+            kc.SlotImage(tp._ctx, o)
+        record("resize_%s_1024_to_8192_rgba_node" % filt.name.lower(), "src/shared.rs:141-216, four planes in one launch",
+               4 * 8192 * 8192, 4 + 4 / 64.0, rs4, reps=10)
+    del L4
+
+    # a constant plane somebody insists on seeing as pixels (kc_fill_kernel)
+    def fill():
+        cst = kc.SlotImage.from_value(tp, Size(8192, 8192), 0.25, False)        # a fresh descriptor: materialising turns it into pixels for good
+        call("kc_image_materialize", tp._ctx._h, C.byref(cst._im), 1)
+    record("fill_constant_plane_8192", "src/slot_image.rs:28-64 (vec![v; n])", 8192 * 8192, 4, fill, reps=10)
+
     big = kc.SlotImage.from_planes(tp, [rnd(6, 8192, 8192)])
 
     def down():
