@@ -417,13 +417,69 @@ def wl_mix_8192(env, steps, size=8192):
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# small-graph latency: the 32-node graph at 256^2, where the HOST is the bound (src/engine.rs:128-307 polls every 1 ms)
+# ---------------------------------------------------------------------------------------------
+def wl_small_graph(env, size=256, evals=300):
+    kc, tp = env.kc, env.tp
+    from kanter_core_b200 import SlotId
+    from tests import graphs
+    out_d = {"workload": "the 32-node graph of configs[4] at %dx%d, one evaluation after another (new inputs embedded each time): microseconds per evaluation, host + device, wall clock over %d evaluations" % (size, size, evals),
+             "reference": "src/engine.rs:128-307 (the reference needs >= 1 ms per DAG level: a polling loop)"}
+
+    def measure(replay):
+        g, out = graphs.config5_graph(size)
+        inputs = graphs.config5_inputs(77, size)
+        lg = tp.new_live_graph()
+        lg.set_node_graph(g)
+        lg.set_replay(replay)
+        imgs = [kc.SlotImage.from_planes(tp, planes) for planes in inputs]
+        for eid, img in enumerate(imgs):
+            lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, img), eid)
+
+        def one():
+            for eid, img in enumerate(imgs):
+                lg.replace_embedded(img, eid)
+            lg.request(out)
+        for _ in range(20):
+            one()
+        tp.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(evals):
+            one()
+        tp.synchronize()
+        us = (time.perf_counter() - t0) / evals * 1e6
+        got = lg.slot_data(out, SlotId(0)).image.planes()
+        want = graphs.config5_oracle(g, out, inputs)
+        ok = all(bits_equal(got[c], want[c]) for c in range(4)) if tp._ctx is not None else False
+        return us, lg.last_run_stats()["kernels"], lg.replay_stats(), ok
+
+    def body():
+        tp.set_math_mode(kc.MATH_EXACT)
+        a = measure(False)
+        b = measure(True)
+        tp.set_math_mode(kc.MATH_FAST)
+        return a, b
+    res, err = guarded(env, body)
+    if err is not None:
+        tp.set_math_mode(kc.MATH_FAST)
+        out_d["unavailable"] = err
+        return out_d
+    (us0, k0, _, ok0), (us1, k1, st1, ok1) = res
+    out_d.update({"math": "exact", "ordinary_us_per_evaluation": us0, "replay_us_per_evaluation": us1, "kernels_per_evaluation": k0,
+                  "replay": "evaluation replay (kc_live_graph_set_replay): the captured CUDA graph of the same %d kernels, one launch" % k1,
+                  "replay_stats": st1, "parity": {"ok": bool(ok0 and ok1), "sample": "every sample of the last evaluation of either mode, bit-identical to the CPU oracle"}})
+    return out_d
+
+
 def run_all(env, steps):
     """Every workload in turn; each is independent of the others' success."""
     out = {}
     for name, fn in (("height_to_normal_8192", lambda: wl_height_to_normal(env, steps)),
                      ("resize_1024_to_8192_rgba", lambda: wl_resize(env, steps)),
                      ("graphs32_batch64_4096", lambda: wl_graph_batch(env)),
-                     ("mix_rgba_8192", lambda: wl_mix_8192(env, steps))):
+                     ("mix_rgba_8192", lambda: wl_mix_8192(env, steps)),
+                     ("graph32_latency_256", lambda: wl_small_graph(env))):
         t0 = time.perf_counter()
         out[name] = fn()
         if isinstance(out[name], dict):

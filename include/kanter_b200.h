@@ -442,6 +442,12 @@ int32_t kc_live_graph_update(kc_live_graph* lg, size_t* n_processed);           
 /* ONE engine turn with priority admission (src/engine.rs:128-307 + src/process_pack.rs:33-96): the closest processable
  * ancestors of the wanted nodes, at most max_processing_nodes of them, highest propagated priority first; the ids of the
  * nodes that ran come back in that order (admitted == NULL: just the count). */
+/* Evaluation replay (no reference counterpart: the engine re-runs dirty nodes one by one, src/engine.rs:128-307).  With it on,
+ * the second identical kc_live_graph_request over an unchanged graph and the same input PLANES (new pixel content in the same
+ * buffers, or the same images embedded again) is captured into one executable CUDA graph and later ones replay it: no planner,
+ * no per-node work, one launch.  Results are those of the ordinary evaluation, bit for bit.  Off by default. */
+int32_t kc_live_graph_set_replay(kc_live_graph* lg, int32_t on);
+int32_t kc_live_graph_replay_stats(const kc_live_graph* lg, uint64_t* captures, uint64_t* replays);
 int32_t kc_live_graph_update_turn(kc_live_graph* lg, uint32_t* admitted, size_t cap, size_t* n_admitted);
 int32_t kc_live_graph_set_priority(kc_live_graph* lg, uint32_t node_id, int8_t priority);   /* node(id)?.priority.set_priority(v) */
 int32_t kc_live_graph_remove_edge(kc_live_graph* lg, const kc_edge* e);           /* remove_edge, :551-566 */

@@ -99,6 +99,8 @@ SIGNATURES = {
     "kc_graph_set_node_priority": (i32, [vp, u32, C.c_int8]),
     "kc_graph_node_priority": (i32, [vp, u32, P(C.c_int8), P(C.c_int8)]),
     "kc_live_graph_update_turn": (i32, [vp, P(u32), sz, P(sz)]),
+    "kc_live_graph_set_replay": (i32, [vp, i32]),
+    "kc_live_graph_replay_stats": (i32, [vp, P(u64), P(u64)]),
     "kc_live_graph_set_priority": (i32, [vp, u32, C.c_int8]),
     "kc_plane_in_memory": (i32, [vp, P(i32)]),
     "kc_live_graph_slot_in_memory": (i32, [vp, u32, u32, P(i32)]),

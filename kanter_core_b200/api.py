@@ -1000,6 +1000,16 @@ class LiveGraph(_GraphView):
         call("kc_live_graph_update", self._h, C.byref(n))
         return n.value
 
+    def set_replay(self, on=True):
+        """Evaluation replay: the second identical request over an unchanged graph and the same input planes is captured into
+        one CUDA graph, later ones replay it (kc_live_graph_set_replay)."""
+        call("kc_live_graph_set_replay", self._h, int(bool(on)))
+
+    def replay_stats(self):
+        c, r = C.c_uint64(), C.c_uint64()
+        call("kc_live_graph_replay_stats", self._h, C.byref(c), C.byref(r))
+        return {"captures": c.value, "replays": r.value}
+
     def update_turn(self):
         """ONE engine turn with priority admission (src/engine.rs:128-307, src/process_pack.rs:33-96): at most
         `set_max_processing_nodes` closest-processable nodes run, highest propagated priority first.  Returns

@@ -260,6 +260,14 @@ extern "C" int32_t kc_context_stats(const kc_context* ctx, uint64_t* kernel_laun
 // ---------------------------------------------------------------------------
 int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out) try {
     if (ctx->closed) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "the context was destroyed");
+    if (KcArena* a = ctx->arena_active) {   // an evaluation is being captured: allocation i is slot i of the plan's arena
+        if (a->next >= a->slots.size() || a->bytes[a->next] != bytes)
+            KC_FAIL(KC_ERR_GENERIC, "evaluation replay: allocation %zu (%zu bytes) does not match the recorded plan", a->next, bytes);
+        *out = a->slots[a->next++];
+        a->live++;
+        return KC_OK;
+    }
+    if (ctx->alloc_log) ctx->alloc_log->push_back(bytes);
     auto it = ctx->free_lists.find(bytes);
     if (it != ctx->free_lists.end() && !it->second.empty()) {
         *out = it->second.back();
@@ -277,8 +285,33 @@ int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out) try {
     return KC_OK;
 } KC_ABI_CATCH
 
+static void arena_destroy(KcArena* a) {
+    if (a->base) cudaFree(a->base);
+    delete a;
+}
+void kc_arena_orphan(kc_context* ctx, KcArena* a) {   // the plan that owned it is gone
+    if (!a) return;
+    if (a->live == 0) {
+        ctx->arenas.erase(std::remove(ctx->arenas.begin(), ctx->arenas.end(), a), ctx->arenas.end());
+        if (!ctx->closed) cudaStreamSynchronize(ctx->stream);
+        arena_destroy(a);
+    } else {
+        a->orphaned = true;
+    }
+}
+
 void kc_dev_free(kc_context* ctx, void* p, size_t bytes) {
     if (!p) return;
+    for (size_t i = 0; i < ctx->arenas.size(); ++i) {   // (empty unless a live graph replays its evaluations)
+        KcArena* a = ctx->arenas[i];
+        if (p < a->base || p >= (char*)a->base + ((char*)a->slots.back() - (char*)a->base) + a->bytes.back()) continue;
+        if (--a->live == 0 && a->orphaned) {
+            ctx->arenas.erase(ctx->arenas.begin() + i);
+            if (!ctx->closed) cudaStreamSynchronize(ctx->stream);
+            arena_destroy(a);
+        }
+        return;                                          // arena memory never enters the free lists
+    }
     if (ctx->closed) {   // a plane that outlived its context: the streams are gone, free synchronously
         cudaFree(p);
         return;
@@ -414,6 +447,7 @@ int32_t kc_enforce_threshold(kc_context* ctx) try {
 } KC_ABI_CATCH
 int32_t kcp_reload(kc_context* ctx, kc_plane* p) {
     if (p->kind != KC_PLANE_SPILLED) return KC_OK;
+    if (ctx->capturing) KC_FAIL(KC_ERR_GENERIC, "a plane would have to come back from host memory during a stream capture");
     const size_t bytes = plane_alloc_bytes(p);
     void* d = nullptr;
     KC_TRY(kc_dev_alloc(ctx, bytes, &d));
@@ -704,6 +738,7 @@ extern "C" int32_t kc_image_from_u8(kc_context* ctx, const uint8_t* samples, uin
     if (!ctx || !samples || !out) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "NULL argument");
     if (channels < 1 || channels > 4) KC_FAIL(KC_ERR_INVALID_BUFFER_COUNT, "channels must be 1..4, got %u", channels);
     KcGuard g(ctx);
+    if (ctx->capturing) KC_FAIL(KC_ERR_GENERIC, "an image would have to be uploaded during a stream capture");
     kci_clear(out);
     out->kind = KC_IMAGE_RGBA;
     out->width = w;

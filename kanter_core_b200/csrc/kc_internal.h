@@ -112,6 +112,17 @@ struct kc_plane {
     size_t bytes() const { return count() * sizeof(float); }
 };
 
+// Device memory of a frozen evaluation plan (kc_exec.cu, kc_live_graph replay): every allocation the evaluation makes
+// gets a slot of its own, the same one on every replay, so the captured kernels' pointer arguments stay valid.
+struct KcArena {
+    void* base = nullptr;
+    std::vector<void*> slots;
+    std::vector<size_t> bytes;
+    size_t next = 0;          // the slot the next allocation of the capturing evaluation gets
+    int live = 0;             // buffers handed out and not yet released
+    bool orphaned = false;    // the plan is gone: the memory goes when `live` reaches 0
+};
+
 struct kc_context {
     // Planes and live graphs point back at their context.  Each of them, and the caller's own
     // handle, holds one count; kc_context_destroy releases the device side at once (`closed`)
@@ -170,6 +181,12 @@ struct kc_context {
     // 4096-wide map an input error e becomes an output error of about e * W / 2 -- so the 4e-7 of FAST pow would
     // leave the north star's 1e-5 / 1e-6; bit-identical inputs keep FAST HeightToNormal inside it.
     int exact_scope = 0;
+    // evaluation replay: a log of allocation sizes while a plan is being recorded, the arena that serves allocations
+    // while one is being captured, and every arena that still has buffers out
+    std::vector<size_t>* alloc_log = nullptr;
+    KcArena* arena_active = nullptr;
+    std::vector<KcArena*> arenas;
+    bool capturing = false;                    // ctx->stream is in CUDA stream capture: nothing but kernel launches may be enqueued
     unsigned int* d_halo_timeouts = nullptr;   // device counter of waits that gave up (this context's kernels only)
     bool halo_used = false;
     uint32_t halo_timeouts_seen = 0;
@@ -276,6 +293,7 @@ struct KcTuning {
 };
 extern KcTuning g_kc_tuning;
 // kc_jit.cu
+uint64_t kcj_generation();   // bumped whenever a specialised kernel becomes available: captured plans older than that are re-captured
 int32_t kcj_try_launch(kc_context* ctx, const KcTapeArgs& args, int ns_max, int v, int ctas, int stages, bool* launched);
 
 // raise a kernel's dynamic shared-memory limit once per context (= per device)
@@ -291,6 +309,7 @@ inline int32_t kc_ensure_smem_attr(kc_context* ctx, const void* fn, int bytes) {
 int32_t kc_dev_alloc(kc_context* ctx, size_t bytes, void** out);
 void kc_dev_free(kc_context* ctx, void* p, size_t bytes);
 void kc_dev_trim(kc_context* ctx);
+void kc_arena_orphan(kc_context* ctx, KcArena* a);
 
 // ---- NUMA placement of pinned host memory (kc_numa.cu) ---------------------------------
 int kc_device_numa_node(int device);                                  // -1: unknown

@@ -31,37 +31,66 @@ __global__ void __launch_bounds__(TVM_THREADS, MINB)
 // byte / 255.0f, correctly rounded, without the generic div.rn expansion: q = b*y, q += (b - 255 q)*y
 // with y = RN(1/255).  All 256 inputs are checked against the oracle's `as f32 / 255.` by
 // tests/test_gpu_ops.py::test_u8_roundtrip_every_value.
-__device__ __forceinline__ float kc_u8_over_255(uint32_t byte) {
-    const float a = (float)byte, y = 0x1.010102p-8f;
+// The integer -> float step is the 2^23 trick: byte k of the word is dropped into the mantissa of 8388608.0f by ONE
+// byte permute and the bias subtracted (both full-rate; I2F.U8 runs on the quarter-rate conversion unit and was where
+// 74 % of the kernel's stall samples sat, profiles/ncu_full_from_u8_r02.txt).
+template <int K>
+__device__ __forceinline__ float kc_u8_over_255(uint32_t word) {
+    const float a = __fsub_rn(__uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650u | K)), 8388608.0f);   // exact: 0..255
+    const float y = 0x1.010102p-8f;
     const float q = __fmul_rn(a, y);
     return __fmaf_rn(__fmaf_rn(-255.0f, q, a), y, q);
 }
 
 // deconstruct_image, src/shared.rs:27-33: plane_c[i] = samples[i*C + c] as f32 / 255.
-// One thread converts 4 consecutive pixels: it reads 4*C bytes and writes one
-// float4 per channel plane.
+// One thread converts 4 consecutive pixels per item (4*C bytes in, one float4 per channel plane out) and keeps
+// FU8_ITEMS items in flight, their loads issued together: the kernel is a pure stream and lives on bytes in flight.
+constexpr int FU8_ITEMS = 2;
 template <int C>
-__global__ void __launch_bounds__(256) kc_from_u8_kernel(const uint8_t* __restrict__ s, size_t n,
+__global__ void __launch_bounds__(256, 6) kc_from_u8_kernel(const uint8_t* __restrict__ s, size_t n,
                                                           float* __restrict__ p0, float* __restrict__ p1,
                                                           float* __restrict__ p2, float* __restrict__ p3) {
     const size_t nvec = n >> 2;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     float* planes[4] = {p0, p1, p2, p3};
-    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += stride) {
-        // 4*C bytes starting at a 4-byte aligned offset: C 32-bit loads
-        uint32_t wds[C];
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(s + 4 * C * v);
+    for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * FU8_ITEMS) {
+        uint32_t wds[FU8_ITEMS][C];
 #pragma unroll
-        for (int k = 0; k < C; ++k) wds[k] = __ldcs(src + k);
-        float vals[4][C];
+        for (int it = 0; it < FU8_ITEMS; ++it) {
+            const size_t v = v0 + it * stride;
+            if (v < nvec) {
+                // 4*C bytes starting at a 4-byte aligned offset: one 128-bit load when C == 4, C 32-bit loads otherwise
+                if (C == 4) {
+                    const uint4 q = __ldcs(reinterpret_cast<const uint4*>(s) + v);
+                    wds[it][0] = q.x; wds[it][1 % C] = q.y; wds[it][2 % C] = q.z; wds[it][3 % C] = q.w;
+                } else {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(s + 4 * C * v);
 #pragma unroll
-        for (int b = 0; b < 4 * C; ++b) {
-            const uint32_t byte = (wds[b >> 2] >> (8 * (b & 3))) & 0xffu;
-            vals[b / C][b % C] = kc_u8_over_255(byte);
+                    for (int k = 0; k < C; ++k) wds[it][k] = __ldcs(src + k);
+                }
+            }
         }
 #pragma unroll
-        for (int c = 0; c < C; ++c)
-            __stcs(reinterpret_cast<float4*>(planes[c]) + v, make_float4(vals[0][c], vals[1][c], vals[2][c], vals[3][c]));
+        for (int it = 0; it < FU8_ITEMS; ++it) {
+            const size_t v = v0 + it * stride;
+            if (v >= nvec) break;
+            float vals[4][C];
+#pragma unroll
+            for (int b = 0; b < 4 * C; ++b) {
+                const uint32_t w = wds[it][b >> 2];
+                float f;
+                switch (b & 3) {
+                    case 0: f = kc_u8_over_255<0>(w); break;
+                    case 1: f = kc_u8_over_255<1>(w); break;
+                    case 2: f = kc_u8_over_255<2>(w); break;
+                    default: f = kc_u8_over_255<3>(w); break;
+                }
+                vals[b / C][b % C] = f;
+            }
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                __stcs(reinterpret_cast<float4*>(planes[c]) + v, make_float4(vals[0][c], vals[1][c], vals[2][c], vals[3][c]));
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (size_t i = 4 * nvec; i < n; ++i)
@@ -185,7 +214,7 @@ int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
 int32_t kck_from_u8(kc_context* ctx, const uint8_t* d_samples, uint32_t channels, size_t n,
                     float* const planes[4]) {
     if (n == 0) return KC_OK;
-    const int grid = grid_for(ctx, (n + 3) >> 2, 256, 5);   // 5 CTAs of 256 threads are resident per SM: one wave
+    const int grid = grid_for(ctx, (n + 3) >> 2, 256, 6);   // 6 CTAs of 256 threads are resident per SM (<= 40 registers): one full wave
     KcTimed timed(ctx, KC_KERNEL_FROM_U8);
     switch (channels) {
         case 1: kc_from_u8_kernel<1><<<grid, 256, 0, ctx->stream>>>(d_samples, n, planes[0], planes[1], planes[2], planes[3]); break;

@@ -117,6 +117,7 @@ int32_t get_axis(kc_context* ctx, uint32_t src_len, uint32_t dst_len, int filter
         out = it->second;
         return KC_OK;
     }
+    if (ctx->capturing) KC_FAIL(KC_ERR_GENERIC, "a tap table would have to be uploaded during a stream capture");
     auto t = std::make_shared<KcAxisTable>();
     t->src_len = src_len;
     t->dst_len = dst_len;
@@ -993,6 +994,7 @@ __global__ void __launch_bounds__(VM_THREADS) kc_resize_v_march_kernel(const flo
 // window of a ring slot, or a real weight is NaN (the sentinel) -- the caller then falls back
 int32_t build_march_tables(kc_context* ctx, KcAxisTable& t) {
     if (t.march_state != 0) return KC_OK;
+    if (ctx->capturing) KC_FAIL(KC_ERR_GENERIC, "a marching table would have to be uploaded during a stream capture");
     t.march_state = -1;
     const uint32_t S = t.src_len, D = t.dst_len;
     std::vector<float> w((size_t)S * VM_SLOTS, nanf(""));

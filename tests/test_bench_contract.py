@@ -71,7 +71,9 @@ def test_own_arm_prints_one_contract_line():
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
     # the other BASELINE configs ride in the same line, each with ms, bytes, a roofline fraction and a parity verdict
     w = d["workloads"]
-    assert set(w) == {"height_to_normal_8192", "resize_1024_to_8192_rgba", "graphs32_batch64_4096", "mix_rgba_8192"}
+    assert set(w) == {"height_to_normal_8192", "resize_1024_to_8192_rgba", "graphs32_batch64_4096", "mix_rgba_8192", "graph32_latency_256"}
+    lat = w["graph32_latency_256"]
+    assert lat["parity"]["ok"] is True and 0 < lat["replay_us_per_evaluation"] < lat["ordinary_us_per_evaluation"], lat
     for mode in ("fast", "exact"):
         e = w["height_to_normal_8192"][mode]
         assert e["ms"] > 0 and 0.2 < e["roofline"]["frac"] <= 1.05 and e["parity"]["ok"] is True, e

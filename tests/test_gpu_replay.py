@@ -1,0 +1,173 @@
+"""Evaluation replay (kc_live_graph_set_replay): the second identical request over an unchanged graph and the same input
+planes is captured into one executable CUDA graph and later ones replay it.  What must hold: results identical to the
+ordinary evaluation (and so to the oracle) bit for bit whatever the pixel content, planes somebody still holds are never
+overwritten, any change of the graph or of its inputs' identity falls back and re-captures."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import kanter_core_b200 as kc
+import oracle
+from kanter_core_b200 import MixType, Node, NodeType, SlotId
+from kanter_core_b200._lib import call, kc_image
+from tests import graphs
+
+pytestmark = pytest.mark.gpu
+
+
+def bits_equal(a, b):
+    return np.array_equal(np.ascontiguousarray(a).view(np.uint32), np.ascontiguousarray(b).view(np.uint32))
+
+
+class Buffers:
+    """Images over planes whose CONTENT is rewritten in place (kc_plane_upload): what a caller streaming frames through
+    fixed device buffers does."""
+
+    def __init__(self, tp, shapes):
+        self.tp, self.images = tp, []
+        for n, (h, w) in shapes:
+            im = kc_image()
+            im.kind, im.width, im.height = (1 if n == 4 else 0), w, h
+            for c in range(n):
+                pl = C.c_void_p()
+                call("kc_plane_create", tp._ctx._h, w, h, C.byref(pl))
+                im.planes[c] = pl
+            self.images.append(kc.SlotImage(tp._ctx, im))
+
+    def fill(self, planes_per_image):
+        for img, planes in zip(self.images, planes_per_image):
+            for c, p in enumerate(planes):
+                a = np.ascontiguousarray(p, dtype=np.float32)
+                call("kc_plane_upload", img._im.planes[c], a.ctypes.data)
+
+
+def _config5(tp, size):
+    g, out = graphs.config5_graph(size)
+    lsize = max(1, size // 4)
+    bufs = Buffers(tp, [(4, (size, size)), (1, (size, size)), (4, (lsize, lsize))])
+    lg = tp.new_live_graph()
+    lg.set_node_graph(g)
+    for eid, img in enumerate(bufs.images):
+        lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, img), eid)
+    return g, out, bufs, lg
+
+
+@pytest.mark.parametrize("size", [64, 256])
+def test_replay_is_bit_identical_to_the_oracle_frame_after_frame(tex_pro, size):
+    g, out, bufs, lg = _config5(tex_pro, size)
+    lg.set_replay(True)
+    for frame in range(7):
+        inputs = graphs.config5_inputs(300 + frame, size)
+        bufs.fill(inputs)
+        for eid, img in enumerate(bufs.images):            # "new inputs arrived": same planes, new content
+            lg.replace_embedded(img, eid)
+        lg.request(out)
+        got = lg.slot_data(out, SlotId(0)).image.planes()
+        want = graphs.config5_oracle(g, out, inputs)
+        for c in range(4):
+            assert bits_equal(got[c], want[c]), (frame, c)
+        del got
+    st = lg.replay_stats()
+    assert st["captures"] >= 1 and st["replays"] >= 3, st     # (a specialised kernel arriving from another test's compile re-captures once)
+    assert lg.last_run_stats()["kernels"] > 0
+
+
+def test_replay_never_overwrites_a_plane_somebody_holds(tex_pro):
+    size = 64
+    g, out, bufs, lg = _config5(tex_pro, size)
+    lg.set_replay(True)
+    held, held_want = None, None
+    for frame in range(8):
+        inputs = graphs.config5_inputs(400 + frame, size)
+        bufs.fill(inputs)
+        for eid, img in enumerate(bufs.images):
+            lg.replace_embedded(img, eid)
+        lg.request(out)
+        want = graphs.config5_oracle(g, out, inputs)
+        img = lg.slot_data(out, SlotId(0)).image
+        for c in range(4):
+            assert bits_equal(img.planes()[c], want[c]), (frame, c)
+        if held is not None:                                # the frame before this one, still in a caller's hands
+            for c in range(4):
+                assert bits_equal(held.planes()[c], held_want[c]), ("held", frame, c)
+        if frame in (3, 4):
+            held, held_want = img, want                     # keep it across the next evaluation
+        else:
+            held, held_want = None, None
+        del img
+    st = lg.replay_stats()
+    assert st["captures"] >= 1 and st["replays"] >= 2, st   # replays resume once the caller lets go
+
+
+def test_replay_follows_changes_of_the_graph_and_of_the_inputs(tex_pro):
+    tp = tex_pro
+    size = 96
+    r = np.random.default_rng(5)
+    a0, b0 = r.random((size, size), dtype=np.float32), r.random((size, size), dtype=np.float32)
+    bufs = Buffers(tp, [(1, (size, size)), (1, (size, size))])
+    bufs.fill([[a0], [b0]])
+    lg = tp.new_live_graph()
+    lg.set_replay(True)
+    for eid, img in enumerate(bufs.images):
+        lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, img), eid)
+    ea = lg.add_node(Node.new(NodeType.Embed(0)))
+    eb = lg.add_node(Node.new(NodeType.Embed(1)))
+    m = lg.add_node(Node.new(NodeType.Mix(MixType.Multiply)))
+    h = lg.add_node(Node.new(NodeType.HeightToNormal))
+    o = lg.add_node(Node.new(NodeType.OutputRgba("out")))
+    lg.connect(ea, m, SlotId(0), SlotId(0))
+    lg.connect(eb, m, SlotId(0), SlotId(1))
+    lg.connect(m, h, SlotId(0), SlotId(0))
+    lg.connect(h, o, SlotId(0), SlotId(0))
+
+    def frame(op, a, b):
+        for eid, img in enumerate(bufs.images):
+            lg.replace_embedded(img, eid)
+        lg.request(o)
+        got = lg.slot_data(o, SlotId(0)).image.planes()
+        want = oracle.height_to_normal(oracle.mix_plane(op, a, b))
+        for c in range(3):
+            assert bits_equal(got[c], want[c]), c
+
+    for _ in range(4):
+        frame(2, a0, b0)
+    assert lg.replay_stats()["replays"] >= 2
+    lg.set_mix_type(m, MixType.Add)                         # the graph changed: the plan is gone
+    for _ in range(4):
+        frame(0, a0, b0)
+    a1 = r.random((size, size), dtype=np.float32)
+    other = kc.SlotImage.from_planes(tp, [a1])              # ANOTHER plane embedded under id 0: another plan
+    for _ in range(4):
+        lg.replace_embedded(other, 0)
+        lg.replace_embedded(bufs.images[1], 1)
+        lg.request(o)
+        got = lg.slot_data(o, SlotId(0)).image.planes()
+        want = oracle.height_to_normal(oracle.mix_plane(0, a1, b0))
+        for c in range(3):
+            assert bits_equal(got[c], want[c]), c
+    st = lg.replay_stats()
+    assert st["captures"] >= 3, st
+    lg.set_replay(False)
+    frame(0, a0, b0)                                        # and off again: the ordinary path
+
+
+@pytest.mark.parametrize("name", sorted(n for n in graphs.GOLDEN_CASES if graphs.GOLDEN_CASES[n]().embeds))
+def test_replay_on_the_reference_goldens(tex_pro, name):
+    """The reference's golden graphs that take embedded images, evaluated five times with replay on (the images embedded
+    again before each): the reference's bytes every time, through the ordinary pass, the capture and the replays."""
+    case = graphs.GOLDEN_CASES[name]()
+    lg = tex_pro.new_live_graph()
+    lg.set_node_graph(case.graph)
+    lg.set_replay(True)
+    imgs = {eid: kc.SlotImage.from_u8(tex_pro, graphs.decode(path)) for eid, path in case.embeds.items()}
+    for eid, img in imgs.items():
+        lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, img), eid)
+    want = case.expected()
+    for i in range(5):
+        for eid, img in imgs.items():
+            lg.replace_embedded(img, eid)
+        lg.request(case.node)
+        got = lg.buffer_rgba(case.node, SlotId(0))
+        assert np.array_equal(got, want), (i, int((got != want).sum()))
+    assert lg.replay_stats()["replays"] >= 2
