@@ -70,6 +70,7 @@ struct KcAxisTable {
     // slot whose window holds r (NaN: none), and the output that is complete after r (-1: none)
     int march_state = 0;           // 0 not built, 1 usable, -1 this axis cannot march (falls back)
     float* d_march_w = nullptr;    // [src_len][8]
+    float* d_march_w2 = nullptr;   // [src_len][8][2]: every weight twice (the TMA-fed march reads FFMA2 operand pairs)
     int32_t* d_march_o = nullptr;  // [src_len][8]
 };
 

@@ -990,6 +990,144 @@ __global__ void __launch_bounds__(VM_THREADS) kc_resize_v_march_kernel(const flo
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// The same march fed by the TMA.  The kernel above lives on the loads each warp has in flight between two stretches of
+// arithmetic (issue eight rows, wait, compute them, repeat): at 443 threads per SM that is latency-bound at 3.7 TB/s.  Here a
+// PRODUCER warp keeps VT_STAGES stages of VT_R source rows x 512 columns in flight as 2-D tensor-map loads (two 256-column
+// boxes per stage, completing on an mbarrier, with the L2 hints of the kernel above: rows the block above also needs are
+// evict-last, the rest evict-first) plus the stage's slice of the marching tables as two 1-D bulk copies; four COMPUTE warps
+// (a thread owns four columns) consume the stages out of shared memory and hand them back through an "empty" mbarrier.  Bytes
+// in flight are set by the stage ring, not by what the compute warps happen to be doing.  Arithmetic and order are those of
+// kc_resize_v_march_kernel.
+// ---------------------------------------------------------------------------
+constexpr int VT_R = 8;                       // source rows per stage
+constexpr int VT_STAGES = 4;
+constexpr int VT_COLS = 512;                  // source columns per block (128 compute threads x 4)
+constexpr int VT_PIX_BYTES = VT_R * VT_COLS * 4;
+constexpr int VT_STAGE_BYTES = VT_PIX_BYTES + VT_R * 64 + VT_R * 32;  // pixels + weights (each one twice: an FFMA2 operand pair) + retire ids
+
+__device__ __forceinline__ void vt_tma_load_2d_hint(void* dst, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                     ft_smem(dst)),
+                 "l"(map), "r"(c0), "r"(c1), "r"(ft_smem(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void vt_bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ft_smem(dst)), "l"(src), "r"(bytes),
+                 "r"(ft_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void vt_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ft_smem(bar)) : "memory");
+}
+
+template <bool EXACT>
+__global__ void __launch_bounds__(160) kc_resize_v_tma_kernel(const __grid_constant__ CUtensorMap tm_src, uint32_t sw4, uint32_t sh, float4* __restrict__ tmp,
+                                                              uint32_t dh, const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount,
+                                                              const float2* __restrict__ mw2, const int* __restrict__ mo, uint32_t rows_per_cta, float one) {
+    extern __shared__ __align__(128) unsigned char vts[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(vts);               // [VT_STAGES]
+    uint64_t* empty = full + VT_STAGES;                              // [VT_STAGES]
+    unsigned char* stage0 = vts + 128;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t oyA = blockIdx.y * rows_per_cta, oyB = min(oyA + rows_per_cta, dh);
+    const uint32_t r0 = __ldg(vleft + oyA), r1 = __ldg(vleft + oyB - 1) + __ldg(vcount + oyB - 1);
+    const uint32_t nr = r1 - r0;
+    const uint32_t r_shared = oyA == 0 ? r0 : min(r1, __ldg(vleft + oyA - 1) + __ldg(vcount + oyA - 1));
+    const uint32_t n_shared = r_shared > r0 ? r_shared - r0 : 0u;    // rows the block above needs as well
+    const uint32_t nstage = (nr + VT_R - 1) / VT_R;
+    const uint32_t cx0 = blockIdx.x * VT_COLS;
+    if (tid == 0) {
+        for (int i = 0; i < VT_STAGES; ++i) {
+            ft_mbar_init(&full[i], 1);
+            ft_mbar_init(&empty[i], 4);                              // one arrival per compute warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 4) {
+        // ---- producer ----
+        if (lane == 0) {
+            const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+            for (uint32_t k = 0; k < nstage; ++k) {
+                const int st = k % VT_STAGES;
+                if (k >= VT_STAGES) ft_mbar_wait(&empty[st], ((k / VT_STAGES) - 1) & 1u);
+                unsigned char* S = stage0 + (size_t)st * VT_STAGE_BYTES;
+                const uint32_t row = r0 + k * VT_R;                  // rows past the image arrive as zeros and are never used
+                const uint32_t trows = min((uint32_t)VT_R, sh - row);                    // table rows that exist
+                ft_mbar_expect_tx(&full[st], VT_PIX_BYTES + trows * 64 + trows * 32);
+                const uint64_t pol = k * VT_R < n_shared ? pol_keep : pol_stream;
+                vt_tma_load_2d_hint(S, &tm_src, cx0, row, &full[st], pol);
+                vt_tma_load_2d_hint(S + VT_R * 256 * 4, &tm_src, cx0 + 256, row, &full[st], pol);
+                vt_bulk_load_1d(S + VT_PIX_BYTES, mw2 + (size_t)row * VM_SLOTS, trows * 64, &full[st]);
+                vt_bulk_load_1d(S + VT_PIX_BYTES + VT_R * 64, mo + (size_t)row * VM_SLOTS, trows * 32, &full[st]);
+            }
+        }
+        return;
+    }
+    // ---- compute: thread t owns columns cx0 + 4t .. 4t+3 ----
+    const uint32_t x4 = blockIdx.x * (VT_COLS / 4) + tid;
+    const bool live = x4 < sw4;
+    const uint64_t pol_keep = l2_policy_evict_last();
+    // the four columns' running sums of the eight open outputs, as the two operand pairs of an FFMA2
+    float2 alo[VM_SLOTS], ahi[VM_SLOTS];
+#pragma unroll
+    for (int s = 0; s < VM_SLOTS; ++s) alo[s] = ahi[s] = make_float2(0.f, 0.f);
+    const uint32_t half = tid >> 6, c4 = tid & 63;                   // which 256-column box, which float4 in its rows
+    for (uint32_t k = 0; k < nstage; ++k) {
+        const int st = k % VT_STAGES;
+        ft_mbar_wait(&full[st], (k / VT_STAGES) & 1u);
+        const unsigned char* S = stage0 + (size_t)st * VT_STAGE_BYTES;
+        const float4* px = reinterpret_cast<const float4*>(S + (size_t)half * VT_R * 256 * 4) + c4;
+        const float4* wt = reinterpret_cast<const float4*>(S + VT_PIX_BYTES);               // per row: (w0,w0,w1,w1) (w2,w2,w3,w3) ...
+        const int4* ot = reinterpret_cast<const int4*>(S + VT_PIX_BYTES + VT_R * 64);
+#pragma unroll
+        for (int u = 0; u < VT_R; ++u) {
+            const uint32_t r = k * VT_R + u;                         // relative to r0
+            if (r >= nr) break;                                      // uniform
+            const float4 v = px[u * 64];
+            const float2 vlo = make_float2(v.x, v.y), vhi = make_float2(v.z, v.w);
+#pragma unroll
+            for (int q = 0; q < VM_SLOTS / 2; ++q) {
+                const float4 wp = wt[4 * u + q];                     // the weights of slots 2q and 2q+1, each already a pair
+                if (wp.x == wp.x) {                                  // NaN: the row is in no window of that slot
+                    const float2 ww = make_float2(wp.x, wp.y);
+                    if (EXACT) {
+                        alo[2 * q] = __ffma2_rn(alo[2 * q], make_float2(one, one), __fmul2_rn(vlo, ww));
+                        ahi[2 * q] = __ffma2_rn(ahi[2 * q], make_float2(one, one), __fmul2_rn(vhi, ww));
+                    } else {
+                        alo[2 * q] = __ffma2_rn(vlo, ww, alo[2 * q]);
+                        ahi[2 * q] = __ffma2_rn(vhi, ww, ahi[2 * q]);
+                    }
+                }
+                if (wp.z == wp.z) {
+                    const float2 ww = make_float2(wp.z, wp.w);
+                    if (EXACT) {
+                        alo[2 * q + 1] = __ffma2_rn(alo[2 * q + 1], make_float2(one, one), __fmul2_rn(vlo, ww));
+                        ahi[2 * q + 1] = __ffma2_rn(ahi[2 * q + 1], make_float2(one, one), __fmul2_rn(vhi, ww));
+                    } else {
+                        alo[2 * q + 1] = __ffma2_rn(vlo, ww, alo[2 * q + 1]);
+                        ahi[2 * q + 1] = __ffma2_rn(vhi, ww, ahi[2 * q + 1]);
+                    }
+                }
+            }
+            const int4 oa = ot[2 * u], ob = ot[2 * u + 1];
+            if ((oa.x & oa.y & oa.z & oa.w & ob.x & ob.y & ob.z & ob.w) < 0) continue;      // nothing completes on this row
+            const int o[VM_SLOTS] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+#pragma unroll
+            for (int s = 0; s < VM_SLOTS; ++s)
+                if (o[s] >= 0) {
+                    if (live && (uint32_t)o[s] >= oyA && (uint32_t)o[s] < oyB)
+                        st_hint4(tmp + (size_t)o[s] * sw4 + x4, make_float4(alo[s].x, alo[s].y, ahi[s].x, ahi[s].y), pol_keep);
+                    alo[s] = ahi[s] = make_float2(0.f, 0.f);
+                }
+        }
+        __syncwarp();
+        if (lane == 0) vt_mbar_arrive(&empty[st]);                   // this warp is done with the stage
+    }
+}
+
 // host: the marching tables of an axis; false when some source index sits in more than one
 // window of a ring slot, or a real weight is NaN (the sentinel) -- the caller then falls back
 int32_t build_march_tables(kc_context* ctx, KcAxisTable& t) {
@@ -1010,6 +1148,13 @@ int32_t build_march_tables(kc_context* ctx, KcAxisTable& t) {
         }
         if (o[(size_t)(l + n - 1) * VM_SLOTS + s] >= 0) return KC_OK;
         o[(size_t)(l + n - 1) * VM_SLOTS + s] = (int32_t)oy;
+    }
+    {   // the same weights with every entry doubled: an aligned (w, w) pair is what an FFMA2 takes as its broadcast operand
+        std::vector<float> w2(w.size() * 2);
+        for (size_t i = 0; i < w.size(); ++i) w2[2 * i] = w2[2 * i + 1] = w[i];
+        KC_CUDA(cudaMalloc((void**)&t.d_march_w2, w2.size() * sizeof(float)));
+        KC_CUDA(cudaMemcpyAsync(t.d_march_w2, w2.data(), w2.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        KC_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     KC_CUDA(cudaMalloc((void**)&t.d_march_w, w.size() * sizeof(float)));
     KC_CUDA(cudaMalloc((void**)&t.d_march_o, o.size() * sizeof(int32_t)));
@@ -1235,10 +1380,34 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
                 }
                 return mx;
             };
-            while (rows > 1 && (size_t)range(rows) * 64 > 64 * 1024) rows >>= 1;
+            // the TMA-fed march (default where its shape fits: widths that are multiples of four, a tensor-map encoder at hand)
+            static const bool no_vtma = getenv("KC_RESIZE_NO_VTMA") != nullptr;
+            if (!no_vtma && !ctx->capturing && tensor_map_encoder() && (((uintptr_t)src | (uintptr_t)tmp) & 15u) == 0 && sw >= (uint32_t)VT_COLS / 2) {
+                CUtensorMap m_src;
+                // output rows per block: a whole wave of blocks at three per SM, never fewer than 16 rows
+                const uint32_t strips = (sw + VT_COLS - 1) / VT_COLS;
+                const uint32_t want_gy = std::max<uint32_t>(1u, (uint32_t)(ctx->sm_count * 3) / strips);
+                uint32_t rpc = std::max<uint32_t>(16u, (dh + want_gy - 1) / want_gy);
+                if (env_rows > 0) rpc = (uint32_t)env_rows;
+                const uint32_t gy2 = (dh + rpc - 1) / rpc;
+                const size_t smem2 = 128 + (size_t)VT_STAGES * VT_STAGE_BYTES;
+                if (gy2 <= 65535u && make_tensor_map_2d(&m_src, src, sw, sh, 256u, (uint32_t)VT_R)) {
+                    const void* fn = exact ? (const void*)kc_resize_v_tma_kernel<true> : (const void*)kc_resize_v_tma_kernel<false>;
+                    KC_TRY(kc_ensure_smem_attr(ctx, fn, 100 * 1024));
+                    const uint32_t sw4 = sw >> 2;
+                    float4* tmp4 = (float4*)tmp;
+                    const float one = 1.0f;
+                    void* args[] = {(void*)&m_src, (void*)&sw4, (void*)&sh, (void*)&tmp4, (void*)&dh, (void*)&tv->d_left, (void*)&tv->d_count,
+                                    (void*)&tv->d_march_w2, (void*)&tv->d_march_o, (void*)&rpc, (void*)&one};
+                    KcTimed timed(ctx, KC_KERNEL_RESIZE_V);
+                    KC_CUDA(cudaLaunchKernel(fn, dim3(strips, gy2), dim3(160), args, smem2, ctx->stream));
+                    marched = true;
+                }
+            }
+            while (!marched && rows > 1 && (size_t)range(rows) * 64 > 64 * 1024) rows >>= 1;
             const size_t smem = (size_t)range(rows) * 64;
             const uint32_t gy = (dh + rows - 1) / rows;
-            if (smem <= 64 * 1024 && gy <= 65535u) {
+            if (!marched && smem <= 64 * 1024 && gy <= 65535u) {
                 KC_TRY(kc_ensure_smem_attr(ctx, exact ? (const void*)kc_resize_v_march_kernel<true> : (const void*)kc_resize_v_march_kernel<false>, 64 * 1024));
                 dim3 grid(((sw >> 2) + VM_THREADS - 1) / VM_THREADS, gy);
                 KcTimed timed(ctx, KC_KERNEL_RESIZE_V);
