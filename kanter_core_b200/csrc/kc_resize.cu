@@ -554,6 +554,23 @@ __device__ __forceinline__ void ft_tma_store_2d(const CUtensorMap* map, uint32_t
                  : "memory");
 }
 
+// N vertical taps of four adjacent source columns for FOUR consecutive output rows that share one window: each source
+// float4 is loaded once for the four rows, their weights arrive as one float4 per tap (rows are adjacent in the table)
+template <bool EXACT, int N, int WP>
+__device__ __forceinline__ void ft_vtaps4(const float* sp, uint32_t pitch, const float* wc, float one, float2 (&a0)[4], float2 (&a1)[4]) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const float4 v = *reinterpret_cast<const float4*>(sp + k * pitch);
+        const float4 w4 = *reinterpret_cast<const float4*>(wc + k * WP);
+        const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            a0[j] = tap2<EXACT>(a0[j], make_float2(v.x, v.y), w[j], one);
+            a1[j] = tap2<EXACT>(a1[j], make_float2(v.z, v.w), w[j], one);
+        }
+    }
+}
+
 // clamp to [lo, hi]; `sat`: the bounds are [0, 1] and a is known to be a number, so one saturating add does it
 __device__ __forceinline__ float ft_clamp(float a, float lo, float hi, bool sat) {
     if (sat) {
@@ -677,8 +694,7 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
         const uint32_t live_rows = min((uint32_t)G, nrows - g * G);   // rows past the strip compute nothing (their table rows may be real)
         // ---- vertical pass: Tm[c][r] = sum_k S[vl[r]-ry0+k][c] * wv[k][r] ----
         const uint32_t nquad = (ncx + 3) >> 2;
-        for (uint32_t i = tid; i < nquad * G; i += FT_THREADS) {
-            const uint32_t cq = i / G, r = i % G;
+        auto vrow = [&](uint32_t cq, uint32_t r) {                    // one output row of four source columns
             const uint32_t n = r < live_rows ? VT[VP + r] : 0u;
             const float* sp = S + (size_t)(VT[r] - ry0) * pcols + 4 * cq;
             float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
@@ -705,6 +721,52 @@ __global__ void __launch_bounds__(FT_THREADS, MINB) kc_resize_tma_kernel(
             asm("max.NaN.f32 %0, %1, %2;" : "=f"(m1) : "f"(fabsf(a1.x)), "f"(fabsf(a1.y)));
             asm("max.NaN.f32 %0, %1, %2;" : "=f"(m0) : "f"(m0), "f"(m1));
             if (!(m0 <= 3.402823466e+38f)) nonfinite[it] = 1u;
+        };
+        if (((row0 + g * G) & 3u) == 0) {
+            // items of four output rows: when they share one window (always, for integer ratios >= 4) each source value is
+            // loaded once for the four and a tap's four weights are one LDS.128
+            for (uint32_t i = tid; i < nquad * (G / 4); i += FT_THREADS) {
+                const uint32_t cq = i / (G / 4), r = 4 * (i % (G / 4));
+                const uint4 l4 = *reinterpret_cast<const uint4*>(VT + r), c4 = *reinterpret_cast<const uint4*>(VT + VP + r);
+                const bool same = l4.x == l4.y && l4.x == l4.z && l4.x == l4.w && c4.x == c4.y && c4.x == c4.z && c4.x == c4.w && r + 3 < live_rows;
+                if (!same) {
+#pragma unroll 1
+                    for (uint32_t j = 0; j < 4; ++j) vrow(cq, r + j);
+                    continue;
+                }
+                const float* sp = S + (size_t)(l4.x - ry0) * pcols + 4 * cq;
+                const float* wc = WV + r;
+                float2 a0[4], a1[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) a0[j] = a1[j] = make_float2(0.0f, 0.0f);
+                switch (c4.x) {
+                    case 1: ft_vtaps4<EXACT, 1, VP>(sp, pcols, wc, one, a0, a1); break;
+                    case 2: ft_vtaps4<EXACT, 2, VP>(sp, pcols, wc, one, a0, a1); break;
+                    case 3: ft_vtaps4<EXACT, 3, VP>(sp, pcols, wc, one, a0, a1); break;
+                    case 4: ft_vtaps4<EXACT, 4, VP>(sp, pcols, wc, one, a0, a1); break;
+                    case 5: ft_vtaps4<EXACT, 5, VP>(sp, pcols, wc, one, a0, a1); break;
+                    case 6: ft_vtaps4<EXACT, 6, VP>(sp, pcols, wc, one, a0, a1); break;
+                    case 7: ft_vtaps4<EXACT, 7, VP>(sp, pcols, wc, one, a0, a1); break;
+                    case 8: ft_vtaps4<EXACT, 8, VP>(sp, pcols, wc, one, a0, a1); break;
+                    default: break;
+                }
+                float4* t = reinterpret_cast<float4*>(Tm + (size_t)(4 * cq) * TP + r);      // column-major: four rows of a column are one float4
+                t[0] = make_float4(a0[0].x, a0[1].x, a0[2].x, a0[3].x);
+                t[TP / 4] = make_float4(a0[0].y, a0[1].y, a0[2].y, a0[3].y);
+                t[2 * (TP / 4)] = make_float4(a1[0].x, a1[1].x, a1[2].x, a1[3].x);
+                t[3 * (TP / 4)] = make_float4(a1[0].y, a1[1].y, a1[2].y, a1[3].y);
+                float m = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(fabsf(a0[j].x)));
+                    asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(fabsf(a0[j].y)));
+                    asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(fabsf(a1[j].x)));
+                    asm("max.NaN.f32 %0, %0, %1;" : "+f"(m) : "f"(fabsf(a1[j].y)));
+                }
+                if (!(m <= 3.402823466e+38f)) nonfinite[it] = 1u;
+            }
+        } else {   // a strip that starts off the four-row grid of the table: row by row
+            for (uint32_t i = tid; i < nquad * G; i += FT_THREADS) vrow(i / G, i % G);
         }
         // block-wide stores: the two tensor stores of the previous group must have READ the tile before it is overwritten
         if (!WARP_STORE && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");

@@ -10,7 +10,7 @@ ASAN=$(gcc -print-file-name=libasan.so)
 if [ "$1" = build ]; then
     python -c "import sys; sys.path.insert(0, 'kanter_core_b200'); import build; build.write_jit_prelude()"
     mkdir -p $OUT
-    for s in kc_context kc_kernels kc_fusion kc_h2n kc_resize kc_graph kc_exec kc_png kc_jit; do
+    for s in kc_context kc_kernels kc_fusion kc_h2n kc_resize kc_graph kc_exec kc_png kc_jit kc_numa; do
         nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O1 -g -std=c++17 --fmad=false \
             -Xcompiler -fPIC,-fsanitize=address,-fno-omit-frame-pointer -cudart static \
             -c kanter_core_b200/csrc/$s.cu -o $OUT/$s.o &
