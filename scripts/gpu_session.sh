@@ -31,7 +31,7 @@ full fused_cfg2_exact "kc_jit_entry" 1 exact config2_fused
 full resize_tma_lanczos3_fast kc_resize_tma 3 fast resize_lanczos3_1024_to_8192_plane
 full resize_tma_lanczos3_exact kc_resize_tma 3 exact resize_lanczos3_1024_to_8192_plane
 full resize_tma_rgba_node_fast kc_resize_tma 3 fast resize_lanczos3_1024_to_8192_rgba
-full resize_down_v kc_resize_v_march 2 fast resize_lanczos3_8192
+full resize_down_v "kc_resize_v_tma|kc_resize_v_march" 2 fast resize_lanczos3_8192
 full resize_down_h kc_resize_h_tile 2 fast resize_lanczos3_8192
 full h2n_fast kc_h2n_vec 3 fast height_to_normal
 full h2n_exact kc_h2n_vec 3 exact height_to_normal
