@@ -524,7 +524,7 @@ def ours(args, rank, world, local_rank):
         if workloads is not None:
             line["workloads"] = workloads
         if world == 1 and not args.no_cpu:
-            v, _ms, threads, sample = run_cpu(1, 0)
+            v, _ms, threads, sample = run_cpu(3, 1)      # one warm-up (first touch of 8 GB of planes), three timed steps
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
 
