@@ -763,6 +763,74 @@ struct KcPlan {
     uint64_t kernels = 0, groups = 0, bytes = 0, jit_generation = 0;
 };
 
+// The capture is a chain (every launch went to the one compute stream).  With the footprint of every launch at hand the
+// chain is replaced by the true dependencies -- a launch waits for the latest earlier launches that wrote what it reads, read
+// or wrote what it writes -- so independent branches of the graph (the resizes next to the stencil chain) run side by side.
+// Anything unexpected (a node that is not a kernel, a count that does not match the log) leaves the chain as it is.
+static void plan_parallelise(cudaGraph_t graph, const std::vector<KcFootprint>& log) {
+    static const bool trace = getenv("KC_TRACE_REPLAY") != nullptr;
+    size_t n = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n != log.size() || n < 3) {
+        if (trace) fprintf(stderr, "[kc replay] graph has %zu nodes, %zu launches were logged: the chain stays\n", n, log.size());
+        cudaGetLastError();
+        return;
+    }
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) { cudaGetLastError(); return; }
+    size_t ne = 0;
+    if (cudaGraphGetEdges(graph, nullptr, nullptr, &ne) != cudaSuccess || ne != n - 1) { cudaGetLastError(); return; }
+    std::vector<cudaGraphNode_t> from(ne), to(ne);
+    if (cudaGraphGetEdges(graph, from.data(), to.data(), &ne) != cudaSuccess) { cudaGetLastError(); return; }
+    for (cudaGraphNode_t nd : nodes) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nd, &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) { cudaGetLastError(); return; }
+    }
+    // launch order = the chain from its root
+    std::map<cudaGraphNode_t, cudaGraphNode_t> next;
+    std::set<cudaGraphNode_t> has_pred;
+    for (size_t i = 0; i < ne; ++i) {
+        if (next.count(from[i]) || has_pred.count(to[i])) return;     // not a chain
+        next[from[i]] = to[i];
+        has_pred.insert(to[i]);
+    }
+    cudaGraphNode_t cur = nullptr;
+    for (cudaGraphNode_t nd : nodes)
+        if (!has_pred.count(nd)) { if (cur) return; cur = nd; }
+    std::vector<cudaGraphNode_t> order;
+    while (cur) {
+        order.push_back(cur);
+        auto it = next.find(cur);
+        cur = it == next.end() ? nullptr : it->second;
+    }
+    if (order.size() != n) return;
+    auto overlap = [](const std::vector<KcSpan>& a, const std::vector<KcSpan>& b) {
+        for (const KcSpan& x : a)
+            for (const KcSpan& y : b)
+                if ((const char*)x.p < (const char*)y.p + y.n && (const char*)y.p < (const char*)x.p + x.n) return true;
+        return false;
+    };
+    std::vector<cudaGraphNode_t> nf, nt;
+    for (size_t i = 1; i < n; ++i)
+        for (size_t j = 0; j < i; ++j)
+            if (overlap(log[j].writes, log[i].reads) || overlap(log[j].writes, log[i].writes) || overlap(log[j].reads, log[i].writes)) {
+                nf.push_back(order[j]);
+                nt.push_back(order[i]);
+            }
+    if (trace) {
+        fprintf(stderr, "[kc replay] %zu kernels, chain of %zu edges -> %zu true dependencies:", n, ne, nf.size());
+        for (size_t i = 0; i < nf.size(); ++i) {
+            const size_t a = std::find(order.begin(), order.end(), nf[i]) - order.begin(), b = std::find(order.begin(), order.end(), nt[i]) - order.begin();
+            fprintf(stderr, " %zu->%zu", a, b);
+        }
+        fprintf(stderr, "\n");
+    }
+    if (cudaGraphRemoveDependencies(graph, from.data(), to.data(), ne) != cudaSuccess) { cudaGetLastError(); return; }
+    if (!nf.empty() && cudaGraphAddDependencies(graph, nf.data(), nt.data(), nf.size()) != cudaSuccess) {
+        cudaGetLastError();
+        cudaGraphAddDependencies(graph, from.data(), to.data(), ne);   // back to the chain
+    }
+}
+
 void kc_live_graph::drop_plan() {
     if (!plan) return;
     plan->snapshot.clear();
@@ -886,10 +954,13 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed);
     int32_t rc = KC_OK;
+    std::vector<KcFootprint> footprints;
     if (e == cudaSuccess) {
         ctx->arena_active = plan->arena;
         ctx->capturing = true;
+        ctx->capture_log = &footprints;
         rc = evaluate_impl(ids, n_ids, materialise);
+        ctx->capture_log = nullptr;
         ctx->capturing = false;
         ctx->arena_active = nullptr;
         e = cudaStreamEndCapture(ctx->stream, &graph);
@@ -902,6 +973,8 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
                 ok &= kind == KC_PLANE_DEVICE || kind == KC_PLANE_CONST;
             }
     }
+    static const bool chain_only = getenv("KC_REPLAY_CHAIN") != nullptr;    // A/B: keep the captured chain
+    if (ok && !chain_only) plan_parallelise(graph, footprints);
     if (ok) ok = cudaGraphInstantiate(&plan->exec, graph, 0) == cudaSuccess;
     if (graph) cudaGraphDestroy(graph);
     if (!ok) {

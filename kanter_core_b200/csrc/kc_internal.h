@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <initializer_list>
 #include <map>
 #include <set>
 #include <memory>
@@ -124,6 +125,11 @@ struct KcArena {
     bool orphaned = false;    // the plan is gone: the memory goes when `live` reaches 0
 };
 
+// What one kernel launch reads and writes, logged while an evaluation is captured for replay: the captured graph is a chain
+// (one stream), the log lets the plan replace the chain by the true dependencies so that independent branches run side by side.
+struct KcSpan { const void* p; size_t n; };
+struct KcFootprint { std::vector<KcSpan> reads, writes; };
+
 struct kc_context {
     // Planes and live graphs point back at their context.  Each of them, and the caller's own
     // handle, holds one count; kc_context_destroy releases the device side at once (`closed`)
@@ -187,6 +193,7 @@ struct kc_context {
     std::vector<size_t>* alloc_log = nullptr;
     KcArena* arena_active = nullptr;
     std::vector<KcArena*> arenas;
+    std::vector<KcFootprint>* capture_log = nullptr;   // one entry per kernel launch, in launch order (only while capturing)
     bool capturing = false;                    // ctx->stream is in CUDA stream capture: nothing but kernel launches may be enqueued
     unsigned int* d_halo_timeouts = nullptr;   // device counter of waits that gave up (this context's kernels only)
     bool halo_used = false;
@@ -225,6 +232,14 @@ struct KcExactScope {
     KcExactScope(const KcExactScope&) = delete;
     KcExactScope& operator=(const KcExactScope&) = delete;
 };
+
+inline void kc_log_launch(kc_context* ctx, std::initializer_list<KcSpan> reads, std::initializer_list<KcSpan> writes) {
+    if (!ctx->capture_log) return;
+    KcFootprint f;
+    for (const KcSpan& s : reads) if (s.p && s.n) f.reads.push_back(s);
+    for (const KcSpan& s : writes) if (s.p && s.n) f.writes.push_back(s);
+    ctx->capture_log->push_back(std::move(f));
+}
 
 // RAII device selection + context lock
 inline void kc_ctx_ref(kc_context* c) { c->handles.fetch_add(1, std::memory_order_relaxed); }

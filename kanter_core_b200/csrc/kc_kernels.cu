@@ -149,8 +149,11 @@ TvmConfig pick_config(int ns_max, int nt_max, unsigned long long n) {
     for (int pass = 0; pass < 2; ++pass) {  // pass 0 honours the tuning overrides, pass 1 ignores them
         for (const TvmConfig& c : order) {
             if (pass == 0 && ((force_v && c.v != force_v) || (force_ctas && c.ctas != force_ctas))) continue;
-            // do not use a tile (much) bigger than the plane
+            // do not use a tile (much) bigger than the plane -- nor tiles so big that a small plane is a handful of them:
+            // below ~150 tiles the launch is latency-bound and every SM that gets a tile shortens it (a 256^2 plane is
+            // 16 tiles of 4096 pixels but 64 of 1024; with glibc-exact pow in the tape that was 6 us of fp64 per block)
             if (c.v > 1 && n <= (unsigned long long)512 * c.v) continue;
+            if (pass == 0 && !force_v && c.v > 1 && (n + 1024ull * c.v - 1) / (1024ull * c.v) < 148ull) continue;
             const size_t budget = (size_t)(227 * 1024) / (size_t)c.ctas - 1024 - 128;
             const size_t tile_b = (size_t)4096 * c.v;
             for (int st = 4; st >= (force_stages == 1 ? 1 : 2); --st) {
@@ -175,6 +178,16 @@ extern "C" int32_t kc_debug_last_tile_config(int32_t* v, int32_t* ctas, int32_t*
 
 int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     if (args.n == 0 || args.n_seg == 0) return KC_OK;
+    if (ctx->capture_log) {   // what this launch touches (either kernel below is ONE launch)
+        KcFootprint f;
+        for (uint32_t q = 0; q < args.n_seg; ++q) {
+            const KcSegment& sg = args.seg[q];
+            for (uint32_t k = 0; k < sg.n_src; ++k) f.reads.push_back({sg.src[k], (size_t)args.n * 4});
+            for (int m = 0; m < KC_MAX_OUT; ++m) if (sg.out[m]) f.writes.push_back({sg.out[m], (size_t)args.n * 4});
+            if (sg.out_rgba8) f.writes.push_back({sg.out_rgba8, (size_t)args.n * 4});
+        }
+        ctx->capture_log->push_back(std::move(f));
+    }
     KcHostTimer hp(KC_HP_LAUNCH_TAPE);
     int ns_max = 0;
     for (uint32_t s = 0; s < args.n_seg; ++s) ns_max = std::max<int>(ns_max, (int)args.seg[s].n_src);

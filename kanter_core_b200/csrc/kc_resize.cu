@@ -1329,6 +1329,14 @@ int32_t kck_resize_planes_rows_batched(kc_context* ctx, const float* const* srcs
     const uint32_t ngroups = (nrows + G - 1) / G;
     const uint32_t lanes = std::max<uint32_t>(1u, std::min<uint32_t>(ngroups, (uint32_t)(ctx->sm_count * per_sm) / std::max(strips * (uint32_t)n, 1u)));
     dim3 grid(strips, std::min<uint32_t>(lanes, 65535u), (unsigned)n);
+    if (ctx->capture_log) {
+        KcFootprint f;
+        for (int i = 0; i < n; ++i) {
+            f.reads.push_back({srcs[i], (size_t)sw * sh * 4});
+            f.writes.push_back({dsts[i], (size_t)dw * nrows * 4});
+        }
+        ctx->capture_log->push_back(std::move(f));
+    }
     KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
     const float one = 1.0f;
     void* args[] = {(void*)&pm, (void*)&m_vt, (void*)&sh, (void*)&dw, (void*)&tv->d_left, (void*)&tv->max_taps,
@@ -1396,6 +1404,7 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
             const uint32_t lanes = std::max<uint32_t>(1u, std::min<uint32_t>(ngroups, (uint32_t)(ctx->sm_count * per_sm) / std::max(strips, 1u)));
             {
                 dim3 grid(strips, std::min<uint32_t>(lanes, 65535u));
+                kc_log_launch(ctx, {{src, (size_t)sw * sh * 4}}, {{dst, (size_t)dw * nrows * 4}});
                 KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
                 const float one = 1.0f;
                 void* args[] = {(void*)&src, (void*)&sw, (void*)&sh, (void*)&dst, (void*)&dw, (void*)&dh,
@@ -1427,6 +1436,7 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
     KC_TRY(kc_dev_alloc(ctx, tmp_bytes, (void**)&tmp));
     const bool exact = ctx->opts.math_mode == KC_MATH_EXACT;
     bool marched = false;
+    kc_log_launch(ctx, {{src, (size_t)sw * sh * 4}}, {{tmp, (size_t)sw * dh * 4}});      // the vertical pass below, whichever kernel runs it
     static const bool no_march = getenv("KC_RESIZE_NO_MARCH") != nullptr;
     if (!no_march && (sw & 3u) == 0 && tv->max_taps > (uint32_t)FS_MAXT) {
         KC_TRY(build_march_tables(ctx, *tv));
@@ -1444,7 +1454,7 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
             };
             // the TMA-fed march (default where its shape fits: widths that are multiples of four, a tensor-map encoder at hand)
             static const bool no_vtma = getenv("KC_RESIZE_NO_VTMA") != nullptr;
-            if (!no_vtma && !ctx->capturing && tensor_map_encoder() && (((uintptr_t)src | (uintptr_t)tmp) & 15u) == 0 && sw >= (uint32_t)VT_COLS / 2) {
+            if (!no_vtma && tensor_map_encoder() && (((uintptr_t)src | (uintptr_t)tmp) & 15u) == 0 && sw >= (uint32_t)VT_COLS / 2) {
                 CUtensorMap m_src;
                 // output rows per block: a whole wave of blocks at three per SM, never fewer than 16 rows
                 const uint32_t strips = (sw + VT_COLS - 1) / VT_COLS;
@@ -1485,6 +1495,7 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
         if (exact) kc_resize_v_kernel<true><<<grid, 256, 0, ctx->stream>>>(src, sw, tmp, dh, tv->d_left, tv->d_count, tv->d_weights);
         else kc_resize_v_kernel<false><<<grid, 256, 0, ctx->stream>>>(src, sw, tmp, dh, tv->d_left, tv->d_count, tv->d_weights);
     }
+    kc_log_launch(ctx, {{tmp, (size_t)sw * dh * 4}}, {{dst, (size_t)dw * dh * 4}});      // the horizontal pass
     const uint32_t hwin = max_window(*th, 256);
     const size_t hsmem = sizeof(float4) * ((size_t)hwin + (hwin >> 3) + 2);
     const uint32_t hgy = (dh + HT_ROWS - 1) / HT_ROWS;
