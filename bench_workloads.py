@@ -272,7 +272,7 @@ def wl_resize(env, steps, src=1024, dst=8192):
 # ---------------------------------------------------------------------------------------------
 # configs[4]: 64 x 32-node graphs at 4096^2, whole graphs split over the ranks
 # ---------------------------------------------------------------------------------------------
-def wl_graph_batch(env, n_graphs=64, size=4096, distinct=2):
+def wl_graph_batch(env, n_graphs=64, size=4096, distinct=2, replay=True):
     kc, tp = env.kc, env.tp
     from kanter_core_b200 import SlotId
     from tests import graphs
@@ -287,6 +287,7 @@ def wl_graph_batch(env, n_graphs=64, size=4096, distinct=2):
             inputs = graphs.config5_inputs(100 + env.rank * 1000 + d, S)
             lg = tp.new_live_graph()
             lg.set_node_graph(g)
+            lg.set_replay(replay)       # evaluation replay: the batch re-evaluates ONE graph structure on new inputs, the case it is for
             imgs = [kc.SlotImage.from_planes(tp, planes) for planes in inputs]
             for eid, img in enumerate(imgs):
                 lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, img), eid)
@@ -305,6 +306,7 @@ def wl_graph_batch(env, n_graphs=64, size=4096, distinct=2):
         run_share()
         kc.jit_wait()                              # hot tapes are specialised in the background: measure what serves them from then on
         run_share()
+        run_share()                                # (with replay: ordinary pass, capture, and from here on replays)
         tp.synchronize()
         return True
 
@@ -318,6 +320,7 @@ def wl_graph_batch(env, n_graphs=64, size=4096, distinct=2):
     mpix = S * S / 1e6
     out = {"workload": "configs[4]: %d x 32-node graphs (Separate/Mix/HeightToNormal/Resize/Combine + nested Graph) at %dx%d%s" % (n_graphs, S, S, "" if env.world == 1 else ", whole graphs split over %d ranks, no collective" % env.world),
            "scaling": "strong" if env.world > 1 else "single GPU", "math": "fast", "graphs": n_graphs, "graphs_per_gpu": len(mine),
+           "evaluation_replay": dict(lg0_stats := st["sets"][0][0].replay_stats(), on=replay),
            "ms_total": ms_all, "ms_per_graph_per_gpu": per_graph, "mpixel_per_s": n_graphs * mpix / (ms_all / 1e3),
            "kernels_per_graph": stats["kernels"], "fused_groups_per_graph": stats["fused_groups"],
            "algorithmic_bytes": stats["algorithmic_bytes"], "algorithmic_bytes_note": "per graph, as the library counted it: each distinct plane read once + each result written once per kernel",
