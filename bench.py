@@ -343,10 +343,16 @@ def ours(args, rank, world, local_rank):
         lg.read_rgba(out, SlotId(0), kc.Size(SIZE, SIZE), out=host_outs[i % 2], sync=False)
         call("kc_event_record_download", ctx, done[i % 2])
 
-    def run_e2e(n, stamps=None):
+    def run_e2e(n, stamps=None, overlap=True):
+        """overlap: step i is enqueued before the host waits for step i-1 (its upload runs under step i-1's download: full
+        duplex).  Not overlapped: step i-1's bytes are on the host before step i is enqueued (one direction at a time)."""
         for i in range(n):
+            if not overlap and i > 0:
+                call("kc_event_synchronize", done[(i - 1) % 2])
+                if stamps is not None:
+                    stamps.append(time.perf_counter())
             enqueue_e2e(i)
-            if i > 0:
+            if overlap and i > 0:
                 call("kc_event_synchronize", done[(i - 1) % 2])      # step i-1's bytes are on the host
                 if stamps is not None:
                     stamps.append(time.perf_counter())
@@ -358,12 +364,25 @@ def ours(args, rank, world, local_rank):
     run_e2e(3)
     kc.jit_wait()        # the fused RGBA8-export tape of this path, same as above
     run_e2e(2)
+    # Which schedule does THIS box favour?  One GPU's PCIe link is full duplex, and overlapping wins; eight ranks share one host
+    # fabric that moves less in total when both directions are busy (the `pcie` probe below: 241 GB/s host->device alone,
+    # 163 GB/s with both directions at 8 ranks), and there one direction at a time wins.  Measured, not assumed: four steps
+    # of each, max over ranks, the faster one is used for the timed region (every rank takes the same decision).
+    trial = {}
+    for name, ov in (("overlapped", True), ("one_direction_at_a_time", False)):
+        barrier()
+        tp.synchronize()
+        tt = time.perf_counter()
+        run_e2e(4, overlap=ov)
+        tp.synchronize()
+        trial[name] = max_over_ranks(time.perf_counter() - tt) / 4 * 1e3
+    e2e_overlap = trial["overlapped"] <= trial["one_direction_at_a_time"]
     barrier()
     tp.synchronize()
     stamps = []
     x0 = tp.transfer_stats()
     t0 = time.perf_counter()
-    run_e2e(e2e_steps, stamps)
+    run_e2e(e2e_steps, stamps, overlap=e2e_overlap)
     tp.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     x1 = tp.transfer_stats()
@@ -511,7 +530,9 @@ def ours(args, rank, world, local_rank):
                        "parity": parity},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "step_ms_min_median_max": [min(e2e_step_ms), float(np.median(e2e_step_ms)), max(e2e_step_ms)], "u8_inputs": e2e_u8, "path": "8 pinned host f32 planes per step -> deferred upload of the 6 planes the graph reads (upload stream) -> fused mul/pow/to_u8 kernel -> RGBA8 on pinned host (read_rgba, download stream); steps pipelined one deep; bytes as counted by the library"},
+                    "steps": e2e_steps, "step_ms_min_median_max": [min(e2e_step_ms), float(np.median(e2e_step_ms)), max(e2e_step_ms)],
+                    "schedule": "overlapped (step i enqueued before step i-1's bytes are awaited)" if e2e_overlap else "one direction at a time (step i-1's bytes on the host before step i is enqueued)",
+                    "schedule_trial_ms_per_step": {k: round(v, 3) for k, v in trial.items()}, "u8_inputs": e2e_u8, "path": "8 pinned host f32 planes per step -> deferred upload of the 6 planes the graph reads (upload stream) -> fused mul/pow/to_u8 kernel -> RGBA8 on pinned host (read_rgba, download stream); steps pipelined one deep unless the trial says otherwise (`schedule`); bytes as counted by the library"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "kernel": kernel_name,
