@@ -174,6 +174,8 @@ static void axis_table_free(KcAxisTable& t) {
     if (t.d_march_o) cudaFree(t.d_march_o);
     if (t.d_march_w2) cudaFree(t.d_march_w2);
     t.d_march_w2 = nullptr;
+    if (t.d_march_info) cudaFree(t.d_march_info);
+    t.d_march_info = nullptr;
     if (t.d_vtab) cudaFree(t.d_vtab);
     t.d_vtab = nullptr;
     t.d_march_w = nullptr;

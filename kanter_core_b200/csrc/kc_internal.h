@@ -73,6 +73,7 @@ struct KcAxisTable {
     float* d_march_w = nullptr;    // [src_len][8]
     float* d_march_w2 = nullptr;   // [src_len][8][2]: every weight twice (the TMA-fed march reads FFMA2 operand pairs)
     int32_t* d_march_o = nullptr;  // [src_len][8]
+    int32_t* d_march_info = nullptr;  // [src_len][12]: the eight output ids, a flag word (completing slots | tap slots << 8), padding
 };
 
 // ---- planes -------------------------------------------------------------------

@@ -1067,7 +1067,8 @@ constexpr int VT_R = 8;                       // source rows per stage
 constexpr int VT_STAGES = 4;
 constexpr int VT_COLS = 512;                  // source columns per block (128 compute threads x 4)
 constexpr int VT_PIX_BYTES = VT_R * VT_COLS * 4;
-constexpr int VT_STAGE_BYTES = VT_PIX_BYTES + VT_R * 64 + VT_R * 32;  // pixels + weights (each one twice: an FFMA2 operand pair) + retire ids
+constexpr int VT_INFO = 12;                   // ints per source row in the retire table: eight output ids, the flag word, padding
+constexpr int VT_STAGE_BYTES = VT_PIX_BYTES + VT_R * 64 + VT_R * VT_INFO * 4;  // pixels + weights (each one twice: an FFMA2 operand pair) + retire info
 
 __device__ __forceinline__ void vt_tma_load_2d_hint(void* dst, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint64_t* bar, uint64_t policy) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
@@ -1084,10 +1085,22 @@ __device__ __forceinline__ void vt_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ft_smem(bar)) : "memory");
 }
 
+// one source row into one open output: four columns as two FFMA2 operand pairs (EXACT: the product rounds on its own)
+template <bool EXACT>
+__device__ __forceinline__ void vt_tap(float2& alo, float2& ahi, const float2& vlo, const float2& vhi, const float2& ww, float one) {
+    if (EXACT) {
+        alo = __ffma2_rn(alo, make_float2(one, one), __fmul2_rn(vlo, ww));
+        ahi = __ffma2_rn(ahi, make_float2(one, one), __fmul2_rn(vhi, ww));
+    } else {
+        alo = __ffma2_rn(vlo, ww, alo);
+        ahi = __ffma2_rn(vhi, ww, ahi);
+    }
+}
+
 template <bool EXACT>
 __global__ void __launch_bounds__(160) kc_resize_v_tma_kernel(const __grid_constant__ CUtensorMap tm_src, uint32_t sw4, uint32_t sh, float4* __restrict__ tmp,
                                                               uint32_t dh, const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount,
-                                                              const float2* __restrict__ mw2, const int* __restrict__ mo, uint32_t rows_per_cta, float one) {
+                                                              const float2* __restrict__ mw2, const int* __restrict__ mi, uint32_t rows_per_cta, float one) {
     extern __shared__ __align__(128) unsigned char vts[];
     uint64_t* full = reinterpret_cast<uint64_t*>(vts);               // [VT_STAGES]
     uint64_t* empty = full + VT_STAGES;                              // [VT_STAGES]
@@ -1118,12 +1131,12 @@ __global__ void __launch_bounds__(160) kc_resize_v_tma_kernel(const __grid_const
                 unsigned char* S = stage0 + (size_t)st * VT_STAGE_BYTES;
                 const uint32_t row = r0 + k * VT_R;                  // rows past the image arrive as zeros and are never used
                 const uint32_t trows = min((uint32_t)VT_R, sh - row);                    // table rows that exist
-                ft_mbar_expect_tx(&full[st], VT_PIX_BYTES + trows * 64 + trows * 32);
+                ft_mbar_expect_tx(&full[st], VT_PIX_BYTES + trows * 64 + trows * VT_INFO * 4);
                 const uint64_t pol = k * VT_R < n_shared ? pol_keep : pol_stream;
                 vt_tma_load_2d_hint(S, &tm_src, cx0, row, &full[st], pol);
                 vt_tma_load_2d_hint(S + VT_R * 256 * 4, &tm_src, cx0 + 256, row, &full[st], pol);
                 vt_bulk_load_1d(S + VT_PIX_BYTES, mw2 + (size_t)row * VM_SLOTS, trows * 64, &full[st]);
-                vt_bulk_load_1d(S + VT_PIX_BYTES + VT_R * 64, mo + (size_t)row * VM_SLOTS, trows * 32, &full[st]);
+                vt_bulk_load_1d(S + VT_PIX_BYTES + VT_R * 64, mi + (size_t)row * VT_INFO, trows * VT_INFO * 4, &full[st]);
             }
         }
         return;
@@ -1143,45 +1156,53 @@ __global__ void __launch_bounds__(160) kc_resize_v_tma_kernel(const __grid_const
         const unsigned char* S = stage0 + (size_t)st * VT_STAGE_BYTES;
         const float4* px = reinterpret_cast<const float4*>(S + (size_t)half * VT_R * 256 * 4) + c4;
         const float4* wt = reinterpret_cast<const float4*>(S + VT_PIX_BYTES);               // per row: (w0,w0,w1,w1) (w2,w2,w3,w3) ...
-        const int4* ot = reinterpret_cast<const int4*>(S + VT_PIX_BYTES + VT_R * 64);
+        const int* ot = reinterpret_cast<const int*>(S + VT_PIX_BYTES + VT_R * 64);         // per row: eight output ids, flags
+        const uint32_t ucount = min((uint32_t)VT_R, nr - k * VT_R);
+        // the operands of a row are fetched one row ahead of their use, so the shared-memory latency sits behind the
+        // sixteen FFMA2 of the row before (rows past ucount are fetched from the stage too, and not used)
+        float4 v_n = px[0], w_n[VM_SLOTS / 2];
+        uint32_t flags_n = (uint32_t)ot[8];
+#pragma unroll
+        for (int q = 0; q < VM_SLOTS / 2; ++q) w_n[q] = wt[q];
 #pragma unroll
         for (int u = 0; u < VT_R; ++u) {
-            const uint32_t r = k * VT_R + u;                         // relative to r0
-            if (r >= nr) break;                                      // uniform
-            const float4 v = px[u * 64];
-            const float2 vlo = make_float2(v.x, v.y), vhi = make_float2(v.z, v.w);
+            if ((uint32_t)u >= ucount) break;                        // uniform
+            const float4 v = v_n;
+            const uint32_t flags = flags_n;                          // bits 0-7: slots completing on this row; 8-15: slots it is a tap of
+            float4 w[VM_SLOTS / 2];                                  // the weights of slots 2q and 2q+1, each already a pair
 #pragma unroll
-            for (int q = 0; q < VM_SLOTS / 2; ++q) {
-                const float4 wp = wt[4 * u + q];                     // the weights of slots 2q and 2q+1, each already a pair
-                if (wp.x == wp.x) {                                  // NaN: the row is in no window of that slot
-                    const float2 ww = make_float2(wp.x, wp.y);
-                    if (EXACT) {
-                        alo[2 * q] = __ffma2_rn(alo[2 * q], make_float2(one, one), __fmul2_rn(vlo, ww));
-                        ahi[2 * q] = __ffma2_rn(ahi[2 * q], make_float2(one, one), __fmul2_rn(vhi, ww));
-                    } else {
-                        alo[2 * q] = __ffma2_rn(vlo, ww, alo[2 * q]);
-                        ahi[2 * q] = __ffma2_rn(vhi, ww, ahi[2 * q]);
-                    }
+            for (int q = 0; q < VM_SLOTS / 2; ++q) w[q] = w_n[q];
+            if (u + 1 < VT_R) {
+                v_n = px[(u + 1) * 64];
+                flags_n = (uint32_t)ot[VT_INFO * (u + 1) + 8];
+#pragma unroll
+                for (int q = 0; q < VM_SLOTS / 2; ++q) w_n[q] = wt[4 * (u + 1) + q];
+            }
+            const float2 vlo = make_float2(v.x, v.y), vhi = make_float2(v.z, v.w);
+            // A slot the row is no tap of has weight 0 and a running sum of +0 (it was cleared when its last output left):
+            // +0 + 0*v stays +0 for every finite v, so the products need no test per slot.  A non-finite v would turn
+            // that +0 into NaN; those four columns take the tested path for the row.
+            const float2 chk = __ffma2_rn(vlo, make_float2(0.f, 0.f), __fmul2_rn(vhi, make_float2(0.f, 0.f)));
+            if (chk.x + chk.y == 0.f) {
+#pragma unroll
+                for (int q = 0; q < VM_SLOTS / 2; ++q) {
+                    vt_tap<EXACT>(alo[2 * q], ahi[2 * q], vlo, vhi, make_float2(w[q].x, w[q].y), one);
+                    vt_tap<EXACT>(alo[2 * q + 1], ahi[2 * q + 1], vlo, vhi, make_float2(w[q].z, w[q].w), one);
                 }
-                if (wp.z == wp.z) {
-                    const float2 ww = make_float2(wp.z, wp.w);
-                    if (EXACT) {
-                        alo[2 * q + 1] = __ffma2_rn(alo[2 * q + 1], make_float2(one, one), __fmul2_rn(vlo, ww));
-                        ahi[2 * q + 1] = __ffma2_rn(ahi[2 * q + 1], make_float2(one, one), __fmul2_rn(vhi, ww));
-                    } else {
-                        alo[2 * q + 1] = __ffma2_rn(vlo, ww, alo[2 * q + 1]);
-                        ahi[2 * q + 1] = __ffma2_rn(vhi, ww, ahi[2 * q + 1]);
-                    }
+            } else {
+#pragma unroll
+                for (int q = 0; q < VM_SLOTS / 2; ++q) {
+                    if (flags & (0x100u << (2 * q))) vt_tap<EXACT>(alo[2 * q], ahi[2 * q], vlo, vhi, make_float2(w[q].x, w[q].y), one);
+                    if (flags & (0x200u << (2 * q))) vt_tap<EXACT>(alo[2 * q + 1], ahi[2 * q + 1], vlo, vhi, make_float2(w[q].z, w[q].w), one);
                 }
             }
-            const int4 oa = ot[2 * u], ob = ot[2 * u + 1];
-            if ((oa.x & oa.y & oa.z & oa.w & ob.x & ob.y & ob.z & ob.w) < 0) continue;      // nothing completes on this row
-            const int o[VM_SLOTS] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+            if ((flags & 0xffu) == 0u) continue;                     // nothing completes on this row
 #pragma unroll
             for (int s = 0; s < VM_SLOTS; ++s)
-                if (o[s] >= 0) {
-                    if (live && (uint32_t)o[s] >= oyA && (uint32_t)o[s] < oyB)
-                        st_hint4(tmp + (size_t)o[s] * sw4 + x4, make_float4(alo[s].x, alo[s].y, ahi[s].x, ahi[s].y), pol_keep);
+                if (flags & (1u << s)) {
+                    const uint32_t o = (uint32_t)ot[VT_INFO * u + s];
+                    if (live && o >= oyA && o < oyB)
+                        st_hint4(tmp + (size_t)o * sw4 + x4, make_float4(alo[s].x, alo[s].y, ahi[s].x, ahi[s].y), pol_keep);
                     alo[s] = ahi[s] = make_float2(0.f, 0.f);
                 }
         }
@@ -1211,11 +1232,27 @@ int32_t build_march_tables(kc_context* ctx, KcAxisTable& t) {
         if (o[(size_t)(l + n - 1) * VM_SLOTS + s] >= 0) return KC_OK;
         o[(size_t)(l + n - 1) * VM_SLOTS + s] = (int32_t)oy;
     }
-    {   // the same weights with every entry doubled: an aligned (w, w) pair is what an FFMA2 takes as its broadcast operand
+    {   // the TMA-fed march's tables.  Weights: every entry doubled (an aligned (w, w) pair is what an FFMA2 takes as its
+        // broadcast operand) and 0 where the row is no tap of the slot.  Info: the eight output ids and a flag word per row
+        // (bits 0-7 the slots completing there, bits 8-15 the slots the row is a tap of).
         std::vector<float> w2(w.size() * 2);
-        for (size_t i = 0; i < w.size(); ++i) w2[2 * i] = w2[2 * i + 1] = w[i];
+        std::vector<int32_t> info((size_t)S * VT_INFO, 0);
+        for (size_t r = 0; r < S; ++r) {
+            uint32_t flags = 0;
+            for (int sl = 0; sl < VM_SLOTS; ++sl) {
+                const size_t i = r * VM_SLOTS + sl;
+                const bool tap = w[i] == w[i];
+                w2[2 * i] = w2[2 * i + 1] = tap ? w[i] : 0.0f;
+                if (tap) flags |= 0x100u << sl;
+                if (o[i] >= 0) flags |= 1u << sl;
+                info[r * VT_INFO + sl] = o[i];
+            }
+            info[r * VT_INFO + 8] = (int32_t)flags;
+        }
         KC_CUDA(cudaMalloc((void**)&t.d_march_w2, w2.size() * sizeof(float)));
+        KC_CUDA(cudaMalloc((void**)&t.d_march_info, info.size() * sizeof(int32_t)));
         KC_CUDA(cudaMemcpyAsync(t.d_march_w2, w2.data(), w2.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        KC_CUDA(cudaMemcpyAsync(t.d_march_info, info.data(), info.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
         KC_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     KC_CUDA(cudaMalloc((void**)&t.d_march_w, w.size() * sizeof(float)));
@@ -1470,7 +1507,7 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
                     float4* tmp4 = (float4*)tmp;
                     const float one = 1.0f;
                     void* args[] = {(void*)&m_src, (void*)&sw4, (void*)&sh, (void*)&tmp4, (void*)&dh, (void*)&tv->d_left, (void*)&tv->d_count,
-                                    (void*)&tv->d_march_w2, (void*)&tv->d_march_o, (void*)&rpc, (void*)&one};
+                                    (void*)&tv->d_march_w2, (void*)&tv->d_march_info, (void*)&rpc, (void*)&one};
                     KcTimed timed(ctx, KC_KERNEL_RESIZE_V);
                     KC_CUDA(cudaLaunchKernel(fn, dim3(strips, gy2), dim3(160), args, smem2, ctx->stream));
                     marched = true;

@@ -1,0 +1,77 @@
+// Probe: how fast can 148 SMs READ a 8192x8192 f32 plane, as a function of the access pattern?
+//   seq      : grid-stride float4 loads over the whole plane (the copy kernels' pattern)
+//   strips W : blocks own a W-column strip and a band of rows and walk down the band row by row,
+//              W/4 threads x 8 rows in flight (the vertical march's pattern)
+// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o probes/read_pattern probes/read_pattern.cu
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+__global__ void seq_kernel(const float4* __restrict__ p, size_t n4, float* out) {
+    float s = 0.f;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {
+        const float4 a = __ldcs(p + i), b = __ldcs(p + i + stride), c = __ldcs(p + i + 2 * stride), d = __ldcs(p + i + 3 * stride);
+        s += a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w + c.x + c.y + c.z + c.w + d.x + d.y + d.z + d.w;
+    }
+    for (; i < n4; i += stride) { const float4 a = __ldcs(p + i); s += a.x + a.y + a.z + a.w; }
+    if (s == 123.456f) *out = s;
+}
+
+template <int U>
+__global__ void strip_kernel(const float4* __restrict__ p, uint32_t w4, uint32_t h, uint32_t rows_per_band, float* out) {
+    const uint32_t x4 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r0 = blockIdx.y * rows_per_band, r1 = min(r0 + rows_per_band, h);
+    float s = 0.f;
+    if (x4 < w4) {
+        uint32_t r = r0;
+        for (; r + U <= r1; r += U) {
+            float4 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = __ldcs(p + (size_t)(r + u) * w4 + x4);
+#pragma unroll
+            for (int u = 0; u < U; ++u) s += v[u].x + v[u].y + v[u].z + v[u].w;
+        }
+        for (; r < r1; ++r) { const float4 a = __ldcs(p + (size_t)r * w4 + x4); s += a.x + a.y + a.z + a.w; }
+    }
+    if (s == 123.456f) *out = s;
+}
+
+int main() {
+    const uint32_t W = 8192, H = 8192;
+    const size_t n = (size_t)W * H;
+    float *d, *out, *flush;
+    cudaMalloc(&d, n * 4); cudaMalloc(&out, 4); cudaMalloc(&flush, 512u << 20);
+    cudaMemset(d, 0, n * 4);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    auto time = [&](const char* name, auto launch) {
+        float best = 1e9f, sum = 0.f; const int reps = 10;
+        for (int i = 0; i < reps + 2; ++i) {
+            cudaMemsetAsync(flush, i, 512u << 20);
+            cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+            float ms; cudaEventElapsedTime(&ms, e0, e1);
+            if (i >= 2) { best = ms < best ? ms : best; sum += ms; }
+        }
+        printf("%-28s mean %.4f ms  best %.4f ms  %.0f GB/s (mean)  %s\n", name, sum / reps, best, n * 4 / (sum / reps) * 1e-6, cudaGetErrorString(cudaGetLastError()));
+    };
+    time("seq 148x8 blocks x256", [&] { seq_kernel<<<148 * 8, 256>>>((const float4*)d, n / 4, out); });
+    time("seq 148x4 blocks x512", [&] { seq_kernel<<<148 * 4, 512>>>((const float4*)d, n / 4, out); });
+    for (uint32_t sw : {256u, 512u, 1024u, 2048u, 4096u, 8192u}) {
+        const uint32_t threads = sw / 4 > 256 ? 256 : sw / 4;
+        const uint32_t gx = W / 4 / threads;
+        for (uint32_t per_sm : {3u, 6u}) {
+            const uint32_t gy = (148 * per_sm * (128 / (threads < 128 ? threads : 128)) + gx - 1) / gx;
+            const uint32_t rows = (H + gy - 1) / gy;
+            char name[64]; snprintf(name, sizeof name, "strips %u thr=%u grid %ux%u", sw, threads, gx, (H + rows - 1) / rows);
+            time(name, [&] { strip_kernel<8><<<dim3(gx, (H + rows - 1) / rows), threads>>>((const float4*)d, W / 4, H, rows, out); });
+        }
+    }
+    // the march's exact shape: 128 threads, 16 strips x 27 bands, 8 rows in flight; and with 16
+    time("march shape 16x27 U8", [&] { strip_kernel<8><<<dim3(16, 27), 128>>>((const float4*)d, W / 4, H, 304, out); });
+    time("march shape 16x27 U16", [&] { strip_kernel<16><<<dim3(16, 27), 128>>>((const float4*)d, W / 4, H, 304, out); });
+    time("march shape 16x37 U16", [&] { strip_kernel<16><<<dim3(16, 37), 128>>>((const float4*)d, W / 4, H, 222, out); });
+    time("march shape 16x74 U16", [&] { strip_kernel<16><<<dim3(16, 74), 128>>>((const float4*)d, W / 4, H, 111, out); });
+    return 0;
+}

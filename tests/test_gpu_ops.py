@@ -329,6 +329,34 @@ def test_resize_downsample_exact(tex_pro, filt, src, dst):
     assert bits_equal(got, oracle.resize_plane(p, dw, dh, int(filt)))
 
 
+@pytest.mark.parametrize("mode", ["exact", "fast"])
+@pytest.mark.parametrize("filt", [ResizeFilter.Triangle, ResizeFilter.Gaussian, ResizeFilter.Lanczos3])
+def test_resize_downsample_signed_zeros_and_non_finite_rows(tex_pro, tex_pro_fast, mode, filt):
+    """The marching vertical pass multiplies rows that are no tap of an open output by a weight of 0 instead of skipping
+    them: that must leave no trace -- bands of -0.0, of negative denormals and of values whose products underflow, and
+    whole rows of inf / NaN just outside a window, come out exactly as the oracle's per-window sums (EXACT: bit for bit
+    including the sign of zero and the NaN positions; FAST: same NaN positions, values within tolerance)."""
+    tp = tex_pro if mode == "exact" else tex_pro_fast
+    sw, sh, dw, dh = 512, 1024, 64, 96
+    p = rnd(23, sh, sw, -0.25, 1.25)
+    p[0:200] = -0.0
+    p[200:330, ::2] = np.float32(-1e-44)
+    p[200:330, 1::2] = np.float32(1e-30)
+    p[400] = np.inf                         # whole rows: every column of the block takes the tested path there
+    p[401] = -np.inf
+    p[640, 100:300] = np.nan
+    p[900:, 17] = np.nan
+    img = kc.SlotImage.from_planes(tp, [p])
+    got = _resize_direct(tp, img, dw, dh, filt).planes()[0]
+    want = oracle.resize_plane(p, dw, dh, int(filt))
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    if mode == "exact":
+        assert bits_equal(got, want)
+    else:
+        ok = ~np.isnan(want)
+        assert close(got[ok], want[ok])
+
+
 @pytest.mark.parametrize("filt", [ResizeFilter.Triangle, ResizeFilter.Lanczos3])
 def test_resize_rgba_planes_in_one_launch(tex_pro, filt):
     """An RGBA image whose planes all need pixels goes through ONE launch of the tensor-map kernel (grid.z = plane): every
