@@ -170,6 +170,10 @@ static void axis_table_free(KcAxisTable& t) {
     if (t.d_left) cudaFree(t.d_left);
     if (t.d_count) cudaFree(t.d_count);
     if (t.d_weights) cudaFree(t.d_weights);
+    for (float*& p : t.d_weights_eo) {
+        if (p) cudaFree(p);
+        p = nullptr;
+    }
     if (t.d_march_w) cudaFree(t.d_march_w);
     if (t.d_march_o) cudaFree(t.d_march_o);
     if (t.d_march_w2) cudaFree(t.d_march_w2);

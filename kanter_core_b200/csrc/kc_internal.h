@@ -61,6 +61,7 @@ struct KcAxisTable {
     uint32_t* d_left = nullptr;
     uint32_t* d_count = nullptr;
     float* d_weights = nullptr;
+    float* d_weights_eo[3] = {nullptr, nullptr, nullptr};   // block-wise copies for the long-window horizontal pass (256 / 128 / 64 outputs per block), built on first use
     // the same three arrays as ONE 2-D table of 32-bit words, [2 + max_taps][dst_len]: row 0 = left, row 1 = count,
     // rows 2.. = the weights tap by tap -- the TMA resize kernel fetches a group's slice of it with one tensor load
     uint32_t* d_vtab = nullptr;

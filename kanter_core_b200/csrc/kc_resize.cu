@@ -181,6 +181,14 @@ __device__ __forceinline__ float tap(float acc, float s, float w) {
     return EXACT ? __fadd_rn(acc, __fmul_rn(s, w)) : fmaf(s, w, acc);
 }
 
+// the same for two sums at once (one FFMA2).  EXACT: the product and the sum round separately, as in the reference -- the
+// sum as acc * one + product with `one` a kernel argument: ptxas contracts __fadd2_rn(acc, __fmul2_rn(s, w)) into one FFMA2
+// (seen as 1-ulp differences against the oracle), which it cannot do when the multiplier is not a compile-time 1
+template <bool EXACT>
+__device__ __forceinline__ float2 tap2(float2 acc, float2 s, float2 w, float one) {
+    return EXACT ? __ffma2_rn(acc, make_float2(one, one), __fmul2_rn(s, w)) : __ffma2_rn(s, w, acc);
+}
+
 // vertical_sample: tmp[oy][x] = sum_i src[left[oy]+i][x] * wv[i][oy]   (no clamp)
 // One thread per (x, oy); consecutive threads walk x, so every tap row is a
 // coalesced read and the store is coalesced.
@@ -916,56 +924,154 @@ __device__ __forceinline__ void st_hint4(float4* a, const float4& v, uint64_t po
 }
 
 constexpr int HT_ROWS = 4;
-__device__ __forceinline__ uint32_t ht_slot(uint32_t i) { return i + (i >> 3); }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(256) kc_resize_h_tile_kernel(const float* __restrict__ tmp, uint32_t sw, float* __restrict__ dst, uint32_t dw,
-                                                               uint32_t dh, const uint32_t* __restrict__ left, const uint32_t* __restrict__ count,
-                                                               const float* __restrict__ wh, float clo, float chi) {
-    extern __shared__ __align__(16) float4 htile4[];               // [ht_slot(ncol)] x (4 rows)
-    const uint32_t ox0 = blockIdx.x * 256, oxl = min(ox0 + 256, dw) - 1;
-    const uint32_t y0 = blockIdx.y * HT_ROWS, nrow = min((uint32_t)HT_ROWS, dh - y0);
-    const uint32_t c0 = __ldg(left + ox0), ncol = __ldg(left + oxl) + __ldg(count + oxl) - c0;
+__device__ __forceinline__ void vt_bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ft_smem(dst)), "l"(src), "r"(bytes),
+                 "r"(ft_smem(bar))
+                 : "memory");
+}
+
+// T threads, 2 T output columns per block: a thread owns two ADJACENT outputs.  Their windows overlap (by five sixths at a
+// ratio of 8 with Lanczos3), and a tap value fetched from shared memory once serves both; the block's tap weights arrive in
+// shared memory by one bulk copy (the host lays them out block by block) and the tile is staged with float4 loads.  Each
+// output still sums its own taps left to right.  Measured, 8192 -> 1024 columns x 1024 rows (round 2): 0.019-0.021 ms for
+// every block shape tried, against 0.023 ms for one output per thread with weights from L2 -- the remainder is the read of
+// the intermediate, which ncu shows coming from DRAM (42 MB read, L2 hit rate 19 %) although the march stores it
+// evict-last; neither the load hint nor the shape of the blocks changes that.
+__device__ __forceinline__ uint32_t ht_slot2(uint32_t i) { return i + (i >> 4); }   // lanes 2 x ratio columns apart: 17 float4 at a ratio of 8
+
+template <bool EXACT, int T>
+__global__ void __launch_bounds__(T * 4) kc_resize_h_tile_kernel(const float* __restrict__ tmp, uint32_t sw, float* __restrict__ dst, uint32_t dw,
+                                                             uint32_t dh, const uint32_t* __restrict__ left, const uint32_t* __restrict__ count,
+                                                             const float* __restrict__ weo, uint32_t max_taps, uint32_t tile_f4, float clo, float chi,
+                                                             float one) {
+    // shared memory: the block's tap weights [max_taps][T even outputs | T odd outputs] (one bulk copy: the host lays the
+    // table out block by block), then the tile [ht_slot2(ncol)] x (4 rows)
+    extern __shared__ __align__(128) unsigned char hts[];
+    uint64_t* wbar = reinterpret_cast<uint64_t*>(hts);
+    float* ws = reinterpret_cast<float*>(hts + 16);
+    const uint32_t wbytes = max_taps * (2 * T) * (uint32_t)sizeof(float);
+    // blockDim.y groups of four rows share the weights (what limits the resident warps is shared memory); a tile each
+    float4* htile4 = reinterpret_cast<float4*>(hts + 16 + wbytes) + (size_t)threadIdx.y * tile_f4;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        ft_mbar_init(wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ft_mbar_expect_tx(wbar, wbytes);
+        vt_bulk_load_1d(ws, weo + (size_t)blockIdx.x * max_taps * (2 * T), wbytes, wbar);
+    }
+    const uint32_t ox0 = blockIdx.x * (2 * T), oxl = min(ox0 + 2 * T, dw) - 1;
+    const uint32_t grp = blockIdx.y * blockDim.y + threadIdx.y;
+    const bool live = grp * HT_ROWS < dh;                           // a group past the last row stages row 0 and stores nothing
+    const uint32_t y0 = live ? grp * HT_ROWS : 0u, nrow = live ? min((uint32_t)HT_ROWS, dh - y0) : 1u;
+    // the block's window starts at a multiple of four columns where rows are 16-byte aligned: the staging then moves float4s
+    const bool vec = (sw & 3u) == 0 && (reinterpret_cast<uintptr_t>(tmp) & 15u) == 0;
+    const uint32_t c0 = vec ? __ldg(left + ox0) & ~3u : __ldg(left + ox0), ncol = __ldg(left + oxl) + __ldg(count + oxl) - c0;
     const float* r0 = tmp + (size_t)y0 * sw + c0;
     const float* r1 = tmp + (size_t)(y0 + min(1u, nrow - 1)) * sw + c0;   // rows past nrow: duplicates, never stored
     const float* r2 = tmp + (size_t)(y0 + min(2u, nrow - 1)) * sw + c0;
     const float* r3 = tmp + (size_t)(y0 + min(3u, nrow - 1)) * sw + c0;
-    // staging: eight loads per thread in flight together (two columns x four rows).  The intermediate sits in L2 (the vertical
-    // march wrote it evict-last); this is its last use, so the reads demote it again (evict-first)
+    // staging.  The intermediate sits in L2 (the vertical march wrote it evict-last); this is its last use, so the reads demote
+    // it again (evict-first).  The pass is bound by the latency of these loads: four columns x four rows per load group, two
+    // groups in flight per thread
     const uint64_t pol = l2_policy_evict_first();
-    for (uint32_t i0 = threadIdx.x; i0 < ncol; i0 += 512) {
-        const uint32_t ia = i0, ib = min(i0 + 256u, ncol - 1);
-        const float4 va = make_float4(ld_nc_hint(r0 + ia, pol), ld_nc_hint(r1 + ia, pol), ld_nc_hint(r2 + ia, pol), ld_nc_hint(r3 + ia, pol));
-        const float4 vb = make_float4(ld_nc_hint(r0 + ib, pol), ld_nc_hint(r1 + ib, pol), ld_nc_hint(r2 + ib, pol), ld_nc_hint(r3 + ib, pol));
-        htile4[ht_slot(ia)] = va;
-        if (i0 + 256u < ncol) htile4[ht_slot(i0 + 256u)] = vb;
-    }
-    __syncthreads();
-    const uint32_t ox = ox0 + threadIdx.x;
-    if (ox > oxl) return;
-    const uint32_t l = __ldg(left + ox) - c0, n = __ldg(count + ox);
-    float4 acc = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    const float* wp = wh + ox;
-    constexpr int WB = 8;                                          // tap weights fetched WB at a time
-    for (uint32_t j0 = 0; j0 < n; j0 += WB) {
-        float w[WB];
-#pragma unroll
-        for (int k = 0; k < WB; ++k) w[k] = __ldg(wp + (size_t)min(j0 + k, n - 1) * dw);
-#pragma unroll
-        for (int k = 0; k < WB; ++k) {
-            if (j0 + k < n) {
-                const float4 sv = htile4[ht_slot(l + j0 + k)];
-                acc.x = tap<EXACT>(acc.x, sv.x, w[k]);
-                acc.y = tap<EXACT>(acc.y, sv.y, w[k]);
-                acc.z = tap<EXACT>(acc.z, sv.z, w[k]);
-                acc.w = tap<EXACT>(acc.w, sv.w, w[k]);
+    if (vec) {
+        const uint32_t ncol4 = (ncol + 3u) >> 2;                   // sw % 4 == 0: the last float4 ends inside the row
+        const float4 *q0 = reinterpret_cast<const float4*>(r0), *q1 = reinterpret_cast<const float4*>(r1), *q2 = reinterpret_cast<const float4*>(r2),
+                     *q3 = reinterpret_cast<const float4*>(r3);
+        for (uint32_t i0 = threadIdx.x; i0 < ncol4; i0 += 2 * T) {
+            const uint32_t ia = i0, ib = min(i0 + (uint32_t)T, ncol4 - 1);
+            const float4 a0 = ld_nc_hint4(q0 + ia, pol), a1 = ld_nc_hint4(q1 + ia, pol), a2 = ld_nc_hint4(q2 + ia, pol), a3 = ld_nc_hint4(q3 + ia, pol);
+            const float4 b0 = ld_nc_hint4(q0 + ib, pol), b1 = ld_nc_hint4(q1 + ib, pol), b2 = ld_nc_hint4(q2 + ib, pol), b3 = ld_nc_hint4(q3 + ib, pol);
+            htile4[ht_slot2(4 * ia + 0)] = make_float4(a0.x, a1.x, a2.x, a3.x);
+            htile4[ht_slot2(4 * ia + 1)] = make_float4(a0.y, a1.y, a2.y, a3.y);
+            htile4[ht_slot2(4 * ia + 2)] = make_float4(a0.z, a1.z, a2.z, a3.z);
+            htile4[ht_slot2(4 * ia + 3)] = make_float4(a0.w, a1.w, a2.w, a3.w);
+            if (i0 + (uint32_t)T < ncol4) {
+                htile4[ht_slot2(4 * ib + 0)] = make_float4(b0.x, b1.x, b2.x, b3.x);
+                htile4[ht_slot2(4 * ib + 1)] = make_float4(b0.y, b1.y, b2.y, b3.y);
+                htile4[ht_slot2(4 * ib + 2)] = make_float4(b0.z, b1.z, b2.z, b3.z);
+                htile4[ht_slot2(4 * ib + 3)] = make_float4(b0.w, b1.w, b2.w, b3.w);
             }
         }
+    } else {
+        for (uint32_t i0 = threadIdx.x; i0 < ncol; i0 += 2 * T) {
+            const uint32_t ia = i0, ib = min(i0 + (uint32_t)T, ncol - 1);
+            const float4 va = make_float4(ld_nc_hint(r0 + ia, pol), ld_nc_hint(r1 + ia, pol), ld_nc_hint(r2 + ia, pol), ld_nc_hint(r3 + ia, pol));
+            const float4 vb = make_float4(ld_nc_hint(r0 + ib, pol), ld_nc_hint(r1 + ib, pol), ld_nc_hint(r2 + ib, pol), ld_nc_hint(r3 + ib, pol));
+            htile4[ht_slot2(ia)] = va;
+            if (i0 + (uint32_t)T < ncol) htile4[ht_slot2(i0 + (uint32_t)T)] = vb;
+        }
     }
-    const float a[HT_ROWS] = {acc.x, acc.y, acc.z, acc.w};
+    __syncthreads();
+    ft_mbar_wait(wbar, 0);
+    const uint32_t xa = ox0 + 2 * threadIdx.x, xb = xa + 1;
+    if (xa > oxl || !live) return;
+    const bool hb = xb <= oxl;
+    // windows [ca, ea) and [cb, eb) in tile columns; the four rows of an output as two FFMA2 operand pairs, the weight table
+    // holding every weight as a (w, w) pair
+    uint32_t ca = __ldg(left + xa) - c0, cb = hb ? __ldg(left + xb) - c0 : 0u;
+    const uint32_t ea = ca + __ldg(count + xa), eb = hb ? cb + __ldg(count + xb) : 0u;
+    const float* wa = ws + threadIdx.x;                            // next weight of a: wa[0], then wa += 2 T
+    const float* wb = ws + T + threadIdx.x;
+    constexpr int WS = 2 * T;
+    float2 a01 = make_float2(0.0f, 0.0f), a23 = a01, b01 = a01, b23 = a01;
+    // taps of a alone, left of b's window
+    for (const uint32_t e = min(ea, hb ? cb : ea); ca < e; ++ca, wa += WS) {
+        const float w = wa[0];
+        const float4 sv = htile4[ht_slot2(ca)];
+        a01 = tap2<EXACT>(a01, make_float2(sv.x, sv.y), make_float2(w, w), one);
+        a23 = tap2<EXACT>(a23, make_float2(sv.z, sv.w), make_float2(w, w), one);
+    }
+    // the columns both windows hold: one fetch, four FFMA2
+    if (hb && ca == cb) {
+        const uint32_t e = min(ea, eb);
+        constexpr int WB = 4;
+        for (; ca + WB <= e; ca += WB, wa += WB * WS, wb += WB * WS) {
+#pragma unroll
+            for (int k = 0; k < WB; ++k) {
+                const float u = wa[k * WS], v = wb[k * WS];
+                const float4 sv = htile4[ht_slot2(ca + k)];
+                const float2 lo = make_float2(sv.x, sv.y), hi = make_float2(sv.z, sv.w);
+                a01 = tap2<EXACT>(a01, lo, make_float2(u, u), one);
+                a23 = tap2<EXACT>(a23, hi, make_float2(u, u), one);
+                b01 = tap2<EXACT>(b01, lo, make_float2(v, v), one);
+                b23 = tap2<EXACT>(b23, hi, make_float2(v, v), one);
+            }
+        }
+        for (; ca < e; ++ca, wa += WS, wb += WS) {
+            const float u = wa[0], v = wb[0];
+            const float4 sv = htile4[ht_slot2(ca)];
+            const float2 lo = make_float2(sv.x, sv.y), hi = make_float2(sv.z, sv.w);
+            a01 = tap2<EXACT>(a01, lo, make_float2(u, u), one);
+            a23 = tap2<EXACT>(a23, hi, make_float2(u, u), one);
+            b01 = tap2<EXACT>(b01, lo, make_float2(v, v), one);
+            b23 = tap2<EXACT>(b23, hi, make_float2(v, v), one);
+        }
+        cb = ca;
+    }
+    // what is left of either window
+    for (; ca < ea; ++ca, wa += WS) {
+        const float w = wa[0];
+        const float4 sv = htile4[ht_slot2(ca)];
+        a01 = tap2<EXACT>(a01, make_float2(sv.x, sv.y), make_float2(w, w), one);
+        a23 = tap2<EXACT>(a23, make_float2(sv.z, sv.w), make_float2(w, w), one);
+    }
+    for (; cb < eb; ++cb, wb += WS) {
+        const float w = wb[0];
+        const float4 sv = htile4[ht_slot2(cb)];
+        b01 = tap2<EXACT>(b01, make_float2(sv.x, sv.y), make_float2(w, w), one);
+        b23 = tap2<EXACT>(b23, make_float2(sv.z, sv.w), make_float2(w, w), one);
+    }
+    const float a[HT_ROWS] = {a01.x, a01.y, a23.x, a23.y}, b[HT_ROWS] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
     for (int r = 0; r < HT_ROWS; ++r)
-        if ((uint32_t)r < nrow) dst[(size_t)(y0 + r) * dw + ox] = a[r] < clo ? clo : (a[r] > chi ? chi : a[r]);   // image::math::utils::clamp keeps NaN
+        if ((uint32_t)r < nrow) {
+            float* o = dst + (size_t)(y0 + r) * dw + xa;
+            const float va = a[r] < clo ? clo : (a[r] > chi ? chi : a[r]);   // image::math::utils::clamp keeps NaN
+            const float vb = b[r] < clo ? clo : (b[r] > chi ? chi : b[r]);
+            o[0] = va;
+            if (hb) o[1] = vb;
+        }
 }
 
 // ---------------------------------------------------------------------------
@@ -1074,11 +1180,6 @@ __device__ __forceinline__ void vt_tma_load_2d_hint(void* dst, const CUtensorMap
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
                      ft_smem(dst)),
                  "l"(map), "r"(c0), "r"(c1), "r"(ft_smem(bar)), "l"(policy)
-                 : "memory");
-}
-__device__ __forceinline__ void vt_bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ft_smem(dst)), "l"(src), "r"(bytes),
-                 "r"(ft_smem(bar))
                  : "memory");
 }
 __device__ __forceinline__ void vt_mbar_arrive(uint64_t* bar) {
@@ -1209,6 +1310,25 @@ __global__ void __launch_bounds__(160) kc_resize_v_tma_kernel(const __grid_const
         __syncwarp();
         if (lane == 0) vt_mbar_arrive(&empty[st]);                   // this warp is done with the stage
     }
+}
+
+// host: the weights of an axis as the long-window horizontal pass wants them: block by block of `t2` outputs, tap-major inside
+// a block, the even outputs of the block before the odd ones -- [block][tap][t2/2 even | t2/2 odd]; one bulk copy per block
+int32_t build_block_weights(kc_context* ctx, KcAxisTable& t, uint32_t t2, const float** out) {
+    const int slot = t2 == 256 ? 0 : t2 == 128 ? 1 : 2;
+    if (t.d_weights_eo[slot]) { *out = t.d_weights_eo[slot]; return KC_OK; }
+    if (ctx->capturing) KC_FAIL(KC_ERR_GENERIC, "a weight table would have to be uploaded during a stream capture");
+    const uint32_t nblk = (t.dst_len + t2 - 1) / t2, half = t2 / 2;
+    std::vector<float> w((size_t)nblk * t.max_taps * t2, 0.0f);
+    for (uint32_t o = 0; o < t.dst_len; ++o) {
+        const uint32_t b = o / t2, i = o % t2, pos = (i & 1u) * half + (i >> 1);
+        for (uint32_t k = 0; k < t.max_taps; ++k) w[((size_t)b * t.max_taps + k) * t2 + pos] = t.h_weights[(size_t)o * t.max_taps + k];
+    }
+    KC_CUDA(cudaMalloc((void**)&t.d_weights_eo[slot], w.size() * sizeof(float)));
+    KC_CUDA(cudaMemcpyAsync(t.d_weights_eo[slot], w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    KC_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = t.d_weights_eo[slot];
+    return KC_OK;
 }
 
 // host: the marching tables of an axis; false when some source index sits in more than one
@@ -1533,15 +1653,45 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
         else kc_resize_v_kernel<false><<<grid, 256, 0, ctx->stream>>>(src, sw, tmp, dh, tv->d_left, tv->d_count, tv->d_weights);
     }
     kc_log_launch(ctx, {{tmp, (size_t)sw * dh * 4}}, {{dst, (size_t)dw * dh * 4}});      // the horizontal pass
-    const uint32_t hwin = max_window(*th, 256);
-    const size_t hsmem = sizeof(float4) * ((size_t)hwin + (hwin >> 3) + 2);
-    const uint32_t hgy = (dh + HT_ROWS - 1) / HT_ROWS;
-    if (!no_march && th->max_taps > (uint32_t)FS_MAXT && hsmem <= 96 * 1024 && hgy <= 65535u) {
-        KC_TRY(kc_ensure_smem_attr(ctx, exact ? (const void*)kc_resize_h_tile_kernel<true> : (const void*)kc_resize_h_tile_kernel<false>, 96 * 1024));
-        dim3 grid((dw + 255) / 256, hgy);
+    // outputs per block (two per thread) and groups of four rows per block (they share the block's copy of the weights; what
+    // limits the resident warps is shared memory): the pair with the fewest rounds over the resident slots, weighted by the
+    // columns a round stages
+    static const int env_ht = getenv("KC_RESIZE_HT") ? atoi(getenv("KC_RESIZE_HT")) : 0;
+    static const int env_hrw = getenv("KC_RESIZE_HRW") ? atoi(getenv("KC_RESIZE_HRW")) : 0;
+    const uint32_t hgroups = (dh + HT_ROWS - 1) / HT_ROWS;
+    uint32_t ht = 0, hrw = 0, htile_f4 = 0;
+    size_t hsmem = 0;
+    {
+        double best = 1e300;
+        for (uint32_t t : {256u, 128u, 64u})
+            for (uint32_t rw : {4u, 2u, 1u}) {
+                if ((env_ht > 0 && (uint32_t)env_ht != t) || (env_hrw > 0 && (uint32_t)env_hrw != rw)) continue;
+                const uint32_t win = max_window(*th, t) + 8;                   // the staging may start up to 3 columns early and end up to 3 late
+                const uint32_t tile = win + (win >> 4) + 2;
+                const size_t sm = 16 + sizeof(float) * (size_t)th->max_taps * t + sizeof(float4) * (size_t)tile * rw;
+                if (sm > 96 * 1024 || (t / 2) * rw > 512) continue;
+                const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)2048 / ((t / 2) * rw), 32u, (uint64_t)(227 * 1024) / (sm + 1024)}));
+                const uint64_t blocks = (uint64_t)((dw + t - 1) / t) * ((hgroups + rw - 1) / rw), slots = per_sm * (uint64_t)ctx->sm_count;
+                const uint64_t rounds = (blocks + slots - 1) / slots;
+                // a round lasts about as long as one warp's work (latency-bound), shorter the more warps share an SM
+                const double cost = (double)rounds * (win + 64) / std::sqrt((double)per_sm * (t / 64) * rw);
+                if (cost < best) { best = cost; ht = t; hrw = rw; hsmem = sm; htile_f4 = tile; }
+            }
+    }
+    const uint32_t hgy = hrw ? (hgroups + hrw - 1) / hrw : 0;
+    if (!no_march && th->max_taps > (uint32_t)FS_MAXT && ht != 0 && hgy <= 65535u) {
+        const void* fn = ht == 256 ? (exact ? (const void*)kc_resize_h_tile_kernel<true, 128> : (const void*)kc_resize_h_tile_kernel<false, 128>)
+                       : ht == 128 ? (exact ? (const void*)kc_resize_h_tile_kernel<true, 64> : (const void*)kc_resize_h_tile_kernel<false, 64>)
+                                   : (exact ? (const void*)kc_resize_h_tile_kernel<true, 32> : (const void*)kc_resize_h_tile_kernel<false, 32>);
+        KC_TRY(kc_ensure_smem_attr(ctx, fn, 96 * 1024));
+        const float* weo = nullptr;
+        KC_TRY(build_block_weights(ctx, *th, ht, &weo));
+        const float* tmp_c = tmp;
+        const float one = 1.0f;
+        void* args[] = {(void*)&tmp_c, (void*)&sw, (void*)&dst, (void*)&dw, (void*)&dh, (void*)&th->d_left, (void*)&th->d_count, (void*)&weo,
+                        (void*)&th->max_taps, (void*)&htile_f4, (void*)&clo, (void*)&chi, (void*)&one};
         KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
-        if (exact) kc_resize_h_tile_kernel<true><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, clo, chi);
-        else kc_resize_h_tile_kernel<false><<<grid, 256, hsmem, ctx->stream>>>(tmp, sw, dst, dw, dh, th->d_left, th->d_count, th->d_weights, clo, chi);
+        KC_CUDA(cudaLaunchKernel(fn, dim3((dw + ht - 1) / ht, hgy), dim3(ht / 2, hrw), args, hsmem, ctx->stream));
     } else {
         dim3 grid((dw + 255) / 256, std::min<uint32_t>(dh, 65535u));
         KcTimed timed(ctx, KC_KERNEL_RESIZE_H);
