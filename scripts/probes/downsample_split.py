@@ -1,16 +1,32 @@
-import ctypes as C, sys, numpy as np
-sys.path.insert(0,'/root/repo')
+"""Per-kernel device time of the long-window resize 8192^2 -> 1024^2 (events around every launch)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import kanter_core_b200 as kc
-from kanter_core_b200 import ResizeFilter
-from kanter_core_b200._lib import call, kc_image
-tp=kc.TextureProcessor.new(math_mode=kc.MATH_FAST); ctx=tp._ctx._h
-big=kc.SlotImage.from_planes(tp,[np.random.default_rng(6).random((8192,8192),dtype=np.float32)])
-def down():
-    o=kc_image(); call("kc_resize",ctx,C.byref(big._im),1024,1024,int(ResizeFilter.Lanczos3),C.byref(o)); kc.SlotImage(tp._ctx,o)
-for _ in range(3): down()
+from kanter_core_b200._lib import call
+from kanter_core_b200.api import ResizeFilter, Size
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "fast"
+from kanter_core_b200 import _lib
+tp = kc.TextureProcessor(math_mode=_lib.MATH_FAST if mode == "fast" else _lib.MATH_EXACT)
+rng = np.random.default_rng(1)
+img = kc.SlotImage.from_planes(tp, [rng.random((8192, 8192), dtype=np.float32)])
+flush = kc.SlotImage.from_planes(tp, [np.zeros((8192, 8192), np.float32)])
+for _ in range(3):
+    out = kc.resize(tp, img, Size(1024, 1024), ResizeFilter.Lanczos3)
 tp.synchronize()
-ms,n=C.c_double(),C.c_uint64()
-call("kc_context_set_timing",ctx,1); call("kc_context_timing_read",ctx,-1,C.byref(ms),C.byref(n))
-for _ in range(5): down()
-for kind,name in ((4,"V"),(5,"H")):
-    call("kc_context_timing_read",ctx,kind,C.byref(ms),C.byref(n)); print(name, ms.value/max(1,n.value), n.value)
+ctx = tp._ctx._h
+ms, n = C.c_double(), C.c_uint64()
+call("kc_context_set_timing", ctx, 1)
+call("kc_context_timing_read", ctx, -1, C.byref(ms), C.byref(n))
+reps = 10
+for _ in range(reps):
+    out = kc.resize(tp, img, Size(1024, 1024), ResizeFilter.Lanczos3)
+tp.synchronize()
+for kind, name in {4: "vertical march", 5: "horizontal pass"}.items():
+    call("kc_context_timing_read", ctx, kind, C.byref(ms), C.byref(n))
+    print("%-16s %.4f ms  (%d launches)" % (name, ms.value / reps, n.value))

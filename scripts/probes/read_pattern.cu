@@ -2,7 +2,7 @@
 //   seq      : grid-stride float4 loads over the whole plane (the copy kernels' pattern)
 //   strips W : blocks own a W-column strip and a band of rows and walk down the band row by row,
 //              W/4 threads x 8 rows in flight (the vertical march's pattern)
-// Build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o probes/read_pattern probes/read_pattern.cu
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o scripts/probes/read_pattern.bin scripts/probes/read_pattern.cu
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
