@@ -272,7 +272,7 @@ def wl_resize(env, steps, src=1024, dst=8192):
 # ---------------------------------------------------------------------------------------------
 # configs[4]: 64 x 32-node graphs at 4096^2, whole graphs split over the ranks
 # ---------------------------------------------------------------------------------------------
-def wl_graph_batch(env, n_graphs=64, size=4096, distinct=2, replay=True):
+def wl_graph_batch(env, n_graphs=64, size=4096, distinct=3, replay=True, lanes=3):
     kc, tp = env.kc, env.tp
     from kanter_core_b200 import SlotId
     from tests import graphs
@@ -295,11 +295,14 @@ def wl_graph_batch(env, n_graphs=64, size=4096, distinct=2, replay=True):
         return True
 
     def run_share():
-        for i, _gid in enumerate(mine):
-            lg, imgs, _ = st["sets"][i % len(st["sets"])]
-            for eid, img in enumerate(imgs):       # "new inputs arrived": everything downstream is dirty again
-                lg.replace_embedded(img, eid)
-            lg.request(st["out"])
+        # independent graphs side by side: the reference's thread pool runs ready nodes of the batch concurrently
+        # (src/process_pack.rs:27); here the replays of the `distinct` live graphs alternate between `lanes` side streams
+        with tp.concurrent(lanes if replay else 1):
+            for i, _gid in enumerate(mine):
+                lg, imgs, _ = st["sets"][i % len(st["sets"])]
+                for eid, img in enumerate(imgs):       # "new inputs arrived": everything downstream is dirty again
+                    lg.replace_embedded(img, eid)
+                lg.request(st["out"])
 
     def warm():
         setup()
@@ -321,6 +324,7 @@ def wl_graph_batch(env, n_graphs=64, size=4096, distinct=2, replay=True):
     out = {"workload": "configs[4]: %d x 32-node graphs (Separate/Mix/HeightToNormal/Resize/Combine + nested Graph) at %dx%d%s" % (n_graphs, S, S, "" if env.world == 1 else ", whole graphs split over %d ranks, no collective" % env.world),
            "scaling": "strong" if env.world > 1 else "single GPU", "math": "fast", "graphs": n_graphs, "graphs_per_gpu": len(mine),
            "evaluation_replay": dict(lg0_stats := st["sets"][0][0].replay_stats(), on=replay),
+           "concurrent_lanes": lanes if replay else 1,
            "ms_total": ms_all, "ms_per_graph_per_gpu": per_graph, "mpixel_per_s": n_graphs * mpix / (ms_all / 1e3),
            "kernels_per_graph": stats["kernels"], "fused_groups_per_graph": stats["fused_groups"],
            "algorithmic_bytes": stats["algorithmic_bytes"], "algorithmic_bytes_note": "per graph, as the library counted it: each distinct plane read once + each result written once per kernel",

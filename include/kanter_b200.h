@@ -226,6 +226,19 @@ int32_t kc_context_set_memory_threshold(kc_context* ctx, uint64_t bytes);
  *      admits at most this many closest-processable nodes, highest PROPAGATED priority first.
  *      set_max_processing_nodes, src/texture_processor.rs:111-114; default = the host's logical CPUs (num_cpus::get()). */
 int32_t kc_context_set_max_processing_nodes(kc_context* ctx, size_t count);
+
+/* Concurrent section: the reference's engine runs up to `max_processing_nodes` ready nodes side by side on its thread
+ * pool (src/process_pack.rs:27, src/engine.rs:288), and nodes of DIFFERENT live graphs are the easy case.  Between
+ * begin and end, evaluations that are served by evaluation replay (kc_live_graph_set_replay) are launched on `lanes`
+ * side streams instead of the context's stream -- a plan keeps its lane, so replays of the same live graph stay in
+ * order -- and graphs whose kernels are bound by different units (a glibc-exact pow cone on the fp64 pipe next to
+ * HBM-bound kernels) overlap on the device.  The caller's side of the contract: the live graphs evaluated inside one
+ * section do not consume each other's results, and nothing else reads or overwrites their inputs or results before the
+ * section ends.  kc_context_concurrent_end -- and, as a safety net, kc_context_synchronize, every download, and every
+ * call that computes on the context's stream -- makes that stream wait for the lanes.  lanes = 1 is the ordinary
+ * behaviour. */
+int32_t kc_context_concurrent_begin(kc_context* ctx, int32_t lanes);
+int32_t kc_context_concurrent_end(kc_context* ctx);
 int32_t kc_context_max_processing_nodes(const kc_context* ctx, size_t* count);
 int32_t kc_context_spill_stats(const kc_context* ctx, uint64_t* bytes_spilled, uint64_t* spills, uint64_t* reloads);
 int32_t kc_plane_in_memory(const kc_plane* p, int32_t* in_memory);   /* TransientBufferContainer::in_memory */

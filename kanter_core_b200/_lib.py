@@ -95,6 +95,8 @@ SIGNATURES = {
     "kc_context_set_memory_threshold": (i32, [vp, u64]),
     "kc_context_spill_stats": (i32, [vp, P(u64), P(u64), P(u64)]),
     "kc_context_set_max_processing_nodes": (i32, [vp, sz]),
+    "kc_context_concurrent_begin": (i32, [vp, i32]),
+    "kc_context_concurrent_end": (i32, [vp]),
     "kc_context_max_processing_nodes": (i32, [vp, P(sz)]),
     "kc_graph_set_node_priority": (i32, [vp, u32, C.c_int8]),
     "kc_graph_node_priority": (i32, [vp, u32, P(C.c_int8), P(C.c_int8)]),

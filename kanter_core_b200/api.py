@@ -806,6 +806,23 @@ class TextureProcessor:
         call("kc_context_max_processing_nodes", self._ctx._h, C.byref(n))
         return n.value
 
+    def concurrent(self, lanes=2):
+        """Concurrent section (`with tex_pro.concurrent(2): ...`): live graphs evaluated inside it and served by evaluation
+        replay run on `lanes` side streams, so independent graphs overlap on the device -- what the reference's thread
+        pool does with ready nodes (src/process_pack.rs:27, src/engine.rs:288).  The graphs of one section must not consume
+        each other's results; read results after the section (include/kanter_b200.h, kc_context_concurrent_begin)."""
+        tp = self
+
+        class _Section:
+            def __enter__(self_inner):
+                call("kc_context_concurrent_begin", tp._ctx._h, int(lanes))
+                return tp
+
+            def __exit__(self_inner, *exc):
+                call("kc_context_concurrent_end", tp._ctx._h)
+                return False
+        return _Section()
+
     def set_math_mode(self, mode):
         call("kc_context_set_math_mode", self._ctx._h, int(mode))
 

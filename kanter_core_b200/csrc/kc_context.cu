@@ -198,6 +198,12 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) try {
         cudaStreamSynchronize(ctx->download_stream);
         if (ctx->dl_staging) cudaFreeAsync(ctx->dl_staging, ctx->stream);
         if (ctx->d_halo_timeouts) { cudaFree(ctx->d_halo_timeouts); ctx->d_halo_timeouts = nullptr; }
+        for (cudaStream_t st : ctx->lane_streams) cudaStreamDestroy(st);
+        for (cudaEvent_t ev : ctx->lane_events) cudaEventDestroy(ev);
+        if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
+        ctx->lane_streams.clear();
+        ctx->lane_events.clear();
+        ctx->lane_fork = nullptr;
         kc_dev_trim(ctx);
         for (auto& kv : ctx->axis_tables) axis_table_free(*kv.second);
         ctx->axis_tables.clear();
@@ -220,9 +226,62 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) try {
     return KC_OK;
 } KC_ABI_CATCH
 
+// ---- concurrent sections ---------------------------------------------------------------------------------------
+int32_t kc_lanes_join(kc_context* ctx) {
+    if (!ctx->lanes_dirty) return KC_OK;
+    for (size_t i = 0; i < ctx->lane_streams.size(); ++i)
+        if (ctx->lane_used[i]) {
+            KC_CUDA(cudaEventRecord(ctx->lane_events[i], ctx->lane_streams[i]));
+            KC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->lane_events[i], 0));
+            ctx->lane_used[i] = 0;
+        }
+    ctx->lanes_dirty = false;
+    return KC_OK;
+}
+
+int32_t kc_lane_acquire(kc_context* ctx, int* plan_lane, cudaStream_t* out) {
+    const int n = ctx->lanes_open;
+    while ((int)ctx->lane_streams.size() < n) {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev = nullptr;
+        KC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        KC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->lane_streams.push_back(st);
+        ctx->lane_events.push_back(ev);
+        ctx->lane_used.push_back(0);
+    }
+    if (!ctx->lane_fork) KC_CUDA(cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
+    if (*plan_lane < 0 || *plan_lane >= n) *plan_lane = ctx->lane_next++ % n;
+    const int l = *plan_lane;
+    // everything the compute stream holds so far (uploads of this plan's inputs included) comes first
+    KC_CUDA(cudaEventRecord(ctx->lane_fork, ctx->stream));
+    KC_CUDA(cudaStreamWaitEvent(ctx->lane_streams[l], ctx->lane_fork, 0));
+    ctx->lane_used[l] = 1;
+    ctx->lanes_dirty = true;
+    *out = ctx->lane_streams[l];
+    return KC_OK;
+}
+
+extern "C" int32_t kc_context_concurrent_begin(kc_context* ctx, int32_t lanes) try {
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    if (lanes < 1 || lanes > 8) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "lanes must be 1..8, got %d", lanes);
+    KcGuard g(ctx);
+    KC_TRY(kc_lanes_join(ctx));
+    ctx->lanes_open = lanes > 1 ? lanes : 0;
+    return KC_OK;
+} KC_ABI_CATCH
+
+extern "C" int32_t kc_context_concurrent_end(kc_context* ctx) try {
+    if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
+    KcGuard g(ctx);
+    ctx->lanes_open = 0;
+    return kc_lanes_join(ctx);
+} KC_ABI_CATCH
+
 extern "C" int32_t kc_context_synchronize(kc_context* ctx) try {
     if (!ctx) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "ctx is NULL");
     KcGuard g(ctx);
+    KC_TRY(kc_lanes_join(ctx));
     // uploads are waited for by `stream` (event), downloads are not
     KC_CUDA(cudaStreamSynchronize(ctx->stream));
     KC_CUDA(cudaStreamSynchronize(ctx->download_stream));
@@ -728,6 +787,7 @@ extern "C" int32_t kc_plane_download(kc_plane* p, float* host) try {
         return KC_OK;
     }
     KcGuard g(p->ctx);
+    KC_TRY(kc_lanes_join(p->ctx));
     KC_TRY(kcp_force(p->ctx, &p, 1));
     KC_CUDA(cudaMemcpyAsync(host, p->dptr, p->bytes(), cudaMemcpyDeviceToHost, p->ctx->stream));
     KC_CUDA(cudaStreamSynchronize(p->ctx->stream));
@@ -855,6 +915,7 @@ extern "C" int32_t kc_image_download(kc_context* ctx, const kc_image* in, float*
     for (int c = 0; c < kci_nplanes(in); ++c)
         if (!in->planes[c] || !host_planes[c]) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "image has no plane %d (released?) or no destination for it", c);
     KcGuard g(ctx);
+    KC_TRY(kc_lanes_join(ctx));
     int np = kci_nplanes(in);
     // one fused launch for whatever is still lazy, then the copies
     std::vector<kc_plane*> lazy;
@@ -901,6 +962,7 @@ extern "C" int32_t kc_image_to_u8_device(kc_context* ctx, const kc_image* in, in
 // the copy to the host runs on the download stream.  The buffer is rewritten only after the
 // previous download has finished (ev_dl_done).
 static int32_t to_u8_enqueue(kc_context* ctx, const kc_image* in, int32_t srgb, uint8_t* host_rgba8) {
+    KC_TRY(kc_lanes_join(ctx));
     for (int c = 0; c < kci_nplanes(in); ++c)
         if (!in->planes[c]) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "image has no plane %d (released?)", c);
     const size_t n = (size_t)in->planes[0]->w * in->planes[0]->h;
@@ -1043,6 +1105,7 @@ extern "C" int32_t kc_debug_set_tuning(const char* key, int32_t value) try {
     if (k == "tile_v") g_kc_tuning.tile_v = value;
     else if (k == "ctas") g_kc_tuning.ctas = value;
     else if (k == "stages") g_kc_tuning.stages = value;
+    else if (k == "smem_cap_kb") g_kc_tuning.smem_cap_kb = value;
     else if (k == "src_soft_cap") g_kc_tuning.src_soft_cap = value;
     else if (k == "resize_threads") g_kc_tuning.resize_threads = value;
     else if (k == "jit") g_kc_tuning.jit = value;

@@ -761,6 +761,7 @@ struct KcPlan {
     std::map<uint32_t, int> states;      // node states after it
     std::vector<uint32_t> cleaned;       // nodes it turned Clean (LiveGraph::changed)
     uint64_t kernels = 0, groups = 0, bytes = 0, jit_generation = 0;
+    int lane = -1;                       // its side stream inside concurrent sections (kc_context_concurrent_begin)
 };
 
 // The capture is a chain (every launch went to the one compute stream).  With the footprint of every launch at hand the
@@ -853,6 +854,7 @@ static std::string plan_key(kc_live_graph& lg, const uint32_t* ids, size_t n_ids
     key_add(k, lg.ctx->opts.fuse);
     key_add(k, lg.ctx->opts.resize_unclamped);
     key_add(k, g_kc_tuning);
+    key_add(k, lg.ctx->lanes_open > 1);          // launches captured inside a concurrent section size themselves for a shared SM
     for (const auto& kv : lg.state) { key_add(k, kv.first); key_add(k, kv.second); }
     auto img = [&](const kc_image& im) {
         key_add(k, im.kind);
@@ -902,7 +904,9 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
             slot_datas = plan->snapshot;
             for (const auto& kv : plan->states) state[kv.first] = kv.second;
             for (uint32_t id : plan->cleaned) changed.insert(id);
-            cudaError_t e = cudaGraphLaunch(plan->exec, ctx->stream);
+            cudaStream_t where = ctx->stream;
+            if (ctx->lanes_open > 1) KC_TRY(kc_lane_acquire(ctx, &plan->lane, &where));
+            cudaError_t e = cudaGraphLaunch(plan->exec, where);
             if (e != cudaSuccess) KC_FAIL(KC_ERR_CUDA, "cudaGraphLaunch failed: %s", cudaGetErrorString(e));
             ctx->kernel_launches += plan->kernels;
             ctx->run_kernels += plan->kernels;
@@ -1007,6 +1011,7 @@ int32_t kc_live_graph::evaluate(const uint32_t* ids, size_t n_ids, bool material
 }
 
 int32_t kc_live_graph::evaluate_impl(const uint32_t* ids, size_t n_ids, bool materialise) {
+    KC_TRY(kc_lanes_join(ctx));         // the ordinary path runs on the compute stream: after whatever the lanes hold
     KcGuard guard(ctx);
     KcHostTimer hp(KC_HP_EVALUATE);
     ctx->cancel.store(false);

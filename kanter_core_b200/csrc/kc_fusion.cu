@@ -572,6 +572,7 @@ int32_t kcp_prefetch_leaves(kc_context* ctx, kc_plane* const* roots, size_t n) {
 
 int32_t kcp_force(kc_context* ctx, kc_plane* const* roots, size_t n) {
     KcHostTimer hp(KC_HP_FORCE);
+    KC_TRY(kc_lanes_join(ctx));        // whoever asks for pixels on the compute stream comes after the lanes of a concurrent section
     int32_t rc = force_impl(ctx, roots, n, 0, 0, nullptr, 0);
     // the evaluation held its operands in HBM (pins); now that they are released the queue may settle --
     // except for the planes the caller asked for: it is about to read them

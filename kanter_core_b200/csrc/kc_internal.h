@@ -195,6 +195,15 @@ struct kc_context {
     std::vector<size_t>* alloc_log = nullptr;
     KcArena* arena_active = nullptr;
     std::vector<KcArena*> arenas;
+    // concurrent section (kc_context_concurrent_begin/end): replays of DIFFERENT plans go to side streams ("lanes"), so that
+    // independent graphs overlap on the device; a plan keeps its lane (its replays write the same arena and stay in order)
+    int lanes_open = 0;                    // lanes of the open section, 0: none
+    int lane_next = 0;
+    bool lanes_dirty = false;              // a lane has work the compute stream has not been made to wait for
+    std::vector<cudaStream_t> lane_streams;
+    std::vector<cudaEvent_t> lane_events;
+    std::vector<char> lane_used;
+    cudaEvent_t lane_fork = nullptr;
     std::vector<KcFootprint>* capture_log = nullptr;   // one entry per kernel launch, in launch order (only while capturing)
     bool capturing = false;                    // ctx->stream is in CUDA stream capture: nothing but kernel launches may be enqueued
     unsigned int* d_halo_timeouts = nullptr;   // device counter of waits that gave up (this context's kernels only)
@@ -300,6 +309,7 @@ struct KcTuning {
     int tile_v = 0;          // float4s per thread per tile of the fused elementwise kernel (1, 2, 4)
     int ctas = 0;            // resident CTAs per SM of that kernel (1..3)
     int stages = 0;          // its pipeline depth (2..4)
+    int smem_cap_kb = 0;     // shared memory per SM that kernel sizes itself for (default 227): less leaves room for a kernel of another lane
     int src_soft_cap = 0;    // merge independent outputs that only share SOURCES while the union has <= this many
     int resize_threads = 0;  // threads per CTA of the fused resize kernel (32, 64, 128)
     int jit = 0;             // per-tape specialisation of the fused kernel: 0 auto (hot, long tapes on large planes), 1 always, -1 never
@@ -400,6 +410,10 @@ int32_t kck_halo_ack(kc_context* ctx, const kc_halo_link* inbox, uint64_t step);
 uint32_t kck_halo_width(const kc_halo_link* l);
 // after a synchronisation of ctx->stream: KC_ERR_CUDA if a wait on a peer's flag gave up since the last check
 int32_t kck_halo_check_timeouts(kc_context* ctx);
+// the compute stream waits for everything the lanes of a concurrent section were given (no-op when there is nothing)
+int32_t kc_lanes_join(kc_context* ctx);
+// the lane of a plan inside a concurrent section (made to wait for what the compute stream holds so far)
+int32_t kc_lane_acquire(kc_context* ctx, int* plan_lane, cudaStream_t* out);
 int32_t kck_resize_plane(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst,
                          uint32_t dw, uint32_t dh, int filter);
 int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, uint32_t sh, float* dst, uint32_t dw,

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
     ap.add_argument("--distinct", type=int, default=2)
+    ap.add_argument("--lanes", type=int, default=1, help="> 1: evaluation replay, the live graphs' replays on this many side streams (TextureProcessor.concurrent)")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
@@ -78,19 +79,24 @@ def main():
         inputs = graphs.config5_inputs(100 + rank * 1000 + d, S)
         lg = tp.new_live_graph()
         lg.set_node_graph(g)
+        if args.lanes > 1:
+            lg.set_replay(True)
         imgs = [kc.SlotImage.from_planes(tp, planes) for planes in inputs]
         for eid, img in enumerate(imgs):
             lg.embed_slot_data_with_id(kc.SlotData.new(0, 0, img), eid)
         sets.append((lg, imgs, inputs if (rank == 0 and d == 0) else None))
 
     def run_share():
-        for i, _gid in enumerate(mine):
-            lg, imgs, _ = sets[i % len(sets)]
-            for eid, img in enumerate(imgs):       # "new inputs arrived": everything downstream is dirty again
-                lg.replace_embedded(img, eid)
-            lg.request(out)
+        with tp.concurrent(max(1, args.lanes)):
+            for i, _gid in enumerate(mine):
+                lg, imgs, _ = sets[i % len(sets)]
+                for eid, img in enumerate(imgs):       # "new inputs arrived": everything downstream is dirty again
+                    lg.replace_embedded(img, eid)
+                lg.request(out)
 
     run_share()                                     # warm-up (also builds the resize tap tables)
+    if args.lanes > 1:
+        run_share()                                 # (replay: ordinary pass, capture, replays from here on)
     kc.jit_wait()                                   # hot tapes are compiled in the background; measure what serves them from then on
     run_share()
     tp.synchronize()

@@ -228,3 +228,39 @@ def test_replay_at_a_size_the_tensor_map_kernels_take(tex_pro):
             assert bits_equal(got[c], want[c]), (frame, c)
         del got
     assert lg.replay_stats()["replays"] >= 1, lg.replay_stats()
+
+
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_concurrent_section_runs_independent_graphs_on_lanes_bit_identically(tex_pro, lanes):
+    """kc_context_concurrent_begin/end: the replays of several live graphs go to side streams.  Frame after frame (inputs
+    rewritten in place between sections) every graph's result equals the oracle bit for bit; a download inside a section is
+    ordered behind the lanes; a graph that has no plan yet simply evaluates on the context's stream."""
+    size, n = 128, 4
+    sets = [_config5(tex_pro, size) for _ in range(n)]
+    for g, out, bufs, lg in sets:
+        lg.set_replay(True)
+    for frame in range(6):
+        inputs = [graphs.config5_inputs(900 + 10 * frame + i, size) for i in range(n)]
+        for (g, out, bufs, lg), inp in zip(sets, inputs):
+            bufs.fill(inp)
+        with tex_pro.concurrent(lanes):
+            for rep in range(2):                                  # twice: the second round replays over the first one's arenas
+                for g, out, bufs, lg in sets:
+                    for eid, img in enumerate(bufs.images):
+                        lg.replace_embedded(img, eid)
+                    lg.request(out)
+            if frame == 3:                                        # reading inside the section: the download waits for the lanes
+                g, out, bufs, lg = sets[1]
+                got = lg.slot_data(out, SlotId(0)).image.planes()
+                want = graphs.config5_oracle(g, out, inputs[1])
+                assert all(bits_equal(got[c], want[c]) for c in range(4))
+                del got
+        for i, (g, out, bufs, lg) in enumerate(sets):
+            got = lg.slot_data(out, SlotId(0)).image.planes()
+            want = graphs.config5_oracle(g, out, inputs[i])
+            for c in range(4):
+                assert bits_equal(got[c], want[c]), (frame, i, c)
+            del got
+    assert sum(lg.replay_stats()["replays"] for _, _, _, lg in sets) >= n * 4
+    with pytest.raises(Exception):
+        call("kc_context_concurrent_begin", tex_pro._ctx._h, 99)
