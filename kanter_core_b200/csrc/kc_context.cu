@@ -193,6 +193,8 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) try {
     if (ctx->closed) KC_FAIL(KC_ERR_INVALID_ARGUMENT, "the context was destroyed already");
     {
         KcGuard g(ctx);
+        ctx->lanes_open = 0;
+        kc_lanes_join(ctx);
         cudaStreamSynchronize(ctx->upload_stream);
         cudaStreamSynchronize(ctx->stream);
         cudaStreamSynchronize(ctx->download_stream);
@@ -203,6 +205,7 @@ extern "C" int32_t kc_context_destroy(kc_context* ctx) try {
         if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
         ctx->lane_streams.clear();
         ctx->lane_events.clear();
+        ctx->lane_used.clear();
         ctx->lane_fork = nullptr;
         kc_dev_trim(ctx);
         for (auto& kv : ctx->axis_tables) axis_table_free(*kv.second);
@@ -360,6 +363,7 @@ void kc_arena_orphan(kc_context* ctx, KcArena* a) {   // the plan that owned it 
     if (!a) return;
     if (a->live == 0) {
         ctx->arenas.erase(std::remove(ctx->arenas.begin(), ctx->arenas.end(), a), ctx->arenas.end());
+        if (!ctx->closed) kc_lanes_join(ctx);              // a replay on a lane of a concurrent section may still write into it
         if (!ctx->closed) cudaStreamSynchronize(ctx->stream);
         arena_destroy(a);
     } else {
@@ -374,6 +378,7 @@ void kc_dev_free(kc_context* ctx, void* p, size_t bytes) {
         if (p < a->base || p >= (char*)a->base + ((char*)a->slots.back() - (char*)a->base) + a->bytes.back()) continue;
         if (--a->live == 0 && a->orphaned) {
             ctx->arenas.erase(ctx->arenas.begin() + i);
+            if (!ctx->closed) kc_lanes_join(ctx);
             if (!ctx->closed) cudaStreamSynchronize(ctx->stream);
             arena_destroy(a);
         }

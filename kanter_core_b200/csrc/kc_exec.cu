@@ -835,6 +835,10 @@ static void plan_parallelise(cudaGraph_t graph, const std::vector<KcFootprint>& 
 void kc_live_graph::drop_plan() {
     if (!plan) return;
     plan->snapshot.clear();
+    if (plan->exec && ctx->lanes_dirty && !ctx->closed) {   // its last replay may still be running on a lane of a concurrent section
+        kc_lanes_join(ctx);
+        cudaStreamSynchronize(ctx->stream);
+    }
     if (plan->exec) cudaGraphExecDestroy(plan->exec);
     if (plan->arena) kc_arena_orphan(ctx, plan->arena);
     delete plan;

@@ -264,3 +264,36 @@ def test_concurrent_section_runs_independent_graphs_on_lanes_bit_identically(tex
     assert sum(lg.replay_stats()["replays"] for _, _, _, lg in sets) >= n * 4
     with pytest.raises(Exception):
         call("kc_context_concurrent_begin", tex_pro._ctx._h, 99)
+
+
+def test_concurrent_section_survives_teardown_while_lanes_are_busy():
+    """A plan dropped (graph replaced), a live graph released and the context destroyed while replays are still running on
+    the lanes: every teardown path waits for the lanes before it frees what they write."""
+    tp = kc.TextureProcessor()
+    size, n = 256, 3
+    sets = [_config5(tp, size) for _ in range(n)]
+    inputs = [graphs.config5_inputs(950 + i, size) for i in range(n)]
+    for (g, out, bufs, lg), inp in zip(sets, inputs):
+        lg.set_replay(True)
+        bufs.fill(inp)
+    for _ in range(3):                                            # ordinary pass, capture, first replay
+        with tp.concurrent(3):
+            for g, out, bufs, lg in sets:
+                for eid, img in enumerate(bufs.images):
+                    lg.replace_embedded(img, eid)
+                lg.request(out)
+    call("kc_context_concurrent_begin", tp._ctx._h, 3)
+    for g, out, bufs, lg in sets:
+        for eid, img in enumerate(bufs.images):
+            lg.replace_embedded(img, eid)
+        lg.request(out)
+    g1, out1, bufs1, lg1 = sets[1]
+    lg1.set_node_graph(graphs.config5_graph(size)[0])           # a new graph: the plan goes while its replay may still run
+    g2, out2, bufs2, lg2 = sets.pop(2)
+    del lg2, bufs2                                                # a live graph and its inputs released inside the section
+    g0, out0, bufs0, lg0 = sets[0]
+    got = lg0.slot_data(out0, SlotId(0)).image.planes()           # (a download: ordered behind the lanes)
+    want = graphs.config5_oracle(g0, out0, inputs[0])
+    assert all(bits_equal(got[c], want[c]) for c in range(4))
+    del got, lg0, lg1, bufs0, bufs1, sets
+    del tp                                                        # the context goes with the section still open
