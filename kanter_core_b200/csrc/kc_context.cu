@@ -1111,6 +1111,7 @@ extern "C" int32_t kc_debug_set_tuning(const char* key, int32_t value) try {
     else if (k == "ctas") g_kc_tuning.ctas = value;
     else if (k == "stages") g_kc_tuning.stages = value;
     else if (k == "smem_cap_kb") g_kc_tuning.smem_cap_kb = value;
+    else if (k == "smem_cap_exact_kb") g_kc_tuning.smem_cap_exact_kb = value;
     else if (k == "src_soft_cap") g_kc_tuning.src_soft_cap = value;
     else if (k == "resize_threads") g_kc_tuning.resize_threads = value;
     else if (k == "jit") g_kc_tuning.jit = value;

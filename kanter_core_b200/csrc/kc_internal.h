@@ -310,6 +310,7 @@ struct KcTuning {
     int ctas = 0;            // resident CTAs per SM of that kernel (1..3)
     int stages = 0;          // its pipeline depth (2..4)
     int smem_cap_kb = 0;     // shared memory per SM that kernel sizes itself for (default 227): less leaves room for a kernel of another lane
+    int smem_cap_exact_kb = 0;  // the same for launches of a glibc-exact cone inside a concurrent section (default 113, like the others)
     int src_soft_cap = 0;    // merge independent outputs that only share SOURCES while the union has <= this many
     int resize_threads = 0;  // threads per CTA of the fused resize kernel (32, 64, 128)
     int jit = 0;             // per-tape specialisation of the fused kernel: 0 auto (hot, long tapes on large planes), 1 always, -1 never

@@ -143,7 +143,7 @@ struct TvmConfig { int v, ctas, stages; };
 // nt_max shared-memory temporaries per segment.  Measured on B200 (profiles/):
 // 4096-pixel tiles beat smaller ones (the dispatch is amortised over 16 pixels per
 // thread), 3 resident CTAs beat 2 beat 1, and 2 stages are as good as 4.
-TvmConfig pick_config(int ns_max, int nt_max, unsigned long long n, bool shared_sm) {
+TvmConfig pick_config(int ns_max, int nt_max, unsigned long long n, int shared_cap_kb) {
     const int force_v = g_kc_tuning.tile_v, force_stages = g_kc_tuning.stages, force_ctas = g_kc_tuning.ctas;
     static const TvmConfig order[] = {{4, 3, 0}, {4, 2, 0}, {2, 3, 0}, {2, 2, 0}, {1, 3, 0}, {1, 2, 0}, {4, 1, 0}, {2, 1, 0}, {1, 1, 0}};
     for (int pass = 0; pass < 2; ++pass) {  // pass 0 honours the tuning overrides, pass 1 ignores them
@@ -157,7 +157,7 @@ TvmConfig pick_config(int ns_max, int nt_max, unsigned long long n, bool shared_
             // inside a concurrent section (kc_context_concurrent_begin) a launch sizes itself for half an SM's shared memory,
             // so that a kernel of another lane finds room beside it: the persistent grid would otherwise hold every SM to
             // itself until its last tile (configs[4], 3 lanes: 0.345 ms per graph with the whole SM, 0.332 with half)
-            const size_t cap_kb = g_kc_tuning.smem_cap_kb >= 16 && g_kc_tuning.smem_cap_kb <= 227 ? (size_t)g_kc_tuning.smem_cap_kb : shared_sm ? 113 : 227;
+            const size_t cap_kb = g_kc_tuning.smem_cap_kb >= 16 && g_kc_tuning.smem_cap_kb <= 227 ? (size_t)g_kc_tuning.smem_cap_kb : shared_cap_kb > 0 ? (size_t)shared_cap_kb : 227;
             const size_t budget = cap_kb * 1024 / (size_t)c.ctas - 1024 - 128;
             const size_t tile_b = (size_t)4096 * c.v;
             for (int st = 4; st >= (force_stages == 1 ? 1 : 2); --st) {
@@ -196,15 +196,16 @@ int32_t kck_launch_tape(kc_context* ctx, const KcTapeArgs& args) {
     int ns_max = 0;
     for (uint32_t s = 0; s < args.n_seg; ++s) ns_max = std::max<int>(ns_max, (int)args.seg[s].n_src);
     const int nt_max = (int)args.variant;  // temporaries the tapes touch (set by the planner)
-    const TvmConfig c = pick_config(ns_max, nt_max, args.n, ctx->lanes_open > 1);
+    const bool exact = kc_tape_exact(ctx);   // EXACT mode, or the operand cone of a stencil (KcExactScope)
+    const int shared_cap = ctx->lanes_open > 1 ? (exact && g_kc_tuning.smem_cap_exact_kb > 0 ? g_kc_tuning.smem_cap_exact_kb : 113) : 0;
+    const TvmConfig c = pick_config(ns_max, nt_max, args.n, shared_cap);
     g_kc_last_tile_config[0] = c.v; g_kc_last_tile_config[1] = c.ctas; g_kc_last_tile_config[2] = c.stages;
     KcTimed timed(ctx, KC_KERNEL_TAPE);
     int32_t rc;
-    const bool exact = kc_tape_exact(ctx);   // EXACT mode, or the operand cone of a stencil (KcExactScope)
     {
         // a kernel specialised for this tape (kc_jit.cu): its temporaries are registers, so the launch
         // configuration is chosen for zero shared-memory temporaries, V bounded by the register budget
-        TvmConfig j = pick_config(ns_max, 0, args.n, ctx->lanes_open > 1);
+        TvmConfig j = pick_config(ns_max, 0, args.n, shared_cap);
         while (j.v > 1 && (2 + nt_max) * 4 * j.v > 96) j.v >>= 1;
         bool launched = false;
         KC_TRY(kcj_try_launch(ctx, args, ns_max, j.v, j.ctas, j.stages, &launched));

@@ -21,7 +21,7 @@ for spec in sys.argv[1:] or ["1:2", "2:2", "2:4", "4:4"]:
     parts = spec.split(":")
     lanes, distinct = int(parts[0]), int(parts[1])
     knobs = dict(kv.split("=") for kv in parts[2].split(",")) if len(parts) > 2 else {}
-    for k in ("ctas", "stages", "tile_v", "smem_cap_kb"):
+    for k in ("ctas", "stages", "tile_v", "smem_cap_kb", "smem_cap_exact_kb"):
         _lib.call("kc_debug_set_tuning", k.encode(), int(knobs.get(k, 0)))
     r = bw.wl_graph_batch(env, distinct=distinct, lanes=lanes)
     print(spec, "lanes %d distinct %d: %.4f ms/graph  frac %.3f  parity %s  %s" % (
