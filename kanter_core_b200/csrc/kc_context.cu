@@ -248,7 +248,10 @@ int32_t kc_lane_acquire(kc_context* ctx, int* plan_lane, cudaStream_t* out) {
         cudaStream_t st = nullptr;
         cudaEvent_t ev = nullptr;
         KC_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        KC_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+            cudaStreamDestroy(st);
+            KC_FAIL(KC_ERR_CUDA, "could not create the event of a lane: %s", cudaGetErrorString(cudaGetLastError()));
+        }
         ctx->lane_streams.push_back(st);
         ctx->lane_events.push_back(ev);
         ctx->lane_used.push_back(0);

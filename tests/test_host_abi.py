@@ -470,3 +470,12 @@ def test_propagate_priority():
     node.resize_filter = kc.ResizeFilter.Nearest
     assert g.clone().node(n3).priority.priority() == 8
     assert NodeGraph.from_json(g.export_json_string()).node(n3).priority.priority() == 0
+
+
+def test_concurrent_section_entry_points_reject_a_null_context():
+    """kc_context_concurrent_begin / _end without a context: an error code and a message, no crash (no GPU needed)."""
+    from kanter_core_b200._lib import call
+    for name, args in (("kc_context_concurrent_begin", (None, 2)), ("kc_context_concurrent_end", (None,))):
+        with pytest.raises(Exception) as e:
+            call(name, *args)
+        assert "NULL" in str(e.value)
