@@ -1170,7 +1170,6 @@ __global__ void __launch_bounds__(VM_THREADS) kc_resize_v_march_kernel(const flo
 // kc_resize_v_march_kernel.
 // ---------------------------------------------------------------------------
 constexpr int VT_R = 8;                       // source rows per stage
-constexpr int VT_STAGES = 4;
 constexpr int VT_COLS = 512;                  // source columns per block (128 compute threads x 4)
 constexpr int VT_PIX_BYTES = VT_R * VT_COLS * 4;
 constexpr int VT_INFO = 12;                   // ints per source row in the retire table: eight output ids, the flag word, padding
@@ -1198,8 +1197,12 @@ __device__ __forceinline__ void vt_tap(float2& alo, float2& ahi, const float2& v
     }
 }
 
-template <bool EXACT>
-__global__ void __launch_bounds__(160) kc_resize_v_tma_kernel(const __grid_constant__ CUtensorMap tm_src, uint32_t sw4, uint32_t sh, float4* __restrict__ tmp,
+// CTAS: resident blocks per SM the kernel is compiled for (the register budget), VT_STAGES: depth of its ring.  The pass is bound
+// by the latency of a warp's row (its time is proportional to the source rows per block whether one or three blocks share an
+// SM), so what pays is MORE blocks with fewer rows each: four per SM in FAST (94 registers); EXACT needs 107 and stays at
+// three.  The ring's depth does not matter (two stages are as fast as four).
+template <bool EXACT, int CTAS, int VT_STAGES>
+__global__ void __launch_bounds__(160, CTAS) kc_resize_v_tma_kernel(const __grid_constant__ CUtensorMap tm_src, uint32_t sw4, uint32_t sh, float4* __restrict__ tmp,
                                                               uint32_t dh, const uint32_t* __restrict__ vleft, const uint32_t* __restrict__ vcount,
                                                               const float2* __restrict__ mw2, const int* __restrict__ mi, uint32_t rows_per_cta, float one) {
     extern __shared__ __align__(128) unsigned char vts[];
@@ -1222,24 +1225,27 @@ __global__ void __launch_bounds__(160) kc_resize_v_tma_kernel(const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // one stage's loads: two tensor boxes of pixels, the stage's slice of the two marching tables
+    auto issue = [&](uint32_t k) {
+        const int st = k % VT_STAGES;
+        unsigned char* S = stage0 + (size_t)st * VT_STAGE_BYTES;
+        const uint32_t row = r0 + k * VT_R;                          // rows past the image arrive as zeros and are never used
+        const uint32_t trows = min((uint32_t)VT_R, sh - row);        // table rows that exist
+        ft_mbar_expect_tx(&full[st], VT_PIX_BYTES + trows * 64 + trows * VT_INFO * 4);
+        const uint64_t pol = k * VT_R < n_shared ? l2_policy_evict_last() : l2_policy_evict_first();
+        vt_tma_load_2d_hint(S, &tm_src, cx0, row, &full[st], pol);
+        vt_tma_load_2d_hint(S + VT_R * 256 * 4, &tm_src, cx0 + 256, row, &full[st], pol);
+        vt_bulk_load_1d(S + VT_PIX_BYTES, mw2 + (size_t)row * VM_SLOTS, trows * 64, &full[st]);
+        vt_bulk_load_1d(S + VT_PIX_BYTES + VT_R * 64, mi + (size_t)row * VT_INFO, trows * VT_INFO * 4, &full[st]);
+    };
     if (warp == 4) {
-        // ---- producer ----
-        if (lane == 0) {
-            const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+        // ---- producer warp (folding its work into thread 0 of a compute warp, for 128-thread blocks and five per SM, was
+        // slower: 0.070 against 0.062 ms -- that warp waits for the others before every refill) ----
+        if (lane == 0)
             for (uint32_t k = 0; k < nstage; ++k) {
-                const int st = k % VT_STAGES;
-                if (k >= VT_STAGES) ft_mbar_wait(&empty[st], ((k / VT_STAGES) - 1) & 1u);
-                unsigned char* S = stage0 + (size_t)st * VT_STAGE_BYTES;
-                const uint32_t row = r0 + k * VT_R;                  // rows past the image arrive as zeros and are never used
-                const uint32_t trows = min((uint32_t)VT_R, sh - row);                    // table rows that exist
-                ft_mbar_expect_tx(&full[st], VT_PIX_BYTES + trows * 64 + trows * VT_INFO * 4);
-                const uint64_t pol = k * VT_R < n_shared ? pol_keep : pol_stream;
-                vt_tma_load_2d_hint(S, &tm_src, cx0, row, &full[st], pol);
-                vt_tma_load_2d_hint(S + VT_R * 256 * 4, &tm_src, cx0 + 256, row, &full[st], pol);
-                vt_bulk_load_1d(S + VT_PIX_BYTES, mw2 + (size_t)row * VM_SLOTS, trows * 64, &full[st]);
-                vt_bulk_load_1d(S + VT_PIX_BYTES + VT_R * 64, mi + (size_t)row * VT_INFO, trows * VT_INFO * 4, &full[st]);
+                if (k >= (uint32_t)VT_STAGES) ft_mbar_wait(&empty[k % VT_STAGES], ((k / VT_STAGES) - 1) & 1u);
+                issue(k);
             }
-        }
         return;
     }
     // ---- compute: thread t owns columns cx0 + 4t .. 4t+3 ----
@@ -1613,15 +1619,29 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
             static const bool no_vtma = getenv("KC_RESIZE_NO_VTMA") != nullptr;
             if (!no_vtma && tensor_map_encoder() && (((uintptr_t)src | (uintptr_t)tmp) & 15u) == 0 && sw >= (uint32_t)VT_COLS / 2) {
                 CUtensorMap m_src;
-                // output rows per block: a whole wave of blocks at three per SM, never fewer than 16 rows
+                // output rows per block: one whole wave of blocks at the kernel's residency (FAST four per SM, EXACT three;
+                // two stages either way), never fewer than 16 rows.  Measured 8192^2 -> 1024^2 Lanczos3, ms FAST / EXACT:
+                // 3 per SM x 4 stages 0.066 / 0.079, 3 x 2 0.064 / 0.077, 4 x 3 0.062 / 0.079, 4 x 2 0.062 / 0.080.  KC_VT_SHAPE=<ctas><stages> picks another compiled shape
+                static const int env_shape = getenv("KC_VT_SHAPE") ? atoi(getenv("KC_VT_SHAPE")) : 0;
+                const int shape = env_shape ? env_shape : exact ? 32 : 42;
+                const int ctas = shape / 10, stages = shape % 10;
                 const uint32_t strips = (sw + VT_COLS - 1) / VT_COLS;
-                const uint32_t want_gy = std::max<uint32_t>(1u, (uint32_t)(ctx->sm_count * 3) / strips);
+                const uint32_t want_gy = std::max<uint32_t>(1u, (uint32_t)(ctx->sm_count * ctas) / strips);
                 uint32_t rpc = std::max<uint32_t>(16u, (dh + want_gy - 1) / want_gy);
                 if (env_rows > 0) rpc = (uint32_t)env_rows;
                 const uint32_t gy2 = (dh + rpc - 1) / rpc;
-                const size_t smem2 = 128 + (size_t)VT_STAGES * VT_STAGE_BYTES;
-                if (gy2 <= 65535u && make_tensor_map_2d(&m_src, src, sw, sh, 256u, (uint32_t)VT_R)) {
-                    const void* fn = exact ? (const void*)kc_resize_v_tma_kernel<true> : (const void*)kc_resize_v_tma_kernel<false>;
+                const size_t smem2 = 128 + (size_t)stages * VT_STAGE_BYTES;
+                const void* fn = nullptr;
+#define KC_VT(C, S) (exact ? (const void*)kc_resize_v_tma_kernel<true, C, S> : (const void*)kc_resize_v_tma_kernel<false, C, S>)
+                switch (shape) {
+                    case 34: fn = KC_VT(3, 4); break;
+                    case 32: fn = KC_VT(3, 2); break;
+                    case 43: fn = KC_VT(4, 3); break;
+                    case 42: fn = KC_VT(4, 2); break;
+                    default: break;
+                }
+#undef KC_VT
+                if (fn && gy2 <= 65535u && make_tensor_map_2d(&m_src, src, sw, sh, 256u, (uint32_t)VT_R)) {
                     KC_TRY(kc_ensure_smem_attr(ctx, fn, 100 * 1024));
                     const uint32_t sw4 = sw >> 2;
                     float4* tmp4 = (float4*)tmp;
