@@ -1267,15 +1267,25 @@ __global__ void __launch_bounds__(160, CTAS) kc_resize_v_tma_kernel(const __grid
         const uint32_t ucount = min((uint32_t)VT_R, nr - k * VT_R);
         // the operands of a row are fetched one row ahead of their use, so the shared-memory latency sits behind the
         // sixteen FFMA2 of the row before (rows past ucount are fetched from the stage too, and not used)
+        // A slot the row is no tap of has weight 0 and a running sum of +0 (it was cleared when its last output left):
+        // +0 + 0*v stays +0 for every finite v, so the products need no test per slot.  A non-finite v would turn that +0
+        // into NaN; those four columns take the tested path for the row.  The test of a row (0*v summed over the four
+        // columns is 0) is made one row ahead as well: the branch never waits for its predicate.
+        auto all_finite = [](const float4& p) {
+            const float2 c = __ffma2_rn(make_float2(p.x, p.y), make_float2(0.f, 0.f), __fmul2_rn(make_float2(p.z, p.w), make_float2(0.f, 0.f)));
+            return c.x + c.y == 0.f;
+        };
         float4 v_n = px[0], w_n[VM_SLOTS / 2];
         uint32_t flags_n = (uint32_t)ot[8];
 #pragma unroll
         for (int q = 0; q < VM_SLOTS / 2; ++q) w_n[q] = wt[q];
+        bool fin_n = all_finite(v_n);
 #pragma unroll
         for (int u = 0; u < VT_R; ++u) {
             if ((uint32_t)u >= ucount) break;                        // uniform
             const float4 v = v_n;
             const uint32_t flags = flags_n;                          // bits 0-7: slots completing on this row; 8-15: slots it is a tap of
+            const bool fin = fin_n;
             float4 w[VM_SLOTS / 2];                                  // the weights of slots 2q and 2q+1, each already a pair
 #pragma unroll
             for (int q = 0; q < VM_SLOTS / 2; ++q) w[q] = w_n[q];
@@ -1286,11 +1296,7 @@ __global__ void __launch_bounds__(160, CTAS) kc_resize_v_tma_kernel(const __grid
                 for (int q = 0; q < VM_SLOTS / 2; ++q) w_n[q] = wt[4 * (u + 1) + q];
             }
             const float2 vlo = make_float2(v.x, v.y), vhi = make_float2(v.z, v.w);
-            // A slot the row is no tap of has weight 0 and a running sum of +0 (it was cleared when its last output left):
-            // +0 + 0*v stays +0 for every finite v, so the products need no test per slot.  A non-finite v would turn
-            // that +0 into NaN; those four columns take the tested path for the row.
-            const float2 chk = __ffma2_rn(vlo, make_float2(0.f, 0.f), __fmul2_rn(vhi, make_float2(0.f, 0.f)));
-            if (chk.x + chk.y == 0.f) {
+            if (fin) {
 #pragma unroll
                 for (int q = 0; q < VM_SLOTS / 2; ++q) {
                     vt_tap<EXACT>(alo[2 * q], ahi[2 * q], vlo, vhi, make_float2(w[q].x, w[q].y), one);
@@ -1303,6 +1309,7 @@ __global__ void __launch_bounds__(160, CTAS) kc_resize_v_tma_kernel(const __grid
                     if (flags & (0x200u << (2 * q))) vt_tap<EXACT>(alo[2 * q + 1], ahi[2 * q + 1], vlo, vhi, make_float2(w[q].z, w[q].w), one);
                 }
             }
+            if (u + 1 < VT_R) fin_n = all_finite(v_n);
             if ((flags & 0xffu) == 0u) continue;                     // nothing completes on this row
 #pragma unroll
             for (int s = 0; s < VM_SLOTS; ++s)
