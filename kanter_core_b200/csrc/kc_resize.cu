@@ -1681,29 +1681,29 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
     }
     kc_log_launch(ctx, {{tmp, (size_t)sw * dh * 4}}, {{dst, (size_t)dw * dh * 4}});      // the horizontal pass
     // outputs per block (two per thread) and groups of four rows per block (they share the block's copy of the weights; what
-    // limits the resident warps is shared memory): the pair with the fewest rounds over the resident slots, weighted by the
-    // columns a round stages
+    // limits the resident warps is shared memory).  Measured (scripts/probes/downsample_split.py, four shapes from 4096 -> 512
+    // to 8192 -> 2048 columns): 128 outputs x 4 groups is the fastest or tied everywhere it fits (0.0191 / 0.0352 ms against
+    // 0.0209 / 0.0374 for 64 x 4 and 0.0230 / 0.0414 for 64 x 1), so: the first shape of that order that fits 96 KB and still
+    // gives every SM a block; failing that, the one with the most blocks.
     static const int env_ht = getenv("KC_RESIZE_HT") ? atoi(getenv("KC_RESIZE_HT")) : 0;
     static const int env_hrw = getenv("KC_RESIZE_HRW") ? atoi(getenv("KC_RESIZE_HRW")) : 0;
     const uint32_t hgroups = (dh + HT_ROWS - 1) / HT_ROWS;
     uint32_t ht = 0, hrw = 0, htile_f4 = 0;
     size_t hsmem = 0;
     {
-        double best = 1e300;
-        for (uint32_t t : {256u, 128u, 64u})
-            for (uint32_t rw : {4u, 2u, 1u}) {
-                if ((env_ht > 0 && (uint32_t)env_ht != t) || (env_hrw > 0 && (uint32_t)env_hrw != rw)) continue;
-                const uint32_t win = max_window(*th, t) + 8;                   // the staging may start up to 3 columns early and end up to 3 late
-                const uint32_t tile = win + (win >> 4) + 2;
-                const size_t sm = 16 + sizeof(float) * (size_t)th->max_taps * t + sizeof(float4) * (size_t)tile * rw;
-                if (sm > 96 * 1024 || (t / 2) * rw > 512) continue;
-                const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>({(uint64_t)2048 / ((t / 2) * rw), 32u, (uint64_t)(227 * 1024) / (sm + 1024)}));
-                const uint64_t blocks = (uint64_t)((dw + t - 1) / t) * ((hgroups + rw - 1) / rw), slots = per_sm * (uint64_t)ctx->sm_count;
-                const uint64_t rounds = (blocks + slots - 1) / slots;
-                // a round lasts about as long as one warp's work (latency-bound), shorter the more warps share an SM
-                const double cost = (double)rounds * (win + 64) / std::sqrt((double)per_sm * (t / 64) * rw);
-                if (cost < best) { best = cost; ht = t; hrw = rw; hsmem = sm; htile_f4 = tile; }
-            }
+        static const uint32_t order[][2] = {{128, 4}, {128, 2}, {64, 4}, {64, 2}, {256, 1}, {128, 1}, {64, 1}};
+        uint64_t most = 0;
+        for (const auto& c : order) {
+            const uint32_t t = c[0], rw = c[1];
+            if ((env_ht > 0 && (uint32_t)env_ht != t) || (env_hrw > 0 && (uint32_t)env_hrw != rw)) continue;
+            const uint32_t win = max_window(*th, t) + 8;                   // the staging may start up to 3 columns early and end up to 3 late
+            const uint32_t tile = win + (win >> 4) + 2;
+            const size_t sm = 16 + sizeof(float) * (size_t)th->max_taps * t + sizeof(float4) * (size_t)tile * rw;
+            if (sm > 96 * 1024) continue;
+            const uint64_t blocks = (uint64_t)((dw + t - 1) / t) * ((hgroups + rw - 1) / rw);
+            if (blocks > most) { most = blocks; ht = t; hrw = rw; hsmem = sm; htile_f4 = tile; }
+            if (blocks >= (uint64_t)ctx->sm_count) break;
+        }
     }
     const uint32_t hgy = hrw ? (hgroups + hrw - 1) / hrw : 0;
     if (!no_march && th->max_taps > (uint32_t)FS_MAXT && ht != 0 && hgy <= 65535u) {
