@@ -1634,7 +1634,8 @@ int32_t kck_resize_plane_rows(kc_context* ctx, const float* src, uint32_t sw, ui
                 const int ctas = shape / 10, stages = shape % 10;
                 const uint32_t strips = (sw + VT_COLS - 1) / VT_COLS;
                 const uint32_t want_gy = std::max<uint32_t>(1u, (uint32_t)(ctx->sm_count * ctas) / strips);
-                uint32_t rpc = std::max<uint32_t>(16u, (dh + want_gy - 1) / want_gy);
+                static const uint32_t min_rpc = getenv("KC_VT_MIN_ROWS") ? (uint32_t)atoi(getenv("KC_VT_MIN_ROWS")) : 4u;
+                uint32_t rpc = std::max<uint32_t>(std::max(1u, min_rpc), (dh + want_gy - 1) / want_gy);
                 if (env_rows > 0) rpc = (uint32_t)env_rows;
                 const uint32_t gy2 = (dh + rpc - 1) / rpc;
                 const size_t smem2 = 128 + (size_t)stages * VT_STAGE_BYTES;
