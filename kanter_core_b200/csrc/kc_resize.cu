@@ -978,19 +978,26 @@ __global__ void __launch_bounds__(T * 4) kc_resize_h_tile_kernel(const float* __
         const uint32_t ncol4 = (ncol + 3u) >> 2;                   // sw % 4 == 0: the last float4 ends inside the row
         const float4 *q0 = reinterpret_cast<const float4*>(r0), *q1 = reinterpret_cast<const float4*>(r1), *q2 = reinterpret_cast<const float4*>(r2),
                      *q3 = reinterpret_cast<const float4*>(r3);
-        for (uint32_t i0 = threadIdx.x; i0 < ncol4; i0 += 2 * T) {
-            const uint32_t ia = i0, ib = min(i0 + (uint32_t)T, ncol4 - 1);
-            const float4 a0 = ld_nc_hint4(q0 + ia, pol), a1 = ld_nc_hint4(q1 + ia, pol), a2 = ld_nc_hint4(q2 + ia, pol), a3 = ld_nc_hint4(q3 + ia, pol);
-            const float4 b0 = ld_nc_hint4(q0 + ib, pol), b1 = ld_nc_hint4(q1 + ib, pol), b2 = ld_nc_hint4(q2 + ib, pol), b3 = ld_nc_hint4(q3 + ib, pol);
-            htile4[ht_slot2(4 * ia + 0)] = make_float4(a0.x, a1.x, a2.x, a3.x);
-            htile4[ht_slot2(4 * ia + 1)] = make_float4(a0.y, a1.y, a2.y, a3.y);
-            htile4[ht_slot2(4 * ia + 2)] = make_float4(a0.z, a1.z, a2.z, a3.z);
-            htile4[ht_slot2(4 * ia + 3)] = make_float4(a0.w, a1.w, a2.w, a3.w);
-            if (i0 + (uint32_t)T < ncol4) {
-                htile4[ht_slot2(4 * ib + 0)] = make_float4(b0.x, b1.x, b2.x, b3.x);
-                htile4[ht_slot2(4 * ib + 1)] = make_float4(b0.y, b1.y, b2.y, b3.y);
-                htile4[ht_slot2(4 * ib + 2)] = make_float4(b0.z, b1.z, b2.z, b3.z);
-                htile4[ht_slot2(4 * ib + 3)] = make_float4(b0.w, b1.w, b2.w, b3.w);
+        constexpr int NG = 4;                                        // load groups in flight per thread (16 float4 loads)
+        for (uint32_t i0 = threadIdx.x; i0 < ncol4; i0 += NG * T) {
+            float4 v[NG][4];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const uint32_t i = min(i0 + (uint32_t)(g * T), ncol4 - 1);
+                v[g][0] = ld_nc_hint4(q0 + i, pol);
+                v[g][1] = ld_nc_hint4(q1 + i, pol);
+                v[g][2] = ld_nc_hint4(q2 + i, pol);
+                v[g][3] = ld_nc_hint4(q3 + i, pol);
+            }
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const uint32_t i = i0 + (uint32_t)(g * T);
+                if (i < ncol4) {
+                    htile4[ht_slot2(4 * i + 0)] = make_float4(v[g][0].x, v[g][1].x, v[g][2].x, v[g][3].x);
+                    htile4[ht_slot2(4 * i + 1)] = make_float4(v[g][0].y, v[g][1].y, v[g][2].y, v[g][3].y);
+                    htile4[ht_slot2(4 * i + 2)] = make_float4(v[g][0].z, v[g][1].z, v[g][2].z, v[g][3].z);
+                    htile4[ht_slot2(4 * i + 3)] = make_float4(v[g][0].w, v[g][1].w, v[g][2].w, v[g][3].w);
+                }
             }
         }
     } else {
