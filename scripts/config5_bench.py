@@ -94,11 +94,11 @@ def main():
                     lg.replace_embedded(img, eid)
                 lg.request(out)
 
-    run_share()                                     # warm-up (also builds the resize tap tables)
-    if args.lanes > 1:
-        run_share()                                 # (replay: ordinary pass, capture, replays from here on)
-    kc.jit_wait()                                   # hot tapes are compiled in the background; measure what serves them from then on
+    for _ in range(4):                              # warm-up (also builds the resize tap tables); hot tapes are compiled in the
+        run_share()                                 # background, a bounded number at a time: passes and waits alternate until
+        kc.jit_wait()                               # nothing is compiling, then measure what serves the batch from there on
     run_share()
+    run_share()                                     # (replay: ordinary pass, capture, replays from here on)
     tp.synchronize()
     stats = sets[0][0].last_run_stats()
     ev0, ev1 = C.c_void_p(), C.c_void_p()
