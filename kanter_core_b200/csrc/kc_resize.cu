@@ -970,9 +970,8 @@ __global__ void __launch_bounds__(T * 4) kc_resize_h_tile_kernel(const float* __
     const float* r1 = tmp + (size_t)(y0 + min(1u, nrow - 1)) * sw + c0;   // rows past nrow: duplicates, never stored
     const float* r2 = tmp + (size_t)(y0 + min(2u, nrow - 1)) * sw + c0;
     const float* r3 = tmp + (size_t)(y0 + min(3u, nrow - 1)) * sw + c0;
-    // staging.  The intermediate sits in L2 (the vertical march wrote it evict-last); this is its last use, so the reads demote
-    // it again (evict-first).  The pass is bound by the latency of these loads: four columns x four rows per load group, two
-    // groups in flight per thread
+    // staging.  The march stored the intermediate evict-last (ncu: most of it comes back from DRAM all the same); this is its
+    // last use, so the reads are evict-first.  Four columns x four rows per load group, four groups in flight per thread
     const uint64_t pol = l2_policy_evict_first();
     if (vec) {
         const uint32_t ncol4 = (ncol + 3u) >> 2;                   // sw % 4 == 0: the last float4 ends inside the row
