@@ -719,3 +719,35 @@ def test_resize_clamp_is_switchable(tex_pro, filt, sizes):
     assert bits_equal(np.clip(free, np.float32(0), np.float32(1)), clamped)
     v = kc.SlotImage.from_value(tex_pro, Size(1, 1), 1.75, False)
     assert kc.resize(tex_pro, v, Size(8, 8), filt).planes()[0][3, 3] == np.float32(1.0)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_resize_long_window_random_shapes_bit_exact(tex_pro, seed):
+    """Seeded random downsampling shapes through the long-window kernels (TMA-fed vertical march with zero-weight idle slots,
+    horizontal pass with two adjacent outputs per thread and block-wise weights): ratios from 1.3 to 40 per axis, independent
+    per axis (two cases upsample along one axis and downsample along the other), widths that are and are not multiples of four
+    (the latter take the per-output fallbacks), every filter, NaN and inf samples -- bit for bit against the oracle."""
+    rng = np.random.default_rng(4000 + seed)
+    for case in range(7):
+        dw, dh = int(rng.integers(3, 90)), int(rng.integers(3, 70))
+        rx, ry = float(rng.uniform(1.3, 12.0)), float(rng.uniform(1.3, 12.0))
+        if case == 5:
+            rx, ry = float(rng.uniform(20, 40)), float(rng.uniform(2, 4))        # one very long horizontal window
+        if case == 4:
+            rx = float(rng.uniform(0.3, 0.9))                                     # upsampling along x, a long window along y
+        if case == 6:
+            ry = float(rng.uniform(0.3, 0.9))                                     # and the other way round
+        sw, sh = max(2, int(dw * rx)), max(2, int(dh * ry))
+        if case % 3 != 2:
+            sw = (sw + 3) & ~3                                                    # the TMA-fed march needs whole float4 columns
+        sw, sh = min(sw, 2600), min(sh, 1400)
+        filt = list(ResizeFilter)[int(rng.integers(0, len(ResizeFilter)))]
+        p = rnd(int(rng.integers(1, 1 << 30)), sh, sw, -0.25, 1.25)
+        if case % 2 == 0:
+            p[int(rng.integers(0, sh)), int(rng.integers(0, sw))] = np.nan
+            p[int(rng.integers(0, sh)), int(rng.integers(0, sw))] = np.inf
+            p[int(rng.integers(0, sh))] = -0.0
+        img = kc.SlotImage.from_planes(tex_pro, [p])
+        got = _resize_direct(tex_pro, img, dw, dh, filt).planes()[0]
+        want = oracle.resize_plane(p, dw, dh, int(filt))
+        assert bits_equal(got, want), (seed, case, (sw, sh), (dw, dh), filt)
